@@ -1,0 +1,148 @@
+/*
+ * tspcuda.h -- C ABI of libtspcuda.so: the B200-native (sm_100a) heuristic core of the C TSP solver
+ * enricobolzonello/TravellingSalesmanOptimization.
+ *
+ * Plain C, plain pointers and sizes; no CUDA, torch or reference types in any signature.  Every
+ * entry point returns one of the reference's ERROR_CODE values (src/utils/errors.h:33-51), so the
+ * interposer (travellingsalesmanoptimization_b200/csrc/interpose.c) can hand them straight back to the unchanged driver.
+ * There is NO CPU fallback anywhere behind this header: without a CUDA device every call that
+ * needs one returns TSPCUDA_UNAVAILABLE and tspcuda_last_error() says why.
+ *
+ * Reference interface each entry point replaces (file:line under the reference's src/):
+ *   tspcuda_cost_matrix           tsp_compute_costs            tsp.c:608-636
+ *   tspcuda_nn                    h_greedyutil                 algorithms/heuristics.c:216-288
+ *   tspcuda_nn_multi              h_Greedy_iterative loop      algorithms/heuristics.c:34-72
+ *   tspcuda_two_opt               ref_2opt (sans incumbent)    algorithms/refinment.c:3-37
+ *   tspcuda_two_opt_once          ref_2opt_once                algorithms/refinment.c:39-93
+ *                                 (+ ref_reverse_path          algorithms/refinment.c:95-114)
+ *   tspcuda_tabu_move             tabu_best_move               algorithms/metaheuristic.c:188-245
+ *   tspcuda_multistart_two_opt    h_greedy_2opt loop           algorithms/heuristics.c:74-116
+ *
+ * Tours cross the boundary exactly as the reference stores them: a successor array int path[n],
+ * path[i] = node visited after node i (src/utils/utils.h:42-47).  Costs are doubles holding
+ * integers (the reference's rounded edge costs), bit-identical to the reference's.
+ */
+#ifndef TSPCUDA_H_
+#define TSPCUDA_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ERROR_CODE values of the reference (src/utils/errors.h:33-51) used by this library. */
+enum {
+    TSPCUDA_OK = 0,                 /* T_OK */
+    TSPCUDA_CANCELLED = 1,          /* CANCELLED (not an error, errors.c:31-37) */
+    TSPCUDA_INVALID_ARGUMENT = 3,   /* bad pointer / not a single-cycle successor array */
+    TSPCUDA_DEADLINE_EXCEEDED = 4,  /* time limit hit between scans (refinment.c:17-24); not an error */
+    TSPCUDA_RESOURCE_EXHAUSTED = 8, /* device memory */
+    TSPCUDA_OUT_OF_RANGE = 11,      /* n or coordinate extent beyond what the packed key supports */
+    TSPCUDA_UNIMPLEMENTED = 12,
+    TSPCUDA_INTERNAL = 13,          /* CUDA failure */
+    TSPCUDA_UNAVAILABLE = 14        /* no CUDA device, or start node out of range (heuristics.c:223-226) */
+};
+
+/* Edge-weight rule.  Only EUC_REF exists in the reference (tsp.c:629: float sqrt, round half up);
+ * the others follow TSPLIB95 and have no reference behaviour ("parity unpinned"). */
+enum { TSPCUDA_EUC_REF = 0, TSPCUDA_CEIL_2D = 1, TSPCUDA_ATT = 2 };
+
+#define TSPCUDA_MAX_NODES 131072      /* 17-bit node ids in the packed (delta,a,b) argmin key */
+
+typedef struct tspcuda_ctx tspcuda_ctx;
+
+typedef struct {
+    int32_t a, b;        /* node ids, a < b: the reference's best_swap (refinment.c:65-66) */
+    int32_t delta;       /* best_delta (integer-valued) */
+    int32_t reserved;
+} tspcuda_move;
+
+typedef struct {
+    int64_t scans;            /* 2-opt neighbourhood scans run (each n(n-1)/2 pair evaluations) */
+    int64_t moves;            /* moves applied */
+    int64_t pair_evals;       /* scans * n(n-1)/2 */
+    int64_t kernel_launches;  /* kernels of this library launched since the context was created */
+    double scan_kernel_ms;    /* CUDA-event time of the descent kernels (scan + apply), accumulated */
+    double last_kernel_ms;    /* CUDA-event time of the most recent timed kernel */
+    int64_t h2d_bytes;        /* bytes copied host->device by this context */
+    int64_t d2h_bytes;        /* bytes copied device->host by this context */
+} tspcuda_stats;
+
+/* ---- library -------------------------------------------------------------------------------- */
+int tspcuda_device_count(void);                 /* 0 when no usable CUDA device */
+const char *tspcuda_last_error(void);           /* thread-local description of the last failure */
+const char *tspcuda_version(void);
+
+/* ---- instance context ----------------------------------------------------------------------- */
+/* xy: n points, AoS {x,y} doubles exactly as the reference's `point` array (utils.h:37-40).
+ * The coordinates are copied to the device; the caller keeps ownership of xy. */
+int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int weight_type, int device);
+void tspcuda_destroy(tspcuda_ctx *ctx);
+int tspcuda_nnodes(const tspcuda_ctx *ctx);
+int tspcuda_get_stats(tspcuda_ctx *ctx, tspcuda_stats *out);
+int tspcuda_reset_stats(tspcuda_ctx *ctx);
+
+/* ---- K1: cost matrix (tsp.c:608-636) -------------------------------------------------------- */
+/* Fills host_out[n*n] (row-major doubles, diagonal -1.0).  The matrix is built in HBM with
+ * 128-bit stores and copied back; size_t indexing (the reference's int n*n overflows at 46341). */
+int tspcuda_cost_matrix(tspcuda_ctx *ctx, double *host_out);
+/* Device-only build (kept in HBM, nothing copied): kernel time in *ms_out.  For measurement. */
+int tspcuda_cost_matrix_device(tspcuda_ctx *ctx, double *ms_out);
+/* Device-side checksum (sum of all entries, exact in int64) of the HBM-resident matrix. */
+int tspcuda_cost_matrix_checksum(tspcuda_ctx *ctx, int64_t *sum_out);
+
+/* ---- nearest neighbour (heuristics.c:216-288) ----------------------------------------------- */
+int tspcuda_nn(tspcuda_ctx *ctx, int start, int *path_out, double *cost_out);
+/* Starts first_start + k*stride, k in [0,nstarts): per-start costs, and the best tour with the
+ * reference's tie rule (strict '<' in ascending start order => lowest start wins, heuristics.c:58).
+ * costs_out / best_path_out may be NULL. */
+int tspcuda_nn_multi(tspcuda_ctx *ctx, int first_start, int nstarts, int stride, double *costs_out,
+                     int *best_start_out, int *best_path_out, double *best_cost_out);
+
+/* ---- 2-opt (refinment.c) --------------------------------------------------------------------- */
+/* Host tour in, host tour out.  Recomputes the cost (refinment.c:6-9), then repeats
+ * best-improvement scan + segment reversal while best_delta < -1e-7 (:15-27).
+ * max_moves < 0: until the local optimum.  time_limit_s < 0: none; otherwise checked between
+ * batches of scans and TSPCUDA_DEADLINE_EXCEEDED is returned with the tour reached so far.
+ * log (may be NULL): the first log_cap moves (a,b,delta). */
+int tspcuda_two_opt(tspcuda_ctx *ctx, int *path, double *cost_out, int64_t max_moves, double time_limit_s,
+                    int64_t *moves_out, tspcuda_move *log, int64_t log_cap);
+/* One scan (+ move if best_delta < -1e-7): *cost_inout += best_delta; returns best_delta in
+ * *best_delta_out (0 at a local optimum), the move in *move_out (a = -1 if none; may be NULL). */
+int tspcuda_two_opt_once(tspcuda_ctx *ctx, int *path, double *cost_inout, double *best_delta_out,
+                         tspcuda_move *move_out);
+/* tabu_best_move (metaheuristic.c:188-245): best admissible move even if worsening; applies it,
+ * *cost_inout += delta, stamps tabu_list[a,b,succ_a,succ_b] = iter.  move_out->a = -1 if every
+ * pair was tabu.  tabu_list: int[n], -1 = never (metaheuristic.c:68-70). */
+int tspcuda_tabu_move(tspcuda_ctx *ctx, int *path, double *cost_inout, int *tabu_list, int tenure, int iter,
+                      tspcuda_move *move_out);
+
+/* Device-resident variants (inputs already in HBM; used for kernel-only measurement and by the
+ * multi-start drivers): upload once, descend in place, download when wanted. */
+int tspcuda_tour_upload(tspcuda_ctx *ctx, const int *path);
+int tspcuda_tour_descend(tspcuda_ctx *ctx, int64_t max_moves, int64_t *moves_out, int *at_local_optimum);
+int tspcuda_tour_download(tspcuda_ctx *ctx, int *path_out, double *cost_out);
+int tspcuda_tour_movelog(tspcuda_ctx *ctx, tspcuda_move *log, int64_t cap, int64_t *count_out);
+
+/* ---- multi-start NN + 2-opt (heuristics.c:74-116) ------------------------------------------- */
+/* Starts first_start + k*stride.  Per-start NN costs, final costs and move counts (any may be
+ * NULL); best tour under the reference's incumbent rule (strict '<', tsp.c:671, ascending start
+ * order => lowest start wins ties). */
+int tspcuda_multistart_two_opt(tspcuda_ctx *ctx, int first_start, int nstarts, int stride, double *nn_costs_out,
+                               double *final_costs_out, int64_t *moves_out, int *best_start_out,
+                               int *best_path_out, double *best_cost_out);
+
+/* ---- measurement helpers -------------------------------------------------------------------- */
+/* Register-only pipe-rate microbenchmarks run on the context's device; result in operations/s
+ * (thread-level, not warp-level).  kind: 0 DADD, 1 DMUL, 2 DFMA, 3 F2F.F32.F64, 4 MUFU.RSQ,
+ * 5 FFMA, 6 the full EUC_REF edge-cost sequence (edge costs/s). */
+int tspcuda_pipe_rate(tspcuda_ctx *ctx, int kind, double *ops_per_s_out);
+/* Exhaustive self-check of the in-kernel float sqrt against IEEE sqrt.rn.f32 over every float in
+ * [2^-60, 2^64): number of mismatches in *mismatches_out (must be 0). */
+int tspcuda_selfcheck_sqrt(tspcuda_ctx *ctx, int64_t *mismatches_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSPCUDA_H_ */

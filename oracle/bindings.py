@@ -130,6 +130,13 @@ class Oracle:
         d = self.L.orc_two_opt_scan(_d(xy), xy.shape[0], wt, _i(path), C.byref(a), C.byref(b))
         return d, a.value, b.value
 
+    def two_opt_once(self, xy, path, cost, wt=EUC_REF):
+        """ref_2opt_once in place on path (int32 array): returns (best_delta, new cost, a, b)."""
+        c = C.c_double(cost)
+        a, b = C.c_int(-1), C.c_int(-1)
+        d = self.L.orc_two_opt_once(_d(xy), xy.shape[0], wt, _i(path), C.byref(c), C.byref(a), C.byref(b))
+        return d, c.value, a.value, b.value
+
     def two_opt(self, xy, path, wt=EUC_REF, max_moves=-1, log=True):
         """Returns (moves, path, cost, log_a, log_b, log_delta)."""
         n = xy.shape[0]

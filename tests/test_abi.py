@@ -1,0 +1,71 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, and exports every symbol include/tspcuda.h
+declares; without a GPU every compute entry point refuses loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    src = open(os.path.join(ROOT, "include", "tspcuda.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(tspcuda_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_symbols_exported():
+    import travellingsalesmanoptimization_b200 as T
+    L = T.lib()
+    declared = _declared_symbols()
+    assert len(declared) >= 20
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert sorted(T.EXPORTS) == declared       # the Python mirror binds exactly the header's surface
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/tspcuda.h must compile as C99 with no CUDA / C++ / torch types."""
+    src = tmp_path / "t.c"
+    src.write_text('#include "tspcuda.h"\nint main(void){ tspcuda_move m; m.a = TSPCUDA_OK; return m.a + (int)sizeof(tspcuda_stats) * 0; }\n')
+    import subprocess
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_error_codes_match_reference_enum():
+    """ERROR_CODE values of src/utils/errors.h:33-51 that cross the boundary."""
+    hdr = open(os.path.join(ROOT, "include", "tspcuda.h")).read()
+    want = {"TSPCUDA_OK": 0, "TSPCUDA_CANCELLED": 1, "TSPCUDA_INVALID_ARGUMENT": 3, "TSPCUDA_DEADLINE_EXCEEDED": 4,
+            "TSPCUDA_RESOURCE_EXHAUSTED": 8, "TSPCUDA_OUT_OF_RANGE": 11, "TSPCUDA_UNIMPLEMENTED": 12,
+            "TSPCUDA_INTERNAL": 13, "TSPCUDA_UNAVAILABLE": 14}
+    for k, v in want.items():
+        assert re.search(r"%s\s*=\s*%d\b" % (k, v), hdr), k
+
+
+def test_no_cpu_fallback_without_device():
+    import travellingsalesmanoptimization_b200 as T
+    if T.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(T.TspCudaError) as ei:
+        T.Instance(np.zeros((8, 2)))
+    assert ei.value.code == T.UNAVAILABLE and "no CPU fallback" in str(ei.value)
+
+
+def test_product_never_imports_oracle():
+    """Only tests/, __graft_entry__.smoke() and bench.py may touch oracle/."""
+    pkg = os.path.join(ROOT, "travellingsalesmanoptimization_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("no oracle", ""), os.path.join(dp, f)
+
+
+def test_sass_is_sm100a():
+    import subprocess
+    import travellingsalesmanoptimization_b200 as T
+    T.lib()
+    out = subprocess.run(["cuobjdump", "-lelf", T.LIB], capture_output=True, text=True).stdout
+    assert "sm_100a" in out

@@ -1,0 +1,373 @@
+"""GPU parity tests (-m gpu): libtspcuda.so through its C ABI against the CPU oracle on the same
+seeded inputs, against the golden fixtures generated from the unmodified reference objects
+(tests/golden/golden.json), and -- at BASELINE.json's full sizes -- through the move-log audit
+and size-independent properties.  Bar: bit-exact integer tours (successor arrays), identical move
+logs (a, b, delta), cost equal (integer-valued doubles; 1e-9 relative is trivially met)."""
+import numpy as np
+import pytest
+
+from oracle.bindings import ATT, CEIL_2D, EUC_REF, fnv1a, load_instance
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand_xy(seed, n, integer, lo=-5000, hi=5000):
+    rng = np.random.default_rng(seed)
+    xy = rng.uniform(lo, hi, size=(n, 2))
+    return np.ascontiguousarray(np.round(xy) if integer else xy)
+
+
+def _rand_tour(seed, n):
+    rng = np.random.default_rng(seed)
+    perm = rng.permutation(n).astype(np.int32)
+    path = np.empty(n, dtype=np.int32)
+    path[perm] = np.roll(perm, -1)
+    return path
+
+
+def _log3(la, lb, ld):
+    return [(int(a), int(b), int(d)) for a, b, d in zip(la, lb, ld)]
+
+
+# ---- arithmetic -----------------------------------------------------------------------------
+def test_device_sqrt_is_ieee(tsp):
+    """The in-kernel float sqrt equals sqrt.rn.f32 on every float in [2^-60, 2^64)."""
+    with tsp.Instance(np.zeros((4, 2))) as I:
+        assert I.selfcheck_sqrt() == 0
+
+
+@pytest.mark.parametrize("name", ["berlin52", "u1060", "fl1577", "pr2392"])
+def test_cost_matrix_instances(tsp, oracle, name):
+    xy, _ = load_instance(name)
+    with tsp.Instance(xy) as I:
+        M = I.cost_matrix()
+    assert np.array_equal(M, oracle.cost_matrix(xy))
+
+
+@pytest.mark.parametrize("n,integer", [(1, True), (2, False), (3, True), (7, False), (64, True), (129, False), (1000, False), (1001, True)])
+def test_cost_matrix_random(tsp, oracle, n, integer):
+    xy = _rand_xy(100 + n, n, integer)
+    with tsp.Instance(xy) as I:
+        M = I.cost_matrix()
+        ms = I.cost_matrix_device()
+        assert ms >= 0 and I.cost_matrix_checksum() == int(M.sum())
+    E = oracle.cost_matrix(xy)
+    assert np.array_equal(M, E) and np.all(np.diag(M) == -1.0)
+
+
+def test_cost_matrix_large_coordinates(tsp, oracle):
+    """Magnitudes of usa13509 / pla85900 (where float-sqrt rounding differs most from TSPLIB)."""
+    xy = _rand_xy(5, 600, False, 245552.778, 1244961.111)
+    with tsp.Instance(xy) as I:
+        assert np.array_equal(I.cost_matrix(), oracle.cost_matrix(xy))
+    xy = _rand_xy(6, 600, True, 548000, 1452000)
+    with tsp.Instance(xy) as I:
+        assert np.array_equal(I.cost_matrix(), oracle.cost_matrix(xy))
+
+
+def test_usa13509_matrix_checksum(tsp, oracle):
+    """Full-size K1: 1.46 GB matrix stays in HBM; its checksum equals the oracle's sum of a sample of
+    rows scaled is not possible, so compare the exact total against row sums from the oracle."""
+    xy, _ = load_instance("usa13509")
+    with tsp.Instance(xy) as I:
+        I.cost_matrix_device()
+        total = I.cost_matrix_checksum()
+    E = oracle.cost_matrix(xy)
+    assert total == int(E.sum())
+
+
+# ---- nearest neighbour ----------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["berlin52", "pcb442", "u1060", "rl1304"])
+def test_nn_instances(tsp, oracle, golden, name):
+    xy, _ = load_instance(name)
+    n = xy.shape[0]
+    with tsp.Instance(xy) as I:
+        code, p, c = I.nn(0)
+        assert code == 0 and int(c) == golden[name]["nn0"]["cost"] and fnv1a(p) == golden[name]["nn0"]["hash"]
+        for s in (1, n // 3, n - 1):
+            code, p, c = I.nn(s)
+            e, po, co = oracle.nn(xy, s)
+            assert code == 0 and np.array_equal(p, po) and c == co
+        assert I.nn(n)[0] == tsp.UNAVAILABLE and I.nn(-1)[0] == tsp.UNAVAILABLE      # heuristics.c:223-226
+
+
+@pytest.mark.parametrize("name", ["berlin52", "kroA100", "pcb442", "pr1002"])
+def test_all_start_nn(tsp, golden, name):
+    xy, _ = load_instance(name)
+    g = golden[name]["allnn"]
+    with tsp.Instance(xy) as I:
+        bs, bp, bc, costs = I.nn_multi(0, xy.shape[0])
+    assert (int(bc), bs, fnv1a(bp)) == (g["cost"], g["start"], g["hash"])
+    if "greedy_2opt" in golden[name]:
+        assert [int(c) for c in costs] == [r[0] for r in golden[name]["greedy_2opt"]["per_start"]]
+
+
+def test_nn_ties_and_duplicates(tsp, oracle):
+    xy = np.array([[0.0, 0.0], [5.0, 5.0], [0.0, 0.0], [5.0, 5.0], [9.0, 1.0], [0.0, 0.0]])
+    with tsp.Instance(xy) as I:
+        for s in range(6):
+            code, p, c = I.nn(s)
+            e, po, co = oracle.nn(xy, s)
+            assert np.array_equal(p, po) and c == co
+    # lattice: massive distance ties, lowest node id must win every step
+    g = np.stack(np.meshgrid(np.arange(12.0), np.arange(11.0)), -1).reshape(-1, 2)
+    with tsp.Instance(g) as I:
+        for s in (0, 17, 131):
+            code, p, c = I.nn(s)
+            e, po, co = oracle.nn(g, s)
+            assert np.array_equal(p, po) and c == co
+
+
+# ---- 2-opt ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["berlin52", "eil51", "kroA100", "pcb442", "pr1002", "u1060", "rl1304", "fl1577", "pr2392"])
+def test_descent_golden(tsp, oracle, golden, name):
+    xy, _ = load_instance(name)
+    g = golden[name]["nn0_2opt"]
+    e, p, c = oracle.nn(xy, 0)
+    with tsp.Instance(xy) as I:
+        code, moves, p2, c2, log = I.two_opt(p, log_cap=64)
+    assert code == 0 and moves == g["moves"] and int(c2) == g["cost"] and fnv1a(p2) == g["hash"]
+    assert [list(x) for x in log[:len(g["first_moves"])]] == g["first_moves"]
+
+
+@pytest.mark.parametrize("n", [4, 5, 6, 9, 31, 126, 127, 128, 129, 130, 131, 254, 255, 256, 257, 383, 509, 777])
+@pytest.mark.parametrize("integer", [True, False])
+def test_descent_random_vs_oracle(tsp, oracle, n, integer):
+    """Sizes straddle the 127-row strip and 32-column block boundaries of the scan kernel."""
+    xy = _rand_xy(n * 2 + integer, n, integer)
+    path = _rand_tour(n, n)                     # random tours: long and wrap-around reversals
+    m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, path)
+    with tsp.Instance(xy) as I:
+        code, moves, p2, c2, log = I.two_opt(path, log_cap=len(la) + 8)
+    assert code == 0 and moves == m_o and c2 == c_o
+    assert log == _log3(la, lb, ld)
+    assert np.array_equal(p2, p_o)
+
+
+def test_descent_lattice_ties(tsp, oracle):
+    """Integer lattice: many equal deltas; the lexicographically smallest (a,b) must win each scan."""
+    g = np.stack(np.meshgrid(np.arange(20.0), np.arange(15.0)), -1).reshape(-1, 2) * 10.0
+    for seed in (1, 2):
+        path = _rand_tour(seed, g.shape[0])
+        m_o, p_o, c_o, la, lb, ld = oracle.two_opt(g, path)
+        with tsp.Instance(g) as I:
+            code, moves, p2, c2, log = I.two_opt(path, log_cap=len(la) + 8)
+        assert log == _log3(la, lb, ld) and np.array_equal(p2, p_o) and c2 == c_o
+
+
+def test_two_opt_once_steps(tsp, oracle):
+    """ref_2opt_once semantics: one scan+move per call, returns best_delta, 0 at the local optimum."""
+    xy, _ = load_instance("kroA100")
+    e, p, c = oracle.nn(xy, 0)
+    po, co = p.copy(), c
+    pg, cg = p.copy(), c
+    with tsp.Instance(xy) as I:
+        for _ in range(40):
+            d_o, co, a_o, b_o = oracle.two_opt_once(xy, po, co)
+            d_g, cg, (a, b) = I.two_opt_once(pg, cg)
+            assert d_g == d_o and np.array_equal(pg, po) and cg == co
+            if d_g == 0:
+                assert (a, b) == (-1, -1)
+            else:
+                assert (a, b) == (a_o, b_o)
+            if d_g == 0:
+                break
+        else:
+            pytest.fail("no local optimum within 40 moves")
+
+
+def test_small_and_degenerate(tsp, oracle):
+    for n in (1, 2, 3):
+        xy = np.array([[0.0, 0.0], [3.0, 4.0], [10.0, 0.0]])[:n].copy()
+        with tsp.Instance(xy) as I:
+            code, p, c = I.nn(0)
+            e, po, co = oracle.nn(xy, 0)
+            assert np.array_equal(p, po) and c == co
+            code, moves, p2, c2, _ = I.two_opt(p)
+            assert code == 0 and moves == 0 and np.array_equal(p2, p) and c2 == oracle.tour_cost(xy, p)
+    # all points identical: every edge costs 0, no improving move
+    xy = np.zeros((40, 2)) + 7.0
+    with tsp.Instance(xy) as I:
+        code, p, c = I.nn(5)
+        e, po, co = oracle.nn(xy, 5)
+        assert np.array_equal(p, po) and c == co == 0
+        code, moves, p2, c2, _ = I.two_opt(p)
+        assert moves == 0 and c2 == 0
+
+
+def test_invalid_inputs(tsp):
+    xy = _rand_xy(1, 50, True)
+    with tsp.Instance(xy) as I:
+        bad = np.arange(50, dtype=np.int32)            # self loops: not a tour
+        with pytest.raises(tsp.TspCudaError) as ei:
+            I.two_opt(bad)
+        assert ei.value.code == tsp.INVALID_ARGUMENT
+        two = np.roll(np.arange(50, dtype=np.int32), -1)
+        two[24] = 0; two[49] = 25                      # two cycles of 25
+        with pytest.raises(tsp.TspCudaError) as ei:
+            I.two_opt(two)
+        assert ei.value.code == tsp.INVALID_ARGUMENT
+    with pytest.raises(tsp.TspCudaError) as ei:
+        tsp.Instance(np.zeros((131073, 2)))
+    assert ei.value.code == tsp.OUT_OF_RANGE
+    with pytest.raises(tsp.TspCudaError) as ei:
+        tsp.Instance(np.array([[0.0, 0.0], [9e6, 9e6], [1.0, 2.0], [5.0, 5.0]]))
+    assert ei.value.code == tsp.OUT_OF_RANGE
+
+
+def test_time_limit_returns_deadline_exceeded(tsp, oracle):
+    """refinment.c:17-24: DEADLINE_EXCEEDED with a valid partial result; err_ok() treats it as success."""
+    xy, _ = load_instance("d15112")
+    e, p, c = oracle.nn(xy, 0)
+    with tsp.Instance(xy) as I:
+        code, moves, p2, c2, _ = I.two_opt(p, time_limit=0.0)
+    assert code == tsp.DEADLINE_EXCEEDED and moves > 0 and oracle.is_tour(p2) and c2 == oracle.tour_cost(xy, p2) and c2 < c
+
+
+# ---- tabu -----------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["berlin52", "kroA100", "pcb442"])
+def test_tabu_steps_golden(tsp, oracle, golden, name):
+    xy, _ = load_instance(name)
+    n = xy.shape[0]
+    g = golden[name]["tabu_steps"]
+    e, p, c = oracle.nn(xy, 0)
+    with tsp.Instance(xy) as I:
+        code, moves, p, c, _ = I.two_opt(p)
+        tenure, lo, hi = oracle.tabu_init(n)
+        inc = True
+        tl = np.full(n, -1, dtype=np.int32)
+        for k, (g_tenure, g_cost, g_hash) in enumerate(g["log"]):
+            tenure, inc = oracle.tabu_linear_step(tenure, lo, hi, inc)
+            c, mv = I.tabu_move(p, c, tl, tenure, k)
+            assert (tenure, int(c), fnv1a(p)) == (g_tenure, g_cost, g_hash), (name, k)
+        assert fnv1a(tl) == g["tabu_list_hash"]
+
+
+def test_tabu_vs_oracle_random(tsp, oracle):
+    xy = _rand_xy(77, 300, False)
+    path = _rand_tour(3, 300)
+    m, p, c, *_ = oracle.two_opt(xy, path, log=False)
+    po, pg, co, cg = p.copy(), p.copy(), c, c
+    to = np.full(300, -1, dtype=np.int32)
+    tg = to.copy()
+    with tsp.Instance(xy) as I:
+        for k in range(60):
+            tenure = 20 + (k % 7)
+            co, a, b, d = oracle.tabu_move(xy, po, co, to, tenure, k)
+            cg, mv = I.tabu_move(pg, cg, tg, tenure, k)
+            assert mv == (a, b, int(d)) and cg == co and np.array_equal(pg, po) and np.array_equal(tg, to), k
+    # everything tabu: no admissible pair, nothing changes (metaheuristic.c:225 guard)
+    with tsp.Instance(xy) as I:
+        tl = np.zeros(300, dtype=np.int32)
+        before = pg.copy()
+        cg2, mv = I.tabu_move(pg, cg, tl, 1000, 5)
+        assert mv[0] == -1 and cg2 == cg and np.array_equal(pg, before) and np.all(tl == 0)
+
+
+# ---- VNS local search (metaheuristic.c:279-320): host kicks, GPU descents ---------------------
+def test_vns_loop(tsp, oracle):
+    xy, _ = load_instance("kroA100")
+    e, p, c = oracle.nn(xy, 0)
+    po, pg = p.copy(), p.copy()
+    import ctypes
+    libc = ctypes.CDLL(None)
+    with tsp.Instance(xy) as I:
+        for it in range(10):
+            m_o, po, c_o, *_ = oracle.two_opt(xy, po, log=False)
+            code, moves, pg, c_g, _ = I.two_opt(pg)
+            assert moves == m_o and c_g == c_o and np.array_equal(pg, po), it
+            libc.srand(99 + it); oracle.vns_kick(po)
+            libc.srand(99 + it); oracle.vns_kick(pg)      # the kick is host code in the reference (unchanged driver)
+            assert np.array_equal(po, pg)
+
+
+# ---- TSPLIB95 weight types (no reference behaviour: parity unpinned, oracle = TSPLIB95) ---------
+def test_ceil2d_and_att(tsp, oracle):
+    xy, _ = load_instance("pla7397")
+    xy = np.ascontiguousarray(xy[:900])
+    with tsp.Instance(xy, tsp.CEIL_2D) as I:
+        assert np.array_equal(I.cost_matrix(), oracle.cost_matrix(xy, CEIL_2D))
+        e, po, co = oracle.nn(xy, 0, CEIL_2D)
+        code, p, c = I.nn(0)
+        assert np.array_equal(p, po) and c == co
+        m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, po, CEIL_2D)
+        code, moves, p2, c2, log = I.two_opt(p, log_cap=len(la) + 4)
+        assert log == _log3(la, lb, ld) and np.array_equal(p2, p_o) and c2 == c_o
+    xy, _ = load_instance("att532")
+    with tsp.Instance(xy, tsp.ATT) as I:
+        assert np.array_equal(I.cost_matrix(), oracle.cost_matrix(xy, ATT))
+        e, po, co = oracle.nn(xy, 0, ATT)
+        m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, po, ATT)
+        code, moves, p2, c2, log = I.two_opt(po, log_cap=len(la) + 4)
+        assert log == _log3(la, lb, ld) and np.array_equal(p2, p_o) and c2 == c_o
+
+
+# ---- multi-start (h_greedy_2opt, heuristics.c:74-116) -----------------------------------------
+@pytest.mark.parametrize("name", ["berlin52", "eil51", "kroA100"])
+def test_multistart_golden(tsp, golden, name):
+    xy, _ = load_instance(name)
+    g = golden[name]["greedy_2opt"]
+    with tsp.Instance(xy) as I:
+        bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(0, xy.shape[0])
+    assert [[int(a), int(m), int(f)] for a, m, f in zip(nn_costs, moves, final)] == g["per_start"]
+    assert (int(bc), bs, fnv1a(bp)) == (g["cost"], g["first_start"], g["hash"])
+
+
+def test_multistart_pr2392_first8_and_strided(tsp, golden):
+    xy, _ = load_instance("pr2392")
+    g = golden["pr2392"]["greedy_2opt_first8"]
+    with tsp.Instance(xy) as I:
+        bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(0, 8)
+        assert [[int(a), int(m), int(f)] for a, m, f in zip(nn_costs, moves, final)] == [r[:3] for r in g]
+        best = min(r[2] for r in g)
+        first = [r[2] for r in g].index(best)
+        assert int(bc) == best and bs == first and fnv1a(bp) == g[first][3]
+        # block-cyclic shard of rank 1 of 4 (starts 1, 5): what one GPU of a 4-GPU run computes
+        bs2, bp2, bc2, nn2, fin2, mv2 = I.multistart_two_opt(1, 2, 4)
+        assert [int(f) for f in fin2] == [g[1][2], g[5][2]]
+
+
+# ---- full-size configs ------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["usa13509", "d15112"])
+def test_large_first_moves_golden(tsp, golden, name):
+    xy, _ = load_instance(name)
+    g = golden[name]
+    with tsp.Instance(xy) as I:
+        code, p, c = I.nn(0)
+        assert int(c) == g["nn0"]["cost"] and fnv1a(p) == g["nn0"]["hash"]
+        code, moves, p2, c2, log = I.two_opt(p, max_moves=20, log_cap=20)
+    g2 = g["nn0_2opt_20"]
+    assert moves == 20 and int(c2) == g2["cost"] and fnv1a(p2) == g2["hash"] and [list(x) for x in log] == g2["first_moves"]
+
+
+def test_usa13509_full_descent(tsp, oracle, golden):
+    """Config 3: NN(0) tour to the 2-opt local optimum with on-the-fly FP64 distances.  The
+    reference objects need 2567 s for this: 1983 moves -> 21119812."""
+    xy, _ = load_instance("usa13509")
+    with tsp.Instance(xy) as I:
+        code, p, c = I.nn(0)
+        code, moves, p2, c2, log = I.two_opt(p, log_cap=4096)
+    s = golden["usa13509"]["nn0_2opt_survey"]
+    assert (moves, int(c2)) == (s["moves"], s["cost"])
+    assert oracle.is_tour(p2) and oracle.tour_cost(xy, p2) == c2
+    # audit: every logged delta re-derived on the CPU, full CPU scans at a few iterations, local optimality
+    la = [x[0] for x in log]; lb = [x[1] for x in log]; ld = [float(x[2]) for x in log]
+    r, pend = oracle.audit_moves(xy, p, la, lb, ld, [0, 1, 500, 1982])
+    assert r == 0 and np.array_equal(pend, p2)
+    d, a, b = oracle.two_opt_scan(xy, p2)
+    assert d >= -1e-7                                   # local optimum (refinment.c:27)
+
+
+def test_pla85900_descent_audit(tsp, oracle):
+    """Config 4 size (n = 85 900, 3.689e9 pairs per scan): the reference cannot run it (int overflow,
+    tsp.c:614) so parity is the SURVEY 8c audit against the 64-bit oracle, plus invariants."""
+    xy, _ = load_instance("pla85900")
+    with tsp.Instance(xy) as I:
+        code, p, c = I.nn(0)
+        assert code == 0 and oracle.is_tour(p) and oracle.tour_cost(xy, p) == c
+        code, moves, p2, c2, log = I.two_opt(p, max_moves=48, log_cap=48)
+    assert moves == 48 and oracle.is_tour(p2) and oracle.tour_cost(xy, p2) == c2
+    la = [x[0] for x in log]; lb = [x[1] for x in log]; ld = [float(x[2]) for x in log]
+    assert c2 == c + sum(ld) and all(d < 0 for d in ld)
+    r, pend = oracle.audit_moves(xy, p, la, lb, ld, [0, 47])
+    assert r == 0 and np.array_equal(pend, p2)

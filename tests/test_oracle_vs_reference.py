@@ -1,0 +1,107 @@
+"""CPU: pin the oracle restatement (oracle/onfly.c) against the UNMODIFIED reference objects
+(oracle/_ref/libtspref.so through oracle/ref_api.c), move for move, on fresh seeded inputs.
+Skipped where oracle/_ref was never built (it needs /root/reference at build time)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle.bindings import fnv1a, load_instance
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _cwd_with_results():
+    old = os.getcwd()
+    td = tempfile.mkdtemp()
+    os.makedirs(os.path.join(td, "results"))      # metaheuristic.c:97 writes results/TabuResults.dat
+    os.chdir(td)
+    yield
+    os.chdir(old)
+
+
+def _rand_instance(rng, n, integer):
+    xy = rng.uniform(-5000, 5000, size=(n, 2))
+    return np.ascontiguousarray(np.round(xy) if integer else xy)
+
+
+@pytest.mark.parametrize("n,integer,seed", [(5, True, 1), (17, False, 2), (200, True, 3), (333, False, 4), (700, False, 5)])
+def test_costs_nn_descent_random(oracle, reference, n, integer, seed):
+    rng = np.random.default_rng(seed)
+    xy = _rand_instance(rng, n, integer)
+    reference.set_points(xy)
+    assert np.array_equal(oracle.cost_matrix(xy), reference.costs())
+    for start in sorted(set([0, n // 2, n - 1])):
+        e_r, p_r, c_r = reference.nn(start)
+        e_o, p_o, c_o = oracle.nn(xy, start)
+        assert e_r == e_o == 0 and np.array_equal(p_r, p_o) and c_r == c_o
+        m_r, q_r, d_r, la, lb, ld = reference.two_opt(p_r)
+        m_o, q_o, d_o, oa, ob, od = oracle.two_opt(xy, p_o)
+        assert m_r == m_o and d_r == d_o and np.array_equal(q_r, q_o)
+        assert np.array_equal(la, oa) and np.array_equal(lb, ob) and np.array_equal(ld, od)
+
+
+def test_descent_from_random_tours(oracle, reference):
+    """Random (non-NN) tours exercise wrap-around segments and long reversals."""
+    rng = np.random.default_rng(11)
+    xy = _rand_instance(rng, 150, True)
+    reference.set_points(xy)
+    for _ in range(3):
+        perm = rng.permutation(150).astype(np.int32)
+        path = np.empty(150, dtype=np.int32)
+        path[perm] = np.roll(perm, -1)
+        m_r, q_r, d_r, la, lb, ld = reference.two_opt(path)
+        m_o, q_o, d_o, oa, ob, od = oracle.two_opt(xy, path)
+        assert m_r == m_o and d_r == d_o and np.array_equal(q_r, q_o) and np.array_equal(la, oa) and np.array_equal(lb, ob)
+
+
+@pytest.mark.parametrize("name,K", [("berlin52", 150), ("pcb442", 25)])
+def test_tabu_moves(oracle, reference, name, K):
+    xy, _ = load_instance(name)
+    n = xy.shape[0]
+    reference.set_points(xy)
+    e, p, c = reference.nn(0)
+    m, p, c, *_ = reference.two_opt(p)
+    pr, po = p.copy(), p.copy()
+    cr, co = c, c
+    tr = np.full(n, -1, dtype=np.int32)
+    to = tr.copy()
+    ten_r, lo_r, hi_r = reference.tabu_init(n)
+    assert (ten_r, lo_r, hi_r) == oracle.tabu_init(n)
+    ten_o, inc_r, inc_o = ten_r, True, True
+    for k in range(K):
+        ten_r, inc_r = reference.tabu_linear_step(ten_r, lo_r, hi_r, inc_r)
+        ten_o, inc_o = oracle.tabu_linear_step(ten_o, lo_r, hi_r, inc_o)
+        assert (ten_r, inc_r) == (ten_o, inc_o)
+        cr = reference.tabu_move(pr, cr, tr, ten_r, k)
+        co, a, b, d = oracle.tabu_move(xy, po, co, to, ten_o, k)
+        assert cr == co and np.array_equal(pr, po) and np.array_equal(tr, to), (name, k)
+
+
+def test_vns_kick_and_descent(oracle, reference):
+    """vns_kick (metaheuristic.c:344-409) under the same glibc rand() stream, then ref_2opt."""
+    xy, _ = load_instance("kroA100")
+    reference.set_points(xy)
+    e, p, c = reference.nn(0)
+    m, p, c, *_ = reference.two_opt(p)
+    pr, po = p.copy(), p.copy()
+    for it in range(12):
+        reference.srand(1000 + it)
+        reference.vns_kick(pr)
+        reference.srand(1000 + it)          # same process, same libc: identical stream for the restatement
+        oracle.vns_kick(po)
+        assert np.array_equal(pr, po), it
+        m_r, pr, c_r, *_ = reference.two_opt(pr)
+        m_o, po, c_o, *_ = oracle.two_opt(xy, po, log=False)
+        assert m_r == m_o and c_r == c_o and np.array_equal(pr, po)
+
+
+def test_whole_algorithms_match_golden(reference, golden):
+    """The reference's own entry points reproduce golden.json (guards the harness itself)."""
+    xy, _ = load_instance("berlin52")
+    reference.set_points(xy)
+    e, p, c, s = reference.run(2)
+    g = golden["berlin52"]["greedy_2opt"]
+    assert (int(c), fnv1a(p), s) == (g["cost"], g["hash"], g["starting_node_field"])
+    e, p, c, s = reference.run(3, 200)
+    assert (int(c), fnv1a(p)) == (golden["berlin52"]["tabu_search_k200"]["cost"], golden["berlin52"]["tabu_search_k200"]["hash"])

@@ -1,0 +1,242 @@
+"""travellingsalesmanoptimization_b200 -- host-side Python mirror of libtspcuda.so's C ABI (include/tspcuda.h).
+
+The product is the shared library (hand-written sm_100a CUDA behind a plain C ABI); this module
+is a thin ctypes binding used by tests/, bench.py and __graft_entry__.py.  It contains no
+algorithm and no CPU fallback: if the library or a CUDA device is missing, calls raise.
+Names mirror the reference helpers they replace (see include/tspcuda.h for file:line):
+  Instance.cost_matrix()   tsp_compute_costs      Instance.nn(start)       h_greedyutil
+  Instance.two_opt(path)   ref_2opt               Instance.two_opt_once()  ref_2opt_once
+  Instance.tabu_move()     tabu_best_move         Instance.multistart_two_opt()  h_greedy_2opt loop
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB, build
+
+EUC_REF, CEIL_2D, ATT = 0, 1, 2
+WT_BY_NAME = {"EUC_2D": EUC_REF, "EUC_REF": EUC_REF, "CEIL_2D": CEIL_2D, "ATT": ATT}
+ERROR_NAMES = {0: "T_OK", 1: "CANCELLED", 3: "INVALID_ARGUMENT", 4: "DEADLINE_EXCEEDED", 8: "RESOURCE_EXHAUSTED",
+               11: "OUT_OF_RANGE", 12: "UNIMPLEMENTED", 13: "INTERNAL", 14: "UNAVAILABLE"}
+OK, DEADLINE_EXCEEDED, INVALID_ARGUMENT, OUT_OF_RANGE, UNAVAILABLE = 0, 4, 3, 11, 14
+
+EXPORTS = [
+    "tspcuda_device_count", "tspcuda_last_error", "tspcuda_version", "tspcuda_create", "tspcuda_destroy",
+    "tspcuda_nnodes", "tspcuda_get_stats", "tspcuda_reset_stats", "tspcuda_cost_matrix", "tspcuda_cost_matrix_device",
+    "tspcuda_cost_matrix_checksum", "tspcuda_nn", "tspcuda_nn_multi", "tspcuda_two_opt", "tspcuda_two_opt_once",
+    "tspcuda_tabu_move", "tspcuda_tour_upload", "tspcuda_tour_descend", "tspcuda_tour_download", "tspcuda_tour_movelog",
+    "tspcuda_multistart_two_opt", "tspcuda_pipe_rate", "tspcuda_selfcheck_sqrt",
+]
+
+
+class TspCudaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"tspcuda error {code} ({ERROR_NAMES.get(code, '?')}): {msg}")
+        self.code = code
+
+
+class Move(C.Structure):
+    _fields_ = [("a", C.c_int32), ("b", C.c_int32), ("delta", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("scans", C.c_int64), ("moves", C.c_int64), ("pair_evals", C.c_int64), ("kernel_launches", C.c_int64),
+                ("scan_kernel_ms", C.c_double), ("last_kernel_ms", C.c_double), ("h2d_bytes", C.c_int64),
+                ("d2h_bytes", C.c_int64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+_dp, _ip, _vp = C.POINTER(C.c_double), C.POINTER(C.c_int), C.c_void_p
+_i64p = C.POINTER(C.c_int64)
+_lib = None
+
+
+def lib():
+    """Load libtspcuda.so (building it first if the sources are newer). Raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB):
+        build()
+    L = C.CDLL(LIB)
+    L.tspcuda_last_error.restype = C.c_char_p
+    L.tspcuda_version.restype = C.c_char_p
+    L.tspcuda_create.argtypes = [C.POINTER(_vp), _dp, C.c_int, C.c_int, C.c_int]
+    L.tspcuda_destroy.argtypes = [_vp]
+    L.tspcuda_destroy.restype = None
+    L.tspcuda_nnodes.argtypes = [_vp]
+    L.tspcuda_get_stats.argtypes = [_vp, C.POINTER(Stats)]
+    L.tspcuda_reset_stats.argtypes = [_vp]
+    L.tspcuda_cost_matrix.argtypes = [_vp, _dp]
+    L.tspcuda_cost_matrix_device.argtypes = [_vp, _dp]
+    L.tspcuda_cost_matrix_checksum.argtypes = [_vp, _i64p]
+    L.tspcuda_nn.argtypes = [_vp, C.c_int, _ip, _dp]
+    L.tspcuda_nn_multi.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _ip, _ip, _dp]
+    L.tspcuda_two_opt.argtypes = [_vp, _ip, _dp, C.c_int64, C.c_double, _i64p, C.POINTER(Move), C.c_int64]
+    L.tspcuda_two_opt_once.argtypes = [_vp, _ip, _dp, _dp, C.POINTER(Move)]
+    L.tspcuda_tabu_move.argtypes = [_vp, _ip, _dp, _ip, C.c_int, C.c_int, C.POINTER(Move)]
+    L.tspcuda_tour_upload.argtypes = [_vp, _ip]
+    L.tspcuda_tour_descend.argtypes = [_vp, C.c_int64, _i64p, _ip]
+    L.tspcuda_tour_download.argtypes = [_vp, _ip, _dp]
+    L.tspcuda_tour_movelog.argtypes = [_vp, C.POINTER(Move), C.c_int64, _i64p]
+    L.tspcuda_multistart_two_opt.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _i64p, _ip, _ip, _dp]
+    L.tspcuda_pipe_rate.argtypes = [_vp, C.c_int, _dp]
+    L.tspcuda_selfcheck_sqrt.argtypes = [_vp, _i64p]
+    _lib = L
+    return L
+
+
+def device_count():
+    return lib().tspcuda_device_count()
+
+
+def _chk(code, allow=()):
+    if code != 0 and code not in allow:
+        raise TspCudaError(code, lib().tspcuda_last_error().decode())
+    return code
+
+
+def _ipc(a):
+    return a.ctypes.data_as(_ip)
+
+
+def _dpc(a):
+    return a.ctypes.data_as(_dp)
+
+
+class Instance:
+    """One TSP instance resident on one GPU (tspcuda_ctx)."""
+
+    def __init__(self, xy, weight_type=EUC_REF, device=0):
+        self.xy = np.ascontiguousarray(xy, dtype=np.float64)
+        assert self.xy.ndim == 2 and self.xy.shape[1] == 2
+        self.n = self.xy.shape[0]
+        self._h = _vp()
+        _chk(lib().tspcuda_create(C.byref(self._h), _dpc(self.xy), self.n, weight_type, device))
+
+    def close(self):
+        if self._h:
+            lib().tspcuda_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- stats -----------------------------------------------------------------------------------
+    def stats(self):
+        s = Stats()
+        _chk(lib().tspcuda_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def reset_stats(self):
+        _chk(lib().tspcuda_reset_stats(self._h))
+
+    # -- K1 ----------------------------------------------------------------------------------------
+    def cost_matrix(self):
+        out = np.empty((self.n, self.n), dtype=np.float64)
+        _chk(lib().tspcuda_cost_matrix(self._h, _dpc(out)))
+        return out
+
+    def cost_matrix_device(self):
+        ms = C.c_double(0)
+        _chk(lib().tspcuda_cost_matrix_device(self._h, C.byref(ms)))
+        return ms.value
+
+    def cost_matrix_checksum(self):
+        s = C.c_int64(0)
+        _chk(lib().tspcuda_cost_matrix_checksum(self._h, C.byref(s)))
+        return s.value
+
+    # -- NN ----------------------------------------------------------------------------------------
+    def nn(self, start):
+        path = np.full(self.n, -7, dtype=np.int32)
+        cost = C.c_double(0)
+        code = lib().tspcuda_nn(self._h, start, _ipc(path), C.byref(cost))
+        return code, path, cost.value
+
+    def nn_multi(self, first_start, nstarts, stride=1):
+        costs = np.zeros(nstarts, dtype=np.float64)
+        best_path = np.zeros(self.n, dtype=np.int32)
+        bs, bc = C.c_int(-1), C.c_double(0)
+        _chk(lib().tspcuda_nn_multi(self._h, first_start, nstarts, stride, _dpc(costs), C.byref(bs), _ipc(best_path), C.byref(bc)))
+        return bs.value, best_path, bc.value, costs
+
+    # -- 2-opt -------------------------------------------------------------------------------------
+    def two_opt(self, path, max_moves=-1, time_limit=-1.0, log_cap=0):
+        """ref_2opt: returns (code, moves, path, cost, log[(a,b,delta)...])."""
+        path = np.array(path, dtype=np.int32, copy=True)
+        cost, moves = C.c_double(0), C.c_int64(0)
+        log = (Move * max(1, log_cap))()
+        code = _chk(lib().tspcuda_two_opt(self._h, _ipc(path), C.byref(cost), max_moves, time_limit, C.byref(moves),
+                                          log if log_cap else None, log_cap), allow=(DEADLINE_EXCEEDED,))
+        k = min(moves.value, log_cap)
+        return code, moves.value, path, cost.value, [(log[i].a, log[i].b, log[i].delta) for i in range(k)]
+
+    def two_opt_once(self, path, cost):
+        """ref_2opt_once in place on `path` (int32 array): returns (best_delta, new cost, (a,b))."""
+        c, d, mv = C.c_double(cost), C.c_double(0), Move()
+        _chk(lib().tspcuda_two_opt_once(self._h, _ipc(path), C.byref(c), C.byref(d), C.byref(mv)))
+        return d.value, c.value, (mv.a, mv.b)
+
+    def tabu_move(self, path, cost, tabu_list, tenure, it):
+        """tabu_best_move in place on path / tabu_list: returns (new cost, (a,b,delta))."""
+        c, mv = C.c_double(cost), Move()
+        _chk(lib().tspcuda_tabu_move(self._h, _ipc(path), C.byref(c), _ipc(tabu_list), tenure, it, C.byref(mv)))
+        return c.value, (mv.a, mv.b, mv.delta)
+
+    # -- device-resident tour ----------------------------------------------------------------------
+    def tour_upload(self, path):
+        path = np.ascontiguousarray(path, dtype=np.int32)
+        _chk(lib().tspcuda_tour_upload(self._h, _ipc(path)))
+
+    def tour_descend(self, max_moves=-1):
+        m, opt = C.c_int64(0), C.c_int(0)
+        _chk(lib().tspcuda_tour_descend(self._h, max_moves, C.byref(m), C.byref(opt)))
+        return m.value, bool(opt.value)
+
+    def tour_download(self):
+        path = np.zeros(self.n, dtype=np.int32)
+        cost = C.c_double(0)
+        _chk(lib().tspcuda_tour_download(self._h, _ipc(path), C.byref(cost)))
+        return path, cost.value
+
+    def tour_movelog(self, cap):
+        log = (Move * max(1, cap))()
+        cnt = C.c_int64(0)
+        _chk(lib().tspcuda_tour_movelog(self._h, log, cap, C.byref(cnt)))
+        k = min(cnt.value, cap)
+        return cnt.value, [(log[i].a, log[i].b, log[i].delta) for i in range(k)]
+
+    # -- multi-start ---------------------------------------------------------------------------------
+    def multistart_two_opt(self, first_start, nstarts, stride=1):
+        nn_costs = np.zeros(nstarts, dtype=np.float64)
+        final = np.zeros(nstarts, dtype=np.float64)
+        moves = np.zeros(nstarts, dtype=np.int64)
+        best_path = np.zeros(self.n, dtype=np.int32)
+        bs, bc = C.c_int(-1), C.c_double(0)
+        _chk(lib().tspcuda_multistart_two_opt(self._h, first_start, nstarts, stride, _dpc(nn_costs), _dpc(final),
+                                              moves.ctypes.data_as(_i64p), C.byref(bs), _ipc(best_path), C.byref(bc)))
+        return bs.value, best_path, bc.value, nn_costs, final, moves
+
+    # -- measurement ---------------------------------------------------------------------------------
+    def pipe_rate(self, kind):
+        r = C.c_double(0)
+        _chk(lib().tspcuda_pipe_rate(self._h, kind, C.byref(r)))
+        return r.value
+
+    def selfcheck_sqrt(self):
+        m = C.c_int64(-1)
+        _chk(lib().tspcuda_selfcheck_sqrt(self._h, C.byref(m)))
+        return m.value

@@ -1,0 +1,100 @@
+// metric.cuh -- bit-exact edge-cost functors for sm_100a.
+//
+// The reference's ONLY cost routine is src/tsp.c:629
+//     (double)((int)(sqrtf(pow(dx,2) + pow(dy,2)) + 0.5))
+// which gcc -O3 (no -ffast-math, baseline x86-64 => no FMA) turns into
+//     subsd subsd mulsd mulsd addsd cvtsd2ss sqrtss cvtss2sd addsd(0.5) cvttsd2si cvtsi2sd.
+// EucRef reproduces that value for every input whose cost is below 2^23 (checked at context
+// creation) with 5 FP64 instructions, one F2F.F32.F64, one MUFU.RSQ and 8 FP32 instructions:
+//
+//   * dx, dy, dx*dx, dy*dy, sum: explicit round-to-nearest intrinsics, so nvcc cannot contract
+//     dx*dx + dy*dy into an FMA (with non-integer coordinates such as usa13509's that would
+//     change the double before the float rounding).  With all-integer coordinates below 2^25 every
+//     intermediate is exact, so the INTEGER variant may use one FMA (4 FP64 instructions).
+//   * sqrtf: sqrt_rn_pos() is the IEEE round-to-nearest square root for positive normal floats
+//     (MUFU.RSQ seed + one Newton step with an exact FMA residual).  It is checked exhaustively
+//     against sqrt.rn.f32 on the device by tspcuda_selfcheck_sqrt (tests/test_gpu_parity.py).
+//   * (int)(r + 0.5) for r >= 0 is floor(r + 0.5).  r + 0.5 is formed in FP32 with round-DOWN
+//     (v <= r+0.5 and v >= floor(r+0.5) because that integer is representable => same floor), and
+//     adding 2^23 with round-down leaves 2^23 + floor(v) in the float, whose bit pattern is
+//     0x4B000000 + cost.  Costs therefore travel as "K-offset" int32 values; the offset cancels
+//     in every 2-opt delta (two costs added, two subtracted), so no F2I/I2F conversion is needed.
+//
+// CEIL_2D and ATT follow TSPLIB95 in FP64 (IEEE sqrt/div), "parity unpinned": the reference
+// rejects those files (src/tsp.c:576-583).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace tspcuda {
+
+constexpr int KOFF = 0x4B000000;        // bit pattern of 8388608.0f (2^23)
+constexpr int BIGPEN = 1 << 27;         // penalty that removes a pair from the argmin
+constexpr int DELTA_BIAS = 1 << 29;     // bias of the delta field in the packed key
+constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+
+// IEEE-754 round-to-nearest sqrt for f in [2^-60, 2^64] (normal, positive).
+__device__ __forceinline__ float sqrt_rn_pos(float f) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(f));
+    float g = __fmul_rn(f, y);
+    float h = __fmul_rn(y, 0.5f);
+    float e = __fmaf_rn(-g, g, f);
+    return __fmaf_rn(e, h, g);
+}
+
+// K-offset cost from the float that the reference hands to sqrtf().
+__device__ __forceinline__ int koff_from_sumsq(float f) {
+    f = fmaxf(f, 8.673617379884035e-19f);      // 2^-60: keeps rsqrt finite; any f < 0.25 costs 0
+    float r = sqrt_rn_pos(f);
+    float v = __fadd_rd(r, 0.5f);
+    float w = __fadd_rd(v, 8388608.0f);
+    return __float_as_int(w);
+}
+
+template <bool INTEGER>
+struct EucRef {
+    static __device__ __forceinline__ int K(double xi, double yi, double xj, double yj) {
+        double dx = __dsub_rn(xj, xi);
+        double dy = __dsub_rn(yj, yi);
+        double s;
+        if (INTEGER) {
+            s = __fma_rn(dx, dx, __dmul_rn(dy, dy));          // exact either way
+        } else {
+            s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        }
+        return koff_from_sumsq(__double2float_rn(s));
+    }
+};
+
+// TSPLIB95 CEIL_2D: ceil(sqrt(dx^2+dy^2)) in double.
+struct Ceil2D {
+    static __device__ __forceinline__ int K(double xi, double yi, double xj, double yj) {
+        double dx = __dsub_rn(xj, xi);
+        double dy = __dsub_rn(yj, yi);
+        double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        return KOFF + (int)ceil(__dsqrt_rn(s));
+    }
+};
+
+// TSPLIB95 ATT: r = sqrt((dx^2+dy^2)/10); t = nint(r); t < r ? t+1 : t.
+struct Att {
+    static __device__ __forceinline__ int K(double xi, double yi, double xj, double yj) {
+        double dx = __dsub_rn(xj, xi);
+        double dy = __dsub_rn(yj, yi);
+        double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        double r = __dsqrt_rn(__ddiv_rn(s, 10.0));
+        double t = (double)(long long)__dadd_rn(r, 0.5);
+        return KOFF + (int)((t < r) ? t + 1.0 : t);
+    }
+};
+
+__device__ __forceinline__ unsigned long long pack_key(int delta, int u, int v) {
+    unsigned lo = (unsigned)min(u, v), hi = (unsigned)max(u, v);
+    return ((unsigned long long)(unsigned)(delta + DELTA_BIAS) << 34) | ((unsigned long long)lo << 17) |
+           (unsigned long long)hi;
+}
+__device__ __host__ __forceinline__ int key_delta(unsigned long long k) { return (int)(k >> 34) - DELTA_BIAS; }
+__device__ __host__ __forceinline__ int key_a(unsigned long long k) { return (int)((k >> 17) & 0x1FFFF); }
+__device__ __host__ __forceinline__ int key_b(unsigned long long k) { return (int)(k & 0x1FFFF); }
+
+}  // namespace tspcuda

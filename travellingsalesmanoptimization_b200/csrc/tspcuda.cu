@@ -1,0 +1,690 @@
+// tspcuda.cu -- host side of libtspcuda.so: the C ABI of include/tspcuda.h over the sm_100a
+// kernels of kernels.cuh.  No CPU implementation of any algorithm lives here: without a CUDA
+// device every compute entry point fails with TSPCUDA_UNAVAILABLE.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tspcuda.h"
+#include "kernels.cuh"
+
+using namespace tspcuda;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return fail(e_ == cudaErrorMemoryAllocation ? TSPCUDA_RESOURCE_EXHAUSTED : TSPCUDA_INTERNAL, \
+                        "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
+    } while (0)
+
+enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3 };
+
+#define DISPATCH_METRIC(mid, EXPR)                                        \
+    switch (mid) {                                                        \
+        case M_EUC_GENERAL: { using M = EucRef<false>; EXPR; } break;     \
+        case M_EUC_INTEGER: { using M = EucRef<true>; EXPR; } break;      \
+        case M_CEIL: { using M = Ceil2D; EXPR; } break;                   \
+        default: { using M = Att; EXPR; } break;                          \
+    }
+
+struct tspcuda_ctx {
+    int n = 0, wt = 0, device = 0, metric = 0;
+    int num_sms = 0, max_coop_blocks = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double2 *d_xy = nullptr;
+    TourView tour{};
+    int *d_path = nullptr, *d_order = nullptr, *d_tabu = nullptr;
+    unsigned long long *d_key = nullptr;
+    DescState *d_state = nullptr, *h_state = nullptr;
+    MoveRec *d_log = nullptr;
+    long long log_cap = 0;
+    int *h_buf = nullptr;            // pinned, n ints
+    double *d_matrix = nullptr;
+    long long *d_sum = nullptr;
+    bool tour_loaded = false;
+    std::vector<int> h_cache;        // successor array the device tour currently represents
+    tspcuda_stats stats{};
+    double est_scan_s = 0;
+    long long dev_moves = 0;         // host mirror of d_state->moves
+};
+
+extern "C" const char *tspcuda_last_error(void) { return g_err.c_str(); }
+extern "C" const char *tspcuda_version(void) { return "tspcuda 0.1 (sm_100a)"; }
+
+extern "C" int tspcuda_device_count(void) {
+    int c = 0;
+    if (cudaGetDeviceCount(&c) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return c;
+}
+
+static int use(tspcuda_ctx *c) {
+    if (!c) return fail(TSPCUDA_INVALID_ARGUMENT, "null context");
+    CK(cudaSetDevice(c->device));
+    return TSPCUDA_OK;
+}
+
+template <class M>
+static int coop_blocks_per_sm() {
+    int b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, descend_kernel<M>, BLOCK, 0);
+    return b;
+}
+
+extern "C" void tspcuda_destroy(tspcuda_ctx *c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_xy); cudaFree(c->tour.pxy); cudaFree(c->tour.tid); cudaFree(c->tour.dn);
+    cudaFree(c->tour.dns); cudaFree(c->tour.pos); cudaFree(c->d_path); cudaFree(c->d_order);
+    cudaFree(c->d_tabu); cudaFree(c->d_key); cudaFree(c->d_state); cudaFree(c->d_log);
+    cudaFree(c->d_matrix); cudaFree(c->d_sum);
+    if (c->h_state) cudaFreeHost(c->h_state);
+    if (c->h_buf) cudaFreeHost(c->h_buf);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int weight_type, int device) {
+    if (!out || !xy) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (n <= 0) return fail(TSPCUDA_INVALID_ARGUMENT, "n = %d", n);
+    if (n > TSPCUDA_MAX_NODES) return fail(TSPCUDA_OUT_OF_RANGE, "n = %d exceeds %d (17-bit node ids in the packed key)", n, TSPCUDA_MAX_NODES);
+    if (weight_type < TSPCUDA_EUC_REF || weight_type > TSPCUDA_ATT) return fail(TSPCUDA_UNIMPLEMENTED, "weight type %d", weight_type);
+    int ndev = tspcuda_device_count();
+    if (ndev <= 0) return fail(TSPCUDA_UNAVAILABLE, "no CUDA device: libtspcuda has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(TSPCUDA_INVALID_ARGUMENT, "device %d of %d", device, ndev);
+
+    bool integer = true;
+    double xmin = xy[0], xmax = xy[0], ymin = xy[1], ymax = xy[1];
+    for (int i = 0; i < n; i++) {
+        const double x = xy[2 * i], y = xy[2 * i + 1];
+        if (!std::isfinite(x) || !std::isfinite(y)) return fail(TSPCUDA_INVALID_ARGUMENT, "non-finite coordinate at node %d", i);
+        if (x != std::floor(x) || y != std::floor(y) || std::fabs(x) >= 33554432.0 || std::fabs(y) >= 33554432.0) integer = false;
+        xmin = std::min(xmin, x); xmax = std::max(xmax, x); ymin = std::min(ymin, y); ymax = std::max(ymax, y);
+    }
+    const double diag = std::sqrt((xmax - xmin) * (xmax - xmin) + (ymax - ymin) * (ymax - ymin));
+    if (diag >= 8388000.0)
+        return fail(TSPCUDA_OUT_OF_RANGE, "bounding-box diagonal %.0f: edge costs must stay below 2^23 for the K-offset encoding", diag);
+
+    tspcuda_ctx *c = new tspcuda_ctx();
+    c->n = n; c->wt = weight_type; c->device = device;
+    c->metric = weight_type == TSPCUDA_EUC_REF ? (integer ? M_EUC_INTEGER : M_EUC_GENERAL) : (weight_type == TSPCUDA_CEIL_2D ? M_CEIL : M_ATT);
+#define CKC(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            int code_ = fail(e_ == cudaErrorMemoryAllocation ? TSPCUDA_RESOURCE_EXHAUSTED : TSPCUDA_INTERNAL, \
+                             "%s failed: %s", #call, cudaGetErrorString(e_));                          \
+            tspcuda_destroy(c);                                                                       \
+            return code_;                                                                             \
+        }                                                                                             \
+    } while (0)
+    CKC(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKC(cudaGetDeviceProperties(&prop, device));
+    if (!prop.cooperativeLaunch) { tspcuda_destroy(c); return fail(TSPCUDA_UNAVAILABLE, "device lacks cooperative launch"); }
+    c->num_sms = prop.multiProcessorCount;
+    int bps = 0;
+    DISPATCH_METRIC(c->metric, bps = coop_blocks_per_sm<M>());
+    if (bps <= 0) { tspcuda_destroy(c); return fail(TSPCUDA_INTERNAL, "descent kernel cannot be resident (built for sm_100a; device is sm_%d%d)", prop.major, prop.minor); }
+    c->max_coop_blocks = bps * c->num_sms;
+    CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&c->ev0));
+    CKC(cudaEventCreate(&c->ev1));
+    const size_t n1 = (size_t)n + 1;
+    CKC(cudaMalloc(&c->d_xy, sizeof(double2) * n));
+    CKC(cudaMalloc(&c->tour.pxy, sizeof(double2) * n1));
+    CKC(cudaMalloc(&c->tour.tid, sizeof(int) * n1));
+    CKC(cudaMalloc(&c->tour.dn, sizeof(int) * n1));
+    CKC(cudaMalloc(&c->tour.dns, sizeof(int) * n1));
+    CKC(cudaMalloc(&c->tour.pos, sizeof(int) * n));
+    c->tour.n = n;
+    CKC(cudaMalloc(&c->d_path, sizeof(int) * n));
+    CKC(cudaMalloc(&c->d_order, sizeof(int) * n));
+    CKC(cudaMalloc(&c->d_tabu, sizeof(int) * n));
+    CKC(cudaMalloc(&c->d_key, sizeof(unsigned long long) * 2));
+    CKC(cudaMalloc(&c->d_state, sizeof(DescState)));
+    CKC(cudaMalloc(&c->d_sum, sizeof(long long)));
+    c->log_cap = std::max<long long>(4096, 8LL * n);
+    CKC(cudaMalloc(&c->d_log, sizeof(MoveRec) * c->log_cap));
+    CKC(cudaMallocHost(&c->h_state, sizeof(DescState)));
+    CKC(cudaMallocHost(&c->h_buf, sizeof(int) * n));
+    CKC(cudaMemcpyAsync(c->d_xy, xy, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+    CKC(cudaStreamSynchronize(c->stream));
+    c->stats.h2d_bytes += (int64_t)sizeof(double2) * n;
+    const double pairs = 0.5 * (double)n * (double)(n - 1);
+    c->est_scan_s = std::max(pairs / 5e11, 8e-6);
+    *out = c;
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_nnodes(const tspcuda_ctx *c) { return c ? c->n : -1; }
+
+extern "C" int tspcuda_get_stats(tspcuda_ctx *c, tspcuda_stats *out) {
+    if (!c || !out) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
+    *out = c->stats;
+    return TSPCUDA_OK;
+}
+extern "C" int tspcuda_reset_stats(tspcuda_ctx *c) {
+    if (!c) return fail(TSPCUDA_INVALID_ARGUMENT, "null context");
+    c->stats = tspcuda_stats{};
+    return TSPCUDA_OK;
+}
+
+static inline int grid_for(int n, int cap) { return std::max(1, std::min(cap, (n + 255) / 256)); }
+
+// ---- tour slot -----------------------------------------------------------------------------
+// order already in c->d_order (device): build pxy/tid/pos/dn and the cost.
+static int tour_from_device_order(tspcuda_ctx *c) {
+    const int n = c->n;
+    const int g = grid_for(n + 1, 4 * c->num_sms);
+    CK(cudaMemsetAsync(c->d_state, 0, sizeof(DescState), c->stream));
+    c->dev_moves = 0;
+    tour_init_kernel<<<g, 256, 0, c->stream>>>(c->tour, c->d_xy, c->d_order);
+    DISPATCH_METRIC(c->metric, (tour_edges_kernel<M><<<g, 256, 0, c->stream>>>(c->tour, c->d_state)));
+    c->stats.kernel_launches += 2;
+    CK(cudaGetLastError());
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_tour_upload(tspcuda_ctx *c, const int *path) {
+    int e = use(c);
+    if (e) return e;
+    if (!path) return fail(TSPCUDA_INVALID_ARGUMENT, "null path");
+    const int n = c->n;
+    if (c->tour_loaded && (int)c->h_cache.size() == n && std::memcmp(c->h_cache.data(), path, sizeof(int) * n) == 0)
+        return TSPCUDA_OK;      // the device tour already is this successor array
+    // successor array -> visit order (data marshalling; also the single-cycle check of tsp.c:642-728)
+    int *order = c->h_buf;
+    int cur = 0;
+    for (int k = 0; k < n; k++) {
+        if (cur < 0 || cur >= n) return fail(TSPCUDA_INVALID_ARGUMENT, "path entry out of range");
+        order[k] = cur;
+        cur = path[cur];
+    }
+    if (cur != 0) return fail(TSPCUDA_INVALID_ARGUMENT, "path is not a single cycle through all nodes");
+    {   // permutation check
+        std::vector<unsigned char> seen(n, 0);
+        for (int k = 0; k < n; k++) {
+            if (seen[order[k]]) return fail(TSPCUDA_INVALID_ARGUMENT, "path is not a single cycle through all nodes");
+            seen[order[k]] = 1;
+        }
+    }
+    CK(cudaMemcpyAsync(c->d_order, order, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += (int64_t)sizeof(int) * n;
+    e = tour_from_device_order(c);
+    if (e) return e;
+    CK(cudaStreamSynchronize(c->stream));      // h_buf is reused
+    c->h_cache.assign(path, path + n);
+    c->tour_loaded = true;
+    return TSPCUDA_OK;
+}
+
+static int read_state(tspcuda_ctx *c) {
+    CK(cudaMemcpyAsync(c->h_state, c->d_state, sizeof(DescState), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += sizeof(DescState);
+    return TSPCUDA_OK;
+}
+
+template <class M>
+static cudaError_t launch_descend(tspcuda_ctx *c, int grid, long long max_moves, int init_best, int dns_is_dn) {
+    TourView V = c->tour;
+    if (dns_is_dn) V.dns = V.dn;
+    unsigned long long *key = c->d_key;
+    DescState *st = c->d_state;
+    MoveRec *log = c->d_log;
+    long long log_cap = c->log_cap;
+    void *args[] = {&V, &key, &st, &log, &log_cap, &max_moves, &init_best, &dns_is_dn};
+    return cudaLaunchCooperativeKernel((void *)descend_kernel<M>, dim3(grid), dim3(BLOCK), args, 0, c->stream);
+}
+
+// Run up to max_moves scan+move iterations on the device-resident tour (max_moves < 0: until no
+// admissible move is left).  mode 0 = 2-opt (improving moves only), 1 = tabu (best admissible).
+// The loop lives on the device; the host only re-launches in chunks of ~0.1 s so that the
+// reference's time limit (refinment.c:17-24) can be honoured between chunks.
+static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_limit_s, bool *deadline) {
+    const int n = c->n;
+    if (deadline) *deadline = false;
+    if (n < 4) {   // refinment.c:55 skips every pair of a tour with fewer than 4 nodes
+        const int one = 1;
+        CK(cudaMemcpyAsync(&c->d_state->status, &one, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+        return read_state(c);
+    }
+    const int nstrips = (n - 2 + SR - 1) / SR;
+    const long long total_cols = (long long)nstrips * (n - 2) - (long long)SR * ((long long)nstrips * (nstrips - 1) / 2);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(c->max_coop_blocks, total_cols / (WARPS * 48)));
+    const auto t0 = std::chrono::steady_clock::now();
+    const long long base = c->dev_moves;
+    const int init_best = mode == 0 ? -1 : BIGPEN / 2;
+    const int zero = 0;
+    CK(cudaMemcpyAsync(&c->d_state->status, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    for (;;) {
+        const long long done = c->dev_moves - base;
+        if (max_moves >= 0 && done >= max_moves) break;
+        long long chunk = (long long)std::max(4.0, std::min(8192.0, 0.1 / c->est_scan_s));
+        if (max_moves >= 0) chunk = std::min(chunk, max_moves - done);
+        CK(cudaMemsetAsync(c->d_key, 0xFF, sizeof(unsigned long long) * 2, c->stream));
+        CK(cudaEventRecord(c->ev0, c->stream));
+        cudaError_t le = cudaSuccess;
+        DISPATCH_METRIC(c->metric, le = launch_descend<M>(c, grid, chunk, init_best, mode == 0 ? 1 : 0));
+        CK(le);
+        CK(cudaEventRecord(c->ev1, c->stream));
+        c->stats.kernel_launches += 1;
+        int e = read_state(c);
+        if (e) return e;
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        const long long applied = c->h_state->moves - c->dev_moves;
+        c->dev_moves = c->h_state->moves;
+        const long long scans = applied + (c->h_state->status == 1 ? 1 : 0);
+        c->stats.moves += applied;
+        c->stats.scans += scans;
+        c->stats.pair_evals += scans * ((long long)n * (n - 1) / 2);
+        c->stats.scan_kernel_ms += ms;
+        c->stats.last_kernel_ms = ms;
+        if (scans > 0) c->est_scan_s = std::max(1e-6, 1e-3 * ms / (double)scans);
+        if (c->h_state->status == 1) break;
+        if (time_limit_s >= 0) {
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (el > time_limit_s) { if (deadline) *deadline = true; break; }
+        }
+    }
+    c->tour_loaded = (c->dev_moves == base) ? c->tour_loaded : false;   // host cache no longer matches
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_tour_descend(tspcuda_ctx *c, int64_t max_moves, int64_t *moves_out, int *at_local_optimum) {
+    int e = use(c);
+    if (e) return e;
+    const long long base = c->dev_moves;
+    e = descend(c, max_moves, 0, -1.0, nullptr);
+    if (e) return e;
+    if (moves_out) *moves_out = c->dev_moves - base;
+    if (at_local_optimum) *at_local_optimum = c->h_state->status == 1;
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_tour_download(tspcuda_ctx *c, int *path_out, double *cost_out) {
+    int e = use(c);
+    if (e) return e;
+    const int n = c->n;
+    if (path_out) {
+        tour_export_kernel<<<grid_for(n, 4 * c->num_sms), 256, 0, c->stream>>>(c->tour, c->d_path);
+        c->stats.kernel_launches += 1;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(c->h_buf, c->d_path, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+        c->stats.d2h_bytes += (int64_t)sizeof(int) * n;
+    }
+    e = read_state(c);
+    if (e) return e;
+    if (path_out) {
+        std::memcpy(path_out, c->h_buf, sizeof(int) * n);
+        c->h_cache.assign(path_out, path_out + n);
+        c->tour_loaded = true;
+    }
+    if (cost_out) *cost_out = (double)c->h_state->cost;
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_tour_movelog(tspcuda_ctx *c, tspcuda_move *log, int64_t cap, int64_t *count_out) {
+    int e = use(c);
+    if (e) return e;
+    e = read_state(c);
+    if (e) return e;
+    const long long have = std::min<long long>(c->h_state->log_count, c->log_cap);
+    const long long cnt = std::min<long long>(have, cap);
+    if (log && cnt > 0) {
+        static_assert(sizeof(tspcuda_move) == sizeof(MoveRec), "move record layout");
+        CK(cudaMemcpyAsync(log, c->d_log, sizeof(MoveRec) * cnt, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->stats.d2h_bytes += (int64_t)sizeof(MoveRec) * cnt;
+    }
+    if (count_out) *count_out = c->h_state->log_count;
+    return TSPCUDA_OK;
+}
+
+// ---- 2-opt entry points ---------------------------------------------------------------------
+extern "C" int tspcuda_two_opt(tspcuda_ctx *c, int *path, double *cost_out, int64_t max_moves, double time_limit_s,
+                               int64_t *moves_out, tspcuda_move *log, int64_t log_cap) {
+    int e = use(c);
+    if (e) return e;
+    c->tour_loaded = false;                       // ref_2opt recomputes the cost from the path it is given
+    e = tspcuda_tour_upload(c, path);
+    if (e) return e;
+    bool deadline = false;
+    e = descend(c, max_moves, 0, time_limit_s, &deadline);
+    if (e) return e;
+    if (moves_out) *moves_out = c->dev_moves;
+    if (log && log_cap > 0) {
+        int64_t cnt = 0;
+        e = tspcuda_tour_movelog(c, log, log_cap, &cnt);
+        if (e) return e;
+    }
+    e = tspcuda_tour_download(c, path, cost_out);
+    if (e) return e;
+    return deadline ? TSPCUDA_DEADLINE_EXCEEDED : TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_two_opt_once(tspcuda_ctx *c, int *path, double *cost_inout, double *best_delta_out,
+                                    tspcuda_move *move_out) {
+    int e = use(c);
+    if (e) return e;
+    if (!cost_inout) return fail(TSPCUDA_INVALID_ARGUMENT, "null cost");
+    e = tspcuda_tour_upload(c, path);
+    if (e) return e;
+    const long long base = c->dev_moves;
+    e = descend(c, 1, 0, -1.0, nullptr);
+    if (e) return e;
+    const bool moved = c->dev_moves > base;
+    if (move_out) {
+        move_out->a = moved ? c->h_state->last_a : -1;
+        move_out->b = moved ? c->h_state->last_b : -1;
+        move_out->delta = moved ? c->h_state->last_delta : 0;
+        move_out->reserved = 0;
+    }
+    if (best_delta_out) *best_delta_out = moved ? (double)c->h_state->last_delta : 0.0;
+    if (moved) {
+        *cost_inout += (double)c->h_state->last_delta;                  // refinment.c:85
+        e = tspcuda_tour_download(c, path, nullptr);
+        if (e) return e;
+    }
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_tabu_move(tspcuda_ctx *c, int *path, double *cost_inout, int *tabu_list, int tenure, int iter,
+                                 tspcuda_move *move_out) {
+    int e = use(c);
+    if (e) return e;
+    if (!cost_inout || !tabu_list) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
+    const int n = c->n;
+    e = tspcuda_tour_upload(c, path);
+    if (e) return e;
+    if (move_out) { move_out->a = -1; move_out->b = -1; move_out->delta = 0; move_out->reserved = 0; }
+    if (n < 4) return TSPCUDA_OK;
+    CK(cudaMemcpyAsync(c->d_tabu, tabu_list, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += (int64_t)sizeof(int) * n;
+    tabu_flags_kernel<<<grid_for(n + 1, 4 * c->num_sms), 256, 0, c->stream>>>(c->tour, c->d_tabu, tenure, iter);
+    c->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    const long long base = c->dev_moves;
+    e = descend(c, 1, 1, -1.0, nullptr);
+    if (e) return e;
+    if (c->dev_moves > base) {
+        const int a = c->h_state->last_a, b = c->h_state->last_b;
+        const int sa = path[a], sb = path[b];                            // successors BEFORE the move
+        *cost_inout += (double)c->h_state->last_delta;                  // metaheuristic.c:232
+        tabu_list[a] = iter; tabu_list[b] = iter; tabu_list[sa] = iter; tabu_list[sb] = iter;   // :235-238
+        if (move_out) { move_out->a = a; move_out->b = b; move_out->delta = c->h_state->last_delta; }
+        e = tspcuda_tour_download(c, path, nullptr);
+        if (e) return e;
+    }
+    return TSPCUDA_OK;
+}
+
+// ---- nearest neighbour ----------------------------------------------------------------------
+struct NNScratch {
+    double2 *cxy = nullptr;
+    int *cid = nullptr, *order = nullptr;
+    long long *cost = nullptr;
+    ~NNScratch() { cudaFree(cxy); cudaFree(cid); cudaFree(order); cudaFree(cost); }
+};
+
+__global__ void order_to_path_kernel(const int *order, int n, int *path) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+        path[order[p]] = order[p + 1 == n ? 0 : p + 1];
+}
+
+static int nn_batch(tspcuda_ctx *c, NNScratch &S, int first_start, int count, int stride, long long *h_cost) {
+    const int n = c->n;
+    DISPATCH_METRIC(c->metric, (nn_kernel<M><<<count, NN_BLOCK, 0, c->stream>>>(c->d_xy, n, first_start, stride, S.cxy, S.cid, S.order, S.cost)));
+    c->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(h_cost, S.cost, sizeof(long long) * count, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (int64_t)sizeof(long long) * count;
+    return TSPCUDA_OK;
+}
+
+static int nn_alloc(tspcuda_ctx *c, NNScratch &S, int batch) {
+    const size_t n = (size_t)c->n;
+    CK(cudaMalloc(&S.cxy, sizeof(double2) * n * batch));
+    CK(cudaMalloc(&S.cid, sizeof(int) * n * batch));
+    CK(cudaMalloc(&S.order, sizeof(int) * n * batch));
+    CK(cudaMalloc(&S.cost, sizeof(long long) * batch));
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_nn_multi(tspcuda_ctx *c, int first_start, int nstarts, int stride, double *costs_out,
+                                int *best_start_out, int *best_path_out, double *best_cost_out) {
+    int e = use(c);
+    if (e) return e;
+    const int n = c->n;
+    if (nstarts <= 0 || stride <= 0) return fail(TSPCUDA_INVALID_ARGUMENT, "nstarts/stride");
+    const long long last = (long long)first_start + (long long)(nstarts - 1) * stride;
+    if (first_start < 0 || last >= n) return fail(TSPCUDA_UNAVAILABLE, "starting node not correct");   // heuristics.c:223-226
+    const int batch = std::min(nstarts, 8 * c->num_sms);
+    NNScratch S;
+    e = nn_alloc(c, S, batch);
+    if (e) return e;
+    std::vector<long long> hc(batch);
+    long long best = -1;
+    int best_start = -1;
+    for (int done = 0; done < nstarts; done += batch) {
+        const int cnt = std::min(batch, nstarts - done);
+        const int fs = first_start + done * stride;
+        e = nn_batch(c, S, fs, cnt, stride, hc.data());
+        if (e) return e;
+        int bi = -1;
+        for (int k = 0; k < cnt; k++) {
+            if (costs_out) costs_out[done + k] = (double)hc[k];
+            if (best_start < 0 || hc[k] < best) { best = hc[k]; best_start = fs + k * stride; bi = k; }   // strict '<', heuristics.c:58
+        }
+        if (bi >= 0 && best_path_out) {
+            order_to_path_kernel<<<grid_for(n, 4 * c->num_sms), 256, 0, c->stream>>>(S.order + (size_t)bi * n, n, c->d_path);
+            c->stats.kernel_launches += 1;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(best_path_out, c->d_path, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->stats.d2h_bytes += (int64_t)sizeof(int) * n;
+        }
+    }
+    if (best_start_out) *best_start_out = best_start;
+    if (best_cost_out) *best_cost_out = (double)best;
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_nn(tspcuda_ctx *c, int start, int *path_out, double *cost_out) {
+    if (!c) return fail(TSPCUDA_INVALID_ARGUMENT, "null context");
+    if (start < 0 || start >= c->n) return fail(TSPCUDA_UNAVAILABLE, "starting node not correct");     // heuristics.c:223-226
+    int bs = -1;
+    return tspcuda_nn_multi(c, start, 1, 1, nullptr, &bs, path_out, cost_out);
+}
+
+// ---- multi-start NN + 2-opt (heuristics.c:74-116) --------------------------------------------
+extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int nstarts, int stride, double *nn_costs_out,
+                                          double *final_costs_out, int64_t *moves_out, int *best_start_out,
+                                          int *best_path_out, double *best_cost_out) {
+    int e = use(c);
+    if (e) return e;
+    const int n = c->n;
+    if (nstarts <= 0 || stride <= 0) return fail(TSPCUDA_INVALID_ARGUMENT, "nstarts/stride");
+    const long long last = (long long)first_start + (long long)(nstarts - 1) * stride;
+    if (first_start < 0 || last >= n) return fail(TSPCUDA_UNAVAILABLE, "starting node not correct");
+    const int batch = std::min(nstarts, 8 * c->num_sms);
+    NNScratch S;
+    e = nn_alloc(c, S, batch);
+    if (e) return e;
+    int *d_best_path = nullptr;
+    CK(cudaMalloc(&d_best_path, sizeof(int) * n));
+    std::vector<long long> hc(batch);
+    long long best = -1;
+    int best_start = -1;
+    int rc = TSPCUDA_OK;
+    for (int done = 0; done < nstarts && rc == TSPCUDA_OK; done += batch) {
+        const int cnt = std::min(batch, nstarts - done);
+        const int fs = first_start + done * stride;
+        rc = nn_batch(c, S, fs, cnt, stride, hc.data());
+        for (int k = 0; k < cnt && rc == TSPCUDA_OK; k++) {
+            if (nn_costs_out) nn_costs_out[done + k] = (double)hc[k];
+            // the NN visit order IS the tour-position order: no host round trip
+            cudaMemcpyAsync(c->d_order, S.order + (size_t)k * n, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream);
+            rc = tour_from_device_order(c);
+            if (rc) break;
+            c->tour_loaded = false;
+            rc = descend(c, -1, 0, -1.0, nullptr);
+            if (rc) break;
+            const long long fc = c->h_state->cost;
+            if (final_costs_out) final_costs_out[done + k] = (double)fc;
+            if (moves_out) moves_out[done + k] = c->h_state->moves;
+            if (best_start < 0 || fc < best) {                           // strict '<', tsp.c:671
+                best = fc; best_start = fs + k * stride;
+                tour_export_kernel<<<grid_for(n, 4 * c->num_sms), 256, 0, c->stream>>>(c->tour, d_best_path);
+                c->stats.kernel_launches += 1;
+            }
+        }
+    }
+    if (rc == TSPCUDA_OK && best_path_out && best_start >= 0) {
+        cudaError_t ce = cudaMemcpyAsync(best_path_out, d_best_path, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
+        if (ce != cudaSuccess) rc = fail(TSPCUDA_INTERNAL, "best path copy failed: %s", cudaGetErrorString(ce));
+        c->stats.d2h_bytes += (int64_t)sizeof(int) * n;
+    }
+    cudaStreamSynchronize(c->stream);
+    cudaFree(d_best_path);
+    if (rc) return rc;
+    if (best_start_out) *best_start_out = best_start;
+    if (best_cost_out) *best_cost_out = (double)best;
+    return TSPCUDA_OK;
+}
+
+// ---- K1 cost matrix ---------------------------------------------------------------------------
+extern "C" int tspcuda_cost_matrix_device(tspcuda_ctx *c, double *ms_out) {
+    int e = use(c);
+    if (e) return e;
+    const size_t n = (size_t)c->n;
+    if (!c->d_matrix) CK(cudaMalloc(&c->d_matrix, sizeof(double) * n * n));
+    const int grid = (int)std::min<size_t>(n, (size_t)c->num_sms * 8);
+    CK(cudaEventRecord(c->ev0, c->stream));
+    DISPATCH_METRIC(c->metric, (cost_matrix_kernel<M><<<grid, 256, 0, c->stream>>>(c->d_xy, c->n, c->d_matrix)));
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.last_kernel_ms = ms;
+    if (ms_out) *ms_out = ms;
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_cost_matrix(tspcuda_ctx *c, double *host_out) {
+    if (!host_out) return fail(TSPCUDA_INVALID_ARGUMENT, "null output");
+    int e = tspcuda_cost_matrix_device(c, nullptr);
+    if (e) return e;
+    const size_t n = (size_t)c->n;
+    CK(cudaMemcpyAsync(host_out, c->d_matrix, sizeof(double) * n * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stats.d2h_bytes += (int64_t)(sizeof(double) * n * n);
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_cost_matrix_checksum(tspcuda_ctx *c, int64_t *sum_out) {
+    int e = use(c);
+    if (e) return e;
+    if (!c->d_matrix) return fail(TSPCUDA_INVALID_ARGUMENT, "matrix not built: call tspcuda_cost_matrix_device first");
+    const unsigned long long cells = (unsigned long long)c->n * (unsigned long long)c->n;
+    CK(cudaMemsetAsync(c->d_sum, 0, sizeof(long long), c->stream));
+    matrix_checksum_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_matrix, cells, c->d_sum);
+    c->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    long long h = 0;
+    CK(cudaMemcpyAsync(&h, c->d_sum, sizeof(long long), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (sum_out) *sum_out = h;
+    return TSPCUDA_OK;
+}
+
+// ---- measurement helpers ----------------------------------------------------------------------
+template <int KIND>
+static cudaError_t run_pipe(tspcuda_ctx *c, int iters, double *d_sink) {
+    pipe_rate_kernel<KIND><<<c->num_sms * 8, 256, 0, c->stream>>>(iters, 1.5, d_sink);
+    return cudaGetLastError();
+}
+
+extern "C" int tspcuda_pipe_rate(tspcuda_ctx *c, int kind, double *ops_per_s_out) {
+    int e = use(c);
+    if (e) return e;
+    if (kind < 0 || kind > 6 || !ops_per_s_out) return fail(TSPCUDA_INVALID_ARGUMENT, "kind");
+    double *d_sink = nullptr;
+    CK(cudaMalloc(&d_sink, sizeof(double)));
+    const int iters = 4096;
+    float best_ms = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CK(cudaEventRecord(c->ev0, c->stream));
+        cudaError_t le;
+        switch (kind) {
+            case 0: le = run_pipe<0>(c, iters, d_sink); break;
+            case 1: le = run_pipe<1>(c, iters, d_sink); break;
+            case 2: le = run_pipe<2>(c, iters, d_sink); break;
+            case 3: le = run_pipe<3>(c, iters, d_sink); break;
+            case 4: le = run_pipe<4>(c, iters, d_sink); break;
+            case 5: le = run_pipe<5>(c, iters, d_sink); break;
+            default: le = run_pipe<6>(c, iters, d_sink); break;
+        }
+        CK(le);
+        CK(cudaEventRecord(c->ev1, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        c->stats.kernel_launches += 1;
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (rep > 0) best_ms = std::min(best_ms, ms);
+    }
+    cudaFree(d_sink);
+    const double per_iter = (kind == 3) ? 16.0 : 8.0;       // kind 3 = F2F.F32.F64 + F2F.F64.F32 per chain step
+    const double ops = (double)c->num_sms * 8 * 256 * (double)iters * per_iter;
+    *ops_per_s_out = ops / (best_ms * 1e-3);
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_selfcheck_sqrt(tspcuda_ctx *c, int64_t *mismatches_out) {
+    int e = use(c);
+    if (e) return e;
+    unsigned long long *d_bad = nullptr;
+    CK(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+    // floats in [2^-60, 2^64): bit patterns [ (127-60)<<23, (127+64)<<23 )
+    const unsigned lo = (unsigned)(127 - 60) << 23, hi = (unsigned)(127 + 64) << 23;
+    sqrt_selfcheck_kernel<<<c->num_sms * 16, 256, 0, c->stream>>>(lo, hi, d_bad);
+    c->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    unsigned long long h = 0;
+    CK(cudaMemcpyAsync(&h, d_bad, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    cudaFree(d_bad);
+    if (mismatches_out) *mismatches_out = (int64_t)h;
+    return TSPCUDA_OK;
+}
