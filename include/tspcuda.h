@@ -134,6 +134,13 @@ int tspcuda_multistart_two_opt(tspcuda_ctx *ctx, int first_start, int nstarts, i
                                int *best_path_out, double *best_cost_out);
 
 /* ---- measurement helpers -------------------------------------------------------------------- */
+/* CUDA-event bracket on the stream every kernel of this context is launched on (torch.cuda.Event
+ * only sees torch's own stream): start records an event, stop records another, synchronises and
+ * returns the elapsed device time in *ms_out. */
+int tspcuda_timer_start(tspcuda_ctx *ctx);
+int tspcuda_timer_stop(tspcuda_ctx *ctx, double *ms_out);
+/* Overwrites a scratch buffer larger than the 126 MB L2 (between timed iterations). */
+int tspcuda_flush_l2(tspcuda_ctx *ctx);
 /* Register-only pipe-rate microbenchmarks run on the context's device; result in operations/s
  * (thread-level, not warp-level).  kind: 0 DADD, 1 DMUL, 2 DFMA, 3 F2F.F32.F64, 4 MUFU.RSQ,
  * 5 FFMA, 6 the full EUC_REF edge-cost sequence (edge costs/s). */

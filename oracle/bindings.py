@@ -71,6 +71,8 @@ class Oracle:
         L.orc_nn_all.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp, _dp]
         L.orc_two_opt_scan.restype = C.c_double
         L.orc_two_opt_scan.argtypes = [_dp, C.c_int, C.c_int, _ip, _ip, _ip]
+        L.orc_two_opt_scan_rows.restype = C.c_longlong
+        L.orc_two_opt_scan_rows.argtypes = [_dp, C.c_int, C.c_int, _ip, C.c_int, C.c_int, _ip, _ip, _dp]
         L.orc_two_opt_once.restype = C.c_double
         L.orc_two_opt_once.argtypes = [_dp, C.c_int, C.c_int, _ip, _dp, _ip, _ip]
         L.orc_two_opt.restype = C.c_long
@@ -129,6 +131,13 @@ class Oracle:
         path = np.ascontiguousarray(path, dtype=np.int32)
         d = self.L.orc_two_opt_scan(_d(xy), xy.shape[0], wt, _i(path), C.byref(a), C.byref(b))
         return d, a.value, b.value
+
+    def two_opt_scan_rows(self, xy, path, a_lo, a_hi, wt=EUC_REF):
+        """Rows [a_lo, a_hi) of one scan: returns (pair iterations covered, delta, a, b)."""
+        a, b, d = C.c_int(-1), C.c_int(-1), C.c_double(0)
+        path = np.ascontiguousarray(path, dtype=np.int32)
+        pairs = self.L.orc_two_opt_scan_rows(_d(xy), xy.shape[0], wt, _i(path), a_lo, a_hi, C.byref(a), C.byref(b), C.byref(d))
+        return pairs, d.value, a.value, b.value
 
     def two_opt_once(self, xy, path, cost, wt=EUC_REF):
         """ref_2opt_once in place on path (int32 array): returns (best_delta, new cost, a, b)."""

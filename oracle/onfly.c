@@ -214,8 +214,18 @@ ORC_ROW_FN(orc_row_ceil, ORC_CEIL_2D)
 ORC_ROW_FN(orc_row_att, ORC_ATT)
 ORC_ROW_FN(orc_row_geo, ORC_GEO)
 
+static orc_move orc_scan_rows(const double *xy, int n, int wt, const int *path, double init,
+                              const int *tabu_list, int tenure, int iter, int a_lo, int a_hi);
+
 static orc_move orc_scan(const double *xy, int n, int wt, const int *path, double init,
                          const int *tabu_list, int tenure, int iter) {
+    return orc_scan_rows(xy, n, wt, path, init, tabu_list, tenure, iter, 0, n - 1);
+}
+
+/* The pair loop restricted to rows a in [a_lo, a_hi) (all b > a): the whole scan when
+ * [0, n-1); a bounded sample of it for CPU-baseline timing. */
+static orc_move orc_scan_rows(const double *xy, int n, int wt, const int *path, double init,
+                              const int *tabu_list, int tenure, int iter, int a_lo, int a_hi) {
     double *x = (double *)malloc((size_t)n * sizeof(double));
     double *y = (double *)malloc((size_t)n * sizeof(double));
     double *sx = (double *)malloc((size_t)n * sizeof(double));
@@ -240,7 +250,7 @@ static orc_move orc_scan(const double *xy, int n, int wt, const int *path, doubl
         orc_move loc = { init, -1, -1 };
         double *row = (double *)malloc((size_t)n * sizeof(double));
 #pragma omp for schedule(dynamic, 8) nowait
-        for (int a = 0; a < n - 1; a++) {
+        for (int a = a_lo; a < a_hi; a++) {
             if (tm[a]) continue;                                  /* metaheuristic.c:208 (a or succ_a tabu) */
             switch (wt) {
                 case ORC_EUC_REF: orc_row_euc(a, n, x, y, sx, sy, dn, row); break;
@@ -342,6 +352,21 @@ double orc_two_opt_scan(const double *xy, int n, int wt, const int *path, int *a
     orc_move m = orc_scan(xy, n, wt, path, 0.0, NULL, 0, 0);
     *a = m.a; *b = m.b;
     return m.delta;
+}
+
+/* Bounded sample of one scan: rows a in [a_lo, a_hi).  Returns the number of (a,b) pair
+ * iterations it covered (for pair-evals/s), the partial argmin in *a,*b,*delta. */
+long long orc_two_opt_scan_rows(const double *xy, int n, int wt, const int *path, int a_lo, int a_hi,
+                                int *a, int *b, double *delta) {
+    if (a_lo < 0) a_lo = 0;
+    if (a_hi > n - 1) a_hi = n - 1;
+    orc_move m = orc_scan_rows(xy, n, wt, path, 0.0, NULL, 0, 0, a_lo, a_hi);
+    if (a) *a = m.a;
+    if (b) *b = m.b;
+    if (delta) *delta = m.delta;
+    long long pairs = 0;
+    for (int r = a_lo; r < a_hi; r++) pairs += (long long)(n - 1 - r);
+    return pairs;
 }
 
 /* refinment.c:39-93 ref_2opt_once: scan, and if best_delta < EPSILON apply + cost += delta. */

@@ -26,7 +26,8 @@ EXPORTS = [
     "tspcuda_nnodes", "tspcuda_get_stats", "tspcuda_reset_stats", "tspcuda_cost_matrix", "tspcuda_cost_matrix_device",
     "tspcuda_cost_matrix_checksum", "tspcuda_nn", "tspcuda_nn_multi", "tspcuda_two_opt", "tspcuda_two_opt_once",
     "tspcuda_tabu_move", "tspcuda_tour_upload", "tspcuda_tour_descend", "tspcuda_tour_download", "tspcuda_tour_movelog",
-    "tspcuda_multistart_two_opt", "tspcuda_pipe_rate", "tspcuda_selfcheck_sqrt",
+    "tspcuda_multistart_two_opt", "tspcuda_pipe_rate", "tspcuda_selfcheck_sqrt", "tspcuda_timer_start",
+    "tspcuda_timer_stop", "tspcuda_flush_l2",
 ]
 
 
@@ -59,9 +60,10 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB):
+    path = os.environ.get("TSPCUDA_LIB", LIB)      # development override: an alternative build of the SAME library
+    if path == LIB and not os.path.exists(LIB):
         build()
-    L = C.CDLL(LIB)
+    L = C.CDLL(path)
     L.tspcuda_last_error.restype = C.c_char_p
     L.tspcuda_version.restype = C.c_char_p
     L.tspcuda_create.argtypes = [C.POINTER(_vp), _dp, C.c_int, C.c_int, C.c_int]
@@ -85,6 +87,9 @@ def lib():
     L.tspcuda_multistart_two_opt.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _i64p, _ip, _ip, _dp]
     L.tspcuda_pipe_rate.argtypes = [_vp, C.c_int, _dp]
     L.tspcuda_selfcheck_sqrt.argtypes = [_vp, _i64p]
+    L.tspcuda_timer_start.argtypes = [_vp]
+    L.tspcuda_timer_stop.argtypes = [_vp, _dp]
+    L.tspcuda_flush_l2.argtypes = [_vp]
     _lib = L
     return L
 
@@ -240,3 +245,14 @@ class Instance:
         m = C.c_int64(-1)
         _chk(lib().tspcuda_selfcheck_sqrt(self._h, C.byref(m)))
         return m.value
+
+    def timer_start(self):
+        _chk(lib().tspcuda_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_double(0)
+        _chk(lib().tspcuda_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def flush_l2(self):
+        _chk(lib().tspcuda_flush_l2(self._h))

@@ -1,0 +1,293 @@
+/*
+ * interpose.c -- the reference-side binding of libtspcuda.so: definitions of the reference's OWN
+ * hot-path symbols (same names, same signatures) that forward to the tspcuda_* C ABI.
+ *
+ * How it becomes a drop-in: the reference's translation
+ * units are compiled unchanged with -fPIC into libtspref.so; gcc's default semantic interposition
+ * routes even the intra-library calls (ref_2opt -> ref_2opt_once, h_greedy_2opt -> h_greedyutil,
+ * mh_TabuSearch -> tabu_best_move, tsp_read_input -> tsp_compute_costs ...) through the PLT, so the
+ * definitions below -- linked (or LD_PRELOADed) ahead of libtspref.so -- are the ones the
+ * unchanged driver and the unchanged src/algorithms entry points call.  This file is compiled
+ * against the reference's own headers (-I<reference>/src), so ERROR_CODE, tsp_solution,
+ * tabu_search, instance and options cannot drift; it is C, not C++ (bool is _Bool).
+ *
+ * Replaced symbols (reference file:line of the definition they shadow):
+ *   tsp_compute_costs   src/tsp.c:608          h_greedyutil     src/algorithms/heuristics.c:216
+ *   ref_2opt            refinment.c:3          ref_2opt_once    src/algorithms/refinment.c:39
+ *   tabu_best_move      metaheuristic.c:188
+ *   h_Greedy_iterative  heuristics.c:34  and  h_greedy_2opt  heuristics.c:74  (whole-loop overrides:
+ *                       all starts in one batched call; TSPCUDA_BATCH=0 keeps the reference's loops,
+ *                       which then call the interposed helpers start by start)
+ * ref_reverse_path (refinment.c:95) keeps the reference's definition: once ref_2opt_once and
+ * tabu_best_move run on the device nothing on this path calls it.
+ *
+ * No CPU fallback: if the GPU library fails the reference's error path is taken (INTERNAL, which
+ * the callers treat as fatal), never a silent host computation.  A foreign cost matrix (the
+ * fractional matrices of h_Greedy_2opt_mod_costs, heuristics.c:118, a CPLEX-only caller that is out
+ * of scope) is refused with UNIMPLEMENTED.
+ */
+#define _GNU_SOURCE
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include "algorithms/metaheuristic.h" /* reference header: -> heuristics.h -> refinment.h -> tsp.h */
+#include "tspcuda.h"
+
+static tspcuda_ctx *g_ctx = NULL;
+static point *g_points = NULL;
+static int g_n = -1;
+static long g_calls[8];
+enum { C_COSTS, C_NN, C_2OPT, C_2OPT_ONCE, C_TABU, C_ALLNN, C_MULTI };
+static const char *g_names[] = {"tsp_compute_costs", "h_greedyutil", "ref_2opt", "ref_2opt_once",
+                                "tabu_best_move", "h_Greedy_iterative", "h_greedy_2opt"};
+
+/* Exit hook.  Prints the call counters (TSPCUDA_STATS=1), flushes stdio and leaves with _exit().
+ * The last step shields the process from a latent heap overflow in the UNCHANGED driver:
+ * tsp_plot_solution (src/tsp.c:505-508) hands basename(tsp_env.inputfile) to utils_format_title
+ * (src/utils/utils.c:69-121), which strncpy()s strlen+51 bytes back into that strdup()ed buffer.
+ * The reference CPU binary happens to survive it; with more heap traffic in the process (the CUDA
+ * runtime) glibc can detect the smashed chunk header in a LATER exit handler and abort() after the
+ * result was printed but before stdout is flushed.  TSPCUDA_FAST_EXIT=0 disables the shield. */
+static void on_exit_hook(int status, void *arg) {
+    (void)arg;
+    const char *s = getenv("TSPCUDA_STATS");
+    if (s && *s == '1') {
+        fprintf(stderr, "[tspcuda] interposed calls:");
+        for (int i = 0; i < 7; i++) fprintf(stderr, " %s=%ld", g_names[i], g_calls[i]);
+        fprintf(stderr, "\n");
+    }
+    const char *f = getenv("TSPCUDA_FAST_EXIT");
+    if (f && *f == '0') return;
+    fflush(NULL);
+    _exit(status);
+}
+
+__attribute__((constructor)) static void selfcheck(void) {
+    /* a mis-link must not masquerade as a pass: the hot symbols have to resolve into THIS object */
+    Dl_info me, hot;
+    void *sym = dlsym(RTLD_DEFAULT, "ref_2opt_once");
+    if (dladdr((void *)&selfcheck, &me) && sym && dladdr(sym, &hot) && strcmp(me.dli_fname, hot.dli_fname) != 0)
+        fprintf(stderr, "[tspcuda] WARNING: ref_2opt_once resolves to %s, not to the interposer %s: the GPU path is NOT active "
+                        "(link with -Wl,--no-as-needed before libtspref, or LD_PRELOAD)\n", hot.dli_fname, me.dli_fname);
+    on_exit(on_exit_hook, NULL);
+}
+
+/* Heap shield for the overflow described above: the driver strdup()s the input file name
+ * (src/tsp.c:78,183) and later writes strlen+51 bytes into it.  This definition precedes libc's in
+ * the lookup order and gives every strdup() 128 spare bytes, so the overflow lands in slack instead
+ * of in the next chunk's header (glibc would abort in tsp_free_instance's free(), src/tsp.c:745). */
+char *strdup(const char *s) {
+    size_t n = strlen(s) + 1;
+    char *p = (char *)malloc(n + 128);
+    if (p) memcpy(p, s, n);
+    return p;
+}
+
+static int device_index(void) {
+    const char *d = getenv("TSPCUDA_DEVICE");
+    return d ? atoi(d) : 0;
+}
+
+static tspcuda_ctx *ctx_for_instance(void) {
+    if (g_ctx && g_points == tsp_inst.points && g_n == tsp_inst.nnodes) return g_ctx;
+    if (g_ctx) { tspcuda_destroy(g_ctx); g_ctx = NULL; }
+    /* `point` is {double x; double y;} (utils.h:37-40): the array IS the AoS layout of the ABI */
+    int e = tspcuda_create(&g_ctx, (const double *)tsp_inst.points, tsp_inst.nnodes, TSPCUDA_EUC_REF, device_index());
+    if (e != TSPCUDA_OK) {
+        log_error("code %d : libtspcuda: %s", e, tspcuda_last_error());
+        g_ctx = NULL;
+        return NULL;
+    }
+    g_points = tsp_inst.points;
+    g_n = tsp_inst.nnodes;
+    return g_ctx;
+}
+
+static double time_left(void) {          /* -1: no limit; otherwise seconds (may be <= 0) */
+    if (tsp_env.timelimit == -1.0) return -1.0;
+    double left = tsp_env.timelimit - utils_timeelapsed(&tsp_inst.c);
+    return left > 0 ? left : 0.0;
+}
+
+static bool batch_enabled(void) {
+    const char *b = getenv("TSPCUDA_BATCH");
+    return !(b && *b == '0');
+}
+
+/* ---- tsp_compute_costs, src/tsp.c:608-636 --------------------------------------------------- */
+ERROR_CODE tsp_compute_costs(void) {
+    g_calls[C_COSTS]++;
+    if (tsp_inst.nnodes <= 0) {
+        log_fatal("computing costs of empty graph");
+        tsp_handlefatal();
+    }
+    tspcuda_ctx *c = ctx_for_instance();
+    if (!c) return INTERNAL;
+    /* The unchanged host code still reads tsp_inst.costs (tsp_get_cost users: ExtraMileage, CPLEX,
+     * tsp_solution_cost), and free()s it (tsp.c:747): allocate with calloc as the reference does and
+     * fill it from the device -- when it can exist at all (the reference's int n*n overflows at
+     * 46341, tsp.c:614).  Beyond that, or with TSPCUDA_MATRIX=off, it stays NULL and only the
+     * on-the-fly device paths are served. */
+    const char *m = getenv("TSPCUDA_MATRIX");
+    size_t n = (size_t)tsp_inst.nnodes;
+    if ((m && strcmp(m, "off") == 0) || n > 46340) {
+        tsp_inst.costs = NULL;
+        log_warn("libtspcuda: host cost matrix not materialised (n = %d); on-the-fly device costs only", tsp_inst.nnodes);
+        return T_OK;
+    }
+    tsp_inst.costs = (double *)calloc(n * n, sizeof(double));
+    if (!tsp_inst.costs) return RESOURCE_EXHAUSTED;
+    int e = tspcuda_cost_matrix(c, tsp_inst.costs);
+    if (e != TSPCUDA_OK) {
+        log_error("code %d : libtspcuda: %s", e, tspcuda_last_error());
+        return (ERROR_CODE)e;
+    }
+    return T_OK;
+}
+
+static bool foreign_costs(const double *costs) { return costs != tsp_inst.costs; }
+
+/* ---- h_greedyutil, src/algorithms/heuristics.c:216-288 ------------------------------------- */
+ERROR_CODE h_greedyutil(int starting_node, tsp_solution *solution, double *costs) {
+    g_calls[C_NN]++;
+    if (costs == NULL && tsp_inst.costs != NULL) {           /* :218-221 */
+        log_error("matrix of costs not found");
+        return INTERNAL;
+    }
+    if (starting_node >= tsp_inst.nnodes || starting_node < 0) {   /* :223-226 */
+        log_error("starting node not correct");
+        return UNAVAILABLE;
+    }
+    if (foreign_costs(costs)) {
+        log_error("libtspcuda: h_greedyutil on a foreign cost matrix is not implemented on the device");
+        return UNIMPLEMENTED;
+    }
+    if (tsp_env.timelimit != -1.0 && utils_timeelapsed(&tsp_inst.c) > tsp_env.timelimit) {   /* :240-246 */
+        log_warn("time limit exceeded in greedy util");
+        return DEADLINE_EXCEEDED;
+    }
+    tspcuda_ctx *c = ctx_for_instance();
+    if (!c) return INTERNAL;
+    int e = tspcuda_nn(c, starting_node, solution->path, &solution->cost);
+    if (e != TSPCUDA_OK) log_error("code %d : libtspcuda: %s", e, tspcuda_last_error());
+    return (ERROR_CODE)e;
+}
+
+/* ---- ref_2opt, src/algorithms/refinment.c:3-37 --------------------------------------------- */
+ERROR_CODE ref_2opt(tsp_solution *solution, double *costs, bool update_incumbent) {
+    g_calls[C_2OPT]++;
+    if (foreign_costs(costs)) {
+        log_error("libtspcuda: ref_2opt on a foreign cost matrix is not implemented on the device");
+        return UNIMPLEMENTED;
+    }
+    tspcuda_ctx *c = ctx_for_instance();
+    if (!c) return INTERNAL;
+    ERROR_CODE e = T_OK;
+    double left = time_left();
+    int64_t moves = 0;
+    /* left == 0: the reference recomputes the cost (:6-9) and leaves at the first time check (:17-24) */
+    int rc = tspcuda_two_opt(c, solution->path, &solution->cost, left == 0.0 ? 0 : -1, left, &moves, NULL, 0);
+    if (rc == TSPCUDA_DEADLINE_EXCEEDED || left == 0.0) {
+        log_debug("time limit exceeded in 2opt");
+        e = DEADLINE_EXCEEDED;
+    } else if (rc != TSPCUDA_OK) {
+        log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
+        return (ERROR_CODE)rc;
+    }
+    if (update_incumbent) {                                     /* :29-34 */
+        ERROR_CODE error = tsp_update_best_solution(solution);
+        if (!err_ok(error)) log_error("code %d : Error in 2opt solution update", error);
+    }
+    return e;
+}
+
+/* ---- ref_2opt_once, src/algorithms/refinment.c:39-93 --------------------------------------- */
+double ref_2opt_once(tsp_solution *solution, double *costs) {
+    g_calls[C_2OPT_ONCE]++;
+    tspcuda_ctx *c = foreign_costs(costs) ? NULL : ctx_for_instance();
+    if (!c) {
+        log_fatal("libtspcuda: ref_2opt_once cannot run (foreign cost matrix or no device): %s", tspcuda_last_error());
+        tsp_handlefatal();
+    }
+    double delta = 0;
+    int rc = tspcuda_two_opt_once(c, solution->path, &solution->cost, &delta, NULL);
+    if (rc != TSPCUDA_OK) {
+        log_fatal("code %d : libtspcuda: %s", rc, tspcuda_last_error());
+        tsp_handlefatal();
+    }
+    return delta;
+}
+
+/* ---- tabu_best_move, src/algorithms/metaheuristic.c:188-245 -------------------------------- */
+ERROR_CODE tabu_best_move(int *solution_path, double *solution_cost, tabu_search *ts, int current_iteration) {
+    g_calls[C_TABU]++;
+    tspcuda_ctx *c = ctx_for_instance();
+    if (!c) return INTERNAL;
+    int rc = tspcuda_tabu_move(c, solution_path, solution_cost, ts->tabu_list, ts->tenure, current_iteration, NULL);
+    if (rc != TSPCUDA_OK) {
+        log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
+        return (ERROR_CODE)rc;
+    }
+    return T_OK;
+}
+
+/* ---- whole-loop overrides ------------------------------------------------------------------- */
+typedef ERROR_CODE (*void_fn)(void);
+
+/* h_Greedy_iterative, heuristics.c:34-72: every start in ascending order; the incumbent changes only
+ * on a strictly smaller cost (:58 and tsp.c:671), so its final state is the FIRST start attaining
+ * the minimum -- exactly what tspcuda_nn_multi returns -- and starting_node is that start (:60). */
+ERROR_CODE h_Greedy_iterative(void) {
+    if (!batch_enabled() || tsp_env.timelimit != -1.0)
+        return ((void_fn)dlsym(RTLD_NEXT, "h_Greedy_iterative"))();      /* the reference loop over the interposed helpers */
+    g_calls[C_ALLNN]++;
+    log_info("running All Nearest Neighbour");
+    tspcuda_ctx *c = ctx_for_instance();
+    if (!c) return INTERNAL;
+    tsp_solution solution;
+    tsp_init_solution(tsp_inst.nnodes, &solution);
+    int best_start = -1;
+    int rc = tspcuda_nn_multi(c, 0, tsp_inst.nnodes, 1, NULL, &best_start, solution.path, &solution.cost);
+    if (rc != TSPCUDA_OK) {
+        log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
+        utils_safe_free(solution.path);
+        return (ERROR_CODE)rc;
+    }
+    if (solution.cost < tsp_inst.best_solution.cost) {
+        log_info("found new best, node %d", best_start);
+        tsp_inst.starting_node = best_start;
+        ERROR_CODE error = tsp_update_best_solution(&solution);
+        if (!err_ok(error)) log_error("code %d : error in updating best solution of greedy iterative", error);
+    }
+    utils_safe_free(solution.path);
+    return T_OK;
+}
+
+/* h_greedy_2opt, heuristics.c:74-116: NN + ref_2opt(update_incumbent) per start.  Final incumbent =
+ * first start attaining the minimum final cost; starting_node is set on EVERY iteration whose
+ * ref_2opt returns T_OK (:105-109), so it ends as nnodes-1. */
+ERROR_CODE h_greedy_2opt(void) {
+    if (!batch_enabled() || tsp_env.timelimit != -1.0)
+        return ((void_fn)dlsym(RTLD_NEXT, "h_greedy_2opt"))();
+    g_calls[C_MULTI]++;
+    log_info("running All Nearest Neighbour + 2OPT");
+    tspcuda_ctx *c = ctx_for_instance();
+    if (!c) return INTERNAL;
+    tsp_solution solution;
+    tsp_init_solution(tsp_inst.nnodes, &solution);
+    int best_start = -1;
+    int rc = tspcuda_multistart_two_opt(c, 0, tsp_inst.nnodes, 1, NULL, NULL, NULL, &best_start, solution.path, &solution.cost);
+    if (rc != TSPCUDA_OK) {
+        log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
+        utils_safe_free(solution.path);
+        return (ERROR_CODE)rc;
+    }
+    ERROR_CODE error = tsp_update_best_solution(&solution);
+    if (!err_ok(error)) log_error("code %d : Error in 2opt solution update", error);
+    tsp_inst.starting_node = tsp_inst.nnodes - 1;
+    utils_safe_free(solution.path);
+    return T_OK;
+}

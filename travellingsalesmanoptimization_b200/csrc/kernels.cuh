@@ -23,10 +23,18 @@ namespace cg = cooperative_groups;
 
 namespace tspcuda {
 
-constexpr int R = 4;                 // tour positions (rows) owned by one lane
+#ifndef TSP_R
+#define TSP_R 4
+#endif
+#ifndef TSP_UNROLL
+#define TSP_UNROLL 2
+#endif
+constexpr int R = TSP_R;             // tour positions (rows) owned by one lane
 constexpr int SR = 32 * R - 1;       // pair rows per warp strip (last D row is the next strip's first)
-constexpr int BLOCK = 256;
-constexpr int WARPS = BLOCK / 32;
+constexpr int UNROLL = TSP_UNROLL;
+constexpr int BLOCK_SMALL = 256;      // descent kernel block size for n < BIG_N (fewer, lighter CTAs: cheaper grid syncs)
+constexpr int BLOCK_BIG = 512;        // and for n >= BIG_N (64 regs/thread, 32 warps/SM: +12% pair rate, profiles/)
+constexpr int BIG_N = 8192;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct TourView {
@@ -65,7 +73,7 @@ __device__ __forceinline__ void sweep_block(const TourView &V, int i0, int c, in
                                             unsigned long long &bestkey, int *blk_best) {
     const int lane = threadIdx.x & 31;
     const int n = V.n;
-#pragma unroll 2
+#pragma unroll UNROLL
     for (int k = 0; k < cnt; ++k) {
         const double2 cj = sxy[k];
         const int dj = sdn[k];
@@ -82,7 +90,10 @@ __device__ __forceinline__ void sweep_block(const TourView &V, int i0, int c, in
             for (int r = 0; r < R; ++r)
                 if (j - (i0 + lane * R + r) < 2) m[r] += BIGPEN;
         }
-        int mm = min(min(m[0], m[1]), min(m[2], m[3])) - dj;
+        int mm = m[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) mm = min(mm, m[r]);
+        mm -= dj;
         if (__any_sync(FULL, mm <= best)) {
             // rare path: a pair at least as good as the warp's running best
             const int j = c + k - 1;
@@ -232,10 +243,11 @@ __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int 
 // init_best = -1  : 2-opt, only improving moves (best_delta < -1e-7 on integer deltas)
 // init_best = BIGPEN/2 : tabu, best admissible move even if worsening (metaheuristic.c:189,225)
 // ---------------------------------------------------------------------------------------------
-template <class M>
-__global__ void __launch_bounds__(BLOCK, 2)
+template <class M, int BLK>
+__global__ void __launch_bounds__(BLK, 1024 / BLK)
 descend_kernel(TourView V, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
                long long max_moves, int init_best, int dns_is_dn) {
+    constexpr int WARPS = BLK / 32;
     cg::grid_group grid = cg::this_grid();
     __shared__ double2 s_xy[WARPS][32];
     __shared__ int s_dn[WARPS][32];
@@ -249,8 +261,8 @@ descend_kernel(TourView V, unsigned long long *key, DescState *st, MoveRec *log,
     const long long gw = (long long)blockIdx.x * WARPS + warp;
     const long long W = (long long)gridDim.x * WARPS;
     const long long lo = total * gw / W, hi = total * (gw + 1) / W;
-    const int gtid = blockIdx.x * BLOCK + threadIdx.x;
-    const int gsize = gridDim.x * BLOCK;
+    const int gtid = blockIdx.x * BLK + threadIdx.x;
+    const int gsize = gridDim.x * BLK;
 
     for (long long it = 0; it < max_moves; ++it) {
         if (threadIdx.x == 0) { s_key = KEY_EMPTY; s_best = init_best; }

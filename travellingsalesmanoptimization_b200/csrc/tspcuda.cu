@@ -49,7 +49,7 @@ enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3 };
 
 struct tspcuda_ctx {
     int n = 0, wt = 0, device = 0, metric = 0;
-    int num_sms = 0, max_coop_blocks = 0;
+    int num_sms = 0, max_coop_blocks = 0, block = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double2 *d_xy = nullptr;
@@ -67,6 +67,8 @@ struct tspcuda_ctx {
     tspcuda_stats stats{};
     double est_scan_s = 0;
     long long dev_moves = 0;         // host mirror of d_state->moves
+    cudaEvent_t tev0 = nullptr, tev1 = nullptr;
+    void *d_flush = nullptr;
 };
 
 extern "C" const char *tspcuda_last_error(void) { return g_err.c_str(); }
@@ -84,10 +86,10 @@ static int use(tspcuda_ctx *c) {
     return TSPCUDA_OK;
 }
 
-template <class M>
+template <class M, int BLK>
 static int coop_blocks_per_sm() {
     int b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, descend_kernel<M>, BLOCK, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, descend_kernel<M, BLK>, BLK, 0);
     return b;
 }
 
@@ -98,7 +100,9 @@ extern "C" void tspcuda_destroy(tspcuda_ctx *c) {
     cudaFree(c->d_xy); cudaFree(c->tour.pxy); cudaFree(c->tour.tid); cudaFree(c->tour.dn);
     cudaFree(c->tour.dns); cudaFree(c->tour.pos); cudaFree(c->d_path); cudaFree(c->d_order);
     cudaFree(c->d_tabu); cudaFree(c->d_key); cudaFree(c->d_state); cudaFree(c->d_log);
-    cudaFree(c->d_matrix); cudaFree(c->d_sum);
+    cudaFree(c->d_matrix); cudaFree(c->d_sum); cudaFree(c->d_flush);
+    if (c->tev0) cudaEventDestroy(c->tev0);
+    if (c->tev1) cudaEventDestroy(c->tev1);
     if (c->h_state) cudaFreeHost(c->h_state);
     if (c->h_buf) cudaFreeHost(c->h_buf);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -148,12 +152,16 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
     if (!prop.cooperativeLaunch) { tspcuda_destroy(c); return fail(TSPCUDA_UNAVAILABLE, "device lacks cooperative launch"); }
     c->num_sms = prop.multiProcessorCount;
     int bps = 0;
-    DISPATCH_METRIC(c->metric, bps = coop_blocks_per_sm<M>());
+    c->block = n >= BIG_N ? BLOCK_BIG : BLOCK_SMALL;
+    if (c->block == BLOCK_BIG) { DISPATCH_METRIC(c->metric, (bps = coop_blocks_per_sm<M, BLOCK_BIG>())); }
+    else { DISPATCH_METRIC(c->metric, (bps = coop_blocks_per_sm<M, BLOCK_SMALL>())); }
     if (bps <= 0) { tspcuda_destroy(c); return fail(TSPCUDA_INTERNAL, "descent kernel cannot be resident (built for sm_100a; device is sm_%d%d)", prop.major, prop.minor); }
     c->max_coop_blocks = bps * c->num_sms;
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CKC(cudaEventCreate(&c->ev0));
     CKC(cudaEventCreate(&c->ev1));
+    CKC(cudaEventCreate(&c->tev0));
+    CKC(cudaEventCreate(&c->tev1));
     const size_t n1 = (size_t)n + 1;
     CKC(cudaMalloc(&c->d_xy, sizeof(double2) * n));
     CKC(cudaMalloc(&c->tour.pxy, sizeof(double2) * n1));
@@ -259,7 +267,9 @@ static cudaError_t launch_descend(tspcuda_ctx *c, int grid, long long max_moves,
     MoveRec *log = c->d_log;
     long long log_cap = c->log_cap;
     void *args[] = {&V, &key, &st, &log, &log_cap, &max_moves, &init_best, &dns_is_dn};
-    return cudaLaunchCooperativeKernel((void *)descend_kernel<M>, dim3(grid), dim3(BLOCK), args, 0, c->stream);
+    if (c->block == BLOCK_BIG)
+        return cudaLaunchCooperativeKernel((void *)descend_kernel<M, BLOCK_BIG>, dim3(grid), dim3(BLOCK_BIG), args, 0, c->stream);
+    return cudaLaunchCooperativeKernel((void *)descend_kernel<M, BLOCK_SMALL>, dim3(grid), dim3(BLOCK_SMALL), args, 0, c->stream);
 }
 
 // Run up to max_moves scan+move iterations on the device-resident tour (max_moves < 0: until no
@@ -276,7 +286,7 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
     }
     const int nstrips = (n - 2 + SR - 1) / SR;
     const long long total_cols = (long long)nstrips * (n - 2) - (long long)SR * ((long long)nstrips * (nstrips - 1) / 2);
-    const int grid = (int)std::max<long long>(1, std::min<long long>(c->max_coop_blocks, total_cols / (WARPS * 48)));
+    const int grid = (int)std::max<long long>(1, std::min<long long>(c->max_coop_blocks, total_cols / ((c->block / 32) * 48)));
     const auto t0 = std::chrono::steady_clock::now();
     const long long base = c->dev_moves;
     const int init_best = mode == 0 ? -1 : BIGPEN / 2;
@@ -686,5 +696,33 @@ extern "C" int tspcuda_selfcheck_sqrt(tspcuda_ctx *c, int64_t *mismatches_out) {
     CK(cudaStreamSynchronize(c->stream));
     cudaFree(d_bad);
     if (mismatches_out) *mismatches_out = (int64_t)h;
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_timer_start(tspcuda_ctx *c) {
+    int e = use(c);
+    if (e) return e;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaEventRecord(c->tev0, c->stream));
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_timer_stop(tspcuda_ctx *c, double *ms_out) {
+    int e = use(c);
+    if (e) return e;
+    CK(cudaEventRecord(c->tev1, c->stream));
+    CK(cudaEventSynchronize(c->tev1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->tev0, c->tev1));
+    if (ms_out) *ms_out = ms;
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_flush_l2(tspcuda_ctx *c) {
+    int e = use(c);
+    if (e) return e;
+    const size_t bytes = 192u << 20;
+    if (!c->d_flush) CK(cudaMalloc(&c->d_flush, bytes));
+    CK(cudaMemsetAsync(c->d_flush, 0x5A, bytes, c->stream));
     return TSPCUDA_OK;
 }
