@@ -98,6 +98,10 @@ def main():
         per.append([int(c), int(m), int(c2), fnv1a(p2)])
     G["pr2392"]["greedy_2opt_first8"] = per
     G["pr2392"]["greedy_2opt_survey"] = {"cost": 393339, "first_start": 359}
+    # h_greedy_2opt per contiguous start range [lo, hi): best cost, first start reaching it
+    # (reference objects, 6 processes, 16 846 core-seconds in the survey; not re-run here)
+    G["pr2392"]["greedy_2opt_survey_ranges"] = [[0, 399, 393339, 359], [399, 798, 395324, 694], [798, 1197, 394366, 1127],
+                                                [1197, 1596, 396407, 1478], [1596, 1995, 394973, 1888], [1995, 2392, 395463, 2182]]
     print("pr2392 first8", per, flush=True)
 
     # tabu: step-level log on berlin52 / kroA100 from the NN(0)+2-opt tour, linear tenure

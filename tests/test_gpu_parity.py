@@ -327,6 +327,43 @@ def test_multistart_pr2392_first8_and_strided(tsp, golden):
         assert [int(f) for f in fin2] == [g[1][2], g[5][2]]
 
 
+def test_multistart_cta_paths_vs_grid_path(tsp, oracle):
+    """The CTA-per-descent kernel (n <= 7600; 512- and 1024-thread variants) and the grid-wide
+    descent kernel must produce the same tours: compare multistart (CTA path) with nn + two_opt
+    (grid path) start by start, and one start of each size with the CPU oracle."""
+    for n, starts in ((130, 6), (1500, 4), (3700, 3)):
+        xy = _rand_xy(900 + n, n, n % 2 == 0)
+        with tsp.Instance(xy) as I:
+            bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(2, starts, 5)
+            per = []
+            for k in range(starts):
+                code, p, c = I.nn(2 + 5 * k)
+                code, mv, p2, c2, _ = I.two_opt(p)
+                per.append((c, mv, c2, p2))
+            assert [(a, m, f) for a, m, f in zip(nn_costs, moves, final)] == [(c, mv, c2) for c, mv, c2, _ in per]
+            best = min(range(starts), key=lambda k: (per[k][2], k))
+            assert bs == 2 + 5 * best and bc == per[best][2] and np.array_equal(bp, per[best][3])
+        e, po, co = oracle.nn(xy, 2)
+        m_o, p_o, c_o, *_ = oracle.two_opt(xy, po, log=False)
+        assert (co, m_o, c_o) == per[0][:3] and np.array_equal(p_o, per[0][3])
+
+
+def test_pr2392_all_start_config2(tsp, golden):
+    """Config 2: all 2392 starts NN + 2-opt on one B200.  The reference objects need 4.68 core-hours
+    (BASELINE.md section 3): 393339, first reached at start 359; per-range bests for sharding checks."""
+    xy, _ = load_instance("pr2392")
+    with tsp.Instance(xy) as I:
+        bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(0, 2392)
+        bs_nn, bp_nn, bc_nn, _ = I.nn_multi(0, 2392)
+    assert (int(bc), bs) == (golden["pr2392"]["greedy_2opt_survey"]["cost"], golden["pr2392"]["greedy_2opt_survey"]["first_start"])
+    for lo, hi, cost, first in golden["pr2392"]["greedy_2opt_survey_ranges"]:
+        seg = final[lo:hi]
+        assert int(seg.min()) == cost and lo + int(np.argmin(seg)) == first, (lo, hi)
+    assert [[int(a), int(m), int(f)] for a, m, f in zip(nn_costs[:8], moves[:8], final[:8])] == \
+        [r[:3] for r in golden["pr2392"]["greedy_2opt_first8"]]
+    assert (int(bc_nn), bs_nn, fnv1a(bp_nn)) == (golden["pr2392"]["allnn"]["cost"], golden["pr2392"]["allnn"]["start"], golden["pr2392"]["allnn"]["hash"])
+
+
 # ---- full-size configs ------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["usa13509", "d15112"])
 def test_large_first_moves_golden(tsp, golden, name):

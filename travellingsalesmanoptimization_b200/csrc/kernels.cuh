@@ -299,6 +299,106 @@ descend_kernel(TourView V, unsigned long long *key, DescState *st, MoveRec *log,
 }
 
 // ---------------------------------------------------------------------------------------------
+// K6: one CTA per descent, whole tour resident in shared memory (n <= CTA_MAX_N).  Used for
+// multi-start work on small instances (h_greedy_2opt on pr2392-class inputs), where one scan is a
+// few microseconds of whole-GPU work and a grid-wide barrier per move would dominate: here a move
+// costs three __syncthreads.  CTAs pull starts from an atomic counter; up to three CTAs share an SM.
+// The scan and the move are the SAME device functions as in descend_kernel (scan_range,
+// apply_move), only pointed at shared memory, so results are identical by construction.
+// ---------------------------------------------------------------------------------------------
+constexpr int CTA_MAX_N = 7600;          // 28 B/node + staging must fit 227 KB
+constexpr int CTA_SMALL_N = 3600;        // up to here two 512-thread CTAs share an SM; above, one of 1024
+
+__host__ __device__ inline size_t cta_smem_bytes(int n, int CTA_WARPS) {
+    const size_t n1 = (size_t)n + 1;
+    size_t b = 16 * n1;                  // pxy
+    b += 4 * n1 * 2;                     // tid, dn
+    b += 4 * (size_t)n;                  // pos
+    b = (b + 15) & ~(size_t)15;
+    b += (size_t)CTA_WARPS * 32 * (16 + 4);   // per-warp column staging
+    return b + 64;
+}
+
+template <class M, int CTA_BLOCK>
+__global__ void __launch_bounds__(CTA_BLOCK, 1024 / CTA_BLOCK)
+descend_cta_kernel(const double2 *__restrict__ xy, int n, const int *__restrict__ order_all, int nstarts,
+                   int *next_start, long long *final_cost, long long *moves_out, int *path_all) {
+    constexpr int CTA_WARPS = CTA_BLOCK / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ unsigned long long s_key;
+    __shared__ int s_best, s_cur;
+    __shared__ long long s_cost;
+    const size_t n1 = (size_t)n + 1;
+    TourView V;
+    V.n = n;
+    V.pxy = reinterpret_cast<double2 *>(smem_raw);
+    V.tid = reinterpret_cast<int *>(smem_raw + 16 * n1);
+    V.dn = V.tid + n1;
+    V.dns = V.dn;
+    V.pos = V.dn + n1;
+    size_t off = (16 * n1 + 4 * n1 * 2 + 4 * (size_t)n + 15) & ~(size_t)15;
+    double2 *stage_xy = reinterpret_cast<double2 *>(smem_raw + off);
+    int *stage_dn = reinterpret_cast<int *>(smem_raw + off + (size_t)CTA_WARPS * 32 * 16);
+
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int nstrips = (n - 2 + SR - 1) / SR;
+    const long long total = strip_prefix(nstrips, n);
+    const long long lo = total * warp / CTA_WARPS, hi = total * (warp + 1) / CTA_WARPS;
+
+    for (;;) {
+        if (t == 0) s_cur = atomicAdd(next_start, 1);
+        __syncthreads();
+        const int cur = s_cur;
+        if (cur >= nstarts) break;
+        const int *order = order_all + (size_t)cur * n;
+        for (int p = t; p <= n; p += CTA_BLOCK) {
+            const int node = order[p == n ? 0 : p];
+            V.pxy[p] = xy[node];
+            V.tid[p] = node;
+            if (p < n) V.pos[node] = p;
+        }
+        if (t == 0) s_cost = 0;
+        __syncthreads();
+        long long local = 0;
+        for (int p = t; p < n; p += CTA_BLOCK) {
+            const double2 u = V.pxy[p], v = V.pxy[p + 1];
+            const int k = M::K(u.x, u.y, v.x, v.y);
+            V.dn[p] = k;
+            if (p == 0) V.dn[n] = k;
+            local += (long long)(k - KOFF);
+        }
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(FULL, local, o);
+        if (lane == 0) atomicAdd((unsigned long long *)&s_cost, (unsigned long long)local);
+        long long moves = 0;
+        for (;;) {
+            if (t == 0) { s_key = KEY_EMPTY; s_best = -1; }
+            __syncthreads();
+            int best = -1;
+            unsigned long long bestkey = KEY_EMPTY;
+            scan_range<M>(V, lo, hi, nstrips, best, bestkey, stage_xy + warp * 32, stage_dn + warp * 32, &s_best);
+            bestkey = warp_min_key(bestkey);
+            if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
+            __syncthreads();
+            const unsigned long long kbest = s_key;
+            if (kbest == KEY_EMPTY) break;                      // local optimum (refinment.c:27)
+            const int a = key_a(kbest), b = key_b(kbest);
+            int seg_s, seg_e;
+            apply_move<M>(V, a, b, t, CTA_BLOCK, false, seg_s, seg_e);
+            if (t == 0) s_cost += key_delta(kbest);
+            ++moves;
+            __syncthreads();
+            if (t == 0) { V.pos[b] = seg_s; V.pos[V.tid[seg_e]] = seg_e; }
+        }
+        if (t == 0) { final_cost[cur] = s_cost; moves_out[cur] = moves; }
+        if (path_all) {
+            int *path = path_all + (size_t)cur * n;
+            for (int p = t; p < n; p += CTA_BLOCK) path[V.tid[p]] = V.tid[p + 1];
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Tour set-up / export kernels.
 // ---------------------------------------------------------------------------------------------
 // order[p] = node at position p (host walked the successor array).  Fills pxy, tid, pos.

@@ -535,6 +535,26 @@ extern "C" int tspcuda_nn(tspcuda_ctx *c, int start, int *path_out, double *cost
 }
 
 // ---- multi-start NN + 2-opt (heuristics.c:74-116) --------------------------------------------
+template <class M, int BLK>
+static cudaError_t launch_cta_descents(tspcuda_ctx *c, const int *d_order, int count, int *d_next, long long *d_cost,
+                                       long long *d_moves, int *d_paths) {
+    const size_t smem = cta_smem_bytes(c->n, BLK / 32);
+    cudaError_t e = cudaFuncSetAttribute(descend_cta_kernel<M, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descend_cta_kernel<M, BLK>, BLK, smem);
+    if (e != cudaSuccess) return e;
+    const int grid = std::max(1, std::min(count, std::max(1, per_sm) * c->num_sms));
+    descend_cta_kernel<M, BLK><<<grid, BLK, smem, c->stream>>>(c->d_xy, c->n, d_order, count, d_next, d_cost, d_moves, d_paths);
+    return cudaGetLastError();
+}
+
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
 extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int nstarts, int stride, double *nn_costs_out,
                                           double *final_costs_out, int64_t *moves_out, int *best_start_out,
                                           int *best_path_out, double *best_cost_out) {
@@ -544,48 +564,84 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
     if (nstarts <= 0 || stride <= 0) return fail(TSPCUDA_INVALID_ARGUMENT, "nstarts/stride");
     const long long last = (long long)first_start + (long long)(nstarts - 1) * stride;
     if (first_start < 0 || last >= n) return fail(TSPCUDA_UNAVAILABLE, "starting node not correct");
-    const int batch = std::min(nstarts, 8 * c->num_sms);
+    const bool cta_path = n >= 4 && n <= CTA_MAX_N;       // whole tour fits one CTA's shared memory
+    const int batch = std::min(nstarts, (cta_path ? 16 : 8) * c->num_sms);
     NNScratch S;
     e = nn_alloc(c, S, batch);
     if (e) return e;
-    int *d_best_path = nullptr;
-    CK(cudaMalloc(&d_best_path, sizeof(int) * n));
-    std::vector<long long> hc(batch);
+    DevBuf best_path, next, dcost, dmoves, dpaths;
+    CK(cudaMalloc(&best_path.p, sizeof(int) * n));
+    std::vector<long long> hc(batch), hf(batch), hm(batch);
+    if (cta_path) {
+        CK(cudaMalloc(&next.p, sizeof(int)));
+        CK(cudaMalloc(&dcost.p, sizeof(long long) * batch));
+        CK(cudaMalloc(&dmoves.p, sizeof(long long) * batch));
+        CK(cudaMalloc(&dpaths.p, sizeof(int) * (size_t)n * batch));
+    }
     long long best = -1;
     int best_start = -1;
-    int rc = TSPCUDA_OK;
-    for (int done = 0; done < nstarts && rc == TSPCUDA_OK; done += batch) {
+    for (int done = 0; done < nstarts; done += batch) {
         const int cnt = std::min(batch, nstarts - done);
         const int fs = first_start + done * stride;
-        rc = nn_batch(c, S, fs, cnt, stride, hc.data());
-        for (int k = 0; k < cnt && rc == TSPCUDA_OK; k++) {
+        e = nn_batch(c, S, fs, cnt, stride, hc.data());
+        if (e) return e;
+        if (cta_path) {
+            // K6: every start of the batch descends inside one CTA, no grid barrier per move
+            CK(cudaMemsetAsync(next.p, 0, sizeof(int), c->stream));
+            CK(cudaEventRecord(c->ev0, c->stream));
+            cudaError_t le = cudaSuccess;
+            if (n <= CTA_SMALL_N) { DISPATCH_METRIC(c->metric, (le = launch_cta_descents<M, 512>(c, S.order, cnt, next.as<int>(), dcost.as<long long>(), dmoves.as<long long>(), dpaths.as<int>()))); }
+            else { DISPATCH_METRIC(c->metric, (le = launch_cta_descents<M, 1024>(c, S.order, cnt, next.as<int>(), dcost.as<long long>(), dmoves.as<long long>(), dpaths.as<int>()))); }
+            CK(le);
+            CK(cudaEventRecord(c->ev1, c->stream));
+            c->stats.kernel_launches += 1;
+            CK(cudaMemcpyAsync(hf.data(), dcost.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(hm.data(), dmoves.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->stats.d2h_bytes += (int64_t)sizeof(long long) * 2 * cnt;
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            c->stats.scan_kernel_ms += ms;
+            c->stats.last_kernel_ms = ms;
+            int bi = -1;
+            for (int k = 0; k < cnt; k++) {
+                c->stats.moves += hm[k];
+                c->stats.scans += hm[k] + 1;
+                c->stats.pair_evals += (hm[k] + 1) * ((long long)n * (n - 1) / 2);
+                if (nn_costs_out) nn_costs_out[done + k] = (double)hc[k];
+                if (final_costs_out) final_costs_out[done + k] = (double)hf[k];
+                if (moves_out) moves_out[done + k] = hm[k];
+                if (best_start < 0 || hf[k] < best) { best = hf[k]; best_start = fs + k * stride; bi = k; }   // strict '<', tsp.c:671
+            }
+            if (bi >= 0)
+                CK(cudaMemcpyAsync(best_path.p, dpaths.as<int>() + (size_t)bi * n, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
+            continue;
+        }
+        for (int k = 0; k < cnt; k++) {
             if (nn_costs_out) nn_costs_out[done + k] = (double)hc[k];
             // the NN visit order IS the tour-position order: no host round trip
-            cudaMemcpyAsync(c->d_order, S.order + (size_t)k * n, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream);
-            rc = tour_from_device_order(c);
-            if (rc) break;
+            CK(cudaMemcpyAsync(c->d_order, S.order + (size_t)k * n, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
+            e = tour_from_device_order(c);
+            if (e) return e;
             c->tour_loaded = false;
-            rc = descend(c, -1, 0, -1.0, nullptr);
-            if (rc) break;
+            e = descend(c, -1, 0, -1.0, nullptr);
+            if (e) return e;
             const long long fc = c->h_state->cost;
             if (final_costs_out) final_costs_out[done + k] = (double)fc;
             if (moves_out) moves_out[done + k] = c->h_state->moves;
             if (best_start < 0 || fc < best) {                           // strict '<', tsp.c:671
                 best = fc; best_start = fs + k * stride;
-                tour_export_kernel<<<grid_for(n, 4 * c->num_sms), 256, 0, c->stream>>>(c->tour, d_best_path);
+                tour_export_kernel<<<grid_for(n, 4 * c->num_sms), 256, 0, c->stream>>>(c->tour, best_path.as<int>());
                 c->stats.kernel_launches += 1;
+                CK(cudaGetLastError());
             }
         }
     }
-    if (rc == TSPCUDA_OK && best_path_out && best_start >= 0) {
-        cudaError_t ce = cudaMemcpyAsync(best_path_out, d_best_path, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(c->stream);
-        if (ce != cudaSuccess) rc = fail(TSPCUDA_INTERNAL, "best path copy failed: %s", cudaGetErrorString(ce));
+    if (best_path_out && best_start >= 0) {
+        CK(cudaMemcpyAsync(best_path_out, best_path.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
         c->stats.d2h_bytes += (int64_t)sizeof(int) * n;
     }
-    cudaStreamSynchronize(c->stream);
-    cudaFree(d_best_path);
-    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
     if (best_start_out) *best_start_out = best_start;
     if (best_cost_out) *best_cost_out = (double)best;
     return TSPCUDA_OK;
