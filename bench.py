@@ -15,7 +15,7 @@ reversal) of the 2-opt descent of refinment.c:15-27, continuing the same descent
   e2e    = same steps through the reference-facing call tspcuda_two_opt() with HOST buffers: the
            successor array goes host->device and comes back every step (wall clock, max over ranks).
 Multi-GPU: starts are sharded block-cyclically (rank r takes start r), no data-path collective; one
-NCCL all-reduce(min) of the packed (cost,start) key + one broadcast of the winning tour at the end.
+NCCL all-reduce(min) of the packed (cost,start) key + one all-reduce carrying the winning tour at the end.
 """
 import argparse
 import json
@@ -204,29 +204,37 @@ def main():
     torch.cuda.synchronize()
     clocks = sampler.finish()
     st = I.stats()
-    # best-tour reduction of the multi-start job: one all-reduce(min) + one broadcast (NCCL / NVLink)
+    # best-tour reduction of the multi-start job: all-reduce(min) of the packed (cost,start) key + one
+    # all-reduce carrying the winning tour (NCCL over NVLink).  Job time = slowest rank's device time
+    # for its K steps + the reduction, which is timed after a barrier so that rank skew (already
+    # covered by the max over ranks) is not counted twice.
     path_now, cost_now = I.tour_download()
     red_ms = 0.0
     best_cost, best_start = cost_now, start
+    rank_ms = [ms]
     if world > 1:
         from travellingsalesmanoptimization_b200 import multistart as MS
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         tour = torch.from_numpy(path_now).cuda()
+        barrier()
         e0.record()
         best_cost, best_start, tour = MS.reduce_best(dist, torch.device("cuda", local), cost_now, start, tour)
         e1.record()
         torch.cuda.synchronize()
         red_ms = e0.elapsed_time(e1)
-    total_ms = ms + red_ms
-    if world > 1:
-        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms = float(t.item())
+        t = torch.zeros(world, dtype=torch.float64, device="cuda")
+        t[rank] = ms
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        rank_ms = [float(v) for v in t.tolist()]
+        r = torch.tensor([red_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(r, op=dist.ReduceOp.MAX)
+        red_ms = float(r.item())
         cnt = torch.tensor([st["pair_evals"], st["kernel_launches"], st["scans"]], dtype=torch.int64, device="cuda")
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
         all_pairs, all_launches, all_scans = [int(v) for v in cnt.tolist()]
     else:
         all_pairs, all_launches, all_scans = st["pair_evals"], st["kernel_launches"], st["scans"]
+    total_ms = max(rank_ms) + red_ms
     value = all_pairs / (total_ms * 1e-3)
 
     # ---- roofline of the dominant kernel (descend_kernel), measured live ------------------------
@@ -275,7 +283,7 @@ def main():
         "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "TSPLIB pla85900 coordinates (tests/golden/instances); tours built on device",
         "config": dict(workload_config(args.workload, n, MOVES), parallelism="starts sharded block-cyclically, rank r -> start r",
-                       best_tour_reduction_ms=red_ms, best_cost=int(best_cost), best_start=int(best_start)),
+                       best_tour_reduction_ms=red_ms, rank_ms=[round(v, 3) for v in rank_ms], best_cost=int(best_cost), best_start=int(best_start)),
         "roofline": roofline, "roofline_executed": roofline_executed, "e2e": e2e, "gpu_launches": int(all_launches),
         "clocks": clocks, "scans": int(all_scans),
     }

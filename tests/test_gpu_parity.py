@@ -144,6 +144,28 @@ def test_descent_random_vs_oracle(tsp, oracle, n, integer):
     assert np.array_equal(p2, p_o)
 
 
+@pytest.mark.parametrize("force", ["", "general"])
+@pytest.mark.parametrize("dups", [False, True])
+def test_metric_variants_agree(tsp, oracle, monkeypatch, force, dups):
+    """Both implementations of tsp.c:629 (integer coordinates: FMA + 2^-60 addend, no clamp; general:
+    separate roundings + clamp) must give the same move log as the oracle -- with and without
+    coincident nodes (zero-cost edges)."""
+    n = 700
+    xy = _rand_xy(91, n, True, lo=-300000, hi=900000)
+    if dups:
+        xy[5] = xy[400]; xy[6] = xy[400]; xy[699] = xy[0]
+    if force:
+        monkeypatch.setenv("TSPCUDA_FORCE_METRIC", force)
+    path = _rand_tour(17, n)
+    m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, path)
+    with tsp.Instance(xy) as I:
+        code, moves, p2, c2, log = I.two_opt(path, log_cap=len(la) + 8)
+        assert np.array_equal(I.cost_matrix(), oracle.cost_matrix(xy))
+    assert code == 0 and moves == m_o and c2 == c_o
+    assert log == _log3(la, lb, ld)
+    assert np.array_equal(p2, p_o)
+
+
 def test_descent_lattice_ties(tsp, oracle):
     """Integer lattice: many equal deltas; the lexicographically smallest (a,b) must win each scan."""
     g = np.stack(np.meshgrid(np.arange(20.0), np.arange(15.0)), -1).reshape(-1, 2) * 10.0

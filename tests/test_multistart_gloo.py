@@ -1,5 +1,5 @@
 """CPU, world_size 2, gloo: the N>1 host logic of multi-start work (sharding by start node + the
-packed-key all-reduce(min) + winner broadcast) reproduces the reference's incumbent rule."""
+packed-key all-reduce(min) + winner all-reduce) reproduces the reference's incumbent rule."""
 import json
 import os
 import socket

@@ -60,7 +60,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    path = os.environ.get("TSPCUDA_LIB", LIB)      # development override: an alternative build of the SAME library
+    path = os.environ.get("TSPCUDA_LIB") or LIB      # development override: an alternative build of the SAME library
     if path == LIB and not os.path.exists(LIB):
         build()
     L = C.CDLL(path)

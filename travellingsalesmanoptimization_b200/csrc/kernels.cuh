@@ -33,7 +33,13 @@ constexpr int R = TSP_R;             // tour positions (rows) owned by one lane
 constexpr int SR = 32 * R - 1;       // pair rows per warp strip (last D row is the next strip's first)
 constexpr int UNROLL = TSP_UNROLL;
 constexpr int BLOCK_SMALL = 256;      // descent kernel block size for n < BIG_N (fewer, lighter CTAs: cheaper grid syncs)
-constexpr int BLOCK_BIG = 512;        // and for n >= BIG_N (64 regs/thread, 32 warps/SM: +12% pair rate, profiles/)
+#ifndef TSP_BLOCK_BIG
+#define TSP_BLOCK_BIG 512
+#endif
+#ifndef TSP_MINB_BIG
+#define TSP_MINB_BIG (1024 / TSP_BLOCK_BIG)
+#endif
+constexpr int BLOCK_BIG = TSP_BLOCK_BIG;   // and for n >= BIG_N (64 regs/thread, 32 warps/SM: +12% pair rate, profiles/)
 constexpr int BIG_N = 8192;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -244,7 +250,7 @@ __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int 
 // init_best = BIGPEN/2 : tabu, best admissible move even if worsening (metaheuristic.c:189,225)
 // ---------------------------------------------------------------------------------------------
 template <class M, int BLK>
-__global__ void __launch_bounds__(BLK, 1024 / BLK)
+__global__ void __launch_bounds__(BLK, (BLK == BLOCK_BIG ? TSP_MINB_BIG : 1024 / BLK))
 descend_kernel(TourView V, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
                long long max_moves, int init_best, int dns_is_dn) {
     constexpr int WARPS = BLK / 32;
@@ -589,7 +595,7 @@ __global__ void pipe_rate_kernel(int iters, double seed, double *sink) {
             else if (KIND == 3) { f[k] = __double2float_rn(d[k]); d[k] = (double)f[k]; }
             else if (KIND == 4) { asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(f[k]) : "f"(f[k])); }
             else if (KIND == 5) f[k] = __fmaf_rn(f[k], 1.0000001f, 1e-7f);
-            else if (KIND == 6) { int kk = EucRef<false>::K(d[k], d[(k + 1) & 7], 3.25, 7.5); d[k] = d[k] + (double)(kk & 1) * 1e-12; }
+            else if (KIND == 6) { int kk = EucGeneral::K(d[k], d[(k + 1) & 7], 3.25, 7.5); d[k] = d[k] + (double)(kk & 1) * 1e-12; }
         }
     }
     double acc = 0;

@@ -4,13 +4,14 @@
 //     (double)((int)(sqrtf(pow(dx,2) + pow(dy,2)) + 0.5))
 // which gcc -O3 (no -ffast-math, baseline x86-64 => no FMA) turns into
 //     subsd subsd mulsd mulsd addsd cvtsd2ss sqrtss cvtss2sd addsd(0.5) cvttsd2si cvtsi2sd.
-// EucRef reproduces that value for every input whose cost is below 2^23 (checked at context
-// creation) with 5 FP64 instructions, one F2F.F32.F64, one MUFU.RSQ and 8 FP32 instructions:
+// EucGeneral / EucInt reproduce that value for every input whose cost is below 2^23 (checked at
+// context creation) with 4-5 FP64 instructions, one F2F.F32.F64, one MUFU.RSQ and 6-7 FP32 ones:
 //
 //   * dx, dy, dx*dx, dy*dy, sum: explicit round-to-nearest intrinsics, so nvcc cannot contract
 //     dx*dx + dy*dy into an FMA (with non-integer coordinates such as usa13509's that would
-//     change the double before the float rounding).  With all-integer coordinates below 2^25 every
-//     intermediate is exact, so the INTEGER variant may use one FMA (4 FP64 instructions).
+//     change the double before the float rounding): EucGeneral.  With all-integer coordinates
+//     below 2^25 every intermediate is an exact integer, so EucInt may use FMAs (4 FP64
+//     instructions) and folds the zero guard into them (see there).
 //   * sqrtf: sqrt_rn_pos() is the IEEE round-to-nearest square root for positive normal floats
 //     (MUFU.RSQ seed + one Newton step with an exact FMA residual).  It is checked exhaustively
 //     against sqrt.rn.f32 on the device by tspcuda_selfcheck_sqrt (tests/test_gpu_parity.py).
@@ -31,6 +32,8 @@ constexpr int KOFF = 0x4B000000;        // bit pattern of 8388608.0f (2^23)
 constexpr int BIGPEN = 1 << 27;         // penalty that removes a pair from the argmin
 constexpr int DELTA_BIAS = 1 << 29;     // bias of the delta field in the packed key
 constexpr unsigned long long KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+#define TINY_F 8.673617379884035e-19f        /* 2^-60: keeps rsqrt finite; any f < 0.25 costs 0 */
+#define TINY_D 8.673617379884035e-19
 
 // IEEE-754 round-to-nearest sqrt for f in [2^-60, 2^64] (normal, positive).
 __device__ __forceinline__ float sqrt_rn_pos(float f) {
@@ -43,25 +46,31 @@ __device__ __forceinline__ float sqrt_rn_pos(float f) {
 }
 
 // K-offset cost from the float that the reference hands to sqrtf().
-__device__ __forceinline__ int koff_from_sumsq(float f) {
-    f = fmaxf(f, 8.673617379884035e-19f);      // 2^-60: keeps rsqrt finite; any f < 0.25 costs 0
+__device__ __forceinline__ int koff_from_sumsq(float f) {     // f > 0 (callers clamp or add 2^-60)
     float r = sqrt_rn_pos(f);
     float v = __fadd_rd(r, 0.5f);
     float w = __fadd_rd(v, 8388608.0f);
     return __float_as_int(w);
 }
 
-template <bool INTEGER>
-struct EucRef {
+// tsp.c:629 for arbitrary (non-integer) coordinates: separate roundings, clamp against s == 0.
+struct EucGeneral {
     static __device__ __forceinline__ int K(double xi, double yi, double xj, double yj) {
         double dx = __dsub_rn(xj, xi);
         double dy = __dsub_rn(yj, yi);
-        double s;
-        if (INTEGER) {
-            s = __fma_rn(dx, dx, __dmul_rn(dy, dy));          // exact either way
-        } else {
-            s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
-        }
+        double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
+        return koff_from_sumsq(fmaxf(__double2float_rn(s), TINY_F));
+    }
+};
+
+// All-integer coordinates below 2^25: every intermediate is an exact integer < 2^53, so FMAs are
+// allowed.  The 2^-60 addend only survives when dx == dy == 0 (coincident nodes, cost 0) and keeps
+// rsqrt finite there without a clamp instruction.
+struct EucInt {
+    static __device__ __forceinline__ int K(double xi, double yi, double xj, double yj) {
+        double dx = __dsub_rn(xj, xi);
+        double dy = __dsub_rn(yj, yi);
+        double s = __fma_rn(dx, dx, __fma_rn(dy, dy, TINY_D));
         return koff_from_sumsq(__double2float_rn(s));
     }
 };

@@ -41,8 +41,8 @@ enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3 };
 
 #define DISPATCH_METRIC(mid, EXPR)                                        \
     switch (mid) {                                                        \
-        case M_EUC_GENERAL: { using M = EucRef<false>; EXPR; } break;     \
-        case M_EUC_INTEGER: { using M = EucRef<true>; EXPR; } break;      \
+        case M_EUC_GENERAL: { using M = EucGeneral; EXPR; } break;        \
+        case M_EUC_INTEGER: { using M = EucInt; EXPR; } break;            \
         case M_CEIL: { using M = Ceil2D; EXPR; } break;                   \
         default: { using M = Att; EXPR; } break;                          \
     }
@@ -136,6 +136,11 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
     tspcuda_ctx *c = new tspcuda_ctx();
     c->n = n; c->wt = weight_type; c->device = device;
     c->metric = weight_type == TSPCUDA_EUC_REF ? (integer ? M_EUC_INTEGER : M_EUC_GENERAL) : (weight_type == TSPCUDA_CEIL_2D ? M_CEIL : M_ATT);
+    if (const char *force = getenv("TSPCUDA_FORCE_METRIC")) {     // test hook: a SLOWER exact variant of the same rule
+        if (weight_type == TSPCUDA_EUC_REF) {
+            if (!strcmp(force, "general")) c->metric = M_EUC_GENERAL;
+        }
+    }
 #define CKC(call)                                                                                     \
     do {                                                                                              \
         cudaError_t e_ = (call);                                                                      \

@@ -3,7 +3,7 @@
 The path shards by START NODE: starts are independent units (heuristics.c:42,82 loop over them), so
 rank r of W takes starts r, r+W, r+2W, ... (block-cyclic keeps descent lengths balanced) and there
 is NO data-path collective.  The only exchange is the incumbent: one all-reduce(min) of a packed
-64-bit key and one broadcast of the winning successor array.
+64-bit key and one all-reduce(sum) that carries the winning successor array (zeros elsewhere).
 
 Key = cost << 20 | start.  Costs are integers < 2^42, starts < 2^20 (n <= 131072): the integer order
 of the key is (cost, start) lexicographic, i.e. the reference's strict-'<' incumbent rule evaluated in
@@ -42,6 +42,9 @@ def reduce_best(dist, device, local_cost, local_start, local_path, first_start=0
     dist.all_reduce(key, op=dist.ReduceOp.MIN)
     cost, start = unpack_key(key.item())
     owner = (start - first_start) % world
-    path = local_path.to(device) if dist.get_rank() == owner else torch.empty_like(local_path, device=device)
-    dist.broadcast(path, src=owner)
+    # The winner's successor array travels as a second all-reduce (sum of the winner's array and
+    # zeros from everybody else): same communicator, same ring/NVLS channels as the min-reduce, so no
+    # lazily-built per-root broadcast connections appear inside a timed region.
+    path = local_path.to(device) if dist.get_rank() == owner else torch.zeros_like(local_path, device=device)
+    dist.all_reduce(path, op=dist.ReduceOp.SUM)
     return cost, start, path
