@@ -67,6 +67,10 @@ typedef struct {
     double last_kernel_ms;    /* CUDA-event time of the most recent timed kernel */
     int64_t h2d_bytes;        /* bytes copied host->device by this context */
     int64_t d2h_bytes;        /* bytes copied device->host by this context */
+    int64_t pruned_scans;     /* scans (of `scans`) answered by the exact candidate-pruned kernel; they
+                                 add nothing to pair_evals / scan_kernel_ms */
+    int64_t candidate_evals;  /* candidate nodes examined by those scans */
+    double pruned_kernel_ms;  /* CUDA-event time of the pruned descent kernels, accumulated */
 } tspcuda_stats;
 
 /* ---- library -------------------------------------------------------------------------------- */
@@ -117,6 +121,14 @@ int tspcuda_two_opt_once(tspcuda_ctx *ctx, int *path, double *cost_inout, double
  * pair was tabu.  tabu_list: int[n], -1 = never (metaheuristic.c:68-70). */
 int tspcuda_tabu_move(tspcuda_ctx *ctx, int *path, double *cost_inout, int *tabu_list, int tenure, int iter,
                       tspcuda_move *move_out);
+
+/* How 2-opt descents scan the neighbourhood.  FULL evaluates all n(n-1)/2 pairs per scan, as the
+ * reference does (refinment.c:49-69).  PRUNED evaluates only the pairs that can improve the tour
+ * (found by fixed-radius searches over a grid of the nodes, csrc/pruned.cuh) and provably returns
+ * the same move, ties included.  AUTO (default) measures both and uses the faster one.  The tabu
+ * scan (best admissible move, even worsening) always uses FULL.  Environment: TSPCUDA_SCAN=full|pruned. */
+enum { TSPCUDA_SCAN_AUTO = 0, TSPCUDA_SCAN_FULL = 1, TSPCUDA_SCAN_PRUNED = 2 };
+int tspcuda_set_scan_mode(tspcuda_ctx *ctx, int mode);
 
 /* Device-resident variants (inputs already in HBM; used for kernel-only measurement and by the
  * multi-start drivers): upload once, descend in place, download when wanted. */

@@ -25,6 +25,17 @@ def _rand_tour(seed, n):
     return path
 
 
+SCANS = ["full", "pruned"]
+
+
+def _inst(tsp, xy, scan, wt=EUC_REF):
+    """Instance with the 2-opt scan kernel pinned: 'full' = every pair as the reference (descend_kernel),
+    'pruned' = exact candidate pruning (descend_pruned_kernel), 'auto' = the library's own choice."""
+    I = tsp.Instance(xy, wt)
+    I.set_scan_mode({"auto": tsp.SCAN_AUTO, "full": tsp.SCAN_FULL, "pruned": tsp.SCAN_PRUNED}[scan])
+    return I
+
+
 def _log3(la, lb, ld):
     return [(int(a), int(b), int(d)) for a, b, d in zip(la, lb, ld)]
 
@@ -120,11 +131,12 @@ def test_nn_ties_and_duplicates(tsp, oracle):
 
 # ---- 2-opt ----------------------------------------------------------------------------------
 @pytest.mark.parametrize("name", ["berlin52", "eil51", "kroA100", "pcb442", "pr1002", "u1060", "rl1304", "fl1577", "pr2392"])
-def test_descent_golden(tsp, oracle, golden, name):
+@pytest.mark.parametrize("scan", SCANS)
+def test_descent_golden(tsp, oracle, golden, name, scan):
     xy, _ = load_instance(name)
     g = golden[name]["nn0_2opt"]
     e, p, c = oracle.nn(xy, 0)
-    with tsp.Instance(xy) as I:
+    with _inst(tsp, xy, scan) as I:
         code, moves, p2, c2, log = I.two_opt(p, log_cap=64)
     assert code == 0 and moves == g["moves"] and int(c2) == g["cost"] and fnv1a(p2) == g["hash"]
     assert [list(x) for x in log[:len(g["first_moves"])]] == g["first_moves"]
@@ -132,12 +144,13 @@ def test_descent_golden(tsp, oracle, golden, name):
 
 @pytest.mark.parametrize("n", [4, 5, 6, 9, 31, 126, 127, 128, 129, 130, 131, 254, 255, 256, 257, 383, 509, 777])
 @pytest.mark.parametrize("integer", [True, False])
-def test_descent_random_vs_oracle(tsp, oracle, n, integer):
+@pytest.mark.parametrize("scan", SCANS)
+def test_descent_random_vs_oracle(tsp, oracle, n, integer, scan):
     """Sizes straddle the 127-row strip and 32-column block boundaries of the scan kernel."""
     xy = _rand_xy(n * 2 + integer, n, integer)
     path = _rand_tour(n, n)                     # random tours: long and wrap-around reversals
     m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, path)
-    with tsp.Instance(xy) as I:
+    with _inst(tsp, xy, scan) as I:
         code, moves, p2, c2, log = I.two_opt(path, log_cap=len(la) + 8)
     assert code == 0 and moves == m_o and c2 == c_o
     assert log == _log3(la, lb, ld)
@@ -146,7 +159,8 @@ def test_descent_random_vs_oracle(tsp, oracle, n, integer):
 
 @pytest.mark.parametrize("force", ["", "general"])
 @pytest.mark.parametrize("dups", [False, True])
-def test_metric_variants_agree(tsp, oracle, monkeypatch, force, dups):
+@pytest.mark.parametrize("scan", SCANS)
+def test_metric_variants_agree(tsp, oracle, monkeypatch, force, dups, scan):
     """Both implementations of tsp.c:629 (integer coordinates: FMA + 2^-60 addend, no clamp; general:
     separate roundings + clamp) must give the same move log as the oracle -- with and without
     coincident nodes (zero-cost edges)."""
@@ -158,7 +172,7 @@ def test_metric_variants_agree(tsp, oracle, monkeypatch, force, dups):
         monkeypatch.setenv("TSPCUDA_FORCE_METRIC", force)
     path = _rand_tour(17, n)
     m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, path)
-    with tsp.Instance(xy) as I:
+    with _inst(tsp, xy, scan) as I:
         code, moves, p2, c2, log = I.two_opt(path, log_cap=len(la) + 8)
         assert np.array_equal(I.cost_matrix(), oracle.cost_matrix(xy))
     assert code == 0 and moves == m_o and c2 == c_o
@@ -166,13 +180,14 @@ def test_metric_variants_agree(tsp, oracle, monkeypatch, force, dups):
     assert np.array_equal(p2, p_o)
 
 
-def test_descent_lattice_ties(tsp, oracle):
+@pytest.mark.parametrize("scan", SCANS + ["auto"])
+def test_descent_lattice_ties(tsp, oracle, scan):
     """Integer lattice: many equal deltas; the lexicographically smallest (a,b) must win each scan."""
     g = np.stack(np.meshgrid(np.arange(20.0), np.arange(15.0)), -1).reshape(-1, 2) * 10.0
     for seed in (1, 2):
         path = _rand_tour(seed, g.shape[0])
         m_o, p_o, c_o, la, lb, ld = oracle.two_opt(g, path)
-        with tsp.Instance(g) as I:
+        with _inst(tsp, g, scan) as I:
             code, moves, p2, c2, log = I.two_opt(path, log_cap=len(la) + 8)
         assert log == _log3(la, lb, ld) and np.array_equal(p2, p_o) and c2 == c_o
 
@@ -399,11 +414,12 @@ def test_large_first_moves_golden(tsp, golden, name):
     assert moves == 20 and int(c2) == g2["cost"] and fnv1a(p2) == g2["hash"] and [list(x) for x in log] == g2["first_moves"]
 
 
-def test_usa13509_full_descent(tsp, oracle, golden):
+@pytest.mark.parametrize("scan", SCANS + ["auto"])
+def test_usa13509_full_descent(tsp, oracle, golden, scan):
     """Config 3: NN(0) tour to the 2-opt local optimum with on-the-fly FP64 distances.  The
     reference objects need 2567 s for this: 1983 moves -> 21119812."""
     xy, _ = load_instance("usa13509")
-    with tsp.Instance(xy) as I:
+    with _inst(tsp, xy, scan) as I:
         code, p, c = I.nn(0)
         code, moves, p2, c2, log = I.two_opt(p, log_cap=4096)
     s = golden["usa13509"]["nn0_2opt_survey"]
@@ -417,11 +433,12 @@ def test_usa13509_full_descent(tsp, oracle, golden):
     assert d >= -1e-7                                   # local optimum (refinment.c:27)
 
 
-def test_pla85900_descent_audit(tsp, oracle):
+@pytest.mark.parametrize("scan", SCANS)
+def test_pla85900_descent_audit(tsp, oracle, scan):
     """Config 4 size (n = 85 900, 3.689e9 pairs per scan): the reference cannot run it (int overflow,
     tsp.c:614) so parity is the SURVEY 8c audit against the 64-bit oracle, plus invariants."""
     xy, _ = load_instance("pla85900")
-    with tsp.Instance(xy) as I:
+    with _inst(tsp, xy, scan) as I:
         code, p, c = I.nn(0)
         assert code == 0 and oracle.is_tour(p) and oracle.tour_cost(xy, p) == c
         code, moves, p2, c2, log = I.two_opt(p, max_moves=48, log_cap=48)
@@ -430,3 +447,50 @@ def test_pla85900_descent_audit(tsp, oracle):
     assert c2 == c + sum(ld) and all(d < 0 for d in ld)
     r, pend = oracle.audit_moves(xy, p, la, lb, ld, [0, 47])
     assert r == 0 and np.array_equal(pend, p2)
+
+
+def test_pla85900_pruned_descent_matches_full_scan(tsp, oracle):
+    """The whole pla85900 NN(0) descent through the pruned kernel: same first 64 moves as the full
+    scan, and the end state the full-scan descent reaches (5589 moves -> 148543747, measured with
+    descend_kernel in profiles/r01_bench_first.json); every logged delta is re-derived by the oracle,
+    full CPU scans confirm the argmin at sampled iterations and the final tour is a local optimum."""
+    xy, _ = load_instance("pla85900")
+    with _inst(tsp, xy, "full") as I:
+        code, p, c = I.nn(0)
+        code, m64, pf, cf, log_full = I.two_opt(p, max_moves=64, log_cap=64)
+    with _inst(tsp, xy, "pruned") as I:
+        code, moves, p2, c2, log = I.two_opt(p, log_cap=8192)
+        st = I.stats()
+    assert log[:64] == log_full
+    assert (moves, int(c2)) == (5589, 148543747)
+    assert st["pruned_scans"] == moves + 1 and st["pair_evals"] == 0
+    la = [x[0] for x in log]; lb = [x[1] for x in log]; ld = [float(x[2]) for x in log]
+    r, pend = oracle.audit_moves(xy, p, la, lb, ld, [2500, 5588])
+    assert r == 0 and np.array_equal(pend, p2)
+    d, a, b = oracle.two_opt_scan(xy, p2)
+    assert d >= -1e-7
+
+
+@pytest.mark.parametrize("wt", [CEIL_2D, ATT])
+def test_pruned_scan_other_metrics(tsp, oracle, wt):
+    """Search radius of the pruned scan under the TSPLIB95 metrics (parity unpinned, oracle only)."""
+    xy = _rand_xy(5, 600, True, lo=0, hi=3000)
+    path = _rand_tour(3, 600)
+    m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, path, wt)
+    with _inst(tsp, xy, "pruned", wt) as I:
+        code, moves, p2, c2, log = I.two_opt(path, log_cap=len(la) + 8)
+    assert moves == m_o and c2 == c_o and log == _log3(la, lb, ld) and np.array_equal(p2, p_o)
+
+
+def test_auto_scan_mode_random_tour(tsp, oracle):
+    """AUTO starts on a random tour (every search box is huge: the full scan is faster), probes the
+    pruned kernel and switches as the tour shortens; the result never depends on the choice."""
+    n = 3000
+    xy = _rand_xy(77, n, False)
+    path = _rand_tour(5, n)
+    m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, path)
+    with _inst(tsp, xy, "auto") as I:
+        code, moves, p2, c2, log = I.two_opt(path, log_cap=len(la) + 8)
+        st = I.stats()
+    assert moves == m_o and c2 == c_o and log == _log3(la, lb, ld) and np.array_equal(p2, p_o)
+    assert st["scans"] == moves + 1 and st["pruned_scans"] > 0

@@ -16,6 +16,7 @@ import numpy as np
 from .build import LIB, build
 
 EUC_REF, CEIL_2D, ATT = 0, 1, 2
+SCAN_AUTO, SCAN_FULL, SCAN_PRUNED = 0, 1, 2
 WT_BY_NAME = {"EUC_2D": EUC_REF, "EUC_REF": EUC_REF, "CEIL_2D": CEIL_2D, "ATT": ATT}
 ERROR_NAMES = {0: "T_OK", 1: "CANCELLED", 3: "INVALID_ARGUMENT", 4: "DEADLINE_EXCEEDED", 8: "RESOURCE_EXHAUSTED",
                11: "OUT_OF_RANGE", 12: "UNIMPLEMENTED", 13: "INTERNAL", 14: "UNAVAILABLE"}
@@ -27,7 +28,7 @@ EXPORTS = [
     "tspcuda_cost_matrix_checksum", "tspcuda_nn", "tspcuda_nn_multi", "tspcuda_two_opt", "tspcuda_two_opt_once",
     "tspcuda_tabu_move", "tspcuda_tour_upload", "tspcuda_tour_descend", "tspcuda_tour_download", "tspcuda_tour_movelog",
     "tspcuda_multistart_two_opt", "tspcuda_pipe_rate", "tspcuda_selfcheck_sqrt", "tspcuda_timer_start",
-    "tspcuda_timer_stop", "tspcuda_flush_l2",
+    "tspcuda_timer_stop", "tspcuda_flush_l2", "tspcuda_set_scan_mode",
 ]
 
 
@@ -44,7 +45,8 @@ class Move(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("scans", C.c_int64), ("moves", C.c_int64), ("pair_evals", C.c_int64), ("kernel_launches", C.c_int64),
                 ("scan_kernel_ms", C.c_double), ("last_kernel_ms", C.c_double), ("h2d_bytes", C.c_int64),
-                ("d2h_bytes", C.c_int64)]
+                ("d2h_bytes", C.c_int64), ("pruned_scans", C.c_int64), ("candidate_evals", C.c_int64),
+                ("pruned_kernel_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -90,6 +92,7 @@ def lib():
     L.tspcuda_timer_start.argtypes = [_vp]
     L.tspcuda_timer_stop.argtypes = [_vp, _dp]
     L.tspcuda_flush_l2.argtypes = [_vp]
+    L.tspcuda_set_scan_mode.argtypes = [_vp, C.c_int]
     _lib = L
     return L
 
@@ -147,6 +150,10 @@ class Instance:
 
     def reset_stats(self):
         _chk(lib().tspcuda_reset_stats(self._h))
+
+    def set_scan_mode(self, mode):
+        """SCAN_AUTO / SCAN_FULL (every pair, as the reference) / SCAN_PRUNED (exact candidate pruning)."""
+        _chk(lib().tspcuda_set_scan_mode(self._h, mode))
 
     # -- K1 ----------------------------------------------------------------------------------------
     def cost_matrix(self):

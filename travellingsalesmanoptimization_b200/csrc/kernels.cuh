@@ -58,6 +58,7 @@ struct DescState {
     long long log_count;   // entries written to the move log
     int status;            // 0 running / move cap hit, 1 local optimum (no admissible move)
     int last_a, last_b, last_delta;
+    long long candidates;  // candidate nodes examined by the pruned scan (pruned.cuh)
 };
 
 struct MoveRec { int a, b, delta, reserved; };

@@ -61,6 +61,9 @@ struct EucGeneral {
         double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         return koff_from_sumsq(fmaxf(__double2float_rn(s), TINY_F));
     }
+    // Euclidean radius that contains every w with cost(u,w) < r (pruned.cuh): cost <= r-1 means
+    // sqrtf(f) < r - 0.5 with f, sqrtf within 2^-23 relative of the exact values.
+    static __device__ __forceinline__ double radius(double r) { return r * 1.000001 + 1.0; }
 };
 
 // All-integer coordinates below 2^25: every intermediate is an exact integer < 2^53, so FMAs are
@@ -73,6 +76,7 @@ struct EucInt {
         double s = __fma_rn(dx, dx, __fma_rn(dy, dy, TINY_D));
         return koff_from_sumsq(__double2float_rn(s));
     }
+    static __device__ __forceinline__ double radius(double r) { return r * 1.000001 + 1.0; }
 };
 
 // TSPLIB95 CEIL_2D: ceil(sqrt(dx^2+dy^2)) in double.
@@ -83,6 +87,7 @@ struct Ceil2D {
         double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         return KOFF + (int)ceil(__dsqrt_rn(s));
     }
+    static __device__ __forceinline__ double radius(double r) { return r * 1.000001 + 1.0; }      // ceil(d) < r => d < r
 };
 
 // TSPLIB95 ATT: r = sqrt((dx^2+dy^2)/10); t = nint(r); t < r ? t+1 : t.
@@ -95,6 +100,8 @@ struct Att {
         double t = (double)(long long)__dadd_rn(r, 0.5);
         return KOFF + (int)((t < r) ? t + 1.0 : t);
     }
+    // cost >= sqrt(s/10) - 1  =>  cost < r implies d < (r + 1) * sqrt(10)
+    static __device__ __forceinline__ double radius(double r) { return (r + 1.0) * 3.1622777 + 1.0; }
 };
 
 __device__ __forceinline__ unsigned long long pack_key(int delta, int u, int v) {

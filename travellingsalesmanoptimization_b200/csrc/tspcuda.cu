@@ -14,6 +14,7 @@
 
 #include "../../include/tspcuda.h"
 #include "kernels.cuh"
+#include "pruned.cuh"
 
 using namespace tspcuda;
 
@@ -69,6 +70,17 @@ struct tspcuda_ctx {
     long long dev_moves = 0;         // host mirror of d_state->moves
     cudaEvent_t tev0 = nullptr, tev1 = nullptr;
     void *d_flush = nullptr;
+    // K7 (pruned.cuh): static uniform grid over the node coordinates + the big-box queue
+    SpatialGrid grid{};
+    int *d_cell_start = nullptr, *d_cell_count = nullptr, *d_cnode = nullptr;
+    double2 *d_cxy = nullptr;
+    unsigned long long *d_qctr = nullptr;
+    BigBox *d_boxes = nullptr;
+    int pruned_blocks = 0;           // cooperative grid of descend_pruned_kernel (0: unavailable)
+    int scan_mode = TSPCUDA_SCAN_AUTO;
+    double est_pruned_s = 0, est_full_s = 0;
+    long long chunk_no = 0;
+    long long dev_candidates = 0;    // host mirror of d_state->candidates
 };
 
 extern "C" const char *tspcuda_last_error(void) { return g_err.c_str(); }
@@ -101,6 +113,8 @@ extern "C" void tspcuda_destroy(tspcuda_ctx *c) {
     cudaFree(c->tour.dns); cudaFree(c->tour.pos); cudaFree(c->d_path); cudaFree(c->d_order);
     cudaFree(c->d_tabu); cudaFree(c->d_key); cudaFree(c->d_state); cudaFree(c->d_log);
     cudaFree(c->d_matrix); cudaFree(c->d_sum); cudaFree(c->d_flush);
+    cudaFree(c->d_cell_start); cudaFree(c->d_cell_count); cudaFree(c->d_cnode); cudaFree(c->d_cxy);
+    cudaFree(c->d_qctr); cudaFree(c->d_boxes);
     if (c->tev0) cudaEventDestroy(c->tev0);
     if (c->tev1) cudaEventDestroy(c->tev1);
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -190,7 +204,50 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
     c->stats.h2d_bytes += (int64_t)sizeof(double2) * n;
     const double pairs = 0.5 * (double)n * (double)(n - 1);
     c->est_scan_s = std::max(pairs / 5e11, 8e-6);
+    c->est_full_s = pairs / 1.0e12 + 8e-6;
+    if (const char *sm = getenv("TSPCUDA_SCAN")) {
+        if (!strcmp(sm, "full")) c->scan_mode = TSPCUDA_SCAN_FULL;
+        else if (!strcmp(sm, "pruned")) c->scan_mode = TSPCUDA_SCAN_PRUNED;
+    }
+    {   // K7: uniform grid, about two nodes per cell, built on the device
+        const double w = xmax - xmin, h = ymax - ymin;
+        const double target = std::max(1.0, 0.5 * (double)n);
+        double cell = (w > 0 && h > 0) ? std::sqrt(w * h / target) : std::max(w, h) / target;
+        if (!(cell > 0)) cell = 1.0;
+        cell = std::max(cell, std::max(w, h) / 2048.0);
+        SpatialGrid &G = c->grid;
+        G.gx0 = xmin; G.gy0 = ymin; G.inv_cell = 1.0 / cell;
+        G.W = (int)std::min(2048.0, std::floor(w / cell) + 1.0);
+        G.H = (int)std::min(2048.0, std::floor(h / cell) + 1.0);
+        const int ncells = G.W * G.H;
+        CKC(cudaMalloc(&c->d_cell_start, sizeof(int) * (ncells + 1)));
+        CKC(cudaMalloc(&c->d_cell_count, sizeof(int) * ncells));
+        CKC(cudaMalloc(&c->d_cnode, sizeof(int) * n));
+        CKC(cudaMalloc(&c->d_cxy, sizeof(double2) * n));
+        CKC(cudaMalloc(&c->d_qctr, sizeof(unsigned long long)));
+        CKC(cudaMalloc(&c->d_boxes, sizeof(BigBox) * n));
+        G.cell_start = c->d_cell_start; G.cnode = c->d_cnode; G.cxy = c->d_cxy;
+        CKC(cudaMemsetAsync(c->d_cell_count, 0, sizeof(int) * ncells, c->stream));
+        CKC(cudaMemsetAsync(c->d_qctr, 0, sizeof(unsigned long long), c->stream));
+        const int g = std::max(1, std::min(4 * c->num_sms, (n + 255) / 256));
+        grid_count_kernel<<<g, 256, 0, c->stream>>>(G, c->d_xy, n, c->d_cell_count);
+        grid_scan_kernel<<<1, 1024, 0, c->stream>>>(c->d_cell_count, c->d_cell_start, ncells);
+        grid_fill_kernel<<<g, 256, 0, c->stream>>>(G, c->d_xy, n, c->d_cell_count, c->d_cnode, c->d_cxy);
+        c->stats.kernel_launches += 3;
+        CKC(cudaGetLastError());
+        CKC(cudaStreamSynchronize(c->stream));
+        int pb = 0;
+        DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, PRUNED_BLOCK>, PRUNED_BLOCK, 0)));
+        c->pruned_blocks = pb > 0 ? c->num_sms : 0;      // one CTA per SM: cheapest grid barrier
+    }
     *out = c;
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_set_scan_mode(tspcuda_ctx *c, int mode) {
+    if (!c) return fail(TSPCUDA_INVALID_ARGUMENT, "null context");
+    if (mode < TSPCUDA_SCAN_AUTO || mode > TSPCUDA_SCAN_PRUNED) return fail(TSPCUDA_INVALID_ARGUMENT, "scan mode %d", mode);
+    c->scan_mode = mode;
     return TSPCUDA_OK;
 }
 
@@ -216,6 +273,7 @@ static int tour_from_device_order(tspcuda_ctx *c) {
     const int g = grid_for(n + 1, 4 * c->num_sms);
     CK(cudaMemsetAsync(c->d_state, 0, sizeof(DescState), c->stream));
     c->dev_moves = 0;
+    c->dev_candidates = 0;
     tour_init_kernel<<<g, 256, 0, c->stream>>>(c->tour, c->d_xy, c->d_order);
     DISPATCH_METRIC(c->metric, (tour_edges_kernel<M><<<g, 256, 0, c->stream>>>(c->tour, c->d_state)));
     c->stats.kernel_launches += 2;
@@ -277,6 +335,20 @@ static cudaError_t launch_descend(tspcuda_ctx *c, int grid, long long max_moves,
     return cudaLaunchCooperativeKernel((void *)descend_kernel<M, BLOCK_SMALL>, dim3(grid), dim3(BLOCK_SMALL), args, 0, c->stream);
 }
 
+template <class M>
+static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max_moves) {
+    TourView V = c->tour;
+    V.dns = V.dn;
+    SpatialGrid G = c->grid;
+    unsigned long long *key = c->d_key, *qctr = c->d_qctr;
+    DescState *st = c->d_state;
+    MoveRec *log = c->d_log;
+    long long log_cap = c->log_cap;
+    BigBox *boxes = c->d_boxes;
+    void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &qctr, &boxes};
+    return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
+}
+
 // Run up to max_moves scan+move iterations on the device-resident tour (max_moves < 0: until no
 // admissible move is left).  mode 0 = 2-opt (improving moves only), 1 = tabu (best admissible).
 // The loop lives on the device; the host only re-launches in chunks of ~0.1 s so that the
@@ -297,15 +369,30 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
     const int init_best = mode == 0 ? -1 : BIGPEN / 2;
     const int zero = 0;
     CK(cudaMemcpyAsync(&c->d_state->status, &zero, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    // 2-opt descents may use the exact pruned scan (K7).  It returns the same move as the full scan,
+    // so the choice is only about speed: AUTO probes it with a short chunk and keeps whichever
+    // kernel has the lower measured time per scan, re-probing every 8th chunk.
+    const bool can_prune = mode == 0 && c->pruned_blocks > 0 && c->scan_mode != TSPCUDA_SCAN_FULL;
+    const int pgrid = std::max(1, std::min(c->pruned_blocks, (n + PRUNED_BLOCK - 1) / PRUNED_BLOCK));
     for (;;) {
         const long long done = c->dev_moves - base;
         if (max_moves >= 0 && done >= max_moves) break;
-        long long chunk = (long long)std::max(4.0, std::min(8192.0, 0.1 / c->est_scan_s));
+        bool pruned = false, probe = false;
+        if (can_prune) {
+            if (c->scan_mode == TSPCUDA_SCAN_PRUNED) pruned = true;
+            else if (c->est_pruned_s <= 0 || (c->chunk_no & 7) == 7) pruned = probe = true;
+            else pruned = c->est_pruned_s <= c->est_full_s;
+        }
+        c->chunk_no++;
+        const double est = pruned ? std::max(c->est_pruned_s, 2e-6) : c->est_scan_s;
+        long long chunk = (long long)std::max(4.0, std::min(8192.0, 0.1 / est));
+        if (probe) chunk = 4;
         if (max_moves >= 0) chunk = std::min(chunk, max_moves - done);
         CK(cudaMemsetAsync(c->d_key, 0xFF, sizeof(unsigned long long) * 2, c->stream));
         CK(cudaEventRecord(c->ev0, c->stream));
         cudaError_t le = cudaSuccess;
-        DISPATCH_METRIC(c->metric, le = launch_descend<M>(c, grid, chunk, init_best, mode == 0 ? 1 : 0));
+        if (pruned) { DISPATCH_METRIC(c->metric, le = launch_descend_pruned<M>(c, pgrid, chunk)); }
+        else { DISPATCH_METRIC(c->metric, le = launch_descend<M>(c, grid, chunk, init_best, mode == 0 ? 1 : 0)); }
         CK(le);
         CK(cudaEventRecord(c->ev1, c->stream));
         c->stats.kernel_launches += 1;
@@ -318,10 +405,21 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
         const long long scans = applied + (c->h_state->status == 1 ? 1 : 0);
         c->stats.moves += applied;
         c->stats.scans += scans;
-        c->stats.pair_evals += scans * ((long long)n * (n - 1) / 2);
-        c->stats.scan_kernel_ms += ms;
+        if (pruned) {
+            c->stats.pruned_scans += scans;
+            c->stats.candidate_evals += c->h_state->candidates - c->dev_candidates;
+            c->stats.pruned_kernel_ms += ms;
+            if (scans > 0) c->est_pruned_s = std::max(1e-6, 1e-3 * ms / (double)scans);
+        } else {
+            c->stats.pair_evals += scans * ((long long)n * (n - 1) / 2);
+            c->stats.scan_kernel_ms += ms;
+            if (scans > 0) {
+                c->est_scan_s = std::max(1e-6, 1e-3 * ms / (double)scans);
+                if (mode == 0) c->est_full_s = c->est_scan_s;
+            }
+        }
+        c->dev_candidates = c->h_state->candidates;
         c->stats.last_kernel_ms = ms;
-        if (scans > 0) c->est_scan_s = std::max(1e-6, 1e-3 * ms / (double)scans);
         if (c->h_state->status == 1) break;
         if (time_limit_s >= 0) {
             const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
