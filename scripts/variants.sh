@@ -1,9 +1,6 @@
 #!/bin/bash
-# Times every build variant under build/variants (scripts/build_variants.sh) on the GPU box,
-# with the metric the library picks (norm-expanded integer scan) and with the dx/dy integer scan forced.
-for f in "" build/variants/*.so; do
-  for m in "" int; do
-    echo -n "metric=${m:-auto} "
-    TSPCUDA_FORCE_METRIC=$m TSPCUDA_LIB=${f:+$PWD/$f} timeout 180 python scripts/variant_time.py 2>&1 | tail -1
-  done
+# Runs $1 (a python script + args) under every build variant in build/variants.
+for f in build/variants/*.so; do
+  echo "== $f"
+  TSPCUDA_LIB=$PWD/$f timeout 300 python "$@" 2>&1 | grep -v "auto \|full  "
 done

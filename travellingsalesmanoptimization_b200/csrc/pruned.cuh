@@ -36,9 +36,23 @@ struct BigBox {
     long long base;             // first unit (row) index of this box in the flattened unit space
 };
 
-constexpr int PRUNED_BLOCK = 512;
+#ifndef TSP_PRUNED_BLOCK
+#define TSP_PRUNED_BLOCK 512
+#endif
+#ifndef TSP_PR_SMALL_NODES
+#define TSP_PR_SMALL_NODES 32
+#endif
+constexpr int PRUNED_BLOCK = TSP_PRUNED_BLOCK;
+#ifndef TSP_PR_NC
+#define TSP_PR_NC 4
+#endif
+constexpr int PR_NC = TSP_PR_NC;            // candidates evaluated together (latency overlap), phase 1
+#ifndef TSP_PR_NC2
+#define TSP_PR_NC2 2
+#endif
+constexpr int PR_NC2 = TSP_PR_NC2;          // the same per lane in phase 2
 constexpr int PR_SMALL_ROWS = 12;
-constexpr int PR_SMALL_NODES = 160;
+constexpr int PR_SMALL_NODES = TSP_PR_SMALL_NODES;
 constexpr unsigned long long PR_UNIT_MASK = (1ull << 40) - 1;
 
 // ---- grid construction ------------------------------------------------------------------------
@@ -110,35 +124,61 @@ __device__ __forceinline__ void probe_load(const TourView &V, int p, Probe &P) {
 // two positions from registers instead of racing with that write.
 struct PosPatch { int node0, pos0, node1, pos1; };
 
-template <class M>
-__device__ __forceinline__ void cand_eval(const TourView &V, const Probe &P, const PosPatch &F, int w, double wx, double wy,
-                                          int &best, unsigned long long &bestkey) {
+// Evaluates up to NC candidates w[j] (coordinates wx/wy, valid[j]) of the search around P in
+// STAGES -- all edge costs, then all pos[] gathers, then all coordinate / edge-cost gathers, then
+// the deltas -- so that the dependent L2 round trips (cost -> pos -> pxy/dn) of the candidates
+// overlap instead of queueing behind one another.  Gathers of rejected candidates are redirected
+// to index 0 rather than branched around: the loads stay unconditional and issue back to back.
+template <class M, int NC>
+__device__ __forceinline__ void cand_eval_n(const TourView &V, const Probe &P, const PosPatch &F, const int (&w)[NC],
+                                            const double (&wx)[NC], const double (&wy)[NC], const bool (&valid)[NC],
+                                            int &best, unsigned long long &bestkey) {
     const int n = V.n;
-    const int K = M::K(P.ux, P.uy, wx, wy);
-    const bool c1 = K < P.dnp, c2 = K < P.dnm;
-    if (!(c1 | c2)) return;
-    const int q = (w == F.node0) ? F.pos0 : (w == F.node1) ? F.pos1 : V.pos[w];
-    const int diff = abs(P.p - q);
-    if (diff <= 1 || diff == n - 1) return;       // same node / tour neighbours: refinment.c:55
-    if (c1) {                                      // pair {p, q}: edges (p,p+1), (q,q+1) out, (p,q), (p+1,q+1) in
-        const double2 ws = V.pxy[q + 1];
-        const int K2 = M::K(P.sx, P.sy, ws.x, ws.y);
-        const int d = (int)((unsigned)K + (unsigned)K2 - (unsigned)P.dnp - (unsigned)V.dn[q]);
-        if (d <= best) {
-            best = d;
-            const unsigned long long key = pack_key(d, P.ida, w);
-            if (key < bestkey) bestkey = key;
-        }
+    int K[NC], q[NC];
+    bool c1[NC], c2[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        K[j] = M::K(P.ux, P.uy, wx[j], wy[j]);
+        c1[j] = valid[j] && K[j] < P.dnp;
+        c2[j] = valid[j] && K[j] < P.dnm;
     }
-    if (c2) {                                      // pair {p-1, q-1}: (p,q) is its second new edge
-        const int qm = q == 0 ? n - 1 : q - 1;
-        const double2 wp = V.pxy[qm];
-        const int K2 = M::K(P.px, P.py, wp.x, wp.y);
-        const int d = (int)((unsigned)K2 + (unsigned)K - (unsigned)P.dnm - (unsigned)V.dn[qm]);
-        if (d <= best) {
-            best = d;
-            const unsigned long long key = pack_key(d, P.idm, V.tid[qm]);
-            if (key < bestkey) bestkey = key;
+#pragma unroll
+    for (int j = 0; j < NC; ++j) q[j] = V.pos[(c1[j] | c2[j]) ? w[j] : P.ida];
+    double2 ws[NC], wp[NC];
+    int dq[NC], dqm[NC], qm[NC];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        if (w[j] == F.node0) q[j] = F.pos0;
+        if (w[j] == F.node1) q[j] = F.pos1;
+        const int diff = abs(P.p - q[j]);
+        const bool ok = diff > 1 && diff != n - 1;           // same node / tour neighbours: refinment.c:55
+        c1[j] = c1[j] && ok;
+        c2[j] = c2[j] && ok;
+        qm[j] = q[j] == 0 ? n - 1 : q[j] - 1;
+        ws[j] = V.pxy[c1[j] ? q[j] + 1 : 0];
+        dq[j] = V.dn[c1[j] ? q[j] : 0];
+        wp[j] = V.pxy[c2[j] ? qm[j] : 0];
+        dqm[j] = V.dn[c2[j] ? qm[j] : 0];
+    }
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+        if (c1[j]) {                                   // pair {p, q}: edges (p,p+1), (q,q+1) out, (p,q), (p+1,q+1) in
+            const int K2 = M::K(P.sx, P.sy, ws[j].x, ws[j].y);
+            const int d = (int)((unsigned)K[j] + (unsigned)K2 - (unsigned)P.dnp - (unsigned)dq[j]);
+            if (d <= best) {
+                best = d;
+                const unsigned long long key = pack_key(d, P.ida, w[j]);
+                if (key < bestkey) bestkey = key;
+            }
+        }
+        if (c2[j]) {                                   // pair {p-1, q-1}: (p,q) is its second new edge
+            const int K2 = M::K(P.px, P.py, wp[j].x, wp[j].y);
+            const int d = (int)((unsigned)K2 + (unsigned)K[j] - (unsigned)P.dnm - (unsigned)dqm[j]);
+            if (d <= best) {
+                best = d;
+                const unsigned long long key = pack_key(d, P.idm, V.tid[qm[j]]);
+                if (key < bestkey) bestkey = key;
+            }
         }
     }
 }
@@ -162,6 +202,7 @@ __global__ void __launch_bounds__(BLK, 1)
 descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
                       long long max_moves, unsigned long long *qctr, BigBox *boxes) {
     constexpr int WARPS = BLK / 32;
+    constexpr int NC1 = BLK > 512 ? 2 : PR_NC;      // 1024-thread CTAs have 64 registers per thread
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned long long s_key;
     const int n = V.n;
@@ -171,6 +212,19 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
     const long long gw = (long long)blockIdx.x * WARPS + warp;
     const long long Wtot = (long long)gridDim.x * WARPS;
     PosPatch F = {-1, 0, -1, 0};
+#ifdef TSP_PHASE_TIMING
+    unsigned long long tprev = 0;
+    if (gtid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tprev));
+#define PHASE_MARK(slot)                                                       \
+    if (gtid == 0) {                                                           \
+        unsigned long long tn_;                                                \
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn_));                 \
+        st->phase_ns[slot] += (long long)(tn_ - tprev);                        \
+        tprev = tn_;                                                           \
+    }
+#else
+#define PHASE_MARK(slot)
+#endif
 
     for (long long it = 0; it < max_moves; ++it) {
         if (threadIdx.x == 0) s_key = KEY_EMPTY;
@@ -180,50 +234,106 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         long long ncand = 0;
 
         // ---- phase 1: one thread per position, small boxes inline, large boxes queued ----------
-        for (int p = gtid; p < n; p += gsize) {
+        for (int p0 = gtid - lane; p0 < n; p0 += gsize) {          // warp-uniform trip count
+            const int p = p0 + lane;
             Probe P;
-            probe_load(V, p, P);
-            int cx0, cx1, cy0, cy1;
-            if (!probe_box<M>(G, P, cx0, cx1, cy0, cy1)) continue;
-            const int nrows = cy1 - cy0 + 1;
-            int total = PR_SMALL_NODES + 1;
-            if (nrows <= PR_SMALL_ROWS) {
-                total = 0;
-                for (int cy = cy0; cy <= cy1; ++cy)
-                    total += G.cell_start[cy * G.W + cx1 + 1] - G.cell_start[cy * G.W + cx0];
+            int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = -1;
+            bool has = false;
+            if (p < n) {
+                probe_load(V, p, P);
+                has = probe_box<M>(G, P, cx0, cx1, cy0, cy1);
             }
-            if (total > PR_SMALL_NODES) {
-                const unsigned long long old = atomicAdd(qctr, (1ull << 40) | (unsigned long long)nrows);
-                BigBox b;
-                b.p = p; b.cy0 = cy0; b.cx0 = cx0; b.cx1 = cx1; b.nrows = nrows; b.pad = 0;
-                b.base = (long long)(old & PR_UNIT_MASK);
-                boxes[old >> 40] = b;
-                continue;
+            const int nrows = has ? cy1 - cy0 + 1 : 0;
+            int total = 0;
+            if (has) {
+                if (nrows <= PR_SMALL_ROWS) {
+#pragma unroll
+                    for (int r = 0; r < PR_SMALL_ROWS; ++r) {      // unrolled: all row bounds in flight at once
+                        const int cy = min(cy0 + r, cy1);
+                        const int cnt = G.cell_start[cy * G.W + cx1 + 1] - G.cell_start[cy * G.W + cx0];
+                        total += (cy0 + r <= cy1) ? cnt : 0;
+                    }
+                } else {
+                    total = PR_SMALL_NODES + 1;
+                }
             }
-            ncand += total;
-            for (int cy = cy0; cy <= cy1; ++cy) {
-                const int lo = G.cell_start[cy * G.W + cx0], hi = G.cell_start[cy * G.W + cx1 + 1];
-                for (int k = lo; k < hi; ++k) {
-                    const double2 wxy = G.cxy[k];
-                    cand_eval<M>(V, P, F, G.cnode[k], wxy.x, wxy.y, best, bestkey);
+            const bool big = total > PR_SMALL_NODES;
+            const unsigned bigmask = __ballot_sync(FULL, big);
+            if (bigmask) {                                         // one queue atomic per warp
+                const int myrows = big ? nrows : 0;
+                int incl = myrows;
+#pragma unroll
+                for (int off = 1; off < 32; off <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, off);
+                    if (lane >= off) incl += v;
+                }
+                const int totrows = __shfl_sync(FULL, incl, 31);
+                unsigned long long old = 0;
+                if (lane == 0)
+                    old = atomicAdd(qctr, ((unsigned long long)__popc(bigmask) << 40) | (unsigned long long)totrows);
+                old = __shfl_sync(FULL, old, 0);
+                if (big) {
+                    BigBox bx;
+                    bx.p = p; bx.cy0 = cy0; bx.cx0 = cx0; bx.cx1 = cx1; bx.nrows = nrows; bx.pad = 0;
+                    bx.base = (long long)(old & PR_UNIT_MASK) + (incl - myrows);
+                    boxes[(old >> 40) + __popc(bigmask & ((1u << lane) - 1))] = bx;
+                }
+            }
+            if (has && !big) {
+                ncand += total;
+                // the box's candidates as ONE stream across its cell rows (row bounds are L1 hits by now),
+                // NC1 at a time through the staged evaluation
+                int cy = cy0, k = 0, hi = 0, last = 0;
+                for (int done = 0; done < total; done += NC1) {
+                    int w[NC1]; double wx[NC1], wy[NC1]; bool valid[NC1];
+                    int kk[NC1];
+#pragma unroll
+                    for (int j = 0; j < NC1; ++j) {
+                        valid[j] = done + j < total;
+                        if (valid[j]) {
+                            while (k >= hi) {
+                                k = G.cell_start[cy * G.W + cx0];
+                                hi = G.cell_start[cy * G.W + cx1 + 1];
+                                ++cy;
+                            }
+                            last = k++;
+                        }
+                        kk[j] = last;
+                    }
+#pragma unroll
+                    for (int j = 0; j < NC1; ++j) {
+                        const double2 c = G.cxy[kk[j]];
+                        w[j] = G.cnode[kk[j]]; wx[j] = c.x; wy[j] = c.y;
+                    }
+                    cand_eval_n<M, NC1>(V, P, F, w, wx, wy, valid, best, bestkey);
                 }
             }
         }
         grid.sync();
+        PHASE_MARK(0)
 
         // ---- phase 2: queued boxes, (box,row) units split evenly over the warps of the grid ----
         {
             const unsigned long long q = *(volatile unsigned long long *)qctr;
             const long long nunits = (long long)(q & PR_UNIT_MASK);
             const int nboxes = (int)(q >> 40);
+#ifdef TSP_PHASE_TIMING
+            if (gtid == 0) { st->phase_ns[4] += nunits; st->phase_ns[5] += nboxes; }
+#endif
             if (nunits > 0) {
                 const long long per = (nunits + Wtot - 1) / Wtot;
                 const long long g0 = gw * per, g1 = min(nunits, g0 + per);
                 if (g0 < g1) {
-                    int lo_b = 0, hi_b = nboxes - 1;            // last box with base <= g0
-                    while (lo_b < hi_b) {
-                        const int mid = (lo_b + hi_b + 1) >> 1;
-                        if (boxes[mid].base <= g0) lo_b = mid; else hi_b = mid - 1;
+                    // last box with base <= g0: 33-ary search, one probe per lane and step
+                    int lo_b = 0, hi_b = nboxes;
+                    while (hi_b - lo_b > 1) {
+                        const int step = (hi_b - lo_b + 32) / 33;
+                        const int idx = lo_b + (lane + 1) * step;
+                        const bool ok = idx < hi_b && boxes[idx].base <= g0;
+                        const int cnt = __popc(__ballot_sync(FULL, ok));     // bases ascend: the ok lanes are a prefix
+                        const int nlo = lo_b + cnt * step;
+                        hi_b = min(hi_b, lo_b + (cnt + 1) * step);
+                        lo_b = nlo;
                     }
                     int bi = lo_b;
                     BigBox b = boxes[bi];
@@ -234,9 +344,16 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
                         const int cy = b.cy0 + (int)(g - b.base);
                         const int lo = G.cell_start[cy * G.W + b.cx0], hi = G.cell_start[cy * G.W + b.cx1 + 1];
                         if (lane == 0) ncand += hi - lo;
-                        for (int k = lo + lane; k < hi; k += 32) {
-                            const double2 wxy = G.cxy[k];
-                            cand_eval<M>(V, P, F, G.cnode[k], wxy.x, wxy.y, best, bestkey);
+                        for (int k = lo + lane; k < hi; k += 32 * PR_NC2) {
+                            int w[PR_NC2]; double wx[PR_NC2], wy[PR_NC2]; bool valid[PR_NC2];
+#pragma unroll
+                            for (int j = 0; j < PR_NC2; ++j) {
+                                valid[j] = k + 32 * j < hi;
+                                const int kk = min(k + 32 * j, hi - 1);
+                                const double2 c = G.cxy[kk];
+                                w[j] = G.cnode[kk]; wx[j] = c.x; wy[j] = c.y;
+                            }
+                            cand_eval_n<M, PR_NC2>(V, P, F, w, wx, wy, valid, best, bestkey);
                         }
                     }
                 }
@@ -252,6 +369,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         unsigned long long *kslot = key + (it & 1);
         if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(kslot, s_key);
         grid.sync();
+        PHASE_MARK(1)
         const unsigned long long kbest = *(volatile unsigned long long *)kslot;
         if (kbest == KEY_EMPTY) {
             if (gtid == 0) { st->status = 1; *qctr = 0; }
@@ -271,6 +389,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
             st->last_a = a; st->last_b = b; st->last_delta = delta;
         }
         grid.sync();
+        PHASE_MARK(2)
         F.node0 = b; F.pos0 = seg_s; F.node1 = V.tid[seg_e]; F.pos1 = seg_e;
         if (gtid == 0) { V.pos[F.node0] = F.pos0; V.pos[F.node1] = F.pos1; }   // deferred end-node positions
     }

@@ -77,9 +77,11 @@ struct tspcuda_ctx {
     unsigned long long *d_qctr = nullptr;
     BigBox *d_boxes = nullptr;
     int pruned_blocks = 0;           // cooperative grid of descend_pruned_kernel (0: unavailable)
+    int pruned_block = 0;            // its CTA size
     int scan_mode = TSPCUDA_SCAN_AUTO;
     double est_pruned_s = 0, est_full_s = 0;
     long long chunk_no = 0;
+    bool probe_due = false;
     long long dev_candidates = 0;    // host mirror of d_state->candidates
 };
 
@@ -236,9 +238,13 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         c->stats.kernel_launches += 3;
         CKC(cudaGetLastError());
         CKC(cudaStreamSynchronize(c->stream));
+        // one CTA per SM (cheapest grid barrier); 1024-thread CTAs when 512 per SM would leave some
+        // threads with two tour positions in phase 1
+        c->pruned_block = (long long)c->num_sms * PRUNED_BLOCK >= n ? PRUNED_BLOCK : 1024;
         int pb = 0;
-        DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, PRUNED_BLOCK>, PRUNED_BLOCK, 0)));
-        c->pruned_blocks = pb > 0 ? c->num_sms : 0;      // one CTA per SM: cheapest grid barrier
+        if (c->pruned_block == PRUNED_BLOCK) { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, PRUNED_BLOCK>, PRUNED_BLOCK, 0))); }
+        else { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, 1024>, 1024, 0))); }
+        c->pruned_blocks = pb > 0 ? c->num_sms : 0;
     }
     *out = c;
     return TSPCUDA_OK;
@@ -346,6 +352,8 @@ static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max
     long long log_cap = c->log_cap;
     BigBox *boxes = c->d_boxes;
     void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &qctr, &boxes};
+    if (c->pruned_block == 1024)
+        return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, 1024>, dim3(grid), dim3(1024), args, 0, c->stream);
     return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
 }
 
@@ -373,20 +381,24 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
     // so the choice is only about speed: AUTO probes it with a short chunk and keeps whichever
     // kernel has the lower measured time per scan, re-probing every 8th chunk.
     const bool can_prune = mode == 0 && c->pruned_blocks > 0 && c->scan_mode != TSPCUDA_SCAN_FULL;
-    const int pgrid = std::max(1, std::min(c->pruned_blocks, (n + PRUNED_BLOCK - 1) / PRUNED_BLOCK));
+    const int pgrid = c->pruned_blocks;          // every SM: phase 2 splits the queued boxes over all warps
     for (;;) {
         const long long done = c->dev_moves - base;
         if (max_moves >= 0 && done >= max_moves) break;
         bool pruned = false, probe = false;
+        const long long remaining = max_moves >= 0 ? max_moves - done : (1LL << 60);
         if (can_prune) {
             if (c->scan_mode == TSPCUDA_SCAN_PRUNED) pruned = true;
-            else if (c->est_pruned_s <= 0 || (c->chunk_no & 7) == 7) pruned = probe = true;
-            else pruned = c->est_pruned_s <= c->est_full_s;
+            else if (c->est_pruned_s <= 0) pruned = probe = true;                       // never measured
+            else if (c->est_pruned_s <= c->est_full_s) pruned = true;
+            else if (remaining >= 64 ? c->probe_due : (c->chunk_no & 7) == 7) pruned = probe = true;
         }
         c->chunk_no++;
         const double est = pruned ? std::max(c->est_pruned_s, 2e-6) : c->est_scan_s;
         long long chunk = (long long)std::max(4.0, std::min(8192.0, 0.1 / est));
         if (probe) chunk = 4;
+        else if (can_prune && !pruned) chunk = std::min<long long>(chunk, 96);         // full scans in AUTO: re-probe soon
+        c->probe_due = can_prune && !pruned;                                         // after a full chunk, probe again
         if (max_moves >= 0) chunk = std::min(chunk, max_moves - done);
         CK(cudaMemsetAsync(c->d_key, 0xFF, sizeof(unsigned long long) * 2, c->stream));
         CK(cudaEventRecord(c->ev0, c->stream));
@@ -420,6 +432,13 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
         }
         c->dev_candidates = c->h_state->candidates;
         c->stats.last_kernel_ms = ms;
+#ifdef TSP_PHASE_TIMING
+        if (pruned && c->h_state->status == 1)
+            fprintf(stderr, "[tspcuda] pruned phases: scan1 %.1f ms  scan2 %.1f ms  apply %.1f ms | units/scan %.0f boxes/scan %.0f\n",
+                    c->h_state->phase_ns[0] * 1e-6, c->h_state->phase_ns[1] * 1e-6, c->h_state->phase_ns[2] * 1e-6,
+                    (double)c->h_state->phase_ns[4] / std::max<long long>(1, c->h_state->moves + 1),
+                    (double)c->h_state->phase_ns[5] / std::max<long long>(1, c->h_state->moves + 1));
+#endif
         if (c->h_state->status == 1) break;
         if (time_limit_s >= 0) {
             const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
