@@ -16,6 +16,7 @@
  *   tspcuda_two_opt_once          ref_2opt_once                algorithms/refinment.c:39-93
  *                                 (+ ref_reverse_path          algorithms/refinment.c:95-114)
  *   tspcuda_tabu_move             tabu_best_move               algorithms/metaheuristic.c:188-245
+ *   tspcuda_tabu_search           mh_TabuSearch inner loop     algorithms/metaheuristic.c:128-164
  *   tspcuda_multistart_two_opt    h_greedy_2opt loop           algorithms/heuristics.c:74-116
  *
  * Tours cross the boundary exactly as the reference stores them: a successor array int path[n],
@@ -121,6 +122,19 @@ int tspcuda_two_opt_once(tspcuda_ctx *ctx, int *path, double *cost_inout, double
  * pair was tabu.  tabu_list: int[n], -1 = never (metaheuristic.c:68-70). */
 int tspcuda_tabu_move(tspcuda_ctx *ctx, int *path, double *cost_inout, int *tabu_list, int tenure, int iter,
                       tspcuda_move *move_out);
+
+/* n_iters iterations of the tabu loop of mh_TabuSearch (metaheuristic.c:128-164) in one device-resident
+ * run: iteration k uses tenure tenures[k] (computed ahead by the caller with the reference's own
+ * policy functions, metaheuristic.c:7-59, which do not depend on the search state) and iteration
+ * number first_iter + k, exactly as n_iters calls of tspcuda_tabu_move would.  path / *cost_inout /
+ * tabu_list are updated in place; cost_trace_out[k] = tour cost after iteration k (the
+ * results/TabuResults.dat column).  The incumbent rule of tsp_update_best_solution (strict '<',
+ * tsp.c:671) is applied on the device against incumbent_cost: if some iteration improves on it,
+ * *best_iter_out is the last such iteration (-1 otherwise) and best_path_out / *best_cost_out hold
+ * that tour.  Any output pointer except path, cost_inout and tabu_list may be NULL. */
+int tspcuda_tabu_search(tspcuda_ctx *ctx, int *path, double *cost_inout, int *tabu_list, const int *tenures,
+                        int first_iter, int n_iters, double incumbent_cost, double *cost_trace_out,
+                        int *best_path_out, double *best_cost_out, int *best_iter_out);
 
 /* How 2-opt descents scan the neighbourhood.  FULL evaluates all n(n-1)/2 pairs per scan, as the
  * reference does (refinment.c:49-69).  PRUNED evaluates only the pairs that can improve the tour

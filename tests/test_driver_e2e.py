@@ -79,7 +79,16 @@ def test_berlin52_cli_golden(workdir, alg, extra, cost):
     if alg == "GREEDY":
         assert c["h_greedyutil"] == 1
     if alg == "TABU_SEARCH":
-        assert c["tabu_best_move"] == 200 and c["h_greedy_2opt"] == 1
+        assert c["mh_TabuSearch"] == 1 and c["tabu_best_move"] == 0 and c["h_greedy_2opt"] == 1
+        with open(os.path.join(workdir, "results", "TabuResults.dat")) as f:
+            lines = f.read().split()
+        assert len(lines) == 200 and lines[0].startswith("0,") and min(float(x.split(",")[1]) for x in lines) == 7542.0
+        # the reference's own loop over the interposed tabu_best_move: same result, same results file
+        r0 = run_cli(TSP_GPU, workdir, ["-f", "berlin52.tsp", "-q", "-alg", alg] + extra, {"TSPCUDA_BATCH": "0"})
+        c0 = calls(r0.stderr)
+        assert r0.stdout == r.stdout and c0["tabu_best_move"] == 200 and c0["mh_TabuSearch"] == 0
+        with open(os.path.join(workdir, "results", "TabuResults.dat")) as f:
+            assert f.read().split() == lines
     if alg == "VNS":
         assert c["ref_2opt"] == 50 and c["h_Greedy_iterative"] == 1
 

@@ -301,6 +301,63 @@ def test_tabu_vs_oracle_random(tsp, oracle):
         assert mv[0] == -1 and cg2 == cg and np.array_equal(pg, before) and np.all(tl == 0)
 
 
+@pytest.mark.parametrize("name", ["berlin52", "kroA100", "pcb442"])
+def test_tabu_search_device_loop_golden(tsp, oracle, golden, name):
+    """tspcuda_tabu_search (the k-loop of mh_TabuSearch in one device-resident run) against the step
+    log generated from the unmodified reference objects: cost after every iteration, final tour,
+    final tabu list; best tour = the first iteration reaching the minimum cost (tsp.c:671)."""
+    xy, _ = load_instance(name)
+    n = xy.shape[0]
+    g = golden[name]["tabu_steps"]
+    e, p, c = oracle.nn(xy, 0)
+    tenure, lo, hi = oracle.tabu_init(n)
+    inc, tenures = True, []
+    for _ in g["log"]:
+        tenure, inc = oracle.tabu_linear_step(tenure, lo, hi, inc)
+        tenures.append(tenure)
+    assert tenures == [t for t, _, _ in g["log"]]
+    with tsp.Instance(xy) as I:
+        code, moves, p, c, _ = I.two_opt(p)
+        p_step, tl_step, c_step = p.copy(), np.full(n, -1, dtype=np.int32), c
+        tl = np.full(n, -1, dtype=np.int32)
+        cost, trace, best_iter, best_path, best_cost = I.tabu_search(p, c, tl, tenures)
+        # the same iterations one call at a time (tabu_best_move semantics), for the best tour
+        seen_best, seen_iter, seen_path = c, -1, None
+        for k, t in enumerate(tenures):
+            c_step, mv = I.tabu_move(p_step, c_step, tl_step, t, k)
+            if c_step < seen_best:
+                seen_best, seen_iter, seen_path = c_step, k, p_step.copy()
+    assert [int(x) for x in trace] == [gc for _, gc, _ in g["log"]]
+    assert int(cost) == g["log"][-1][1] and fnv1a(p) == g["log"][-1][2] and fnv1a(tl) == g["tabu_list_hash"]
+    assert np.array_equal(p, p_step) and np.array_equal(tl, tl_step)
+    assert best_iter == seen_iter and (best_iter < 0 or (best_cost == seen_best and np.array_equal(best_path, seen_path)))
+
+
+def test_tabu_search_device_loop_vs_oracle(tsp, oracle):
+    """Random instance, non-integer coordinates, 300 iterations split over two calls (first_iter
+    continues), tenures that make every pair tabu for a while (iterations without a move)."""
+    n = 400
+    xy = _rand_xy(123, n, False)
+    path = _rand_tour(9, n)
+    m, p, c, *_ = oracle.two_opt(xy, path, log=False)
+    tenures = [3 + (k * 7) % 90 for k in range(300)]
+    tenures[50:60] = [100000] * 10
+    po, co, to = p.copy(), c, np.full(n, -1, dtype=np.int32)
+    trace_o = []
+    for k, t in enumerate(tenures):
+        co, a, b, d = oracle.tabu_move(xy, po, co, to, t, k)
+        trace_o.append(co)
+    pg, tg = p.copy(), np.full(n, -1, dtype=np.int32)
+    with tsp.Instance(xy) as I:
+        c1, tr1, bi1, bp1, bc1 = I.tabu_search(pg, c, tg, tenures[:170])
+        c2, tr2, bi2, bp2, bc2 = I.tabu_search(pg, c1, tg, tenures[170:], first_iter=170, incumbent_cost=bc1 if bi1 >= 0 else c)
+    assert list(tr1) + list(tr2) == trace_o and c2 == co
+    assert np.array_equal(pg, po) and np.array_equal(tg, to)
+    best = min(trace_o)
+    if best < c:
+        assert min(bc1 if bi1 >= 0 else c, bc2 if bi2 >= 0 else c) == best
+
+
 # ---- VNS local search (metaheuristic.c:279-320): host kicks, GPU descents ---------------------
 def test_vns_loop(tsp, oracle):
     xy, _ = load_instance("kroA100")

@@ -28,7 +28,7 @@ EXPORTS = [
     "tspcuda_cost_matrix_checksum", "tspcuda_nn", "tspcuda_nn_multi", "tspcuda_two_opt", "tspcuda_two_opt_once",
     "tspcuda_tabu_move", "tspcuda_tour_upload", "tspcuda_tour_descend", "tspcuda_tour_download", "tspcuda_tour_movelog",
     "tspcuda_multistart_two_opt", "tspcuda_pipe_rate", "tspcuda_selfcheck_sqrt", "tspcuda_timer_start",
-    "tspcuda_timer_stop", "tspcuda_flush_l2", "tspcuda_set_scan_mode",
+    "tspcuda_timer_stop", "tspcuda_flush_l2", "tspcuda_set_scan_mode", "tspcuda_tabu_search",
 ]
 
 
@@ -93,6 +93,7 @@ def lib():
     L.tspcuda_timer_stop.argtypes = [_vp, _dp]
     L.tspcuda_flush_l2.argtypes = [_vp]
     L.tspcuda_set_scan_mode.argtypes = [_vp, C.c_int]
+    L.tspcuda_tabu_search.argtypes = [_vp, _ip, _dp, _ip, _ip, C.c_int, C.c_int, C.c_double, _dp, _ip, _dp, _ip]
     _lib = L
     return L
 
@@ -207,6 +208,20 @@ class Instance:
         c, mv = C.c_double(cost), Move()
         _chk(lib().tspcuda_tabu_move(self._h, _ipc(path), C.byref(c), _ipc(tabu_list), tenure, it, C.byref(mv)))
         return c.value, (mv.a, mv.b, mv.delta)
+
+    def tabu_search(self, path, cost, tabu_list, tenures, first_iter=0, incumbent_cost=None):
+        """Device-resident tabu loop (mh_TabuSearch's k-loop).  path / tabu_list are updated in place.
+        Returns (cost, trace[k], best_iter, best_path or None, best_cost)."""
+        tenures = np.ascontiguousarray(tenures, dtype=np.int32)
+        k = tenures.shape[0]
+        c = C.c_double(cost)
+        trace = np.zeros(k, dtype=np.float64)
+        best_path = np.zeros(self.n, dtype=np.int32)
+        bc, bi = C.c_double(0), C.c_int(-1)
+        inc = cost if incumbent_cost is None else incumbent_cost
+        _chk(lib().tspcuda_tabu_search(self._h, _ipc(path), C.byref(c), _ipc(tabu_list), _ipc(tenures), first_iter, k,
+                                       inc, _dpc(trace), _ipc(best_path), C.byref(bc), C.byref(bi)))
+        return c.value, trace, bi.value, (best_path if bi.value >= 0 else None), bc.value
 
     # -- device-resident tour ----------------------------------------------------------------------
     def tour_upload(self, path):

@@ -18,6 +18,9 @@
  *   h_Greedy_iterative  heuristics.c:34  and  h_greedy_2opt  heuristics.c:74  (whole-loop overrides:
  *                       all starts in one batched call; TSPCUDA_BATCH=0 keeps the reference's loops,
  *                       which then call the interposed helpers start by start)
+ *   mh_TabuSearch       metaheuristic.c:86  (whole-loop override: the k tabu iterations run in one
+ *                       device-resident call; TSPCUDA_BATCH=0 keeps the reference's loop, which then
+ *                       calls the interposed tabu_best_move once per iteration)
  * ref_reverse_path (refinment.c:95) keeps the reference's definition: once ref_2opt_once and
  * tabu_best_move run on the device nothing on this path calls it.
  *
@@ -40,9 +43,9 @@ static tspcuda_ctx *g_ctx = NULL;
 static point *g_points = NULL;
 static int g_n = -1;
 static long g_calls[8];
-enum { C_COSTS, C_NN, C_2OPT, C_2OPT_ONCE, C_TABU, C_ALLNN, C_MULTI };
+enum { C_COSTS, C_NN, C_2OPT, C_2OPT_ONCE, C_TABU, C_ALLNN, C_MULTI, C_TABULOOP };
 static const char *g_names[] = {"tsp_compute_costs", "h_greedyutil", "ref_2opt", "ref_2opt_once",
-                                "tabu_best_move", "h_Greedy_iterative", "h_greedy_2opt"};
+                                "tabu_best_move", "h_Greedy_iterative", "h_greedy_2opt", "mh_TabuSearch"};
 
 /* Exit hook.  Prints the call counters (TSPCUDA_STATS=1), flushes stdio and leaves with _exit().
  * The last step shields the process from a latent heap overflow in the UNCHANGED driver:
@@ -56,7 +59,7 @@ static void on_exit_hook(int status, void *arg) {
     const char *s = getenv("TSPCUDA_STATS");
     if (s && *s == '1') {
         fprintf(stderr, "[tspcuda] interposed calls:");
-        for (int i = 0; i < 7; i++) fprintf(stderr, " %s=%ld", g_names[i], g_calls[i]);
+        for (int i = 0; i < 8; i++) fprintf(stderr, " %s=%ld", g_names[i], g_calls[i]);
         fprintf(stderr, "\n");
     }
     const char *f = getenv("TSPCUDA_FAST_EXIT");
@@ -290,4 +293,83 @@ ERROR_CODE h_greedy_2opt(void) {
     tsp_inst.starting_node = tsp_inst.nnodes - 1;
     utils_safe_free(solution.path);
     return T_OK;
+}
+
+/* mh_TabuSearch, metaheuristic.c:86-186.  Same steps in the same order -- tabu_init, results file,
+ * h_greedy_2opt start solution, k iterations of {tenure policy; tabu_best_move; incumbent update; one
+ * line of results/TabuResults.dat}, plot, clean-up -- except that the k iterations run in one
+ * device-resident call.  The tenure policies (metaheuristic.c:7-59) depend only on the tabu_search
+ * struct and rand(), never on the tour, so the reference's OWN policy functions are run ahead to lay
+ * out the tenure of every iteration.  The incumbent changes only on strictly smaller costs
+ * (tsp.c:671), so one tsp_update_best_solution with the first tour that reaches the minimum cost of
+ * the run leaves the same incumbent as the per-iteration calls. */
+ERROR_CODE mh_TabuSearch(void) {
+    if (!batch_enabled())
+        return ((void_fn)dlsym(RTLD_NEXT, "mh_TabuSearch"))();
+    g_calls[C_TABULOOP]++;
+    tabu_search ts;
+    if (!err_ok(tabu_init(&ts, tsp_inst.nnodes))) {
+        log_fatal("code %d : Error in init tabu search");
+        tsp_handlefatal();
+    }
+    ERROR_CODE e = T_OK;
+    FILE *f = fopen("results/TabuResults.dat", "w+");
+    tsp_solution solution;
+    tsp_init_solution(tsp_inst.nnodes, &solution);
+    if (!err_ok(h_greedy_2opt())) {
+        log_fatal("code %d : Error in greedy solution computation");
+        tsp_handlefatal();
+    }
+    solution.cost = tsp_inst.best_solution.cost;
+    memcpy(solution.path, tsp_inst.best_solution.path, tsp_inst.nnodes * sizeof(int));
+    log_debug("2opt greedy sol cost: %f", solution.cost);
+
+    const int K = tsp_env.k > 0 ? tsp_env.k : 0;
+    int *tenures = (int *)malloc(sizeof(int) * (K > 0 ? K : 1));
+    double *trace = (double *)malloc(sizeof(double) * (K > 0 ? K : 1));
+    for (int k = 0; k < K; k++) {                                   /* :136-156 */
+        switch (tsp_env.policy) {
+            case POL_FIXED: e = tabu_fixed_policy(&ts, 30); break;
+            case POL_LINEAR: e = tabu_linear_policy(&ts); break;
+            case POL_RANDOM: e = tabu_random_policy(&ts); break;
+            case POL_SIZE: e = tabu_dependent_policy(&ts); break;
+            default: e = UNKNOWN; break;
+        }
+        if (!err_ok(e)) log_warn("using already set policy %d", tsp_env.policy);
+        tenures[k] = ts.tenure;
+    }
+    tspcuda_ctx *c = ctx_for_instance();
+    tsp_solution best;
+    tsp_init_solution(tsp_inst.nnodes, &best);
+    int best_iter = -1;
+    int rc = c ? tspcuda_tabu_search(c, solution.path, &solution.cost, ts.tabu_list, tenures, 0, K, tsp_inst.best_solution.cost,
+                                     trace, best.path, &best.cost, &best_iter)
+               : TSPCUDA_INTERNAL;
+    if (rc != TSPCUDA_OK) {
+        log_fatal("code %d : Error in tabu best move (libtspcuda: %s)", rc, tspcuda_last_error());
+        tsp_handlefatal();
+    }
+    e = K > 0 ? CANCELLED : e;                                      /* what the last tsp_update_best_solution returns */
+    if (best_iter >= 0) {
+        ERROR_CODE u = tsp_update_best_solution(&best);
+        if (!err_ok(u)) {
+            log_fatal("code %d : Error in updating best solution", u);
+            tsp_handlefatal();
+        }
+        if (best_iter == K - 1) e = u;
+    }
+    if (f) {
+        for (int k = 0; k < K; k++) fprintf(f, "%d,%f\n", k, trace[k]);     /* :163 */
+        fclose(f);
+    }
+    PLOT plot = plot_open("TabuIterationsPlot");
+    if (tsp_env.tofile) plot_tofile(plot, "TabuIterationsPlot");
+    plot_stats(plot, "results/TabuResults.dat");
+    plot_free(plot);
+    utils_safe_free(solution.path);
+    utils_safe_free(best.path);
+    free(tenures);
+    free(trace);
+    tabu_free(&ts);
+    return e;
 }

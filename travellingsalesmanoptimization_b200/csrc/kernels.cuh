@@ -307,6 +307,93 @@ descend_kernel(TourView V, unsigned long long *key, DescState *st, MoveRec *log,
 }
 
 // ---------------------------------------------------------------------------------------------
+// K5b: device-resident tabu search, the loop of mh_TabuSearch (metaheuristic.c:128-164) around
+// tabu_best_move (:188-245) in ONE cooperative launch: per iteration  flags -> scan -> move -> stamp.
+// The tenure of every iteration comes from the host (the reference's own policy functions,
+// metaheuristic.c:7-59, computed ahead: they do not depend on the search state).  Every thread
+// keeps the running cost and the best cost in registers (same deterministic updates), so the
+// "new incumbent" decision (strict '<', tsp.c:671) needs no extra communication.
+// ---------------------------------------------------------------------------------------------
+struct TabuCtl {
+    int *tabu_list;            // [n] last iteration in which the node took part in a move, -1 never
+    const int *tenure;         // [iters] tenure in force at iteration first_iter + k
+    long long *trace;          // [iters] tour cost after iteration k (results/TabuResults.dat)
+    int *best_tid;             // [n+1] tour-position order of the best tour seen (valid if improved)
+    long long cost, best_cost; // in: current tour cost, incumbent cost
+    int first_iter, pad;
+};
+struct TabuOut { long long cost, best_cost, moves; int best_iter, pad; };
+
+template <class M, int BLK>
+__global__ void __launch_bounds__(BLK, 1024 / BLK)
+tabu_kernel(TourView V, unsigned long long *key, TabuCtl T, TabuOut *out, long long iters) {
+    constexpr int WARPS = BLK / 32;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double2 s_xy[WARPS][32];
+    __shared__ int s_dn[WARPS][32];
+    __shared__ unsigned long long s_key;
+    __shared__ int s_best;
+
+    const int n = V.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nstrips = (n - 2 + SR - 1) / SR;
+    const long long total = strip_prefix(nstrips, n);
+    const long long gw = (long long)blockIdx.x * WARPS + warp;
+    const long long W = (long long)gridDim.x * WARPS;
+    const long long lo = total * gw / W, hi = total * (gw + 1) / W;
+    const int gtid = blockIdx.x * BLK + threadIdx.x;
+    const int gsize = gridDim.x * BLK;
+    long long cost = T.cost, best_cost = T.best_cost, moves = 0;
+    int best_iter = -1;
+
+    for (long long k = 0; k < iters; ++k) {
+        const int iter = T.first_iter + (int)k;
+        const int tenure = T.tenure[k];
+        // dns[p] = dn[p] - BIGPEN where node(p) or node(p+1) is tabu (metaheuristic.c:208, :416-418)
+        for (int p = gtid; p <= n; p += gsize) {
+            const int u = V.tid[p], v = V.tid[p == n ? 1 : p + 1];
+            const int tu = T.tabu_list[u], tv = T.tabu_list[v];
+            const bool f = (iter - tu < tenure && tu != -1) || (iter - tv < tenure && tv != -1);
+            V.dns[p] = V.dn[p] - (f ? BIGPEN : 0);
+        }
+        if (threadIdx.x == 0) { s_key = KEY_EMPTY; s_best = BIGPEN / 2; }
+        grid.sync();
+        int best = BIGPEN / 2;                       // best admissible move even if worsening (:189)
+        unsigned long long bestkey = KEY_EMPTY;
+        scan_range<M>(V, lo, hi, nstrips, best, bestkey, s_xy[warp], s_dn[warp], &s_best);
+        bestkey = warp_min_key(bestkey);
+        if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
+        __syncthreads();
+        unsigned long long *kslot = key + (k & 1);
+        if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(kslot, s_key);
+        grid.sync();
+        const unsigned long long kbest = *(volatile unsigned long long *)kslot;
+        int seg_s = -1, seg_e = -1, b = -1;
+        if (kbest != KEY_EMPTY) {                    // every pair tabu: no move this iteration (:225)
+            const int a = key_a(kbest);
+            b = key_b(kbest);
+            if (gtid == 0) {                         // stamp a, b and their successors BEFORE the move (:235-238)
+                const int i = V.pos[a], j = V.pos[b];
+                const int sa = V.tid[i + 1], sb = V.tid[j + 1];
+                T.tabu_list[a] = iter; T.tabu_list[b] = iter; T.tabu_list[sa] = iter; T.tabu_list[sb] = iter;
+            }
+            apply_move<M>(V, a, b, gtid, gsize, false, seg_s, seg_e);
+            cost += key_delta(kbest);
+            ++moves;
+        }
+        if (gtid == 0) { key[(k + 1) & 1] = KEY_EMPTY; T.trace[k] = cost; }
+        grid.sync();
+        if (b >= 0 && gtid == 0) { V.pos[b] = seg_s; V.pos[V.tid[seg_e]] = seg_e; }
+        if (cost < best_cost) {                      // tsp_update_best_solution, strict '<' (tsp.c:671)
+            best_cost = cost;
+            best_iter = iter;
+            for (int p = gtid; p <= n; p += gsize) T.best_tid[p] = V.tid[p];
+        }
+    }
+    if (gtid == 0) { out->cost = cost; out->best_cost = best_cost; out->moves = moves; out->best_iter = best_iter; }
+}
+
+// ---------------------------------------------------------------------------------------------
 // K6: one CTA per descent, whole tour resident in shared memory (n <= CTA_MAX_N).  Used for
 // multi-start work on small instances (h_greedy_2opt on pr2392-class inputs), where one scan is a
 // few microseconds of whole-GPU work and a grid-wide barrier per move would dominate: here a move

@@ -577,6 +577,123 @@ extern "C" int tspcuda_tabu_move(tspcuda_ctx *c, int *path, double *cost_inout, 
     return TSPCUDA_OK;
 }
 
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    template <class T> T *as() { return reinterpret_cast<T *>(p); }
+};
+
+__global__ void order_to_path_kernel(const int *order, int n, int *path) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+        path[order[p]] = order[p + 1 == n ? 0 : p + 1];
+}
+
+// ---- device-resident tabu search (metaheuristic.c:128-164 around :188-245) ---------------------
+template <class M>
+static cudaError_t launch_tabu(tspcuda_ctx *c, int grid, TabuCtl T, TabuOut *out, long long iters) {
+    TourView V = c->tour;
+    unsigned long long *key = c->d_key;
+    void *args[] = {&V, &key, &T, &out, &iters};
+    if (c->block == BLOCK_BIG)
+        return cudaLaunchCooperativeKernel((void *)tabu_kernel<M, BLOCK_BIG>, dim3(grid), dim3(BLOCK_BIG), args, 0, c->stream);
+    return cudaLaunchCooperativeKernel((void *)tabu_kernel<M, BLOCK_SMALL>, dim3(grid), dim3(BLOCK_SMALL), args, 0, c->stream);
+}
+
+extern "C" int tspcuda_tabu_search(tspcuda_ctx *c, int *path, double *cost_inout, int *tabu_list, const int *tenures,
+                                   int first_iter, int n_iters, double incumbent_cost, double *cost_trace_out,
+                                   int *best_path_out, double *best_cost_out, int *best_iter_out) {
+    int e = use(c);
+    if (e) return e;
+    if (!path || !cost_inout || !tabu_list || (n_iters > 0 && !tenures)) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
+    if (n_iters < 0) return fail(TSPCUDA_INVALID_ARGUMENT, "n_iters = %d", n_iters);
+    const int n = c->n;
+    if (best_iter_out) *best_iter_out = -1;
+    if (best_cost_out) *best_cost_out = incumbent_cost;
+    e = tspcuda_tour_upload(c, path);
+    if (e) return e;
+    if (n < 4 || n_iters == 0) {                       // no admissible pair exists (refinment.c:55 rule)
+        for (int k = 0; k < n_iters && cost_trace_out; k++) cost_trace_out[k] = *cost_inout;
+        return TSPCUDA_OK;
+    }
+    DevBuf d_ten, d_trace, d_best, d_out;
+    CK(cudaMalloc(&d_ten.p, sizeof(int) * n_iters));
+    CK(cudaMalloc(&d_trace.p, sizeof(long long) * n_iters));
+    CK(cudaMalloc(&d_best.p, sizeof(int) * ((size_t)n + 1)));
+    CK(cudaMalloc(&d_out.p, sizeof(TabuOut)));
+    CK(cudaMemcpyAsync(d_ten.p, tenures, sizeof(int) * n_iters, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(c->d_tabu, tabu_list, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    c->stats.h2d_bytes += (int64_t)sizeof(int) * ((int64_t)n + n_iters);
+    const int nstrips = (n - 2 + SR - 1) / SR;
+    const long long total_cols = (long long)nstrips * (n - 2) - (long long)SR * ((long long)nstrips * (nstrips - 1) / 2);
+    const int grid = (int)std::max<long long>(1, std::min<long long>(c->max_coop_blocks, total_cols / ((c->block / 32) * 48)));
+    TabuCtl T;
+    T.tabu_list = c->d_tabu; T.best_tid = d_best.as<int>();
+    T.cost = (long long)*cost_inout; T.best_cost = (long long)incumbent_cost; T.pad = 0;
+    TabuOut h_out{};
+    h_out.best_iter = -1;
+    long long moves = 0;
+    const int CHUNK = 4096;                            // iterations per launch
+    for (int done = 0; done < n_iters; done += CHUNK) {
+        const int cnt = std::min(CHUNK, n_iters - done);
+        T.tenure = d_ten.as<int>() + done;
+        T.trace = d_trace.as<long long>() + done;
+        T.first_iter = first_iter + done;
+        CK(cudaMemsetAsync(c->d_key, 0xFF, sizeof(unsigned long long) * 2, c->stream));
+        CK(cudaEventRecord(c->ev0, c->stream));
+        cudaError_t le = cudaSuccess;
+        DISPATCH_METRIC(c->metric, le = launch_tabu<M>(c, grid, T, d_out.as<TabuOut>(), cnt));
+        CK(le);
+        CK(cudaEventRecord(c->ev1, c->stream));
+        c->stats.kernel_launches += 1;
+        TabuOut o{};
+        CK(cudaMemcpyAsync(&o, d_out.p, sizeof(TabuOut), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->stats.scan_kernel_ms += ms;
+        c->stats.last_kernel_ms = ms;
+        c->stats.scans += cnt;
+        c->stats.moves += o.moves;
+        c->stats.pair_evals += (long long)cnt * ((long long)n * (n - 1) / 2);
+        moves += o.moves;
+        T.cost = o.cost; T.best_cost = o.best_cost;
+        h_out.cost = o.cost; h_out.best_cost = o.best_cost;
+        if (o.best_iter >= 0) h_out.best_iter = o.best_iter;
+    }
+    c->tour_loaded = false;
+    c->dev_moves += moves;
+    // results: trace, tabu list, final tour, best tour
+    if (cost_trace_out) {
+        std::vector<long long> tr(n_iters);
+        CK(cudaMemcpyAsync(tr.data(), d_trace.p, sizeof(long long) * n_iters, cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        for (int k = 0; k < n_iters; k++) cost_trace_out[k] = (double)tr[k];
+        c->stats.d2h_bytes += (int64_t)sizeof(long long) * n_iters;
+    }
+    CK(cudaMemcpyAsync(tabu_list, c->d_tabu, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    c->stats.d2h_bytes += (int64_t)sizeof(int) * n;
+    {   // d_state->cost mirrors the device tour for later tour_download calls
+        const long long cst = h_out.cost;
+        CK(cudaMemcpyAsync(&c->d_state->cost, &cst, sizeof(long long), cudaMemcpyHostToDevice, c->stream));
+    }
+    e = tspcuda_tour_download(c, path, nullptr);
+    if (e) return e;
+    *cost_inout = (double)h_out.cost;
+    if (h_out.best_iter >= 0) {
+        if (best_path_out) {
+            order_to_path_kernel<<<grid_for(n, 4 * c->num_sms), 256, 0, c->stream>>>(d_best.as<int>(), n, c->d_path);
+            c->stats.kernel_launches += 1;
+            CK(cudaGetLastError());
+            CK(cudaMemcpyAsync(best_path_out, c->d_path, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->stats.d2h_bytes += (int64_t)sizeof(int) * n;
+        }
+        if (best_cost_out) *best_cost_out = (double)h_out.best_cost;
+        if (best_iter_out) *best_iter_out = h_out.best_iter;
+    }
+    return TSPCUDA_OK;
+}
+
 // ---- nearest neighbour ----------------------------------------------------------------------
 struct NNScratch {
     double2 *cxy = nullptr;
@@ -584,11 +701,6 @@ struct NNScratch {
     long long *cost = nullptr;
     ~NNScratch() { cudaFree(cxy); cudaFree(cid); cudaFree(order); cudaFree(cost); }
 };
-
-__global__ void order_to_path_kernel(const int *order, int n, int *path) {
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
-        path[order[p]] = order[p + 1 == n ? 0 : p + 1];
-}
 
 static int nn_batch(tspcuda_ctx *c, NNScratch &S, int first_start, int count, int stride, long long *h_cost) {
     const int n = c->n;
@@ -670,12 +782,6 @@ static cudaError_t launch_cta_descents(tspcuda_ctx *c, const int *d_order, int c
     descend_cta_kernel<M, BLK><<<grid, BLK, smem, c->stream>>>(c->d_xy, c->n, d_order, count, d_next, d_cost, d_moves, d_paths);
     return cudaGetLastError();
 }
-
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf() { cudaFree(p); }
-    template <class T> T *as() { return reinterpret_cast<T *>(p); }
-};
 
 extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int nstarts, int stride, double *nn_costs_out,
                                           double *final_costs_out, int64_t *moves_out, int *best_start_out,
