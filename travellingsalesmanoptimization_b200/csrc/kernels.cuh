@@ -343,8 +343,11 @@ tabu_kernel(TourView V, unsigned long long *key, TabuCtl T, TabuOut *out, long l
     const long long lo = total * gw / W, hi = total * (gw + 1) / W;
     const int gtid = blockIdx.x * BLK + threadIdx.x;
     const int gsize = gridDim.x * BLK;
-    long long cost = T.cost, best_cost = T.best_cost, moves = 0;
-    int best_iter = -1;
+    // running cost / best cost / counters live in shared memory (one replica per CTA, same
+    // deterministic updates everywhere) so that they hold no registers during the scan
+    __shared__ long long s_cost, s_bestcost, s_moves;
+    __shared__ int s_bestiter;
+    if (threadIdx.x == 0) { s_cost = T.cost; s_bestcost = T.best_cost; s_moves = 0; s_bestiter = -1; }
 
     for (long long k = 0; k < iters; ++k) {
         const int iter = T.first_iter + (int)k;
@@ -358,11 +361,13 @@ tabu_kernel(TourView V, unsigned long long *key, TabuCtl T, TabuOut *out, long l
         }
         if (threadIdx.x == 0) { s_key = KEY_EMPTY; s_best = BIGPEN / 2; }
         grid.sync();
-        int best = BIGPEN / 2;                       // best admissible move even if worsening (:189)
-        unsigned long long bestkey = KEY_EMPTY;
-        scan_range<M>(V, lo, hi, nstrips, best, bestkey, s_xy[warp], s_dn[warp], &s_best);
-        bestkey = warp_min_key(bestkey);
-        if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
+        {
+            int best = BIGPEN / 2;                   // best admissible move even if worsening (:189)
+            unsigned long long bestkey = KEY_EMPTY;
+            scan_range<M>(V, lo, hi, nstrips, best, bestkey, s_xy[warp], s_dn[warp], &s_best);
+            bestkey = warp_min_key(bestkey);
+            if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
+        }
         __syncthreads();
         unsigned long long *kslot = key + (k & 1);
         if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(kslot, s_key);
@@ -378,19 +383,19 @@ tabu_kernel(TourView V, unsigned long long *key, TabuCtl T, TabuOut *out, long l
                 T.tabu_list[a] = iter; T.tabu_list[b] = iter; T.tabu_list[sa] = iter; T.tabu_list[sb] = iter;
             }
             apply_move<M>(V, a, b, gtid, gsize, false, seg_s, seg_e);
-            cost += key_delta(kbest);
-            ++moves;
+            if (threadIdx.x == 0) { s_cost += key_delta(kbest); s_moves += 1; }
         }
-        if (gtid == 0) { key[(k + 1) & 1] = KEY_EMPTY; T.trace[k] = cost; }
+        if (gtid == 0) { key[(k + 1) & 1] = KEY_EMPTY; T.trace[k] = s_cost; }
         grid.sync();
         if (b >= 0 && gtid == 0) { V.pos[b] = seg_s; V.pos[V.tid[seg_e]] = seg_e; }
-        if (cost < best_cost) {                      // tsp_update_best_solution, strict '<' (tsp.c:671)
-            best_cost = cost;
-            best_iter = iter;
+        const bool improved = s_cost < s_bestcost;   // tsp_update_best_solution, strict '<' (tsp.c:671)
+        if (improved)
             for (int p = gtid; p <= n; p += gsize) T.best_tid[p] = V.tid[p];
-        }
+        __syncthreads();
+        if (improved && threadIdx.x == 0) { s_bestcost = s_cost; s_bestiter = iter; }
     }
-    if (gtid == 0) { out->cost = cost; out->best_cost = best_cost; out->moves = moves; out->best_iter = best_iter; }
+    __syncthreads();
+    if (gtid == 0) { out->cost = s_cost; out->best_cost = s_bestcost; out->moves = s_moves; out->best_iter = s_bestiter; }
 }
 
 // ---------------------------------------------------------------------------------------------
