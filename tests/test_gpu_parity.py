@@ -398,10 +398,12 @@ def test_ceil2d_and_att(tsp, oracle):
 
 # ---- multi-start (h_greedy_2opt, heuristics.c:74-116) -----------------------------------------
 @pytest.mark.parametrize("name", ["berlin52", "eil51", "kroA100"])
-def test_multistart_golden(tsp, golden, name):
+@pytest.mark.parametrize("scan", ["full", "auto"])
+def test_multistart_golden(tsp, golden, name, scan):
+    """All starts: 'full' = K6 (CTA per descent, every pair), 'auto' = K8 (CTA per descent, pruned scan)."""
     xy, _ = load_instance(name)
     g = golden[name]["greedy_2opt"]
-    with tsp.Instance(xy) as I:
+    with _inst(tsp, xy, scan) as I:
         bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(0, xy.shape[0])
     assert [[int(a), int(m), int(f)] for a, m, f in zip(nn_costs, moves, final)] == g["per_start"]
     assert (int(bc), bs, fnv1a(bp)) == (g["cost"], g["first_start"], g["hash"])
@@ -421,15 +423,20 @@ def test_multistart_pr2392_first8_and_strided(tsp, golden):
         assert [int(f) for f in fin2] == [g[1][2], g[5][2]]
 
 
-def test_multistart_cta_paths_vs_grid_path(tsp, oracle):
-    """The CTA-per-descent kernel (n <= 7600; 512- and 1024-thread variants) and the grid-wide
-    descent kernel must produce the same tours: compare multistart (CTA path) with nn + two_opt
-    (grid path) start by start, and one start of each size with the CPU oracle."""
-    for n, starts in ((130, 6), (1500, 4), (3700, 3)):
+@pytest.mark.parametrize("scan", ["full", "auto"])
+def test_multistart_cta_paths_vs_grid_path(tsp, oracle, scan):
+    """The CTA-per-descent kernels (K6: full scan, n <= 7100, 512- and 1024-thread variants; K8: pruned
+    scan, any n, used from num_sms/4 starts up) and the grid-wide descent kernels must produce the same
+    tours: compare multistart with nn + two_opt start by start, and one start of each size with the
+    CPU oracle."""
+    for n, starts in ((130, 6), (1500, 4), (3700, 3), (900, 60), (9000, 40)):
+        if scan == "full" and n == 9000:
+            continue
         xy = _rand_xy(900 + n, n, n % 2 == 0)
-        with tsp.Instance(xy) as I:
+        with _inst(tsp, xy, scan) as I:
             bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(2, starts, 5)
             per = []
+            I.set_scan_mode(tsp.SCAN_FULL if n < 5000 else tsp.SCAN_AUTO)
             for k in range(starts):
                 code, p, c = I.nn(2 + 5 * k)
                 code, mv, p2, c2, _ = I.two_opt(p)
@@ -449,6 +456,8 @@ def test_pr2392_all_start_config2(tsp, golden):
     with tsp.Instance(xy) as I:
         bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(0, 2392)
         bs_nn, bp_nn, bc_nn, _ = I.nn_multi(0, 2392)
+        st = I.stats()
+    assert st["pruned_scans"] == int(moves.sum()) + 2392        # K8 answered every scan
     assert (int(bc), bs) == (golden["pr2392"]["greedy_2opt_survey"]["cost"], golden["pr2392"]["greedy_2opt_survey"]["first_start"])
     for lo, hi, cost, first in golden["pr2392"]["greedy_2opt_survey_ranges"]:
         seg = final[lo:hi]

@@ -196,7 +196,143 @@ __device__ __forceinline__ bool probe_box(const SpatialGrid &G, const Probe &P, 
     return true;
 }
 
-// ---- K7 ---------------------------------------------------------------------------------------
+// ---- the two scan phases, shared by the whole-GPU kernel (K7) and the CTA-per-descent kernel (K8) --
+// Phase 1: thread `t` of `nthreads` cooperating threads (a grid or one CTA; t's warp is complete and
+// nthreads is a multiple of 32) takes tour positions t, t + nthreads, ...  Search boxes with at most
+// PR_SMALL_NODES nodes are walked inline, larger ones are appended to boxes[] through the packed
+// counter *qctr (boxes in the high 24 bits, cell rows in the low 40; one atomic per warp).
+template <class M, int NC1>
+__device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGrid &G, const PosPatch &F, int t, int nthreads,
+                                              unsigned long long *qctr, BigBox *boxes, int &best,
+                                              unsigned long long &bestkey, long long &ncand) {
+    const int n = V.n;
+    const int lane = threadIdx.x & 31;
+    for (int p0 = t - lane; p0 < n; p0 += nthreads) {              // warp-uniform trip count
+        const int p = p0 + lane;
+        Probe P;
+        int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = -1;
+        bool has = false;
+        if (p < n) {
+            probe_load(V, p, P);
+            has = probe_box<M>(G, P, cx0, cx1, cy0, cy1);
+        }
+        const int nrows = has ? cy1 - cy0 + 1 : 0;
+        int total = 0;
+        if (has) {
+            if (nrows <= PR_SMALL_ROWS) {
+#pragma unroll
+                for (int r = 0; r < PR_SMALL_ROWS; ++r) {          // unrolled: all row bounds in flight at once
+                    const int cy = min(cy0 + r, cy1);
+                    const int cnt = G.cell_start[cy * G.W + cx1 + 1] - G.cell_start[cy * G.W + cx0];
+                    total += (cy0 + r <= cy1) ? cnt : 0;
+                }
+            } else {
+                total = PR_SMALL_NODES + 1;
+            }
+        }
+        const bool big = total > PR_SMALL_NODES;
+        const unsigned bigmask = __ballot_sync(FULL, big);
+        if (bigmask) {                                             // one queue atomic per warp
+            const int myrows = big ? nrows : 0;
+            int incl = myrows;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(FULL, incl, off);
+                if (lane >= off) incl += v;
+            }
+            const int totrows = __shfl_sync(FULL, incl, 31);
+            unsigned long long old = 0;
+            if (lane == 0)
+                old = atomicAdd(qctr, ((unsigned long long)__popc(bigmask) << 40) | (unsigned long long)totrows);
+            old = __shfl_sync(FULL, old, 0);
+            if (big) {
+                BigBox bx;
+                bx.p = p; bx.cy0 = cy0; bx.cx0 = cx0; bx.cx1 = cx1; bx.nrows = nrows; bx.pad = 0;
+                bx.base = (long long)(old & PR_UNIT_MASK) + (incl - myrows);
+                boxes[(old >> 40) + __popc(bigmask & ((1u << lane) - 1))] = bx;
+            }
+        }
+        if (has && !big) {
+            ncand += total;
+            // the box's candidates as ONE stream across its cell rows (row bounds are L1 hits by now),
+            // NC1 at a time through the staged evaluation
+            int cy = cy0, k = 0, hi = 0, last = 0;
+            for (int done = 0; done < total; done += NC1) {
+                int w[NC1]; double wx[NC1], wy[NC1]; bool valid[NC1];
+                int kk[NC1];
+#pragma unroll
+                for (int j = 0; j < NC1; ++j) {
+                    valid[j] = done + j < total;
+                    if (valid[j]) {
+                        while (k >= hi) {
+                            k = G.cell_start[cy * G.W + cx0];
+                            hi = G.cell_start[cy * G.W + cx1 + 1];
+                            ++cy;
+                        }
+                        last = k++;
+                    }
+                    kk[j] = last;
+                }
+#pragma unroll
+                for (int j = 0; j < NC1; ++j) {
+                    const double2 c = G.cxy[kk[j]];
+                    w[j] = G.cnode[kk[j]]; wx[j] = c.x; wy[j] = c.y;
+                }
+                cand_eval_n<M, NC1>(V, P, F, w, wx, wy, valid, best, bestkey);
+            }
+        }
+    }
+}
+
+// Phase 2 (behind a barrier): the queued boxes, cut into (box, cell row) units -- one contiguous
+// range of the cell-sorted node array each -- split evenly over the `nwarps` cooperating warps;
+// this warp is number `gw`.  q = the packed counter after phase 1.
+template <class M>
+__device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGrid &G, const PosPatch &F, long long gw,
+                                              long long nwarps, unsigned long long q, const BigBox *boxes, int &best,
+                                              unsigned long long &bestkey, long long &ncand) {
+    const int lane = threadIdx.x & 31;
+    const long long nunits = (long long)(q & PR_UNIT_MASK);
+    const int nboxes = (int)(q >> 40);
+    if (nunits <= 0) return;
+    const long long per = (nunits + nwarps - 1) / nwarps;
+    const long long g0 = gw * per, g1 = min(nunits, g0 + per);
+    if (g0 >= g1) return;
+    // last box with base <= g0: 33-ary search, one probe per lane and step
+    int lo_b = 0, hi_b = nboxes;
+    while (hi_b - lo_b > 1) {
+        const int step = (hi_b - lo_b + 32) / 33;
+        const int idx = lo_b + (lane + 1) * step;
+        const bool ok = idx < hi_b && boxes[idx].base <= g0;
+        const int cnt = __popc(__ballot_sync(FULL, ok));           // bases ascend: the ok lanes are a prefix
+        const int nlo = lo_b + cnt * step;
+        hi_b = min(hi_b, lo_b + (cnt + 1) * step);
+        lo_b = nlo;
+    }
+    int bi = lo_b;
+    BigBox b = boxes[bi];
+    Probe P;
+    probe_load(V, b.p, P);
+    for (long long g = g0; g < g1; ++g) {
+        while (g >= b.base + b.nrows) { b = boxes[++bi]; probe_load(V, b.p, P); }
+        const int cy = b.cy0 + (int)(g - b.base);
+        const int lo = G.cell_start[cy * G.W + b.cx0], hi = G.cell_start[cy * G.W + b.cx1 + 1];
+        if (lane == 0) ncand += hi - lo;
+        for (int k = lo + lane; k < hi; k += 32 * PR_NC2) {
+            int w[PR_NC2]; double wx[PR_NC2], wy[PR_NC2]; bool valid[PR_NC2];
+#pragma unroll
+            for (int j = 0; j < PR_NC2; ++j) {
+                valid[j] = k + 32 * j < hi;
+                const int kk = min(k + 32 * j, hi - 1);
+                const double2 c = G.cxy[kk];
+                w[j] = G.cnode[kk]; wx[j] = c.x; wy[j] = c.y;
+            }
+            cand_eval_n<M, PR_NC2>(V, P, F, w, wx, wy, valid, best, bestkey);
+        }
+    }
+}
+
+// ---- K7: whole-GPU persistent pruned descent (cooperative launch, one CTA per SM) ----------------
 template <class M, int BLK>
 __global__ void __launch_bounds__(BLK, 1)
 descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
@@ -205,7 +341,6 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
     constexpr int NC1 = BLK > 512 ? 2 : PR_NC;      // 1024-thread CTAs have 64 registers per thread
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned long long s_key;
-    const int n = V.n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gtid = blockIdx.x * BLK + threadIdx.x;
     const int gsize = gridDim.x * BLK;
@@ -232,132 +367,15 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         int best = -1;
         unsigned long long bestkey = KEY_EMPTY;
         long long ncand = 0;
-
-        // ---- phase 1: one thread per position, small boxes inline, large boxes queued ----------
-        for (int p0 = gtid - lane; p0 < n; p0 += gsize) {          // warp-uniform trip count
-            const int p = p0 + lane;
-            Probe P;
-            int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = -1;
-            bool has = false;
-            if (p < n) {
-                probe_load(V, p, P);
-                has = probe_box<M>(G, P, cx0, cx1, cy0, cy1);
-            }
-            const int nrows = has ? cy1 - cy0 + 1 : 0;
-            int total = 0;
-            if (has) {
-                if (nrows <= PR_SMALL_ROWS) {
-#pragma unroll
-                    for (int r = 0; r < PR_SMALL_ROWS; ++r) {      // unrolled: all row bounds in flight at once
-                        const int cy = min(cy0 + r, cy1);
-                        const int cnt = G.cell_start[cy * G.W + cx1 + 1] - G.cell_start[cy * G.W + cx0];
-                        total += (cy0 + r <= cy1) ? cnt : 0;
-                    }
-                } else {
-                    total = PR_SMALL_NODES + 1;
-                }
-            }
-            const bool big = total > PR_SMALL_NODES;
-            const unsigned bigmask = __ballot_sync(FULL, big);
-            if (bigmask) {                                         // one queue atomic per warp
-                const int myrows = big ? nrows : 0;
-                int incl = myrows;
-#pragma unroll
-                for (int off = 1; off < 32; off <<= 1) {
-                    const int v = __shfl_up_sync(FULL, incl, off);
-                    if (lane >= off) incl += v;
-                }
-                const int totrows = __shfl_sync(FULL, incl, 31);
-                unsigned long long old = 0;
-                if (lane == 0)
-                    old = atomicAdd(qctr, ((unsigned long long)__popc(bigmask) << 40) | (unsigned long long)totrows);
-                old = __shfl_sync(FULL, old, 0);
-                if (big) {
-                    BigBox bx;
-                    bx.p = p; bx.cy0 = cy0; bx.cx0 = cx0; bx.cx1 = cx1; bx.nrows = nrows; bx.pad = 0;
-                    bx.base = (long long)(old & PR_UNIT_MASK) + (incl - myrows);
-                    boxes[(old >> 40) + __popc(bigmask & ((1u << lane) - 1))] = bx;
-                }
-            }
-            if (has && !big) {
-                ncand += total;
-                // the box's candidates as ONE stream across its cell rows (row bounds are L1 hits by now),
-                // NC1 at a time through the staged evaluation
-                int cy = cy0, k = 0, hi = 0, last = 0;
-                for (int done = 0; done < total; done += NC1) {
-                    int w[NC1]; double wx[NC1], wy[NC1]; bool valid[NC1];
-                    int kk[NC1];
-#pragma unroll
-                    for (int j = 0; j < NC1; ++j) {
-                        valid[j] = done + j < total;
-                        if (valid[j]) {
-                            while (k >= hi) {
-                                k = G.cell_start[cy * G.W + cx0];
-                                hi = G.cell_start[cy * G.W + cx1 + 1];
-                                ++cy;
-                            }
-                            last = k++;
-                        }
-                        kk[j] = last;
-                    }
-#pragma unroll
-                    for (int j = 0; j < NC1; ++j) {
-                        const double2 c = G.cxy[kk[j]];
-                        w[j] = G.cnode[kk[j]]; wx[j] = c.x; wy[j] = c.y;
-                    }
-                    cand_eval_n<M, NC1>(V, P, F, w, wx, wy, valid, best, bestkey);
-                }
-            }
-        }
+        pruned_phase1<M, NC1>(V, G, F, gtid, gsize, qctr, boxes, best, bestkey, ncand);
         grid.sync();
         PHASE_MARK(0)
-
-        // ---- phase 2: queued boxes, (box,row) units split evenly over the warps of the grid ----
         {
             const unsigned long long q = *(volatile unsigned long long *)qctr;
-            const long long nunits = (long long)(q & PR_UNIT_MASK);
-            const int nboxes = (int)(q >> 40);
 #ifdef TSP_PHASE_TIMING
-            if (gtid == 0) { st->phase_ns[4] += nunits; st->phase_ns[5] += nboxes; }
+            if (gtid == 0) { st->phase_ns[4] += (long long)(q & PR_UNIT_MASK); st->phase_ns[5] += (long long)(q >> 40); }
 #endif
-            if (nunits > 0) {
-                const long long per = (nunits + Wtot - 1) / Wtot;
-                const long long g0 = gw * per, g1 = min(nunits, g0 + per);
-                if (g0 < g1) {
-                    // last box with base <= g0: 33-ary search, one probe per lane and step
-                    int lo_b = 0, hi_b = nboxes;
-                    while (hi_b - lo_b > 1) {
-                        const int step = (hi_b - lo_b + 32) / 33;
-                        const int idx = lo_b + (lane + 1) * step;
-                        const bool ok = idx < hi_b && boxes[idx].base <= g0;
-                        const int cnt = __popc(__ballot_sync(FULL, ok));     // bases ascend: the ok lanes are a prefix
-                        const int nlo = lo_b + cnt * step;
-                        hi_b = min(hi_b, lo_b + (cnt + 1) * step);
-                        lo_b = nlo;
-                    }
-                    int bi = lo_b;
-                    BigBox b = boxes[bi];
-                    Probe P;
-                    probe_load(V, b.p, P);
-                    for (long long g = g0; g < g1; ++g) {
-                        while (g >= b.base + b.nrows) { b = boxes[++bi]; probe_load(V, b.p, P); }
-                        const int cy = b.cy0 + (int)(g - b.base);
-                        const int lo = G.cell_start[cy * G.W + b.cx0], hi = G.cell_start[cy * G.W + b.cx1 + 1];
-                        if (lane == 0) ncand += hi - lo;
-                        for (int k = lo + lane; k < hi; k += 32 * PR_NC2) {
-                            int w[PR_NC2]; double wx[PR_NC2], wy[PR_NC2]; bool valid[PR_NC2];
-#pragma unroll
-                            for (int j = 0; j < PR_NC2; ++j) {
-                                valid[j] = k + 32 * j < hi;
-                                const int kk = min(k + 32 * j, hi - 1);
-                                const double2 c = G.cxy[kk];
-                                w[j] = G.cnode[kk]; wx[j] = c.x; wy[j] = c.y;
-                            }
-                            cand_eval_n<M, PR_NC2>(V, P, F, w, wx, wy, valid, best, bestkey);
-                        }
-                    }
-                }
-            }
+            pruned_phase2<M>(V, G, F, gw, Wtot, q, boxes, best, bestkey, ncand);
         }
         bestkey = warp_min_key(bestkey);
         for (int off = 16; off > 0; off >>= 1) ncand += __shfl_down_sync(FULL, ncand, off);
@@ -393,6 +411,113 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         F.node0 = b; F.pos0 = seg_s; F.node1 = V.tid[seg_e]; F.pos1 = seg_e;
         if (gtid == 0) { V.pos[F.node0] = F.pos0; V.pos[F.node1] = F.pos1; }   // deferred end-node positions
     }
+}
+
+// ---- K8: one CTA per descent, pruned scan, tours in CTA-private global-memory slots -------------------
+// Multi-start work (h_greedy_2opt, heuristics.c:74-116): a pruned scan is a few hundred thousand
+// candidate evaluations, far too little to fill 148 SMs, so the SMs run independent descents
+// instead.  CTAs pull start indices from an atomic counter in ascending order; the tour of the
+// current start lives in the CTA's own slot of global memory (L1/L2 resident, any n), every
+// barrier is a __syncthreads.  Each CTA keeps its best tour under the reference's incumbent rule
+// (strict '<' in ascending start order, tsp.c:671); the host takes the (cost, start)-minimum.
+struct MultiSlots {
+    double2 *pxy;      // [slots][n+1]
+    int *tid, *dn;     // [slots][n+1]
+    int *pos;          // [slots][n]
+    BigBox *boxes;     // [slots][n]
+    int *best_path;    // [slots][n]  successor array of the CTA's best tour
+    long long *best_cost;   // [slots]
+    int *best_start;        // [slots]
+};
+
+template <class M, int BLK>
+__global__ void __launch_bounds__(BLK, 1)
+multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const int *__restrict__ order_all, int first_start,
+                    int stride, int nstarts, int *next_start, MultiSlots S, long long *final_cost, long long *moves_out,
+                    unsigned long long *cand_total) {
+    constexpr int WARPS = BLK / 32;
+    constexpr int NC1 = BLK > 512 ? 2 : PR_NC;
+    __shared__ unsigned long long s_key, s_q;
+    __shared__ long long s_cost, s_bestcost;
+    __shared__ int s_cur;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const size_t n1 = (size_t)n + 1, slot = blockIdx.x;
+    TourView V;
+    V.n = n;
+    V.pxy = S.pxy + slot * n1;
+    V.tid = S.tid + slot * n1;
+    V.dn = S.dn + slot * n1;
+    V.dns = V.dn;
+    V.pos = S.pos + slot * (size_t)n;
+    BigBox *boxes = S.boxes + slot * (size_t)n;
+    int *best_path = S.best_path + slot * (size_t)n;
+    if (t == 0) { s_bestcost = -1; S.best_cost[slot] = -1; S.best_start[slot] = -1; }
+    long long ncand = 0;
+
+    for (;;) {
+        __syncthreads();
+        if (t == 0) s_cur = atomicAdd(next_start, 1);
+        __syncthreads();
+        const int cur = s_cur;
+        if (cur >= nstarts) break;
+        const int *order = order_all + (size_t)cur * n;
+        for (int p = t; p <= n; p += BLK) {
+            const int node = order[p == n ? 0 : p];
+            V.pxy[p] = xy[node];
+            V.tid[p] = node;
+            if (p < n) V.pos[node] = p;
+        }
+        if (t == 0) s_cost = 0;
+        __syncthreads();
+        long long local = 0;
+        for (int p = t; p < n; p += BLK) {
+            const double2 u = V.pxy[p], v = V.pxy[p + 1];
+            const int k = M::K(u.x, u.y, v.x, v.y);
+            V.dn[p] = k;
+            if (p == 0) V.dn[n] = k;
+            local += (long long)(k - KOFF);
+        }
+        for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(FULL, local, o);
+        if (lane == 0) atomicAdd((unsigned long long *)&s_cost, (unsigned long long)local);
+        long long moves = 0;
+        PosPatch F = {-1, 0, -1, 0};
+        for (;;) {
+            if (t == 0) { s_key = KEY_EMPTY; s_q = 0; }
+            __syncthreads();
+            int best = -1;
+            unsigned long long bestkey = KEY_EMPTY;
+            pruned_phase1<M, NC1>(V, G, F, t, BLK, &s_q, boxes, best, bestkey, ncand);
+            __syncthreads();
+            pruned_phase2<M>(V, G, F, warp, WARPS, s_q, boxes, best, bestkey, ncand);
+            bestkey = warp_min_key(bestkey);
+            if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
+            __syncthreads();
+            const unsigned long long kbest = s_key;
+            if (kbest == KEY_EMPTY) break;                      // local optimum (refinment.c:27)
+            const int a = key_a(kbest), b = key_b(kbest);
+            int seg_s, seg_e;
+            apply_move<M>(V, a, b, t, BLK, false, seg_s, seg_e);
+            if (t == 0) s_cost += key_delta(kbest);
+            ++moves;
+            __syncthreads();
+            F.node0 = b; F.pos0 = seg_s; F.node1 = V.tid[seg_e]; F.pos1 = seg_e;
+            if (t == 0) { V.pos[F.node0] = F.pos0; V.pos[F.node1] = F.pos1; }
+        }
+        // kbest == KEY_EMPTY was read behind a barrier: every thread is here, the tour is final
+        const long long fc = s_cost;
+        if (t == 0) { final_cost[cur] = fc; moves_out[cur] = moves; }
+        const bool better = s_bestcost < 0 || fc < s_bestcost;            // strict '<', ascending starts per CTA
+        if (better)
+            for (int p = t; p < n; p += BLK) best_path[V.tid[p]] = V.tid[p + 1];
+        __syncthreads();
+        if (better && t == 0) {
+            s_bestcost = fc;
+            S.best_cost[slot] = fc;
+            S.best_start[slot] = first_start + cur * stride;
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) ncand += __shfl_down_sync(FULL, ncand, off);
+    if (lane == 0 && ncand) atomicAdd(cand_total, (unsigned long long)ncand);
 }
 
 }  // namespace tspcuda

@@ -792,14 +792,41 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
     if (nstarts <= 0 || stride <= 0) return fail(TSPCUDA_INVALID_ARGUMENT, "nstarts/stride");
     const long long last = (long long)first_start + (long long)(nstarts - 1) * stride;
     if (first_start < 0 || last >= n) return fail(TSPCUDA_UNAVAILABLE, "starting node not correct");
-    const bool cta_path = n >= 4 && n <= CTA_MAX_N;       // whole tour fits one CTA's shared memory
-    const int batch = std::min(nstarts, (cta_path ? 16 : 8) * c->num_sms);
+    // K8 (one CTA per descent, pruned scan, any n) when there are enough starts to occupy the SMs;
+    // K6 (one CTA per descent, full scan, tour in shared memory) when every pair must be evaluated;
+    // otherwise the starts descend one after the other on the whole GPU (K2 / K7).
+    const bool multi_path = n >= 4 && c->pruned_blocks > 0 && c->scan_mode != TSPCUDA_SCAN_FULL && nstarts >= c->num_sms / 4;
+    const bool cta_path = !multi_path && n >= 4 && n <= CTA_MAX_N;       // whole tour fits one CTA's shared memory
+    const int batch = std::min(nstarts, ((cta_path || multi_path) ? 16 : 8) * c->num_sms);
     NNScratch S;
     e = nn_alloc(c, S, batch);
     if (e) return e;
     DevBuf best_path, next, dcost, dmoves, dpaths;
     CK(cudaMalloc(&best_path.p, sizeof(int) * n));
     std::vector<long long> hc(batch), hf(batch), hm(batch);
+    DevBuf m_pxy, m_tid, m_dn, m_pos, m_boxes, m_bpath, m_bcost, m_bstart, m_cand;
+    MultiSlots MS{};
+    const int mslots = multi_path ? std::min(batch, c->num_sms) : 0;
+    if (multi_path) {
+        const size_t n1 = (size_t)n + 1, sl = (size_t)mslots;
+        CK(cudaMalloc(&m_pxy.p, sizeof(double2) * n1 * sl));
+        CK(cudaMalloc(&m_tid.p, sizeof(int) * n1 * sl));
+        CK(cudaMalloc(&m_dn.p, sizeof(int) * n1 * sl));
+        CK(cudaMalloc(&m_pos.p, sizeof(int) * (size_t)n * sl));
+        CK(cudaMalloc(&m_boxes.p, sizeof(BigBox) * (size_t)n * sl));
+        CK(cudaMalloc(&m_bpath.p, sizeof(int) * (size_t)n * sl));
+        CK(cudaMalloc(&m_bcost.p, sizeof(long long) * sl));
+        CK(cudaMalloc(&m_bstart.p, sizeof(int) * sl));
+        CK(cudaMalloc(&m_cand.p, sizeof(unsigned long long)));
+        CK(cudaMalloc(&next.p, sizeof(int)));
+        CK(cudaMalloc(&dcost.p, sizeof(long long) * batch));
+        CK(cudaMalloc(&dmoves.p, sizeof(long long) * batch));
+        MS.pxy = m_pxy.as<double2>(); MS.tid = m_tid.as<int>(); MS.dn = m_dn.as<int>(); MS.pos = m_pos.as<int>();
+        MS.boxes = m_boxes.as<BigBox>(); MS.best_path = m_bpath.as<int>(); MS.best_cost = m_bcost.as<long long>();
+        MS.best_start = m_bstart.as<int>();
+    }
+    std::vector<long long> hbc(std::max(1, mslots));
+    std::vector<int> hbs(std::max(1, mslots));
     if (cta_path) {
         CK(cudaMalloc(&next.p, sizeof(int)));
         CK(cudaMalloc(&dcost.p, sizeof(long long) * batch));
@@ -813,6 +840,55 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
         const int fs = first_start + done * stride;
         e = nn_batch(c, S, fs, cnt, stride, hc.data());
         if (e) return e;
+        if (multi_path) {
+            CK(cudaMemsetAsync(next.p, 0, sizeof(int), c->stream));
+            CK(cudaMemsetAsync(m_cand.p, 0, sizeof(unsigned long long), c->stream));
+            CK(cudaEventRecord(c->ev0, c->stream));
+            const int g = std::min(cnt, mslots);
+            const char *kb = getenv("TSPCUDA_K8_BLOCK");
+            const int k8_block = kb ? atoi(kb) : 1024;
+            if (k8_block == 1024) {
+                DISPATCH_METRIC(c->metric, (multi_pruned_kernel<M, 1024><<<g, 1024, 0, c->stream>>>(
+                    c->d_xy, n, c->grid, S.order, fs, stride, cnt, next.as<int>(), MS, dcost.as<long long>(), dmoves.as<long long>(),
+                    m_cand.as<unsigned long long>())));
+            } else {
+                DISPATCH_METRIC(c->metric, (multi_pruned_kernel<M, PRUNED_BLOCK><<<g, PRUNED_BLOCK, 0, c->stream>>>(
+                    c->d_xy, n, c->grid, S.order, fs, stride, cnt, next.as<int>(), MS, dcost.as<long long>(), dmoves.as<long long>(),
+                    m_cand.as<unsigned long long>())));
+            }
+            CK(cudaGetLastError());
+            CK(cudaEventRecord(c->ev1, c->stream));
+            c->stats.kernel_launches += 1;
+            unsigned long long hcand = 0;
+            CK(cudaMemcpyAsync(hf.data(), dcost.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(hm.data(), dmoves.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(hbc.data(), m_bcost.p, sizeof(long long) * g, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(hbs.data(), m_bstart.p, sizeof(int) * g, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(&hcand, m_cand.p, sizeof(hcand), cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaStreamSynchronize(c->stream));
+            c->stats.d2h_bytes += (int64_t)sizeof(long long) * 2 * cnt + 12 * g + 8;
+            float ms = 0;
+            CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+            c->stats.pruned_kernel_ms += ms;
+            c->stats.last_kernel_ms = ms;
+            c->stats.candidate_evals += (int64_t)hcand;
+            for (int k = 0; k < cnt; k++) {
+                c->stats.moves += hm[k];
+                c->stats.scans += hm[k] + 1;
+                c->stats.pruned_scans += hm[k] + 1;
+                if (nn_costs_out) nn_costs_out[done + k] = (double)hc[k];
+                if (final_costs_out) final_costs_out[done + k] = (double)hf[k];
+                if (moves_out) moves_out[done + k] = hm[k];
+            }
+            int bslot = -1;                                  // (cost, start)-minimum over the CTAs' own bests
+            for (int q = 0; q < g; q++) {
+                if (hbs[q] < 0) continue;
+                if (best_start < 0 || hbc[q] < best || (hbc[q] == best && hbs[q] < best_start)) { best = hbc[q]; best_start = hbs[q]; bslot = q; }
+            }
+            if (bslot >= 0)
+                CK(cudaMemcpyAsync(best_path.p, MS.best_path + (size_t)bslot * n, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
+            continue;
+        }
         if (cta_path) {
             // K6: every start of the batch descends inside one CTA, no grid barrier per move
             CK(cudaMemsetAsync(next.p, 0, sizeof(int), c->stream));
