@@ -13,3 +13,7 @@ $SHORT > gpurun_out/short_plain2.json 2> gpurun_out/short_plain2.err &&
 ncu --set full --clock-control none --import-source on -k regex:descend_kernel -s 3 -c 2 -o gpurun_out/prof_descend $SHORT > gpurun_out/ncu_full.log 2>&1
 tail -5 gpurun_out/ncu_full.log
 ls -la gpurun_out
+# K7 (pruned descent): one --set full capture of a mid-descent launch
+python scripts/pruned_time.py pla85900 > gpurun_out/pruned_plain.log 2>&1 &&
+ncu --set full --clock-control none --import-source on -k regex:descend_pruned_kernel -s 2 -c 1 -o gpurun_out/prof_pruned python scripts/pruned_time.py pla85900 > gpurun_out/ncu_pruned.log 2>&1
+tail -3 gpurun_out/ncu_pruned.log
