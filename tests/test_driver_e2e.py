@@ -18,9 +18,9 @@ TSP_GPU = os.path.join(ROOT, "build", "bin", "tsp")
 TSP_REF = os.path.join(ROOT, "oracle", "_ref", "tsp_ref")
 
 
-def write_tsplib(path, name, xy):
+def write_tsplib(path, name, xy, ewt="EUC_2D"):
     with open(path, "w") as f:
-        f.write("NAME : %s\nTYPE : TSP\nDIMENSION : %d\nEDGE_WEIGHT_TYPE : EUC_2D\nNODE_COORD_SECTION\n" % (name, xy.shape[0]))
+        f.write("NAME : %s\nTYPE : TSP\nDIMENSION : %d\nEDGE_WEIGHT_TYPE : %s\nNODE_COORD_SECTION\n" % (name, xy.shape[0], ewt))
         for i, (x, y) in enumerate(xy):
             f.write("%d %s %s\n" % (i + 1, repr(float(x)), repr(float(y))))   # repr round-trips through atof
         f.write("EOF\n")
@@ -33,6 +33,9 @@ def workdir(tmp_path_factory):
     for name in ["berlin52", "kroA100", "rl1304", "usa13509"]:
         xy, _ = load_instance(name)
         write_tsplib(d / (name + ".tsp"), name, xy)
+    for name in ["att48", "att532", "dsj1000", "burma14"]:       # ATT, ATT, CEIL_2D, GEO headers
+        xy, ewt = load_instance(name)
+        write_tsplib(d / (name + ".tsp"), name, xy, ewt)
     return d
 
 
@@ -136,3 +139,30 @@ def test_usa13509_cli(workdir, golden):
     """Config-3 instance through the CLI: 1.46 GB host matrix filled from the device, NN on the device."""
     r = run_cli(TSP_GPU, workdir, ["-f", "usa13509.tsp", "-q", "-alg", "GREEDY"])
     assert r.stdout.strip() == "Cost: %d.00" % golden["usa13509"]["nn0"]["cost"]
+
+
+@pytest.mark.gpu
+def test_reader_extension_att_and_ceil2d(workdir, oracle):
+    """the interposed tsp_read_input accepts CEIL_2D and ATT files (the reference
+    stops at tsp.c:576-583).  No reference behaviour exists: expected values come from the TSPLIB95
+    restatement in the oracle ("parity unpinned")."""
+    from oracle.bindings import ATT, CEIL_2D, EUC_REF
+    for name, wt, alg in (("att48", ATT, "2OPT_GREEDY"), ("att532", ATT, "GREEDY_ITER"), ("dsj1000", CEIL_2D, "GREEDY")):
+        xy, ewt = load_instance(name)
+        n = xy.shape[0]
+        if alg == "GREEDY":
+            expect = oracle.nn(xy, 0, wt)[2]
+        elif alg == "GREEDY_ITER":
+            expect = min(oracle.nn(xy, s, wt)[2] for s in range(n))
+        else:
+            expect = min(oracle.two_opt(xy, oracle.nn(xy, s, wt)[1], wt, log=False)[2] for s in range(n))
+        r = run_cli(TSP_GPU, workdir, ["-f", name + ".tsp", "-q", "-alg", alg])
+        assert r.stdout.strip() == "Cost: %.2f" % expect, (name, alg)
+        assert calls(r.stderr)["tsp_read_input"] == 1
+    # TSPCUDA_WEIGHT=ref: the reference's own rule (tsp.c:629) on a CEIL_2D file -- how bench.py treats pla85900
+    xy, _ = load_instance("dsj1000")
+    r = run_cli(TSP_GPU, workdir, ["-f", "dsj1000.tsp", "-q", "-alg", "GREEDY"], {"TSPCUDA_WEIGHT": "ref"})
+    assert r.stdout.strip() == "Cost: %.2f" % oracle.nn(xy, 0, EUC_REF)[2]
+    # GEO is not implemented on the device: rejected the way the reference rejects it, no result
+    r = run_cli(TSP_GPU, workdir, ["-f", "burma14.tsp", "-q", "-alg", "GREEDY"], check=False)
+    assert "Cost:" not in r.stdout
