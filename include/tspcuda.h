@@ -47,7 +47,7 @@ enum {
 
 /* Edge-weight rule.  Only EUC_REF exists in the reference (tsp.c:629: float sqrt, round half up);
  * the others follow TSPLIB95 and have no reference behaviour ("parity unpinned"). */
-enum { TSPCUDA_EUC_REF = 0, TSPCUDA_CEIL_2D = 1, TSPCUDA_ATT = 2 };
+enum { TSPCUDA_EUC_REF = 0, TSPCUDA_CEIL_2D = 1, TSPCUDA_ATT = 2, TSPCUDA_GEO = 3 };
 
 #define TSPCUDA_MAX_NODES 131072      /* 17-bit node ids in the packed (delta,a,b) argmin key */
 

@@ -142,7 +142,7 @@ def test_usa13509_cli(workdir, golden):
 
 
 @pytest.mark.gpu
-def test_reader_extension_att_and_ceil2d(workdir, oracle):
+def test_reader_extension_att_ceil2d_geo(workdir, oracle):
     """the interposed tsp_read_input accepts CEIL_2D and ATT files (the reference
     stops at tsp.c:576-583).  No reference behaviour exists: expected values come from the TSPLIB95
     restatement in the oracle ("parity unpinned")."""
@@ -163,6 +163,14 @@ def test_reader_extension_att_and_ceil2d(workdir, oracle):
     xy, _ = load_instance("dsj1000")
     r = run_cli(TSP_GPU, workdir, ["-f", "dsj1000.tsp", "-q", "-alg", "GREEDY"], {"TSPCUDA_WEIGHT": "ref"})
     assert r.stdout.strip() == "Cost: %.2f" % oracle.nn(xy, 0, EUC_REF)[2]
-    # GEO is not implemented on the device: rejected the way the reference rejects it, no result
-    r = run_cli(TSP_GPU, workdir, ["-f", "burma14.tsp", "-q", "-alg", "GREEDY"], check=False)
+    # GEO (burma14): all-start NN + 2-opt
+    from oracle.bindings import GEO
+    xy, _ = load_instance("burma14")
+    expect = min(oracle.two_opt(xy, oracle.nn(xy, s, GEO)[1], GEO, log=False)[2] for s in range(xy.shape[0]))
+    r = run_cli(TSP_GPU, workdir, ["-f", "burma14.tsp", "-q", "-alg", "2OPT_GREEDY"])
+    assert r.stdout.strip() == "Cost: %.2f" % expect
+    # an EXPLICIT-matrix file is rejected the way the reference rejects a foreign type: no result
+    with open(workdir / "explicit.tsp", "w") as f:
+        f.write("NAME : x\nTYPE : TSP\nDIMENSION : 3\nEDGE_WEIGHT_TYPE : EXPLICIT\nEDGE_WEIGHT_SECTION\n0 1 2\n1 0 3\n2 3 0\nEOF\n")
+    r = run_cli(TSP_GPU, workdir, ["-f", "explicit.tsp", "-q", "-alg", "GREEDY"], check=False)
     assert "Cost:" not in r.stdout

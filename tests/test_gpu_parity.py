@@ -6,7 +6,7 @@ logs (a, b, delta), cost equal (integer-valued doubles; 1e-9 relative is trivial
 import numpy as np
 import pytest
 
-from oracle.bindings import ATT, CEIL_2D, EUC_REF, fnv1a, load_instance
+from oracle.bindings import ATT, CEIL_2D, EUC_REF, GEO, fnv1a, load_instance
 
 pytestmark = pytest.mark.gpu
 
@@ -394,6 +394,32 @@ def test_ceil2d_and_att(tsp, oracle):
         m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, po, ATT)
         code, moves, p2, c2, log = I.two_opt(po, log_cap=len(la) + 4)
         assert log == _log3(la, lb, ld) and np.array_equal(p2, p_o) and c2 == c_o
+
+
+@pytest.mark.parametrize("name", ["burma14", "ulysses16", "gr666"])
+def test_geo(tsp, oracle, name):
+    """TSPLIB95 GEO on the device (cos/acos from CUDA's libdevice) against the oracle (glibc): cost
+    matrix, NN, descent, all-start multi-start; gr666's canonical tour 1..n costs 423710 (TSPLIB95 KAT).
+    Parity unpinned: the reference rejects GEO files (tsp.c:576-583)."""
+    xy, ewt = load_instance(name)
+    assert ewt == "GEO"
+    n = xy.shape[0]
+    with tsp.Instance(xy, tsp.GEO) as I:
+        assert np.array_equal(I.cost_matrix(), oracle.cost_matrix(xy, GEO))
+        e, po, co = oracle.nn(xy, 0, GEO)
+        code, p, c = I.nn(0)
+        assert np.array_equal(p, po) and c == co
+        m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, po, GEO)
+        code, moves, p2, c2, log = I.two_opt(p, log_cap=len(la) + 4)
+        assert log == _log3(la, lb, ld) and np.array_equal(p2, p_o) and c2 == c_o
+        if name == "gr666":
+            canon = np.roll(np.arange(n, dtype=np.int32), -1)
+            code, mv, pc, cc, _ = I.two_opt(canon, max_moves=0)
+            assert cc == 423710.0
+        else:
+            bs, bp, bc, nn_costs, final, mvs = I.multistart_two_opt(0, n)
+            per = [oracle.two_opt(xy, oracle.nn(xy, s, GEO)[1], GEO, log=False) for s in range(n)]
+            assert [int(f) for f in final] == [int(r[2]) for r in per]
 
 
 # ---- multi-start (h_greedy_2opt, heuristics.c:74-116) -----------------------------------------

@@ -15,9 +15,9 @@ import numpy as np
 
 from .build import LIB, build
 
-EUC_REF, CEIL_2D, ATT = 0, 1, 2
+EUC_REF, CEIL_2D, ATT, GEO = 0, 1, 2, 3
 SCAN_AUTO, SCAN_FULL, SCAN_PRUNED = 0, 1, 2
-WT_BY_NAME = {"EUC_2D": EUC_REF, "EUC_REF": EUC_REF, "CEIL_2D": CEIL_2D, "ATT": ATT}
+WT_BY_NAME = {"EUC_2D": EUC_REF, "EUC_REF": EUC_REF, "CEIL_2D": CEIL_2D, "ATT": ATT, "GEO": GEO}
 ERROR_NAMES = {0: "T_OK", 1: "CANCELLED", 3: "INVALID_ARGUMENT", 4: "DEADLINE_EXCEEDED", 8: "RESOURCE_EXHAUSTED",
                11: "OUT_OF_RANGE", 12: "UNIMPLEMENTED", 13: "INTERNAL", 14: "UNAVAILABLE"}
 OK, DEADLINE_EXCEEDED, INVALID_ARGUMENT, OUT_OF_RANGE, UNAVAILABLE = 0, 4, 3, 11, 14

@@ -21,7 +21,7 @@
  *   mh_TabuSearch       metaheuristic.c:86  (whole-loop override: the k tabu iterations run in one
  *                       device-resident call; TSPCUDA_BATCH=0 keeps the reference's loop, which then
  *                       calls the interposed tabu_best_move once per iteration)
- *   tsp_read_input      tsp.c:527  (EXTENSION: same grammar, additionally accepts CEIL_2D and ATT files)
+ *   tsp_read_input      tsp.c:527  (EXTENSION: same grammar, additionally accepts CEIL_2D, ATT and GEO files)
  * ref_reverse_path (refinment.c:95) keeps the reference's definition: once ref_2opt_once and
  * tabu_best_move run on the device nothing on this path calls it.
  *
@@ -127,7 +127,7 @@ static bool batch_enabled(void) {
  * of the instances it ships in data/ -- pla85900, the headline instance, among them.  This reader
  * accepts the same file grammar (keyword lines split at blanks and ':', node lines "index x y" split
  * at blanks, ':' and ','; index = atoi - 1; values through atof; stops at EOF) and additionally the
- * types the device implements: CEIL_2D and ATT (TSPLIB95 rules -- NO reference behaviour exists for
+ * types the device implements: CEIL_2D, ATT and GEO (TSPLIB95 rules -- NO reference behaviour exists for
  * them, "parity unpinned").  TSPCUDA_WEIGHT=ref keeps the reference's own cost rule (tsp.c:629)
  * whatever the header says (how bench.py treats pla85900).  Everything else is rejected the way the
  * reference rejects it (log_fatal + tsp_handlefatal). */
@@ -137,6 +137,7 @@ static int weight_type_of(const char *tok) {
     if (strncmp(tok, "EUC_2D", 6) == 0) return TSPCUDA_EUC_REF;
     if (strncmp(tok, "CEIL_2D", 7) == 0) return forced_ref ? TSPCUDA_EUC_REF : TSPCUDA_CEIL_2D;
     if (strncmp(tok, "ATT", 3) == 0) return forced_ref ? TSPCUDA_EUC_REF : TSPCUDA_ATT;
+    if (strncmp(tok, "GEO", 3) == 0) return forced_ref ? TSPCUDA_EUC_REF : TSPCUDA_GEO;
     return -1;
 }
 
@@ -173,7 +174,7 @@ void tsp_read_input(void) {
             char *v = strtok(NULL, " :");
             int wt = v ? weight_type_of(v) : -1;
             if (wt < 0) {
-                log_fatal(" format error:  only EDGE_WEIGHT_TYPE == EUC_2D, CEIL_2D, ATT managed");
+                log_fatal(" format error:  only EDGE_WEIGHT_TYPE == EUC_2D, CEIL_2D, ATT, GEO managed");
                 tsp_handlefatal();
             }
             g_weight_type = wt;

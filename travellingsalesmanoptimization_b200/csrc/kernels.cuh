@@ -501,6 +501,14 @@ descend_cta_kernel(const double2 *__restrict__ xy, int n, const int *__restrict_
 // ---------------------------------------------------------------------------------------------
 // Tour set-up / export kernels.
 // ---------------------------------------------------------------------------------------------
+// GEO instances: DDD.MM (latitude, longitude) -> radians, in place, once per instance.
+__global__ void geo_convert_kernel(double2 *xy, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const double2 p = xy[i];
+        xy[i] = make_double2(geo_radians(p.x), geo_radians(p.y));
+    }
+}
+
 // order[p] = node at position p (host walked the successor array).  Fills pxy, tid, pos.
 __global__ void tour_init_kernel(TourView V, const double2 *xy, const int *order) {
     const int n = V.n;

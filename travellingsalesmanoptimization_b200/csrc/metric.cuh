@@ -104,6 +104,28 @@ struct Att {
     static __device__ __forceinline__ double radius(double r) { return (r + 1.0) * 3.1622777 + 1.0; }
 };
 
+// TSPLIB95 GEO (section 2.4).  The node "coordinates" this functor sees are (latitude, longitude) in
+// radians, converted once per instance by geo_convert_kernel with the TSPLIB constants (PI = 3.141592,
+// DDD.MM input).  Same operation order as the definition, no FMA contraction; cos/acos are CUDA's
+// double-precision routines (<= 2 ulp), so a cost can differ from a libm evaluation only where
+// RRR*acos(.)+1 lies within ~1e-8 of an integer.  Parity unpinned (the reference has no GEO rule).
+struct Geo {
+    static __device__ __forceinline__ int K(double lati, double loni, double latj, double lonj) {
+        const double q1 = cos(__dsub_rn(loni, lonj));
+        const double q2 = cos(__dsub_rn(lati, latj));
+        const double q3 = cos(__dadd_rn(lati, latj));
+        const double f = __dmul_rn(0.5, __dsub_rn(__dmul_rn(__dadd_rn(1.0, q1), q2), __dmul_rn(__dsub_rn(1.0, q1), q3)));
+        return KOFF + (int)__dadd_rn(__dmul_rn(6378.388, acos(f)), 1.0);
+    }
+    static __device__ __forceinline__ double radius(double r) { return r; }     // unused: no pruned scan for GEO
+};
+
+__device__ __forceinline__ double geo_radians(double v) {
+    const double deg = (double)(long long)v;                  // truncation toward zero
+    const double min = __dsub_rn(v, deg);
+    return __ddiv_rn(__dmul_rn(3.141592, __dadd_rn(deg, __ddiv_rn(__dmul_rn(5.0, min), 3.0))), 180.0);
+}
+
 __device__ __forceinline__ unsigned long long pack_key(int delta, int u, int v) {
     unsigned lo = (unsigned)min(u, v), hi = (unsigned)max(u, v);
     return ((unsigned long long)(unsigned)(delta + DELTA_BIAS) << 34) | ((unsigned long long)lo << 17) |

@@ -38,13 +38,14 @@ static int fail(int code, const char *fmt, ...) {
                         "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__);   \
     } while (0)
 
-enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3 };
+enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3, M_GEO = 4 };
 
 #define DISPATCH_METRIC(mid, EXPR)                                        \
     switch (mid) {                                                        \
         case M_EUC_GENERAL: { using M = EucGeneral; EXPR; } break;        \
         case M_EUC_INTEGER: { using M = EucInt; EXPR; } break;            \
         case M_CEIL: { using M = Ceil2D; EXPR; } break;                   \
+        case M_GEO: { using M = Geo; EXPR; } break;                       \
         default: { using M = Att; EXPR; } break;                          \
     }
 
@@ -132,7 +133,7 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
     *out = nullptr;
     if (n <= 0) return fail(TSPCUDA_INVALID_ARGUMENT, "n = %d", n);
     if (n > TSPCUDA_MAX_NODES) return fail(TSPCUDA_OUT_OF_RANGE, "n = %d exceeds %d (17-bit node ids in the packed key)", n, TSPCUDA_MAX_NODES);
-    if (weight_type < TSPCUDA_EUC_REF || weight_type > TSPCUDA_ATT) return fail(TSPCUDA_UNIMPLEMENTED, "weight type %d", weight_type);
+    if (weight_type < TSPCUDA_EUC_REF || weight_type > TSPCUDA_GEO) return fail(TSPCUDA_UNIMPLEMENTED, "weight type %d", weight_type);
     int ndev = tspcuda_device_count();
     if (ndev <= 0) return fail(TSPCUDA_UNAVAILABLE, "no CUDA device: libtspcuda has no CPU fallback");
     if (device < 0 || device >= ndev) return fail(TSPCUDA_INVALID_ARGUMENT, "device %d of %d", device, ndev);
@@ -146,12 +147,13 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         xmin = std::min(xmin, x); xmax = std::max(xmax, x); ymin = std::min(ymin, y); ymax = std::max(ymax, y);
     }
     const double diag = std::sqrt((xmax - xmin) * (xmax - xmin) + (ymax - ymin) * (ymax - ymin));
-    if (diag >= 8388000.0)
+    if (diag >= 8388000.0 && weight_type != TSPCUDA_GEO)
         return fail(TSPCUDA_OUT_OF_RANGE, "bounding-box diagonal %.0f: edge costs must stay below 2^23 for the K-offset encoding", diag);
 
     tspcuda_ctx *c = new tspcuda_ctx();
     c->n = n; c->wt = weight_type; c->device = device;
-    c->metric = weight_type == TSPCUDA_EUC_REF ? (integer ? M_EUC_INTEGER : M_EUC_GENERAL) : (weight_type == TSPCUDA_CEIL_2D ? M_CEIL : M_ATT);
+    c->metric = weight_type == TSPCUDA_EUC_REF ? (integer ? M_EUC_INTEGER : M_EUC_GENERAL)
+                : (weight_type == TSPCUDA_CEIL_2D ? M_CEIL : (weight_type == TSPCUDA_ATT ? M_ATT : M_GEO));
     if (const char *force = getenv("TSPCUDA_FORCE_METRIC")) {     // test hook: a SLOWER exact variant of the same rule
         if (weight_type == TSPCUDA_EUC_REF) {
             if (!strcmp(force, "general")) c->metric = M_EUC_GENERAL;
@@ -202,6 +204,11 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
     CKC(cudaMallocHost(&c->h_state, sizeof(DescState)));
     CKC(cudaMallocHost(&c->h_buf, sizeof(int) * n));
     CKC(cudaMemcpyAsync(c->d_xy, xy, sizeof(double2) * n, cudaMemcpyHostToDevice, c->stream));
+    if (c->metric == M_GEO) {
+        geo_convert_kernel<<<std::max(1, std::min(4 * c->num_sms, (n + 255) / 256)), 256, 0, c->stream>>>(c->d_xy, n);
+        c->stats.kernel_launches += 1;
+        CKC(cudaGetLastError());
+    }
     CKC(cudaStreamSynchronize(c->stream));
     c->stats.h2d_bytes += (int64_t)sizeof(double2) * n;
     const double pairs = 0.5 * (double)n * (double)(n - 1);
@@ -244,7 +251,7 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         int pb = 0;
         if (c->pruned_block == PRUNED_BLOCK) { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, PRUNED_BLOCK>, PRUNED_BLOCK, 0))); }
         else { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, 1024>, 1024, 0))); }
-        c->pruned_blocks = pb > 0 ? c->num_sms : 0;
+        c->pruned_blocks = (pb > 0 && c->metric != M_GEO) ? c->num_sms : 0;     // the grid search is Euclidean
     }
     *out = c;
     return TSPCUDA_OK;
