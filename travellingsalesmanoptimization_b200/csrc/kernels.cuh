@@ -564,21 +564,44 @@ __device__ __forceinline__ double cost_as_double(int koff) {
     return __hiloint2double(0x43300000, koff - KOFF) - 4503599627370496.0;
 }
 
+#ifndef TSP_K1_UNROLL
+#define TSP_K1_UNROLL 1
+#endif
+#ifndef TSP_K1_STREAM
+#define TSP_K1_STREAM 1
+#endif
 template <class M>
 __global__ void __launch_bounds__(256)
 cost_matrix_kernel(const double2 *__restrict__ xy, int n, double *__restrict__ out) {
+    constexpr int U = TSP_K1_UNROLL;              // independent 16-byte stores in flight per thread
     for (int i = blockIdx.x; i < n; i += gridDim.x) {
         const double2 pi = xy[i];
         const size_t base = (size_t)i * (size_t)n;
         const int off = (int)(base & 1);            // first cell of the row that is 16-byte aligned
         double *row = out + base;
         const int npairs = (n - off) >> 1;
-        for (int t = threadIdx.x; t < npairs; t += blockDim.x) {
-            const int j = off + 2 * t;
-            const double2 p0 = xy[j], p1 = xy[j + 1];
-            const double v0 = (j == i) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p0.x, p0.y));
-            const double v1 = (j + 1 == i) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p1.x, p1.y));
-            *reinterpret_cast<double2 *>(row + j) = make_double2(v0, v1);
+        for (int t0 = threadIdx.x; t0 < npairs; t0 += blockDim.x * U) {
+            double2 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = min(t0 + u * (int)blockDim.x, npairs - 1);
+                const int j = off + 2 * t;
+                const double2 p0 = xy[j], p1 = xy[j + 1];
+                v[u].x = (j == i) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p0.x, p0.y));
+                v[u].y = (j + 1 == i) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p1.x, p1.y));
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = t0 + u * (int)blockDim.x;
+                if (t < npairs) {
+                    double2 *dst = reinterpret_cast<double2 *>(row + off + 2 * t);
+#if TSP_K1_STREAM
+                    __stcs(dst, v[u]);             // written once, never re-read by this kernel: streaming store
+#else
+                    *dst = v[u];
+#endif
+                }
+            }
         }
         if (threadIdx.x == 0) {
             if (off) { const double2 p = xy[0]; row[0] = (i == 0) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p.x, p.y)); }
