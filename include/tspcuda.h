@@ -18,6 +18,7 @@
  *   tspcuda_tabu_move             tabu_best_move               algorithms/metaheuristic.c:188-245
  *   tspcuda_tabu_search           mh_TabuSearch inner loop     algorithms/metaheuristic.c:128-164
  *   tspcuda_multistart_two_opt    h_greedy_2opt loop           algorithms/heuristics.c:74-116
+ *   tspcuda_mx_nn / _two_opt      h_greedyutil / ref_2opt on a caller's matrix (h_Greedy_2opt_mod_costs, heuristics.c:118-149)
  *
  * Tours cross the boundary exactly as the reference stores them: a successor array int path[n],
  * path[i] = node visited after node i (src/utils/utils.h:42-47).  Costs are doubles holding
@@ -158,6 +159,27 @@ int tspcuda_tour_movelog(tspcuda_ctx *ctx, tspcuda_move *log, int64_t cap, int64
 int tspcuda_multistart_two_opt(tspcuda_ctx *ctx, int first_start, int nstarts, int stride, double *nn_costs_out,
                                double *final_costs_out, int64_t *moves_out, int *best_start_out,
                                int *best_path_out, double *best_cost_out);
+
+/* ---- the `costs`-argument paths: a caller-supplied dense matrix ------------------------------- */
+/* h_greedyutil / ref_2opt / ref_2opt_once called with a matrix other than the instance's own
+ * (heuristics.c:216, refinment.c:3,39), and through them h_Greedy_2opt_mod_costs (heuristics.c:118-149,
+ * the x*-weighted matrices of the CPLEX relaxation callback, cplex_model.c:1187-1217).  The matrix
+ * (row-major n*n doubles, any values; -1.0 = NOT_CONNECTED for the NN step, heuristics.c:257) is
+ * copied to the device once per context.  Deltas are FP64 in the reference's expression order
+ * (refinment.c:60-62); tours and costs are bit-identical to the reference's. */
+typedef struct tspcuda_mx tspcuda_mx;
+typedef struct {
+    int32_t a, b;
+    double delta;
+} tspcuda_move_f;
+int tspcuda_mx_create(tspcuda_mx **out, const double *costs, int n, int device);
+void tspcuda_mx_destroy(tspcuda_mx *mx);
+int tspcuda_mx_get_stats(tspcuda_mx *mx, tspcuda_stats *out);
+/* *len_out (may be NULL): nodes reached; < n when NOT_CONNECTED entries close the path early. */
+int tspcuda_mx_nn(tspcuda_mx *mx, int start, int *path_out, double *cost_out, int *len_out);
+int tspcuda_mx_two_opt(tspcuda_mx *mx, int *path, double *cost_out, int64_t max_moves, double time_limit_s,
+                       int64_t *moves_out, tspcuda_move_f *log, int64_t log_cap);
+int tspcuda_mx_two_opt_once(tspcuda_mx *mx, int *path, double *cost_inout, double *best_delta_out);
 
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* CUDA-event bracket on the stream every kernel of this context is launched on (torch.cuda.Event

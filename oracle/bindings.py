@@ -79,6 +79,8 @@ class Oracle:
         L.orc_two_opt.argtypes = [_dp, C.c_int, C.c_int, _ip, _dp, C.c_long, _ip, _ip, _dp]
         L.orc_two_opt_matrix.restype = C.c_long
         L.orc_two_opt_matrix.argtypes = [_dp, C.c_int, _ip, _dp, C.c_long, _ip, _ip, _dp]
+        L.orc_nn_matrix.argtypes = [_dp, C.c_int, C.c_int, _ip, _dp]
+        L.orc_mod_costs.argtypes = [_dp, C.c_int, _ip, _dp]
         L.orc_tabu_move.argtypes = [_dp, C.c_int, C.c_int, _ip, _dp, _ip, C.c_int, C.c_int, _ip, _ip, _dp]
         L.orc_tabu_init.argtypes = [C.c_int, _ip, _ip, _ip]
         L.orc_tabu_linear_step.argtypes = [_ip, C.c_int, C.c_int, _ip]
@@ -181,6 +183,22 @@ class Oracle:
         m = self.L.orc_two_opt_matrix(_d(costs), n, _i(path), C.byref(cost), cap, _i(la), _i(lb), _d(ld))
         return m, path, cost.value, la[:m], lb[:m], ld[:m]
 
+    def nn_matrix(self, costs, start):
+        """h_greedyutil on an explicit matrix: (code, path, cost)."""
+        n = costs.shape[0]
+        path = np.full(n, -7, dtype=np.int32)
+        c = C.c_double(0)
+        e = self.L.orc_nn_matrix(_d(costs), n, start, _i(path), C.byref(c))
+        return e, path, c.value
+
+    def mod_costs(self, costs):
+        """h_Greedy_2opt_mod_costs (no time limit): (path, cost) = the last start's NN + 2-opt."""
+        n = costs.shape[0]
+        path = np.full(n, -7, dtype=np.int32)
+        c = C.c_double(0)
+        self.L.orc_mod_costs(_d(costs), n, _i(path), C.byref(c))
+        return path, c.value
+
     def tabu_move(self, xy, path, cost, tabu_list, tenure, it, wt=EUC_REF):
         """In-place on path / tabu_list (int32 arrays). Returns (new cost, a, b, delta)."""
         c = C.c_double(cost)
@@ -243,6 +261,9 @@ class Reference:
         L.refapi_two_opt.argtypes = [_ip, _dp, C.c_int, _ip, _ip, _dp]
         L.refapi_ref_2opt.argtypes = [_ip, _dp, C.c_int]
         L.refapi_tabu_move.argtypes = [_ip, _dp, _ip, C.c_int, C.c_int]
+        L.refapi_nn_costs.argtypes = [C.c_int, _dp, _ip, _dp]
+        L.refapi_ref_2opt_costs.argtypes = [_dp, _ip, _dp]
+        L.refapi_mod_costs.argtypes = [_dp, _ip, _dp]
         L.refapi_tabu_init.argtypes = [C.c_int, _ip, _ip, _ip]
         L.refapi_tabu_linear_step.argtypes = [_ip, C.c_int, C.c_int, _ip]
         L.refapi_vns_kick.argtypes = [_ip]
@@ -288,6 +309,24 @@ class Reference:
         c = C.c_double(0)
         m = self.L.refapi_two_opt(_i(path), C.byref(c), cap if max_moves < 0 else max_moves, _i(la), _i(lb), _d(ld))
         return m, path, c.value, la[:m], lb[:m], ld[:m]
+
+    def nn_costs(self, costs, start):
+        path = np.full(self.n, -7, dtype=np.int32)
+        c = C.c_double(0)
+        e = self.L.refapi_nn_costs(start, _d(costs), _i(path), C.byref(c))
+        return e, path, c.value
+
+    def ref_2opt_costs(self, costs, path):
+        path = np.array(path, dtype=np.int32, copy=True)
+        c = C.c_double(0)
+        e = self.L.refapi_ref_2opt_costs(_d(costs), _i(path), C.byref(c))
+        return e, path, c.value
+
+    def mod_costs(self, costs):
+        path = np.full(self.n, -7, dtype=np.int32)
+        c = C.c_double(0)
+        e = self.L.refapi_mod_costs(_d(costs), _i(path), C.byref(c))
+        return e, path, c.value
 
     def tabu_move(self, path, cost, tabu_list, tenure, it):
         c = C.c_double(cost)

@@ -399,6 +399,55 @@ long orc_two_opt(const double *xy, int n, int wt, int *path, double *cost, long 
     return moves;
 }
 
+/* heuristics.c:216-288 h_greedyutil over an explicit row-major matrix (the `costs` argument: the
+ * instance matrix or the fractional matrices of h_Greedy_2opt_mod_costs, heuristics.c:118-149).
+ * Entries equal to NOT_CONNECTED (-1.0) are skipped (:257); if no candidate is left the tour is
+ * closed to `start` (:268-271) -- early when every remaining entry is -1.0, as in the reference.
+ * The cost is accumulated in visit order, closing edge last (:277, :282). */
+int orc_nn_matrix(const double *c, int n, int start, int *path, double *cost) {
+    if (c == NULL) return ORC_INTERNAL;
+    if (start >= n || start < 0) return ORC_UNAVAILABLE;
+    size_t N = (size_t)n;
+    unsigned char *visited = (unsigned char *)calloc(N, 1);
+    int curr = start;
+    visited[curr] = 1;
+    double sol = 0;
+    for (;;) {
+        int min_idx = -1;
+        double min_dist = __DBL_MAX__;
+        const double *row = c + (size_t)curr * N;
+        for (int i = 0; i < n; i++) {
+            if (i != curr && !visited[i]) {
+                double t = row[i];
+                if (t != ORC_NOT_CONNECTED && t < min_dist) { min_dist = t; min_idx = i; }
+            }
+        }
+        path[curr] = min_idx;
+        if (min_idx == -1) { path[curr] = start; break; }
+        visited[min_idx] = 1;
+        curr = min_idx;
+        sol += min_dist;
+    }
+    sol += c[(size_t)curr * N + start];
+    *cost = sol;
+    free(visited);
+    return ORC_T_OK;
+}
+
+/* heuristics.c:118-149 h_Greedy_2opt_mod_costs without a time limit: every start in ascending order,
+ * NN + ref_2opt(update_incumbent = false) into the SAME solution struct, nothing kept between
+ * starts -- so what the caller receives is the result of the LAST start, n-1. */
+long orc_two_opt_matrix(const double *c, int n, int *path, double *cost, long max_moves, int *log_a, int *log_b, double *log_delta);
+int orc_mod_costs(const double *c, int n, int *path, double *cost) {
+    int e = ORC_T_OK;
+    for (int s = 0; s < n; s++) {
+        e = orc_nn_matrix(c, n, s, path, cost);
+        if (e != ORC_T_OK) continue;
+        orc_two_opt_matrix(c, n, path, cost, -1, NULL, NULL, NULL);
+    }
+    return ORC_T_OK;
+}
+
 long orc_two_opt_matrix(const double *c, int n, int *path, double *cost, long max_moves,
                         int *log_a, int *log_b, double *log_delta) {
     size_t N = (size_t)n;

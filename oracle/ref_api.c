@@ -144,6 +144,27 @@ int refapi_ref_2opt(int *path, double *cost, int update_incumbent) {
     return e;
 }
 
+/* The same helpers on a caller-supplied matrix (the `costs` argument of heuristics.c:216, refinment.c:3
+ * and heuristics.c:118): nnodes must have been set through refapi_set_points / refapi_random_points. */
+int refapi_nn_costs(int start, double *costs, int *path, double *cost) {
+    tsp_solution s; s.path = path; s.cost = __DBL_MAX__; s.ncomp = 0; s.comp = NULL;
+    int e = (int)h_greedyutil(start, &s, costs);
+    *cost = s.cost;
+    return e;
+}
+int refapi_ref_2opt_costs(double *costs, int *path, double *cost) {
+    tsp_solution s; s.path = path; s.cost = *cost; s.ncomp = 0; s.comp = NULL;
+    int e = (int)ref_2opt(&s, costs, 0);
+    *cost = s.cost;
+    return e;
+}
+int refapi_mod_costs(double *costs, int *path, double *cost) {
+    tsp_solution s; s.path = path; s.cost = __DBL_MAX__; s.ncomp = 0; s.comp = NULL;
+    int e = (int)h_Greedy_2opt_mod_costs(&s, costs);
+    *cost = s.cost;
+    return e;
+}
+
 int refapi_tabu_move(int *path, double *cost, int *tabu_list, int tenure, int iter) {
     tabu_search ts; memset(&ts, 0, sizeof(ts));
     ts.tenure = tenure; ts.tabu_list = tabu_list;

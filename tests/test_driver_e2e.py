@@ -174,3 +174,30 @@ def test_reader_extension_att_ceil2d_geo(workdir, oracle):
         f.write("NAME : x\nTYPE : TSP\nDIMENSION : 3\nEDGE_WEIGHT_TYPE : EXPLICIT\nEDGE_WEIGHT_SECTION\n0 1 2\n1 0 3\n2 3 0\nEOF\n")
     r = run_cli(TSP_GPU, workdir, ["-f", "explicit.tsp", "-q", "-alg", "GREEDY"], check=False)
     assert "Cost:" not in r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("batch", ["1", "0"])
+def test_mod_costs_through_the_reference_objects(workdir, batch):
+    """h_Greedy_2opt_mod_costs (heuristics.c:118-149; its only caller is the CPLEX relaxation callback,
+    which cannot run here) reached the way the callback reaches it: build/bin/harness_mod_costs is linked
+    like the drop-in CLI (interposer + libtspcuda ahead of the unmodified reference objects).
+    TSPCUDA_BATCH=1: the whole-loop override (computes the last start only); TSPCUDA_BATCH=0: the
+    reference's own loop over the interposed h_greedyutil / ref_2opt with the foreign matrix.  Both must
+    give the result the unmodified reference objects produced (golden_matrix.json)."""
+    import json
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from matrices import xstar_matrix
+    exe = os.path.join(ROOT, "build", "bin", "harness_mod_costs")
+    xstar_matrix(11, 64).tofile(workdir / "m64.f64")
+    r = run_cli(exe, workdir, ["64", "m64.f64"], {"TSPCUDA_BATCH": batch})
+    with open(os.path.join(ROOT, "tests", "golden", "golden_matrix.json")) as f:
+        g = json.load(f)["11_64"]["mod_costs"]
+    e, cost, h = r.stdout.split()
+    assert e == "0" and float.fromhex(cost).hex() == g["cost"] and h == g["hash"]
+    c = calls(r.stderr)
+    if batch == "0":
+        assert c["h_greedyutil"] == 64 and c["ref_2opt"] == 64
+    else:
+        assert c["h_greedyutil"] == 0 and c["ref_2opt"] == 0

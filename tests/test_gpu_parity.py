@@ -586,3 +586,56 @@ def test_auto_scan_mode_random_tour(tsp, oracle):
         st = I.stats()
     assert moves == m_o and c2 == c_o and log == _log3(la, lb, ld) and np.array_equal(p2, p_o)
     assert st["scans"] == moves + 1 and st["pruned_scans"] > 0
+
+
+# ---- the `costs`-argument paths: caller-supplied matrices (heuristics.c:118-149) -----------------
+def test_foreign_matrix_golden_gpu(tsp, oracle):
+    """tspcuda_mx_* against tests/golden/golden_matrix.json (unmodified reference objects on x*-weighted
+    fractional matrices): NN tours, 2-opt local optima and h_Greedy_2opt_mod_costs results; FP64 costs
+    must be bit-equal (hex floats) -- the final costs are ~1e-13 rounding residues of zero-cost tours."""
+    import json
+    import os
+    from matrices import xstar_matrix
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_matrix.json")) as f:
+        G = json.load(f)
+    for key, g in G.items():
+        M = xstar_matrix(g["seed"], g["n"])
+        with tsp.MatrixInstance(M) as I:
+            for r in g["per_start"]:
+                code, p, c, ln = I.nn(r["start"])
+                assert code == 0 and ln == g["n"] and c.hex() == r["nn_cost"] and fnv1a(p) == r["nn_hash"], (key, r["start"])
+                code, moves, p2, c2, _ = I.two_opt(p)
+                assert code == 0 and c2.hex() == r["opt_cost"] and fnv1a(p2) == r["opt_hash"], (key, r["start"])
+            pm, cm = I.mod_costs()
+            assert cm.hex() == g["mod_costs"]["cost"] and fnv1a(pm) == g["mod_costs"]["hash"], key
+
+
+@pytest.mark.parametrize("seed,n,symmetric,nc", [(21, 5, True, 0.0), (22, 33, True, 0.0), (23, 257, True, 0.0), (24, 1200, True, 0.0),
+                                                 (25, 180, False, 0.0), (26, 90, True, 0.03)])
+def test_foreign_matrix_vs_oracle(tsp, oracle, seed, n, symmetric, nc):
+    """Move-for-move against the oracle: log (a, b, FP64 delta), tour, cost; asymmetric matrices (the
+    entries are read at the reference's own indices; bounded number of moves, the descent has no
+    potential function there); NOT_CONNECTED entries in the NN step; ref_2opt_once stepping."""
+    from matrices import xstar_matrix
+    M = xstar_matrix(seed, n, symmetric, nc)
+    with tsp.MatrixInstance(M) as I:
+        for start in sorted({0, n // 2, n - 1}):
+            eo, po, co = oracle.nn_matrix(M, start)
+            code, p, c, ln = I.nn(start)
+            assert code == eo == 0 and c == co and np.array_equal(p, po), start
+        if nc > 0:
+            return
+        path = _rand_tour(seed, n)
+        cap = -1 if symmetric else 40
+        m_o, p_o, c_o, la, lb, ld = oracle.two_opt_matrix(M, path, max_moves=cap)
+        code, moves, p2, c2, log = I.two_opt(path, max_moves=cap, log_cap=len(la) + 8)
+        assert moves == m_o and c2 == c_o and np.array_equal(p2, p_o)
+        assert log == [(int(a), int(b), float(d)) for a, b, d in zip(la, lb, ld)]
+        # ref_2opt_once: one scan per call
+        ps, cs = path.copy(), oracle.two_opt_matrix(M, path, max_moves=0)[2]
+        for k in range(min(6, len(ld))):
+            d, cs = I.two_opt_once(ps, cs)
+            assert d == ld[k]
+        if symmetric:
+            d, c_end = I.two_opt_once(p2.copy(), c2)
+            assert d > -1e-7 and c_end == c2              # local optimum: nothing applied

@@ -144,3 +144,24 @@ def test_edge_cases(oracle):
     xy = np.array([[0.0, 0.0], [5.0, 5.0], [0.0, 0.0], [5.0, 5.0], [9.0, 1.0]])
     e, p, c = oracle.nn(xy, 0)
     assert p[0] == 2 and oracle.is_tour(p)
+
+
+def test_foreign_matrix_golden(oracle):
+    """Oracle restatement of the `costs`-argument paths against tests/golden/golden_matrix.json
+    (generated from the unmodified reference objects by make_golden_matrix.py): FP64 costs bit-equal
+    (hex floats), tours by hash."""
+    import json
+    import os
+    from matrices import xstar_matrix
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_matrix.json")) as f:
+        G = json.load(f)
+    for key, g in G.items():
+        M = xstar_matrix(g["seed"], g["n"])
+        for r in g["per_start"]:
+            e, p, c = oracle.nn_matrix(M, r["start"])
+            assert e == 0 and c.hex() == r["nn_cost"] and fnv1a(p) == r["nn_hash"], (key, r["start"])
+            m, p2, c2, *_ = oracle.two_opt_matrix(M, p)
+            assert c2.hex() == r["opt_cost"] and fnv1a(p2) == r["opt_hash"], (key, r["start"])
+        if g["n"] <= 333:                        # all-start loop: O(n) descents on the CPU
+            pm, cm = oracle.mod_costs(M)
+            assert cm.hex() == g["mod_costs"]["cost"] and fnv1a(pm) == g["mod_costs"]["hash"], key

@@ -105,3 +105,29 @@ def test_whole_algorithms_match_golden(reference, golden):
     assert (int(c), fnv1a(p), s) == (g["cost"], g["hash"], g["starting_node_field"])
     e, p, c, s = reference.run(3, 200)
     assert (int(c), fnv1a(p)) == (golden["berlin52"]["tabu_search_k200"]["cost"], golden["berlin52"]["tabu_search_k200"]["hash"])
+
+
+@pytest.mark.parametrize("seed,n,symmetric,nc", [(1, 40, True, 0.0), (2, 97, True, 0.0), (3, 60, False, 0.0), (4, 50, True, 0.02)])
+def test_foreign_matrix_paths(oracle, reference, seed, n, symmetric, nc):
+    """h_greedyutil / ref_2opt with a caller-supplied matrix and h_Greedy_2opt_mod_costs
+    (heuristics.c:118-149) on x*-weighted fractional matrices: tours and FP64 costs bit-equal."""
+    from matrices import xstar_matrix
+    M = xstar_matrix(seed, n, symmetric, nc)
+    reference.random_points(n, 1)                 # only sets nnodes; the matrix is the caller's
+    for start in (0, n // 2, n - 1):
+        er, pr, cr = reference.nn_costs(M, start)
+        eo, po, co = oracle.nn_matrix(M, start)
+        assert er == eo == 0 and cr == co and np.array_equal(pr, po), start
+        # with -1.0 entries NN may close early (not a tour); on an asymmetric matrix the reference's 2-opt
+        # has no potential function (reversed segments change direction) and need not terminate
+        if nc == 0.0 and symmetric:
+            e2, p2, c2 = reference.ref_2opt_costs(M, pr)
+            m, p3, c3, *_ = oracle.two_opt_matrix(M, po)
+            assert e2 == 0 and c2 == c3 and np.array_equal(p2, p3), start
+    if nc == 0.0 and symmetric:
+        e, pm, cm = reference.mod_costs(M)
+        po, co = oracle.mod_costs(M)
+        assert e == 0 and cm == co and np.array_equal(pm, po)
+        e1, p1, c1 = reference.nn_costs(M, n - 1)
+        e2, p2, c2 = reference.ref_2opt_costs(M, p1)
+        assert c2 == cm and np.array_equal(p2, pm)      # = the LAST start's result (nothing is kept between starts)

@@ -29,6 +29,8 @@ EXPORTS = [
     "tspcuda_tabu_move", "tspcuda_tour_upload", "tspcuda_tour_descend", "tspcuda_tour_download", "tspcuda_tour_movelog",
     "tspcuda_multistart_two_opt", "tspcuda_pipe_rate", "tspcuda_selfcheck_sqrt", "tspcuda_timer_start",
     "tspcuda_timer_stop", "tspcuda_flush_l2", "tspcuda_set_scan_mode", "tspcuda_tabu_search",
+    "tspcuda_mx_create", "tspcuda_mx_destroy", "tspcuda_mx_get_stats", "tspcuda_mx_nn", "tspcuda_mx_two_opt",
+    "tspcuda_mx_two_opt_once",
 ]
 
 
@@ -40,6 +42,10 @@ class TspCudaError(RuntimeError):
 
 class Move(C.Structure):
     _fields_ = [("a", C.c_int32), ("b", C.c_int32), ("delta", C.c_int32), ("reserved", C.c_int32)]
+
+
+class MoveF(C.Structure):
+    _fields_ = [("a", C.c_int32), ("b", C.c_int32), ("delta", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -93,6 +99,13 @@ def lib():
     L.tspcuda_timer_stop.argtypes = [_vp, _dp]
     L.tspcuda_flush_l2.argtypes = [_vp]
     L.tspcuda_set_scan_mode.argtypes = [_vp, C.c_int]
+    L.tspcuda_mx_create.argtypes = [C.POINTER(_vp), _dp, C.c_int, C.c_int]
+    L.tspcuda_mx_destroy.argtypes = [_vp]
+    L.tspcuda_mx_destroy.restype = None
+    L.tspcuda_mx_get_stats.argtypes = [_vp, C.POINTER(Stats)]
+    L.tspcuda_mx_nn.argtypes = [_vp, C.c_int, _ip, _dp, _ip]
+    L.tspcuda_mx_two_opt.argtypes = [_vp, _ip, _dp, C.c_int64, C.c_double, _i64p, C.POINTER(MoveF), C.c_int64]
+    L.tspcuda_mx_two_opt_once.argtypes = [_vp, _ip, _dp, _dp]
     L.tspcuda_tabu_search.argtypes = [_vp, _ip, _dp, _ip, _ip, C.c_int, C.c_int, C.c_double, _dp, _ip, _dp, _ip]
     _lib = L
     return L
@@ -278,3 +291,67 @@ class Instance:
 
     def flush_l2(self):
         _chk(lib().tspcuda_flush_l2(self._h))
+
+
+class MatrixInstance:
+    """A caller-supplied dense cost matrix resident on one GPU (tspcuda_mx): the `costs`-argument paths of
+    h_greedyutil / ref_2opt / ref_2opt_once and, through them, h_Greedy_2opt_mod_costs."""
+
+    def __init__(self, costs, device=0):
+        self.costs = np.ascontiguousarray(costs, dtype=np.float64)
+        assert self.costs.ndim == 2 and self.costs.shape[0] == self.costs.shape[1]
+        self.n = self.costs.shape[0]
+        self._h = _vp()
+        _chk(lib().tspcuda_mx_create(C.byref(self._h), _dpc(self.costs), self.n, device))
+
+    def close(self):
+        if self._h:
+            lib().tspcuda_mx_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def stats(self):
+        s = Stats()
+        _chk(lib().tspcuda_mx_get_stats(self._h, C.byref(s)))
+        return s.as_dict()
+
+    def nn(self, start):
+        """h_greedyutil(start, ., costs): (code, path, cost, nodes reached)."""
+        path = np.full(self.n, -7, dtype=np.int32)
+        cost, ln = C.c_double(0), C.c_int(0)
+        code = lib().tspcuda_mx_nn(self._h, start, _ipc(path), C.byref(cost), C.byref(ln))
+        return code, path, cost.value, ln.value
+
+    def two_opt(self, path, max_moves=-1, time_limit=-1.0, log_cap=0):
+        """ref_2opt(., costs, false): (code, moves, path, cost, log[(a,b,delta)...])."""
+        path = np.array(path, dtype=np.int32, copy=True)
+        cost, moves = C.c_double(0), C.c_int64(0)
+        log = (MoveF * max(1, log_cap))()
+        code = _chk(lib().tspcuda_mx_two_opt(self._h, _ipc(path), C.byref(cost), max_moves, time_limit, C.byref(moves),
+                                             log if log_cap else None, log_cap), allow=(DEADLINE_EXCEEDED,))
+        k = min(moves.value, log_cap)
+        return code, moves.value, path, cost.value, [(log[i].a, log[i].b, log[i].delta) for i in range(k)]
+
+    def two_opt_once(self, path, cost):
+        """ref_2opt_once(., costs) in place on `path`: (best_delta, new cost)."""
+        c, d = C.c_double(cost), C.c_double(0)
+        _chk(lib().tspcuda_mx_two_opt_once(self._h, _ipc(path), C.byref(c), C.byref(d)))
+        return d.value, c.value
+
+    def mod_costs(self):
+        """h_Greedy_2opt_mod_costs without a time limit (heuristics.c:118-149): the loop keeps nothing between
+        starts, so its result is NN(n-1) + 2-opt.  Returns (path, cost)."""
+        code, p, c, ln = self.nn(self.n - 1)
+        code, moves, p, c, _ = self.two_opt(p)
+        return p, c

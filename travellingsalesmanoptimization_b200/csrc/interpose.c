@@ -235,6 +235,19 @@ ERROR_CODE tsp_compute_costs(void) {
 
 static bool foreign_costs(const double *costs) { return costs != tsp_inst.costs; }
 
+/* A caller-supplied matrix (h_Greedy_2opt_mod_costs and its helpers, heuristics.c:118-149): uploaded for
+ * the call.  The content behind the pointer may change between calls (the CPLEX callback refills its
+ * buffers), so nothing is cached across calls. */
+static tspcuda_mx *mx_for(double *costs) {
+    tspcuda_mx *m = NULL;
+    int e = tspcuda_mx_create(&m, costs, tsp_inst.nnodes, device_index());
+    if (e != TSPCUDA_OK) {
+        log_error("code %d : libtspcuda: %s", e, tspcuda_last_error());
+        return NULL;
+    }
+    return m;
+}
+
 /* ---- h_greedyutil, src/algorithms/heuristics.c:216-288 ------------------------------------- */
 ERROR_CODE h_greedyutil(int starting_node, tsp_solution *solution, double *costs) {
     g_calls[C_NN]++;
@@ -246,13 +259,17 @@ ERROR_CODE h_greedyutil(int starting_node, tsp_solution *solution, double *costs
         log_error("starting node not correct");
         return UNAVAILABLE;
     }
-    if (foreign_costs(costs)) {
-        log_error("libtspcuda: h_greedyutil on a foreign cost matrix is not implemented on the device");
-        return UNIMPLEMENTED;
-    }
     if (tsp_env.timelimit != -1.0 && utils_timeelapsed(&tsp_inst.c) > tsp_env.timelimit) {   /* :240-246 */
         log_warn("time limit exceeded in greedy util");
         return DEADLINE_EXCEEDED;
+    }
+    if (foreign_costs(costs)) {
+        tspcuda_mx *m = mx_for(costs);
+        if (!m) return INTERNAL;
+        int rc = tspcuda_mx_nn(m, starting_node, solution->path, &solution->cost, NULL);
+        if (rc != TSPCUDA_OK) log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
+        tspcuda_mx_destroy(m);
+        return (ERROR_CODE)rc;
     }
     tspcuda_ctx *c = ctx_for_instance();
     if (!c) return INTERNAL;
@@ -264,17 +281,21 @@ ERROR_CODE h_greedyutil(int starting_node, tsp_solution *solution, double *costs
 /* ---- ref_2opt, src/algorithms/refinment.c:3-37 --------------------------------------------- */
 ERROR_CODE ref_2opt(tsp_solution *solution, double *costs, bool update_incumbent) {
     g_calls[C_2OPT]++;
-    if (foreign_costs(costs)) {
-        log_error("libtspcuda: ref_2opt on a foreign cost matrix is not implemented on the device");
-        return UNIMPLEMENTED;
-    }
-    tspcuda_ctx *c = ctx_for_instance();
-    if (!c) return INTERNAL;
     ERROR_CODE e = T_OK;
     double left = time_left();
     int64_t moves = 0;
+    int rc;
     /* left == 0: the reference recomputes the cost (:6-9) and leaves at the first time check (:17-24) */
-    int rc = tspcuda_two_opt(c, solution->path, &solution->cost, left == 0.0 ? 0 : -1, left, &moves, NULL, 0);
+    if (foreign_costs(costs)) {
+        tspcuda_mx *m = mx_for(costs);
+        if (!m) return INTERNAL;
+        rc = tspcuda_mx_two_opt(m, solution->path, &solution->cost, left == 0.0 ? 0 : -1, left, &moves, NULL, 0);
+        tspcuda_mx_destroy(m);
+    } else {
+        tspcuda_ctx *c = ctx_for_instance();
+        if (!c) return INTERNAL;
+        rc = tspcuda_two_opt(c, solution->path, &solution->cost, left == 0.0 ? 0 : -1, left, &moves, NULL, 0);
+    }
     if (rc == TSPCUDA_DEADLINE_EXCEEDED || left == 0.0) {
         log_debug("time limit exceeded in 2opt");
         e = DEADLINE_EXCEEDED;
@@ -292,13 +313,16 @@ ERROR_CODE ref_2opt(tsp_solution *solution, double *costs, bool update_incumbent
 /* ---- ref_2opt_once, src/algorithms/refinment.c:39-93 --------------------------------------- */
 double ref_2opt_once(tsp_solution *solution, double *costs) {
     g_calls[C_2OPT_ONCE]++;
-    tspcuda_ctx *c = foreign_costs(costs) ? NULL : ctx_for_instance();
-    if (!c) {
-        log_fatal("libtspcuda: ref_2opt_once cannot run (foreign cost matrix or no device): %s", tspcuda_last_error());
-        tsp_handlefatal();
-    }
     double delta = 0;
-    int rc = tspcuda_two_opt_once(c, solution->path, &solution->cost, &delta, NULL);
+    int rc;
+    if (foreign_costs(costs)) {
+        tspcuda_mx *m = mx_for(costs);
+        rc = m ? tspcuda_mx_two_opt_once(m, solution->path, &solution->cost, &delta) : TSPCUDA_INTERNAL;
+        tspcuda_mx_destroy(m);
+    } else {
+        tspcuda_ctx *c = ctx_for_instance();
+        rc = c ? tspcuda_two_opt_once(c, solution->path, &solution->cost, &delta, NULL) : TSPCUDA_INTERNAL;
+    }
     if (rc != TSPCUDA_OK) {
         log_fatal("code %d : libtspcuda: %s", rc, tspcuda_last_error());
         tsp_handlefatal();
@@ -454,4 +478,31 @@ ERROR_CODE mh_TabuSearch(void) {
     free(trace);
     tabu_free(&ts);
     return e;
+}
+
+/* h_Greedy_2opt_mod_costs, heuristics.c:118-149: NN + ref_2opt(update_incumbent = false) for every start
+ * into the SAME solution struct; nothing is kept between starts, so what the caller receives is the
+ * result of the last start the loop reaches -- n-1 unless the time limit stops it earlier, which on
+ * the device (one upload, ~1 ms per descent) it does not.  Only that start is computed. */
+ERROR_CODE h_Greedy_2opt_mod_costs(tsp_solution *solution, double *costs) {
+    typedef ERROR_CODE (*mod_fn)(tsp_solution *, double *);
+    if (!batch_enabled())
+        return ((mod_fn)dlsym(RTLD_NEXT, "h_Greedy_2opt_mod_costs"))(solution, costs);
+    if (tsp_env.timelimit != -1.0 && utils_timeelapsed(&tsp_inst.c) > tsp_env.timelimit)
+        return DEADLINE_EXCEEDED;                                   /* :124-130, before the first start */
+    if (costs == NULL) {
+        log_error("matrix of costs not found");
+        return T_OK;                                                /* every iteration logs and continues (:134-137) */
+    }
+    tspcuda_mx *m = mx_for(costs);
+    if (!m) return T_OK;                                            /* errors inside the loop are logged, e stays T_OK */
+    int rc = tspcuda_mx_nn(m, tsp_inst.nnodes - 1, solution->path, &solution->cost, NULL);
+    if (rc == TSPCUDA_OK) {
+        int64_t moves = 0;
+        rc = tspcuda_mx_two_opt(m, solution->path, &solution->cost, -1, time_left(), &moves, NULL, 0);
+    }
+    if (rc != TSPCUDA_OK && rc != TSPCUDA_DEADLINE_EXCEEDED)
+        log_error("code %d : error in 2opt (libtspcuda: %s)", rc, tspcuda_last_error());
+    tspcuda_mx_destroy(m);
+    return T_OK;
 }

@@ -15,6 +15,7 @@
 #include "../../include/tspcuda.h"
 #include "kernels.cuh"
 #include "pruned.cuh"
+#include "matrix.cuh"
 
 using namespace tspcuda;
 
@@ -1091,5 +1092,262 @@ extern "C" int tspcuda_flush_l2(tspcuda_ctx *c) {
     const size_t bytes = 192u << 20;
     if (!c->d_flush) CK(cudaMalloc(&c->d_flush, bytes));
     CK(cudaMemsetAsync(c->d_flush, 0x5A, bytes, c->stream));
+    return TSPCUDA_OK;
+}
+
+
+// ===== the `costs`-argument paths: a caller-supplied dense matrix (matrix.cuh) ========================
+struct tspcuda_mx {
+    int n = 0, device = 0, num_sms = 0, coop_blocks = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double *d_C = nullptr, *d_dnp = nullptr, *d_nncost = nullptr;
+    int *d_tid = nullptr, *d_pos = nullptr, *d_order = nullptr, *d_path = nullptr, *d_len = nullptr;
+    unsigned char *d_visited = nullptr;
+    unsigned long long *d_slots = nullptr;
+    MxState *d_state = nullptr, *h_state = nullptr;
+    MxMove *d_log = nullptr;
+    long long log_cap = 0;
+    int *h_buf = nullptr;
+    tspcuda_stats stats{};
+};
+
+extern "C" void tspcuda_mx_destroy(tspcuda_mx *m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    cudaFree(m->d_C); cudaFree(m->d_dnp); cudaFree(m->d_nncost); cudaFree(m->d_tid); cudaFree(m->d_pos);
+    cudaFree(m->d_order); cudaFree(m->d_path); cudaFree(m->d_len); cudaFree(m->d_visited); cudaFree(m->d_slots);
+    cudaFree(m->d_state); cudaFree(m->d_log);
+    if (m->h_state) cudaFreeHost(m->h_state);
+    if (m->h_buf) cudaFreeHost(m->h_buf);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+extern "C" int tspcuda_mx_create(tspcuda_mx **out, const double *costs, int n, int device) {
+    if (!out || !costs) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
+    *out = nullptr;
+    if (n <= 0) return fail(TSPCUDA_INVALID_ARGUMENT, "n = %d", n);
+    int ndev = tspcuda_device_count();
+    if (ndev <= 0) return fail(TSPCUDA_UNAVAILABLE, "no CUDA device: libtspcuda has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(TSPCUDA_INVALID_ARGUMENT, "device %d of %d", device, ndev);
+    tspcuda_mx *m = new tspcuda_mx();
+    m->n = n; m->device = device;
+#define CKM(call)                                                                                     \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            int code_ = fail(e_ == cudaErrorMemoryAllocation ? TSPCUDA_RESOURCE_EXHAUSTED : TSPCUDA_INTERNAL, \
+                             "%s failed: %s", #call, cudaGetErrorString(e_));                          \
+            tspcuda_mx_destroy(m);                                                                    \
+            return code_;                                                                             \
+        }                                                                                             \
+    } while (0)
+    CKM(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CKM(cudaGetDeviceProperties(&prop, device));
+    m->num_sms = prop.multiProcessorCount;
+    int bps = 0;
+    CKM(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, descend_matrix_kernel, MX_BLOCK, 0));
+    if (bps <= 0) { tspcuda_mx_destroy(m); return fail(TSPCUDA_INTERNAL, "matrix descent kernel cannot be resident"); }
+    m->coop_blocks = std::min(bps, 4) * m->num_sms;
+    CKM(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    CKM(cudaEventCreate(&m->ev0));
+    CKM(cudaEventCreate(&m->ev1));
+    const size_t N = (size_t)n;
+    CKM(cudaMalloc(&m->d_C, sizeof(double) * N * N));
+    CKM(cudaMalloc(&m->d_dnp, sizeof(double) * (N + 1)));
+    CKM(cudaMalloc(&m->d_nncost, sizeof(double)));
+    CKM(cudaMalloc(&m->d_tid, sizeof(int) * (N + 1)));
+    CKM(cudaMalloc(&m->d_pos, sizeof(int) * N));
+    CKM(cudaMalloc(&m->d_order, sizeof(int) * N));
+    CKM(cudaMalloc(&m->d_path, sizeof(int) * N));
+    CKM(cudaMalloc(&m->d_len, sizeof(int)));
+    CKM(cudaMalloc(&m->d_visited, N));
+    CKM(cudaMalloc(&m->d_slots, sizeof(unsigned long long) * 4));
+    CKM(cudaMalloc(&m->d_state, sizeof(MxState)));
+    m->log_cap = std::max<long long>(4096, 8LL * n);
+    CKM(cudaMalloc(&m->d_log, sizeof(MxMove) * m->log_cap));
+    CKM(cudaMallocHost(&m->h_state, sizeof(MxState)));
+    CKM(cudaMallocHost(&m->h_buf, sizeof(int) * N));
+    CKM(cudaMemcpyAsync(m->d_C, costs, sizeof(double) * N * N, cudaMemcpyHostToDevice, m->stream));
+    CKM(cudaStreamSynchronize(m->stream));
+    m->stats.h2d_bytes += (int64_t)(sizeof(double) * N * N);
+    *out = m;
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_mx_get_stats(tspcuda_mx *m, tspcuda_stats *out) {
+    if (!m || !out) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
+    *out = m->stats;
+    return TSPCUDA_OK;
+}
+
+static int mx_use(tspcuda_mx *m) {
+    if (!m) return fail(TSPCUDA_INVALID_ARGUMENT, "null context");
+    CK(cudaSetDevice(m->device));
+    return TSPCUDA_OK;
+}
+
+// h_greedyutil(start, solution, costs), heuristics.c:216-288.  *len_out (may be NULL) = nodes reached
+// (< n when NOT_CONNECTED entries close the path early, as in the reference).
+extern "C" int tspcuda_mx_nn(tspcuda_mx *m, int start, int *path_out, double *cost_out, int *len_out) {
+    int e = mx_use(m);
+    if (e) return e;
+    if (start < 0 || start >= m->n) return fail(TSPCUDA_UNAVAILABLE, "starting node not correct");     // :223-226
+    const int n = m->n;
+    nn_matrix_kernel<<<1, MX_NN_BLOCK, 0, m->stream>>>(m->d_C, n, start, 1, m->d_visited, m->d_path, m->d_order, m->d_nncost, m->d_len);
+    m->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    double c = 0;
+    int len = 0;
+    CK(cudaMemcpyAsync(&c, m->d_nncost, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaMemcpyAsync(&len, m->d_len, sizeof(int), cudaMemcpyDeviceToHost, m->stream));
+    if (path_out) CK(cudaMemcpyAsync(m->h_buf, m->d_path, sizeof(int) * n, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->stats.d2h_bytes += 12 + (path_out ? (int64_t)sizeof(int) * n : 0);
+    if (path_out) std::memcpy(path_out, m->h_buf, sizeof(int) * n);
+    if (cost_out) *cost_out = c;
+    if (len_out) *len_out = len;
+    return TSPCUDA_OK;
+}
+
+static int mx_descend(tspcuda_mx *m, long long max_moves, bool recompute, double time_limit_s, bool *deadline) {
+    const int n = m->n;
+    if (deadline) *deadline = false;
+    MxTour T;
+    T.tid = m->d_tid; T.pos = m->d_pos; T.dnp = m->d_dnp; T.n = n;
+    const int grid = std::max(1, std::min(m->coop_blocks, (n + 7) / 8));
+    const auto t0 = std::chrono::steady_clock::now();
+    long long done = 0;
+    bool first = true;
+    for (;;) {
+        if (max_moves >= 0 && done >= max_moves && !(first && recompute)) break;
+        long long chunk = n < 4 ? 0 : 2048;
+        if (max_moves >= 0) chunk = std::min(chunk, max_moves - done);
+        int rc = (first && recompute) ? 1 : 0;
+        CK(cudaMemsetAsync(m->d_slots, 0xFF, sizeof(unsigned long long) * 4, m->stream));
+        CK(cudaEventRecord(m->ev0, m->stream));
+        const double *C = m->d_C;
+        unsigned long long *slots = m->d_slots;
+        MxState *st = m->d_state;
+        MxMove *log = m->d_log;
+        long long log_cap = m->log_cap;
+        void *args[] = {&C, &T, &slots, &st, &log, &log_cap, &chunk, &rc};
+        CK(cudaLaunchCooperativeKernel((void *)descend_matrix_kernel, dim3(grid), dim3(MX_BLOCK), args, 0, m->stream));
+        CK(cudaEventRecord(m->ev1, m->stream));
+        m->stats.kernel_launches += 1;
+        CK(cudaMemcpyAsync(m->h_state, m->d_state, sizeof(MxState), cudaMemcpyDeviceToHost, m->stream));
+        CK(cudaStreamSynchronize(m->stream));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, m->ev0, m->ev1));
+        m->stats.scan_kernel_ms += ms;
+        m->stats.last_kernel_ms = ms;
+        first = false;
+        done = m->h_state->moves;
+        if (m->h_state->status == 1 || n < 4 || chunk == 0) break;
+        if (time_limit_s >= 0) {
+            const double el = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (el > time_limit_s) { if (deadline) *deadline = true; break; }
+        }
+    }
+    return TSPCUDA_OK;
+}
+
+static int mx_upload_tour(tspcuda_mx *m, const int *path) {
+    const int n = m->n;
+    int *order = m->h_buf;
+    int cur = 0;
+    std::vector<unsigned char> seen(n, 0);
+    for (int k = 0; k < n; k++) {
+        if (cur < 0 || cur >= n || seen[cur]) return fail(TSPCUDA_INVALID_ARGUMENT, "path is not a single cycle through all nodes");
+        seen[cur] = 1;
+        order[k] = cur;
+        cur = path[cur];
+    }
+    if (cur != 0) return fail(TSPCUDA_INVALID_ARGUMENT, "path is not a single cycle through all nodes");
+    CK(cudaMemcpyAsync(m->d_order, order, sizeof(int) * n, cudaMemcpyHostToDevice, m->stream));
+    m->stats.h2d_bytes += (int64_t)sizeof(int) * n;
+    MxTour T;
+    T.tid = m->d_tid; T.pos = m->d_pos; T.dnp = m->d_dnp; T.n = n;
+    CK(cudaMemsetAsync(m->d_state, 0, sizeof(MxState), m->stream));
+    mx_tour_init_kernel<<<std::max(1, std::min(4 * m->num_sms, (n + 256) / 256)), 256, 0, m->stream>>>(T, m->d_order);
+    m->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(m->stream));
+    return TSPCUDA_OK;
+}
+
+__global__ void mx_export_kernel(MxTour T, int *path) {
+    const int n = T.n;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) path[T.tid[p]] = T.tid[p + 1];
+}
+
+static int mx_download(tspcuda_mx *m, int *path) {
+    const int n = m->n;
+    MxTour T;
+    T.tid = m->d_tid; T.pos = m->d_pos; T.dnp = m->d_dnp; T.n = n;
+    mx_export_kernel<<<std::max(1, std::min(4 * m->num_sms, (n + 255) / 256)), 256, 0, m->stream>>>(T, m->d_path);
+    m->stats.kernel_launches += 1;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(m->h_buf, m->d_path, sizeof(int) * n, cudaMemcpyDeviceToHost, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->stats.d2h_bytes += (int64_t)sizeof(int) * n;
+    std::memcpy(path, m->h_buf, sizeof(int) * n);
+    return TSPCUDA_OK;
+}
+
+// ref_2opt(solution, costs, false), refinment.c:3-37, on the uploaded matrix.
+extern "C" int tspcuda_mx_two_opt(tspcuda_mx *m, int *path, double *cost_out, int64_t max_moves, double time_limit_s,
+                                  int64_t *moves_out, tspcuda_move_f *log, int64_t log_cap) {
+    int e = mx_use(m);
+    if (e) return e;
+    if (!path) return fail(TSPCUDA_INVALID_ARGUMENT, "null path");
+    e = mx_upload_tour(m, path);
+    if (e) return e;
+    bool deadline = false;
+    e = mx_descend(m, max_moves, true, time_limit_s, &deadline);
+    if (e) return e;
+    m->stats.moves += m->h_state->moves;
+    m->stats.scans += m->h_state->moves + (m->h_state->status == 1 ? 1 : 0);
+    m->stats.pair_evals += (m->h_state->moves + (m->h_state->status == 1 ? 1 : 0)) * ((long long)m->n * (m->n - 1) / 2);
+    if (moves_out) *moves_out = m->h_state->moves;
+    if (cost_out) *cost_out = m->h_state->cost;
+    if (log && log_cap > 0) {
+        static_assert(sizeof(tspcuda_move_f) == sizeof(MxMove), "move record layout");
+        const long long cnt = std::min<long long>(std::min<long long>(m->h_state->log_count, m->log_cap), log_cap);
+        if (cnt > 0) {
+            CK(cudaMemcpyAsync(log, m->d_log, sizeof(MxMove) * cnt, cudaMemcpyDeviceToHost, m->stream));
+            CK(cudaStreamSynchronize(m->stream));
+        }
+    }
+    e = mx_download(m, path);
+    if (e) return e;
+    return deadline ? TSPCUDA_DEADLINE_EXCEEDED : TSPCUDA_OK;
+}
+
+// ref_2opt_once(solution, costs), refinment.c:39-93: one scan; the move is applied iff best_delta < -1e-7.
+extern "C" int tspcuda_mx_two_opt_once(tspcuda_mx *m, int *path, double *cost_inout, double *best_delta_out) {
+    int e = mx_use(m);
+    if (e) return e;
+    if (!path || !cost_inout) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
+    e = mx_upload_tour(m, path);
+    if (e) return e;
+    e = mx_descend(m, 1, false, -1.0, nullptr);
+    if (e) return e;
+    const bool moved = m->h_state->moves > 0;
+    // best_delta: the applied move's delta, or the (non-applicable) minimum found, or 0 when no pair improves
+    const double d = moved ? m->h_state->last_delta : (m->h_state->status == 1 ? m->h_state->last_delta : 0.0);
+    if (best_delta_out) *best_delta_out = d;
+    m->stats.scans += 1;
+    m->stats.moves += moved ? 1 : 0;
+    if (moved) {
+        *cost_inout += d;                                // refinment.c:85
+        e = mx_download(m, path);
+        if (e) return e;
+    }
     return TSPCUDA_OK;
 }
