@@ -18,6 +18,7 @@
  *   tspcuda_tabu_move             tabu_best_move               algorithms/metaheuristic.c:188-245
  *   tspcuda_tabu_search           mh_TabuSearch inner loop     algorithms/metaheuristic.c:128-164
  *   tspcuda_multistart_two_opt    h_greedy_2opt loop           algorithms/heuristics.c:74-116
+ *   tspcuda_extra_mileage         h_ExtraMileage / h_extramileage_util   algorithms/heuristics.c:156-210, :290-367
  *   tspcuda_mx_nn / _two_opt      h_greedyutil / ref_2opt on a caller's matrix (h_Greedy_2opt_mod_costs, heuristics.c:118-149)
  *
  * Tours cross the boundary exactly as the reference stores them: a successor array int path[n],
@@ -159,6 +160,14 @@ int tspcuda_tour_movelog(tspcuda_ctx *ctx, tspcuda_move *log, int64_t cap, int64
 int tspcuda_multistart_two_opt(tspcuda_ctx *ctx, int first_start, int nstarts, int stride, double *nn_costs_out,
                                double *final_costs_out, int64_t *moves_out, int *best_start_out,
                                int *best_path_out, double *best_cost_out);
+
+/* ---- Extra Mileage (heuristics.c:156-210 h_ExtraMileage, :290-367 h_extramileage_util) ---------- */
+/* node_a < 0: the EM_MAX initial edge (first pair i<j with the strictly largest cost, :169-178), else the
+ * given edge (EM_RANDOM draws it on the host with rand(), :180-183).  Then n-2 insertions with the
+ * reference's tie rule (first strict minimum over unvisited i ascending, tour edges in edges[] order).
+ * *cost_out = 2 c(A,B) + the mileage of every insertion (:193, :360); path_out = successor array. */
+int tspcuda_extra_mileage(tspcuda_ctx *ctx, int node_a, int node_b, int *path_out, double *cost_out,
+                          int *node_a_out, int *node_b_out);
 
 /* ---- the `costs`-argument paths: a caller-supplied dense matrix ------------------------------- */
 /* h_greedyutil / ref_2opt / ref_2opt_once called with a matrix other than the instance's own

@@ -79,6 +79,7 @@ class Oracle:
         L.orc_two_opt.argtypes = [_dp, C.c_int, C.c_int, _ip, _dp, C.c_long, _ip, _ip, _dp]
         L.orc_two_opt_matrix.restype = C.c_long
         L.orc_two_opt_matrix.argtypes = [_dp, C.c_int, _ip, _dp, C.c_long, _ip, _ip, _dp]
+        L.orc_extra_mileage.argtypes = [_dp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _dp]
         L.orc_nn_matrix.argtypes = [_dp, C.c_int, C.c_int, _ip, _dp]
         L.orc_mod_costs.argtypes = [_dp, C.c_int, _ip, _dp]
         L.orc_tabu_move.argtypes = [_dp, C.c_int, C.c_int, _ip, _dp, _ip, C.c_int, C.c_int, _ip, _ip, _dp]
@@ -183,6 +184,15 @@ class Oracle:
         m = self.L.orc_two_opt_matrix(_d(costs), n, _i(path), C.byref(cost), cap, _i(la), _i(lb), _d(ld))
         return m, path, cost.value, la[:m], lb[:m], ld[:m]
 
+    def extra_mileage(self, xy, node_a=-1, node_b=-1, wt=EUC_REF):
+        """h_ExtraMileage (node_a < 0: EM_MAX initial edge) / h_extramileage_util: (path, cost)."""
+        n = xy.shape[0]
+        path = np.zeros(n, dtype=np.int32)
+        c = C.c_double(0)
+        e = self.L.orc_extra_mileage(_d(xy), n, wt, node_a, node_b, _i(path), C.byref(c))
+        assert e == 0, e
+        return path, c.value
+
     def nn_matrix(self, costs, start):
         """h_greedyutil on an explicit matrix: (code, path, cost)."""
         n = costs.shape[0]
@@ -261,6 +271,7 @@ class Reference:
         L.refapi_two_opt.argtypes = [_ip, _dp, C.c_int, _ip, _ip, _dp]
         L.refapi_ref_2opt.argtypes = [_ip, _dp, C.c_int]
         L.refapi_tabu_move.argtypes = [_ip, _dp, _ip, C.c_int, C.c_int]
+        L.refapi_extra_mileage_from.argtypes = [C.c_int, C.c_int, _ip, _dp]
         L.refapi_nn_costs.argtypes = [C.c_int, _dp, _ip, _dp]
         L.refapi_ref_2opt_costs.argtypes = [_dp, _ip, _dp]
         L.refapi_mod_costs.argtypes = [_dp, _ip, _dp]
@@ -310,6 +321,12 @@ class Reference:
         m = self.L.refapi_two_opt(_i(path), C.byref(c), cap if max_moves < 0 else max_moves, _i(la), _i(lb), _d(ld))
         return m, path, c.value, la[:m], lb[:m], ld[:m]
 
+    def extra_mileage_from(self, node_a, node_b):
+        path = np.zeros(self.n, dtype=np.int32)
+        c = C.c_double(0)
+        e = self.L.refapi_extra_mileage_from(node_a, node_b, _i(path), C.byref(c))
+        return e, path, c.value
+
     def nn_costs(self, costs, start):
         path = np.full(self.n, -7, dtype=np.int32)
         c = C.c_double(0)
@@ -351,7 +368,7 @@ class Reference:
         assert self.L.refapi_vns_kick(_i(path)) == 0
 
     def run(self, alg, k=2**31 - 1):
-        """alg: 0 GREEDY, 1 GREEDY_ITER, 2 2OPT_GREEDY, 3 TABU_SEARCH, 4 VNS. Needs ./results/ for 3/4."""
+        """alg: 0 GREEDY, 1 GREEDY_ITER, 2 2OPT_GREEDY, 3 TABU_SEARCH, 4 VNS, 5 EXTRA_MILEAGE (EM_MAX). Needs ./results/ for 3/4."""
         path = np.zeros(self.n, dtype=np.int32)
         c, s = C.c_double(0), C.c_int(0)
         e = self.L.refapi_run(alg, k, _i(path), C.byref(c), C.byref(s))

@@ -399,6 +399,66 @@ long orc_two_opt(const double *xy, int n, int wt, int *path, double *cost, long 
     return moves;
 }
 
+/* heuristics.c:156-210 h_ExtraMileage (EM_MAX initialisation :169-178) + :290-367 h_extramileage_util.
+ * nodeA < 0: EM_MAX -- the first pair (i<j, ascending) with the strictly largest cost, (0,1) if every
+ * cost is 0.  Then n-2 insertions: over unvisited i ascending and tour edges j in edges[] order, the
+ * first strict minimum of c(u,i) + c(i,v) - c(u,v) (:321-339); edges[j] becomes (u,i), (i,v) is
+ * appended (:348-356); cost starts at 2 c(A,B) (:193) and grows by the mileage (:362).  O(n^3). */
+int orc_extra_mileage(const double *xy, int n, int wt, int nodeA, int nodeB, int *path, double *cost) {
+    if (n < 2) return ORC_INVALID_ARGUMENT;
+#define ORC_C(i, j) orc_edge(wt, xy[2 * (i)], xy[2 * (i) + 1], xy[2 * (j)], xy[2 * (j) + 1])
+    if (nodeA < 0) {
+        double maxd = 0.0;
+        nodeA = 0; nodeB = 1;
+        for (int i = 0; i < n; i++)
+            for (int j = i + 1; j < n; j++) {
+                double d = ORC_C(i, j);
+                if (d > maxd) { nodeA = i; nodeB = j; maxd = d; }
+            }
+    }
+    unsigned char *visited = (unsigned char *)calloc((size_t)n, 1);
+    int *eu = (int *)malloc(sizeof(int) * (size_t)n), *ev = (int *)malloc(sizeof(int) * (size_t)n);
+    for (int i = 0; i < n; i++) path[i] = 0;              /* tsp_init_solution: calloc'd path */
+    visited[nodeA] = visited[nodeB] = 1;
+    int m = 0;
+    eu[m] = nodeA; ev[m++] = nodeB;
+    eu[m] = nodeB; ev[m++] = nodeA;
+    double sol = 2 * ORC_C(nodeA, nodeB);
+    path[nodeA] = nodeB; path[nodeB] = nodeA;
+    while (m < n) {
+        double mileage = __DBL_MAX__;
+        int bj = -1, bi = -1;
+#pragma omp parallel
+        {
+            double lm = __DBL_MAX__;
+            int lj = -1, li = -1;
+#pragma omp for schedule(static) nowait
+            for (int i = 0; i < n; i++) {
+                if (visited[i]) continue;
+                for (int j = 0; j < m; j++) {
+                    int u = eu[j], v = ev[j];
+                    double d = ORC_C(u, i) + ORC_C(i, v) - ORC_C(u, v);
+                    if (d < lm) { lm = d; lj = j; li = i; }
+                }
+            }
+#pragma omp critical
+            {   /* static schedule: threads own ascending i ranges; keep the (delta, i) lexicographic minimum */
+                if (li >= 0 && (lm < mileage || (lm == mileage && li < bi))) { mileage = lm; bj = lj; bi = li; }
+            }
+        }
+        if (bj == -1) break;
+        int u = eu[bj], v = ev[bj];
+        path[u] = bi; ev[bj] = bi;
+        path[bi] = v; eu[m] = bi; ev[m] = v; m++;
+        visited[bi] = 1;
+        sol += mileage;
+    }
+#undef ORC_C
+    *cost = sol;
+    free(visited); free(eu); free(ev);
+    return ORC_T_OK;
+}
+
 /* heuristics.c:216-288 h_greedyutil over an explicit row-major matrix (the `costs` argument: the
  * instance matrix or the fractional matrices of h_Greedy_2opt_mod_costs, heuristics.c:118-149).
  * Entries equal to NOT_CONNECTED (-1.0) are skipped (:257); if no candidate is left the tour is

@@ -165,6 +165,19 @@ int refapi_mod_costs(double *costs, int *path, double *cost) {
     return e;
 }
 
+/* h_extramileage_util (heuristics.c:290) from a given first edge, set up as h_ExtraMileage does (:189-196). */
+int refapi_extra_mileage_from(int nodeA, int nodeB, int *path, double *cost) {
+    int n = tsp_inst.nnodes;
+    tsp_solution s; s.path = path; s.ncomp = 0; s.comp = NULL;
+    memset(path, 0, (size_t)n * sizeof(int));
+    s.cost = 2 * tsp_get_cost(nodeA, nodeB);
+    path[nodeA] = nodeB;
+    path[nodeB] = nodeA;
+    int e = (int)h_extramileage_util(&s, nodeA, nodeB);
+    *cost = s.cost;
+    return e;
+}
+
 int refapi_tabu_move(int *path, double *cost, int *tabu_list, int tenure, int iter) {
     tabu_search ts; memset(&ts, 0, sizeof(ts));
     ts.tenure = tenure; ts.tabu_list = tabu_list;
@@ -193,7 +206,7 @@ int refapi_vns_kick(int *path) {
 }
 
 /* Whole-algorithm entry points, exactly as src/main.c:4-87 dispatches them (minus plotting).
- * alg: 0 GREEDY, 1 GREEDY_ITER, 2 2OPT_GREEDY, 3 TABU_SEARCH, 4 VNS (tsp.h:45-50). */
+ * alg: 0 GREEDY, 1 GREEDY_ITER, 2 2OPT_GREEDY, 3 TABU_SEARCH, 4 VNS, 5 EXTRA_MILEAGE with EM_MAX (tsp.h:45-50). */
 int refapi_run(int alg, int k, int *best_path, double *best_cost, int *starting_node) {
     int n = tsp_inst.nnodes;
     refapi_reset_incumbent();
@@ -207,6 +220,7 @@ int refapi_run(int alg, int k, int *best_path, double *best_cost, int *starting_
         case 2: e = (int)h_greedy_2opt(); break;
         case 3: e = (int)mh_TabuSearch(); break;
         case 4: e = (int)mh_VNS(); break;
+        case 5: tsp_env.mileage_init = EM_MAX; e = (int)h_ExtraMileage(); break;
         default: return -1;
     }
     memcpy(best_path, tsp_inst.best_solution.path, (size_t)n * sizeof(int));

@@ -72,7 +72,7 @@ def test_cpu_box_fails_loudly(workdir):
 @pytest.mark.gpu
 @pytest.mark.parametrize("alg,extra,cost", [
     ("GREEDY", [], "8980.00"), ("GREEDY_ITER", [], "8181.00"), ("2OPT_GREEDY", [], "7657.00"),
-    ("TABU_SEARCH", ["-k", "200"], "7542.00"), ("VNS", ["-k", "50"], "7670.00")])
+    ("TABU_SEARCH", ["-k", "200"], "7542.00"), ("VNS", ["-k", "50"], "7670.00"), ("EXTRA_MILEAGE", [], "9021.00")])
 def test_berlin52_cli_golden(workdir, alg, extra, cost):
     """Golden values of BASELINE.md section 3 through the unchanged CLI: make/bin/tsp -f F -q -alg A."""
     r = run_cli(TSP_GPU, workdir, ["-f", "berlin52.tsp", "-q", "-alg", alg] + extra)
@@ -94,6 +94,12 @@ def test_berlin52_cli_golden(workdir, alg, extra, cost):
             assert f.read().split() == lines
     if alg == "VNS":
         assert c["ref_2opt"] == 50 and c["h_Greedy_iterative"] == 1
+    if alg == "EXTRA_MILEAGE":
+        assert c["h_ExtraMileage"] == 1
+        # the reference's own h_ExtraMileage (EM_MAX loop over the host matrix) over the interposed util
+        r0 = run_cli(TSP_GPU, workdir, ["-f", "berlin52.tsp", "-q", "-alg", alg], {"TSPCUDA_BATCH": "0"})
+        c0 = calls(r0.stderr)
+        assert r0.stdout == r.stdout and c0["h_extramileage_util"] == 1 and c0["h_ExtraMileage"] == 0
 
 
 @pytest.mark.gpu

@@ -639,3 +639,38 @@ def test_foreign_matrix_vs_oracle(tsp, oracle, seed, n, symmetric, nc):
         if symmetric:
             d, c_end = I.two_opt_once(p2.copy(), c2)
             assert d > -1e-7 and c_end == c2              # local optimum: nothing applied
+
+
+# ---- Extra Mileage (heuristics.c:156-210, :290-367) -------------------------------
+@pytest.mark.parametrize("name", ["berlin52", "eil51", "kroA100", "pcb442", "pr1002", "u1060", "rl1304", "fl1577", "pr2392"])
+def test_extra_mileage_golden(tsp, name):
+    """tests/golden/golden_em.json (unmodified reference objects; the EM_MAX values also are the published
+    `ExtraMileage` column of results/heuristics-ric.csv: rl1304 307898, pr1002 302240, fl1577 26944)."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_em.json")) as f:
+        g = json.load(f)[name]
+    xy, _ = load_instance(name)
+    with tsp.Instance(xy) as I:
+        p, c, ab = I.extra_mileage()
+        assert (int(c), fnv1a(p)) == (g["em_max"]["cost"], g["em_max"]["hash"])
+        for a, b, cost, h in g["from"]:
+            p, c, ab = I.extra_mileage(a, b)
+            assert ab == (a, b) and (int(c), fnv1a(p)) == (cost, h), (a, b)
+
+
+@pytest.mark.parametrize("n,integer", [(2, True), (3, True), (4, False), (33, True), (257, False), (700, True)])
+def test_extra_mileage_vs_oracle(tsp, oracle, n, integer):
+    """Random instances, lattice ties, coincident nodes, the other metrics."""
+    xy = _rand_xy(3 * n + integer, n, integer, lo=0, hi=60 if integer else 1000)      # small integer range: many ties
+    if n >= 33:
+        xy[7] = xy[20]
+    for wt, twt in ((EUC_REF, tsp.EUC_REF), (CEIL_2D, tsp.CEIL_2D), (ATT, tsp.ATT)):
+        with tsp.Instance(xy, twt) as I:
+            p, c, ab = I.extra_mileage()
+            po, co = oracle.extra_mileage(xy, wt=wt)
+            assert c == co and np.array_equal(p, po), (n, wt)
+            if n >= 4:
+                p, c, ab = I.extra_mileage(n - 1, 1)
+                po, co = oracle.extra_mileage(xy, n - 1, 1, wt)
+                assert c == co and np.array_equal(p, po)

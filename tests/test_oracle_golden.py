@@ -165,3 +165,18 @@ def test_foreign_matrix_golden(oracle):
         if g["n"] <= 333:                        # all-start loop: O(n) descents on the CPU
             pm, cm = oracle.mod_costs(M)
             assert cm.hex() == g["mod_costs"]["cost"] and fnv1a(pm) == g["mod_costs"]["hash"], key
+
+
+def test_extra_mileage_golden(oracle):
+    """Oracle restatement of h_ExtraMileage / h_extramileage_util against tests/golden/golden_em.json."""
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_em.json")) as f:
+        G = json.load(f)
+    for name in ["berlin52", "eil51", "kroA100", "pcb442", "pr1002"]:
+        xy, _ = load_instance(name)
+        p, c = oracle.extra_mileage(xy)
+        assert (int(c), fnv1a(p)) == (G[name]["em_max"]["cost"], G[name]["em_max"]["hash"])
+        for a, b, cost, h in G[name]["from"][:2]:
+            p, c = oracle.extra_mileage(xy, a, b)
+            assert (int(c), fnv1a(p)) == (cost, h)

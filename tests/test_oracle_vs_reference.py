@@ -131,3 +131,17 @@ def test_foreign_matrix_paths(oracle, reference, seed, n, symmetric, nc):
         e1, p1, c1 = reference.nn_costs(M, n - 1)
         e2, p2, c2 = reference.ref_2opt_costs(M, p1)
         assert c2 == cm and np.array_equal(p2, pm)      # = the LAST start's result (nothing is kept between starts)
+
+
+def test_extra_mileage_matches_reference(oracle, reference):
+    for name in ("berlin52", "kroA100", "pcb442"):
+        xy, _ = load_instance(name)
+        n = xy.shape[0]
+        reference.set_points(xy)
+        e, p, c, s_ = reference.run(5)
+        po, co = oracle.extra_mileage(xy)
+        assert e == 0 and c == co and np.array_equal(p, po), name
+        for a, b in ((0, 1), (n - 1, 2), (5, 4)):
+            e, p, c = reference.extra_mileage_from(a, b)
+            po, co = oracle.extra_mileage(xy, a, b)
+            assert c == co and np.array_equal(p, po), (name, a, b)

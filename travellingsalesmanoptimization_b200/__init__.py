@@ -29,7 +29,7 @@ EXPORTS = [
     "tspcuda_tabu_move", "tspcuda_tour_upload", "tspcuda_tour_descend", "tspcuda_tour_download", "tspcuda_tour_movelog",
     "tspcuda_multistart_two_opt", "tspcuda_pipe_rate", "tspcuda_selfcheck_sqrt", "tspcuda_timer_start",
     "tspcuda_timer_stop", "tspcuda_flush_l2", "tspcuda_set_scan_mode", "tspcuda_tabu_search",
-    "tspcuda_mx_create", "tspcuda_mx_destroy", "tspcuda_mx_get_stats", "tspcuda_mx_nn", "tspcuda_mx_two_opt",
+    "tspcuda_extra_mileage", "tspcuda_mx_create", "tspcuda_mx_destroy", "tspcuda_mx_get_stats", "tspcuda_mx_nn", "tspcuda_mx_two_opt",
     "tspcuda_mx_two_opt_once",
 ]
 
@@ -99,6 +99,7 @@ def lib():
     L.tspcuda_timer_stop.argtypes = [_vp, _dp]
     L.tspcuda_flush_l2.argtypes = [_vp]
     L.tspcuda_set_scan_mode.argtypes = [_vp, C.c_int]
+    L.tspcuda_extra_mileage.argtypes = [_vp, C.c_int, C.c_int, _ip, _dp, _ip, _ip]
     L.tspcuda_mx_create.argtypes = [C.POINTER(_vp), _dp, C.c_int, C.c_int]
     L.tspcuda_mx_destroy.argtypes = [_vp]
     L.tspcuda_mx_destroy.restype = None
@@ -235,6 +236,13 @@ class Instance:
         _chk(lib().tspcuda_tabu_search(self._h, _ipc(path), C.byref(c), _ipc(tabu_list), _ipc(tenures), first_iter, k,
                                        inc, _dpc(trace), _ipc(best_path), C.byref(bc), C.byref(bi)))
         return c.value, trace, bi.value, (best_path if bi.value >= 0 else None), bc.value
+
+    def extra_mileage(self, node_a=-1, node_b=-1):
+        """h_ExtraMileage (node_a < 0: EM_MAX initial edge) / h_extramileage_util: (path, cost, (A, B))."""
+        path = np.zeros(self.n, dtype=np.int32)
+        cost, a, b = C.c_double(0), C.c_int(-1), C.c_int(-1)
+        _chk(lib().tspcuda_extra_mileage(self._h, node_a, node_b, _ipc(path), C.byref(cost), C.byref(a), C.byref(b)))
+        return path, cost.value, (a.value, b.value)
 
     # -- device-resident tour ----------------------------------------------------------------------
     def tour_upload(self, path):

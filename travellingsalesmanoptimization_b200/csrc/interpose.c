@@ -21,6 +21,8 @@
  *   mh_TabuSearch       metaheuristic.c:86  (whole-loop override: the k tabu iterations run in one
  *                       device-resident call; TSPCUDA_BATCH=0 keeps the reference's loop, which then
  *                       calls the interposed tabu_best_move once per iteration)
+ *   h_extramileage_util heuristics.c:290   and   h_ExtraMileage  heuristics.c:156  (the
+ *                       latter only so that the EM_MAX search also works without a host matrix, n > 46340)
  *   tsp_read_input      tsp.c:527  (EXTENSION: same grammar, additionally accepts CEIL_2D, ATT and GEO files)
  * ref_reverse_path (refinment.c:95) keeps the reference's definition: once ref_2opt_once and
  * tabu_best_move run on the device nothing on this path calls it.
@@ -44,10 +46,11 @@ static tspcuda_ctx *g_ctx = NULL;
 static int g_weight_type = TSPCUDA_EUC_REF;     /* set by the interposed tsp_read_input */
 static point *g_points = NULL;
 static int g_n = -1;
-static long g_calls[9];
-enum { C_COSTS, C_NN, C_2OPT, C_2OPT_ONCE, C_TABU, C_ALLNN, C_MULTI, C_TABULOOP, C_READ };
+static long g_calls[11];
+enum { C_COSTS, C_NN, C_2OPT, C_2OPT_ONCE, C_TABU, C_ALLNN, C_MULTI, C_TABULOOP, C_READ, C_EMUTIL, C_EM };
 static const char *g_names[] = {"tsp_compute_costs", "h_greedyutil", "ref_2opt", "ref_2opt_once",
-                                "tabu_best_move", "h_Greedy_iterative", "h_greedy_2opt", "mh_TabuSearch", "tsp_read_input"};
+                                "tabu_best_move", "h_Greedy_iterative", "h_greedy_2opt", "mh_TabuSearch", "tsp_read_input",
+                                "h_extramileage_util", "h_ExtraMileage"};
 
 /* Exit hook.  Prints the call counters (TSPCUDA_STATS=1), flushes stdio and leaves with _exit().
  * The last step shields the process from a latent heap overflow in the UNCHANGED driver:
@@ -61,7 +64,7 @@ static void on_exit_hook(int status, void *arg) {
     const char *s = getenv("TSPCUDA_STATS");
     if (s && *s == '1') {
         fprintf(stderr, "[tspcuda] interposed calls:");
-        for (int i = 0; i < 9; i++) fprintf(stderr, " %s=%ld", g_names[i], g_calls[i]);
+        for (int i = 0; i < 11; i++) fprintf(stderr, " %s=%ld", g_names[i], g_calls[i]);
         fprintf(stderr, "\n");
     }
     const char *f = getenv("TSPCUDA_FAST_EXIT");
@@ -505,4 +508,42 @@ ERROR_CODE h_Greedy_2opt_mod_costs(tsp_solution *solution, double *costs) {
         log_error("code %d : error in 2opt (libtspcuda: %s)", rc, tspcuda_last_error());
     tspcuda_mx_destroy(m);
     return T_OK;
+}
+
+/* ---- Extra Mileage, heuristics.c:156-210 and :290-367 --------------------------- */
+/* h_extramileage_util: the caller has set path[A] = B, path[B] = A and cost = 2 c(A,B) (:193-196); the
+ * n-2 insertions run on the device, which returns the whole successor array and the final cost. */
+ERROR_CODE h_extramileage_util(tsp_solution *solution, int nodeA, int nodeB) {
+    g_calls[C_EMUTIL]++;
+    if (tsp_env.timelimit != -1.0 && utils_timeelapsed(&tsp_inst.c) > tsp_env.timelimit)
+        return DEADLINE_EXCEEDED;                                   /* :308-314, before the first insertion */
+    tspcuda_ctx *c = ctx_for_instance();
+    if (!c) return INTERNAL;
+    int rc = tspcuda_extra_mileage(c, nodeA, nodeB, solution->path, &solution->cost, NULL, NULL);
+    if (rc != TSPCUDA_OK) {
+        log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
+        return (ERROR_CODE)rc;
+    }
+    return T_OK;
+}
+
+ERROR_CODE h_ExtraMileage(void) {
+    if (!batch_enabled() || tsp_env.mileage_init != EM_MAX)
+        return ((void_fn)dlsym(RTLD_NEXT, "h_ExtraMileage"))();     /* EM_RANDOM: the reference draws the edge, then calls the util above */
+    g_calls[C_EM]++;
+    log_info("running Extra Mileage");
+    tspcuda_ctx *c = ctx_for_instance();
+    if (!c) return INTERNAL;
+    tsp_solution solution;
+    tsp_init_solution(tsp_inst.nnodes, &solution);
+    int nodeA = 0, nodeB = 1;
+    int rc = tspcuda_extra_mileage(c, -1, -1, solution.path, &solution.cost, &nodeA, &nodeB);    /* EM_MAX search on the device */
+    if (rc != TSPCUDA_OK) {
+        log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
+        utils_safe_free(solution.path);
+        return (ERROR_CODE)rc;
+    }
+    log_debug("max edge : (%d, %d)", nodeA, nodeB);
+    tsp_update_best_solution(&solution);                            /* :205 */
+    return T_OK;                                                     /* the reference leaks solution.path here too (:207) */
 }

@@ -16,6 +16,7 @@
 #include "kernels.cuh"
 #include "pruned.cuh"
 #include "matrix.cuh"
+#include "mileage.cuh"
 
 using namespace tspcuda;
 
@@ -1095,6 +1096,70 @@ extern "C" int tspcuda_flush_l2(tspcuda_ctx *c) {
     return TSPCUDA_OK;
 }
 
+
+// ---- Extra Mileage (heuristics.c:156-210, :290-367) ---------------------------------------------
+constexpr int EM_BLOCK = 256;
+
+extern "C" int tspcuda_extra_mileage(tspcuda_ctx *c, int node_a, int node_b, int *path_out, double *cost_out,
+                                     int *node_a_out, int *node_b_out) {
+    int e = use(c);
+    if (e) return e;
+    const int n = c->n;
+    if (n < 2) return fail(TSPCUDA_INVALID_ARGUMENT, "extra mileage needs at least two nodes");
+    if (node_a >= 0 && (node_a >= n || node_b < 0 || node_b >= n || node_a == node_b))
+        return fail(TSPCUDA_INVALID_ARGUMENT, "initial edge (%d,%d)", node_a, node_b);
+    DevBuf vis, eu, ev, best, bedge, list, key, lc, cost, pair;
+    CK(cudaMalloc(&vis.p, sizeof(int) * n)); CK(cudaMalloc(&eu.p, sizeof(int) * n)); CK(cudaMalloc(&ev.p, sizeof(int) * n));
+    CK(cudaMalloc(&best.p, sizeof(int) * n)); CK(cudaMalloc(&bedge.p, sizeof(int) * n)); CK(cudaMalloc(&list.p, sizeof(int) * n));
+    CK(cudaMalloc(&key.p, sizeof(unsigned long long) * 2)); CK(cudaMalloc(&lc.p, sizeof(int) * 2));
+    CK(cudaMalloc(&cost.p, sizeof(long long))); CK(cudaMalloc(&pair.p, sizeof(int) * 2));
+    int h_pair[2] = {node_a, node_b};
+    CK(cudaEventRecord(c->ev0, c->stream));
+    if (node_a < 0) {                                   // EM_MAX, heuristics.c:169-178
+        CK(cudaMemsetAsync(key.p, 0, sizeof(unsigned long long), c->stream));
+        DISPATCH_METRIC(c->metric, (em_max_kernel<M><<<c->num_sms * 8, 256, 0, c->stream>>>(c->d_xy, n, key.as<unsigned long long>())));
+        c->stats.kernel_launches += 1;
+        CK(cudaGetLastError());
+        unsigned long long k = 0;
+        CK(cudaMemcpyAsync(&k, key.p, sizeof(k), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        const unsigned long long ij = 0x3FFFFFFFFull - (k & 0x3FFFFFFFFull);
+        h_pair[0] = k ? (int)(ij >> 17) : 0;
+        h_pair[1] = k ? (int)(ij & 0x1FFFF) : 1;
+    }
+    CK(cudaMemcpyAsync(pair.p, h_pair, sizeof(h_pair), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(key.p, 0xFF, sizeof(unsigned long long) * 2, c->stream));
+    EmState S;
+    S.visited = vis.as<int>(); S.eu = eu.as<int>(); S.ev = ev.as<int>(); S.best = best.as<int>(); S.bedge = bedge.as<int>();
+    S.path = c->d_path; S.list = list.as<int>(); S.key = key.as<unsigned long long>(); S.list_count = lc.as<int>();
+    S.cost = cost.as<long long>(); S.init_pair = pair.as<int>();
+    int bps = 0;
+    DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, extra_mileage_kernel<M, EM_BLOCK>, EM_BLOCK, 0)));
+    if (bps <= 0) return fail(TSPCUDA_INTERNAL, "extra mileage kernel cannot be resident");
+    const int grid = std::max(1, std::min(std::min(bps, 2) * c->num_sms, (n + EM_BLOCK - 1) / EM_BLOCK));
+    const double2 *xy = c->d_xy;
+    int nn = n;
+    void *args[] = {&xy, &nn, &S};
+    cudaError_t le = cudaSuccess;
+    DISPATCH_METRIC(c->metric, (le = cudaLaunchCooperativeKernel((void *)extra_mileage_kernel<M, EM_BLOCK>, dim3(grid), dim3(EM_BLOCK), args, 0, c->stream)));
+    CK(le);
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->stats.kernel_launches += 1;
+    long long h_cost = 0;
+    CK(cudaMemcpyAsync(&h_cost, cost.p, sizeof(h_cost), cudaMemcpyDeviceToHost, c->stream));
+    if (path_out) CK(cudaMemcpyAsync(c->h_buf, c->d_path, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.last_kernel_ms = ms;
+    c->stats.d2h_bytes += 8 + (path_out ? (int64_t)sizeof(int) * n : 0);
+    c->tour_loaded = false;
+    if (path_out) std::memcpy(path_out, c->h_buf, sizeof(int) * n);
+    if (cost_out) *cost_out = (double)h_cost;
+    if (node_a_out) *node_a_out = h_pair[0];
+    if (node_b_out) *node_b_out = h_pair[1];
+    return TSPCUDA_OK;
+}
 
 // ===== the `costs`-argument paths: a caller-supplied dense matrix (matrix.cuh) ========================
 struct tspcuda_mx {
