@@ -674,3 +674,22 @@ def test_extra_mileage_vs_oracle(tsp, oracle, n, integer):
                 p, c, ab = I.extra_mileage(n - 1, 1)
                 po, co = oracle.extra_mileage(xy, n - 1, 1, wt)
                 assert c == co and np.array_equal(p, po)
+
+
+@pytest.mark.parametrize("scan", ["pruned", "auto"])
+def test_pruned_scan_degenerate_geometry(tsp, oracle, scan):
+    """Grids with one row / one column / one cell: collinear nodes, a single cluster of coincident nodes
+    plus outliers, two far-apart clusters (empty cells in between)."""
+    rng = np.random.default_rng(5)
+    n = 300
+    line_x = np.stack([np.round(rng.uniform(0, 5000, n)), np.full(n, 17.0)], -1)
+    line_y = np.stack([np.full(n, -3.0), rng.uniform(0, 900, n)], -1)
+    blob = np.zeros((n, 2)); blob[:10] = np.round(rng.uniform(0, 50, (10, 2)))
+    two = np.round(np.concatenate([rng.uniform(0, 100, (n // 2, 2)), rng.uniform(1e6, 1e6 + 100, (n - n // 2, 2))]))
+    for k, xy in enumerate((line_x, line_y, blob, two)):
+        xy = np.ascontiguousarray(xy)
+        path = _rand_tour(k, n)
+        m_o, p_o, c_o, la, lb, ld = oracle.two_opt(xy, path)
+        with _inst(tsp, xy, scan) as I:
+            code, moves, p2, c2, log = I.two_opt(path, log_cap=len(la) + 8)
+        assert moves == m_o and c2 == c_o and log == _log3(la, lb, ld) and np.array_equal(p2, p_o), k
