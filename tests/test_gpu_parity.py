@@ -693,3 +693,28 @@ def test_pruned_scan_degenerate_geometry(tsp, oracle, scan):
         with _inst(tsp, xy, scan) as I:
             code, moves, p2, c2, log = I.two_opt(path, log_cap=len(la) + 8)
         assert moves == m_o and c2 == c_o and log == _log3(la, lb, ld) and np.array_equal(p2, p_o), k
+
+
+@pytest.mark.parametrize("mode", ["grid", "list"])
+def test_nn_kernels_agree(tsp, oracle, monkeypatch, mode):
+    """K4 (every unvisited node per step) and K4b (grid squares, cost_floor stopping rule) must build the
+    reference's tour: random / clustered / lattice (ties) instances against the oracle, several starts."""
+    monkeypatch.setenv("TSPCUDA_NN", mode)
+    rng = np.random.default_rng(11)
+    clustered = np.round(np.concatenate([rng.normal(c, 30, (150, 2)) for c in ((0, 0), (5000, 200), (300, 9000), (7000, 7000))]))
+    lattice = np.stack(np.meshgrid(np.arange(25.0), np.arange(20.0)), -1).reshape(-1, 2) * 7.0
+    for xy in (_rand_xy(3, 900, False), np.ascontiguousarray(clustered), np.ascontiguousarray(lattice)):
+        n = xy.shape[0]
+        with tsp.Instance(xy) as I:
+            for start in (0, n // 2, n - 1):
+                e, po, co = oracle.nn(xy, start)
+                code, p, c = I.nn(start)
+                assert code == 0 and c == co and np.array_equal(p, po), (mode, n, start)
+            bs, bp, bc, costs = I.nn_multi(0, 40)
+            assert [int(x) for x in costs] == [int(oracle.nn(xy, s)[2]) for s in range(40)]
+    for wt, twt in ((CEIL_2D, tsp.CEIL_2D), (ATT, tsp.ATT)):
+        xy = _rand_xy(8, 700, True, lo=0, hi=4000)
+        with tsp.Instance(xy, twt) as I:
+            e, po, co = oracle.nn(xy, 5, wt)
+            code, p, c = I.nn(5)
+            assert c == co and np.array_equal(p, po), (mode, wt)

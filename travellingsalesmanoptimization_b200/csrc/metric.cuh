@@ -64,6 +64,8 @@ struct EucGeneral {
     // Euclidean radius that contains every w with cost(u,w) < r (pruned.cuh): cost <= r-1 means
     // sqrtf(f) < r - 0.5 with f, sqrtf within 2^-23 relative of the exact values.
     static __device__ __forceinline__ double radius(double r) { return r * 1.000001 + 1.0; }
+    // a cost every node at Euclidean distance >= d is guaranteed to reach (grid-accelerated NN, pruned.cuh)
+    static __device__ __forceinline__ double cost_floor(double d) { return d * 0.999999 - 1.0; }
 };
 
 // All-integer coordinates below 2^25: every intermediate is an exact integer < 2^53, so FMAs are
@@ -77,6 +79,7 @@ struct EucInt {
         return koff_from_sumsq(__double2float_rn(s));
     }
     static __device__ __forceinline__ double radius(double r) { return r * 1.000001 + 1.0; }
+    static __device__ __forceinline__ double cost_floor(double d) { return d * 0.999999 - 1.0; }
 };
 
 // TSPLIB95 CEIL_2D: ceil(sqrt(dx^2+dy^2)) in double.
@@ -88,6 +91,7 @@ struct Ceil2D {
         return KOFF + (int)ceil(__dsqrt_rn(s));
     }
     static __device__ __forceinline__ double radius(double r) { return r * 1.000001 + 1.0; }      // ceil(d) < r => d < r
+    static __device__ __forceinline__ double cost_floor(double d) { return d * 0.999999 - 1.0; }
 };
 
 // TSPLIB95 ATT: r = sqrt((dx^2+dy^2)/10); t = nint(r); t < r ? t+1 : t.
@@ -102,6 +106,7 @@ struct Att {
     }
     // cost >= sqrt(s/10) - 1  =>  cost < r implies d < (r + 1) * sqrt(10)
     static __device__ __forceinline__ double radius(double r) { return (r + 1.0) * 3.1622777 + 1.0; }
+    static __device__ __forceinline__ double cost_floor(double d) { return d * 0.3162277 - 2.0; }
 };
 
 // TSPLIB95 GEO (section 2.4).  The node "coordinates" this functor sees are (latitude, longitude) in
@@ -118,6 +123,7 @@ struct Geo {
         return KOFF + (int)__dadd_rn(__dmul_rn(6378.388, acos(f)), 1.0);
     }
     static __device__ __forceinline__ double radius(double r) { return r; }     // unused: no pruned scan for GEO
+    static __device__ __forceinline__ double cost_floor(double) { return -1.0; }  // unused
 };
 
 __device__ __forceinline__ double geo_radians(double v) {

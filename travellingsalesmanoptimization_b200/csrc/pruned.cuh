@@ -101,6 +101,113 @@ __global__ void grid_fill_kernel(SpatialGrid G, const double2 *xy, int n, int *c
     }
 }
 
+// ---- K4b: nearest neighbour with the grid (heuristics.c:216-288), one CTA per start ---------------
+// The plain kernel (K4, kernels.cuh) looks at every unvisited node in every step.  Here a step looks at
+// the square of cells of half-width r = 1, 2, 4, ... around the current node: that square contains every
+// node closer than r cells, so once the best unvisited node found in it costs less than any node
+// farther than that can cost (Metric::cost_floor) it is the reference's choice -- same packed
+// (cost, node id) argmin, i.e. lowest cost, then lowest id (heuristics.c:253-263).  When the square would
+// hold more nodes than are left, the step scans the compacted list of remaining nodes instead (late in
+// the construction the neighbourhood is exhausted and the next node is far away).
+constexpr int NNG_BLOCK = 512;
+
+template <class M>
+__global__ void __launch_bounds__(NNG_BLOCK)
+nn_grid_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, int first_start, int stride, double2 *cand_xy_all,
+               int *cand_id_all, int *slot_all, int *order_all, long long *cost_out) {
+    extern __shared__ unsigned s_vis[];              // visited bitmap, (n + 31) / 32 words
+    __shared__ unsigned long long s_wkey[NNG_BLOCK / 32];
+    __shared__ unsigned long long s_key;
+    const int sidx = blockIdx.x;
+    const int start = first_start + sidx * stride;
+    double2 *cxy = cand_xy_all + (size_t)sidx * n;
+    int *cid = cand_id_all + (size_t)sidx * n;
+    int *slot = slot_all + (size_t)sidx * n;
+    int *order = order_all + (size_t)sidx * n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double cell = 1.0 / G.inv_cell;
+
+    for (int k = tid; k < (n + 31) / 32; k += NNG_BLOCK) s_vis[k] = 0;
+    for (int k = tid; k < n - 1; k += NNG_BLOCK) {
+        const int node = k + (k >= start ? 1 : 0);
+        cxy[k] = xy[node];
+        cid[k] = node;
+        slot[node] = k;
+    }
+    if (tid == 0) order[0] = start;
+    __syncthreads();
+    if (tid == 0) s_vis[start >> 5] |= 1u << (start & 31);
+    __syncthreads();
+    int cur_node = start;
+    long long cost = 0;
+    int m = n - 1;                                   // unvisited nodes = live entries of the compacted list
+    for (int step = 1; step < n; ++step, --m) {
+        const double2 cur = xy[cur_node];
+        const int ccx = max(0, min(G.W - 1, __double2int_rd((cur.x - G.gx0) * G.inv_cell)));
+        const int ccy = max(0, min(G.H - 1, __double2int_rd((cur.y - G.gy0) * G.inv_cell)));
+        unsigned long long found = KEY_EMPTY;
+        for (int r = 1;; r *= 2) {
+            const int x0 = max(0, ccx - r), x1 = min(G.W - 1, ccx + r), y0 = max(0, ccy - r), y1 = min(G.H - 1, ccy + r);
+            const bool whole = x0 == 0 && y0 == 0 && x1 == G.W - 1 && y1 == G.H - 1;
+            const long long box_nodes_est = 2LL * (x1 - x0 + 1) * (y1 - y0 + 1);
+            unsigned long long bk = KEY_EMPTY;
+            if (whole || box_nodes_est > m) {
+                // remaining nodes are fewer than the square holds: scan the compacted list (complete by itself)
+                for (int k = tid; k < m; k += NNG_BLOCK) {
+                    const double2 p = cxy[k];
+                    const int d = M::K(cur.x, cur.y, p.x, p.y) - KOFF;
+                    bk = min(bk, ((unsigned long long)(unsigned)d << 32) | (unsigned)cid[k]);
+                }
+            } else {
+                const int rows = y1 - y0 + 1;
+                for (int ry = warp; ry < rows; ry += NNG_BLOCK / 32) {       // one warp per cell row of the square
+                    const int cy = y0 + ry;
+                    const int lo = G.cell_start[cy * G.W + x0], hi = G.cell_start[cy * G.W + x1 + 1];
+                    for (int k = lo + lane; k < hi; k += 32) {
+                        const int w = G.cnode[k];
+                        if ((s_vis[w >> 5] >> (w & 31)) & 1u) continue;
+                        const double2 p = G.cxy[k];
+                        const int d = M::K(cur.x, cur.y, p.x, p.y) - KOFF;
+                        bk = min(bk, ((unsigned long long)(unsigned)d << 32) | (unsigned)w);
+                    }
+                }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) bk = min(bk, __shfl_down_sync(FULL, bk, off));
+            if (lane == 0) s_wkey[warp] = bk;
+            __syncthreads();
+            if (warp == 0) {
+                bk = (lane < NNG_BLOCK / 32) ? s_wkey[lane] : KEY_EMPTY;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) bk = min(bk, __shfl_down_sync(FULL, bk, off));
+                if (lane == 0) s_key = bk;
+            }
+            __syncthreads();
+            found = s_key;
+            __syncthreads();                         // s_key / s_wkey are rewritten by the next attempt
+            if (whole || box_nodes_est > m) break;   // complete scans
+            // nodes outside the square are at least r cells away (the current node lies inside its own cell)
+            if (found != KEY_EMPTY && (double)(found >> 32) < M::cost_floor((double)r * cell)) break;
+        }
+        const int w = (int)(found & 0xFFFFFFFFu);
+        if (tid == 0) {
+            order[step] = w;
+            s_vis[w >> 5] |= 1u << (w & 31);
+            const int s = slot[w], last = m - 1;     // swap-remove from the compacted list
+            const int lid = cid[last];
+            cxy[s] = cxy[last]; cid[s] = lid; slot[lid] = s;
+        }
+        cost += (long long)(found >> 32);
+        cur_node = w;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const double2 cur = xy[cur_node], s0 = xy[start];
+        const long long closing = (n > 1) ? (long long)(M::K(cur.x, cur.y, s0.x, s0.y) - KOFF) : -1;   // heuristics.c:282
+        cost_out[sidx] = cost + closing;
+    }
+}
+
 // ---- candidate evaluation ---------------------------------------------------------------------
 // Everything a search around the node at position p needs, loaded once.
 struct Probe {

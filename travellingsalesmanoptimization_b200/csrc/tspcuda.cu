@@ -704,16 +704,31 @@ extern "C" int tspcuda_tabu_search(tspcuda_ctx *c, int *path, double *cost_inout
 }
 
 // ---- nearest neighbour ----------------------------------------------------------------------
+struct NNScratch;
+static bool nn_use_grid(const tspcuda_ctx *c) {
+    if (c->metric == M_GEO || c->pruned_blocks <= 0) return false;      // the grid is Euclidean
+    if (const char *f = getenv("TSPCUDA_NN")) {
+        if (!strcmp(f, "grid")) return true;
+        if (!strcmp(f, "list")) return false;
+    }
+    return c->n >= 12000;          // below, a step of the plain kernel is a handful of iterations per thread
+}
+
 struct NNScratch {
     double2 *cxy = nullptr;
-    int *cid = nullptr, *order = nullptr;
+    int *cid = nullptr, *order = nullptr, *slot = nullptr;
     long long *cost = nullptr;
-    ~NNScratch() { cudaFree(cxy); cudaFree(cid); cudaFree(order); cudaFree(cost); }
+    ~NNScratch() { cudaFree(cxy); cudaFree(cid); cudaFree(order); cudaFree(slot); cudaFree(cost); }
 };
 
 static int nn_batch(tspcuda_ctx *c, NNScratch &S, int first_start, int count, int stride, long long *h_cost) {
     const int n = c->n;
-    DISPATCH_METRIC(c->metric, (nn_kernel<M><<<count, NN_BLOCK, 0, c->stream>>>(c->d_xy, n, first_start, stride, S.cxy, S.cid, S.order, S.cost)));
+    if (S.slot) {                                     // K4b: grid-accelerated (nn_alloc decided)
+        const size_t smem = sizeof(unsigned) * (((size_t)n + 31) / 32);
+        DISPATCH_METRIC(c->metric, (nn_grid_kernel<M><<<count, NNG_BLOCK, smem, c->stream>>>(c->d_xy, n, c->grid, first_start, stride, S.cxy, S.cid, S.slot, S.order, S.cost)));
+    } else {
+        DISPATCH_METRIC(c->metric, (nn_kernel<M><<<count, NN_BLOCK, 0, c->stream>>>(c->d_xy, n, first_start, stride, S.cxy, S.cid, S.order, S.cost)));
+    }
     c->stats.kernel_launches += 1;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(h_cost, S.cost, sizeof(long long) * count, cudaMemcpyDeviceToHost, c->stream));
@@ -728,6 +743,7 @@ static int nn_alloc(tspcuda_ctx *c, NNScratch &S, int batch) {
     CK(cudaMalloc(&S.cid, sizeof(int) * n * batch));
     CK(cudaMalloc(&S.order, sizeof(int) * n * batch));
     CK(cudaMalloc(&S.cost, sizeof(long long) * batch));
+    if (nn_use_grid(c)) CK(cudaMalloc(&S.slot, sizeof(int) * n * batch));
     return TSPCUDA_OK;
 }
 
