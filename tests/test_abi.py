@@ -69,3 +69,11 @@ def test_sass_is_sm100a():
     T.lib()
     out = subprocess.run(["cuobjdump", "-lelf", T.LIB], capture_output=True, text=True).stdout
     assert "sm_100a" in out
+
+
+def test_graft_entry_build_runs():
+    """The driver's "does it build" check: __graft_entry__.build() must compile every native artefact."""
+    import __graft_entry__ as g
+    g.build()
+    import travellingsalesmanoptimization_b200 as T
+    assert os.path.exists(T.LIB)
