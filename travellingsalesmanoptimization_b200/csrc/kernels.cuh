@@ -59,6 +59,7 @@ struct DescState {
     int status;            // 0 running / move cap hit, 1 local optimum (no admissible move)
     int last_a, last_b, last_delta;
     long long candidates;  // candidate nodes examined by the pruned scan (pruned.cuh)
+    long long phase_sum;   // -DTSP_PHASE_TIMING: sum over warps and scans of the phase-1 duration
     long long phase_ns[6]; // -DTSP_PHASE_TIMING: ns in scan phase 1 / phase 2 / apply (each incl. its barrier), -, units, boxes
 };
 

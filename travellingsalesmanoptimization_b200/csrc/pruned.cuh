@@ -46,6 +46,10 @@ constexpr int PRUNED_BLOCK = TSP_PRUNED_BLOCK;
 #ifndef TSP_PR_NC
 #define TSP_PR_NC 4
 #endif
+#ifndef TSP_PR_NC_BIG
+#define TSP_PR_NC_BIG 4
+#endif
+constexpr int PR_NC_BIG = TSP_PR_NC_BIG;    // the same for 1024-thread CTAs (64 registers per thread)
 constexpr int PR_NC = TSP_PR_NC;            // candidates evaluated together (latency overlap), phase 1
 #ifndef TSP_PR_NC2
 #define TSP_PR_NC2 2
@@ -303,15 +307,134 @@ __device__ __forceinline__ bool probe_box(const SpatialGrid &G, const Probe &P, 
     return true;
 }
 
+// ---- collect / evaluate ---------------------------------------------------------------------------
+// A search only needs the candidate's coordinates to decide whether it can matter (cost(u,w) below one
+// of the two tour-edge costs at u); everything after that -- pos[w], the neighbours' coordinates, the
+// edge costs at q, the second new edge -- is a chain of dependent gathers.  The searches therefore only
+// COLLECT the passing (p, w, cost, which-edge) records into a buffer private to the warp (ballot
+// compaction, no atomics), and the records are EVALUATED afterwards one per lane, several in flight
+// per lane: every lane busy whatever the box sizes were, and no gather chain inside the search loops.
+#ifndef TSP_PR_WBUF
+#define TSP_PR_WBUF 2048
+#endif
+constexpr int PR_WBUF = TSP_PR_WBUF;        // records per warp buffer (16 bytes each); flushed when nearly full
+
+template <class M, int NE>
+__device__ __forceinline__ void pairs_eval(const TourView &V, const PosPatch &F, const uint4 *wbuf, int count, int &best,
+                                           unsigned long long &bestkey) {
+    const int n = V.n;
+    const int lane = threadIdx.x & 31;
+    for (int base = 0; base < count; base += 32 * NE) {
+        uint4 e[NE];
+        int q[NE];
+        bool ok[NE];
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+            const int idx = base + lane + 32 * j;
+            e[j] = wbuf[min(idx, count - 1)];
+            if (idx >= count) e[j].w = 0;
+        }
+#pragma unroll
+        for (int j = 0; j < NE; ++j) q[j] = V.pos[e[j].y];
+#pragma unroll
+        for (int j = 0; j < NE; ++j) {
+            if ((int)e[j].y == F.node0) q[j] = F.pos0;
+            if ((int)e[j].y == F.node1) q[j] = F.pos1;
+            const int diff = abs((int)e[j].x - q[j]);
+            ok[j] = diff > 1 && diff != n - 1;                   // same node / tour neighbours: refinment.c:55
+        }
+        {   // pairs {p, q}: edges (p,p+1), (q,q+1) out, (p,q), (p+1,q+1) in
+            double2 s1[NE], w1[NE];
+            int dp[NE], dq[NE];
+#pragma unroll
+            for (int j = 0; j < NE; ++j) {
+                const bool c1 = ok[j] && (e[j].w & 1u);
+                const int p = (int)e[j].x;
+                s1[j] = V.pxy[c1 ? p + 1 : 0];
+                w1[j] = V.pxy[c1 ? q[j] + 1 : 0];
+                dp[j] = V.dn[c1 ? p : 0];
+                dq[j] = V.dn[c1 ? q[j] : 0];
+            }
+#pragma unroll
+            for (int j = 0; j < NE; ++j) {
+                if (ok[j] && (e[j].w & 1u)) {
+                    const int K2 = M::K(s1[j].x, s1[j].y, w1[j].x, w1[j].y);
+                    const int d = (int)(e[j].z + (unsigned)K2 - (unsigned)dp[j] - (unsigned)dq[j]);
+                    if (d <= best) {
+                        best = d;
+                        const unsigned long long key = pack_key(d, V.tid[e[j].x], (int)e[j].y);
+                        if (key < bestkey) bestkey = key;
+                    }
+                }
+            }
+        }
+        {   // pairs {p-1, q-1}: (p,q) is their second new edge
+            double2 s2[NE], w2[NE];
+            int dpm[NE], dqm[NE], pm[NE], qm[NE];
+#pragma unroll
+            for (int j = 0; j < NE; ++j) {
+                const bool c2 = ok[j] && (e[j].w & 2u);
+                const int p = (int)e[j].x;
+                pm[j] = p == 0 ? n - 1 : p - 1;
+                qm[j] = q[j] == 0 ? n - 1 : q[j] - 1;
+                s2[j] = V.pxy[c2 ? pm[j] : 0];
+                w2[j] = V.pxy[c2 ? qm[j] : 0];
+                dpm[j] = V.dn[c2 ? pm[j] : 0];
+                dqm[j] = V.dn[c2 ? qm[j] : 0];
+            }
+#pragma unroll
+            for (int j = 0; j < NE; ++j) {
+                if (ok[j] && (e[j].w & 2u)) {
+                    const int K2 = M::K(s2[j].x, s2[j].y, w2[j].x, w2[j].y);
+                    const int d = (int)((unsigned)K2 + e[j].z - (unsigned)dpm[j] - (unsigned)dqm[j]);
+                    if (d <= best) {
+                        best = d;
+                        const unsigned long long key = pack_key(d, V.tid[pm[j]], V.tid[qm[j]]);
+                        if (key < bestkey) bestkey = key;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// One trip of a search: NCC candidates per lane (slot kk[j] of the cell-sorted arrays, valid[j]) of the
+// search around position p (node coordinates ux/uy, edge costs dnp = dn[p], dnm = dn[p-1]).
+template <class M, int NCC, int NE>
+__device__ __forceinline__ void collect_trip(const TourView &V, const SpatialGrid &G, const PosPatch &F, int p, double ux,
+                                             double uy, int dnp, int dnm, const int (&kk)[NCC], const bool (&valid)[NCC],
+                                             uint4 *wbuf, int &wcount, int &best, unsigned long long &bestkey) {
+    const int lane = threadIdx.x & 31;
+    if (wcount > PR_WBUF - 32 * NCC) {                 // warp-uniform: flush
+        __syncwarp();
+        pairs_eval<M, NE>(V, F, wbuf, wcount, best, bestkey);
+        __syncwarp();
+        wcount = 0;
+    }
+    double2 c[NCC];
+    int w[NCC];
+#pragma unroll
+    for (int j = 0; j < NCC; ++j) { c[j] = G.cxy[kk[j]]; w[j] = G.cnode[kk[j]]; }
+#pragma unroll
+    for (int j = 0; j < NCC; ++j) {
+        const int K = M::K(ux, uy, c[j].x, c[j].y);
+        const unsigned type = valid[j] ? ((K < dnp ? 1u : 0u) | (K < dnm ? 2u : 0u)) : 0u;
+        const unsigned mask = __ballot_sync(FULL, type != 0);
+        if (type) wbuf[wcount + __popc(mask & ((1u << lane) - 1))] = make_uint4((unsigned)p, (unsigned)w[j], (unsigned)K, type);
+        wcount += __popc(mask);
+    }
+}
+
 // ---- the two scan phases, shared by the whole-GPU kernel (K7) and the CTA-per-descent kernel (K8) --
 // Phase 1: thread `t` of `nthreads` cooperating threads (a grid or one CTA; t's warp is complete and
 // nthreads is a multiple of 32) takes tour positions t, t + nthreads, ...  Search boxes with at most
 // PR_SMALL_NODES nodes are walked inline, larger ones are appended to boxes[] through the packed
 // counter *qctr (boxes in the high 24 bits, cell rows in the low 40; one atomic per warp).
-template <class M, int NC1>
+template <class M, int NC1, int NE>
 __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGrid &G, const PosPatch &F, int t, int nthreads,
-                                              unsigned long long *qctr, BigBox *boxes, int &best,
+                                              unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, int &best,
                                               unsigned long long &bestkey, long long &ncand) {
+    int wcount = 0;
     const int n = V.n;
     const int lane = threadIdx.x & 31;
     for (int p0 = t - lane; p0 < n; p0 += nthreads) {              // warp-uniform trip count
@@ -359,45 +482,42 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
                 boxes[(old >> 40) + __popc(bigmask & ((1u << lane) - 1))] = bx;
             }
         }
-        if (has && !big) {
-            ncand += total;
-            // the box's candidates as ONE stream across its cell rows (row bounds are L1 hits by now),
-            // NC1 at a time through the staged evaluation
-            int cy = cy0, k = 0, hi = 0, last = 0;
-            for (int done = 0; done < total; done += NC1) {
-                int w[NC1]; double wx[NC1], wy[NC1]; bool valid[NC1];
-                int kk[NC1];
+        // the small boxes of the warp's 32 positions, in lockstep: each lane streams ITS box across its cell
+        // rows (row bounds are L1 hits by now), NC1 candidates per trip, into the warp's record buffer
+        const int mytotal = (has && !big) ? total : 0;
+        ncand += mytotal;
+        const int maxtotal = __reduce_max_sync(FULL, mytotal);
+        int cy = cy0, k = 0, hi = 0, last = 0;
+        for (int done = 0; done < maxtotal; done += NC1) {
+            int kk[NC1];
+            bool valid[NC1];
 #pragma unroll
-                for (int j = 0; j < NC1; ++j) {
-                    valid[j] = done + j < total;
-                    if (valid[j]) {
-                        while (k >= hi) {
-                            k = G.cell_start[cy * G.W + cx0];
-                            hi = G.cell_start[cy * G.W + cx1 + 1];
-                            ++cy;
-                        }
-                        last = k++;
+            for (int j = 0; j < NC1; ++j) {
+                valid[j] = done + j < mytotal;
+                if (valid[j]) {
+                    while (k >= hi) {
+                        k = G.cell_start[cy * G.W + cx0];
+                        hi = G.cell_start[cy * G.W + cx1 + 1];
+                        ++cy;
                     }
-                    kk[j] = last;
+                    last = k++;
                 }
-#pragma unroll
-                for (int j = 0; j < NC1; ++j) {
-                    const double2 c = G.cxy[kk[j]];
-                    w[j] = G.cnode[kk[j]]; wx[j] = c.x; wy[j] = c.y;
-                }
-                cand_eval_n<M, NC1>(V, P, F, w, wx, wy, valid, best, bestkey);
+                kk[j] = last;
             }
+            collect_trip<M, NC1, NE>(V, G, F, p, P.ux, P.uy, P.dnp, P.dnm, kk, valid, wbuf, wcount, best, bestkey);
         }
     }
+    __syncwarp();
+    pairs_eval<M, NE>(V, F, wbuf, wcount, best, bestkey);
 }
 
 // Phase 2 (behind a barrier): the queued boxes, cut into (box, cell row) units -- one contiguous
 // range of the cell-sorted node array each -- split evenly over the `nwarps` cooperating warps;
 // this warp is number `gw`.  q = the packed counter after phase 1.
-template <class M>
+template <class M, int NE>
 __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGrid &G, const PosPatch &F, long long gw,
-                                              long long nwarps, unsigned long long q, const BigBox *boxes, int &best,
-                                              unsigned long long &bestkey, long long &ncand) {
+                                              long long nwarps, unsigned long long q, const BigBox *boxes, uint4 *wbuf,
+                                              int &best, unsigned long long &bestkey, long long &ncand) {
     const int lane = threadIdx.x & 31;
     const long long nunits = (long long)(q & PR_UNIT_MASK);
     const int nboxes = (int)(q >> 40);
@@ -405,6 +525,7 @@ __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGr
     const long long per = (nunits + nwarps - 1) / nwarps;
     const long long g0 = gw * per, g1 = min(nunits, g0 + per);
     if (g0 >= g1) return;
+    int wcount = 0;
     // last box with base <= g0: 33-ary search, one probe per lane and step
     int lo_b = 0, hi_b = nboxes;
     while (hi_b - lo_b > 1) {
@@ -425,27 +546,30 @@ __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGr
         const int cy = b.cy0 + (int)(g - b.base);
         const int lo = G.cell_start[cy * G.W + b.cx0], hi = G.cell_start[cy * G.W + b.cx1 + 1];
         if (lane == 0) ncand += hi - lo;
-        for (int k = lo + lane; k < hi; k += 32 * PR_NC2) {
-            int w[PR_NC2]; double wx[PR_NC2], wy[PR_NC2]; bool valid[PR_NC2];
+        for (int k0 = lo; k0 < hi; k0 += 32 * PR_NC2) {           // warp-uniform trips over the row
+            int kk[PR_NC2];
+            bool valid[PR_NC2];
 #pragma unroll
             for (int j = 0; j < PR_NC2; ++j) {
-                valid[j] = k + 32 * j < hi;
-                const int kk = min(k + 32 * j, hi - 1);
-                const double2 c = G.cxy[kk];
-                w[j] = G.cnode[kk]; wx[j] = c.x; wy[j] = c.y;
+                const int k = k0 + lane + 32 * j;
+                valid[j] = k < hi;
+                kk[j] = min(k, hi - 1);
             }
-            cand_eval_n<M, PR_NC2>(V, P, F, w, wx, wy, valid, best, bestkey);
+            collect_trip<M, PR_NC2, NE>(V, G, F, b.p, P.ux, P.uy, P.dnp, P.dnm, kk, valid, wbuf, wcount, best, bestkey);
         }
     }
+    __syncwarp();
+    pairs_eval<M, NE>(V, F, wbuf, wcount, best, bestkey);
 }
 
 // ---- K7: whole-GPU persistent pruned descent (cooperative launch, one CTA per SM) ----------------
 template <class M, int BLK>
 __global__ void __launch_bounds__(BLK, 1)
 descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
-                      long long max_moves, unsigned long long *qctr, BigBox *boxes) {
+                      long long max_moves, unsigned long long *qctr, BigBox *boxes, uint4 *wbuf_all) {
     constexpr int WARPS = BLK / 32;
-    constexpr int NC1 = BLK > 512 ? 2 : PR_NC;      // 1024-thread CTAs have 64 registers per thread
+    constexpr int NC1 = BLK > 512 ? PR_NC_BIG : PR_NC;   // candidates per lane and trip while collecting
+    constexpr int NE = BLK > 512 ? 2 : 4;                // records in flight per lane while evaluating (64 / 128 registers)
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned long long s_key;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -453,6 +577,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
     const int gsize = gridDim.x * BLK;
     const long long gw = (long long)blockIdx.x * WARPS + warp;
     const long long Wtot = (long long)gridDim.x * WARPS;
+    uint4 *wbuf = wbuf_all + (size_t)gw * PR_WBUF;
     PosPatch F = {-1, 0, -1, 0};
 #ifdef TSP_PHASE_TIMING
     unsigned long long tprev = 0;
@@ -474,7 +599,16 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         int best = -1;
         unsigned long long bestkey = KEY_EMPTY;
         long long ncand = 0;
-        pruned_phase1<M, NC1>(V, G, F, gtid, gsize, qctr, boxes, best, bestkey, ncand);
+#ifdef TSP_PHASE_TIMING
+        unsigned long long tw0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw0));
+#endif
+        pruned_phase1<M, NC1, NE>(V, G, F, gtid, gsize, qctr, boxes, wbuf, best, bestkey, ncand);
+#ifdef TSP_PHASE_TIMING
+        {   // slowest and average warp of phase 1 (phase_ns[3] = sum over scans of the max, [4]/[5] reused below)
+            unsigned long long tw1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw1));
+            if (lane == 0) { atomicMax((unsigned long long *)&st->phase_ns[3], tw1 - tw0); atomicAdd((unsigned long long *)&st->phase_sum, tw1 - tw0); }
+        }
+#endif
         grid.sync();
         PHASE_MARK(0)
         {
@@ -482,7 +616,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #ifdef TSP_PHASE_TIMING
             if (gtid == 0) { st->phase_ns[4] += (long long)(q & PR_UNIT_MASK); st->phase_ns[5] += (long long)(q >> 40); }
 #endif
-            pruned_phase2<M>(V, G, F, gw, Wtot, q, boxes, best, bestkey, ncand);
+            pruned_phase2<M, NE>(V, G, F, gw, Wtot, q, boxes, wbuf, best, bestkey, ncand);
         }
         bestkey = warp_min_key(bestkey);
         for (int off = 16; off > 0; off >>= 1) ncand += __shfl_down_sync(FULL, ncand, off);
@@ -541,9 +675,10 @@ template <class M, int BLK>
 __global__ void __launch_bounds__(BLK, 1)
 multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const int *__restrict__ order_all, int first_start,
                     int stride, int nstarts, int *next_start, MultiSlots S, long long *final_cost, long long *moves_out,
-                    unsigned long long *cand_total) {
+                    unsigned long long *cand_total, uint4 *wbuf_all) {
     constexpr int WARPS = BLK / 32;
-    constexpr int NC1 = BLK > 512 ? 2 : PR_NC;
+    constexpr int NC1 = BLK > 512 ? PR_NC_BIG : PR_NC;
+    constexpr int NE = BLK > 512 ? 2 : 4;
     __shared__ unsigned long long s_key, s_q;
     __shared__ long long s_cost, s_bestcost;
     __shared__ int s_cur;
@@ -558,6 +693,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     V.pos = S.pos + slot * (size_t)n;
     BigBox *boxes = S.boxes + slot * (size_t)n;
     int *best_path = S.best_path + slot * (size_t)n;
+    uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + warp) * PR_WBUF;
     if (t == 0) { s_bestcost = -1; S.best_cost[slot] = -1; S.best_start[slot] = -1; }
     long long ncand = 0;
 
@@ -593,9 +729,9 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             __syncthreads();
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
-            pruned_phase1<M, NC1>(V, G, F, t, BLK, &s_q, boxes, best, bestkey, ncand);
+            pruned_phase1<M, NC1, NE>(V, G, F, t, BLK, &s_q, boxes, wbuf, best, bestkey, ncand);
             __syncthreads();
-            pruned_phase2<M>(V, G, F, warp, WARPS, s_q, boxes, best, bestkey, ncand);
+            pruned_phase2<M, NE>(V, G, F, warp, WARPS, s_q, boxes, wbuf, best, bestkey, ncand);
             bestkey = warp_min_key(bestkey);
             if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
             __syncthreads();

@@ -79,6 +79,7 @@ struct tspcuda_ctx {
     double2 *d_cxy = nullptr;
     unsigned long long *d_qctr = nullptr;
     BigBox *d_boxes = nullptr;
+    uint4 *d_wbuf = nullptr;         // per-warp record buffers of the pruned kernels (num_sms * 32 warps)
     int pruned_blocks = 0;           // cooperative grid of descend_pruned_kernel (0: unavailable)
     int pruned_block = 0;            // its CTA size
     int scan_mode = TSPCUDA_SCAN_AUTO;
@@ -119,7 +120,7 @@ extern "C" void tspcuda_destroy(tspcuda_ctx *c) {
     cudaFree(c->d_tabu); cudaFree(c->d_key); cudaFree(c->d_state); cudaFree(c->d_log);
     cudaFree(c->d_matrix); cudaFree(c->d_sum); cudaFree(c->d_flush);
     cudaFree(c->d_cell_start); cudaFree(c->d_cell_count); cudaFree(c->d_cnode); cudaFree(c->d_cxy);
-    cudaFree(c->d_qctr); cudaFree(c->d_boxes);
+    cudaFree(c->d_qctr); cudaFree(c->d_boxes); cudaFree(c->d_wbuf);
     if (c->tev0) cudaEventDestroy(c->tev0);
     if (c->tev1) cudaEventDestroy(c->tev1);
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -237,6 +238,7 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         CKC(cudaMalloc(&c->d_cxy, sizeof(double2) * n));
         CKC(cudaMalloc(&c->d_qctr, sizeof(unsigned long long)));
         CKC(cudaMalloc(&c->d_boxes, sizeof(BigBox) * n));
+        CKC(cudaMalloc(&c->d_wbuf, sizeof(uint4) * (size_t)PR_WBUF * 32 * c->num_sms));
         G.cell_start = c->d_cell_start; G.cnode = c->d_cnode; G.cxy = c->d_cxy;
         CKC(cudaMemsetAsync(c->d_cell_count, 0, sizeof(int) * ncells, c->stream));
         CKC(cudaMemsetAsync(c->d_qctr, 0, sizeof(unsigned long long), c->stream));
@@ -360,7 +362,8 @@ static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max
     MoveRec *log = c->d_log;
     long long log_cap = c->log_cap;
     BigBox *boxes = c->d_boxes;
-    void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &qctr, &boxes};
+    uint4 *wbuf = c->d_wbuf;
+    void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &qctr, &boxes, &wbuf};
     if (c->pruned_block == 1024)
         return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, 1024>, dim3(grid), dim3(1024), args, 0, c->stream);
     return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
@@ -443,8 +446,10 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
         c->stats.last_kernel_ms = ms;
 #ifdef TSP_PHASE_TIMING
         if (pruned && c->h_state->status == 1)
-            fprintf(stderr, "[tspcuda] pruned phases: scan1 %.1f ms  scan2 %.1f ms  apply %.1f ms | units/scan %.0f boxes/scan %.0f\n",
-                    c->h_state->phase_ns[0] * 1e-6, c->h_state->phase_ns[1] * 1e-6, c->h_state->phase_ns[2] * 1e-6,
+            fprintf(stderr, "[tspcuda] pruned phases: scan1 %.1f ms (slowest warp ever %.1f us, mean warp %.2f us)  scan2 %.1f ms  apply %.1f ms | units/scan %.0f boxes/scan %.0f\n",
+                    c->h_state->phase_ns[0] * 1e-6, c->h_state->phase_ns[3] * 1e-3,
+                    c->h_state->phase_sum * 1e-3 / ((double)(c->h_state->moves + 1) * c->pruned_blocks * (c->pruned_block / 32)),
+                    c->h_state->phase_ns[1] * 1e-6, c->h_state->phase_ns[2] * 1e-6,
                     (double)c->h_state->phase_ns[4] / std::max<long long>(1, c->h_state->moves + 1),
                     (double)c->h_state->phase_ns[5] / std::max<long long>(1, c->h_state->moves + 1));
 #endif
@@ -875,11 +880,11 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
             if (k8_block == 1024) {
                 DISPATCH_METRIC(c->metric, (multi_pruned_kernel<M, 1024><<<g, 1024, 0, c->stream>>>(
                     c->d_xy, n, c->grid, S.order, fs, stride, cnt, next.as<int>(), MS, dcost.as<long long>(), dmoves.as<long long>(),
-                    m_cand.as<unsigned long long>())));
+                    m_cand.as<unsigned long long>(), c->d_wbuf)));
             } else {
                 DISPATCH_METRIC(c->metric, (multi_pruned_kernel<M, PRUNED_BLOCK><<<g, PRUNED_BLOCK, 0, c->stream>>>(
                     c->d_xy, n, c->grid, S.order, fs, stride, cnt, next.as<int>(), MS, dcost.as<long long>(), dmoves.as<long long>(),
-                    m_cand.as<unsigned long long>())));
+                    m_cand.as<unsigned long long>(), c->d_wbuf)));
             }
             CK(cudaGetLastError());
             CK(cudaEventRecord(c->ev1, c->stream));
