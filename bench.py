@@ -269,7 +269,7 @@ def main():
     pxu = I.pipe_rate(4)                                 # MUFU.RSQ /s: the XU pipe (also runs F2F.F32.F64)
     ach = 15.0 * pairs_per_launch / (avg_launch_ms * 1e-3)
     roofline = {"bound": "fp64", "achieved": ach / 1e12, "peak": p64 / 1e12, "unit": "TFLOP/s", "frac": ach / p64,
-                "traffic": None,
+                "traffic": 2.44e6,   # dram__bytes_read + write per launch, ncu --set full (profiles/r01_descend_pla85900_ncu.md): L2-resident
                 "note": "algorithmic 15 non-FMA FP64 flop per pair (SURVEY 8d: two fresh edge costs + delta) over the DADD "
                         "rate measured in this job; the kernel EXECUTES 4-5 FP64 + 2 XU ops per pair (one edge cost per "
                         "pair by diagonal reuse, integer delta), see roofline_executed and DESIGN.md",
