@@ -275,6 +275,13 @@ def main():
                         "pair by diagonal reuse, integer delta), see roofline_executed and DESIGN.md",
                 "kernel": "descend_kernel", "avg_launch_ms": avg_launch_ms, "pairs_per_launch": pairs_per_launch}
     rate = pairs_per_launch / (avg_launch_ms * 1e-3)
+    pseq = I.pipe_rate(9)                                # the scan's own edge-cost sequence, register-only, same job
+    pf2f = I.pipe_rate(8)
+    roofline_sequence = {"bound": "edge-cost sequence", "achieved": rate / 1e12, "peak": pseq / 1e12, "unit": "Tpair/s",
+                         "frac": rate / pseq,
+                         "note": "peak = the kernel's edge-cost instruction sequence (4 FP64, F2F.F32.F64, MUFU.RSQ, 3 packed FP32x2) "
+                                 "run from registers with nothing else, one cost per pair: what a scan that needs one edge cost per pair "
+                                 "can reach on this chip; F2F.F32.F64 alone runs at %.3g/s, MUFU.RSQ at %.3g/s" % (pf2f, pxu)}
     roofline_executed = {"bound": "xu", "achieved": 2.0 * rate / 1e12, "peak": pxu / 1e12, "unit": "Tinstr/s",
                          "frac": 2.0 * rate / pxu, "note": "F2F.F32.F64 + MUFU.RSQ per pair on the 16-lane/SM XU pipe"}
 
@@ -339,7 +346,7 @@ def main():
         "data": "TSPLIB pla85900 coordinates (tests/golden/instances); tours built on device",
         "config": dict(workload_config(args.workload, n, MOVES), parallelism="starts sharded block-cyclically, rank r -> start r",
                        best_tour_reduction_ms=red_ms, rank_ms=[round(v, 3) for v in rank_ms], best_cost=int(best_cost), best_start=int(best_start)),
-        "roofline": roofline, "roofline_executed": roofline_executed, "e2e": e2e, "gpu_launches": int(all_launches),
+        "roofline": roofline, "roofline_executed": roofline_executed, "roofline_sequence": roofline_sequence, "e2e": e2e, "gpu_launches": int(all_launches),
         "clocks": clocks, "scans": int(all_scans),
     }
     if multistart:

@@ -200,7 +200,9 @@ int tspcuda_timer_stop(tspcuda_ctx *ctx, double *ms_out);
 int tspcuda_flush_l2(tspcuda_ctx *ctx);
 /* Register-only pipe-rate microbenchmarks run on the context's device; result in operations/s
  * (thread-level, not warp-level).  kind: 0 DADD, 1 DMUL, 2 DFMA, 3 F2F.F32.F64, 4 MUFU.RSQ,
- * 5 FFMA, 6 the full EUC_REF edge-cost sequence (edge costs/s). */
+ * 5 FFMA, 6 the full EUC_REF edge-cost sequence (general coordinates), 7 the same for integer coordinates
+ * (edge costs/s: the arithmetic ceiling of a scan that needs one edge cost per pair), 8 F2F.F32.F64 alone,
+ * 9 the integer-coordinate sequence two costs at a time with packed FP32x2 instructions (what the scan runs). */
 int tspcuda_pipe_rate(tspcuda_ctx *ctx, int kind, double *ops_per_s_out);
 /* Exhaustive self-check of the in-kernel float sqrt against IEEE sqrt.rn.f32 over every float in
  * [2^-60, 2^64): number of mismatches in *mismatches_out (must be 0). */

@@ -1,4 +1,4 @@
-"""Time one build variant of libtspcuda.so (TSPCUDA_LIB) on pla85900 / usa13509 descents."""
+"""Time one build variant of libtspcuda.so (TSPCUDA_LIB) on full-scan (SCAN_FULL) descents."""
 import hashlib, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -9,6 +9,7 @@ out = []
 for name, moves, reps in (("pla85900", 32, 3), ("usa13509", 256, 2), ("pr2392", 300, 2)):
     xy, _ = load_instance(name)
     I = T.Instance(xy)
+    I.set_scan_mode(T.SCAN_FULL)
     code, p, c = I.nn(0)
     I.tour_upload(p); I.tour_descend(8)
     best = 0

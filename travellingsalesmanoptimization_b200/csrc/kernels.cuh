@@ -87,8 +87,9 @@ __device__ __forceinline__ void sweep_block(const TourView &V, int i0, int c, in
         const double2 cj = sxy[k];
         const int dj = sdn[k];
         int Dn[R + 1];
+        static_assert(R % 2 == 0, "rows are processed in pairs (packed FP32x2 cost sequence)");
 #pragma unroll
-        for (int r = 0; r < R; ++r) Dn[r] = M::K(rx[r], ry[r], cj.x, cj.y);
+        for (int r = 0; r < R; r += 2) M::K2(rx[r], ry[r], rx[r + 1], ry[r + 1], cj.x, cj.y, Dn[r], Dn[r + 1]);
         Dn[R] = __shfl_down_sync(FULL, Dn[0], 1);
         int m[R];
 #pragma unroll
@@ -145,7 +146,7 @@ __device__ void sweep_strip(const TourView &V, int s, int j0, int j1, int &best,
     {   // warm-up: D(row, j0)
         const double2 c0 = V.pxy[j0];
 #pragma unroll
-        for (int r = 0; r < R; ++r) Dp[r] = M::K(rx[r], ry[r], c0.x, c0.y);
+        for (int r = 0; r < R; r += 2) M::K2(rx[r], ry[r], rx[r + 1], ry[r + 1], c0.x, c0.y, Dp[r], Dp[r + 1]);
     }
     int c = j0 + 1;
     while (c <= j1 + 1) {
@@ -721,7 +722,12 @@ __global__ void pipe_rate_kernel(int iters, double seed, double *sink) {
             else if (KIND == 3) { f[k] = __double2float_rn(d[k]); d[k] = (double)f[k]; }
             else if (KIND == 4) { asm volatile("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(f[k]) : "f"(f[k])); }
             else if (KIND == 5) f[k] = __fmaf_rn(f[k], 1.0000001f, 1e-7f);
-            else if (KIND == 6) { int kk = EucGeneral::K(d[k], d[(k + 1) & 7], 3.25, 7.5); d[k] = d[k] + (double)(kk & 1) * 1e-12; }
+            // 6 / 7: the whole edge-cost sequence; the result flips the low mantissa bit of its own input (one
+            // integer instruction, no conversion) so that the chain cannot be hoisted
+            else if (KIND == 6) { int kk = EucGeneral::K(d[k], d[(k + 1) & 7], 3.25, 7.5); d[k] = __hiloint2double(__double2hiint(d[k]), __double2loint(d[k]) ^ (kk & 1)); }
+            else if (KIND == 8) { f[k] = __double2float_rn(d[k]); d[k] = __hiloint2double(__double2hiint(d[k]), __double2loint(d[k]) ^ (__float_as_int(f[k]) & 1)); }
+            else if (KIND == 9) { int ka, kb; EucInt::K2(d[k], d[(k + 1) & 7], d[(k + 1) & 7], d[k], 3.0, 7.0, ka, kb); d[k] = __hiloint2double(__double2hiint(d[k]), __double2loint(d[k]) ^ ((ka ^ kb) & 1)); }
+            else if (KIND == 7) { int kk = EucInt::K(d[k], d[(k + 1) & 7], 3.0, 7.0); d[k] = __hiloint2double(__double2hiint(d[k]), __double2loint(d[k]) ^ (kk & 1)); }
         }
     }
     double acc = 0;
@@ -738,6 +744,13 @@ __global__ void sqrt_selfcheck_kernel(unsigned lo_bits, unsigned hi_bits, unsign
         const float r0 = __fsqrt_rn(f);
         const float r1 = sqrt_rn_pos(f);
         if (__float_as_uint(r0) != __float_as_uint(r1)) bad++;
+        if (b < ((127u + 46u) << 23)) {               // costs below 2^23: the packed FP32x2 sequence, both halves
+            const float f2 = __uint_as_float((unsigned)b ^ 0x2A5A5u);
+            int k0, k1;
+            koff2_from_negsumsq(-f, -f2, k0, k1);
+            if ((unsigned)k0 != ((unsigned)koff_from_sumsq(f) ^ SCAN_FLIP)) bad++;
+            if ((unsigned)k1 != ((unsigned)koff_from_sumsq(f2) ^ SCAN_FLIP)) bad++;
+        }
     }
     if (bad) atomicAdd(mismatches, bad);
 }

@@ -5,7 +5,8 @@
 // which gcc -O3 (no -ffast-math, baseline x86-64 => no FMA) turns into
 //     subsd subsd mulsd mulsd addsd cvtsd2ss sqrtss cvtss2sd addsd(0.5) cvttsd2si cvtsi2sd.
 // EucGeneral / EucInt reproduce that value for every input whose cost is below 2^23 (checked at
-// context creation) with 4-5 FP64 instructions, one F2F.F32.F64, one MUFU.RSQ and 6-7 FP32 ones:
+// context creation) with 4-5 FP64 instructions, one F2F.F32.F64, one MUFU.RSQ and 6-7 FP32 ones (scalar
+// form K) or 3 packed FP32x2 ones per cost (scan form K2, two costs at a time):
 //
 //   * dx, dy, dx*dx, dy*dy, sum: explicit round-to-nearest intrinsics, so nvcc cannot contract
 //     dx*dx + dy*dy into an FMA (with non-integer coordinates such as usa13509's that would
@@ -53,6 +54,44 @@ __device__ __forceinline__ int koff_from_sumsq(float f) {     // f > 0 (callers 
     return __float_as_int(w);
 }
 
+// ---- the same for TWO costs at once with Blackwell's packed FP32x2 instructions (FMUL2 / FFMA2 / FADD2):
+// half the FP32 issue slots of the scan.  Inputs are the NEGATED sums of squares (the FP64 chain produces
+// -s for free through operand negation), which removes every other negation: with g' = nf*y = -g,
+//   e' = g'*g' + nf = g^2 - f,   r' = h*e' + g' = -(g + h*(f - g^2)) = -r,
+// and floor(r + 0.5) + 2^23 rounded DOWN becomes the same two additions of -0.5 and -2^23 rounded UP
+// (RM(x) = -RP(-x)).  The results therefore carry the bit pattern 0xCB000000 + cost, i.e. the K-offset
+// encoding with the sign bit set: SCAN_FLIP.  Inside a scan every delta adds two such costs and subtracts
+// two K-offset tour-edge costs, so the extra 2 * 2^31 wraps away in 32-bit arithmetic.  Checked
+// exhaustively against koff_from_sumsq on the device (tspcuda_selfcheck_sqrt).
+constexpr unsigned SCAN_FLIP = 0x80000000u;
+
+__device__ __forceinline__ void koff2_from_negsumsq(float nf0, float nf1, int &k0, int &k1) {
+    float y0, y1;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y0) : "f"(fabsf(nf0)));
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y1) : "f"(fabsf(nf1)));
+    unsigned long long nf, y, g, h, e, r, v, w;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(nf) : "f"(nf0), "f"(nf1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(y0), "f"(y1));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(g) : "l"(nf), "l"(y));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(h) : "l"(y), "l"(0x3F0000003F000000ull));
+    asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(e) : "l"(g), "l"(nf));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(h), "l"(e), "l"(g));
+    asm("add.rp.f32x2 %0, %1, %2;" : "=l"(v) : "l"(r), "l"(0xBF000000BF000000ull));
+    asm("add.rp.f32x2 %0, %1, %2;" : "=l"(w) : "l"(v), "l"(0xCB000000CB000000ull));
+    asm("mov.b64 {%0, %1}, %2;" : "=r"(k0), "=r"(k1) : "l"(w));
+}
+
+// Scan-side pair interface of every metric: K2 = the costs of (row a, column) and (row b, column) in
+// the metric's scan encoding K-offset ^ SCAN_XOR (sweep_block, kernels.cuh).
+template <class Derived>
+struct ScalarScan {
+    static constexpr unsigned SCAN_XOR = 0;
+    static __device__ __forceinline__ void K2(double xa, double ya, double xb, double yb, double xj, double yj, int &ka, int &kb) {
+        ka = Derived::K(xa, ya, xj, yj);
+        kb = Derived::K(xb, yb, xj, yj);
+    }
+};
+
 // tsp.c:629 for arbitrary (non-integer) coordinates: separate roundings, clamp against s == 0.
 struct EucGeneral {
     static __device__ __forceinline__ int K(double xi, double yi, double xj, double yj) {
@@ -60,6 +99,13 @@ struct EucGeneral {
         double dy = __dsub_rn(yj, yi);
         double s = __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
         return koff_from_sumsq(fmaxf(__double2float_rn(s), TINY_F));
+    }
+    static constexpr unsigned SCAN_XOR = SCAN_FLIP;
+    static __device__ __forceinline__ void K2(double xa, double ya, double xb, double yb, double xj, double yj, int &ka, int &kb) {
+        const double dxa = __dsub_rn(xj, xa), dya = __dsub_rn(yj, ya), dxb = __dsub_rn(xj, xb), dyb = __dsub_rn(yj, yb);
+        const double sa = __dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya));
+        const double sb = __dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb));
+        koff2_from_negsumsq(fminf(__double2float_rn(-sa), -TINY_F), fminf(__double2float_rn(-sb), -TINY_F), ka, kb);
     }
     // Euclidean radius that contains every w with cost(u,w) < r (pruned.cuh): cost <= r-1 means
     // sqrtf(f) < r - 0.5 with f, sqrtf within 2^-23 relative of the exact values.
@@ -78,12 +124,19 @@ struct EucInt {
         double s = __fma_rn(dx, dx, __fma_rn(dy, dy, TINY_D));
         return koff_from_sumsq(__double2float_rn(s));
     }
+    static constexpr unsigned SCAN_XOR = SCAN_FLIP;
+    static __device__ __forceinline__ void K2(double xa, double ya, double xb, double yb, double xj, double yj, int &ka, int &kb) {
+        const double dxa = __dsub_rn(xj, xa), dya = __dsub_rn(yj, ya), dxb = __dsub_rn(xj, xb), dyb = __dsub_rn(yj, yb);
+        const double nsa = __fma_rn(-dxa, dxa, __fma_rn(-dya, dya, -TINY_D));      // -(dx^2 + dy^2 + 2^-60), exact
+        const double nsb = __fma_rn(-dxb, dxb, __fma_rn(-dyb, dyb, -TINY_D));
+        koff2_from_negsumsq(__double2float_rn(nsa), __double2float_rn(nsb), ka, kb);
+    }
     static __device__ __forceinline__ double radius(double r) { return r * 1.000001 + 1.0; }
     static __device__ __forceinline__ double cost_floor(double d) { return d * 0.999999 - 1.0; }
 };
 
 // TSPLIB95 CEIL_2D: ceil(sqrt(dx^2+dy^2)) in double.
-struct Ceil2D {
+struct Ceil2D : ScalarScan<Ceil2D> {
     static __device__ __forceinline__ int K(double xi, double yi, double xj, double yj) {
         double dx = __dsub_rn(xj, xi);
         double dy = __dsub_rn(yj, yi);
@@ -95,7 +148,7 @@ struct Ceil2D {
 };
 
 // TSPLIB95 ATT: r = sqrt((dx^2+dy^2)/10); t = nint(r); t < r ? t+1 : t.
-struct Att {
+struct Att : ScalarScan<Att> {
     static __device__ __forceinline__ int K(double xi, double yi, double xj, double yj) {
         double dx = __dsub_rn(xj, xi);
         double dy = __dsub_rn(yj, yi);
@@ -114,7 +167,7 @@ struct Att {
 // DDD.MM input).  Same operation order as the definition, no FMA contraction; cos/acos are CUDA's
 // double-precision routines (<= 2 ulp), so a cost can differ from a libm evaluation only where
 // RRR*acos(.)+1 lies within ~1e-8 of an integer.  Parity unpinned (the reference has no GEO rule).
-struct Geo {
+struct Geo : ScalarScan<Geo> {
     static __device__ __forceinline__ int K(double lati, double loni, double latj, double lonj) {
         const double q1 = cos(__dsub_rn(loni, lonj));
         const double q2 = cos(__dsub_rn(lati, latj));

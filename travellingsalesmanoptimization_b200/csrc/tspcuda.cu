@@ -1038,7 +1038,7 @@ static cudaError_t run_pipe(tspcuda_ctx *c, int iters, double *d_sink) {
 extern "C" int tspcuda_pipe_rate(tspcuda_ctx *c, int kind, double *ops_per_s_out) {
     int e = use(c);
     if (e) return e;
-    if (kind < 0 || kind > 6 || !ops_per_s_out) return fail(TSPCUDA_INVALID_ARGUMENT, "kind");
+    if (kind < 0 || kind > 9 || !ops_per_s_out) return fail(TSPCUDA_INVALID_ARGUMENT, "kind");
     double *d_sink = nullptr;
     CK(cudaMalloc(&d_sink, sizeof(double)));
     const int iters = 4096;
@@ -1053,7 +1053,10 @@ extern "C" int tspcuda_pipe_rate(tspcuda_ctx *c, int kind, double *ops_per_s_out
             case 3: le = run_pipe<3>(c, iters, d_sink); break;
             case 4: le = run_pipe<4>(c, iters, d_sink); break;
             case 5: le = run_pipe<5>(c, iters, d_sink); break;
-            default: le = run_pipe<6>(c, iters, d_sink); break;
+            case 6: le = run_pipe<6>(c, iters, d_sink); break;
+            case 7: le = run_pipe<7>(c, iters, d_sink); break;
+            case 8: le = run_pipe<8>(c, iters, d_sink); break;
+            default: le = run_pipe<9>(c, iters, d_sink); break;
         }
         CK(le);
         CK(cudaEventRecord(c->ev1, c->stream));
@@ -1064,7 +1067,7 @@ extern "C" int tspcuda_pipe_rate(tspcuda_ctx *c, int kind, double *ops_per_s_out
         if (rep > 0) best_ms = std::min(best_ms, ms);
     }
     cudaFree(d_sink);
-    const double per_iter = (kind == 3) ? 16.0 : 8.0;       // kind 3 = F2F.F32.F64 + F2F.F64.F32 per chain step
+    const double per_iter = (kind == 3 || kind == 9) ? 16.0 : 8.0;   // kind 3: two conversions, kind 9: two edge costs per chain step       // kind 3 = F2F.F32.F64 + F2F.F64.F32 per chain step
     const double ops = (double)c->num_sms * 8 * 256 * (double)iters * per_iter;
     *ops_per_s_out = ops / (best_ms * 1e-3);
     return TSPCUDA_OK;
