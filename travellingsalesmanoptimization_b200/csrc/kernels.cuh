@@ -33,13 +33,20 @@ constexpr int R = TSP_R;             // tour positions (rows) owned by one lane
 constexpr int SR = 32 * R - 1;       // pair rows per warp strip (last D row is the next strip's first)
 constexpr int UNROLL = TSP_UNROLL;
 constexpr int BLOCK_SMALL = 256;      // descent kernel block size for n < BIG_N (fewer, lighter CTAs: cheaper grid syncs)
+// n >= BIG_N: ONE CTA per SM.  With two 512-thread CTAs per SM the warp scheduler favours the older CTA: it ends its
+// scan a third earlier and then idles at the grid barrier while the other one finishes at half occupancy (measured:
+// scan-end spread 0.79 ms of 2.4 ms on pla85900).  1024 threads (8 warps per scheduler, 64 registers) is best up to
+// HUGE_N, 896 threads (7 per scheduler, 72 registers) above: 1.67 / 1.74e12 pair-evals/s on pla85900, against
+// 1.55e12 with 2 x 512 (profiles/).  Warp counts that are not a multiple of 4 leave the schedulers uneven and lose.
 #ifndef TSP_BLOCK_BIG
-#define TSP_BLOCK_BIG 512
+#define TSP_BLOCK_BIG 1024
 #endif
-#ifndef TSP_MINB_BIG
-#define TSP_MINB_BIG (1024 / TSP_BLOCK_BIG)
+#ifndef TSP_BLOCK_HUGE
+#define TSP_BLOCK_HUGE 896
 #endif
-constexpr int BLOCK_BIG = TSP_BLOCK_BIG;   // and for n >= BIG_N (64 regs/thread, 32 warps/SM: +12% pair rate, profiles/)
+constexpr int BLOCK_BIG = TSP_BLOCK_BIG;
+constexpr int BLOCK_HUGE = TSP_BLOCK_HUGE;
+constexpr int HUGE_N = 32768;
 constexpr int BIG_N = 8192;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
@@ -254,7 +261,7 @@ __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int 
 // init_best = BIGPEN/2 : tabu, best admissible move even if worsening (metaheuristic.c:189,225)
 // ---------------------------------------------------------------------------------------------
 template <class M, int BLK>
-__global__ void __launch_bounds__(BLK, (BLK == BLOCK_BIG ? TSP_MINB_BIG : 1024 / BLK))
+__global__ void __launch_bounds__(BLK, (BLK >= 512 ? 1 : 1024 / BLK))
 descend_kernel(TourView V, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
                long long max_moves, int init_best, int dns_is_dn) {
     constexpr int WARPS = BLK / 32;
@@ -327,7 +334,7 @@ struct TabuCtl {
 struct TabuOut { long long cost, best_cost, moves; int best_iter, pad; };
 
 template <class M, int BLK>
-__global__ void __launch_bounds__(BLK, 1024 / BLK)
+__global__ void __launch_bounds__(BLK, (BLK >= 512 ? 1 : 1024 / BLK))
 tabu_kernel(TourView V, unsigned long long *key, TabuCtl T, TabuOut *out, long long iters) {
     constexpr int WARPS = BLK / 32;
     cg::grid_group grid = cg::this_grid();

@@ -178,8 +178,9 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
     if (!prop.cooperativeLaunch) { tspcuda_destroy(c); return fail(TSPCUDA_UNAVAILABLE, "device lacks cooperative launch"); }
     c->num_sms = prop.multiProcessorCount;
     int bps = 0;
-    c->block = n >= BIG_N ? BLOCK_BIG : BLOCK_SMALL;
-    if (c->block == BLOCK_BIG) { DISPATCH_METRIC(c->metric, (bps = coop_blocks_per_sm<M, BLOCK_BIG>())); }
+    c->block = n >= HUGE_N ? BLOCK_HUGE : (n >= BIG_N ? BLOCK_BIG : BLOCK_SMALL);
+    if (c->block == BLOCK_HUGE) { DISPATCH_METRIC(c->metric, (bps = coop_blocks_per_sm<M, BLOCK_HUGE>())); }
+    else if (c->block == BLOCK_BIG) { DISPATCH_METRIC(c->metric, (bps = coop_blocks_per_sm<M, BLOCK_BIG>())); }
     else { DISPATCH_METRIC(c->metric, (bps = coop_blocks_per_sm<M, BLOCK_SMALL>())); }
     if (bps <= 0) { tspcuda_destroy(c); return fail(TSPCUDA_INTERNAL, "descent kernel cannot be resident (built for sm_100a; device is sm_%d%d)", prop.major, prop.minor); }
     c->max_coop_blocks = bps * c->num_sms;
@@ -347,6 +348,8 @@ static cudaError_t launch_descend(tspcuda_ctx *c, int grid, long long max_moves,
     MoveRec *log = c->d_log;
     long long log_cap = c->log_cap;
     void *args[] = {&V, &key, &st, &log, &log_cap, &max_moves, &init_best, &dns_is_dn};
+    if (c->block == BLOCK_HUGE)
+        return cudaLaunchCooperativeKernel((void *)descend_kernel<M, BLOCK_HUGE>, dim3(grid), dim3(BLOCK_HUGE), args, 0, c->stream);
     if (c->block == BLOCK_BIG)
         return cudaLaunchCooperativeKernel((void *)descend_kernel<M, BLOCK_BIG>, dim3(grid), dim3(BLOCK_BIG), args, 0, c->stream);
     return cudaLaunchCooperativeKernel((void *)descend_kernel<M, BLOCK_SMALL>, dim3(grid), dim3(BLOCK_SMALL), args, 0, c->stream);
@@ -608,6 +611,8 @@ static cudaError_t launch_tabu(tspcuda_ctx *c, int grid, TabuCtl T, TabuOut *out
     TourView V = c->tour;
     unsigned long long *key = c->d_key;
     void *args[] = {&V, &key, &T, &out, &iters};
+    if (c->block == BLOCK_HUGE)
+        return cudaLaunchCooperativeKernel((void *)tabu_kernel<M, BLOCK_HUGE>, dim3(grid), dim3(BLOCK_HUGE), args, 0, c->stream);
     if (c->block == BLOCK_BIG)
         return cudaLaunchCooperativeKernel((void *)tabu_kernel<M, BLOCK_BIG>, dim3(grid), dim3(BLOCK_BIG), args, 0, c->stream);
     return cudaLaunchCooperativeKernel((void *)tabu_kernel<M, BLOCK_SMALL>, dim3(grid), dim3(BLOCK_SMALL), args, 0, c->stream);
