@@ -451,7 +451,7 @@ def test_multistart_pr2392_first8_and_strided(tsp, golden):
 
 @pytest.mark.parametrize("scan", ["full", "auto"])
 def test_multistart_cta_paths_vs_grid_path(tsp, oracle, scan):
-    """The CTA-per-descent kernels (K6: full scan, n <= 7100, 512- and 1024-thread variants; K8: pruned
+    """The CTA-per-descent kernels (K6: full scan, n <= 7600, 512- and 1024-thread variants; K8: pruned
     scan, any n, used from num_sms/4 starts up) and the grid-wide descent kernels must produce the same
     tours: compare multistart with nn + two_opt start by start, and one start of each size with the
     CPU oracle."""
