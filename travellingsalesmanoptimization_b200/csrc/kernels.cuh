@@ -47,7 +47,10 @@ constexpr int BLOCK_SMALL = 256;      // descent kernel block size for n < BIG_N
 constexpr int BLOCK_BIG = TSP_BLOCK_BIG;
 constexpr int BLOCK_HUGE = TSP_BLOCK_HUGE;
 constexpr int HUGE_N = 32768;
-constexpr int BIG_N = 8192;
+#ifndef TSP_BIG_N
+#define TSP_BIG_N 7000
+#endif
+constexpr int BIG_N = TSP_BIG_N;
 constexpr unsigned FULL = 0xFFFFFFFFu;
 
 struct TourView {
