@@ -718,3 +718,25 @@ def test_nn_kernels_agree(tsp, oracle, monkeypatch, mode):
             e, po, co = oracle.nn(xy, 5, wt)
             code, p, c = I.nn(5)
             assert c == co and np.array_equal(p, po), (mode, wt)
+
+
+def test_maximum_size(tsp, oracle):
+    """n = 131072 (TSPCUDA_MAX_NODES: 17-bit node ids in the packed key): NN over the grid, the first 2-opt moves
+    by both scan kernels, audited by the oracle (every logged delta; one full CPU scan, 8.6e9 pairs); one more
+    node is refused with OUT_OF_RANGE."""
+    n = 131072
+    rng = np.random.default_rng(2024)
+    xy = np.ascontiguousarray(np.round(rng.uniform(0, 2_000_000, size=(n, 2))))
+    with _inst(tsp, xy, "full") as I:
+        code, p, c = I.nn(n - 1)
+        assert code == 0 and oracle.is_tour(p) and oracle.tour_cost(xy, p) == c
+        code, mv, p_full, c_full, log_full = I.two_opt(p, max_moves=12, log_cap=12)
+        I.set_scan_mode(tsp.SCAN_PRUNED)
+        code, mv2, p_pr, c_pr, log_pr = I.two_opt(p, max_moves=12, log_cap=12)
+    assert mv == mv2 == 12 and log_full == log_pr and c_full == c_pr and np.array_equal(p_full, p_pr)
+    la = [x[0] for x in log_full]; lb = [x[1] for x in log_full]; ld = [float(x[2]) for x in log_full]
+    r, pend = oracle.audit_moves(xy, p, la, lb, ld, [0])
+    assert r == 0 and np.array_equal(pend, p_full)
+    with pytest.raises(tsp.TspCudaError) as ei:
+        tsp.Instance(np.zeros((n + 1, 2)))
+    assert ei.value.code == tsp.OUT_OF_RANGE
