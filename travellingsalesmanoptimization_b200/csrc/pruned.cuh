@@ -430,15 +430,20 @@ __device__ __forceinline__ void collect_trip(const TourView &V, const SpatialGri
 // nthreads is a multiple of 32) takes tour positions t, t + nthreads, ...  Search boxes with at most
 // PR_SMALL_NODES nodes are walked inline, larger ones are appended to boxes[] through the packed
 // counter *qctr (boxes in the high 24 bits, cell rows in the low 40; one atomic per warp).
-template <class M, int NC1, int NE>
+template <class M, int NC1, int NE, int L>
 __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGrid &G, const PosPatch &F, int t, int nthreads,
                                               unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, int &best,
                                               unsigned long long &bestkey, long long &ncand) {
     int wcount = 0;
     const int n = V.n;
     const int lane = threadIdx.x & 31;
-    for (int p0 = t - lane; p0 < n; p0 += nthreads) {              // warp-uniform trip count
-        const int p = p0 + lane;
+    // L lanes share a position (L = 4 when there are at least four times as many threads as positions, chosen by
+    // the host): lane `sub` of the group walks the cell rows sub, sub + L, ... of the position's box, so the longest
+    // per-lane stream of a warp -- what the whole warp waits for -- shrinks accordingly
+    const int sub = lane & (L - 1);
+    const int per_pass = nthreads / L;                             // positions per pass; nthreads, L: powers-of-two friendly
+    for (int p0 = (t - lane) / L; p0 < n; p0 += per_pass) {        // warp-uniform trip count
+        const int p = p0 + lane / L;
         Probe P;
         int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = -1;
         bool has = false;
@@ -447,7 +452,7 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
             has = probe_box<M>(G, P, cx0, cx1, cy0, cy1);
         }
         const int nrows = has ? cy1 - cy0 + 1 : 0;
-        int total = 0;
+        int total = 0, mine = 0;                                   // nodes in the box / in this lane's rows
         if (has) {
             if (nrows <= PR_SMALL_ROWS) {
 #pragma unroll
@@ -455,12 +460,14 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
                     const int cy = min(cy0 + r, cy1);
                     const int cnt = G.cell_start[cy * G.W + cx1 + 1] - G.cell_start[cy * G.W + cx0];
                     total += (cy0 + r <= cy1) ? cnt : 0;
+                    mine += (cy0 + r <= cy1 && (r & (L - 1)) == sub) ? cnt : 0;
                 }
             } else {
                 total = PR_SMALL_NODES + 1;
             }
         }
-        const bool big = total > PR_SMALL_NODES;
+        if (sub != 0) has = has && total <= PR_SMALL_NODES;        // a large box is queued once, by the group's first lane
+        const bool big = total > PR_SMALL_NODES && sub == 0;
         const unsigned bigmask = __ballot_sync(FULL, big);
         if (bigmask) {                                             // one queue atomic per warp
             const int myrows = big ? nrows : 0;
@@ -484,10 +491,10 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
         }
         // the small boxes of the warp's 32 positions, in lockstep: each lane streams ITS box across its cell
         // rows (row bounds are L1 hits by now), NC1 candidates per trip, into the warp's record buffer
-        const int mytotal = (has && !big) ? total : 0;
+        const int mytotal = (has && !big) ? mine : 0;
         ncand += mytotal;
         const int maxtotal = __reduce_max_sync(FULL, mytotal);
-        int cy = cy0, k = 0, hi = 0, last = 0;
+        int cy = cy0 + sub, k = 0, hi = 0, last = 0;
         for (int done = 0; done < maxtotal; done += NC1) {
             int kk[NC1];
             bool valid[NC1];
@@ -498,7 +505,7 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
                     while (k >= hi) {
                         k = G.cell_start[cy * G.W + cx0];
                         hi = G.cell_start[cy * G.W + cx1 + 1];
-                        ++cy;
+                        cy += L;
                     }
                     last = k++;
                 }
@@ -563,7 +570,7 @@ __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGr
 }
 
 // ---- K7: whole-GPU persistent pruned descent (cooperative launch, one CTA per SM) ----------------
-template <class M, int BLK>
+template <class M, int BLK, int L>
 __global__ void __launch_bounds__(BLK, 1)
 descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
                       long long max_moves, unsigned long long *qctr, BigBox *boxes, uint4 *wbuf_all) {
@@ -602,7 +609,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #ifdef TSP_PHASE_TIMING
         unsigned long long tw0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw0));
 #endif
-        pruned_phase1<M, NC1, NE>(V, G, F, gtid, gsize, qctr, boxes, wbuf, best, bestkey, ncand);
+        pruned_phase1<M, NC1, NE, L>(V, G, F, gtid, gsize, qctr, boxes, wbuf, best, bestkey, ncand);
 #ifdef TSP_PHASE_TIMING
         {   // slowest and average warp of phase 1 (phase_ns[3] = sum over scans of the max, [4]/[5] reused below)
             unsigned long long tw1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw1));
@@ -729,7 +736,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             __syncthreads();
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
-            pruned_phase1<M, NC1, NE>(V, G, F, t, BLK, &s_q, boxes, wbuf, best, bestkey, ncand);
+            pruned_phase1<M, NC1, NE, 1>(V, G, F, t, BLK, &s_q, boxes, wbuf, best, bestkey, ncand);
             __syncthreads();
             pruned_phase2<M, NE>(V, G, F, warp, WARPS, s_q, boxes, wbuf, best, bestkey, ncand);
             bestkey = warp_min_key(bestkey);

@@ -254,8 +254,8 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         // threads with two tour positions in phase 1
         c->pruned_block = (long long)c->num_sms * PRUNED_BLOCK >= n ? PRUNED_BLOCK : 1024;
         int pb = 0;
-        if (c->pruned_block == PRUNED_BLOCK) { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, PRUNED_BLOCK>, PRUNED_BLOCK, 0))); }
-        else { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, 1024>, 1024, 0))); }
+        if (c->pruned_block == PRUNED_BLOCK) { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, PRUNED_BLOCK, 1>, PRUNED_BLOCK, 0))); }
+        else { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, 1024, 1>, 1024, 0))); }
         c->pruned_blocks = (pb > 0 && c->metric != M_GEO) ? c->num_sms : 0;     // the grid search is Euclidean
     }
     *out = c;
@@ -368,8 +368,10 @@ static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max
     uint4 *wbuf = c->d_wbuf;
     void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &qctr, &boxes, &wbuf};
     if (c->pruned_block == 1024)
-        return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, 1024>, dim3(grid), dim3(1024), args, 0, c->stream);
-    return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
+        return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, 1024, 1>, dim3(grid), dim3(1024), args, 0, c->stream);
+    if (4LL * c->n <= (long long)grid * PRUNED_BLOCK)          // four lanes per tour position in phase 1
+        return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK, 4>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
+    return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK, 1>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
 }
 
 // Run up to max_moves scan+move iterations on the device-resident tour (max_moves < 0: until no
