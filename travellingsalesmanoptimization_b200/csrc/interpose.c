@@ -413,7 +413,9 @@ ERROR_CODE h_greedy_2opt(void) {
  * (tsp.c:671), so one tsp_update_best_solution with the first tour that reaches the minimum cost of
  * the run leaves the same incumbent as the per-iteration calls. */
 ERROR_CODE mh_TabuSearch(void) {
-    if (!batch_enabled())
+    /* the default -k is INT_MAX (tsp.c:12: the reference then iterates until it is interrupted): laying out that many
+     * tenures ahead is pointless, keep the reference's own loop over the interposed tabu_best_move there */
+    if (!batch_enabled() || tsp_env.k > (1 << 22))
         return ((void_fn)dlsym(RTLD_NEXT, "mh_TabuSearch"))();
     g_calls[C_TABULOOP]++;
     tabu_search ts;
