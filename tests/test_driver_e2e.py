@@ -207,3 +207,19 @@ def test_mod_costs_through_the_reference_objects(workdir, batch):
         assert c["h_greedyutil"] == 64 and c["ref_2opt"] == 64
     else:
         assert c["h_greedyutil"] == 0 and c["ref_2opt"] == 0
+
+
+@pytest.mark.gpu
+def test_pla85900_opens_through_the_unchanged_driver(workdir):
+    """The headline instance through the drop-in CLI: CEIL_2D header (the reference reader stops there,
+    tsp.c:576-583), n > 46340 (no host matrix: the reference's int n*n overflows, tsp.c:614).
+    TSPCUDA_WEIGHT=ref = the reference's own cost rule, as in bench.py: NN(0) costs 163503308
+    (the start cost of the bench descent); with the file's own CEIL_2D rule the oracle's value."""
+    from oracle.bindings import CEIL_2D, Oracle
+    xy, ewt = load_instance("pla85900")
+    assert ewt == "CEIL_2D"
+    write_tsplib(workdir / "pla85900.tsp", "pla85900", xy, ewt)
+    r = run_cli(TSP_GPU, workdir, ["-f", "pla85900.tsp", "-q", "-alg", "GREEDY"], {"TSPCUDA_WEIGHT": "ref"})
+    assert r.stdout.strip() == "Cost: 163503308.00"
+    r = run_cli(TSP_GPU, workdir, ["-f", "pla85900.tsp", "-q", "-alg", "GREEDY"])
+    assert r.stdout.strip() == "Cost: %.2f" % Oracle().nn(xy, 0, CEIL_2D)[2]
