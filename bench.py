@@ -316,7 +316,7 @@ def main():
         I.set_scan_mode(T.SCAN_AUTO)
         S_total = args.multistart * world
         first, count, stride = MS.shard_starts(0, S_total, rank, world)
-        I.multistart_two_opt(first, min(count, 2), stride)          # warm (module load, allocations)
+        I.multistart_two_opt(first, min(count, 40), stride)         # warm: same kernels (CTA-per-descent path needs >= 37 starts), module load
         barrier()
         I.reset_stats()
         t0 = time.perf_counter()
