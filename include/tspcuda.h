@@ -82,6 +82,9 @@ const char *tspcuda_last_error(void);           /* thread-local description of t
 const char *tspcuda_version(void);
 
 /* ---- instance context ----------------------------------------------------------------------- */
+/* A context owns one CUDA stream, the device copy of the instance and all scratch.  Calls on the SAME
+ * context must not overlap (the reference's heuristic drivers are single-threaded); different contexts
+ * (tspcuda_ctx or tspcuda_mx) may be used from different threads concurrently. */
 /* xy: n points, AoS {x,y} doubles exactly as the reference's `point` array (utils.h:37-40).
  * The coordinates are copied to the device; the caller keeps ownership of xy. */
 int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int weight_type, int device);
