@@ -582,8 +582,14 @@ __device__ __forceinline__ double cost_as_double(int koff) {
 #ifndef TSP_K1_STREAM
 #define TSP_K1_STREAM 1
 #endif
+#ifndef TSP_K1_BLOCK
+#define TSP_K1_BLOCK 256
+#endif
+#ifndef TSP_K1_CTAS
+#define TSP_K1_CTAS 16
+#endif
 template <class M>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TSP_K1_BLOCK)
 cost_matrix_kernel(const double2 *__restrict__ xy, int n, double *__restrict__ out) {
     constexpr int U = TSP_K1_UNROLL;              // independent 16-byte stores in flight per thread
     for (int i = blockIdx.x; i < n; i += gridDim.x) {

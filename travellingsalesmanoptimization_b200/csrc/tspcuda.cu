@@ -994,9 +994,9 @@ extern "C" int tspcuda_cost_matrix_device(tspcuda_ctx *c, double *ms_out) {
     if (e) return e;
     const size_t n = (size_t)c->n;
     if (!c->d_matrix) CK(cudaMalloc(&c->d_matrix, sizeof(double) * n * n));
-    const int grid = (int)std::min<size_t>(n, (size_t)c->num_sms * 8);
+    const int grid = (int)std::min<size_t>(n, (size_t)c->num_sms * TSP_K1_CTAS);
     CK(cudaEventRecord(c->ev0, c->stream));
-    DISPATCH_METRIC(c->metric, (cost_matrix_kernel<M><<<grid, 256, 0, c->stream>>>(c->d_xy, c->n, c->d_matrix)));
+    DISPATCH_METRIC(c->metric, (cost_matrix_kernel<M><<<grid, TSP_K1_BLOCK, 0, c->stream>>>(c->d_xy, c->n, c->d_matrix)));
     CK(cudaEventRecord(c->ev1, c->stream));
     c->stats.kernel_launches += 1;
     CK(cudaGetLastError());
