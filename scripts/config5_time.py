@@ -32,8 +32,8 @@ for name in ("d15112", "rand20000"):
         t_loop = time.perf_counter() - t0; s2 = I.stats()
         assert cb == ca and np.array_equal(pa, pb) and np.array_equal(ta, tb)
         pairs = K * n * (n - 1) / 2
-        print("%-9s n=%d NN(0)+2opt %d moves %.3f s -> %d | tabu K=%d: per-call %.3f s (kernel %.3f s, %.0f Gpair/s e2e)  device loop %.3f s (kernel %.3f s, %.0f Gpair/s e2e)  final %d best %s"
-              % (name, n, moves, t_opt, c, K, t_call, s1["scan_kernel_ms"] * 1e-3, pairs / t_call / 1e9, t_loop, s2["scan_kernel_ms"] * 1e-3, pairs / t_loop / 1e9, cb, bc if bi >= 0 else None), flush=True)
+        print("%-9s n=%d NN(0)+2opt %d moves %.3f s -> %d | tabu K=%d: per-call %.3f s (kernel %.3f s, %.0f Gpair/s e2e)  device loop %.3f s (kernels %.3f s: %d of %d scans by the pruned scan; %.0f Gpair/s full-scan equivalent)  final %d best %s"
+              % (name, n, moves, t_opt, c, K, t_call, s1["scan_kernel_ms"] * 1e-3, pairs / t_call / 1e9, t_loop, (s2["scan_kernel_ms"] + s2["pruned_kernel_ms"]) * 1e-3, s2["pruned_scans"], s2["scans"], pairs / t_loop / 1e9, cb, bc if bi >= 0 else None), flush=True)
         # VNS: K x (kick on the host + ref_2opt on the device), metaheuristic.c:279-320
         import ctypes
         pv, cv = p.copy(), c

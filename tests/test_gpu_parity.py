@@ -740,3 +740,40 @@ def test_maximum_size(tsp, oracle):
     with pytest.raises(tsp.TspCudaError) as ei:
         tsp.Instance(np.zeros((n + 1, 2)))
     assert ei.value.code == tsp.OUT_OF_RANGE
+
+
+@pytest.mark.parametrize("kind", ["random", "lattice", "mostly_tabu"])
+def test_tabu_search_pruned_loop_matches_per_call_path(tsp, oracle, kind):
+    """n >= 4096: tspcuda_tabu_search runs K5c (pruned scan with a bound, falling back to the full-scan loop when the
+    bound is exhausted).  It must reproduce, iteration by iteration, what tabu_best_move gives through
+    tspcuda_tabu_move (full scan, one call per iteration): cost trace, tour, tabu list; the first iterations are
+    also checked against the oracle."""
+    if kind == "lattice":
+        xy = np.ascontiguousarray(np.stack(np.meshgrid(np.arange(70.0), np.arange(64.0)), -1).reshape(-1, 2) * 5.0)
+    else:
+        xy = _rand_xy(41, 5000, kind == "mostly_tabu")
+    n = xy.shape[0]
+    K = 260
+    tenures = [40 + (k * 13) % 200 for k in range(K)]
+    if kind == "mostly_tabu":
+        tenures = [n] * K                               # nothing ever leaves the list: admissible pairs run out
+    with tsp.Instance(xy) as I:
+        code, p, c = I.nn(3)
+        code, mv, p, c, _ = I.two_opt(p)
+        pa, ta, ca, trace_a = p.copy(), np.full(n, -1, dtype=np.int32), c, []
+        for k, t in enumerate(tenures):
+            ca, mvk = I.tabu_move(pa, ca, ta, t, k)
+            trace_a.append(ca)
+        pb, tb = p.copy(), np.full(n, -1, dtype=np.int32)
+        I.reset_stats()
+        cb, trace_b, bi, bp, bc = I.tabu_search(pb, c, tb, tenures)
+        st = I.stats()
+    assert list(trace_b) == trace_a and cb == ca
+    assert np.array_equal(pa, pb) and np.array_equal(ta, tb)
+    assert st["pruned_scans"] > 0
+    best = min(trace_a)
+    assert (bi >= 0) == (best < c) and (bi < 0 or (bc == best and bi == trace_a.index(best)))
+    po, to, co = p.copy(), np.full(n, -1, dtype=np.int32), c
+    for k in range(12):
+        co, a, b, d = oracle.tabu_move(xy, po, co, to, tenures[k], k)
+        assert co == trace_a[k], k

@@ -334,7 +334,7 @@ struct TabuCtl {
     long long cost, best_cost; // in: current tour cost, incumbent cost
     int first_iter, pad;
 };
-struct TabuOut { long long cost, best_cost, moves; int best_iter, pad; };
+struct TabuOut { long long cost, best_cost, moves, done; int best_iter, last_delta; };   // done = iterations completed by the launch
 
 template <class M, int BLK>
 __global__ void __launch_bounds__(BLK, (BLK >= 512 ? 1 : 1024 / BLK))
@@ -407,7 +407,7 @@ tabu_kernel(TourView V, unsigned long long *key, TabuCtl T, TabuOut *out, long l
         if (improved && threadIdx.x == 0) { s_bestcost = s_cost; s_bestiter = iter; }
     }
     __syncthreads();
-    if (gtid == 0) { out->cost = s_cost; out->best_cost = s_bestcost; out->moves = s_moves; out->best_iter = s_bestiter; }
+    if (gtid == 0) { out->cost = s_cost; out->best_cost = s_bestcost; out->moves = s_moves; out->best_iter = s_bestiter; out->done = iters; out->last_delta = 0; }
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -216,10 +216,14 @@ nn_grid_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, int first_s
 // Everything a search around the node at position p needs, loaded once.
 struct Probe {
     double ux, uy, sx, sy, px, py;     // node at p, its successor (p+1), its predecessor (p-1)
-    int p, pm, ida, idm, dnp, dnm;     // pm = p-1 (cyclic); node ids at p and pm; K-offset edge costs
+    int p, pm, ida, idm, dnp, dnm;     // pm = p-1 (cyclic); node ids at p and pm; K-offset edge costs = search thresholds
 };
 
-__device__ __forceinline__ void probe_load(const TourView &V, int p, Probe &P) {
+// TABU: the search is for the best ADMISSIBLE pair with delta < bound: both thresholds grow by
+// h = ceil(bound / 2) (delta < bound implies D(p,q) - dn[p] < h or D(p+1,q+1) - dn[q] < h), and an edge
+// that touches a tabu node (dns flagged: dn - BIGPEN, i.e. below KOFF) starts no search at all.
+template <bool TABU>
+__device__ __forceinline__ void probe_load(const TourView &V, int p, Probe &P, int h) {
     const int n = V.n;
     P.p = p;
     P.pm = p == 0 ? n - 1 : p - 1;
@@ -227,6 +231,10 @@ __device__ __forceinline__ void probe_load(const TourView &V, int p, Probe &P) {
     P.ux = u.x; P.uy = u.y; P.sx = s.x; P.sy = s.y; P.px = q.x; P.py = q.y;
     P.ida = V.tid[p]; P.idm = V.tid[P.pm];
     P.dnp = V.dn[p]; P.dnm = V.dn[P.pm];
+    if (TABU) {                                       // dnp / dnm become the search thresholds
+        P.dnp = (V.dns[p] < KOFF) ? 0 : P.dnp + h;
+        P.dnm = (V.dns[P.pm] < KOFF) ? 0 : P.dnm + h;
+    }
 }
 
 // pos[] of the two end nodes of the segment reversed by the PREVIOUS move is written by one thread
@@ -234,65 +242,6 @@ __device__ __forceinline__ void probe_load(const TourView &V, int p, Probe &P) {
 // apply_move, so it cannot be written earlier); scans that start behind the same barrier take those
 // two positions from registers instead of racing with that write.
 struct PosPatch { int node0, pos0, node1, pos1; };
-
-// Evaluates up to NC candidates w[j] (coordinates wx/wy, valid[j]) of the search around P in
-// STAGES -- all edge costs, then all pos[] gathers, then all coordinate / edge-cost gathers, then
-// the deltas -- so that the dependent L2 round trips (cost -> pos -> pxy/dn) of the candidates
-// overlap instead of queueing behind one another.  Gathers of rejected candidates are redirected
-// to index 0 rather than branched around: the loads stay unconditional and issue back to back.
-template <class M, int NC>
-__device__ __forceinline__ void cand_eval_n(const TourView &V, const Probe &P, const PosPatch &F, const int (&w)[NC],
-                                            const double (&wx)[NC], const double (&wy)[NC], const bool (&valid)[NC],
-                                            int &best, unsigned long long &bestkey) {
-    const int n = V.n;
-    int K[NC], q[NC];
-    bool c1[NC], c2[NC];
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
-        K[j] = M::K(P.ux, P.uy, wx[j], wy[j]);
-        c1[j] = valid[j] && K[j] < P.dnp;
-        c2[j] = valid[j] && K[j] < P.dnm;
-    }
-#pragma unroll
-    for (int j = 0; j < NC; ++j) q[j] = V.pos[(c1[j] | c2[j]) ? w[j] : P.ida];
-    double2 ws[NC], wp[NC];
-    int dq[NC], dqm[NC], qm[NC];
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
-        if (w[j] == F.node0) q[j] = F.pos0;
-        if (w[j] == F.node1) q[j] = F.pos1;
-        const int diff = abs(P.p - q[j]);
-        const bool ok = diff > 1 && diff != n - 1;           // same node / tour neighbours: refinment.c:55
-        c1[j] = c1[j] && ok;
-        c2[j] = c2[j] && ok;
-        qm[j] = q[j] == 0 ? n - 1 : q[j] - 1;
-        ws[j] = V.pxy[c1[j] ? q[j] + 1 : 0];
-        dq[j] = V.dn[c1[j] ? q[j] : 0];
-        wp[j] = V.pxy[c2[j] ? qm[j] : 0];
-        dqm[j] = V.dn[c2[j] ? qm[j] : 0];
-    }
-#pragma unroll
-    for (int j = 0; j < NC; ++j) {
-        if (c1[j]) {                                   // pair {p, q}: edges (p,p+1), (q,q+1) out, (p,q), (p+1,q+1) in
-            const int K2 = M::K(P.sx, P.sy, ws[j].x, ws[j].y);
-            const int d = (int)((unsigned)K[j] + (unsigned)K2 - (unsigned)P.dnp - (unsigned)dq[j]);
-            if (d <= best) {
-                best = d;
-                const unsigned long long key = pack_key(d, P.ida, w[j]);
-                if (key < bestkey) bestkey = key;
-            }
-        }
-        if (c2[j]) {                                   // pair {p-1, q-1}: (p,q) is its second new edge
-            const int K2 = M::K(P.px, P.py, wp[j].x, wp[j].y);
-            const int d = (int)((unsigned)K2 + (unsigned)K[j] - (unsigned)P.dnm - (unsigned)dqm[j]);
-            if (d <= best) {
-                best = d;
-                const unsigned long long key = pack_key(d, P.idm, V.tid[qm[j]]);
-                if (key < bestkey) bestkey = key;
-            }
-        }
-    }
-}
 
 // Cell box that contains every node w with cost(u,w) < max(dn[p], dn[p-1]).  false: empty search.
 template <class M>
@@ -319,7 +268,7 @@ __device__ __forceinline__ bool probe_box(const SpatialGrid &G, const Probe &P, 
 #endif
 constexpr int PR_WBUF = TSP_PR_WBUF;        // records per warp buffer (16 bytes each); flushed when nearly full
 
-template <class M, int NE>
+template <class M, int NE, bool TABU>
 __device__ __forceinline__ void pairs_eval(const TourView &V, const PosPatch &F, const uint4 *wbuf, int count, int &best,
                                            unsigned long long &bestkey) {
     const int n = V.n;
@@ -353,11 +302,11 @@ __device__ __forceinline__ void pairs_eval(const TourView &V, const PosPatch &F,
                 s1[j] = V.pxy[c1 ? p + 1 : 0];
                 w1[j] = V.pxy[c1 ? q[j] + 1 : 0];
                 dp[j] = V.dn[c1 ? p : 0];
-                dq[j] = V.dn[c1 ? q[j] : 0];
+                dq[j] = (TABU ? V.dns : V.dn)[c1 ? q[j] : 0];          // TABU: a flagged edge (below KOFF) makes the pair inadmissible
             }
 #pragma unroll
             for (int j = 0; j < NE; ++j) {
-                if (ok[j] && (e[j].w & 1u)) {
+                if (ok[j] && (e[j].w & 1u) && (!TABU || dq[j] >= KOFF)) {
                     const int K2 = M::K(s1[j].x, s1[j].y, w1[j].x, w1[j].y);
                     const int d = (int)(e[j].z + (unsigned)K2 - (unsigned)dp[j] - (unsigned)dq[j]);
                     if (d <= best) {
@@ -380,11 +329,11 @@ __device__ __forceinline__ void pairs_eval(const TourView &V, const PosPatch &F,
                 s2[j] = V.pxy[c2 ? pm[j] : 0];
                 w2[j] = V.pxy[c2 ? qm[j] : 0];
                 dpm[j] = V.dn[c2 ? pm[j] : 0];
-                dqm[j] = V.dn[c2 ? qm[j] : 0];
+                dqm[j] = (TABU ? V.dns : V.dn)[c2 ? qm[j] : 0];
             }
 #pragma unroll
             for (int j = 0; j < NE; ++j) {
-                if (ok[j] && (e[j].w & 2u)) {
+                if (ok[j] && (e[j].w & 2u) && (!TABU || dqm[j] >= KOFF)) {
                     const int K2 = M::K(s2[j].x, s2[j].y, w2[j].x, w2[j].y);
                     const int d = (int)((unsigned)K2 + e[j].z - (unsigned)dpm[j] - (unsigned)dqm[j]);
                     if (d <= best) {
@@ -400,14 +349,14 @@ __device__ __forceinline__ void pairs_eval(const TourView &V, const PosPatch &F,
 
 // One trip of a search: NCC candidates per lane (slot kk[j] of the cell-sorted arrays, valid[j]) of the
 // search around position p (node coordinates ux/uy, edge costs dnp = dn[p], dnm = dn[p-1]).
-template <class M, int NCC, int NE>
+template <class M, int NCC, int NE, bool TABU>
 __device__ __forceinline__ void collect_trip(const TourView &V, const SpatialGrid &G, const PosPatch &F, int p, double ux,
                                              double uy, int dnp, int dnm, const int (&kk)[NCC], const bool (&valid)[NCC],
                                              uint4 *wbuf, int &wcount, int &best, unsigned long long &bestkey) {
     const int lane = threadIdx.x & 31;
     if (wcount > PR_WBUF - 32 * NCC) {                 // warp-uniform: flush
         __syncwarp();
-        pairs_eval<M, NE>(V, F, wbuf, wcount, best, bestkey);
+        pairs_eval<M, NE, TABU>(V, F, wbuf, wcount, best, bestkey);
         __syncwarp();
         wcount = 0;
     }
@@ -430,10 +379,10 @@ __device__ __forceinline__ void collect_trip(const TourView &V, const SpatialGri
 // nthreads is a multiple of 32) takes tour positions t, t + nthreads, ...  Search boxes with at most
 // PR_SMALL_NODES nodes are walked inline, larger ones are appended to boxes[] through the packed
 // counter *qctr (boxes in the high 24 bits, cell rows in the low 40; one atomic per warp).
-template <class M, int NC1, int NE, int L>
+template <class M, int NC1, int NE, int L, bool TABU>
 __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGrid &G, const PosPatch &F, int t, int nthreads,
                                               unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, int &best,
-                                              unsigned long long &bestkey, long long &ncand) {
+                                              unsigned long long &bestkey, long long &ncand, int h) {
     int wcount = 0;
     const int n = V.n;
     const int lane = threadIdx.x & 31;
@@ -448,7 +397,7 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
         int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = -1;
         bool has = false;
         if (p < n) {
-            probe_load(V, p, P);
+            probe_load<TABU>(V, p, P, h);
             has = probe_box<M>(G, P, cx0, cx1, cy0, cy1);
         }
         const int nrows = has ? cy1 - cy0 + 1 : 0;
@@ -511,20 +460,20 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
                 }
                 kk[j] = last;
             }
-            collect_trip<M, NC1, NE>(V, G, F, p, P.ux, P.uy, P.dnp, P.dnm, kk, valid, wbuf, wcount, best, bestkey);
+            collect_trip<M, NC1, NE, TABU>(V, G, F, p, P.ux, P.uy, P.dnp, P.dnm, kk, valid, wbuf, wcount, best, bestkey);
         }
     }
     __syncwarp();
-    pairs_eval<M, NE>(V, F, wbuf, wcount, best, bestkey);
+    pairs_eval<M, NE, TABU>(V, F, wbuf, wcount, best, bestkey);
 }
 
 // Phase 2 (behind a barrier): the queued boxes, cut into (box, cell row) units -- one contiguous
 // range of the cell-sorted node array each -- split evenly over the `nwarps` cooperating warps;
 // this warp is number `gw`.  q = the packed counter after phase 1.
-template <class M, int NE>
+template <class M, int NE, bool TABU>
 __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGrid &G, const PosPatch &F, long long gw,
                                               long long nwarps, unsigned long long q, const BigBox *boxes, uint4 *wbuf,
-                                              int &best, unsigned long long &bestkey, long long &ncand) {
+                                              int &best, unsigned long long &bestkey, long long &ncand, int h) {
     const int lane = threadIdx.x & 31;
     const long long nunits = (long long)(q & PR_UNIT_MASK);
     const int nboxes = (int)(q >> 40);
@@ -547,9 +496,9 @@ __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGr
     int bi = lo_b;
     BigBox b = boxes[bi];
     Probe P;
-    probe_load(V, b.p, P);
+    probe_load<TABU>(V, b.p, P, h);
     for (long long g = g0; g < g1; ++g) {
-        while (g >= b.base + b.nrows) { b = boxes[++bi]; probe_load(V, b.p, P); }
+        while (g >= b.base + b.nrows) { b = boxes[++bi]; probe_load<TABU>(V, b.p, P, h); }
         const int cy = b.cy0 + (int)(g - b.base);
         const int lo = G.cell_start[cy * G.W + b.cx0], hi = G.cell_start[cy * G.W + b.cx1 + 1];
         if (lane == 0) ncand += hi - lo;
@@ -562,11 +511,11 @@ __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGr
                 valid[j] = k < hi;
                 kk[j] = min(k, hi - 1);
             }
-            collect_trip<M, PR_NC2, NE>(V, G, F, b.p, P.ux, P.uy, P.dnp, P.dnm, kk, valid, wbuf, wcount, best, bestkey);
+            collect_trip<M, PR_NC2, NE, TABU>(V, G, F, b.p, P.ux, P.uy, P.dnp, P.dnm, kk, valid, wbuf, wcount, best, bestkey);
         }
     }
     __syncwarp();
-    pairs_eval<M, NE>(V, F, wbuf, wcount, best, bestkey);
+    pairs_eval<M, NE, TABU>(V, F, wbuf, wcount, best, bestkey);
 }
 
 // ---- K7: whole-GPU persistent pruned descent (cooperative launch, one CTA per SM) ----------------
@@ -609,7 +558,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #ifdef TSP_PHASE_TIMING
         unsigned long long tw0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw0));
 #endif
-        pruned_phase1<M, NC1, NE, L>(V, G, F, gtid, gsize, qctr, boxes, wbuf, best, bestkey, ncand);
+        pruned_phase1<M, NC1, NE, L, false>(V, G, F, gtid, gsize, qctr, boxes, wbuf, best, bestkey, ncand, 0);
 #ifdef TSP_PHASE_TIMING
         {   // slowest and average warp of phase 1 (phase_ns[3] = sum over scans of the max, [4]/[5] reused below)
             unsigned long long tw1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw1));
@@ -623,7 +572,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #ifdef TSP_PHASE_TIMING
             if (gtid == 0) { st->phase_ns[4] += (long long)(q & PR_UNIT_MASK); st->phase_ns[5] += (long long)(q >> 40); }
 #endif
-            pruned_phase2<M, NE>(V, G, F, gw, Wtot, q, boxes, wbuf, best, bestkey, ncand);
+            pruned_phase2<M, NE, false>(V, G, F, gw, Wtot, q, boxes, wbuf, best, bestkey, ncand, 0);
         }
         bestkey = warp_min_key(bestkey);
         for (int off = 16; off > 0; off >>= 1) ncand += __shfl_down_sync(FULL, ncand, off);
@@ -658,6 +607,101 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         PHASE_MARK(2)
         F.node0 = b; F.pos0 = seg_s; F.node1 = V.tid[seg_e]; F.pos1 = seg_e;
         if (gtid == 0) { V.pos[F.node0] = F.pos0; V.pos[F.node1] = F.pos1; }   // deferred end-node positions
+    }
+}
+
+// ---- K5c: device-resident tabu loop over the pruned scan -------------------------------------------------
+// tabu_best_move wants the best ADMISSIBLE pair even if it worsens the tour (metaheuristic.c:189,216), so "only
+// improving pairs can win" does not hold.  But for any bound B every pair with delta < B has
+// D(p,q) - dn[p] < h or D(p+1,q+1) - dn[q] < h with h = ceil(B/2): the same two radius searches with radii
+// enlarged by h enumerate every pair below B.  An iteration searches with a bound guessed from the previous move;
+// if an admissible pair below the bound is found, the argmin over the enumerated pairs is the exact argmin (ties
+// included); otherwise the bound is multiplied by 4 and the scan repeated, and after three failures the kernel
+// returns (out->done iterations completed): the host continues with the full-scan loop (K5b), which is the right
+// tool once most nodes are tabu.  Tabu edges start no search and are rejected as partners (dns flags).  Everything
+// else -- flags, stamps, cost trace, incumbent copy -- is K5b's.
+template <class M, int BLK, int L>
+__global__ void __launch_bounds__(BLK, 1)
+tabu_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, TabuCtl T, TabuOut *out, long long iters,
+                   unsigned long long *qctr, BigBox *boxes, uint4 *wbuf_all, int bound0) {
+    constexpr int WARPS = BLK / 32;
+    constexpr int NC1 = BLK > 512 ? PR_NC_BIG : PR_NC;
+    constexpr int NE = BLK > 512 ? 2 : 4;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned long long s_key;
+    __shared__ long long s_cost, s_bestcost, s_moves;
+    __shared__ int s_bestiter, s_lastdelta;
+    const int n = V.n;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int gtid = blockIdx.x * BLK + threadIdx.x;
+    const int gsize = gridDim.x * BLK;
+    const long long gw = (long long)blockIdx.x * WARPS + warp;
+    const long long Wtot = (long long)gridDim.x * WARPS;
+    uint4 *wbuf = wbuf_all + (size_t)gw * PR_WBUF;
+    PosPatch F = {-1, 0, -1, 0};
+    if (threadIdx.x == 0) { s_cost = T.cost; s_bestcost = T.best_cost; s_moves = 0; s_bestiter = -1; s_lastdelta = 0; }
+    int bound = bound0;
+    unsigned slot = 0;
+    long long k = 0;
+    for (; k < iters; ++k) {
+        const int iter = T.first_iter + (int)k;
+        const int tenure = T.tenure[k];
+        for (int p = gtid; p <= n; p += gsize) {       // dns flags, metaheuristic.c:208, :416-418
+            const int u = V.tid[p], v = V.tid[p == n ? 1 : p + 1];
+            const int tu = T.tabu_list[u], tv = T.tabu_list[v];
+            const bool f = (iter - tu < tenure && tu != -1) || (iter - tv < tenure && tv != -1);
+            V.dns[p] = V.dn[p] - (f ? BIGPEN : 0);
+        }
+        grid.sync();
+        unsigned long long kbest = KEY_EMPTY;
+        int B = bound;
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            if (threadIdx.x == 0) s_key = KEY_EMPTY;
+            __syncthreads();
+            int best = B - 1;                           // pairs with delta < B
+            unsigned long long bestkey = KEY_EMPTY;
+            long long ncand = 0;
+            const int h = (B + 1) / 2;
+            pruned_phase1<M, NC1, NE, L, true>(V, G, F, gtid, gsize, qctr, boxes, wbuf, best, bestkey, ncand, h);
+            grid.sync();
+            pruned_phase2<M, NE, true>(V, G, F, gw, Wtot, *(volatile unsigned long long *)qctr, boxes, wbuf, best, bestkey, ncand, h);
+            bestkey = warp_min_key(bestkey);
+            if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
+            __syncthreads();
+            if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(key + slot, s_key);
+            grid.sync();
+            kbest = *(volatile unsigned long long *)(key + slot);
+            if (gtid == 0) { key[slot ^ 1] = KEY_EMPTY; *qctr = 0; }
+            slot ^= 1;
+            if (kbest != KEY_EMPTY) break;
+            B *= 4;
+            grid.sync();                                // the queue counter is reset before anybody enqueues again
+        }
+        if (kbest == KEY_EMPTY) break;                  // bound exhausted: the host goes on with the full scan
+        const int a = key_a(kbest), b = key_b(kbest), delta = key_delta(kbest);
+        if (gtid == 0) {                                // stamp a, b and their successors BEFORE the move (:235-238)
+            const int i = V.pos[a], j = V.pos[b];
+            const int sa = V.tid[i + 1], sb = V.tid[j + 1];
+            T.tabu_list[a] = iter; T.tabu_list[b] = iter; T.tabu_list[sa] = iter; T.tabu_list[sb] = iter;
+        }
+        int seg_s, seg_e;
+        apply_move<M>(V, a, b, gtid, gsize, false, seg_s, seg_e);
+        if (threadIdx.x == 0) { s_cost += delta; s_moves += 1; s_lastdelta = delta; }
+        if (gtid == 0) T.trace[k] = s_cost;             // updated just above by this very thread
+        grid.sync();
+        F.node0 = b; F.pos0 = seg_s; F.node1 = V.tid[seg_e]; F.pos1 = seg_e;
+        if (gtid == 0) { V.pos[F.node0] = F.pos0; V.pos[F.node1] = F.pos1; }
+        const bool improved = s_cost < s_bestcost;      // tsp_update_best_solution, strict '<' (tsp.c:671)
+        if (improved)
+            for (int p = gtid; p <= n; p += gsize) T.best_tid[p] = V.tid[p];
+        __syncthreads();
+        if (improved && threadIdx.x == 0) { s_bestcost = s_cost; s_bestiter = iter; }
+        bound = delta > 0 ? 2 * delta + 64 : 64;
+    }
+    __syncthreads();
+    if (gtid == 0) {
+        out->cost = s_cost; out->best_cost = s_bestcost; out->moves = s_moves; out->best_iter = s_bestiter;
+        out->done = k; out->last_delta = s_lastdelta;
     }
 }
 
@@ -736,9 +780,9 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             __syncthreads();
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
-            pruned_phase1<M, NC1, NE, 1>(V, G, F, t, BLK, &s_q, boxes, wbuf, best, bestkey, ncand);
+            pruned_phase1<M, NC1, NE, 1, false>(V, G, F, t, BLK, &s_q, boxes, wbuf, best, bestkey, ncand, 0);
             __syncthreads();
-            pruned_phase2<M, NE>(V, G, F, warp, WARPS, s_q, boxes, wbuf, best, bestkey, ncand);
+            pruned_phase2<M, NE, false>(V, G, F, warp, WARPS, s_q, boxes, wbuf, best, bestkey, ncand, 0);
             bestkey = warp_min_key(bestkey);
             if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
             __syncthreads();

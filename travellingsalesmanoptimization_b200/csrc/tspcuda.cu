@@ -654,15 +654,36 @@ extern "C" int tspcuda_tabu_search(tspcuda_ctx *c, int *path, double *cost_inout
     h_out.best_iter = -1;
     long long moves = 0;
     const int CHUNK = 4096;                            // iterations per launch
-    for (int done = 0; done < n_iters; done += CHUNK) {
-        const int cnt = std::min(CHUNK, n_iters - done);
+    // K5c (pruned scan) while it keeps finding an admissible pair below its bound, K5b (full scan) for FALLBACK
+    // iterations whenever it gives up; both continue the same device-resident state.
+    const bool can_prune = c->pruned_blocks > 0 && c->scan_mode != TSPCUDA_SCAN_FULL && n >= 4096;
+    const int FALLBACK = 32;
+    int cooldown = 0, bound = 64;
+    for (int done = 0; done < n_iters;) {
+        const bool pruned = can_prune && cooldown == 0;
+        const int cnt = pruned ? std::min(CHUNK, n_iters - done) : std::min(std::min(CHUNK, n_iters - done), cooldown > 0 ? cooldown : CHUNK);
         T.tenure = d_ten.as<int>() + done;
         T.trace = d_trace.as<long long>() + done;
         T.first_iter = first_iter + done;
         CK(cudaMemsetAsync(c->d_key, 0xFF, sizeof(unsigned long long) * 2, c->stream));
         CK(cudaEventRecord(c->ev0, c->stream));
         cudaError_t le = cudaSuccess;
-        DISPATCH_METRIC(c->metric, le = launch_tabu<M>(c, grid, T, d_out.as<TabuOut>(), cnt));
+        if (pruned) {
+            CK(cudaMemsetAsync(c->d_qctr, 0, sizeof(unsigned long long), c->stream));
+            TourView V = c->tour;
+            SpatialGrid G = c->grid;
+            unsigned long long *key = c->d_key, *qctr = c->d_qctr;
+            TabuOut *o = d_out.as<TabuOut>();
+            long long iters = cnt;
+            BigBox *boxes = c->d_boxes;
+            uint4 *wbuf = c->d_wbuf;
+            void *args[] = {&V, &G, &key, &T, &o, &iters, &qctr, &boxes, &wbuf, &bound};
+            const bool four = 4LL * n <= (long long)c->pruned_blocks * PRUNED_BLOCK;
+            if (four) { DISPATCH_METRIC(c->metric, le = cudaLaunchCooperativeKernel((void *)tabu_pruned_kernel<M, PRUNED_BLOCK, 4>, dim3(c->pruned_blocks), dim3(PRUNED_BLOCK), args, 0, c->stream)); }
+            else { DISPATCH_METRIC(c->metric, le = cudaLaunchCooperativeKernel((void *)tabu_pruned_kernel<M, PRUNED_BLOCK, 1>, dim3(c->pruned_blocks), dim3(PRUNED_BLOCK), args, 0, c->stream)); }
+        } else {
+            DISPATCH_METRIC(c->metric, le = launch_tabu<M>(c, grid, T, d_out.as<TabuOut>(), cnt));
+        }
         CK(le);
         CK(cudaEventRecord(c->ev1, c->stream));
         c->stats.kernel_launches += 1;
@@ -671,15 +692,24 @@ extern "C" int tspcuda_tabu_search(tspcuda_ctx *c, int *path, double *cost_inout
         CK(cudaStreamSynchronize(c->stream));
         float ms = 0;
         CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-        c->stats.scan_kernel_ms += ms;
         c->stats.last_kernel_ms = ms;
-        c->stats.scans += cnt;
+        c->stats.scans += o.done;
         c->stats.moves += o.moves;
-        c->stats.pair_evals += (long long)cnt * ((long long)n * (n - 1) / 2);
+        if (pruned) {
+            c->stats.pruned_kernel_ms += ms;
+            c->stats.pruned_scans += o.done;
+            cooldown = o.done < cnt ? FALLBACK : 0;
+            if (o.last_delta > 0) bound = 2 * o.last_delta + 64;
+        } else {
+            c->stats.scan_kernel_ms += ms;
+            c->stats.pair_evals += o.done * ((long long)n * (n - 1) / 2);
+            if (cooldown > 0) cooldown = std::max(0, cooldown - (int)o.done);
+        }
         moves += o.moves;
         T.cost = o.cost; T.best_cost = o.best_cost;
         h_out.cost = o.cost; h_out.best_cost = o.best_cost;
         if (o.best_iter >= 0) h_out.best_iter = o.best_iter;
+        done += (int)o.done;
     }
     c->tour_loaded = false;
     c->dev_moves += moves;
