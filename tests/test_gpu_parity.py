@@ -777,3 +777,23 @@ def test_tabu_search_pruned_loop_matches_per_call_path(tsp, oracle, kind):
     for k in range(12):
         co, a, b, d = oracle.tabu_move(xy, po, co, to, tenures[k], k)
         assert co == trace_a[k], k
+
+
+def test_tabu_search_pruned_vs_full_loop_pla85900(tsp):
+    """K5c against K5b at the headline size (more tour positions than phase-1 threads: several trips per thread)."""
+    xy, _ = load_instance("pla85900")
+    n = xy.shape[0]
+    tenures = [30 + (k * 7) % 50 for k in range(40)]
+    with tsp.Instance(xy) as I:
+        code, p, c = I.nn(0)
+        code, mv, p, c, _ = I.two_opt(p)
+        res = {}
+        for mode in (tsp.SCAN_FULL, tsp.SCAN_AUTO):
+            I.set_scan_mode(mode)
+            pm, tm = p.copy(), np.full(n, -1, dtype=np.int32)
+            I.reset_stats()
+            cm, trace, bi, bp, bc = I.tabu_search(pm, c, tm, tenures)
+            res[mode] = (cm, list(trace), bi, bc, pm, tm, I.stats()["pruned_scans"])
+    f, a = res[tsp.SCAN_FULL], res[tsp.SCAN_AUTO]
+    assert f[:4] == a[:4] and np.array_equal(f[4], a[4]) and np.array_equal(f[5], a[5])
+    assert f[6] == 0 and a[6] > 0
