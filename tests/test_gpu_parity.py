@@ -797,3 +797,30 @@ def test_tabu_search_pruned_vs_full_loop_pla85900(tsp):
     f, a = res[tsp.SCAN_FULL], res[tsp.SCAN_AUTO]
     assert f[:4] == a[:4] and np.array_equal(f[4], a[4]) and np.array_equal(f[5], a[5])
     assert f[6] == 0 and a[6] > 0
+
+
+def test_tabu_restarts_helper(tsp, oracle):
+    """multistart.tabu_restarts (config 5: restarts = start nodes, sharded like the multi-start drivers): the tenure
+    schedule equals the reference's tabu_init + tabu_linear_policy, the shard result equals the restarts run by hand."""
+    from travellingsalesmanoptimization_b200 import multistart as MS
+    xy, _ = load_instance("kroA100")
+    n = xy.shape[0]
+    tenure, lo, hi = oracle.tabu_init(n)
+    inc, ref = True, []
+    for _ in range(150):
+        tenure, inc = oracle.tabu_linear_step(tenure, lo, hi, inc)
+        ref.append(tenure)
+    assert MS.tabu_tenures(n, 150) == ref
+    with tsp.Instance(xy) as I:
+        bc, bs, bp = MS.tabu_restarts(I, 1, 3, 4, 60)             # starts 1, 5, 9: rank 1 of 4
+        by_hand = []
+        for start in (1, 5, 9):
+            code, p, c = I.nn(start)
+            code, mv, p, c, _ = I.two_opt(p)
+            tl, best = np.full(n, -1, dtype=np.int32), c
+            for k, t in enumerate(ref[:60]):
+                c, _ = I.tabu_move(p, c, tl, t, k)
+                best = min(best, c)
+            by_hand.append(best)
+    assert bc == min(by_hand) and bs == (1, 5, 9)[by_hand.index(min(by_hand))]
+    assert oracle.is_tour(bp) and oracle.tour_cost(xy, bp) == bc

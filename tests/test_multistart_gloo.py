@@ -71,3 +71,16 @@ def test_shard_and_key():
     assert MS.unpack_key(MS.pack_key(148543747, 85899)) == (148543747, 85899)
     # a rank that owns no start cannot win
     assert MS.NO_RESULT > MS.pack_key((1 << 42) - 1, (1 << 20) - 1)
+
+
+def test_tabu_tenure_schedule_matches_reference_policy(oracle):
+    """multistart.tabu_tenures (host logic of the sharded tabu restarts) against the oracle's restatement of
+    tabu_init + tabu_linear_policy (metaheuristic.c:40-84, pinned on the reference objects elsewhere)."""
+    from travellingsalesmanoptimization_b200 import multistart as MS
+    for n in (8, 52, 100, 2392, 15112, 20000):
+        tenure, lo, hi = oracle.tabu_init(n)
+        inc, ref = True, []
+        for _ in range(3 * max(1, hi - lo) + 7):
+            tenure, inc = oracle.tabu_linear_step(tenure, lo, hi, inc)
+            ref.append(tenure)
+        assert MS.tabu_tenures(n, len(ref)) == ref, n

@@ -48,3 +48,38 @@ def reduce_best(dist, device, local_cost, local_start, local_path, first_start=0
     path = local_path.to(device) if dist.get_rank() == owner else torch.zeros_like(local_path, device=device)
     dist.all_reduce(path, op=dist.ReduceOp.SUM)
     return cost, start, path
+
+
+def tabu_tenures(n, k):
+    """The reference's tenure schedule: tabu_init (metaheuristic.c:65-84: MIN_FRACTION 0.125, MAX_FRACTION 0.25) followed by
+    k steps of tabu_linear_policy (:40-59) -- pure integer bookkeeping that depends on n and k only."""
+    lo, hi = int(0.125 * n), int(0.25 * n)
+    tenure, inc, out = int(0.125 * n + 1), True, []
+    for _ in range(k):
+        if tenure == hi or tenure == lo:
+            inc = not inc
+        tenure += 1 if inc else -1
+        out.append(tenure)
+    return out
+
+
+def tabu_restarts(inst, first_start, count, stride, k):
+    """Config 5 "restarts" (a framework addition -- the reference has one trajectory): restart r = start node
+    first_start + r*stride: NN tour -> 2-opt local optimum -> k tabu iterations (linear tenure), all device-resident.
+    Returns this shard's best (cost, start, path) under the incumbent rule (strict '<', ascending starts), or
+    (None, -1, None) for an empty shard; reduce_best() merges the shards."""
+    import numpy as np
+    best_cost, best_start, best_path = None, -1, None
+    tenures = tabu_tenures(inst.n, k)
+    for r in range(count):
+        start = first_start + r * stride
+        code, path, cost = inst.nn(start)
+        code, moves, path, cost, _ = inst.two_opt(path)
+        tl = np.full(inst.n, -1, dtype=np.int32)
+        run_best, run_path = cost, path.copy()
+        final, trace, bi, bp, bc = inst.tabu_search(path, cost, tl, tenures, incumbent_cost=cost)
+        if bi >= 0:
+            run_best, run_path = bc, bp
+        if best_cost is None or run_best < best_cost:
+            best_cost, best_start, best_path = run_best, start, run_path
+    return best_cost, best_start, best_path
