@@ -100,6 +100,7 @@ def cpu_sample(xy, path, seconds):
     """Oracle port (oracle/onfly.c), all host threads, on a bounded row range of one pla85900 scan."""
     from oracle.bindings import Oracle
     O = Oracle()
+    O.set_num_threads(len(os.sched_getaffinity(0)))
     n = xy.shape[0]
     threads = O.num_threads()
     t = time.perf_counter()
@@ -120,6 +121,9 @@ def run_reference(args):
         return
     from oracle.bindings import Oracle, load_instance
     O = Oracle()
+    # every host core this process may use: torchrun exports OMP_NUM_THREADS=1 to its workers, which would
+    # silently make the CPU arm single-threaded (the other ranks do no work in this arm)
+    O.set_num_threads(len(os.sched_getaffinity(0)))
     xy, _ = load_instance(args.workload)
     n = xy.shape[0]
     # the same tour our arm starts from: nearest neighbour from node 0, built by the oracle (setup, untimed)
