@@ -413,9 +413,7 @@ ERROR_CODE h_greedy_2opt(void) {
  * (tsp.c:671), so one tsp_update_best_solution with the first tour that reaches the minimum cost of
  * the run leaves the same incumbent as the per-iteration calls. */
 ERROR_CODE mh_TabuSearch(void) {
-    /* the default -k is INT_MAX (tsp.c:12: the reference then iterates until it is interrupted): laying out that many
-     * tenures ahead is pointless, keep the reference's own loop over the interposed tabu_best_move there */
-    if (!batch_enabled() || tsp_env.k > (1 << 22))
+    if (!batch_enabled())
         return ((void_fn)dlsym(RTLD_NEXT, "mh_TabuSearch"))();
     g_calls[C_TABULOOP]++;
     tabu_search ts;
@@ -435,44 +433,51 @@ ERROR_CODE mh_TabuSearch(void) {
     memcpy(solution.path, tsp_inst.best_solution.path, tsp_inst.nnodes * sizeof(int));
     log_debug("2opt greedy sol cost: %f", solution.cost);
 
+    /* The k iterations in blocks of at most 2^20 (the default -k is INT_MAX, tsp.c:12: the reference then iterates
+     * until it is interrupted, and so does this loop): tenures of the block from the reference's own policy functions,
+     * one device-resident run, then the block's incumbent update and results lines. */
     const int K = tsp_env.k > 0 ? tsp_env.k : 0;
-    int *tenures = (int *)malloc(sizeof(int) * (K > 0 ? K : 1));
-    double *trace = (double *)malloc(sizeof(double) * (K > 0 ? K : 1));
-    for (int k = 0; k < K; k++) {                                   /* :136-156 */
-        switch (tsp_env.policy) {
-            case POL_FIXED: e = tabu_fixed_policy(&ts, 30); break;
-            case POL_LINEAR: e = tabu_linear_policy(&ts); break;
-            case POL_RANDOM: e = tabu_random_policy(&ts); break;
-            case POL_SIZE: e = tabu_dependent_policy(&ts); break;
-            default: e = UNKNOWN; break;
-        }
-        if (!err_ok(e)) log_warn("using already set policy %d", tsp_env.policy);
-        tenures[k] = ts.tenure;
-    }
+    const int BLOCK = 1 << 20;
+    const int cap = K < BLOCK ? (K > 0 ? K : 1) : BLOCK;
+    int *tenures = (int *)malloc(sizeof(int) * cap);
+    double *trace = (double *)malloc(sizeof(double) * cap);
     tspcuda_ctx *c = ctx_for_instance();
     tsp_solution best;
     tsp_init_solution(tsp_inst.nnodes, &best);
-    int best_iter = -1;
-    int rc = c ? tspcuda_tabu_search(c, solution.path, &solution.cost, ts.tabu_list, tenures, 0, K, tsp_inst.best_solution.cost,
-                                     trace, best.path, &best.cost, &best_iter)
-               : TSPCUDA_INTERNAL;
-    if (rc != TSPCUDA_OK) {
-        log_fatal("code %d : Error in tabu best move (libtspcuda: %s)", rc, tspcuda_last_error());
-        tsp_handlefatal();
-    }
-    e = K > 0 ? CANCELLED : e;                                      /* what the last tsp_update_best_solution returns */
-    if (best_iter >= 0) {
-        ERROR_CODE u = tsp_update_best_solution(&best);
-        if (!err_ok(u)) {
-            log_fatal("code %d : Error in updating best solution", u);
+    for (int k0 = 0; k0 < K; k0 += BLOCK) {
+        const int cnt = K - k0 < BLOCK ? K - k0 : BLOCK;
+        for (int k = 0; k < cnt; k++) {                             /* :136-156 */
+            switch (tsp_env.policy) {
+                case POL_FIXED: e = tabu_fixed_policy(&ts, 30); break;
+                case POL_LINEAR: e = tabu_linear_policy(&ts); break;
+                case POL_RANDOM: e = tabu_random_policy(&ts); break;
+                case POL_SIZE: e = tabu_dependent_policy(&ts); break;
+                default: e = UNKNOWN; break;
+            }
+            if (!err_ok(e)) log_warn("using already set policy %d", tsp_env.policy);
+            tenures[k] = ts.tenure;
+        }
+        int best_iter = -1;
+        int rc = c ? tspcuda_tabu_search(c, solution.path, &solution.cost, ts.tabu_list, tenures, k0, cnt,
+                                         tsp_inst.best_solution.cost, trace, best.path, &best.cost, &best_iter)
+                   : TSPCUDA_INTERNAL;
+        if (rc != TSPCUDA_OK) {
+            log_fatal("code %d : Error in tabu best move (libtspcuda: %s)", rc, tspcuda_last_error());
             tsp_handlefatal();
         }
-        if (best_iter == K - 1) e = u;
+        e = CANCELLED;                                              /* what the last tsp_update_best_solution returns */
+        if (best_iter >= 0) {
+            ERROR_CODE u = tsp_update_best_solution(&best);
+            if (!err_ok(u)) {
+                log_fatal("code %d : Error in updating best solution", u);
+                tsp_handlefatal();
+            }
+            if (best_iter == k0 + cnt - 1) e = u;
+        }
+        if (f)
+            for (int k = 0; k < cnt; k++) fprintf(f, "%d,%f\n", k0 + k, trace[k]);     /* :163 */
     }
-    if (f) {
-        for (int k = 0; k < K; k++) fprintf(f, "%d,%f\n", k, trace[k]);     /* :163 */
-        fclose(f);
-    }
+    if (f) fclose(f);
     PLOT plot = plot_open("TabuIterationsPlot");
     if (tsp_env.tofile) plot_tofile(plot, "TabuIterationsPlot");
     plot_stats(plot, "results/TabuResults.dat");
