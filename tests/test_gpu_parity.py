@@ -351,6 +351,11 @@ def test_tabu_search_device_loop_vs_oracle(tsp, oracle):
     with tsp.Instance(xy) as I:
         c1, tr1, bi1, bp1, bc1 = I.tabu_search(pg, c, tg, tenures[:170])
         c2, tr2, bi2, bp2, bc2 = I.tabu_search(pg, c1, tg, tenures[170:], first_iter=170, incumbent_cost=bc1 if bi1 >= 0 else c)
+        # a per-call tabu move right after the device loop, same context, tour still resident (regression: the
+        # host mirror of the device move counter must not drift)
+        c3, mv3 = I.tabu_move(pg, c2, tg, 25, 300)
+    co3, a3, b3, d3 = oracle.tabu_move(xy, po, co, to, 25, 300)
+    assert mv3 == (a3, b3, int(d3)) and c3 == co3
     assert list(tr1) + list(tr2) == trace_o and c2 == co
     assert np.array_equal(pg, po) and np.array_equal(tg, to)
     best = min(trace_o)

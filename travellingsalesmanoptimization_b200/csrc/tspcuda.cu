@@ -711,8 +711,8 @@ extern "C" int tspcuda_tabu_search(tspcuda_ctx *c, int *path, double *cost_inout
         if (o.best_iter >= 0) h_out.best_iter = o.best_iter;
         done += (int)o.done;
     }
-    c->tour_loaded = false;
-    c->dev_moves += moves;
+    c->tour_loaded = false;                            // (the tabu kernels do not touch d_state->moves: dev_moves stays its mirror)
+    (void)moves;
     // results: trace, tabu list, final tour, best tour
     if (cost_trace_out) {
         std::vector<long long> tr(n_iters);
