@@ -674,7 +674,7 @@ tabu_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, TabuCtl T
             if (gtid == 0) { key[slot ^ 1] = KEY_EMPTY; *qctr = 0; }
             slot ^= 1;
             if (kbest != KEY_EMPTY) break;
-            B *= 4;
+            B = B < (1 << 26) ? B * 4 : (1 << 28);      // deltas stay below 2^29 (packed key)
             grid.sync();                                // the queue counter is reset before anybody enqueues again
         }
         if (kbest == KEY_EMPTY) break;                  // bound exhausted: the host goes on with the full scan
@@ -696,7 +696,7 @@ tabu_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, TabuCtl T
             for (int p = gtid; p <= n; p += gsize) T.best_tid[p] = V.tid[p];
         __syncthreads();
         if (improved && threadIdx.x == 0) { s_bestcost = s_cost; s_bestiter = iter; }
-        bound = delta > 0 ? 2 * delta + 64 : 64;
+        bound = delta > 0 ? min(2 * delta + 64, 1 << 26) : 64;
     }
     __syncthreads();
     if (gtid == 0) {

@@ -699,7 +699,7 @@ extern "C" int tspcuda_tabu_search(tspcuda_ctx *c, int *path, double *cost_inout
             c->stats.pruned_kernel_ms += ms;
             c->stats.pruned_scans += o.done;
             cooldown = o.done < cnt ? FALLBACK : 0;
-            if (o.last_delta > 0) bound = 2 * o.last_delta + 64;
+            if (o.last_delta > 0) bound = std::min(2 * o.last_delta + 64, 1 << 26);
         } else {
             c->stats.scan_kernel_ms += ms;
             c->stats.pair_evals += o.done * ((long long)n * (n - 1) / 2);
