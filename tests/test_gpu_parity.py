@@ -829,3 +829,45 @@ def test_tabu_restarts_helper(tsp, oracle):
             by_hand.append(best)
     assert bc == min(by_hand) and bs == (1, 5, 9)[by_hand.index(min(by_hand))]
     assert oracle.is_tour(bp) and oracle.tour_cost(xy, bp) == bc
+
+
+@pytest.mark.parametrize("name", ["d15112", "rand20000"])
+def test_full_size_properties(tsp, oracle, name):
+    """Size-independent properties at config-5 sizes: successor-array round trip through the device tour slot;
+    a random tour descended 80 moves gives the same log under FULL, PRUNED and AUTO (which switches kernels on the
+    way); cost bookkeeping equals the oracle's recomputation; a local optimum is a fixed point (0 moves, same tour)."""
+    xy = oracle.random_points(20000, 123) if name == "rand20000" else load_instance(name)[0]
+    n = xy.shape[0]
+    rnd = _rand_tour(99, n)
+    logs = {}
+    with tsp.Instance(xy) as I:
+        I.tour_upload(rnd)
+        back, cost0 = I.tour_download()
+        assert np.array_equal(back, rnd) and cost0 == oracle.tour_cost(xy, rnd)
+        for scan, mode in (("full", tsp.SCAN_FULL), ("pruned", tsp.SCAN_PRUNED), ("auto", tsp.SCAN_AUTO)):
+            I.set_scan_mode(mode)
+            code, mv, p2, c2, log = I.two_opt(rnd, max_moves=80, log_cap=80)
+            logs[scan] = (mv, c2, log, p2)
+        assert logs["full"][:3] == logs["pruned"][:3] == logs["auto"][:3]
+        assert np.array_equal(logs["full"][3], logs["pruned"][3]) and np.array_equal(logs["full"][3], logs["auto"][3])
+        assert logs["full"][1] == oracle.tour_cost(xy, logs["full"][3]) == cost0 + sum(d for _, _, d in logs["full"][2])
+        code, p, c = I.nn(7)
+        code, mv, popt, copt, _ = I.two_opt(p)
+        code, mv2, popt2, copt2, _ = I.two_opt(popt)
+        assert mv2 == 0 and copt2 == copt and np.array_equal(popt2, popt)
+        d, a, b = oracle.two_opt_scan(xy, popt)
+        assert d >= -1e-7
+
+
+def test_scan_mode_environment(tsp, oracle, monkeypatch):
+    """TSPCUDA_SCAN pins the kernel for contexts created afterwards (how the unchanged CLI selects it)."""
+    xy = _rand_xy(12, 1500, True)
+    path = _rand_tour(4, 1500)
+    m_o, p_o, c_o, *_ = oracle.two_opt(xy, path, log=False)
+    for val, pruned_expected in (("full", False), ("pruned", True)):
+        monkeypatch.setenv("TSPCUDA_SCAN", val)
+        with tsp.Instance(xy) as I:
+            code, mv, p2, c2, _ = I.two_opt(path)
+            st = I.stats()
+        assert mv == m_o and c2 == c_o and np.array_equal(p2, p_o)
+        assert (st["pruned_scans"] == st["scans"]) == pruned_expected and (st["pruned_scans"] == 0) == (not pruned_expected)
