@@ -124,7 +124,8 @@ def test_matches_reference_cli(workdir, golden):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,seed,alg,algid,k", [(300, 7, "2OPT_GREEDY", 2, None), (200, 11, "TABU_SEARCH", 3, 40), (150, 5, "GREEDY_ITER", 1, None)])
+@pytest.mark.parametrize("n,seed,alg,algid,k", [(300, 7, "2OPT_GREEDY", 2, None), (200, 11, "TABU_SEARCH", 3, 40), (150, 5, "GREEDY_ITER", 1, None),
+                                                 (250, 3, "VNS", 4, 12), (180, 9, "EXTRA_MILEAGE", 5, None), (90, 2, "GREEDY", 0, None)])
 def test_random_instances_match_reference_objects(workdir, reference, n, seed, alg, algid, k):
     """`-n N -seed S` (src/tsp.c:468-481).  The reference's own CLI aborts at exit for -n on this glibc
     (free(): invalid pointer, the utils_format_title overflow on its 40-byte plot-name buffer), so the
