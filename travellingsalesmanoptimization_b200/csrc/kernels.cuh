@@ -576,11 +576,8 @@ __device__ __forceinline__ double cost_as_double(int koff) {
     return __hiloint2double(0x43300000, koff - KOFF) - 4503599627370496.0;
 }
 
-#ifndef TSP_K1_UNROLL
-#define TSP_K1_UNROLL 1
-#endif
-#ifndef TSP_K1_STREAM
-#define TSP_K1_STREAM 1
+#ifndef TSP_K1_ROWS
+#define TSP_K1_ROWS 8
 #endif
 #ifndef TSP_K1_BLOCK
 #define TSP_K1_BLOCK 256
@@ -588,42 +585,45 @@ __device__ __forceinline__ double cost_as_double(int koff) {
 #ifndef TSP_K1_CTAS
 #define TSP_K1_CTAS 16
 #endif
+// A CTA fills TSP_K1_ROWS rows at a time, so that the column coordinates -- which every row needs and which do not
+// fit L1 for large n -- are read from L2 once per row group instead of once per row (ncu on the one-row version:
+// long-scoreboard stalls on those loads dominate, L2->SM traffic is twice the bytes written).  Rows of a group have the
+// same 16-byte alignment: consecutive rows when n is even, every other row when n is odd (row i starts at cell i*n).
 template <class M>
 __global__ void __launch_bounds__(TSP_K1_BLOCK)
 cost_matrix_kernel(const double2 *__restrict__ xy, int n, double *__restrict__ out) {
-    constexpr int U = TSP_K1_UNROLL;              // independent 16-byte stores in flight per thread
-    for (int i = blockIdx.x; i < n; i += gridDim.x) {
-        const double2 pi = xy[i];
-        const size_t base = (size_t)i * (size_t)n;
-        const int off = (int)(base & 1);            // first cell of the row that is 16-byte aligned
-        double *row = out + base;
+    constexpr int RB = TSP_K1_ROWS;
+    const int s = (n & 1) ? 2 : 1;                       // row stride inside a group
+    const int span = RB * s;                             // consecutive rows covered by s groups
+    const int ngroups = ((n + span - 1) / span) * s;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int first = (g / s) * span + (g % s);      // rows first, first + s, ...
+        const int off = (int)(((size_t)first * (size_t)n) & 1);
+        double2 pr[RB];
+#pragma unroll
+        for (int k = 0; k < RB; ++k) pr[k] = xy[min(first + k * s, n - 1)];
         const int npairs = (n - off) >> 1;
-        for (int t0 = threadIdx.x; t0 < npairs; t0 += blockDim.x * U) {
-            double2 v[U];
+        for (int t = threadIdx.x; t < npairs; t += blockDim.x) {
+            const int j = off + 2 * t;
+            const double2 p0 = xy[j], p1 = xy[j + 1];
 #pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int t = min(t0 + u * (int)blockDim.x, npairs - 1);
-                const int j = off + 2 * t;
-                const double2 p0 = xy[j], p1 = xy[j + 1];
-                v[u].x = (j == i) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p0.x, p0.y));
-                v[u].y = (j + 1 == i) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p1.x, p1.y));
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int t = t0 + u * (int)blockDim.x;
-                if (t < npairs) {
-                    double2 *dst = reinterpret_cast<double2 *>(row + off + 2 * t);
-#if TSP_K1_STREAM
-                    __stcs(dst, v[u]);             // written once, never re-read by this kernel: streaming store
-#else
-                    *dst = v[u];
-#endif
+            for (int k = 0; k < RB; ++k) {
+                const int i = first + k * s;
+                if (i < n) {
+                    const double v0 = (j == i) ? -1.0 : cost_as_double(M::K(pr[k].x, pr[k].y, p0.x, p0.y));
+                    const double v1 = (j + 1 == i) ? -1.0 : cost_as_double(M::K(pr[k].x, pr[k].y, p1.x, p1.y));
+                    __stcs(reinterpret_cast<double2 *>(out + (size_t)i * (size_t)n + j), make_double2(v0, v1));   // written once: streaming store
                 }
             }
         }
-        if (threadIdx.x == 0) {
-            if (off) { const double2 p = xy[0]; row[0] = (i == 0) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p.x, p.y)); }
-            if ((n - off) & 1) { const double2 p = xy[n - 1]; row[n - 1] = (i == n - 1) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p.x, p.y)); }
+        if (threadIdx.x < RB) {                          // the unpaired first / last cell of each row
+            const int k = threadIdx.x, i = first + k * s;
+            if (i < n) {
+                double *row = out + (size_t)i * (size_t)n;
+                const double2 pi = xy[i];
+                if (off) { const double2 p = xy[0]; row[0] = (i == 0) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p.x, p.y)); }
+                if ((n - off) & 1) { const double2 p = xy[n - 1]; row[n - 1] = (i == n - 1) ? -1.0 : cost_as_double(M::K(pi.x, pi.y, p.x, p.y)); }
+            }
         }
     }
 }
