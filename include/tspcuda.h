@@ -20,6 +20,7 @@
  *   tspcuda_multistart_two_opt    h_greedy_2opt loop           algorithms/heuristics.c:74-116
  *   tspcuda_extra_mileage         h_ExtraMileage / h_extramileage_util   algorithms/heuristics.c:156-210, :290-367
  *   tspcuda_mx_nn / _two_opt      h_greedyutil / ref_2opt on a caller's matrix (h_Greedy_2opt_mod_costs, heuristics.c:118-149)
+ *   tspcuda_patching              cx_patching (+ its while (ncomp > 1) loop)   algorithms/cplex_model.c:693-755, :205-212
  *
  * Tours cross the boundary exactly as the reference stores them: a successor array int path[n],
  * path[i] = node visited after node i (src/utils/utils.h:42-47).  Costs are doubles holding
@@ -41,6 +42,7 @@ enum {
     TSPCUDA_INVALID_ARGUMENT = 3,   /* bad pointer / not a single-cycle successor array */
     TSPCUDA_DEADLINE_EXCEEDED = 4,  /* time limit hit between scans (refinment.c:17-24); not an error */
     TSPCUDA_RESOURCE_EXHAUSTED = 8, /* device memory */
+    TSPCUDA_FAILED_PRECONDITION = 9,/* patching: no admissible pair (see tspcuda_patching) */
     TSPCUDA_OUT_OF_RANGE = 11,      /* n or coordinate extent beyond what the packed key supports */
     TSPCUDA_UNIMPLEMENTED = 12,
     TSPCUDA_INTERNAL = 13,          /* CUDA failure */
@@ -171,6 +173,20 @@ int tspcuda_multistart_two_opt(tspcuda_ctx *ctx, int first_start, int nstarts, i
  * *cost_out = 2 c(A,B) + the mileage of every insertion (:193, :360); path_out = successor array. */
 int tspcuda_extra_mileage(tspcuda_ctx *ctx, int node_a, int node_b, int *path_out, double *cost_out,
                           int *node_a_out, int *node_b_out);
+
+/* ---- patching heuristic of the Benders loop (cplex_model.c:693-755 cx_patching) ------------------------- */
+/* path: a successor array made of *ncomp_inout disjoint cycles, comp[v] = label of the cycle of v (one label
+ * per cycle, as cx_build_sol leaves them; anything else is INVALID_ARGUMENT).  One patch = the first strict
+ * minimum, over ordered node pairs (a,b) of different components in a-major order, of
+ * delta = [c(a,succ b) + c(b,succ a)] - [c(a,succ a) + c(b,succ b)] among the pairs with delta > 0 (:699-722);
+ * then path[a] = succ b, path[b] = succ a, *cost_inout += delta, the cycle of b takes the label of a and
+ * *ncomp_inout decreases (:727-754).  max_patches < 0: until one component is left -- the caller's
+ * `while (solution.ncomp > 1) cx_patching(&solution)` (:205-212) in one device-resident run; 1 = one call of
+ * cx_patching.  log (may be NULL): (a, b, delta) of the first log_cap patches; *patches_out (may be NULL):
+ * patches applied.  If some scan finds no pair with delta > 0 the state reached so far is returned with
+ * TSPCUDA_FAILED_PRECONDITION (the reference has undefined behaviour there: it indexes path[-1], :730-735). */
+int tspcuda_patching(tspcuda_ctx *ctx, int *path, int *comp, int *ncomp_inout, double *cost_inout, int max_patches,
+                     tspcuda_move *log, int64_t log_cap, int *patches_out);
 
 /* ---- the `costs`-argument paths: a caller-supplied dense matrix ------------------------------- */
 /* h_greedyutil / ref_2opt / ref_2opt_once called with a matrix other than the instance's own

@@ -86,6 +86,7 @@ class Oracle:
         L.orc_tabu_init.argtypes = [C.c_int, _ip, _ip, _ip]
         L.orc_tabu_linear_step.argtypes = [_ip, C.c_int, C.c_int, _ip]
         L.orc_vns_kick.argtypes = [C.c_int, _ip]
+        L.orc_patching.argtypes = [_dp, C.c_int, C.c_int, _ip, _ip, _ip, _dp, _ip, _ip, _dp]
         L.orc_audit_moves.restype = C.c_long
         L.orc_audit_moves.argtypes = [_dp, C.c_int, C.c_int, _ip, C.c_long, _ip, _ip, _dp, _lp, C.c_long]
         L.orc_num_threads.restype = C.c_int
@@ -230,6 +231,14 @@ class Oracle:
     def vns_kick(self, path):
         self.L.orc_vns_kick(path.shape[0], _i(path))
 
+    def patching(self, xy, path, comp, ncomp, cost, wt=EUC_REF):
+        """cx_patching, one patch in place on path / comp: (applied, ncomp, cost, a, b, delta)."""
+        nc, c = C.c_int(ncomp), C.c_double(cost)
+        a, b, d = C.c_int(-1), C.c_int(-1), C.c_double(0)
+        r = self.L.orc_patching(_d(xy), xy.shape[0], wt, _i(path), _i(comp), C.byref(nc), C.byref(c), C.byref(a),
+                                C.byref(b), C.byref(d))
+        return bool(r), nc.value, c.value, a.value, b.value, d.value
+
     def audit_moves(self, xy, path, log_a, log_b, log_delta, full_at, wt=EUC_REF):
         path = np.array(path, dtype=np.int32, copy=True)
         la = np.ascontiguousarray(log_a, dtype=np.int32); lb = np.ascontiguousarray(log_b, dtype=np.int32)
@@ -278,6 +287,7 @@ class Reference:
         L.refapi_tabu_init.argtypes = [C.c_int, _ip, _ip, _ip]
         L.refapi_tabu_linear_step.argtypes = [_ip, C.c_int, C.c_int, _ip]
         L.refapi_vns_kick.argtypes = [_ip]
+        L.refapi_patching.argtypes = [_ip, _ip, _ip, _dp]
         L.refapi_run.argtypes = [C.c_int, C.c_int, _ip, _dp, _ip]
         L.refapi_reverse_calls.restype = C.c_long
         L.refapi_last_move.argtypes = [_ip, _ip]
@@ -366,6 +376,12 @@ class Reference:
 
     def vns_kick(self, path):
         assert self.L.refapi_vns_kick(_i(path)) == 0
+
+    def patching(self, path, comp, ncomp, cost):
+        """The reference's cx_patching (cplex_model.c:693), one patch in place: (ncomp, cost)."""
+        nc, c = C.c_int(ncomp), C.c_double(cost)
+        self.L.refapi_patching(_i(path), _i(comp), C.byref(nc), C.byref(c))
+        return nc.value, c.value
 
     def run(self, alg, k=2**31 - 1):
         """alg: 0 GREEDY, 1 GREEDY_ITER, 2 2OPT_GREEDY, 3 TABU_SEARCH, 4 VNS, 5 EXTRA_MILEAGE (EM_MAX). Needs ./results/ for 3/4."""

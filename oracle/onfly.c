@@ -586,6 +586,48 @@ void orc_vns_kick(int n, int *path) {
     free(tour);
 }
 
+/* cplex_model.c:693-755 cx_patching: ONE patch of a successor array made of several cycles (comp[v] =
+ * label of the cycle of v, *ncomp of them).  Ordered pairs (a,b), a-major / b-minor, of different
+ * components (:699-706); delta = [c(a,succ b) + c(b,succ a)] - [c(a,succ a) + c(b,succ b)] (:712-714);
+ * kept on strict '<' AND delta > 0 (:716).  Then path[a] = succ b, path[b] = succ a, cost += delta, the
+ * cycle of b is relabelled with comp[a] by walking from succ b until b, ncomp-- (:727-754).
+ * Returns 1 and the pair in *a_out / *b_out / *delta_out (any may be NULL) if a patch was applied; 0 and
+ * no change when no pair has delta > 0 (the reference then indexes path[-1], :730-735: undefined).
+ * Costs on the fly with 64-bit-safe indexing (the reference reads tsp_inst.costs through tsp_get_cost). */
+int orc_patching(const double *xy, int n, int wt, int *path, int *comp, int *ncomp, double *cost, int *a_out,
+                 int *b_out, double *delta_out) {
+    double best_delta = __DBL_MAX__;
+    int ba = -1, bb = -1;
+    for (int a = 0; a < n; a++) {
+        int sa = path[a];
+        double casa = orc_edge(wt, xy[2 * a], xy[2 * a + 1], xy[2 * sa], xy[2 * sa + 1]);
+        for (int b = 0; b < n; b++) {
+            if (comp[a] == comp[b]) continue;
+            int sb = path[b];
+            double current = casa + orc_edge(wt, xy[2 * b], xy[2 * b + 1], xy[2 * sb], xy[2 * sb + 1]);
+            double swapped = orc_edge(wt, xy[2 * a], xy[2 * a + 1], xy[2 * sb], xy[2 * sb + 1]) +
+                             orc_edge(wt, xy[2 * b], xy[2 * b + 1], xy[2 * sa], xy[2 * sa + 1]);
+            double delta = swapped - current;
+            if (delta < best_delta && delta > 0) { best_delta = delta; ba = a; bb = b; }
+        }
+    }
+    if (ba < 0) return 0;
+    int sa = path[ba], sb = path[bb];
+    path[ba] = sb;
+    path[bb] = sa;
+    *cost += best_delta;
+    int label = comp[ba];
+    for (int i = sb;; i = path[i]) {          /* path[bb] already points at sa, as in the reference's walk */
+        comp[i] = label;
+        if (i == bb) break;
+    }
+    *ncomp -= 1;
+    if (a_out) *a_out = ba;
+    if (b_out) *b_out = bb;
+    if (delta_out) *delta_out = best_delta;
+    return 1;
+}
+
 /* ---------------------------------------------------------------------------------------------
  * Audit of a GPU move log on instances too big for a full CPU descent:
  * replays `nmoves` logged moves (a,b,delta) from `path`; every logged delta is recomputed in

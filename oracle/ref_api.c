@@ -14,6 +14,9 @@
  *   ref_2opt            src/algorithms/refinment.c:3
  *   tabu_best_move      src/algorithms/metaheuristic.c:188
  *   h_Greedy_iterative / h_greedy_2opt / mh_TabuSearch / mh_VNS  (whole-algorithm entry points)
+ *   cx_patching         src/algorithms/cplex_model.c:693  (plain C; that file is compiled unchanged against
+ *                       oracle/stubs/cx/cplex.h, every CPX* / CCcut_* entry point it mentions is a generated
+ *                       stub that aborts -- cx_patching calls none of them)
  */
 #define _GNU_SOURCE
 #include <signal.h>
@@ -204,6 +207,17 @@ int refapi_vns_kick(int *path) {
     tsp_solution s; s.path = path; s.cost = 0; s.ncomp = 0; s.comp = NULL;
     return (int)vns_kick(&s);
 }
+
+/* cx_patching (cplex_model.c:693-755): one patch.  comp / ncomp as cx_build_sol leaves them. */
+void cx_patching(tsp_solution *solution);
+int refapi_patching(int *path, int *comp, int *ncomp, double *cost) {
+    tsp_solution s; s.path = path; s.cost = *cost; s.ncomp = *ncomp; s.comp = comp;
+    cx_patching(&s);
+    *cost = s.cost; *ncomp = s.ncomp;
+    return 0;
+}
+
+double refapi_solution_cost(const int *path) { return tsp_solution_cost((int *)path); }   /* src/tsp.c:730 */
 
 /* Whole-algorithm entry points, exactly as src/main.c:4-87 dispatches them (minus plotting).
  * alg: 0 GREEDY, 1 GREEDY_ITER, 2 2OPT_GREEDY, 3 TABU_SEARCH, 4 VNS, 5 EXTRA_MILEAGE with EM_MAX (tsp.h:45-50). */

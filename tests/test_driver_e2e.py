@@ -211,6 +211,30 @@ def test_mod_costs_through_the_reference_objects(workdir, batch):
 
 
 @pytest.mark.gpu
+def test_patching_through_the_reference_objects(workdir, reference):
+    """cx_patching (cplex_model.c:693-755; its only caller is the CPLEX-backed Benders loop, :205-212) reached the way
+    that loop reaches it: build/bin/harness_patching is linked like the drop-in CLI, so the reference-side call lands
+    in the interposer.  Result = what the unmodified reference objects give in this process on the same solution."""
+    from components import cycles_solution
+    from oracle.bindings import fnv1a
+    exe = os.path.join(ROOT, "build", "bin", "harness_patching")
+    n, seed = 400, 5
+    xy = reference.random_points(n, seed)
+    path, comp, nc = cycles_solution(seed, n, 37, True, xy)
+    np.concatenate([path, comp]).astype(np.int32).tofile(workdir / "sol.i32")
+    r = run_cli(exe, workdir, [str(n), str(seed), "sol.i32"])
+    patches, cost, h = r.stdout.split()
+    k = sum(float(reference.costs()[i, path[i]]) for i in range(n))
+    count = 0
+    while nc > 1:
+        nc, k = reference.patching(path, comp, nc, k)
+        count += 1
+    assert int(patches) == count == 36 and float.fromhex(cost) == k
+    assert h == fnv1a(np.concatenate([path, comp]).astype(np.int32))
+    assert calls(r.stderr)["cx_patching"] == 36
+
+
+@pytest.mark.gpu
 def test_pla85900_opens_through_the_unchanged_driver(workdir):
     """The headline instance through the drop-in CLI: CEIL_2D header (the reference reader stops there,
     tsp.c:576-583), n > 46340 (no host matrix: the reference's int n*n overflows, tsp.c:614).

@@ -871,3 +871,88 @@ def test_scan_mode_environment(tsp, oracle, monkeypatch):
             st = I.stats()
         assert mv == m_o and c2 == c_o and np.array_equal(p2, p_o)
         assert (st["pruned_scans"] == st["scans"]) == pruned_expected and (st["pruned_scans"] == 0) == (not pruned_expected)
+
+
+# ---- patching (cplex_model.c:693-755 cx_patching) ---------------------------------------
+def _golden_patching():
+    import json
+    import os
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_patching.json")) as f:
+        return json.load(f)
+
+
+@pytest.mark.parametrize("key", sorted(_golden_patching().keys()))
+def test_patching_golden(tsp, oracle, key):
+    """The whole `while (ncomp > 1) cx_patching` loop in one call against tests/golden/golden_patching.json
+    (unmodified reference cplex_model.c), and the same solution one cx_patching at a time (max_patches = 1)."""
+    from components import cycles_solution, solution_cost
+    g = _golden_patching()[key]
+    name, seed, ncomp, local = key.rsplit("_", 3)
+    xy, _ = load_instance(name)
+    path, comp, nc = cycles_solution(int(seed), xy.shape[0], int(ncomp), bool(int(local)), xy)
+    with tsp.Instance(xy) as I:
+        cost = float(g["start_cost"])
+        code, p, c, n1, k1, log = I.patching(path, comp, nc, cost)
+        assert code == 0 and n1 == 1 and len(log) == g["patches"] == nc - 1
+        assert (k1, fnv1a(p), fnv1a(c)) == (g["cost"], g["path_hash"], g["comp_hash"])
+        assert all(a < b and d > 0 for a, b, d in log) and k1 == cost + sum(d for _, _, d in log)
+        p2, c2, n2, k2, steps = path, comp, nc, cost, []
+        for _ in range(min(nc - 1, 12)):
+            code, p2, c2, n2, k2, lg = I.patching(p2, c2, n2, k2, max_patches=1)
+            assert code == 0 and len(lg) == 1
+            steps += lg
+        assert steps == log[:len(steps)] and n2 == nc - len(steps)
+
+
+@pytest.mark.parametrize("n,integer,ncomp,local", [(6, True, 2, False), (9, True, 3, False), (60, False, 20, False), (257, True, 30, True),
+                                                   (700, False, 233, False), (1500, True, 40, True)])
+def test_patching_vs_oracle(tsp, oracle, n, integer, ncomp, local):
+    """Patch by patch against the CPU restatement: lattice ties, non-integer coordinates, every metric."""
+    from components import cycles_solution, solution_cost
+    xy = _rand_xy(7 * n + integer, n, integer, lo=0, hi=40 if integer else 3000)
+    for wt, twt in ((EUC_REF, tsp.EUC_REF), (CEIL_2D, tsp.CEIL_2D), (ATT, tsp.ATT)):
+        path, comp, nc = cycles_solution(n, n, ncomp, local, xy)
+        cost = solution_cost(oracle, xy, path, wt)
+        with tsp.Instance(xy, twt) as I:
+            code, p, c, n1, k1, log = I.patching(path, comp, nc, cost, allow=(tsp.FAILED_PRECONDITION,))
+            po, co, no, ko = path.copy(), comp.copy(), nc, cost
+            for a, b, d in log:
+                ok, no, ko, ao, bo, do = oracle.patching(xy, po, co, no, ko, wt)
+                assert ok and (a, b, d) == (ao, bo, do), (wt, a, b, d, ao, bo, do)
+            if code == tsp.FAILED_PRECONDITION:                 # coarse lattices can run out of pairs with delta > 0
+                assert not oracle.patching(xy, po.copy(), co.copy(), no, ko, wt)[0]
+            else:
+                assert n1 == 1 and len(log) == nc - 1
+            assert n1 == no and k1 == ko and np.array_equal(p, po) and np.array_equal(c, co)
+
+
+def test_patching_geo(tsp, oracle):
+    xy, ewt = load_instance("gr666")
+    from components import cycles_solution, solution_cost
+    path, comp, nc = cycles_solution(3, xy.shape[0], 25, True, xy)
+    cost = solution_cost(oracle, xy, path, GEO)
+    with tsp.Instance(xy, tsp.GEO) as I:
+        code, p, c, n1, k1, log = I.patching(path, comp, nc, cost)
+    for a, b, d in log:
+        ok, nc, cost, ao, bo, do = oracle.patching(xy, path, comp, nc, cost, GEO)
+        assert ok and (a, b, d) == (ao, bo, do)
+    assert n1 == 1 and k1 == cost and np.array_equal(p, path) and np.array_equal(c, comp)
+
+
+def test_patching_edge_cases(tsp):
+    xy = np.array([[0, 0], [10, 0], [0, 0], [10, 0], [5, 5], [6, 6]], dtype=np.float64)
+    with tsp.Instance(xy[:4].copy()) as I:
+        # coincident 2-cycles: every cross pair has delta <= 0 (the reference indexes path[-1], cplex_model.c:730-735)
+        code, p, c, nc, k, log = I.patching([1, 0, 3, 2], [1, 1, 2, 2], 2, 40.0, allow=(tsp.FAILED_PRECONDITION,))
+        assert code == tsp.FAILED_PRECONDITION and nc == 2 and k == 40.0 and p.tolist() == [1, 0, 3, 2] and log == []
+        # one component: nothing to do
+        code, p, c, nc, k, log = I.patching([1, 2, 3, 0], [7, 7, 7, 7], 1, 40.0)
+        assert code == 0 and nc == 1 and k == 40.0 and p.tolist() == [1, 2, 3, 0] and log == []
+        for bad_path, bad_comp, bad_nc in (([1, 0, 3, 2], [1, 1, 1, 2], 2),      # label not constant on a cycle
+                                           ([1, 0, 3, 2], [1, 1, 1, 1], 2),      # two cycles share a label
+                                           ([1, 0, 3, 2], [1, 1, 2, 2], 3),      # wrong ncomp
+                                           ([1, 1, 3, 2], [1, 1, 2, 2], 2),      # not a permutation
+                                           ([0, 2, 3, 1], [1, 2, 2, 2], 2)):     # self-loop
+            with pytest.raises(tsp.TspCudaError) as ei:
+                I.patching(bad_path, bad_comp, bad_nc, 0.0)
+            assert ei.value.code == tsp.INVALID_ARGUMENT

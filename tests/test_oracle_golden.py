@@ -180,3 +180,38 @@ def test_extra_mileage_golden(oracle):
         for a, b, cost, h in G[name]["from"][:2]:
             p, c = oracle.extra_mileage(xy, a, b)
             assert (int(c), fnv1a(p)) == (cost, h)
+
+
+def test_patching_golden(oracle):
+    """Oracle restatement of cx_patching (cplex_model.c:693-755, repeated while ncomp > 1) against
+    tests/golden/golden_patching.json (the unmodified reference cplex_model.c, compiled with a stub <cplex.h>)."""
+    import json
+    import os
+    from components import cycles_solution, solution_cost
+    with open(os.path.join(os.path.dirname(__file__), "golden", "golden_patching.json")) as f:
+        G = json.load(f)
+    for key, g in G.items():
+        name, seed, ncomp, local = key.rsplit("_", 3)
+        xy, _ = load_instance(name)
+        if xy.shape[0] > 1400:
+            continue                                   # the larger cases are checked on the GPU only (CPU time)
+        path, comp, nc = cycles_solution(int(seed), xy.shape[0], int(ncomp), bool(int(local)), xy)
+        cost = solution_cost(oracle, xy, path)
+        assert cost == g["start_cost"]
+        patches = 0
+        while nc > 1:
+            ok, nc, cost, a, b, d = oracle.patching(xy, path, comp, nc, cost)
+            assert ok and d > 0 and a < b
+            patches += 1
+        assert (patches, cost, fnv1a(path), fnv1a(comp)) == (g["patches"], g["cost"], g["path_hash"], g["comp_hash"]), key
+        assert oracle.is_tour(path) and len(set(comp.tolist())) == 1
+
+
+def test_patching_no_admissible_pair(oracle):
+    """Every cross pair has delta <= 0 (coincident 2-cycles): the reference would index path[-1]
+    (cplex_model.c:730-735); the restatement reports 'no patch' and changes nothing."""
+    xy = np.array([[0, 0], [10, 0], [0, 0], [10, 0]], dtype=np.float64)
+    path = np.array([1, 0, 3, 2], dtype=np.int32)
+    comp = np.array([1, 1, 2, 2], dtype=np.int32)
+    ok, nc, cost, a, b, d = oracle.patching(xy, path, comp, 2, 40.0)
+    assert not ok and nc == 2 and cost == 40.0 and path.tolist() == [1, 0, 3, 2] and comp.tolist() == [1, 1, 2, 2]

@@ -145,3 +145,24 @@ def test_extra_mileage_matches_reference(oracle, reference):
             e, p, c = reference.extra_mileage_from(a, b)
             po, co = oracle.extra_mileage(xy, a, b)
             assert c == co and np.array_equal(p, po), (name, a, b)
+
+
+@pytest.mark.parametrize("n,integer,ncomp,local,seed", [(9, True, 3, False, 1), (60, False, 20, False, 2), (300, True, 12, True, 3),
+                                                        (500, False, 150, False, 4), (900, False, 9, True, 5)])
+def test_patching_step_by_step(oracle, reference, n, integer, ncomp, local, seed):
+    """cx_patching (cplex_model.c:693-755; the reference's file compiled unchanged with a stub <cplex.h>) against
+    the restatement, patch by patch: successor array, component labels, ncomp and cost after every call."""
+    from components import cycles_solution, solution_cost
+    rng = np.random.default_rng(seed)
+    xy = _rand_instance(rng, n, integer)
+    if integer:
+        xy = np.ascontiguousarray(np.round(xy / 100.0))       # coarse lattice: many equal deltas, the tie rule decides
+    reference.set_points(xy)
+    path, comp, nc = cycles_solution(seed, n, ncomp, local, xy)
+    cost = solution_cost(oracle, xy, path)
+    p2, c2, n2, k2 = path.copy(), comp.copy(), nc, cost
+    while nc > 1:
+        ok, nc, cost, a, b, d = oracle.patching(xy, path, comp, nc, cost)
+        n2, k2 = reference.patching(p2, c2, n2, k2)
+        assert ok and nc == n2 and cost == k2 and np.array_equal(path, p2) and np.array_equal(comp, c2), (a, b, d)
+    assert oracle.is_tour(path)

@@ -18,9 +18,10 @@ from .build import LIB, build
 EUC_REF, CEIL_2D, ATT, GEO = 0, 1, 2, 3
 SCAN_AUTO, SCAN_FULL, SCAN_PRUNED = 0, 1, 2
 WT_BY_NAME = {"EUC_2D": EUC_REF, "EUC_REF": EUC_REF, "CEIL_2D": CEIL_2D, "ATT": ATT, "GEO": GEO}
-ERROR_NAMES = {0: "T_OK", 1: "CANCELLED", 3: "INVALID_ARGUMENT", 4: "DEADLINE_EXCEEDED", 8: "RESOURCE_EXHAUSTED",
+ERROR_NAMES = {0: "T_OK", 1: "CANCELLED", 3: "INVALID_ARGUMENT", 4: "DEADLINE_EXCEEDED", 8: "RESOURCE_EXHAUSTED", 9: "FAILED_PRECONDITION",
                11: "OUT_OF_RANGE", 12: "UNIMPLEMENTED", 13: "INTERNAL", 14: "UNAVAILABLE"}
 OK, DEADLINE_EXCEEDED, INVALID_ARGUMENT, OUT_OF_RANGE, UNAVAILABLE = 0, 4, 3, 11, 14
+FAILED_PRECONDITION = 9
 
 EXPORTS = [
     "tspcuda_device_count", "tspcuda_last_error", "tspcuda_version", "tspcuda_create", "tspcuda_destroy",
@@ -30,7 +31,7 @@ EXPORTS = [
     "tspcuda_multistart_two_opt", "tspcuda_pipe_rate", "tspcuda_selfcheck_sqrt", "tspcuda_timer_start",
     "tspcuda_timer_stop", "tspcuda_flush_l2", "tspcuda_set_scan_mode", "tspcuda_tabu_search",
     "tspcuda_extra_mileage", "tspcuda_mx_create", "tspcuda_mx_destroy", "tspcuda_mx_get_stats", "tspcuda_mx_nn", "tspcuda_mx_two_opt",
-    "tspcuda_mx_two_opt_once",
+    "tspcuda_mx_two_opt_once", "tspcuda_patching",
 ]
 
 
@@ -100,6 +101,7 @@ def lib():
     L.tspcuda_flush_l2.argtypes = [_vp]
     L.tspcuda_set_scan_mode.argtypes = [_vp, C.c_int]
     L.tspcuda_extra_mileage.argtypes = [_vp, C.c_int, C.c_int, _ip, _dp, _ip, _ip]
+    L.tspcuda_patching.argtypes = [_vp, _ip, _ip, _ip, _dp, C.c_int, C.POINTER(Move), C.c_int64, _ip]
     L.tspcuda_mx_create.argtypes = [C.POINTER(_vp), _dp, C.c_int, C.c_int]
     L.tspcuda_mx_destroy.argtypes = [_vp]
     L.tspcuda_mx_destroy.restype = None
@@ -243,6 +245,18 @@ class Instance:
         cost, a, b = C.c_double(0), C.c_int(-1), C.c_int(-1)
         _chk(lib().tspcuda_extra_mileage(self._h, node_a, node_b, _ipc(path), C.byref(cost), C.byref(a), C.byref(b)))
         return path, cost.value, (a.value, b.value)
+
+    def patching(self, path, comp, ncomp, cost, max_patches=-1, allow=()):
+        """cx_patching (cplex_model.c:693-755); max_patches < 0: the caller's while (ncomp > 1) loop (:205-212).
+        Returns (code, path, comp, ncomp, cost, [(a, b, delta) per patch])."""
+        path = np.ascontiguousarray(path, dtype=np.int32).copy()
+        comp = np.ascontiguousarray(comp, dtype=np.int32).copy()
+        nc, c, done = C.c_int(ncomp), C.c_double(cost), C.c_int(0)
+        cap = max(1, ncomp)
+        log = (Move * cap)()
+        code = _chk(lib().tspcuda_patching(self._h, _ipc(path), _ipc(comp), C.byref(nc), C.byref(c), max_patches, log, cap,
+                                           C.byref(done)), allow=allow)
+        return code, path, comp, nc.value, c.value, [(log[k].a, log[k].b, log[k].delta) for k in range(done.value)]
 
     # -- device-resident tour ----------------------------------------------------------------------
     def tour_upload(self, path):

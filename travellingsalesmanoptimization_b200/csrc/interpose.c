@@ -23,6 +23,8 @@
  *                       calls the interposed tabu_best_move once per iteration)
  *   h_extramileage_util heuristics.c:290   and   h_ExtraMileage  heuristics.c:156  (the
  *                       latter only so that the EM_MAX search also works without a host matrix, n > 46340)
+ *   cx_patching         cplex_model.c:693  (the patching heuristic of the Benders loop; reached
+ *                       only from CPLEX-backed code, i.e. by users who build the reference with CPLEX)
  *   tsp_read_input      tsp.c:527  (EXTENSION: same grammar, additionally accepts CEIL_2D, ATT and GEO files)
  * ref_reverse_path (refinment.c:95) keeps the reference's definition: once ref_2opt_once and
  * tabu_best_move run on the device nothing on this path calls it.
@@ -46,11 +48,12 @@ static tspcuda_ctx *g_ctx = NULL;
 static int g_weight_type = TSPCUDA_EUC_REF;     /* set by the interposed tsp_read_input */
 static point *g_points = NULL;
 static int g_n = -1;
-static long g_calls[11];
-enum { C_COSTS, C_NN, C_2OPT, C_2OPT_ONCE, C_TABU, C_ALLNN, C_MULTI, C_TABULOOP, C_READ, C_EMUTIL, C_EM };
+#define N_CALLS 12
+static long g_calls[N_CALLS];
+enum { C_COSTS, C_NN, C_2OPT, C_2OPT_ONCE, C_TABU, C_ALLNN, C_MULTI, C_TABULOOP, C_READ, C_EMUTIL, C_EM, C_PATCH };
 static const char *g_names[] = {"tsp_compute_costs", "h_greedyutil", "ref_2opt", "ref_2opt_once",
                                 "tabu_best_move", "h_Greedy_iterative", "h_greedy_2opt", "mh_TabuSearch", "tsp_read_input",
-                                "h_extramileage_util", "h_ExtraMileage"};
+                                "h_extramileage_util", "h_ExtraMileage", "cx_patching"};
 
 /* Exit hook.  Prints the call counters (TSPCUDA_STATS=1), flushes stdio and leaves with _exit().
  * The last step shields the process from a latent heap overflow in the UNCHANGED driver:
@@ -64,7 +67,7 @@ static void on_exit_hook(int status, void *arg) {
     const char *s = getenv("TSPCUDA_STATS");
     if (s && *s == '1') {
         fprintf(stderr, "[tspcuda] interposed calls:");
-        for (int i = 0; i < 11; i++) fprintf(stderr, " %s=%ld", g_names[i], g_calls[i]);
+        for (int i = 0; i < N_CALLS; i++) fprintf(stderr, " %s=%ld", g_names[i], g_calls[i]);
         fprintf(stderr, "\n");
     }
     const char *f = getenv("TSPCUDA_FAST_EXIT");
@@ -553,4 +556,21 @@ ERROR_CODE h_ExtraMileage(void) {
     log_debug("max edge : (%d, %d)", nodeA, nodeB);
     tsp_update_best_solution(&solution);                            /* :205 */
     return T_OK;                                                     /* the reference leaks solution.path here too (:207) */
+}
+
+/* ---- cx_patching, cplex_model.c:693-755 ------------------------------------------
+ * One patch of a multi-cycle solution.  The prototype lives in cplex_model.h, which needs <cplex.h>; the
+ * signature is restated here over the reference's own tsp_solution (utils.h:42-47).  The reference returns
+ * nothing; it has undefined behaviour (path[-1]) when no pair of nodes in different components has
+ * delta > 0, and its caller loops `while (ncomp > 1)` (:205-212): that case, like any device failure, is
+ * fatal here (tsp_handlefatal) rather than an endless loop or a silent host computation. */
+void cx_patching(tsp_solution *solution) {
+    g_calls[C_PATCH]++;
+    tspcuda_ctx *c = ctx_for_instance();
+    int rc = c ? tspcuda_patching(c, solution->path, solution->comp, &solution->ncomp, &solution->cost, 1, NULL, 0, NULL)
+               : TSPCUDA_INTERNAL;
+    if (rc != TSPCUDA_OK) {
+        log_fatal("code %d : libtspcuda: %s", rc, c ? tspcuda_last_error() : "no device context");
+        tsp_handlefatal();
+    }
 }

@@ -17,6 +17,7 @@
 #include "pruned.cuh"
 #include "matrix.cuh"
 #include "mileage.cuh"
+#include "patching.cuh"
 
 using namespace tspcuda;
 
@@ -1219,6 +1220,93 @@ extern "C" int tspcuda_extra_mileage(tspcuda_ctx *c, int node_a, int node_b, int
     if (cost_out) *cost_out = (double)h_cost;
     if (node_a_out) *node_a_out = h_pair[0];
     if (node_b_out) *node_b_out = h_pair[1];
+    return TSPCUDA_OK;
+}
+
+// ---- patching (cplex_model.c:693-755 cx_patching, the Benders loop's while (ncomp > 1), :205-212) -----
+extern "C" int tspcuda_patching(tspcuda_ctx *c, int *path, int *comp, int *ncomp_inout, double *cost_inout,
+                                int max_patches, tspcuda_move *log, int64_t log_cap, int *patches_out) {
+    int e = use(c);
+    if (e) return e;
+    const int n = c->n;
+    if (!path || !comp || !ncomp_inout) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
+    if (patches_out) *patches_out = 0;
+    // the successor array must be a permutation whose cycles carry one label each, distinct between cycles
+    // (cx_build_sol's output); the relabelling below relies on it
+    {
+        std::vector<char> seen(n, 0);
+        std::vector<int> labels;
+        int cycles = 0;
+        for (int v = 0; v < n; ++v) {
+            if (seen[v]) continue;
+            int len = 0;
+            for (int u = v; !seen[u]; u = path[u]) {
+                seen[u] = 1;
+                ++len;
+                if (comp[u] != comp[v]) return fail(TSPCUDA_INVALID_ARGUMENT, "comp[] is not constant on the cycle of node %d", v);
+                if (path[u] < 0 || path[u] >= n) return fail(TSPCUDA_INVALID_ARGUMENT, "successor of node %d out of range", u);
+                if (seen[path[u]] && path[u] != v) return fail(TSPCUDA_INVALID_ARGUMENT, "path[] is not a permutation (node %d)", u);
+            }
+            if (len < 2) return fail(TSPCUDA_INVALID_ARGUMENT, "node %d is its own successor", v);
+            labels.push_back(comp[v]);
+            ++cycles;
+        }
+        std::sort(labels.begin(), labels.end());
+        if (std::adjacent_find(labels.begin(), labels.end()) != labels.end())
+            return fail(TSPCUDA_INVALID_ARGUMENT, "two cycles share a component label");
+        if (cycles != *ncomp_inout) return fail(TSPCUDA_INVALID_ARGUMENT, "ncomp = %d but path[] has %d cycles", *ncomp_inout, cycles);
+    }
+    int todo = *ncomp_inout - 1;
+    if (max_patches >= 0) todo = std::min(todo, max_patches);
+    if (todo <= 0) return TSPCUDA_OK;
+    DevBuf dpath, dcomp, sxy, dn, key, cost, info, dlog;
+    CK(cudaMalloc(&dpath.p, sizeof(int) * n)); CK(cudaMalloc(&dcomp.p, sizeof(int) * n));
+    CK(cudaMalloc(&sxy.p, sizeof(double2) * n)); CK(cudaMalloc(&dn.p, sizeof(int) * n));
+    CK(cudaMalloc(&key.p, sizeof(unsigned long long))); CK(cudaMalloc(&cost.p, sizeof(long long)));
+    CK(cudaMalloc(&info.p, sizeof(int) * 2)); CK(cudaMalloc(&dlog.p, sizeof(int) * 3 * (size_t)todo));
+    CK(cudaMemcpyAsync(dpath.p, path, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemcpyAsync(dcomp.p, comp, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaMemsetAsync(key.p, 0xFF, sizeof(unsigned long long), c->stream));
+    CK(cudaMemsetAsync(cost.p, 0, sizeof(long long), c->stream));
+    CK(cudaMemsetAsync(info.p, 0, sizeof(int) * 2, c->stream));
+    c->stats.h2d_bytes += 2 * (int64_t)sizeof(int) * n;
+    PatchState S;
+    S.path = dpath.as<int>(); S.comp = dcomp.as<int>(); S.sxy = sxy.as<double2>(); S.dn = dn.as<int>();
+    S.key = key.as<unsigned long long>(); S.cost = cost.as<long long>(); S.info = info.as<int>();
+    S.log = dlog.as<int>(); S.log_cap = todo;
+    const int ntiles = (n + PATCH_TILE - 1) / PATCH_TILE;
+    const int slices = std::max(1, std::min(ntiles, 4 * c->num_sms / ntiles));
+    CK(cudaEventRecord(c->ev0, c->stream));
+    DISPATCH_METRIC(c->metric, (patch_prep_kernel<M><<<grid_for(n, c->num_sms * 4), 256, 0, c->stream>>>(c->d_xy, n, S)));
+    for (int k = 0; k < todo; ++k) {
+        DISPATCH_METRIC(c->metric, (patch_scan_kernel<M><<<dim3(ntiles, slices), PATCH_TILE, 0, c->stream>>>(c->d_xy, n, S)));
+        DISPATCH_METRIC(c->metric, (patch_apply_kernel<M><<<1, 1024, 0, c->stream>>>(c->d_xy, n, S)));
+    }
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(c->ev1, c->stream));
+    c->stats.kernel_launches += 1 + 2 * (int64_t)todo;
+    int h_info[2] = {0, 0};
+    std::vector<int> h_log(3 * (size_t)todo);
+    CK(cudaMemcpyAsync(h_info, info.p, sizeof(h_info), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(h_log.data(), dlog.p, sizeof(int) * h_log.size(), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(path, dpath.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(comp, dcomp.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+    c->stats.last_kernel_ms = ms;
+    c->stats.d2h_bytes += 2 * (int64_t)sizeof(int) * n + (int64_t)sizeof(int) * h_log.size() + 8;
+    c->tour_loaded = false;
+    const int done = h_info[0];
+    for (int k = 0; k < done; ++k) {
+        if (cost_inout) *cost_inout += (double)h_log[3 * k + 2];          // cplex_model.c:738, patch by patch
+        if (log && k < log_cap) { log[k].a = h_log[3 * k]; log[k].b = h_log[3 * k + 1]; log[k].delta = h_log[3 * k + 2]; log[k].reserved = 0; }
+    }
+    *ncomp_inout -= done;
+    if (patches_out) *patches_out = done;
+    if (h_info[1])
+        return fail(TSPCUDA_FAILED_PRECONDITION, "no pair of nodes in different components has delta > 0 after %d patches "
+                    "(the reference indexes path[-1] here, cplex_model.c:730-735)", done);
     return TSPCUDA_OK;
 }
 
