@@ -209,6 +209,25 @@ int tspcuda_mx_two_opt(tspcuda_mx *mx, int *path, double *cost_out, int64_t max_
                        int64_t *moves_out, tspcuda_move_f *log, int64_t log_cap);
 int tspcuda_mx_two_opt_once(tspcuda_mx *mx, int *path, double *cost_inout, double *best_delta_out);
 
+/* ---- multi-start work over the GPUs of one box, from inside the library ------------------ */
+/* One worker thread and one context per GPU; starts are sharded block-cyclically (GPU g of G takes the caller's
+ * starts g, g+G, ...), no data-path collective; the incumbent is merged by ONE ncclAllReduce(min) of the 64-bit key
+ * cost << 20 | start node (= the reference's strict-'<' rule in ascending start order, tsp.c:671, heuristics.c:58/82:
+ * the lowest start wins cost ties) and ONE ncclBroadcast of the winner's successor array.  NCCL is loaded at run time
+ * (libnccl.so.2); without it, or with fewer visible GPUs than asked for, the calls return TSPCUDA_UNAVAILABLE.
+ * ndev <= 0: every visible GPU; devices == NULL: 0..ndev-1.  With ndev == 1 no NCCL is needed or loaded.
+ * This is what the interposer uses for h_Greedy_iterative / h_greedy_2opt when TSPCUDA_GPUS > 1. */
+typedef struct tspcuda_mgpu tspcuda_mgpu;
+int tspcuda_mgpu_create(tspcuda_mgpu **out, const double *xy, int n, int weight_type, int ndev, const int *devices);
+void tspcuda_mgpu_destroy(tspcuda_mgpu *m);
+int tspcuda_mgpu_ndev(const tspcuda_mgpu *m);
+/* two_opt = 0: all-start nearest neighbour (h_Greedy_iterative, heuristics.c:34-72); 1: NN + 2-opt per start
+ * (h_greedy_2opt, :74-116).  Starts first_start + k*stride, k in [0,nstarts).  Same results as the single-GPU calls
+ * tspcuda_nn_multi / tspcuda_multistart_two_opt.  *compute_ms_out / *reduce_ms_out (may be NULL): wall time of the
+ * slowest shard and of the incumbent reduction (max over GPUs). */
+int tspcuda_mgpu_multistart(tspcuda_mgpu *m, int two_opt, int first_start, int nstarts, int stride, int *best_start_out,
+                            int *best_path_out, double *best_cost_out, double *compute_ms_out, double *reduce_ms_out);
+
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* CUDA-event bracket on the stream every kernel of this context is launched on (torch.cuda.Event
  * only sees torch's own stream): start records an event, stop records another, synchronises and

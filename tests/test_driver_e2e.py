@@ -235,6 +235,23 @@ def test_patching_through_the_reference_objects(workdir, reference):
 
 
 @pytest.mark.gpu
+def test_cli_multi_gpu(workdir):
+    """TSPCUDA_GPUS: the whole-loop overrides shard their starts over the GPUs of the box (NCCL incumbent
+    reduction inside libtspcuda); the Cost line must not change.  More GPUs than visible: loud failure."""
+    import travellingsalesmanoptimization_b200 as T
+    r = run_cli(TSP_GPU, workdir, ["-f", "berlin52.tsp", "-q", "-alg", "2OPT_GREEDY"], {"TSPCUDA_GPUS": "99"}, check=False)
+    assert "Cost:" not in r.stdout or r.returncode != 0
+    g = T.device_count()
+    if g < 2:
+        pytest.skip("needs 2 GPUs")
+    for alg in ("GREEDY_ITER", "2OPT_GREEDY"):
+        one = run_cli(TSP_GPU, workdir, ["-f", "rl1304.tsp", "-q", "-alg", alg])
+        many = run_cli(TSP_GPU, workdir, ["-f", "rl1304.tsp", "-q", "-alg", alg], {"TSPCUDA_GPUS": "all"})
+        assert one.stdout == many.stdout and "Cost:" in one.stdout
+        assert calls(many.stderr)["gpus"] == g and calls(one.stderr)["gpus"] == 1
+
+
+@pytest.mark.gpu
 def test_pla85900_opens_through_the_unchanged_driver(workdir):
     """The headline instance through the drop-in CLI: CEIL_2D header (the reference reader stops there,
     tsp.c:576-583), n > 46340 (no host matrix: the reference's int n*n overflows, tsp.c:614).

@@ -956,3 +956,39 @@ def test_patching_edge_cases(tsp):
             with pytest.raises(tsp.TspCudaError) as ei:
                 I.patching(bad_path, bad_comp, bad_nc, 0.0)
             assert ei.value.code == tsp.INVALID_ARGUMENT
+
+
+# ---- multi-GPU inside the library (tspcuda_mgpu: worker thread + context per GPU, NCCL incumbent reduction) ------
+def _ndev_params(tsp_mod=None):
+    return [1, 2, 4, 8]
+
+
+@pytest.mark.parametrize("ndev", _ndev_params())
+def test_mgpu_multistart_matches_single_gpu(tsp, ndev):
+    """Sharding the starts over the GPUs of the box must not change the incumbent: same (cost, start, tour) as the
+    single-GPU calls, including cost ties (lowest start wins, tsp.c:671) and shards that own no start."""
+    if ndev > tsp.device_count():
+        pytest.skip("needs %d GPUs" % ndev)
+    for name, first, nstarts, stride in (("berlin52", 0, 52, 1), ("berlin52", 3, 5, 7), ("berlin52", 10, 1, 1), ("pr2392", 0, 400, 5)):
+        xy, _ = load_instance(name)
+        with tsp.Instance(xy) as I, tsp.MultiGpuInstance(xy, ndev=ndev) as M:
+            assert M.ndev == ndev
+            bs, bp, bc, *_ = I.multistart_two_opt(first, nstarts, stride)
+            ms, mp, mc, t_c, t_r = M.multistart(True, first, nstarts, stride)
+            assert (ms, mc) == (bs, bc) and np.array_equal(mp, bp), (name, first, nstarts, stride)
+            bs, bp, bc, _ = I.nn_multi(first, nstarts, stride)
+            ms, mp, mc, t_c, t_r = M.multistart(False, first, nstarts, stride)
+            assert (ms, mc) == (bs, bc) and np.array_equal(mp, bp), (name, first, nstarts, stride)
+    # lattice instance: many starts reach the same cost, the lowest start must win on every GPU count
+    xy = _rand_xy(11, 64, True, lo=0, hi=6)
+    with tsp.Instance(xy) as I, tsp.MultiGpuInstance(xy, ndev=ndev) as M:
+        bs, bp, bc, *_ = I.multistart_two_opt(0, 64, 1)
+        ms, mp, mc, *_ = M.multistart(True, 0, 64, 1)
+        assert (ms, mc) == (bs, bc) and np.array_equal(mp, bp)
+
+
+def test_mgpu_more_gpus_than_visible_fails_loudly(tsp):
+    xy, _ = load_instance("berlin52")
+    with pytest.raises(tsp.TspCudaError) as ei:
+        tsp.MultiGpuInstance(xy, ndev=tsp.device_count() + 1)
+    assert ei.value.code == tsp.UNAVAILABLE

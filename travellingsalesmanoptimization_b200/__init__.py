@@ -31,7 +31,8 @@ EXPORTS = [
     "tspcuda_multistart_two_opt", "tspcuda_pipe_rate", "tspcuda_selfcheck_sqrt", "tspcuda_timer_start",
     "tspcuda_timer_stop", "tspcuda_flush_l2", "tspcuda_set_scan_mode", "tspcuda_tabu_search",
     "tspcuda_extra_mileage", "tspcuda_mx_create", "tspcuda_mx_destroy", "tspcuda_mx_get_stats", "tspcuda_mx_nn", "tspcuda_mx_two_opt",
-    "tspcuda_mx_two_opt_once", "tspcuda_patching",
+    "tspcuda_mx_two_opt_once", "tspcuda_patching", "tspcuda_mgpu_create", "tspcuda_mgpu_destroy", "tspcuda_mgpu_ndev",
+    "tspcuda_mgpu_multistart",
 ]
 
 
@@ -102,6 +103,11 @@ def lib():
     L.tspcuda_set_scan_mode.argtypes = [_vp, C.c_int]
     L.tspcuda_extra_mileage.argtypes = [_vp, C.c_int, C.c_int, _ip, _dp, _ip, _ip]
     L.tspcuda_patching.argtypes = [_vp, _ip, _ip, _ip, _dp, C.c_int, C.POINTER(Move), C.c_int64, _ip]
+    L.tspcuda_mgpu_create.argtypes = [C.POINTER(_vp), _dp, C.c_int, C.c_int, C.c_int, _ip]
+    L.tspcuda_mgpu_destroy.argtypes = [_vp]
+    L.tspcuda_mgpu_destroy.restype = None
+    L.tspcuda_mgpu_ndev.argtypes = [_vp]
+    L.tspcuda_mgpu_multistart.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
     L.tspcuda_mx_create.argtypes = [C.POINTER(_vp), _dp, C.c_int, C.c_int]
     L.tspcuda_mx_destroy.argtypes = [_vp]
     L.tspcuda_mx_destroy.restype = None
@@ -377,3 +383,43 @@ class MatrixInstance:
         code, p, c, ln = self.nn(self.n - 1)
         code, moves, p, c, _ = self.two_opt(p)
         return p, c
+
+
+class MultiGpuInstance:
+    """tspcuda_mgpu: one context per GPU of this box inside ONE process (what the drop-in CLI uses with
+    TSPCUDA_GPUS > 1); multi-start work sharded block-cyclically, NCCL all-reduce(min) + broadcast of the best tour."""
+
+    def __init__(self, xy, weight_type=EUC_REF, ndev=0, devices=None):
+        self.xy = np.ascontiguousarray(xy, dtype=np.float64)
+        self.n = self.xy.shape[0]
+        self._h = _vp()
+        dev = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        _chk(lib().tspcuda_mgpu_create(C.byref(self._h), _dpc(self.xy), self.n, weight_type, ndev,
+                                       None if dev is None else _ipc(dev)))
+        self.ndev = lib().tspcuda_mgpu_ndev(self._h)
+
+    def close(self):
+        if self._h:
+            lib().tspcuda_mgpu_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def multistart(self, two_opt=True, first_start=0, nstarts=None, stride=1):
+        """(best_start, best_path, best_cost, compute_ms, reduce_ms) over starts first_start + k*stride."""
+        nstarts = self.n if nstarts is None else nstarts
+        path = np.zeros(self.n, dtype=np.int32)
+        bs, bc, cm, rm = C.c_int(-1), C.c_double(0), C.c_double(0), C.c_double(0)
+        _chk(lib().tspcuda_mgpu_multistart(self._h, 1 if two_opt else 0, first_start, nstarts, stride, C.byref(bs), _ipc(path),
+                                           C.byref(bc), C.byref(cm), C.byref(rm)))
+        return bs.value, path, bc.value, cm.value, rm.value

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtspcuda.so")
 SOURCES = [os.path.join(CSRC, "tspcuda.cu")]
-DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("kernels.cuh", "metric.cuh", "pruned.cuh", "matrix.cuh", "mileage.cuh", "patching.cuh")] + [
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in ("kernels.cuh", "metric.cuh", "pruned.cuh", "matrix.cuh", "mileage.cuh", "patching.cuh", "mgpu.cuh")] + [
     os.path.join(HERE, "..", "include", "tspcuda.h")]
 
 NVCC_FLAGS = [

@@ -45,6 +45,9 @@
 #include "tspcuda.h"
 
 static tspcuda_ctx *g_ctx = NULL;
+static tspcuda_mgpu *g_mgpu = NULL;             /* TSPCUDA_GPUS > 1: one context per GPU for the whole-loop overrides */
+static point *g_mgpu_points = NULL;
+static int g_mgpu_n = -1;
 static int g_weight_type = TSPCUDA_EUC_REF;     /* set by the interposed tsp_read_input */
 static point *g_points = NULL;
 static int g_n = -1;
@@ -68,6 +71,7 @@ static void on_exit_hook(int status, void *arg) {
     if (s && *s == '1') {
         fprintf(stderr, "[tspcuda] interposed calls:");
         for (int i = 0; i < N_CALLS; i++) fprintf(stderr, " %s=%ld", g_names[i], g_calls[i]);
+        fprintf(stderr, " gpus=%d", g_mgpu ? tspcuda_mgpu_ndev(g_mgpu) : 1);
         fprintf(stderr, "\n");
     }
     const char *f = getenv("TSPCUDA_FAST_EXIT");
@@ -115,6 +119,43 @@ static tspcuda_ctx *ctx_for_instance(void) {
     g_points = tsp_inst.points;
     g_n = tsp_inst.nnodes;
     return g_ctx;
+}
+
+/* TSPCUDA_GPUS=N (or "all"): the multi-start whole-loop overrides (h_Greedy_iterative, h_greedy_2opt) shard their
+ * starts over N GPUs of this box (tspcuda_mgpu: NCCL all-reduce(min) of (cost, start) + broadcast of the best tour).
+ * Default 1.  Asking for more GPUs than are visible is an error, never a silent single-GPU run. */
+static int gpus_requested(void) {
+    const char *g = getenv("TSPCUDA_GPUS");
+    if (!g || !*g) return 1;
+    if (strcmp(g, "all") == 0) return tspcuda_device_count();
+    return atoi(g) > 0 ? atoi(g) : 1;
+}
+
+static tspcuda_mgpu *mgpu_for_instance(void) {
+    if (g_mgpu && g_mgpu_points == tsp_inst.points && g_mgpu_n == tsp_inst.nnodes) return g_mgpu;
+    if (g_mgpu) { tspcuda_mgpu_destroy(g_mgpu); g_mgpu = NULL; }
+    int e = tspcuda_mgpu_create(&g_mgpu, (const double *)tsp_inst.points, tsp_inst.nnodes, g_weight_type, gpus_requested(), NULL);
+    if (e != TSPCUDA_OK) {
+        log_error("code %d : libtspcuda: %s", e, tspcuda_last_error());
+        g_mgpu = NULL;
+        return NULL;
+    }
+    g_mgpu_points = tsp_inst.points;
+    g_mgpu_n = tsp_inst.nnodes;
+    return g_mgpu;
+}
+
+/* all starts 0..n-1 of the current instance, on one GPU or sharded over TSPCUDA_GPUS of them */
+static int all_starts(int two_opt, int *best_start, int *path, double *cost) {
+    if (gpus_requested() > 1) {
+        tspcuda_mgpu *m = mgpu_for_instance();
+        if (!m) return TSPCUDA_INTERNAL;
+        return tspcuda_mgpu_multistart(m, two_opt, 0, tsp_inst.nnodes, 1, best_start, path, cost, NULL, NULL);
+    }
+    tspcuda_ctx *c = ctx_for_instance();
+    if (!c) return TSPCUDA_INTERNAL;
+    return two_opt ? tspcuda_multistart_two_opt(c, 0, tsp_inst.nnodes, 1, NULL, NULL, NULL, best_start, path, cost)
+                   : tspcuda_nn_multi(c, 0, tsp_inst.nnodes, 1, NULL, best_start, path, cost);
 }
 
 static double time_left(void) {          /* -1: no limit; otherwise seconds (may be <= 0) */
@@ -360,12 +401,10 @@ ERROR_CODE h_Greedy_iterative(void) {
         return ((void_fn)dlsym(RTLD_NEXT, "h_Greedy_iterative"))();      /* the reference loop over the interposed helpers */
     g_calls[C_ALLNN]++;
     log_info("running All Nearest Neighbour");
-    tspcuda_ctx *c = ctx_for_instance();
-    if (!c) return INTERNAL;
     tsp_solution solution;
     tsp_init_solution(tsp_inst.nnodes, &solution);
     int best_start = -1;
-    int rc = tspcuda_nn_multi(c, 0, tsp_inst.nnodes, 1, NULL, &best_start, solution.path, &solution.cost);
+    int rc = all_starts(0, &best_start, solution.path, &solution.cost);
     if (rc != TSPCUDA_OK) {
         log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
         utils_safe_free(solution.path);
@@ -389,12 +428,10 @@ ERROR_CODE h_greedy_2opt(void) {
         return ((void_fn)dlsym(RTLD_NEXT, "h_greedy_2opt"))();
     g_calls[C_MULTI]++;
     log_info("running All Nearest Neighbour + 2OPT");
-    tspcuda_ctx *c = ctx_for_instance();
-    if (!c) return INTERNAL;
     tsp_solution solution;
     tsp_init_solution(tsp_inst.nnodes, &solution);
     int best_start = -1;
-    int rc = tspcuda_multistart_two_opt(c, 0, tsp_inst.nnodes, 1, NULL, NULL, NULL, &best_start, solution.path, &solution.cost);
+    int rc = all_starts(1, &best_start, solution.path, &solution.cost);
     if (rc != TSPCUDA_OK) {
         log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
         utils_safe_free(solution.path);

@@ -1565,3 +1565,6 @@ extern "C" int tspcuda_mx_two_opt_once(tspcuda_mx *m, int *path, double *cost_in
     }
     return TSPCUDA_OK;
 }
+
+// ===== multi-GPU multi-start inside the library (one worker thread + context per GPU, NCCL incumbent reduction) =====
+#include "mgpu.cuh"
