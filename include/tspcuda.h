@@ -20,6 +20,7 @@
  *   tspcuda_multistart_two_opt    h_greedy_2opt loop           algorithms/heuristics.c:74-116
  *   tspcuda_extra_mileage         h_ExtraMileage / h_extramileage_util   algorithms/heuristics.c:156-210, :290-367
  *   tspcuda_mx_nn / _two_opt      h_greedyutil / ref_2opt on a caller's matrix (h_Greedy_2opt_mod_costs, heuristics.c:118-149)
+ *   tspcuda_vns_search            mh_VNS loop (ref_2opt + vns_kick)              algorithms/metaheuristic.c:277-321, :344-409
  *   tspcuda_patching              cx_patching (+ its while (ncomp > 1) loop)   algorithms/cplex_model.c:693-755, :205-212
  *
  * Tours cross the boundary exactly as the reference stores them: a successor array int path[n],
@@ -142,6 +143,22 @@ int tspcuda_tabu_move(tspcuda_ctx *ctx, int *path, double *cost_inout, int *tabu
 int tspcuda_tabu_search(tspcuda_ctx *ctx, int *path, double *cost_inout, int *tabu_list, const int *tenures,
                         int first_iter, int n_iters, double incumbent_cost, double *cost_trace_out,
                         int *best_path_out, double *best_cost_out, int *best_iter_out);
+
+/* n_iters iterations of the loop of mh_VNS (metaheuristic.c:277-321) with the tour resident on the device:
+ * iteration i = ref_2opt to the local optimum (:288), incumbent test on a strictly smaller cost (:296-300),
+ * cost_trace_out[i] = that cost (the results/VNSResults.dat column, :303), then rand() % 9 - 2 kicks (:306-316;
+ * vns_kick :344-409 = three random positions with the reference's rejection test, segment exchange of tabu_make_move
+ * case 7).  The kick runs on the host on the tour order and draws from the PROCESS's rand() stream, in the reference's
+ * order -- the caller seeds it (or does not: the reference never seeds it on file instances); per iteration the tour
+ * order travels device -> host and back (2 x 4n bytes), nothing else.  time_limit_s < 0: none; otherwise seconds from
+ * the call, tested at the top of every iteration and inside the descents (TSPCUDA_DEADLINE_EXCEEDED).
+ * path: in = start tour, out = the tour after the last kicks (what the reference's `solution` holds at the end);
+ * *cost_inout: cost after the last descent.  *best_cost_inout: in = the cost to beat (mh_VNS: the start cost, :270),
+ * out = the best cost seen; best_path_out / *best_iter_out: that tour and its iteration (-1: no iteration improved
+ * on the input; best_path_out is then untouched).  *iters_done_out: iterations completed. */
+int tspcuda_vns_search(tspcuda_ctx *ctx, int *path, double *cost_inout, int n_iters, double time_limit_s,
+                       double *cost_trace_out, int *best_path_out, double *best_cost_inout, int *best_iter_out,
+                       int *iters_done_out);
 
 /* How 2-opt descents scan the neighbourhood.  FULL evaluates all n(n-1)/2 pairs per scan, as the
  * reference does (refinment.c:49-69).  PRUNED evaluates only the pairs that can improve the tour

@@ -557,9 +557,13 @@ void orc_tabu_linear_step(int *tenure, int min_tenure, int max_tenure, int *incr
 }
 
 /* metaheuristic.c:344-409 vns_kick + :490-500 tabu_make_move case 7, driven by glibc rand().
- * Restated including the position/node-id mix-up of the rejection test (:372); the out-of-bounds
- * reads tour[-1] / tour[n] of the reference are replaced by a value that can never match (they
- * read heap bytes next to a calloc'd block, which is unspecified). */
+ * Restated including the position/node-id mix-up of the rejection test (:372).  The reference reads
+ * tour[-1] and tour[n] out of bounds there (indexes[j] = 0 resp. n-1).  Under glibc both are 0 in
+ * practice -- tour[-1] is the upper half of the chunk's size field, tour[n] lies in the zero-filled
+ * slack of the calloc'd chunk unless 4n fills it exactly (n = 2 mod 4: the next chunk's size field,
+ * heap dependent) -- so 0 is what is restated: after index n-1 was accepted, a draw of 0 is rejected.
+ * Checked against the reference objects on small n, where the case is frequent
+ * (tests/test_oracle_vs_reference.py::test_vns_kick_small_n). */
 void orc_vns_kick(int n, int *path) {
     int *tour = (int *)malloc((size_t)n * sizeof(int));
     int node = 0;
@@ -571,7 +575,7 @@ void orc_vns_kick(int n, int *path) {
             r = rand() % n;
             for (int j = 0; j < i; j++) {
                 int lo = idxs[j] - 1, hi = idxs[j] + 1;
-                int tlo = (lo >= 0) ? tour[lo] : -2, thi = (hi < n) ? tour[hi] : -2;
+                int tlo = (lo >= 0) ? tour[lo] : 0, thi = (hi < n) ? tour[hi] : 0;
                 if (r == idxs[j] || r == tlo || r == thi) { r = -1; break; }
             }
         } while (r == -1);

@@ -1,0 +1,3 @@
+set -x
+python -m pytest tests -x -q -m gpu -k "vns or VNS or berlin52_cli or random_instances" 2>&1 | tail -15
+python scripts/config5_time.py 200 2>&1 | tee gpurun_out/config5_time.log

@@ -45,3 +45,19 @@ for name in ("d15112", "rand20000"):
             mv_total += m
         t_vns = time.perf_counter() - t0; s3 = I.stats()
         print("%-9s VNS %d iterations: %.3f s (%d moves, %d scans, %d pruned; kernels %.3f s)" % (name, min(K, 200), t_vns, mv_total, s3["scans"], s3["pruned_scans"], (s3["scan_kernel_ms"] + s3["pruned_kernel_ms"]) * 1e-3), flush=True)
+        # the loop of mh_VNS itself (descent, then rand() % 9 - 2 kicks): per-call path (host successor arrays in and out of
+        # every ref_2opt, the reference's kick on the host) against the device-resident loop (tspcuda_vns_search)
+        libc = ctypes.CDLL(None)
+        KV = min(K, 200)
+        libc.srand(1); pa = p.copy(); I.reset_stats(); t0 = time.perf_counter()
+        for k in range(KV):
+            code, m, pa, ca, _ = I.two_opt(pa)
+            for _ in range(libc.rand() % 9 - 2):
+                O.vns_kick(pa)
+        t_call = time.perf_counter() - t0
+        libc.srand(1); I.reset_stats(); t0 = time.perf_counter()
+        code, pb, cb, trace, bi, bp, bc, done = I.vns_search(p, KV, c)
+        t_loop = time.perf_counter() - t0; s4 = I.stats()
+        assert np.array_equal(pa, pb) and ca == cb and done == KV
+        print("%-9s mh_VNS loop %d iterations: per-call %.3f s  device-resident %.3f s (kernels %.3f s)  best %s" % (
+            name, KV, t_call, t_loop, (s4["scan_kernel_ms"] + s4["pruned_kernel_ms"]) * 1e-3, bc), flush=True)

@@ -93,7 +93,16 @@ def test_berlin52_cli_golden(workdir, alg, extra, cost):
         with open(os.path.join(workdir, "results", "TabuResults.dat")) as f:
             assert f.read().split() == lines
     if alg == "VNS":
-        assert c["ref_2opt"] == 50 and c["h_Greedy_iterative"] == 1
+        assert c["mh_VNS"] == 1 and c["ref_2opt"] == 0 and c["h_Greedy_iterative"] == 1
+        with open(os.path.join(workdir, "results", "VNSResults.dat")) as f:
+            lines = f.read().split()
+        assert len(lines) == 50
+        # the reference's own loop (its vns_kick, the interposed ref_2opt once per iteration): same result, same file
+        r0 = run_cli(TSP_GPU, workdir, ["-f", "berlin52.tsp", "-q", "-alg", alg] + extra, {"TSPCUDA_BATCH": "0"})
+        c0 = calls(r0.stderr)
+        assert r0.stdout == r.stdout and c0["ref_2opt"] == 50 and c0["mh_VNS"] == 0
+        with open(os.path.join(workdir, "results", "VNSResults.dat")) as f:
+            assert f.read().split() == lines
     if alg == "EXTRA_MILEAGE":
         assert c["h_ExtraMileage"] == 1
         # the reference's own h_ExtraMileage (EM_MAX loop over the host matrix) over the interposed util

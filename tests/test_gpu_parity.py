@@ -380,6 +380,56 @@ def test_vns_loop(tsp, oracle):
             assert np.array_equal(po, pg)
 
 
+@pytest.mark.parametrize("name,k,seed", [("berlin52", 40, 1), ("eil51", 25, 7), ("kroA100", 20, 3), ("pcb442", 10, 5), ("rl1304", 5, 2)])
+def test_vns_search_device_resident_loop(tsp, oracle, name, k, seed):
+    """tspcuda_vns_search (the loop of mh_VNS, metaheuristic.c:277-321, tour resident on the device) against the same
+    loop made of the oracle's ref_2opt and its vns_kick (pinned on the reference objects), same glibc rand() stream:
+    cost trace, incumbent and the final kicked tour."""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    xy, _ = load_instance(name)
+    e, p0, c0 = oracle.nn(xy, 0)
+    libc.srand(seed)
+    po, best, best_path, bi, trace = p0.copy(), c0, None, -1, []
+    for i in range(k):
+        m, po, co, *_ = oracle.two_opt(xy, po, log=False)
+        if co < best:
+            best, best_path, bi = co, po.copy(), i
+        trace.append(co)
+        for _ in range(libc.rand() % 9 - 2):
+            oracle.vns_kick(po)
+    libc.srand(seed)
+    with tsp.Instance(xy) as I:
+        code, pg, cg, tr, gbi, gbp, gbc, done = I.vns_search(p0, k, c0)
+    assert code == 0 and done == k and tr.tolist() == trace and cg == trace[-1]
+    assert np.array_equal(pg, po)
+    assert (gbi, gbc) == (bi, best) and (bi < 0 or np.array_equal(gbp, best_path))
+
+
+def test_vns_restarts_shard_independent(tsp):
+    """multistart.vns_restarts: a restart depends on (instance, start node, seed) only, so the merged best of two shards
+    equals the best of one shard holding every start."""
+    from travellingsalesmanoptimization_b200.multistart import shard_starts, vns_restarts
+    xy, _ = load_instance("kroA100")
+    with tsp.Instance(xy) as I:
+        whole = vns_restarts(I, 0, 6, 1, 8, seed=5)
+        parts = [vns_restarts(I, *shard_starts(0, 6, r, 2), 8, seed=5) for r in range(2)]
+    merged = min((p for p in parts if p[0] is not None), key=lambda p: (p[0], p[1]))
+    assert whole[0] == merged[0] and whole[1] == merged[1] and np.array_equal(whole[2], merged[2])
+
+
+def test_vns_search_limits(tsp, oracle):
+    xy, _ = load_instance("kroA100")
+    e, p0, c0 = oracle.nn(xy, 0)
+    with tsp.Instance(xy) as I:
+        code, pg, cg, tr, bi, bp, bc, done = I.vns_search(p0, 0, c0)                 # k = 0: nothing happens
+        assert code == 0 and done == 0 and np.array_equal(pg, p0) and bi == -1 and bc == c0
+        code, pg, cg, tr, bi, bp, bc, done = I.vns_search(p0, 10**6, c0, time_limit=0.05)
+        assert code == tsp.DEADLINE_EXCEEDED and 0 < done < 10**6 and oracle.is_tour(pg) and bc <= c0
+        code, pg, cg, tr, bi, bp, bc, done = I.vns_search(p0, 3, 0.0)                # nothing beats a cost of 0
+        assert bi == -1 and bp is None and bc == 0.0 and done == 3
+
+
 # ---- TSPLIB95 weight types (no reference behaviour: parity unpinned, oracle = TSPLIB95) ---------
 def test_ceil2d_and_att(tsp, oracle):
     xy, _ = load_instance("pla7397")

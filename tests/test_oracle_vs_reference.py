@@ -166,3 +166,17 @@ def test_patching_step_by_step(oracle, reference, n, integer, ncomp, local, seed
         n2, k2 = reference.patching(p2, c2, n2, k2)
         assert ok and nc == n2 and cost == k2 and np.array_equal(path, p2) and np.array_equal(comp, c2), (a, b, d)
     assert oracle.is_tour(path)
+
+
+@pytest.mark.parametrize("n", [7, 8, 9, 11, 12, 13, 16, 21])
+def test_vns_kick_small_n(oracle, reference, n):
+    """vns_kick's rejection test reads tour[-1] / tour[n] out of bounds (metaheuristic.c:372); under glibc both are 0
+    unless n = 2 (mod 4), so a draw of 0 is rejected once index n-1 has been accepted.  Frequent on small n."""
+    xy = np.ascontiguousarray(np.random.default_rng(n).uniform(0, 100, (n, 2)))
+    reference.set_points(xy)
+    for seed in range(300):
+        p = np.roll(np.arange(n), -1).astype(np.int32)
+        q = p.copy()
+        reference.srand(seed); reference.vns_kick(p)
+        reference.srand(seed); oracle.vns_kick(q)
+        assert np.array_equal(p, q), seed

@@ -32,7 +32,7 @@ EXPORTS = [
     "tspcuda_timer_stop", "tspcuda_flush_l2", "tspcuda_set_scan_mode", "tspcuda_tabu_search",
     "tspcuda_extra_mileage", "tspcuda_mx_create", "tspcuda_mx_destroy", "tspcuda_mx_get_stats", "tspcuda_mx_nn", "tspcuda_mx_two_opt",
     "tspcuda_mx_two_opt_once", "tspcuda_patching", "tspcuda_mgpu_create", "tspcuda_mgpu_destroy", "tspcuda_mgpu_ndev",
-    "tspcuda_mgpu_multistart",
+    "tspcuda_mgpu_multistart", "tspcuda_vns_search",
 ]
 
 
@@ -103,6 +103,7 @@ def lib():
     L.tspcuda_set_scan_mode.argtypes = [_vp, C.c_int]
     L.tspcuda_extra_mileage.argtypes = [_vp, C.c_int, C.c_int, _ip, _dp, _ip, _ip]
     L.tspcuda_patching.argtypes = [_vp, _ip, _ip, _ip, _dp, C.c_int, C.POINTER(Move), C.c_int64, _ip]
+    L.tspcuda_vns_search.argtypes = [_vp, _ip, _dp, C.c_int, C.c_double, _dp, _ip, _dp, _ip, _ip]
     L.tspcuda_mgpu_create.argtypes = [C.POINTER(_vp), _dp, C.c_int, C.c_int, C.c_int, _ip]
     L.tspcuda_mgpu_destroy.argtypes = [_vp]
     L.tspcuda_mgpu_destroy.restype = None
@@ -251,6 +252,17 @@ class Instance:
         cost, a, b = C.c_double(0), C.c_int(-1), C.c_int(-1)
         _chk(lib().tspcuda_extra_mileage(self._h, node_a, node_b, _ipc(path), C.byref(cost), C.byref(a), C.byref(b)))
         return path, cost.value, (a.value, b.value)
+
+    def vns_search(self, path, n_iters, best_cost, time_limit=-1.0):
+        """The loop of mh_VNS (metaheuristic.c:277-321), kicks drawn from the process's rand() stream.
+        Returns (code, path, cost, trace, best_iter, best_path or None, best_cost, iters_done)."""
+        path = np.array(path, dtype=np.int32, copy=True)
+        trace = np.zeros(max(1, n_iters), dtype=np.float64)
+        best_path = np.zeros(self.n, dtype=np.int32)
+        c, bc, bi, done = C.c_double(0), C.c_double(best_cost), C.c_int(-1), C.c_int(0)
+        code = _chk(lib().tspcuda_vns_search(self._h, _ipc(path), C.byref(c), n_iters, time_limit, _dpc(trace), _ipc(best_path),
+                                             C.byref(bc), C.byref(bi), C.byref(done)), allow=(DEADLINE_EXCEEDED,))
+        return code, path, c.value, trace[:done.value], bi.value, (best_path if bi.value >= 0 else None), bc.value, done.value
 
     def patching(self, path, comp, ncomp, cost, max_patches=-1, allow=()):
         """cx_patching (cplex_model.c:693-755); max_patches < 0: the caller's while (ncomp > 1) loop (:205-212).

@@ -21,6 +21,9 @@
  *   mh_TabuSearch       metaheuristic.c:86  (whole-loop override: the k tabu iterations run in one
  *                       device-resident call; TSPCUDA_BATCH=0 keeps the reference's loop, which then
  *                       calls the interposed tabu_best_move once per iteration)
+ *   mh_VNS              metaheuristic.c:251  (whole-loop override: the tour stays on the device between the
+ *                       descents, the kick runs on the host on the tour order with the process's rand() stream;
+ *                       TSPCUDA_BATCH=0 keeps the reference's loop over the interposed ref_2opt and its own vns_kick)
  *   h_extramileage_util heuristics.c:290   and   h_ExtraMileage  heuristics.c:156  (the
  *                       latter only so that the EM_MAX search also works without a host matrix, n > 46340)
  *   cx_patching         cplex_model.c:693  (the patching heuristic of the Benders loop; reached
@@ -51,12 +54,12 @@ static int g_mgpu_n = -1;
 static int g_weight_type = TSPCUDA_EUC_REF;     /* set by the interposed tsp_read_input */
 static point *g_points = NULL;
 static int g_n = -1;
-#define N_CALLS 12
+#define N_CALLS 13
 static long g_calls[N_CALLS];
-enum { C_COSTS, C_NN, C_2OPT, C_2OPT_ONCE, C_TABU, C_ALLNN, C_MULTI, C_TABULOOP, C_READ, C_EMUTIL, C_EM, C_PATCH };
+enum { C_COSTS, C_NN, C_2OPT, C_2OPT_ONCE, C_TABU, C_ALLNN, C_MULTI, C_TABULOOP, C_READ, C_EMUTIL, C_EM, C_PATCH, C_VNSLOOP };
 static const char *g_names[] = {"tsp_compute_costs", "h_greedyutil", "ref_2opt", "ref_2opt_once",
                                 "tabu_best_move", "h_Greedy_iterative", "h_greedy_2opt", "mh_TabuSearch", "tsp_read_input",
-                                "h_extramileage_util", "h_ExtraMileage", "cx_patching"};
+                                "h_extramileage_util", "h_ExtraMileage", "cx_patching", "mh_VNS"};
 
 /* Exit hook.  Prints the call counters (TSPCUDA_STATS=1), flushes stdio and leaves with _exit().
  * The last step shields the process from a latent heap overflow in the UNCHANGED driver:
@@ -527,6 +530,68 @@ ERROR_CODE mh_TabuSearch(void) {
     free(tenures);
     free(trace);
     tabu_free(&ts);
+    return e;
+}
+
+/* mh_VNS, metaheuristic.c:251-341.  Same steps in the same order -- h_Greedy_iterative start solution, results
+ * file, k iterations of {time check; ref_2opt with incumbent update; best_vns test; one line of
+ * results/VNSResults.dat; rand() % 9 - 2 kicks}, final tsp_update_best_solution(&best_vns), plot -- except that the
+ * iterations run in tspcuda_vns_search with the tour resident on the device (per iteration only the tour order
+ * crosses the bus, and no successor-array <-> order walk happens).  rand() is this process's stream, consumed in
+ * the reference's order.  ref_2opt(update_incumbent = true) changes the incumbent only on a strictly smaller cost
+ * (tsp.c:671), which is also when best_vns changes (it starts at the incumbent's cost, :270), so one
+ * tsp_update_best_solution per block with the block's best tour leaves the same incumbent. */
+ERROR_CODE mh_VNS(void) {
+    if (!batch_enabled())
+        return ((void_fn)dlsym(RTLD_NEXT, "mh_VNS"))();
+    g_calls[C_VNSLOOP]++;
+    log_info("running Variable Neighborhood Search");
+    tsp_solution solution;
+    tsp_init_solution(tsp_inst.nnodes, &solution);
+    ERROR_CODE e = h_Greedy_iterative();
+    if (!err_ok(e)) {
+        log_fatal("code %d : Error in greedy", e);
+        tsp_handlefatal();
+    }
+    log_info("Greedy done!");
+    memcpy(solution.path, tsp_inst.best_solution.path, tsp_inst.nnodes * sizeof(int));
+    solution.cost = tsp_inst.best_solution.cost;
+    tsp_solution best_vns;
+    tsp_init_solution(tsp_inst.nnodes, &best_vns);
+    best_vns.cost = solution.cost;
+    FILE *f = fopen("results/VNSResults.dat", "w+");
+    tspcuda_ctx *c = ctx_for_instance();
+    const int K = tsp_env.k > 0 ? tsp_env.k : 0;
+    const int BLOCK = 4096;
+    double *trace = (double *)malloc(sizeof(double) * BLOCK);
+    for (int k0 = 0; k0 < K; k0 += BLOCK) {
+        const int cnt = K - k0 < BLOCK ? K - k0 : BLOCK;
+        int best_iter = -1, done = 0;
+        int rc = c ? tspcuda_vns_search(c, solution.path, &solution.cost, cnt, time_left(), trace, best_vns.path, &best_vns.cost,
+                                        &best_iter, &done)
+                   : TSPCUDA_INTERNAL;
+        if (rc != TSPCUDA_OK && rc != TSPCUDA_DEADLINE_EXCEEDED) {
+            log_fatal("code %d : Error in local search (libtspcuda: %s)", rc, tspcuda_last_error());
+            tsp_handlefatal();
+        }
+        if (best_iter >= 0) {
+            log_info("found new best: %f ", best_vns.cost);
+            tsp_update_best_solution(&best_vns);                    /* what ref_2opt(.., true) did along the way (:288) */
+        }
+        if (f)
+            for (int k = 0; k < done; k++) fprintf(f, "%d,%f\n", k0 + k, trace[k]);      /* :303 */
+        if (rc == TSPCUDA_DEADLINE_EXCEEDED) break;                  /* :279-285 */
+    }
+    if (f) fclose(f);
+    e = tsp_update_best_solution(&best_vns);                        /* :322 */
+    if (!err_ok(e)) log_error("code %d : error in updating best solution of VNS", e);
+    PLOT plot = plot_open("VNSIterationsPlot");
+    if (tsp_env.tofile) plot_tofile(plot, "VNSIterationsPlot");
+    plot_stats(plot, "results/VNSResults.dat");
+    plot_free(plot);
+    free(trace);
+    utils_safe_free(best_vns.path);
+    utils_safe_free(solution.path);
     return e;
 }
 

@@ -1223,6 +1223,99 @@ extern "C" int tspcuda_extra_mileage(tspcuda_ctx *c, int node_a, int node_b, int
     return TSPCUDA_OK;
 }
 
+// ---- VNS loop (metaheuristic.c:277-321 of mh_VNS; vns_kick :344-409, tabu_make_move case 7 :490-500) ----------
+// The kick, on the tour ORDER from node 0 (what vns_kick rebuilds from the successor array at every call): three
+// random positions i0 < i1 < i2 drawn from the process's rand() stream with the reference's rejection test --
+// which compares a drawn POSITION with the NODES next to the positions accepted before (:372) -- then
+// path[A] = succ B, path[C] = succ A, path[B] = succ C, i.e. the blocks (i0, i1] and (i1, i2] swap places.
+// The reference reads tour[-1] / tour[n] out of bounds in that test; under glibc both read 0 unless n = 2 (mod 4)
+// (checked against the reference objects on small n, where the case is frequent), and 0 is
+// what is used here.
+static void vns_kick_order(int n, int *ord, int *tmp) {
+    int idx[3];
+    for (int i = 0; i < 3; i++) {
+        int r;
+        do {
+            r = rand() % n;
+            for (int j = 0; j < i; j++) {
+                const int lo = idx[j] - 1, hi = idx[j] + 1;
+                const int tlo = lo >= 0 ? ord[lo] : 0, thi = hi < n ? ord[hi] : 0;
+                if (r == idx[j] || r == tlo || r == thi) { r = -1; break; }
+            }
+        } while (r == -1);
+        idx[i] = r;
+        for (int j = i; j > 0; j--)
+            if (idx[j] < idx[j - 1]) std::swap(idx[j], idx[j - 1]);
+    }
+    const int i0 = idx[0], i1 = idx[1], i2 = idx[2];
+    const int len1 = i1 - i0, len2 = i2 - i1;                  // blocks (i0, i1] and (i1, i2]
+    std::memcpy(tmp, ord + i0 + 1, sizeof(int) * len1);
+    std::memmove(ord + i0 + 1, ord + i1 + 1, sizeof(int) * len2);
+    std::memcpy(ord + i0 + 1 + len2, tmp, sizeof(int) * len1);
+}
+
+extern "C" int tspcuda_vns_search(tspcuda_ctx *c, int *path, double *cost_inout, int n_iters, double time_limit_s,
+                                  double *cost_trace_out, int *best_path_out, double *best_cost_inout, int *best_iter_out,
+                                  int *iters_done_out) {
+    int e = use(c);
+    if (e) return e;
+    if (!path || !best_cost_inout) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
+    const int n = c->n;
+    if (n < 5) return fail(TSPCUDA_INVALID_ARGUMENT, "the kick needs three non-adjacent positions");
+    if (best_iter_out) *best_iter_out = -1;
+    if (iters_done_out) *iters_done_out = 0;
+    c->tour_loaded = false;
+    e = tspcuda_tour_upload(c, path);                          // validates the tour; device order starts at node 0
+    if (e) return e;
+    std::vector<int> ord(n), tmp(n), best_ord;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); };
+    bool deadline = false;
+    int done = 0, best_iter = -1;
+    double cost = cost_inout ? *cost_inout : 0.0;
+    for (int i = 0; i < n_iters; i++) {
+        if (time_limit_s >= 0 && elapsed() > time_limit_s) { deadline = true; break; }     // :279-285
+        bool dl = false;
+        e = descend(c, -1, 0, time_limit_s >= 0 ? std::max(0.0, time_limit_s - elapsed()) : -1.0, &dl);   // ref_2opt, :288
+        if (e) return e;
+        CK(cudaMemcpyAsync(c->h_buf, c->tour.tid, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
+        e = read_state(c);                                     // synchronises
+        if (e) return e;
+        c->stats.d2h_bytes += (int64_t)sizeof(int) * n;
+        cost = (double)c->h_state->cost;
+        int p0 = 0;
+        while (p0 < n && c->h_buf[p0] != 0) ++p0;              // rotate: the reference's tour[] starts at node 0 (:356-363)
+        if (p0 == n) return fail(TSPCUDA_INTERNAL, "node 0 missing from the device tour");
+        std::memcpy(ord.data(), c->h_buf + p0, sizeof(int) * (n - p0));
+        std::memcpy(ord.data() + (n - p0), c->h_buf, sizeof(int) * p0);
+        if (cost < *best_cost_inout) {                         // :296-300, strict '<'
+            *best_cost_inout = cost;
+            best_ord = ord;
+            best_iter = i;
+        }
+        if (cost_trace_out) cost_trace_out[i] = cost;          // :303
+        done = i + 1;
+        const int r = rand() % (10 - 2 + 1) - 2;               // :306, UPPER 10 / LOWER 2 (metaheuristic.h:7-8)
+        for (int j = 0; j < r; j++) vns_kick_order(n, ord.data(), tmp.data());
+        std::memcpy(c->h_buf, ord.data(), sizeof(int) * n);
+        CK(cudaMemcpyAsync(c->d_order, c->h_buf, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
+        c->stats.h2d_bytes += (int64_t)sizeof(int) * n;
+        e = tour_from_device_order(c);                         // cost recomputed from the kicked tour (refinment.c:6-9)
+        if (e) return e;
+        CK(cudaStreamSynchronize(c->stream));                  // h_buf is reused
+    }
+    // the solution as the reference leaves it: the tour after the last kicks, cost = after the last descent
+    if (done > 0)
+        for (int k = 0; k < n; k++) path[ord[k]] = ord[(k + 1) % n];
+    c->tour_loaded = false;
+    if (cost_inout) *cost_inout = cost;
+    if (best_iter >= 0 && best_path_out)
+        for (int k = 0; k < n; k++) best_path_out[best_ord[k]] = best_ord[(k + 1) % n];
+    if (best_iter_out) *best_iter_out = best_iter;
+    if (iters_done_out) *iters_done_out = done;
+    return deadline ? TSPCUDA_DEADLINE_EXCEEDED : TSPCUDA_OK;
+}
+
 // ---- patching (cplex_model.c:693-755 cx_patching, the Benders loop's while (ncomp > 1), :205-212) -----
 extern "C" int tspcuda_patching(tspcuda_ctx *c, int *path, int *comp, int *ncomp_inout, double *cost_inout,
                                 int max_patches, tspcuda_move *log, int64_t log_cap, int *patches_out) {

@@ -83,3 +83,25 @@ def tabu_restarts(inst, first_start, count, stride, k):
         if best_cost is None or run_best < best_cost:
             best_cost, best_start, best_path = run_best, start, run_path
     return best_cost, best_start, best_path
+
+
+def vns_restarts(inst, first_start, count, stride, k, seed=0):
+    """Config 5 VNS "restarts" (a framework addition, as tabu_restarts): restart r = start node first_start + r*stride with
+    the glibc stream re-seeded to srand(seed + start) (the reference seeds only random instances, tsp.c:469): NN tour ->
+    k iterations of the loop of mh_VNS (metaheuristic.c:277-321: 2-opt descent, incumbent test, rand() % 9 - 2 kicks),
+    tour resident on the device.  A restart depends only on (instance, start, seed), never on the shard it runs in.
+    Returns this shard's best (cost, start, path) under the incumbent rule (strict '<', ascending starts), or
+    (None, -1, None) for an empty shard; reduce_best() merges the shards."""
+    import ctypes
+    libc = ctypes.CDLL(None)
+    best_cost, best_start, best_path = None, -1, None
+    for r in range(count):
+        start = first_start + r * stride
+        libc.srand(ctypes.c_uint(seed + start))
+        code, path, cost = inst.nn(start)
+        # the cost to beat is +inf: the first local optimum always enters (mh_VNS starts from the incumbent's cost, :270,
+        # because its start tour already is the incumbent; a restart has no incumbent yet)
+        code, path, cost, trace, bi, bp, bc, done = inst.vns_search(path, k, float("inf"))
+        if bi >= 0 and (best_cost is None or bc < best_cost):
+            best_cost, best_start, best_path = bc, start, bp
+    return best_cost, best_start, best_path
