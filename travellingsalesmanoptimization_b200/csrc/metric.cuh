@@ -90,6 +90,12 @@ struct ScalarScan {
         ka = Derived::K(xa, ya, xj, yj);
         kb = Derived::K(xb, yb, xj, yj);
     }
+    // two unrelated edges (p,q) and (r,s) at once, same encoding (patching.cuh)
+    static __device__ __forceinline__ void KK(double xp, double yp, double xq, double yq, double xr, double yr, double xs, double ys,
+                                              int &ka, int &kb) {
+        ka = Derived::K(xp, yp, xq, yq);
+        kb = Derived::K(xr, yr, xs, ys);
+    }
 };
 
 // tsp.c:629 for arbitrary (non-integer) coordinates: separate roundings, clamp against s == 0.
@@ -103,6 +109,13 @@ struct EucGeneral {
     static constexpr unsigned SCAN_XOR = SCAN_FLIP;
     static __device__ __forceinline__ void K2(double xa, double ya, double xb, double yb, double xj, double yj, int &ka, int &kb) {
         const double dxa = __dsub_rn(xj, xa), dya = __dsub_rn(yj, ya), dxb = __dsub_rn(xj, xb), dyb = __dsub_rn(yj, yb);
+        const double sa = __dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya));
+        const double sb = __dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb));
+        koff2_from_negsumsq(fminf(__double2float_rn(-sa), -TINY_F), fminf(__double2float_rn(-sb), -TINY_F), ka, kb);
+    }
+    static __device__ __forceinline__ void KK(double xp, double yp, double xq, double yq, double xr, double yr, double xs, double ys,
+                                              int &ka, int &kb) {
+        const double dxa = __dsub_rn(xq, xp), dya = __dsub_rn(yq, yp), dxb = __dsub_rn(xs, xr), dyb = __dsub_rn(ys, yr);
         const double sa = __dadd_rn(__dmul_rn(dxa, dxa), __dmul_rn(dya, dya));
         const double sb = __dadd_rn(__dmul_rn(dxb, dxb), __dmul_rn(dyb, dyb));
         koff2_from_negsumsq(fminf(__double2float_rn(-sa), -TINY_F), fminf(__double2float_rn(-sb), -TINY_F), ka, kb);
@@ -128,6 +141,13 @@ struct EucInt {
     static __device__ __forceinline__ void K2(double xa, double ya, double xb, double yb, double xj, double yj, int &ka, int &kb) {
         const double dxa = __dsub_rn(xj, xa), dya = __dsub_rn(yj, ya), dxb = __dsub_rn(xj, xb), dyb = __dsub_rn(yj, yb);
         const double nsa = __fma_rn(-dxa, dxa, __fma_rn(-dya, dya, -TINY_D));      // -(dx^2 + dy^2 + 2^-60), exact
+        const double nsb = __fma_rn(-dxb, dxb, __fma_rn(-dyb, dyb, -TINY_D));
+        koff2_from_negsumsq(__double2float_rn(nsa), __double2float_rn(nsb), ka, kb);
+    }
+    static __device__ __forceinline__ void KK(double xp, double yp, double xq, double yq, double xr, double yr, double xs, double ys,
+                                              int &ka, int &kb) {
+        const double dxa = __dsub_rn(xq, xp), dya = __dsub_rn(yq, yp), dxb = __dsub_rn(xs, xr), dyb = __dsub_rn(ys, yr);
+        const double nsa = __fma_rn(-dxa, dxa, __fma_rn(-dya, dya, -TINY_D));
         const double nsb = __fma_rn(-dxb, dxb, __fma_rn(-dyb, dyb, -TINY_D));
         koff2_from_negsumsq(__double2float_rn(nsa), __double2float_rn(nsb), ka, kb);
     }

@@ -19,7 +19,6 @@
 
 namespace tspcuda {
 
-constexpr int PATCH_TILE = 256;
 
 struct PatchState {
     int *path, *comp;          // [n] successor array and component labels (in/out)
@@ -41,40 +40,52 @@ __global__ void patch_prep_kernel(const double2 *__restrict__ xy, int n, PatchSt
     }
 }
 
-// K13: one CTA per (a-tile, slice of the b-tiles at or after it).  Thread t owns node a = tile * 256 + t in
-// registers; the b side of a tile is staged in shared memory and read as broadcasts.
-template <class M>
-__global__ void __launch_bounds__(PATCH_TILE)
+// K13: the upper triangle of (a-tile, b-tile) pairs, b-tile >= a-tile, is linearised row by row and dealt out to the
+// CTAs round-robin (tile pair t goes to CTA t mod gridDim.x), so every CTA gets the same number of tile pairs to within
+// one -- all CTAs are resident at once, and a split by a-tile would leave the CTAs of the last rows idle for half the
+// scan.  Within a tile pair thread t owns node a = ta * TILE + t in registers; the b side is staged in shared memory
+// and read as broadcasts.
+template <class M, int TILE>
+__global__ void __launch_bounds__(TILE)
 patch_scan_kernel(const double2 *__restrict__ xy, int n, PatchState S) {
-    __shared__ double2 s_xy[PATCH_TILE], s_sxy[PATCH_TILE];
-    __shared__ int s_dn[PATCH_TILE], s_comp[PATCH_TILE];
+    __shared__ double2 s_xy[TILE], s_sxy[TILE];
+    __shared__ int s_dn[TILE], s_comp[TILE];
     __shared__ unsigned long long s_key;
     if (S.info[1]) return;                               // an earlier scan of this batch found nothing
-    const int ntiles = (n + PATCH_TILE - 1) / PATCH_TILE;
-    const int ta = blockIdx.x;
-    const int a = ta * PATCH_TILE + threadIdx.x;
-    const bool va = a < n;
-    const double2 pa = va ? xy[a] : make_double2(0, 0), psa = va ? S.sxy[a] : make_double2(0, 0);
-    const int dna = va ? S.dn[a] : 0, ca = va ? S.comp[a] : -1;
+    const long long N = (n + TILE - 1) / TILE;
+    const long long T = N * (N + 1) / 2;
     if (threadIdx.x == 0) s_key = KEY_EMPTY;
     int best = 0x3FFFFFFF;
     unsigned long long bestkey = KEY_EMPTY;
-    for (int tb = ta + blockIdx.y; tb < ntiles; tb += gridDim.y) {
+    for (long long t = blockIdx.x; t < T; t += gridDim.x) {
+        // row ta starts at R(ta) = ta * N - ta (ta - 1) / 2
+        long long ta = (long long)(((double)(2 * N + 1) - sqrt((double)((2 * N + 1) * (2 * N + 1) - 8 * t))) * 0.5);
+        ta = max(0ll, min(N - 1, ta));
+        while (ta > 0 && ta * N - ta * (ta - 1) / 2 > t) --ta;
+        while ((ta + 1) * N - (ta + 1) * ta / 2 <= t) ++ta;
+        const int tb = (int)(ta + (t - (ta * N - ta * (ta - 1) / 2)));
+        const int a = (int)ta * TILE + threadIdx.x;
+        const bool va = a < n;
+        const double2 pa = va ? xy[a] : make_double2(0, 0), psa = va ? S.sxy[a] : make_double2(0, 0);
+        const int dna = va ? S.dn[a] : 0, ca = va ? S.comp[a] : -1;
         __syncthreads();
-        const int bl = tb * PATCH_TILE + threadIdx.x;
+        const int bl = tb * TILE + threadIdx.x;
         if (bl < n) { s_xy[threadIdx.x] = xy[bl]; s_sxy[threadIdx.x] = S.sxy[bl]; s_dn[threadIdx.x] = S.dn[bl]; s_comp[threadIdx.x] = S.comp[bl]; }
         __syncthreads();
         if (!va) continue;
-        const int cnt = min(PATCH_TILE, n - tb * PATCH_TILE);
-        const int k0 = (tb == ta) ? threadIdx.x + 1 : 0;      // b > a
+        const int cnt = min(TILE, n - tb * TILE);
+        const int k0 = (tb == (int)ta) ? threadIdx.x + 1 : 0; // b > a
         for (int k = k0; k < cnt; ++k) {
             if (s_comp[k] == ca) continue;                    // :703
             const double2 pb = s_xy[k], psb = s_sxy[k];
-            // swapped - current (:712-714); the four K offsets cancel
-            const int d = M::K(pa.x, pa.y, psb.x, psb.y) + M::K(pb.x, pb.y, psa.x, psa.y) - dna - s_dn[k];
+            // swapped - current (:712-714); the four K offsets cancel (and so do the two sign flips of the packed
+            // FP32x2 cost sequence, metric.cuh: 2 * 2^31 wraps away)
+            int k1, k2;
+            M::KK(pa.x, pa.y, psb.x, psb.y, pb.x, pb.y, psa.x, psa.y, k1, k2);
+            const int d = (int)((unsigned)k1 + (unsigned)k2 - (unsigned)dna - (unsigned)s_dn[k]);
             if (d > 0 && d <= best) {                         // :716 (delta > 0), first strict minimum by the key
                 best = d;
-                const unsigned long long key = pack_key(d, a, tb * PATCH_TILE + k);
+                const unsigned long long key = pack_key(d, a, tb * TILE + k);
                 if (key < bestkey) bestkey = key;
             }
         }

@@ -1367,12 +1367,15 @@ extern "C" int tspcuda_patching(tspcuda_ctx *c, int *path, int *comp, int *ncomp
     S.path = dpath.as<int>(); S.comp = dcomp.as<int>(); S.sxy = sxy.as<double2>(); S.dn = dn.as<int>();
     S.key = key.as<unsigned long long>(); S.cost = cost.as<long long>(); S.info = info.as<int>();
     S.log = dlog.as<int>(); S.log_cap = todo;
-    const int ntiles = (n + PATCH_TILE - 1) / PATCH_TILE;
-    const int slices = std::max(1, std::min(ntiles, 4 * c->num_sms / ntiles));
+    // small instances: 64-node tiles, so that the triangle still yields several hundred tile pairs to spread over the SMs
+    const int tile = n < 12000 ? 64 : 256;
+    const long long ntiles = (n + tile - 1) / tile;
+    const int scan_grid = (int)std::min<long long>(ntiles * (ntiles + 1) / 2, (long long)c->num_sms * (tile == 64 ? 32 : 8));
     CK(cudaEventRecord(c->ev0, c->stream));
     DISPATCH_METRIC(c->metric, (patch_prep_kernel<M><<<grid_for(n, c->num_sms * 4), 256, 0, c->stream>>>(c->d_xy, n, S)));
     for (int k = 0; k < todo; ++k) {
-        DISPATCH_METRIC(c->metric, (patch_scan_kernel<M><<<dim3(ntiles, slices), PATCH_TILE, 0, c->stream>>>(c->d_xy, n, S)));
+        if (tile == 64) { DISPATCH_METRIC(c->metric, (patch_scan_kernel<M, 64><<<scan_grid, 64, 0, c->stream>>>(c->d_xy, n, S))); }
+        else { DISPATCH_METRIC(c->metric, (patch_scan_kernel<M, 256><<<scan_grid, 256, 0, c->stream>>>(c->d_xy, n, S))); }
         DISPATCH_METRIC(c->metric, (patch_apply_kernel<M><<<1, 1024, 0, c->stream>>>(c->d_xy, n, S)));
     }
     CK(cudaGetLastError());
