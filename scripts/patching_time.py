@@ -7,7 +7,8 @@ import travellingsalesmanoptimization_b200 as T
 from oracle.bindings import Oracle, load_instance
 from components import cycles_solution
 O = Oracle()
-for name, ncomp in [("pr2392", 300), ("usa13509", 400), ("d15112", 400), ("pla85900", 60)]:
+CASES = [("pr2392", 300), ("usa13509", 400), ("d15112", 400), ("pla85900", 60)]
+for name, ncomp in [c for c in CASES if len(sys.argv) < 2 or c[0] in sys.argv[1:]]:
     xy, _ = load_instance(name)
     n = xy.shape[0]
     path, comp, nc = cycles_solution(1, n, ncomp, True, xy)
