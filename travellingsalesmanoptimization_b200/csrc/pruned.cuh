@@ -722,7 +722,25 @@ struct MultiSlots {
     int *best_start;        // [slots]
 };
 
-template <class M, int BLK>
+// CL > 1: a thread-block CLUSTER of CL CTAs (CL SMs) shares one descent -- for batches with fewer starts than SMs,
+// where one CTA per descent would leave SMs idle while every descent still takes its full single-SM time.  The
+// tour stays in the cluster's global-memory slot; the few scalars of a scan (argmin key, box-queue counter, cost,
+// current start) live in the shared memory of the cluster's first CTA and are reached by the others through
+// distributed shared memory; every barrier is a cluster barrier (barrier.cluster, release/acquire at cluster scope).
+template <int CL>
+__device__ __forceinline__ void team_sync() {
+    if (CL == 1) {
+        __syncthreads();
+    } else {
+        // the tour lives in GLOBAL memory and is read through each SM's own L1: a gpu-scope fence on either side of the
+        // cluster barrier (release before arriving, acquire after waiting) makes the peers' writes visible
+        __threadfence();
+        cg::this_cluster().sync();
+        __threadfence();
+    }
+}
+
+template <class M, int BLK, int CL>
 __global__ void __launch_bounds__(BLK, 1)
 multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const int *__restrict__ order_all, int first_start,
                     int stride, int nstarts, int *next_start, MultiSlots S, long long *final_cost, long long *moves_out,
@@ -730,11 +748,23 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     constexpr int WARPS = BLK / 32;
     constexpr int NC1 = BLK > 512 ? PR_NC_BIG : PR_NC;
     constexpr int NE = BLK > 512 ? 2 : 4;
-    __shared__ unsigned long long s_key, s_q;
-    __shared__ long long s_cost, s_bestcost;
-    __shared__ int s_cur;
-    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
-    const size_t n1 = (size_t)n + 1, slot = blockIdx.x;
+    constexpr int TEAM = BLK * CL;                      // threads sharing a descent
+    __shared__ unsigned long long s_key_, s_q_;
+    __shared__ long long s_cost_, s_bestcost_;
+    __shared__ int s_cur_;
+    unsigned rank = 0;
+    unsigned long long *s_key = &s_key_, *s_q = &s_q_;
+    long long *s_cost = &s_cost_, *s_bestcost = &s_bestcost_;
+    int *s_cur = &s_cur_;
+    if (CL > 1) {                                       // the scalars of the cluster's first CTA, through DSMEM
+        cg::cluster_group cluster = cg::this_cluster();
+        rank = cluster.block_rank();
+        s_key = cluster.map_shared_rank(&s_key_, 0); s_q = cluster.map_shared_rank(&s_q_, 0);
+        s_cost = cluster.map_shared_rank(&s_cost_, 0); s_bestcost = cluster.map_shared_rank(&s_bestcost_, 0);
+        s_cur = cluster.map_shared_rank(&s_cur_, 0);
+    }
+    const int t = (int)rank * BLK + threadIdx.x, warp = t >> 5, lane = t & 31;
+    const size_t n1 = (size_t)n + 1, slot = blockIdx.x / CL;
     TourView V;
     V.n = n;
     V.pxy = S.pxy + slot * n1;
@@ -744,27 +774,28 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     V.pos = S.pos + slot * (size_t)n;
     BigBox *boxes = S.boxes + slot * (size_t)n;
     int *best_path = S.best_path + slot * (size_t)n;
-    uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + warp) * PR_WBUF;
-    if (t == 0) { s_bestcost = -1; S.best_cost[slot] = -1; S.best_start[slot] = -1; }
+    uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * PR_WBUF;
+    if (t == 0) { *s_bestcost = -1; S.best_cost[slot] = -1; S.best_start[slot] = -1; }
     long long ncand = 0;
 
     for (;;) {
-        __syncthreads();
-        if (t == 0) s_cur = atomicAdd(next_start, 1);
-        __syncthreads();
-        const int cur = s_cur;
+        team_sync<CL>();
+        if (t == 0) *s_cur = atomicAdd(next_start, 1);
+        team_sync<CL>();
+        const int cur = *s_cur;
+        if (CL > 1) team_sync<CL>();                    // nobody leaves (or rewrites s_cur) while a peer still reads it remotely
         if (cur >= nstarts) break;
         const int *order = order_all + (size_t)cur * n;
-        for (int p = t; p <= n; p += BLK) {
+        for (int p = t; p <= n; p += TEAM) {
             const int node = order[p == n ? 0 : p];
             V.pxy[p] = xy[node];
             V.tid[p] = node;
             if (p < n) V.pos[node] = p;
         }
-        if (t == 0) s_cost = 0;
-        __syncthreads();
+        if (t == 0) *s_cost = 0;
+        team_sync<CL>();
         long long local = 0;
-        for (int p = t; p < n; p += BLK) {
+        for (int p = t; p < n; p += TEAM) {
             const double2 u = V.pxy[p], v = V.pxy[p + 1];
             const int k = M::K(u.x, u.y, v.x, v.y);
             V.dn[p] = k;
@@ -772,40 +803,41 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             local += (long long)(k - KOFF);
         }
         for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(FULL, local, o);
-        if (lane == 0) atomicAdd((unsigned long long *)&s_cost, (unsigned long long)local);
+        if (lane == 0) atomicAdd((unsigned long long *)s_cost, (unsigned long long)local);
         long long moves = 0;
         PosPatch F = {-1, 0, -1, 0};
         for (;;) {
-            if (t == 0) { s_key = KEY_EMPTY; s_q = 0; }
-            __syncthreads();
+            if (t == 0) { *s_key = KEY_EMPTY; *s_q = 0; }
+            team_sync<CL>();
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
-            pruned_phase1<M, NC1, NE, 1, false>(V, G, F, t, BLK, &s_q, boxes, wbuf, best, bestkey, ncand, 0);
-            __syncthreads();
-            pruned_phase2<M, NE, false>(V, G, F, warp, WARPS, s_q, boxes, wbuf, best, bestkey, ncand, 0);
+            pruned_phase1<M, NC1, NE, 1, false>(V, G, F, t, TEAM, s_q, boxes, wbuf, best, bestkey, ncand, 0);
+            team_sync<CL>();
+            pruned_phase2<M, NE, false>(V, G, F, warp, WARPS * CL, *s_q, boxes, wbuf, best, bestkey, ncand, 0);
             bestkey = warp_min_key(bestkey);
-            if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
-            __syncthreads();
-            const unsigned long long kbest = s_key;
+            if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(s_key, bestkey);
+            team_sync<CL>();
+            const unsigned long long kbest = *s_key;
             if (kbest == KEY_EMPTY) break;                      // local optimum (refinment.c:27)
             const int a = key_a(kbest), b = key_b(kbest);
             int seg_s, seg_e;
-            apply_move<M>(V, a, b, t, BLK, false, seg_s, seg_e);
-            if (t == 0) s_cost += key_delta(kbest);
+            apply_move<M>(V, a, b, t, TEAM, false, seg_s, seg_e);
+            if (t == 0) *s_cost += key_delta(kbest);
             ++moves;
-            __syncthreads();
+            team_sync<CL>();
             F.node0 = b; F.pos0 = seg_s; F.node1 = V.tid[seg_e]; F.pos1 = seg_e;
             if (t == 0) { V.pos[F.node0] = F.pos0; V.pos[F.node1] = F.pos1; }
         }
         // kbest == KEY_EMPTY was read behind a barrier: every thread is here, the tour is final
-        const long long fc = s_cost;
+        const long long fc = *s_cost;
         if (t == 0) { final_cost[cur] = fc; moves_out[cur] = moves; }
-        const bool better = s_bestcost < 0 || fc < s_bestcost;            // strict '<', ascending starts per CTA
+        const long long bcst = *s_bestcost;
+        const bool better = bcst < 0 || fc < bcst;                        // strict '<', ascending starts per team
         if (better)
-            for (int p = t; p < n; p += BLK) best_path[V.tid[p]] = V.tid[p + 1];
-        __syncthreads();
+            for (int p = t; p < n; p += TEAM) best_path[V.tid[p]] = V.tid[p + 1];
+        team_sync<CL>();
         if (better && t == 0) {
-            s_bestcost = fc;
+            *s_bestcost = fc;
             S.best_cost[slot] = fc;
             S.best_start[slot] = first_start + cur * stride;
         }

@@ -851,6 +851,11 @@ static cudaError_t launch_cta_descents(tspcuda_ctx *c, const int *d_order, int c
     return cudaGetLastError();
 }
 
+// K8 with clusters (a descent shared by 2/4/8 SMs): from this n up a scan is long enough for the cluster barriers not to
+// matter, and from this many starts up a batch beats descending them one after the other on the whole GPU (K7)
+constexpr int K8_CLUSTER_MIN_N = 8192;
+constexpr int K8_CLUSTER_MIN_STARTS = 12;
+
 extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int nstarts, int stride, double *nn_costs_out,
                                           double *final_costs_out, int64_t *moves_out, int *best_start_out,
                                           int *best_path_out, double *best_cost_out) {
@@ -863,7 +868,9 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
     // K8 (one CTA per descent, pruned scan, any n) when there are enough starts to occupy the SMs;
     // K6 (one CTA per descent, full scan, tour in shared memory) when every pair must be evaluated;
     // otherwise the starts descend one after the other on the whole GPU (K2 / K7).
-    const bool multi_path = n >= 4 && c->pruned_blocks > 0 && c->scan_mode != TSPCUDA_SCAN_FULL && nstarts >= c->num_sms / 4;
+    const char *k8env = getenv("TSPCUDA_K8_CLUSTER");       // measurement knob: 0 = never batch (K7 one start after the other), 1/2/4/8 = cluster size
+    const bool multi_path = n >= 4 && c->pruned_blocks > 0 && c->scan_mode != TSPCUDA_SCAN_FULL && !(k8env && atoi(k8env) == 0) &&
+                            nstarts >= (k8env ? 1 : n >= K8_CLUSTER_MIN_N ? K8_CLUSTER_MIN_STARTS : c->num_sms / 4);
     const bool cta_path = !multi_path && n >= 4 && n <= CTA_MAX_N;       // whole tour fits one CTA's shared memory
     const int batch = std::min(nstarts, ((cta_path || multi_path) ? 16 : 8) * c->num_sms);
     NNScratch S;
@@ -912,18 +919,26 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
             CK(cudaMemsetAsync(next.p, 0, sizeof(int), c->stream));
             CK(cudaMemsetAsync(m_cand.p, 0, sizeof(unsigned long long), c->stream));
             CK(cudaEventRecord(c->ev0, c->stream));
-            const int g = std::min(cnt, mslots);
-            const char *kb = getenv("TSPCUDA_K8_BLOCK");
-            const int k8_block = kb ? atoi(kb) : 1024;
-            if (k8_block == 1024) {
-                DISPATCH_METRIC(c->metric, (multi_pruned_kernel<M, 1024><<<g, 1024, 0, c->stream>>>(
-                    c->d_xy, n, c->grid, S.order, fs, stride, cnt, next.as<int>(), MS, dcost.as<long long>(), dmoves.as<long long>(),
-                    m_cand.as<unsigned long long>(), c->d_wbuf)));
-            } else {
-                DISPATCH_METRIC(c->metric, (multi_pruned_kernel<M, PRUNED_BLOCK><<<g, PRUNED_BLOCK, 0, c->stream>>>(
-                    c->d_xy, n, c->grid, S.order, fs, stride, cnt, next.as<int>(), MS, dcost.as<long long>(), dmoves.as<long long>(),
-                    m_cand.as<unsigned long long>(), c->d_wbuf)));
-            }
+            // fewer starts than SMs: a cluster of CL CTAs per descent (pruned.cuh), CL the largest of 8/4/2 that still
+            // gives every start of the batch its own cluster
+            int cl = 1;
+            if (n >= K8_CLUSTER_MIN_N) while (cl < 8 && 2 * cl * cnt <= c->num_sms) cl *= 2;
+            if (const char *kc = getenv("TSPCUDA_K8_CLUSTER")) cl = std::max(1, std::min(8, atoi(kc)));
+            const int g = std::min(cnt, mslots / cl);            // teams (clusters); slots and record buffers are per team / per CTA
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(g * cl); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            cudaError_t le = cudaSuccess;
+#define K8_LAUNCH(CLV)                                                                                                        \
+    DISPATCH_METRIC(c->metric, (le = cudaLaunchKernelEx(&cfg, multi_pruned_kernel<M, 1024, CLV>, (const double2 *)c->d_xy, n, c->grid, \
+        (const int *)S.order, fs, stride, cnt, next.as<int>(), MS, dcost.as<long long>(), dmoves.as<long long>(),                     \
+        m_cand.as<unsigned long long>(), c->d_wbuf)))
+            if (cl == 8) { K8_LAUNCH(8); } else if (cl == 4) { K8_LAUNCH(4); } else if (cl == 2) { K8_LAUNCH(2); } else { K8_LAUNCH(1); }
+#undef K8_LAUNCH
+            CK(le);
             CK(cudaGetLastError());
             CK(cudaEventRecord(c->ev1, c->stream));
             c->stats.kernel_launches += 1;
