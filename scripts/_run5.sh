@@ -1,2 +1,2 @@
 set -x
-timeout 300 python scripts/cluster_sweep.py usa13509 2>&1 | tee gpurun_out/cluster_sweep.log
+timeout 450 python scripts/cluster_sweep.py 2>&1 | tee gpurun_out/cluster_sweep.log

@@ -732,8 +732,9 @@ __device__ __forceinline__ void team_sync() {
     if (CL == 1) {
         __syncthreads();
     } else {
-        // the tour lives in GLOBAL memory and is read through each SM's own L1: a gpu-scope fence on either side of the
-        // cluster barrier (release before arriving, acquire after waiting) makes the peers' writes visible
+        // the tour lives in GLOBAL memory and is read through each SM's own L1.  The cluster barrier's own release /
+        // acquire already orders those accesses (scripts/cluster_probe.cu sees no stale read without fences); the
+        // gpu-scope fences are kept as a cheap guard (~1 us against scans of 0.1 - 2 ms)
         __threadfence();
         cg::this_cluster().sync();
         __threadfence();
@@ -753,13 +754,13 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     __shared__ long long s_cost_, s_bestcost_;
     __shared__ int s_cur_;
     unsigned rank = 0;
-    unsigned long long *s_key = &s_key_, *s_q = &s_q_;
+    unsigned long long *s_q = &s_q_;
     long long *s_cost = &s_cost_, *s_bestcost = &s_bestcost_;
     int *s_cur = &s_cur_;
     if (CL > 1) {                                       // the scalars of the cluster's first CTA, through DSMEM
         cg::cluster_group cluster = cg::this_cluster();
         rank = cluster.block_rank();
-        s_key = cluster.map_shared_rank(&s_key_, 0); s_q = cluster.map_shared_rank(&s_q_, 0);
+        s_q = cluster.map_shared_rank(&s_q_, 0);
         s_cost = cluster.map_shared_rank(&s_cost_, 0); s_bestcost = cluster.map_shared_rank(&s_bestcost_, 0);
         s_cur = cluster.map_shared_rank(&s_cur_, 0);
     }
@@ -807,7 +808,11 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
         long long moves = 0;
         PosPatch F = {-1, 0, -1, 0};
         for (;;) {
-            if (t == 0) { *s_key = KEY_EMPTY; *s_q = 0; }
+            // the argmin key stays per CTA and is combined by reading the peers' copies: a 64-bit atomicMin is not
+            // atomic between a CTA's own shared-memory path and its peers' distributed-shared-memory path
+            // (measured, scripts/cluster_probe.cu: lost updates), 64-bit atomicAdd is
+            if (threadIdx.x == 0) s_key_ = KEY_EMPTY;
+            if (t == 0) *s_q = 0;
             team_sync<CL>();
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
@@ -815,9 +820,14 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             team_sync<CL>();
             pruned_phase2<M, NE, false>(V, G, F, warp, WARPS * CL, *s_q, boxes, wbuf, best, bestkey, ncand, 0);
             bestkey = warp_min_key(bestkey);
-            if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(s_key, bestkey);
+            if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key_, bestkey);
             team_sync<CL>();
-            const unsigned long long kbest = *s_key;
+            unsigned long long kbest = s_key_;
+            if (CL > 1) {
+                cg::cluster_group cluster = cg::this_cluster();
+#pragma unroll
+                for (int r = 0; r < CL; ++r) kbest = min(kbest, *cluster.map_shared_rank(&s_key_, r));
+            }
             if (kbest == KEY_EMPTY) break;                      // local optimum (refinment.c:27)
             const int a = key_a(kbest), b = key_b(kbest);
             int seg_s, seg_e;

@@ -924,7 +924,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
             int cl = 1;
             if (n >= K8_CLUSTER_MIN_N) while (cl < 8 && 2 * cl * cnt <= c->num_sms) cl *= 2;
             if (const char *kc = getenv("TSPCUDA_K8_CLUSTER")) cl = std::max(1, std::min(8, atoi(kc)));
-            const int g = std::min(cnt, mslots / cl);            // teams (clusters); slots and record buffers are per team / per CTA
+            const int g = std::max(1, std::min(std::min(cnt, mslots), c->num_sms / cl));   // teams (clusters): one tour slot each, cl record-buffer sets
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(g * cl); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
             cudaLaunchAttribute attr[1];
