@@ -530,6 +530,27 @@ def test_multistart_cta_paths_vs_grid_path(tsp, oracle, scan):
         assert (co, m_o, c_o) == per[0][:3] and np.array_equal(p_o, per[0][3])
 
 
+@pytest.mark.parametrize("n,starts", [(700, 5), (8500, 9)])
+def test_multistart_cluster_sizes_agree(tsp, oracle, monkeypatch, n, starts):
+    """K8 with a thread-block cluster per descent (2/4/8 SMs share one descent, pruned.cuh) against one CTA per
+    descent (1) and against K7 with one start after the other (0): same per-start costs, move counts and
+    best tour; the first start additionally against the CPU oracle.  n = 700: scans of a few microseconds,
+    i.e. the cluster barriers and the per-CTA argmin keys under the tightest timing."""
+    xy = _rand_xy(4100 + n, n, True)
+    ref = None
+    for cl in (0, 1, 2, 4, 8):
+        monkeypatch.setenv("TSPCUDA_K8_CLUSTER", str(cl))
+        with tsp.Instance(xy) as I:
+            bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(1, starts, 3)
+        key = (bs, int(bc), bp.tobytes(), nn_costs.tobytes(), final.tobytes(), moves.tobytes())
+        if ref is None:
+            ref = key
+            e, po, co = oracle.nn(xy, 1)
+            m_o, p_o, c_o, *_ = oracle.two_opt(xy, po, log=False)
+            assert (co, m_o, c_o) == (int(nn_costs[0]), int(moves[0]), int(final[0]))
+        assert key == ref, cl
+
+
 def test_pr2392_all_start_config2(tsp, golden):
     """Config 2: all 2392 starts NN + 2-opt on one B200.  The reference objects need 4.68 core-hours
     (BASELINE.md section 3): 393339, first reached at start 359; per-range bests for sharding checks."""

@@ -52,7 +52,18 @@ enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3, M_G
         default: { using M = Att; EXPR; } break;                          \
     }
 
+// Grow-only device scratch of the multi-start entry points, kept in the context between calls: cudaFree of the per-call
+// buffers sporadically took 0.1 - 1.5 s on the B200 boxes (TSPCUDA_VERBOSE phase clock, profiles/r01_cluster.md), more
+// than the descents of a small batch.  Released by tspcuda_destroy.
+struct ScratchBuf { void *p = nullptr; size_t bytes = 0; };
+enum {
+    SC_NN_CXY, SC_NN_CID, SC_NN_ORDER, SC_NN_COST, SC_NN_SLOT, SC_BEST_PATH, SC_NEXT, SC_DCOST, SC_DMOVES, SC_DPATHS,
+    SC_M_PXY, SC_M_TID, SC_M_DN, SC_M_POS, SC_M_BOXES, SC_M_BPATH, SC_M_BCOST, SC_M_BSTART, SC_M_CAND,
+    SC_T_TEN, SC_T_TRACE, SC_T_BEST, SC_T_OUT, SC_COUNT
+};
+
 struct tspcuda_ctx {
+    ScratchBuf scratch[SC_COUNT];
     int n = 0, wt = 0, device = 0, metric = 0;
     int num_sms = 0, max_coop_blocks = 0, block = 0;
     cudaStream_t stream = nullptr;
@@ -82,6 +93,7 @@ struct tspcuda_ctx {
     BigBox *d_boxes = nullptr;
     uint4 *d_wbuf = nullptr;         // per-warp record buffers of the pruned kernels (num_sms * 32 warps)
     int pruned_blocks = 0;           // cooperative grid of descend_pruned_kernel (0: unavailable)
+    int k8_clusters[4] = {0, 0, 0, 0};   // co-resident K8 clusters of 1/2/4/8 CTAs (cudaOccupancyMaxActiveClusters), filled at first use
     int pruned_block = 0;            // its CTA size
     int scan_mode = TSPCUDA_SCAN_AUTO;
     double est_pruned_s = 0, est_full_s = 0;
@@ -122,6 +134,7 @@ extern "C" void tspcuda_destroy(tspcuda_ctx *c) {
     cudaFree(c->d_matrix); cudaFree(c->d_sum); cudaFree(c->d_flush);
     cudaFree(c->d_cell_start); cudaFree(c->d_cell_count); cudaFree(c->d_cnode); cudaFree(c->d_cxy);
     cudaFree(c->d_qctr); cudaFree(c->d_boxes); cudaFree(c->d_wbuf);
+    for (ScratchBuf &b : c->scratch) cudaFree(b.p);
     if (c->tev0) cudaEventDestroy(c->tev0);
     if (c->tev1) cudaEventDestroy(c->tev1);
     if (c->h_state) cudaFreeHost(c->h_state);
@@ -599,9 +612,27 @@ extern "C" int tspcuda_tabu_move(tspcuda_ctx *c, int *path, double *cost_inout, 
 
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { cudaFree(p); }
+    bool owned = true;
+    ~DevBuf() { if (owned) cudaFree(p); }
     template <class T> T *as() { return reinterpret_cast<T *>(p); }
 };
+
+static cudaError_t scratch_get(tspcuda_ctx *c, int idx, size_t bytes, void **out) {
+    ScratchBuf &b = c->scratch[idx];
+    if (b.bytes < bytes) {
+        cudaFree(b.p);
+        b.p = nullptr; b.bytes = 0;
+        cudaError_t e = cudaMalloc(&b.p, bytes);
+        if (e != cudaSuccess) return e;
+        b.bytes = bytes;
+    }
+    *out = b.p;
+    return cudaSuccess;
+}
+static cudaError_t scratch_get(tspcuda_ctx *c, int idx, size_t bytes, DevBuf &buf) {
+    buf.owned = false;
+    return scratch_get(c, idx, bytes, &buf.p);
+}
 
 __global__ void order_to_path_kernel(const int *order, int n, int *path) {
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
@@ -638,10 +669,10 @@ extern "C" int tspcuda_tabu_search(tspcuda_ctx *c, int *path, double *cost_inout
         return TSPCUDA_OK;
     }
     DevBuf d_ten, d_trace, d_best, d_out;
-    CK(cudaMalloc(&d_ten.p, sizeof(int) * n_iters));
-    CK(cudaMalloc(&d_trace.p, sizeof(long long) * n_iters));
-    CK(cudaMalloc(&d_best.p, sizeof(int) * ((size_t)n + 1)));
-    CK(cudaMalloc(&d_out.p, sizeof(TabuOut)));
+    CK(scratch_get(c, SC_T_TEN, sizeof(int) * n_iters, d_ten));
+    CK(scratch_get(c, SC_T_TRACE, sizeof(long long) * n_iters, d_trace));
+    CK(scratch_get(c, SC_T_BEST, sizeof(int) * ((size_t)n + 1), d_best));
+    CK(scratch_get(c, SC_T_OUT, sizeof(TabuOut), d_out));
     CK(cudaMemcpyAsync(d_ten.p, tenures, sizeof(int) * n_iters, cudaMemcpyHostToDevice, c->stream));
     CK(cudaMemcpyAsync(c->d_tabu, tabu_list, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
     c->stats.h2d_bytes += (int64_t)sizeof(int) * ((int64_t)n + n_iters);
@@ -761,7 +792,6 @@ struct NNScratch {
     double2 *cxy = nullptr;
     int *cid = nullptr, *order = nullptr, *slot = nullptr;
     long long *cost = nullptr;
-    ~NNScratch() { cudaFree(cxy); cudaFree(cid); cudaFree(order); cudaFree(slot); cudaFree(cost); }
 };
 
 static int nn_batch(tspcuda_ctx *c, NNScratch &S, int first_start, int count, int stride, long long *h_cost) {
@@ -782,11 +812,11 @@ static int nn_batch(tspcuda_ctx *c, NNScratch &S, int first_start, int count, in
 
 static int nn_alloc(tspcuda_ctx *c, NNScratch &S, int batch) {
     const size_t n = (size_t)c->n;
-    CK(cudaMalloc(&S.cxy, sizeof(double2) * n * batch));
-    CK(cudaMalloc(&S.cid, sizeof(int) * n * batch));
-    CK(cudaMalloc(&S.order, sizeof(int) * n * batch));
-    CK(cudaMalloc(&S.cost, sizeof(long long) * batch));
-    if (nn_use_grid(c)) CK(cudaMalloc(&S.slot, sizeof(int) * n * batch));
+    CK(scratch_get(c, SC_NN_CXY, sizeof(double2) * n * batch, (void **)&S.cxy));          // the context's grow-only scratch
+    CK(scratch_get(c, SC_NN_CID, sizeof(int) * n * batch, (void **)&S.cid));
+    CK(scratch_get(c, SC_NN_ORDER, sizeof(int) * n * batch, (void **)&S.order));
+    CK(scratch_get(c, SC_NN_COST, sizeof(long long) * batch, (void **)&S.cost));
+    if (nn_use_grid(c)) CK(scratch_get(c, SC_NN_SLOT, sizeof(int) * n * batch, (void **)&S.slot));
     return TSPCUDA_OK;
 }
 
@@ -851,6 +881,26 @@ static cudaError_t launch_cta_descents(tspcuda_ctx *c, const int *d_order, int c
     return cudaGetLastError();
 }
 
+// TSPCUDA_VERBOSE: where a multi-start call spends its wall clock (allocation / NN / descents / release); declared first
+// in the function so that its destructor runs after the buffers' own
+struct PhaseClock {
+    bool on = getenv("TSPCUDA_VERBOSE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), tl = t0;
+    double alloc = 0, nn = 0, descents = 0, rest = 0;
+    void lap(double &acc) {
+        if (!on) return;
+        const auto t = std::chrono::steady_clock::now();
+        acc += std::chrono::duration<double>(t - tl).count();
+        tl = t;
+    }
+    ~PhaseClock() {
+        if (!on) return;
+        const double total = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        fprintf(stderr, "tspcuda: multistart %.3f s = alloc %.3f + NN %.3f + descents %.3f + copies %.3f + release %.3f\n", total, alloc, nn,
+                descents, rest, total - alloc - nn - descents - rest);
+    }
+};
+
 // K8 with clusters (a descent shared by 2/4/8 SMs): from this n up a scan is long enough for the cluster barriers not to
 // matter, and from this many starts up a batch beats descending them one after the other on the whole GPU (K7)
 constexpr int K8_CLUSTER_MIN_N = 8192;
@@ -859,6 +909,7 @@ constexpr int K8_CLUSTER_MIN_STARTS = 12;
 extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int nstarts, int stride, double *nn_costs_out,
                                           double *final_costs_out, int64_t *moves_out, int *best_start_out,
                                           int *best_path_out, double *best_cost_out) {
+    PhaseClock clk;
     int e = use(c);
     if (e) return e;
     const int n = c->n;
@@ -877,25 +928,25 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
     e = nn_alloc(c, S, batch);
     if (e) return e;
     DevBuf best_path, next, dcost, dmoves, dpaths;
-    CK(cudaMalloc(&best_path.p, sizeof(int) * n));
+    CK(scratch_get(c, SC_BEST_PATH, sizeof(int) * n, best_path));
     std::vector<long long> hc(batch), hf(batch), hm(batch);
     DevBuf m_pxy, m_tid, m_dn, m_pos, m_boxes, m_bpath, m_bcost, m_bstart, m_cand;
     MultiSlots MS{};
     const int mslots = multi_path ? std::min(batch, c->num_sms) : 0;
     if (multi_path) {
         const size_t n1 = (size_t)n + 1, sl = (size_t)mslots;
-        CK(cudaMalloc(&m_pxy.p, sizeof(double2) * n1 * sl));
-        CK(cudaMalloc(&m_tid.p, sizeof(int) * n1 * sl));
-        CK(cudaMalloc(&m_dn.p, sizeof(int) * n1 * sl));
-        CK(cudaMalloc(&m_pos.p, sizeof(int) * (size_t)n * sl));
-        CK(cudaMalloc(&m_boxes.p, sizeof(BigBox) * (size_t)n * sl));
-        CK(cudaMalloc(&m_bpath.p, sizeof(int) * (size_t)n * sl));
-        CK(cudaMalloc(&m_bcost.p, sizeof(long long) * sl));
-        CK(cudaMalloc(&m_bstart.p, sizeof(int) * sl));
-        CK(cudaMalloc(&m_cand.p, sizeof(unsigned long long)));
-        CK(cudaMalloc(&next.p, sizeof(int)));
-        CK(cudaMalloc(&dcost.p, sizeof(long long) * batch));
-        CK(cudaMalloc(&dmoves.p, sizeof(long long) * batch));
+        CK(scratch_get(c, SC_M_PXY, sizeof(double2) * n1 * sl, m_pxy));
+        CK(scratch_get(c, SC_M_TID, sizeof(int) * n1 * sl, m_tid));
+        CK(scratch_get(c, SC_M_DN, sizeof(int) * n1 * sl, m_dn));
+        CK(scratch_get(c, SC_M_POS, sizeof(int) * (size_t)n * sl, m_pos));
+        CK(scratch_get(c, SC_M_BOXES, sizeof(BigBox) * (size_t)n * sl, m_boxes));
+        CK(scratch_get(c, SC_M_BPATH, sizeof(int) * (size_t)n * sl, m_bpath));
+        CK(scratch_get(c, SC_M_BCOST, sizeof(long long) * sl, m_bcost));
+        CK(scratch_get(c, SC_M_BSTART, sizeof(int) * sl, m_bstart));
+        CK(scratch_get(c, SC_M_CAND, sizeof(unsigned long long), m_cand));
+        CK(scratch_get(c, SC_NEXT, sizeof(int), next));
+        CK(scratch_get(c, SC_DCOST, sizeof(long long) * batch, dcost));
+        CK(scratch_get(c, SC_DMOVES, sizeof(long long) * batch, dmoves));
         MS.pxy = m_pxy.as<double2>(); MS.tid = m_tid.as<int>(); MS.dn = m_dn.as<int>(); MS.pos = m_pos.as<int>();
         MS.boxes = m_boxes.as<BigBox>(); MS.best_path = m_bpath.as<int>(); MS.best_cost = m_bcost.as<long long>();
         MS.best_start = m_bstart.as<int>();
@@ -903,28 +954,59 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
     std::vector<long long> hbc(std::max(1, mslots));
     std::vector<int> hbs(std::max(1, mslots));
     if (cta_path) {
-        CK(cudaMalloc(&next.p, sizeof(int)));
-        CK(cudaMalloc(&dcost.p, sizeof(long long) * batch));
-        CK(cudaMalloc(&dmoves.p, sizeof(long long) * batch));
-        CK(cudaMalloc(&dpaths.p, sizeof(int) * (size_t)n * batch));
+        CK(scratch_get(c, SC_NEXT, sizeof(int), next));
+        CK(scratch_get(c, SC_DCOST, sizeof(long long) * batch, dcost));
+        CK(scratch_get(c, SC_DMOVES, sizeof(long long) * batch, dmoves));
+        CK(scratch_get(c, SC_DPATHS, sizeof(int) * (size_t)n * batch, dpaths));
     }
     long long best = -1;
     int best_start = -1;
+    clk.lap(clk.alloc);
     for (int done = 0; done < nstarts; done += batch) {
         const int cnt = std::min(batch, nstarts - done);
         const int fs = first_start + done * stride;
+        clk.lap(clk.rest);
         e = nn_batch(c, S, fs, cnt, stride, hc.data());
         if (e) return e;
+        clk.lap(clk.nn);
         if (multi_path) {
             CK(cudaMemsetAsync(next.p, 0, sizeof(int), c->stream));
             CK(cudaMemsetAsync(m_cand.p, 0, sizeof(unsigned long long), c->stream));
             CK(cudaEventRecord(c->ev0, c->stream));
             // fewer starts than SMs: a cluster of CL CTAs per descent (pruned.cuh), CL the largest of 8/4/2 that still
             // gives every start of the batch its own cluster
-            int cl = 1;
-            if (n >= K8_CLUSTER_MIN_N) while (cl < 8 && 2 * cl * cnt <= c->num_sms) cl *= 2;
-            if (const char *kc = getenv("TSPCUDA_K8_CLUSTER")) cl = std::max(1, std::min(8, atoi(kc)));
-            const int g = std::max(1, std::min(std::min(cnt, mslots), c->num_sms / cl));   // teams (clusters): one tour slot each, cl record-buffer sets
+            // a cluster occupies CL SMs of ONE GPC, so fewer than num_sms / CL clusters are co-resident (GPCs of 16-20 SMs):
+            // the count the driver reports decides, not the SM count (148 SMs: 37 clusters of 4 do not fit and the
+            // last one would start after the others have drained the queue)
+            if (!c->k8_clusters[0]) {
+                for (int k = 0, v = 1; k < 4; ++k, v *= 2) {
+                    cudaLaunchConfig_t q = {};
+                    q.gridDim = dim3(c->num_sms / v * v); q.blockDim = dim3(1024);
+                    cudaLaunchAttribute qa[1];
+                    qa[0].id = cudaLaunchAttributeClusterDimension;
+                    qa[0].val.clusterDim.x = v; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                    q.attrs = qa; q.numAttrs = 1;
+                    int nc = 0;
+                    cudaError_t qe = cudaSuccess;
+                    if (v == 8) { DISPATCH_METRIC(c->metric, (qe = cudaOccupancyMaxActiveClusters(&nc, multi_pruned_kernel<M, 1024, 8>, &q))); }
+                    else if (v == 4) { DISPATCH_METRIC(c->metric, (qe = cudaOccupancyMaxActiveClusters(&nc, multi_pruned_kernel<M, 1024, 4>, &q))); }
+                    else if (v == 2) { DISPATCH_METRIC(c->metric, (qe = cudaOccupancyMaxActiveClusters(&nc, multi_pruned_kernel<M, 1024, 2>, &q))); }
+                    else { DISPATCH_METRIC(c->metric, (qe = cudaOccupancyMaxActiveClusters(&nc, multi_pruned_kernel<M, 1024, 1>, &q))); }
+                    if (qe != cudaSuccess) { cudaGetLastError(); nc = 0; }
+                    c->k8_clusters[k] = std::max(1, std::min(nc, c->num_sms / v));
+                }
+                if (getenv("TSPCUDA_VERBOSE"))
+                    fprintf(stderr, "tspcuda: co-resident K8 clusters of 1/2/4/8 CTAs: %d %d %d %d\n", c->k8_clusters[0], c->k8_clusters[1],
+                            c->k8_clusters[2], c->k8_clusters[3]);
+            }
+            int cl = 1, ck = 0;
+            if (n >= K8_CLUSTER_MIN_N) while (cl < 8 && cnt <= c->k8_clusters[ck + 1]) { cl *= 2; ++ck; }
+            if (const char *kc = getenv("TSPCUDA_K8_CLUSTER")) {
+                cl = std::max(1, std::min(8, atoi(kc)));
+                ck = cl >= 8 ? 3 : cl >= 4 ? 2 : cl >= 2 ? 1 : 0;
+                cl = 1 << ck;
+            }
+            const int g = std::max(1, std::min(std::min(cnt, mslots), c->k8_clusters[ck]));   // teams (clusters): one tour slot each, cl record-buffer sets
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(g * cl); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
             cudaLaunchAttribute attr[1];
@@ -949,6 +1031,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
             CK(cudaMemcpyAsync(hbs.data(), m_bstart.p, sizeof(int) * g, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(&hcand, m_cand.p, sizeof(hcand), cudaMemcpyDeviceToHost, c->stream));
             CK(cudaStreamSynchronize(c->stream));
+            clk.lap(clk.descents);
             c->stats.d2h_bytes += (int64_t)sizeof(long long) * 2 * cnt + 12 * g + 8;
             float ms = 0;
             CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
@@ -1029,6 +1112,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
         c->stats.d2h_bytes += (int64_t)sizeof(int) * n;
     }
     CK(cudaStreamSynchronize(c->stream));
+    clk.lap(clk.rest);
     if (best_start_out) *best_start_out = best_start;
     if (best_cost_out) *best_cost_out = (double)best;
     return TSPCUDA_OK;
