@@ -178,7 +178,9 @@ int tspcuda_tour_movelog(tspcuda_ctx *ctx, tspcuda_move *log, int64_t cap, int64
 /* ---- multi-start NN + 2-opt (heuristics.c:74-116) ------------------------------------------- */
 /* Starts first_start + k*stride.  Per-start NN costs, final costs and move counts (any may be
  * NULL); best tour under the reference's incumbent rule (strict '<', tsp.c:671, ascending start
- * order => lowest start wins ties). */
+ * order => lowest start wins ties).  The device scratch of a batch (28 n bytes per start of a batch of
+ * at most 16 x #SMs starts, 64 n bytes per concurrent descent, at most #SMs) is kept in the
+ * context for later calls and released by tspcuda_destroy. */
 int tspcuda_multistart_two_opt(tspcuda_ctx *ctx, int first_start, int nstarts, int stride, double *nn_costs_out,
                                double *final_costs_out, int64_t *moves_out, int *best_start_out,
                                int *best_path_out, double *best_cost_out);
