@@ -1,0 +1,192 @@
+"""GPU parity tests (-m gpu) at the north_star's OWN sizes -- the configs of BASELINE.json that the small-instance
+tests of test_gpu_parity.py only reach through timing runs:
+
+  config 3 / 4   usa13509 (non-integer coordinates, EucGeneral) and pla85900 through the MULTI-START kernels
+                 (K4b batched NN + K8 multi_pruned_kernel, one CTA or a cluster of 2/4/8 CTAs per descent), start by
+                 start against nn + two_opt on the whole GPU (K7), the reference-run golden of start 0 and the CPU
+                 oracle's move audit (refinment.c:39-93, heuristics.c:74-116)
+  config 5       d15112 and the reference's `-n 20000 -seed 123` instance: full NN(0) descents against
+                 tests/golden/golden_large.json (oracle pinned on the reference objects, tests/golden/make_golden_large.py),
+                 64 tabu iterations and 6 VNS iterations from that local optimum against the golden traces AND against
+                 the oracle run live (metaheuristic.c:188-245, :277-321)
+Bar: bit-exact successor arrays, identical move counts / cost traces."""
+import ctypes
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle.bindings import fnv1a, load_instance
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def large():
+    with open(os.path.join(HERE, "golden", "golden_large.json")) as f:
+        g = json.load(f)
+    tours = np.load(os.path.join(HERE, "golden", "large_tours.npz"))
+    return g, {k: np.ascontiguousarray(tours[k], dtype=np.int32) for k in tours.files}
+
+
+def _xy(oracle, name):
+    return oracle.random_points(20000, 123) if name == "rand20000" else load_instance(name)[0]
+
+
+def _k7_reference(tsp, xy, starts, log_for=None):
+    """nn + two_opt per start on the whole GPU (library default: K4b/K4 + K7): {start: (nn_cost, moves, cost, path, log)}."""
+    out = {}
+    with tsp.Instance(xy) as I:
+        for s in starts:
+            code, p, c = I.nn(s)
+            assert code == 0
+            cap = 16384 if s == log_for else 0
+            code, mv, p2, c2, log = I.two_opt(p, log_cap=cap)
+            assert code == 0
+            out[s] = (c, mv, c2, p2, log, p)
+    return out
+
+
+def _multistart_modes(tsp, monkeypatch, xy, starts_spec, ref, modes):
+    """tspcuda_multistart_two_opt under every TSPCUDA_K8_CLUSTER mode: per-start (nn cost, moves, final cost) and the best
+    tour against the K7 results; then every start alone (so that each start's TOUR is compared, not only the best one)."""
+    first, count, stride = starts_spec
+    starts = [first + k * stride for k in range(count)]
+    best = min(starts, key=lambda s: (ref[s][2], s))
+    for cl in modes:
+        monkeypatch.setenv("TSPCUDA_K8_CLUSTER", str(cl))
+        with tsp.Instance(xy) as I:
+            bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(first, count, stride)
+            st = I.stats()
+        assert st["pruned_scans"] == int(moves.sum()) + count, cl          # K8 answered every scan
+        assert [(a, int(m), f) for a, m, f in zip(nn_costs, moves, final)] == [ref[s][:3] for s in starts], cl
+        assert (bs, bc) == (best, ref[best][2]) and np.array_equal(bp, ref[best][3]), cl
+    monkeypatch.setenv("TSPCUDA_K8_CLUSTER", str(modes[-1]))
+    with tsp.Instance(xy) as I:
+        for s in starts:
+            bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(s, 1, 1)
+            assert (bs, nn_costs[0], int(moves[0]), bc) == (s, ref[s][0], ref[s][1], ref[s][2]), s
+            assert np.array_equal(bp, ref[s][3]), s
+
+
+def test_pla85900_multistart_kernels(tsp, oracle, monkeypatch):
+    """Config 4's own kernels at config-4 size: starts 0, 24, 48 of pla85900 through K4b + K8 under cluster sizes 1/2/4/8.
+    Start 0 = 5589 moves -> 148543747 (the full-scan descent of bench.py / profiles/r01_bench_first.json); start 24 is
+    audited by the oracle: every logged delta re-derived, full CPU scans at sampled iterations, final local optimality."""
+    xy, _ = load_instance("pla85900")
+    ref = _k7_reference(tsp, xy, (0, 24, 48), log_for=24)
+    assert (ref[0][1], int(ref[0][2])) == (5589, 148543747)
+    c, mv, c2, p2, log, p = ref[24]
+    assert len(log) == mv
+    la = [x[0] for x in log]; lb = [x[1] for x in log]; ld = [float(x[2]) for x in log]
+    r, pend = oracle.audit_moves(xy, p, la, lb, ld, [0, mv // 2, mv - 1])
+    assert r == 0 and np.array_equal(pend, p2)
+    d, a, b = oracle.two_opt_scan(xy, p2)
+    assert d >= -1e-7
+    _multistart_modes(tsp, monkeypatch, xy, (0, 3, 24), ref, (1, 2, 4, 8))
+
+
+def test_usa13509_multistart_kernels(tsp, oracle, golden, monkeypatch):
+    """Config 3's instance (13 337 of 13 509 nodes carry decimals: EucGeneral, where an FMA contraction would change
+    costs) through K4b + K8 and the clusters.  Start 0 = the reference objects' own run: 1983 moves -> 21119812."""
+    xy, _ = load_instance("usa13509")
+    assert np.any(xy != np.floor(xy))
+    ref = _k7_reference(tsp, xy, (0, 7, 14, 21, 28))
+    s = golden["usa13509"]["nn0_2opt_survey"]
+    assert (ref[0][1], int(ref[0][2])) == (s["moves"], s["cost"]) and int(ref[0][0]) == golden["usa13509"]["nn0"]["cost"]
+    for st_ in (7, 28):                                       # two more starts against the oracle's own NN tour + cost recomputation
+        e, po, co = oracle.nn(xy, st_)
+        assert co == ref[st_][0] and np.array_equal(po, ref[st_][5])
+        assert oracle.is_tour(ref[st_][3]) and oracle.tour_cost(xy, ref[st_][3]) == ref[st_][2]
+    _multistart_modes(tsp, monkeypatch, xy, (0, 5, 7), ref, (1, 2, 4, 8))
+    monkeypatch.delenv("TSPCUDA_K8_CLUSTER")
+    with tsp.Instance(xy) as I:                               # library default for a batch of this size (>= 12 starts: clusters)
+        bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(0, 15, 2)
+    for s_ in (0, 14, 28):
+        k = s_ // 2
+        assert (nn_costs[k], int(moves[k]), final[k]) == ref[s_][:3]
+
+
+@pytest.mark.parametrize("name", ["d15112", "rand20000"])
+@pytest.mark.parametrize("scan", ["full", "pruned", "auto"])
+def test_config5_full_descent_golden(tsp, oracle, large, name, scan):
+    """NN(0) -> 2-opt local optimum at the config-5 sizes against the pinned oracle's run (d15112: 2060 moves -> 1659198;
+    reference objects: NN(0) and the first 20 moves of the same descent, tests/golden/golden.json)."""
+    g, tours = large
+    xy = _xy(oracle, name)
+    with tsp.Instance(xy) as I:
+        I.set_scan_mode({"auto": tsp.SCAN_AUTO, "full": tsp.SCAN_FULL, "pruned": tsp.SCAN_PRUNED}[scan])
+        code, p, c = I.nn(0)
+        assert (int(c), fnv1a(p)) == (g[name]["nn0"]["cost"], g[name]["nn0"]["hash"])
+        code, moves, p2, c2, log = I.two_opt(p, log_cap=8)
+    e = g[name]["nn0_2opt"]
+    assert (moves, int(c2), fnv1a(p2)) == (e["moves"], e["cost"], e["hash"])
+    assert np.array_equal(p2, tours[name])
+
+
+@pytest.mark.parametrize("name", ["d15112", "rand20000"])
+def test_config5_tabu_vs_oracle(tsp, oracle, large, name):
+    """64 iterations of the tabu loop (linear tenure, metaheuristic.c:40-59) from the local optimum, at config-5 size: the
+    device-resident loop (K5c pruned scan + K5b fallback) and the per-call path against the golden trace and against the
+    oracle's tabu_best_move run live (tour and tabu list compared after every 16th iteration and at the end)."""
+    g, tours = large
+    xy = _xy(oracle, name)
+    n = xy.shape[0]
+    p0, c0 = tours[name], float(g[name]["nn0_2opt"]["cost"])
+    K = g[name]["tabu"]["iters"]
+    tenure, lo, hi = oracle.tabu_init(n)
+    inc, tenures = True, []
+    for _ in range(K):
+        tenure, inc = oracle.tabu_linear_step(tenure, lo, hi, inc)
+        tenures.append(tenure)
+    po, co, to, trace_o, snaps = p0.copy(), c0, np.full(n, -1, dtype=np.int32), [], {}
+    for k, t in enumerate(tenures):
+        co, a, b, d = oracle.tabu_move(xy, po, co, to, t, k)
+        trace_o.append(int(co))
+        if k % 16 == 15:
+            snaps[k] = (po.copy(), to.copy())
+    assert trace_o == g[name]["tabu"]["trace"] and fnv1a(po) == g[name]["tabu"]["hash"] and fnv1a(to) == g[name]["tabu"]["tabu_list_hash"]
+    for mode in (tsp.SCAN_AUTO, tsp.SCAN_FULL):
+        with tsp.Instance(xy) as I:
+            I.set_scan_mode(mode)
+            pg, tg, cg, trace_g = p0.copy(), np.full(n, -1, dtype=np.int32), c0, []
+            for k0 in range(0, K, 16):                      # four device-resident runs of 16 iterations (first_iter continues)
+                cg, tr, bi, bp, bc = I.tabu_search(pg, cg, tg, tenures[k0:k0 + 16], first_iter=k0, incumbent_cost=c0)
+                trace_g += [int(x) for x in tr]
+                assert np.array_equal(pg, snaps[k0 + 15][0]) and np.array_equal(tg, snaps[k0 + 15][1]), (mode, k0)
+            st = I.stats()
+        assert trace_g == trace_o
+        assert (st["pruned_scans"] > 0) == (mode == tsp.SCAN_AUTO)
+    with tsp.Instance(xy) as I:                             # per-call path: tabu_best_move, host tour in and out
+        pg, tg, cg = p0.copy(), np.full(n, -1, dtype=np.int32), c0
+        for k, t in enumerate(tenures[:8]):
+            cg, mv = I.tabu_move(pg, cg, tg, t, k)
+            assert int(cg) == trace_o[k]
+
+
+@pytest.mark.parametrize("name", ["d15112", "rand20000"])
+def test_config5_vns_vs_oracle(tsp, oracle, large, name):
+    """6 iterations of the loop of mh_VNS (metaheuristic.c:277-321: descent, incumbent test, rand() % 9 - 2 kicks) from the
+    local optimum at config-5 size, glibc stream seeded: tspcuda_vns_search against the golden trace and the oracle's loop."""
+    g, tours = large
+    xy = _xy(oracle, name)
+    libc = ctypes.CDLL(None)
+    v = g[name]["vns"]
+    p0, c0 = tours[name], float(g[name]["nn0_2opt"]["cost"])
+    libc.srand(v["seed"])
+    po, trace_o, moves_o = p0.copy(), [], []
+    for i in range(v["iters"]):
+        m, po, co, *_ = oracle.two_opt(xy, po, log=False)
+        trace_o.append(int(co)); moves_o.append(int(m))
+        for _ in range(libc.rand() % 9 - 2):
+            oracle.vns_kick(po)
+    assert (trace_o, moves_o, fnv1a(po)) == (v["trace"], v["moves"], v["hash"])
+    libc.srand(v["seed"])
+    with tsp.Instance(xy) as I:
+        code, pg, cg, tr, bi, bp, bc, done = I.vns_search(p0, v["iters"], c0)
+        st = I.stats()
+    assert code == 0 and done == v["iters"] and [int(x) for x in tr] == trace_o and np.array_equal(pg, po)
+    assert st["moves"] == sum(moves_o)
+    assert (bi, int(bc)) == (v["best_iter"], v["best_cost"])

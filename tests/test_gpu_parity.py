@@ -510,10 +510,11 @@ def test_multistart_cta_paths_vs_grid_path(tsp, oracle, scan):
     scan, any n, used from num_sms/4 starts up) and the grid-wide descent kernels must produce the same
     tours: compare multistart with nn + two_opt start by start, and one start of each size with the
     CPU oracle."""
-    for n, starts in ((130, 6), (1500, 4), (3700, 3), (900, 60), (9000, 40)):
-        if scan == "full" and n == 9000:
+    for n, starts, integer in ((130, 6, True), (131, 6, False), (1500, 4, False), (3700, 3, True), (900, 60, False), (901, 60, True),
+                               (9000, 40, False), (9001, 40, True)):
+        if scan == "full" and n >= 9000:
             continue
-        xy = _rand_xy(900 + n, n, n % 2 == 0)
+        xy = _rand_xy(900 + n, n, integer)                  # integer: EucInt kernels, otherwise EucGeneral (no FMA contraction)
         with _inst(tsp, xy, scan) as I:
             bs, bp, bc, nn_costs, final, moves = I.multistart_two_opt(2, starts, 5)
             per = []
@@ -530,13 +531,13 @@ def test_multistart_cta_paths_vs_grid_path(tsp, oracle, scan):
         assert (co, m_o, c_o) == per[0][:3] and np.array_equal(p_o, per[0][3])
 
 
-@pytest.mark.parametrize("n,starts", [(700, 5), (8500, 9)])
-def test_multistart_cluster_sizes_agree(tsp, oracle, monkeypatch, n, starts):
+@pytest.mark.parametrize("n,starts,integer", [(700, 5, True), (700, 5, False), (8500, 9, True), (8500, 9, False)])
+def test_multistart_cluster_sizes_agree(tsp, oracle, monkeypatch, n, starts, integer):
     """K8 with a thread-block cluster per descent (2/4/8 SMs share one descent, pruned.cuh) against one CTA per
     descent (1) and against K7 with one start after the other (0): same per-start costs, move counts and
     best tour; the first start additionally against the CPU oracle.  n = 700: scans of a few microseconds,
     i.e. the cluster barriers and the per-CTA argmin keys under the tightest timing."""
-    xy = _rand_xy(4100 + n, n, True)
+    xy = _rand_xy(4100 + n, n, integer)
     ref = None
     for cl in (0, 1, 2, 4, 8):
         monkeypatch.setenv("TSPCUDA_K8_CLUSTER", str(cl))
