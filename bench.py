@@ -195,8 +195,7 @@ def main():
         torch.cuda.synchronize()
 
     import travellingsalesmanoptimization_b200 as T
-    from oracle.bindings import load_instance          # instance fixtures only (data, not the oracle)
-    xy, _ = load_instance(args.workload)
+    xy, _ = T.load_instance(args.workload)
     n = xy.shape[0]
     pairs_per_scan = n * (n - 1) // 2
     K, W, MOVES = args.steps, max(3, args.warmup), args.moves_per_step

@@ -22,6 +22,7 @@
  *   tspcuda_mx_nn / _two_opt      h_greedyutil / ref_2opt on a caller's matrix (h_Greedy_2opt_mod_costs, heuristics.c:118-149)
  *   tspcuda_vns_search            mh_VNS loop (ref_2opt + vns_kick)              algorithms/metaheuristic.c:277-321, :344-409
  *   tspcuda_patching              cx_patching (+ its while (ncomp > 1) loop)   algorithms/cplex_model.c:693-755, :205-212
+ *   tspcuda_restarts / _mgpu_*    no counterpart: independent tabu / VNS runs from different start nodes (BASELINE.json configs[4])
  *
  * Tours cross the boundary exactly as the reference stores them: a successor array int path[n],
  * path[i] = node visited after node i (src/utils/utils.h:42-47).  Costs are doubles holding
@@ -109,9 +110,12 @@ int tspcuda_cost_matrix_checksum(tspcuda_ctx *ctx, int64_t *sum_out);
 int tspcuda_nn(tspcuda_ctx *ctx, int start, int *path_out, double *cost_out);
 /* Starts first_start + k*stride, k in [0,nstarts): per-start costs, and the best tour with the
  * reference's tie rule (strict '<' in ascending start order => lowest start wins, heuristics.c:58).
- * costs_out / best_path_out may be NULL. */
-int tspcuda_nn_multi(tspcuda_ctx *ctx, int first_start, int nstarts, int stride, double *costs_out,
-                     int *best_start_out, int *best_path_out, double *best_cost_out);
+ * time_limit_s < 0: none.  Otherwise seconds from the call: the clock is looked at before starts are taken, as the
+ * reference does before every start (heuristics.c:42-50); once it has passed no further start is taken and the call
+ * returns TSPCUDA_DEADLINE_EXCEEDED with the best of the PREFIX of starts it got to (*starts_done_out of them, in
+ * ascending order; *best_start_out = -1 if none).  costs_out / best_path_out / starts_done_out may be NULL. */
+int tspcuda_nn_multi(tspcuda_ctx *ctx, int first_start, int nstarts, int stride, double time_limit_s, double *costs_out,
+                     int *best_start_out, int *best_path_out, double *best_cost_out, int *starts_done_out);
 
 /* ---- 2-opt (refinment.c) --------------------------------------------------------------------- */
 /* Host tour in, host tour out.  Recomputes the cost (refinment.c:6-9), then repeats
@@ -139,7 +143,11 @@ int tspcuda_tabu_move(tspcuda_ctx *ctx, int *path, double *cost_inout, int *tabu
  * results/TabuResults.dat column).  The incumbent rule of tsp_update_best_solution (strict '<',
  * tsp.c:671) is applied on the device against incumbent_cost: if some iteration improves on it,
  * *best_iter_out is the last such iteration (-1 otherwise) and best_path_out / *best_cost_out hold
- * that tour.  Any output pointer except path, cost_inout and tabu_list may be NULL. */
+ * that tour.  Any output pointer except path, cost_inout and tabu_list may be NULL.
+ * incumbent_cost: any value >= 9e18, +infinity and the reference's own "no incumbent yet" DBL_MAX (tsp.c:37) mean that
+ * every cost is an improvement; NaN (and a non-finite *cost_inout) is TSPCUDA_INVALID_ARGUMENT.
+ * Scans: the exact candidate-pruned scan with a bound (K5c, n >= 4096) while it finds an admissible pair, the full scan
+ * (K5b) otherwise and always under TSPCUDA_SCAN_FULL -- identical traces either way. */
 int tspcuda_tabu_search(tspcuda_ctx *ctx, int *path, double *cost_inout, int *tabu_list, const int *tenures,
                         int first_iter, int n_iters, double incumbent_cost, double *cost_trace_out,
                         int *best_path_out, double *best_cost_out, int *best_iter_out);
@@ -163,8 +171,9 @@ int tspcuda_vns_search(tspcuda_ctx *ctx, int *path, double *cost_inout, int n_it
 /* How 2-opt descents scan the neighbourhood.  FULL evaluates all n(n-1)/2 pairs per scan, as the
  * reference does (refinment.c:49-69).  PRUNED evaluates only the pairs that can improve the tour
  * (found by fixed-radius searches over a grid of the nodes, csrc/pruned.cuh) and provably returns
- * the same move, ties included.  AUTO (default) measures both and uses the faster one.  The tabu
- * scan (best admissible move, even worsening) always uses FULL.  Environment: TSPCUDA_SCAN=full|pruned. */
+ * the same move, ties included.  AUTO (default) measures both and uses the faster one.  The per-call tabu
+ * move (tspcuda_tabu_move: best admissible move, even worsening) always uses FULL; the device-resident tabu loop
+ * uses a bounded pruned scan where it can (see tspcuda_tabu_search).  Environment: TSPCUDA_SCAN=full|pruned. */
 enum { TSPCUDA_SCAN_AUTO = 0, TSPCUDA_SCAN_FULL = 1, TSPCUDA_SCAN_PRUNED = 2 };
 int tspcuda_set_scan_mode(tspcuda_ctx *ctx, int mode);
 
@@ -179,11 +188,32 @@ int tspcuda_tour_movelog(tspcuda_ctx *ctx, tspcuda_move *log, int64_t cap, int64
 /* Starts first_start + k*stride.  Per-start NN costs, final costs and move counts (any may be
  * NULL); best tour under the reference's incumbent rule (strict '<', tsp.c:671, ascending start
  * order => lowest start wins ties).  The device scratch of a batch (28 n bytes per start of a batch of
- * at most 16 x #SMs starts, 64 n bytes per concurrent descent, at most #SMs) is kept in the
- * context for later calls and released by tspcuda_destroy. */
-int tspcuda_multistart_two_opt(tspcuda_ctx *ctx, int first_start, int nstarts, int stride, double *nn_costs_out,
-                               double *final_costs_out, int64_t *moves_out, int *best_start_out,
-                               int *best_path_out, double *best_cost_out);
+ * at most 16 x #SMs starts, 192 n bytes per concurrent descent, at most #SMs) is kept in the
+ * context for later calls and released by tspcuda_destroy.
+ * time_limit_s < 0: none.  Otherwise seconds from the call, with the reference's semantics (heuristics.c:83-90,
+ * refinment.c:17-24): the limit is looked at before a start is taken and before every scan of a descent; once it has
+ * passed no further start is taken (starts are handed out in ascending order, so the ones taken are a prefix:
+ * *starts_done_out of them), descents in flight stop where they are and their tours still compete for the incumbent
+ * (as ref_2opt's update_incumbent does after DEADLINE_EXCEEDED), and the call returns TSPCUDA_DEADLINE_EXCEEDED.
+ * Entries of final_costs_out / moves_out for starts never taken are -1; *best_start_out = -1 if none was. */
+int tspcuda_multistart_two_opt(tspcuda_ctx *ctx, int first_start, int nstarts, int stride, double time_limit_s,
+                               double *nn_costs_out, double *final_costs_out, int64_t *moves_out, int *best_start_out,
+                               int *best_path_out, double *best_cost_out, int *starts_done_out);
+
+/* ---- tabu / VNS restarts (BASELINE.json configs[4]; a framework addition: the reference runs one trajectory) ---- */
+/* Restart r = start node first_start + r*stride, an independent unit:
+ *   TSPCUDA_RESTART_TABU  NN(start) -> 2-opt local optimum (ref_2opt) -> `iters` iterations of the loop of mh_TabuSearch
+ *                         (metaheuristic.c:128-164) with the default linear tenure schedule (tabu_init :65-84,
+ *                         tabu_linear_policy :40-59); result = the best tour seen, local optimum included
+ *   TSPCUDA_RESTART_VNS   NN(start) -> `iters` iterations of the loop of mh_VNS (metaheuristic.c:277-321); the kicks
+ *                         draw from a generator private to the restart that yields the sequence srand(seed + start)
+ *                         gives the process stream (glibc random_r), so restarts are reproducible whatever thread or
+ *                         GPU runs them; result = the best local optimum seen
+ * Best over the restarts under the incumbent rule (strict '<' in ascending start order).  time_limit_s as above:
+ * TSPCUDA_DEADLINE_EXCEEDED with the best of the restarts it got to (*restarts_done_out, the last possibly cut short). */
+enum { TSPCUDA_RESTART_TABU = 0, TSPCUDA_RESTART_VNS = 1 };
+int tspcuda_restarts(tspcuda_ctx *ctx, int kind, int first_start, int nstarts, int stride, int iters, unsigned seed,
+                     double time_limit_s, int *best_start_out, int *best_path_out, double *best_cost_out, int *restarts_done_out);
 
 /* ---- Extra Mileage (heuristics.c:156-210 h_ExtraMileage, :290-367 h_extramileage_util) ---------- */
 /* node_a < 0: the EM_MAX initial edge (first pair i<j with the strictly largest cost, :169-178), else the
@@ -221,6 +251,9 @@ typedef struct {
 } tspcuda_move_f;
 int tspcuda_mx_create(tspcuda_mx **out, const double *costs, int n, int device);
 void tspcuda_mx_destroy(tspcuda_mx *mx);
+/* Replaces the matrix of an existing context (same n) without re-allocating anything: for callers that receive a
+ * fresh matrix per call (the relaxation callback, cplex_model.c:1187-1217, thousands of calls per run). */
+int tspcuda_mx_update(tspcuda_mx *mx, const double *costs);
 int tspcuda_mx_get_stats(tspcuda_mx *mx, tspcuda_stats *out);
 /* *len_out (may be NULL): nodes reached; < n when NOT_CONNECTED entries close the path early. */
 int tspcuda_mx_nn(tspcuda_mx *mx, int start, int *path_out, double *cost_out, int *len_out);
@@ -243,9 +276,16 @@ int tspcuda_mgpu_ndev(const tspcuda_mgpu *m);
 /* two_opt = 0: all-start nearest neighbour (h_Greedy_iterative, heuristics.c:34-72); 1: NN + 2-opt per start
  * (h_greedy_2opt, :74-116).  Starts first_start + k*stride, k in [0,nstarts).  Same results as the single-GPU calls
  * tspcuda_nn_multi / tspcuda_multistart_two_opt.  *compute_ms_out / *reduce_ms_out (may be NULL): wall time of the
- * slowest shard and of the incumbent reduction (max over GPUs). */
-int tspcuda_mgpu_multistart(tspcuda_mgpu *m, int two_opt, int first_start, int nstarts, int stride, int *best_start_out,
-                            int *best_path_out, double *best_cost_out, double *compute_ms_out, double *reduce_ms_out);
+ * slowest shard and of the incumbent reduction (max over GPUs).  time_limit_s: every GPU works against the same limit
+ * on its own shard (see the single-GPU calls); TSPCUDA_DEADLINE_EXCEEDED then comes with the best over the prefixes of
+ * the shards, *starts_done_out = starts taken over all GPUs, *best_start_out = -1 if none was. */
+int tspcuda_mgpu_multistart(tspcuda_mgpu *m, int two_opt, int first_start, int nstarts, int stride, double time_limit_s,
+                            int *best_start_out, int *best_path_out, double *best_cost_out, int *starts_done_out,
+                            double *compute_ms_out, double *reduce_ms_out);
+/* tspcuda_restarts sharded the same way (restart r on GPU r mod G), same reduction. */
+int tspcuda_mgpu_restarts(tspcuda_mgpu *m, int kind, int first_start, int nstarts, int stride, int iters, unsigned seed,
+                          double time_limit_s, int *best_start_out, int *best_path_out, double *best_cost_out,
+                          int *restarts_done_out, double *compute_ms_out, double *reduce_ms_out);
 
 /* ---- measurement helpers -------------------------------------------------------------------- */
 /* CUDA-event bracket on the stream every kernel of this context is launched on (torch.cuda.Event

@@ -30,7 +30,7 @@ def write_tsplib(path, name, xy, ewt="EUC_2D"):
 def workdir(tmp_path_factory):
     d = tmp_path_factory.mktemp("driver")
     os.makedirs(d / "results")          # metaheuristic.c:97,275 write results/*.dat relative to cwd
-    for name in ["berlin52", "kroA100", "rl1304", "usa13509"]:
+    for name in ["berlin52", "kroA100", "rl1304", "pr2392", "usa13509"]:
         xy, _ = load_instance(name)
         write_tsplib(d / (name + ".tsp"), name, xy)
     for name in ["att48", "att532", "dsj1000", "burma14"]:       # ATT, ATT, CEIL_2D, GEO headers
@@ -109,6 +109,64 @@ def test_berlin52_cli_golden(workdir, alg, extra, cost):
         r0 = run_cli(TSP_GPU, workdir, ["-f", "berlin52.tsp", "-q", "-alg", alg], {"TSPCUDA_BATCH": "0"})
         c0 = calls(r0.stderr)
         assert r0.stdout == r.stdout and c0["h_extramileage_util"] == 1 and c0["h_ExtraMileage"] == 0
+
+
+def test_mislink_is_fatal(workdir):
+    """a mis-link must not masquerade as a pass.  With the reference objects AHEAD of the interposer in the
+    lookup order, ref_2opt_once resolves into libtspref.so -- every "GPU" result would be the reference's CPU code -- and
+    the interposer's load-time self-check ends the process; TSPCUDA_ALLOW_MISLINK=1 downgrades that to a warning."""
+    import sys
+    ref = os.path.join(ROOT, "build", "ref", "libtspref.so")
+    itp = os.path.join(ROOT, "travellingsalesmanoptimization_b200", "libtspcuda_interpose.so")
+    if not (os.path.exists(ref) and os.path.exists(itp)):
+        pytest.skip("drop-in artefacts not built (needs /root/reference at build time)")
+    code = ("import ctypes; ctypes.CDLL(%r, mode=ctypes.RTLD_GLOBAL); ctypes.CDLL(%r, mode=ctypes.RTLD_GLOBAL); print('survived')" % (ref, itp))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 70 and "survived" not in r.stdout and "FATAL" in r.stderr and "NOT active" in r.stderr
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, env=dict(os.environ, TSPCUDA_ALLOW_MISLINK="1"))
+    assert r.returncode == 0 and "survived" in r.stdout and "WARNING" in r.stderr
+    # the right order (what build/bin/tsp links): the check is silent (with or without a GPU)
+    r = run_cli(TSP_GPU, workdir, ["-f", "berlin52.tsp", "-alg", "GREEDY", "-q"], check=False)
+    assert "NOT active" not in r.stderr and r.returncode != 70
+
+
+def test_cli_does_not_link_the_oracle_directory():
+    """The product binary is the unchanged reference driver + the interposer + libtspcuda; nothing of it may come from
+    oracle/ (test infrastructure)."""
+    if not os.path.exists(TSP_GPU):
+        pytest.skip("build/bin/tsp not built (needs /root/reference at build time)")
+    out = subprocess.run(["readelf", "-d", TSP_GPU], capture_output=True, text=True).stdout
+    assert "oracle" not in out and "libtspcuda_interpose.so" in out and "libtspref.so" in out
+
+
+@pytest.mark.gpu
+def test_time_limit_keeps_the_batched_paths(workdir, golden):
+    """The reference's own tooling always passes -t 600 (scripts/compare_algs.py:18,67).  The limit is honoured INSIDE the
+    batched calls, so the whole-loop overrides stay active: config 2 (pr2392, all 2392 starts) under -t 600 gives the
+    golden 393339 with h_greedy_2opt = 1 and no per-start helper call."""
+    r = run_cli(TSP_GPU, workdir, ["-f", "pr2392.tsp", "-alg", "2OPT_GREEDY", "-t", "600", "-q"])
+    assert r.stdout.strip() == "Cost: %d.00" % golden["pr2392"]["greedy_2opt_survey"]["cost"]
+    c = calls(r.stderr)
+    assert c["h_greedy_2opt"] == 1 and c["h_greedyutil"] == 0 and c["ref_2opt"] == 0
+    r = run_cli(TSP_GPU, workdir, ["-f", "pr2392.tsp", "-alg", "GREEDY_ITER", "-t", "600", "-q"])
+    assert r.stdout.strip() == "Cost: %d.00" % golden["pr2392"]["allnn"]["cost"] and calls(r.stderr)["h_Greedy_iterative"] == 1
+
+
+@pytest.mark.gpu
+def test_time_limit_cuts_a_batch_short(workdir, golden):
+    """-t 1 on usa13509's all-start NN + 2-opt (13 509 descents; the driver's clock starts after the instance is read,
+    main.c:177): the call comes back at the limit with a VALID tour -- the best over the prefix of starts reached, descents in
+    flight cut where they were (heuristics.c:83-90, refinment.c:17-24,29-34) -- and the driver prints its cost and exits 0,
+    as the reference does after DEADLINE_EXCEEDED (main.c:180).  (The exact semantics are tested through the C ABI in
+    test_gpu_northstar.py::test_multistart_time_limit.)"""
+    import time
+    t0 = time.perf_counter()
+    r = run_cli(TSP_GPU, workdir, ["-f", "usa13509.tsp", "-alg", "2OPT_GREEDY", "-t", "1", "-q"], {"TSPCUDA_MATRIX": "off"})
+    wall = time.perf_counter() - t0
+    assert calls(r.stderr)["h_greedy_2opt"] == 1
+    cost = float(r.stdout.strip().split()[1])
+    assert 19.9e6 < cost < golden["usa13509"]["nn0"]["cost"]           # 2-opt tours: below NN(0), above the optimum 19 982 859
+    assert wall < 40.0                                                  # the whole job would take far longer than the limit
 
 
 @pytest.mark.gpu

@@ -190,3 +190,60 @@ def test_config5_vns_vs_oracle(tsp, oracle, large, name):
     assert code == 0 and done == v["iters"] and [int(x) for x in tr] == trace_o and np.array_equal(pg, po)
     assert st["moves"] == sum(moves_o)
     assert (bi, int(bc)) == (v["best_iter"], v["best_cost"])
+
+
+def test_multistart_time_limit(tsp, oracle):
+    """time_limit_s inside the batched multi-start (heuristics.c:83-90, refinment.c:17-24): a limit that cannot be met returns
+    DEADLINE_EXCEEDED with the best over the PREFIX of starts handed out -- complete descents equal their unlimited runs,
+    cut ones hold valid, partially descended tours; a generous limit changes nothing; a limit of 0 takes no start."""
+    xy, _ = load_instance("usa13509")
+    with tsp.Instance(xy) as I:
+        bs0, bp0, bc0, nn0, fin0, mv0 = I.multistart_two_opt(0, 296)                      # unlimited reference run
+        code, done, bs, bp, bc, nn, fin, mv = I.multistart_two_opt(0, 296, time_limit=600.0)
+        assert code == 0 and done == 296 and (bs, bc) == (bs0, bc0) and np.array_equal(bp, bp0) and np.array_equal(fin, fin0)
+        code, done, bs, bp, bc, nn, fin, mv = I.multistart_two_opt(0, 296, time_limit=0.15)
+        assert code == tsp.DEADLINE_EXCEEDED and 0 < done <= 296
+        assert np.all(fin[done:] == -1) and np.all(mv[done:] == -1) and np.all(fin[:done] > 0)
+        assert np.all(mv[:done] <= mv0[:done]) and np.all(fin[:done] >= fin0[:done])       # a cut descent stopped early
+        complete = mv[:done] == mv0[:done]
+        assert np.array_equal(fin[:done][complete], fin0[:done][complete])
+        k = int(np.argmin(fin[:done]))                                                     # first minimum = lowest start
+        assert (bs, bc) == (k, fin[k]) and oracle.is_tour(bp) and oracle.tour_cost(xy, bp) == bc
+        code, done, bs, bp, bc, nn, fin, mv = I.multistart_two_opt(0, 296, time_limit=0.0)
+        assert code == tsp.DEADLINE_EXCEEDED and done == 0 and bs == -1
+        # all-start NN under a limit: a prefix of whole batches
+        bsn0, bpn0, bcn0, costs0 = I.nn_multi(0, 2000)
+        code, done, bsn, bpn, bcn, costs = I.nn_multi(0, 2000, time_limit=600.0)
+        assert code == 0 and done == 2000 and (bsn, bcn) == (bsn0, bcn0) and np.array_equal(costs, costs0)
+        code, done, bsn, bpn, bcn, costs = I.nn_multi(0, 2000, time_limit=0.0)
+        assert code == tsp.DEADLINE_EXCEEDED and done == 0 and bsn == -1
+    # the full-scan multi-start kernel (K6, tours in shared memory) honours the same flag
+    xy = np.ascontiguousarray(np.round(np.random.default_rng(5).uniform(0, 20000, size=(3000, 2))))
+    with tsp.Instance(xy) as I:
+        I.set_scan_mode(tsp.SCAN_FULL)
+        bs0, bp0, bc0, nn0, fin0, mv0 = I.multistart_two_opt(0, 600)
+        code, done, bs, bp, bc, nn, fin, mv = I.multistart_two_opt(0, 600, time_limit=0.05)
+        assert code == tsp.DEADLINE_EXCEEDED and 0 < done <= 600 and np.all(fin[done:] == -1)
+        complete = mv[:done] == mv0[:done]
+        assert np.array_equal(fin[:done][complete], fin0[:done][complete]) and oracle.is_tour(bp) and oracle.tour_cost(xy, bp) == bc
+
+
+def test_restarts_c_abi(tsp, oracle):
+    """tspcuda_restarts (config 5): the C entry point against the same restarts made by hand from the public calls --
+    tabu: NN -> 2-opt -> tabu loop with the reference's tenure schedule; VNS: srand(seed + start), NN -> mh_VNS loop --
+    and shard independence (the merged best of two shards = the best of one call over every start)."""
+    from travellingsalesmanoptimization_b200 import multistart as MS
+    xy, _ = load_instance("rl1304")
+    with tsp.Instance(xy) as I:
+        code, done, bs, bp, bc = I.restarts(tsp.RESTART_TABU, 3, 4, 5, iters=120)
+        hc, hs, hp = MS.tabu_restarts(I, 3, 4, 5, 120)
+        assert code == 0 and done == 4 and (bs, bc) == (hs, hc) and np.array_equal(bp, hp)
+        assert oracle.is_tour(bp) and oracle.tour_cost(xy, bp) == bc
+        code, done, bs, bp, bc = I.restarts(tsp.RESTART_VNS, 0, 6, 1, iters=10, seed=5)
+        hc, hs, hp = MS.vns_restarts(I, 0, 6, 1, 10, seed=5)
+        assert code == 0 and done == 6 and (bs, bc) == (hs, hc) and np.array_equal(bp, hp)
+        parts = [I.restarts(tsp.RESTART_VNS, *MS.shard_starts(0, 6, r, 2), iters=10, seed=5) for r in range(2)]
+        merged = min(parts, key=lambda p: (p[4], p[2]))
+        assert (merged[2], merged[4]) == (bs, bc) and np.array_equal(merged[3], bp)
+        code, done, bs2, bp2, bc2 = I.restarts(tsp.RESTART_TABU, 0, 50, 1, iters=2000, time_limit=0.2)
+        assert code == tsp.DEADLINE_EXCEEDED and 0 < done < 50 and oracle.is_tour(bp2) and oracle.tour_cost(xy, bp2) == bc2

@@ -14,6 +14,7 @@ import os
 import numpy as np
 
 from .build import LIB, build
+from .tsplib import load_instance, read_tsplib  # noqa: F401  (data loading for bench.py / scripts)
 
 EUC_REF, CEIL_2D, ATT, GEO = 0, 1, 2, 3
 SCAN_AUTO, SCAN_FULL, SCAN_PRUNED = 0, 1, 2
@@ -32,8 +33,9 @@ EXPORTS = [
     "tspcuda_timer_stop", "tspcuda_flush_l2", "tspcuda_set_scan_mode", "tspcuda_tabu_search",
     "tspcuda_extra_mileage", "tspcuda_mx_create", "tspcuda_mx_destroy", "tspcuda_mx_get_stats", "tspcuda_mx_nn", "tspcuda_mx_two_opt",
     "tspcuda_mx_two_opt_once", "tspcuda_patching", "tspcuda_mgpu_create", "tspcuda_mgpu_destroy", "tspcuda_mgpu_ndev",
-    "tspcuda_mgpu_multistart", "tspcuda_vns_search",
+    "tspcuda_mgpu_multistart", "tspcuda_vns_search", "tspcuda_restarts", "tspcuda_mgpu_restarts", "tspcuda_mx_update",
 ]
+RESTART_TABU, RESTART_VNS = 0, 1
 
 
 class TspCudaError(RuntimeError):
@@ -66,13 +68,13 @@ _lib = None
 
 
 def lib():
-    """Load libtspcuda.so (building it first if the sources are newer). Raises if impossible."""
+    """Load libtspcuda.so, (re)building it first when it is missing or older than its sources. Raises if impossible."""
     global _lib
     if _lib is not None:
         return _lib
     path = os.environ.get("TSPCUDA_LIB") or LIB      # development override: an alternative build of the SAME library
-    if path == LIB and not os.path.exists(LIB):
-        build()
+    if path == LIB:
+        build()                                      # returns at once unless needs_build()
     L = C.CDLL(path)
     L.tspcuda_last_error.restype = C.c_char_p
     L.tspcuda_version.restype = C.c_char_p
@@ -86,7 +88,7 @@ def lib():
     L.tspcuda_cost_matrix_device.argtypes = [_vp, _dp]
     L.tspcuda_cost_matrix_checksum.argtypes = [_vp, _i64p]
     L.tspcuda_nn.argtypes = [_vp, C.c_int, _ip, _dp]
-    L.tspcuda_nn_multi.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _ip, _ip, _dp]
+    L.tspcuda_nn_multi.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _ip, _ip, _dp, _ip]
     L.tspcuda_two_opt.argtypes = [_vp, _ip, _dp, C.c_int64, C.c_double, _i64p, C.POINTER(Move), C.c_int64]
     L.tspcuda_two_opt_once.argtypes = [_vp, _ip, _dp, _dp, C.POINTER(Move)]
     L.tspcuda_tabu_move.argtypes = [_vp, _ip, _dp, _ip, C.c_int, C.c_int, C.POINTER(Move)]
@@ -94,7 +96,9 @@ def lib():
     L.tspcuda_tour_descend.argtypes = [_vp, C.c_int64, _i64p, _ip]
     L.tspcuda_tour_download.argtypes = [_vp, _ip, _dp]
     L.tspcuda_tour_movelog.argtypes = [_vp, C.POINTER(Move), C.c_int64, _i64p]
-    L.tspcuda_multistart_two_opt.argtypes = [_vp, C.c_int, C.c_int, C.c_int, _dp, _dp, _i64p, _ip, _ip, _dp]
+    L.tspcuda_multistart_two_opt.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_double, _dp, _dp, _i64p, _ip, _ip, _dp, _ip]
+    L.tspcuda_restarts.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_double, _ip, _ip, _dp, _ip]
+    L.tspcuda_mgpu_restarts.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.c_double, _ip, _ip, _dp, _ip, _dp, _dp]
     L.tspcuda_pipe_rate.argtypes = [_vp, C.c_int, _dp]
     L.tspcuda_selfcheck_sqrt.argtypes = [_vp, _i64p]
     L.tspcuda_timer_start.argtypes = [_vp]
@@ -108,10 +112,11 @@ def lib():
     L.tspcuda_mgpu_destroy.argtypes = [_vp]
     L.tspcuda_mgpu_destroy.restype = None
     L.tspcuda_mgpu_ndev.argtypes = [_vp]
-    L.tspcuda_mgpu_multistart.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, _dp, _dp, _dp]
+    L.tspcuda_mgpu_multistart.argtypes = [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _ip, _ip, _dp, _ip, _dp, _dp]
     L.tspcuda_mx_create.argtypes = [C.POINTER(_vp), _dp, C.c_int, C.c_int]
     L.tspcuda_mx_destroy.argtypes = [_vp]
     L.tspcuda_mx_destroy.restype = None
+    L.tspcuda_mx_update.argtypes = [_vp, _dp]
     L.tspcuda_mx_get_stats.argtypes = [_vp, C.POINTER(Stats)]
     L.tspcuda_mx_nn.argtypes = [_vp, C.c_int, _ip, _dp, _ip]
     L.tspcuda_mx_two_opt.argtypes = [_vp, _ip, _dp, C.c_int64, C.c_double, _i64p, C.POINTER(MoveF), C.c_int64]
@@ -202,12 +207,17 @@ class Instance:
         code = lib().tspcuda_nn(self._h, start, _ipc(path), C.byref(cost))
         return code, path, cost.value
 
-    def nn_multi(self, first_start, nstarts, stride=1):
+    def nn_multi(self, first_start, nstarts, stride=1, time_limit=None):
+        """h_Greedy_iterative's loop.  Without time_limit: (best_start, best_path, best_cost, costs); with one (seconds):
+        (code, starts_done, best_start, best_path, best_cost, costs) -- code DEADLINE_EXCEEDED = best of the prefix taken."""
         costs = np.zeros(nstarts, dtype=np.float64)
         best_path = np.zeros(self.n, dtype=np.int32)
-        bs, bc = C.c_int(-1), C.c_double(0)
-        _chk(lib().tspcuda_nn_multi(self._h, first_start, nstarts, stride, _dpc(costs), C.byref(bs), _ipc(best_path), C.byref(bc)))
-        return bs.value, best_path, bc.value, costs
+        bs, bc, done = C.c_int(-1), C.c_double(0), C.c_int(0)
+        code = _chk(lib().tspcuda_nn_multi(self._h, first_start, nstarts, stride, -1.0 if time_limit is None else time_limit, _dpc(costs),
+                                           C.byref(bs), _ipc(best_path), C.byref(bc), C.byref(done)), allow=(DEADLINE_EXCEEDED,))
+        if time_limit is None:
+            return bs.value, best_path, bc.value, costs
+        return code, done.value, bs.value, best_path, bc.value, costs
 
     # -- 2-opt -------------------------------------------------------------------------------------
     def two_opt(self, path, max_moves=-1, time_limit=-1.0, log_cap=0):
@@ -300,15 +310,29 @@ class Instance:
         return cnt.value, [(log[i].a, log[i].b, log[i].delta) for i in range(k)]
 
     # -- multi-start ---------------------------------------------------------------------------------
-    def multistart_two_opt(self, first_start, nstarts, stride=1):
+    def multistart_two_opt(self, first_start, nstarts, stride=1, time_limit=None):
+        """h_greedy_2opt's loop.  Without time_limit: (best_start, best_path, best_cost, nn_costs, final_costs, moves); with one
+        (seconds): (code, starts_done, ...the same six...) -- code DEADLINE_EXCEEDED = best over the prefix of starts taken."""
         nn_costs = np.zeros(nstarts, dtype=np.float64)
         final = np.zeros(nstarts, dtype=np.float64)
         moves = np.zeros(nstarts, dtype=np.int64)
         best_path = np.zeros(self.n, dtype=np.int32)
-        bs, bc = C.c_int(-1), C.c_double(0)
-        _chk(lib().tspcuda_multistart_two_opt(self._h, first_start, nstarts, stride, _dpc(nn_costs), _dpc(final),
-                                              moves.ctypes.data_as(_i64p), C.byref(bs), _ipc(best_path), C.byref(bc)))
-        return bs.value, best_path, bc.value, nn_costs, final, moves
+        bs, bc, done = C.c_int(-1), C.c_double(0), C.c_int(0)
+        code = _chk(lib().tspcuda_multistart_two_opt(self._h, first_start, nstarts, stride, -1.0 if time_limit is None else time_limit,
+                                                     _dpc(nn_costs), _dpc(final), moves.ctypes.data_as(_i64p), C.byref(bs), _ipc(best_path),
+                                                     C.byref(bc), C.byref(done)), allow=(DEADLINE_EXCEEDED,))
+        if time_limit is None:
+            return bs.value, best_path, bc.value, nn_costs, final, moves
+        return code, done.value, bs.value, best_path, bc.value, nn_costs, final, moves
+
+    def restarts(self, kind, first_start, nstarts, stride=1, iters=100, seed=0, time_limit=-1.0):
+        """Config 5: tabu (RESTART_TABU) / VNS (RESTART_VNS) restarts from start nodes first_start + r*stride.
+        Returns (code, restarts_done, best_start, best_path, best_cost)."""
+        best_path = np.zeros(self.n, dtype=np.int32)
+        bs, bc, done = C.c_int(-1), C.c_double(0), C.c_int(0)
+        code = _chk(lib().tspcuda_restarts(self._h, kind, first_start, nstarts, stride, iters, seed, time_limit, C.byref(bs),
+                                           _ipc(best_path), C.byref(bc), C.byref(done)), allow=(DEADLINE_EXCEEDED,))
+        return code, done.value, bs.value, best_path, bc.value
 
     # -- measurement ---------------------------------------------------------------------------------
     def pipe_rate(self, kind):
@@ -365,6 +389,13 @@ class MatrixInstance:
         s = Stats()
         _chk(lib().tspcuda_mx_get_stats(self._h, C.byref(s)))
         return s.as_dict()
+
+    def update(self, costs):
+        """Replace the matrix (same n) in place: no device allocation."""
+        costs = np.ascontiguousarray(costs, dtype=np.float64)
+        assert costs.shape == (self.n, self.n)
+        self.costs = costs
+        _chk(lib().tspcuda_mx_update(self._h, _dpc(self.costs)))
 
     def nn(self, start):
         """h_greedyutil(start, ., costs): (code, path, cost, nodes reached)."""
@@ -427,11 +458,23 @@ class MultiGpuInstance:
     def __exit__(self, *a):
         self.close()
 
-    def multistart(self, two_opt=True, first_start=0, nstarts=None, stride=1):
-        """(best_start, best_path, best_cost, compute_ms, reduce_ms) over starts first_start + k*stride."""
+    def multistart(self, two_opt=True, first_start=0, nstarts=None, stride=1, time_limit=None):
+        """(best_start, best_path, best_cost, compute_ms, reduce_ms) over starts first_start + k*stride; with a time_limit
+        (seconds) the tuple is preceded by (code, starts_done)."""
         nstarts = self.n if nstarts is None else nstarts
         path = np.zeros(self.n, dtype=np.int32)
-        bs, bc, cm, rm = C.c_int(-1), C.c_double(0), C.c_double(0), C.c_double(0)
-        _chk(lib().tspcuda_mgpu_multistart(self._h, 1 if two_opt else 0, first_start, nstarts, stride, C.byref(bs), _ipc(path),
-                                           C.byref(bc), C.byref(cm), C.byref(rm)))
-        return bs.value, path, bc.value, cm.value, rm.value
+        bs, bc, cm, rm, done = C.c_int(-1), C.c_double(0), C.c_double(0), C.c_double(0), C.c_int(0)
+        code = _chk(lib().tspcuda_mgpu_multistart(self._h, 1 if two_opt else 0, first_start, nstarts, stride,
+                                                  -1.0 if time_limit is None else time_limit, C.byref(bs), _ipc(path), C.byref(bc),
+                                                  C.byref(done), C.byref(cm), C.byref(rm)), allow=(DEADLINE_EXCEEDED,))
+        if time_limit is None:
+            return bs.value, path, bc.value, cm.value, rm.value
+        return code, done.value, bs.value, path, bc.value, cm.value, rm.value
+
+    def restarts(self, kind, first_start, nstarts, stride=1, iters=100, seed=0, time_limit=-1.0):
+        """Config 5 restarts sharded over the GPUs: (code, restarts_done, best_start, best_path, best_cost, compute_ms, reduce_ms)."""
+        path = np.zeros(self.n, dtype=np.int32)
+        bs, bc, cm, rm, done = C.c_int(-1), C.c_double(0), C.c_double(0), C.c_double(0), C.c_int(0)
+        code = _chk(lib().tspcuda_mgpu_restarts(self._h, kind, first_start, nstarts, stride, iters, seed, time_limit, C.byref(bs),
+                                                _ipc(path), C.byref(bc), C.byref(done), C.byref(cm), C.byref(rm)), allow=(DEADLINE_EXCEEDED,))
+        return code, done.value, bs.value, path, bc.value, cm.value, rm.value

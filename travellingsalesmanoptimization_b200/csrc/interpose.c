@@ -34,11 +34,15 @@
  *
  * No CPU fallback: if the GPU library fails the reference's error path is taken (INTERNAL, which
  * the callers treat as fatal), never a silent host computation.  A foreign cost matrix (the
- * fractional matrices of h_Greedy_2opt_mod_costs, heuristics.c:118, a CPLEX-only caller that is out
- * of scope) is refused with UNIMPLEMENTED.
+ * fractional matrices h_Greedy_2opt_mod_costs hands down from the CPLEX relaxation callback,
+ * heuristics.c:118, cplex_model.c:1187-1217) is uploaded into a pooled device buffer and served by the
+ * matrix kernels (tspcuda_mx_*), in the reference's FP64 expression order.
+ * Time limits (-t, tsp_env.timelimit) are honoured INSIDE the batched calls (tspcuda.h: time_limit_s), so the
+ * whole-loop overrides stay active under the reference's standard invocation (scripts/compare_algs.py: -t 600).
  */
 #define _GNU_SOURCE
 #include <dlfcn.h>
+#include <pthread.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -54,6 +58,8 @@ static int g_mgpu_n = -1;
 static int g_weight_type = TSPCUDA_EUC_REF;     /* set by the interposed tsp_read_input */
 static point *g_points = NULL;
 static int g_n = -1;
+static int g_ctx_wt = -1;
+static unsigned long g_generation = 0, g_ctx_generation = 0, g_mgpu_generation = 0;   /* bumped whenever the instance is (re)built */
 #define N_CALLS 13
 static long g_calls[N_CALLS];
 enum { C_COSTS, C_NN, C_2OPT, C_2OPT_ONCE, C_TABU, C_ALLNN, C_MULTI, C_TABULOOP, C_READ, C_EMUTIL, C_EM, C_PATCH, C_VNSLOOP };
@@ -61,13 +67,9 @@ static const char *g_names[] = {"tsp_compute_costs", "h_greedyutil", "ref_2opt",
                                 "tabu_best_move", "h_Greedy_iterative", "h_greedy_2opt", "mh_TabuSearch", "tsp_read_input",
                                 "h_extramileage_util", "h_ExtraMileage", "cx_patching", "mh_VNS"};
 
-/* Exit hook.  Prints the call counters (TSPCUDA_STATS=1), flushes stdio and leaves with _exit().
- * The last step shields the process from a latent heap overflow in the UNCHANGED driver:
- * tsp_plot_solution (src/tsp.c:505-508) hands basename(tsp_env.inputfile) to utils_format_title
- * (src/utils/utils.c:69-121), which strncpy()s strlen+51 bytes back into that strdup()ed buffer.
- * The reference CPU binary happens to survive it; with more heap traffic in the process (the CUDA
- * runtime) glibc can detect the smashed chunk header in a LATER exit handler and abort() after the
- * result was printed but before stdout is flushed.  TSPCUDA_FAST_EXIT=0 disables the shield. */
+/* Exit hook: prints the call counters (TSPCUDA_STATS=1).  TSPCUDA_FAST_EXIT=1 (opt-in, off by default) additionally
+ * flushes stdio and leaves with _exit(), skipping later exit handlers and library destructors -- a diagnostic aid for
+ * the reference heap overflow described at pad_inputfile() below, which that function already defuses. */
 static void on_exit_hook(int status, void *arg) {
     (void)arg;
     const char *s = getenv("TSPCUDA_STATS");
@@ -78,30 +80,46 @@ static void on_exit_hook(int status, void *arg) {
         fprintf(stderr, "\n");
     }
     const char *f = getenv("TSPCUDA_FAST_EXIT");
-    if (f && *f == '0') return;
+    if (!(f && *f == '1')) return;
     fflush(NULL);
     _exit(status);
 }
 
 __attribute__((constructor)) static void selfcheck(void) {
-    /* a mis-link must not masquerade as a pass: the hot symbols have to resolve into THIS object */
+    /* A mis-link must not masquerade as a pass: the hot symbols have to resolve into THIS object.  If they do not
+     * (Ubuntu's default --as-needed dropped the interposer, or libtspref precedes it), every "GPU" result would silently
+     * be the reference's CPU code: fatal.  TSPCUDA_ALLOW_MISLINK=1 downgrades it to a warning (for a process that loads
+     * this library for its tspcuda_* symbols only). */
     Dl_info me, hot;
     void *sym = dlsym(RTLD_DEFAULT, "ref_2opt_once");
-    if (dladdr((void *)&selfcheck, &me) && sym && dladdr(sym, &hot) && strcmp(me.dli_fname, hot.dli_fname) != 0)
-        fprintf(stderr, "[tspcuda] WARNING: ref_2opt_once resolves to %s, not to the interposer %s: the GPU path is NOT active "
-                        "(link with -Wl,--no-as-needed before libtspref, or LD_PRELOAD)\n", hot.dli_fname, me.dli_fname);
+    if (dladdr((void *)&selfcheck, &me) && sym && dladdr(sym, &hot) && strcmp(me.dli_fname, hot.dli_fname) != 0) {
+        const char *allow = getenv("TSPCUDA_ALLOW_MISLINK");
+        fprintf(stderr, "[tspcuda] %s: ref_2opt_once resolves to %s, not to the interposer %s: the GPU path is NOT active "
+                        "(link with -Wl,--no-as-needed before libtspref, or LD_PRELOAD)\n",
+                (allow && *allow == '1') ? "WARNING" : "FATAL", hot.dli_fname, me.dli_fname);
+        if (!(allow && *allow == '1')) _exit(70);
+    }
     on_exit(on_exit_hook, NULL);
 }
 
-/* Heap shield for the overflow described above: the driver strdup()s the input file name
- * (src/tsp.c:78,183) and later writes strlen+51 bytes into it.  This definition precedes libc's in
- * the lookup order and gives every strdup() 128 spare bytes, so the overflow lands in slack instead
- * of in the next chunk's header (glibc would abort in tsp_free_instance's free(), src/tsp.c:745). */
-char *strdup(const char *s) {
-    size_t n = strlen(s) + 1;
-    char *p = (char *)malloc(n + 128);
-    if (p) memcpy(p, s, n);
-    return p;
+/* A latent heap overflow in the UNCHANGED driver: tsp_plot_solution (src/tsp.c:505-508) hands
+ * basename(tsp_env.inputfile) to utils_format_title (src/utils/utils.c:69-121), which strncpy()s strlen+51 bytes back
+ * into that buffer -- strdup()ed at src/tsp.c:78,183 or calloc(strlen) at src/main.c:117 (itself one byte short).  The
+ * reference CPU binary happens to survive it; with more heap traffic in the process (the CUDA runtime) glibc detects
+ * the smashed chunk header in tsp_free_instance's free() (src/tsp.c:745) or in a later exit handler and abort()s after
+ * the result was printed.  Nothing process-wide is touched to avoid that: the ONE buffer is re-allocated with slack
+ * before the driver can overflow it (called from tsp_compute_costs, which every instance passes through).  INTEGRATION.md
+ * documents the bug; TSPCUDA_PAD_INPUTFILE=0 leaves the buffer alone. */
+static void pad_inputfile(void) {
+    static char *padded = NULL;
+    const char *off = getenv("TSPCUDA_PAD_INPUTFILE");
+    if ((off && *off == '0') || !tsp_env.inputfile || tsp_env.inputfile == padded) return;
+    size_t n = strlen(tsp_env.inputfile) + 1;
+    char *p = (char *)calloc(n + 256, 1);
+    if (!p) return;
+    memcpy(p, tsp_env.inputfile, n);
+    free(tsp_env.inputfile);                    /* heap memory in every reference path that sets it */
+    tsp_env.inputfile = padded = p;
 }
 
 static int device_index(void) {
@@ -109,8 +127,27 @@ static int device_index(void) {
     return d ? atoi(d) : 0;
 }
 
+/* Device state is released by an atexit handler registered AFTER the first context exists: handlers run in reverse
+ * order of registration, so this one runs before the CUDA runtime's own (registered at its first use) and the NCCL
+ * communicators / streams / buffers are torn down while the runtime is still alive. */
+static tspcuda_mx *g_mx = NULL;
+static void cleanup_device(void) {
+    if (g_mgpu) { tspcuda_mgpu_destroy(g_mgpu); g_mgpu = NULL; }
+    if (g_mx) { tspcuda_mx_destroy(g_mx); g_mx = NULL; }
+    if (g_ctx) { tspcuda_destroy(g_ctx); g_ctx = NULL; }
+}
+static void register_cleanup(void) {
+    static int done = 0;
+    if (!done) { done = 1; atexit(cleanup_device); }
+}
+
+/* The device context is cached per instance.  Pointer + size alone do not identify an instance (after
+ * tsp_free_instance glibc readily hands the same address to the next calloc of that size), so the key also holds the
+ * weight type and a generation counter that tsp_compute_costs -- the one call every new set of points goes through --
+ * bumps. */
 static tspcuda_ctx *ctx_for_instance(void) {
-    if (g_ctx && g_points == tsp_inst.points && g_n == tsp_inst.nnodes) return g_ctx;
+    if (g_ctx && g_points == tsp_inst.points && g_n == tsp_inst.nnodes && g_ctx_wt == g_weight_type && g_ctx_generation == g_generation)
+        return g_ctx;
     if (g_ctx) { tspcuda_destroy(g_ctx); g_ctx = NULL; }
     /* `point` is {double x; double y;} (utils.h:37-40): the array IS the AoS layout of the ABI */
     int e = tspcuda_create(&g_ctx, (const double *)tsp_inst.points, tsp_inst.nnodes, g_weight_type, device_index());
@@ -119,8 +156,11 @@ static tspcuda_ctx *ctx_for_instance(void) {
         g_ctx = NULL;
         return NULL;
     }
+    register_cleanup();
     g_points = tsp_inst.points;
     g_n = tsp_inst.nnodes;
+    g_ctx_wt = g_weight_type;
+    g_ctx_generation = g_generation;
     return g_ctx;
 }
 
@@ -135,7 +175,7 @@ static int gpus_requested(void) {
 }
 
 static tspcuda_mgpu *mgpu_for_instance(void) {
-    if (g_mgpu && g_mgpu_points == tsp_inst.points && g_mgpu_n == tsp_inst.nnodes) return g_mgpu;
+    if (g_mgpu && g_mgpu_points == tsp_inst.points && g_mgpu_n == tsp_inst.nnodes && g_mgpu_generation == g_generation) return g_mgpu;
     if (g_mgpu) { tspcuda_mgpu_destroy(g_mgpu); g_mgpu = NULL; }
     int e = tspcuda_mgpu_create(&g_mgpu, (const double *)tsp_inst.points, tsp_inst.nnodes, g_weight_type, gpus_requested(), NULL);
     if (e != TSPCUDA_OK) {
@@ -143,28 +183,31 @@ static tspcuda_mgpu *mgpu_for_instance(void) {
         g_mgpu = NULL;
         return NULL;
     }
+    register_cleanup();
     g_mgpu_points = tsp_inst.points;
     g_mgpu_n = tsp_inst.nnodes;
+    g_mgpu_generation = g_generation;
     return g_mgpu;
-}
-
-/* all starts 0..n-1 of the current instance, on one GPU or sharded over TSPCUDA_GPUS of them */
-static int all_starts(int two_opt, int *best_start, int *path, double *cost) {
-    if (gpus_requested() > 1) {
-        tspcuda_mgpu *m = mgpu_for_instance();
-        if (!m) return TSPCUDA_INTERNAL;
-        return tspcuda_mgpu_multistart(m, two_opt, 0, tsp_inst.nnodes, 1, best_start, path, cost, NULL, NULL);
-    }
-    tspcuda_ctx *c = ctx_for_instance();
-    if (!c) return TSPCUDA_INTERNAL;
-    return two_opt ? tspcuda_multistart_two_opt(c, 0, tsp_inst.nnodes, 1, NULL, NULL, NULL, best_start, path, cost)
-                   : tspcuda_nn_multi(c, 0, tsp_inst.nnodes, 1, NULL, best_start, path, cost);
 }
 
 static double time_left(void) {          /* -1: no limit; otherwise seconds (may be <= 0) */
     if (tsp_env.timelimit == -1.0) return -1.0;
     double left = tsp_env.timelimit - utils_timeelapsed(&tsp_inst.c);
     return left > 0 ? left : 0.0;
+}
+
+/* all starts 0..n-1 of the current instance, on one GPU or sharded over TSPCUDA_GPUS of them, inside what is left of
+ * the driver's time limit (TSPCUDA_DEADLINE_EXCEEDED: best of the prefix of starts reached, *best_start < 0 if none) */
+static int all_starts(int two_opt, int *best_start, int *path, double *cost) {
+    if (gpus_requested() > 1) {
+        tspcuda_mgpu *m = mgpu_for_instance();
+        if (!m) return TSPCUDA_INTERNAL;
+        return tspcuda_mgpu_multistart(m, two_opt, 0, tsp_inst.nnodes, 1, time_left(), best_start, path, cost, NULL, NULL, NULL);
+    }
+    tspcuda_ctx *c = ctx_for_instance();
+    if (!c) return TSPCUDA_INTERNAL;
+    return two_opt ? tspcuda_multistart_two_opt(c, 0, tsp_inst.nnodes, 1, time_left(), NULL, NULL, NULL, best_start, path, cost, NULL)
+                   : tspcuda_nn_multi(c, 0, tsp_inst.nnodes, 1, time_left(), NULL, best_start, path, cost, NULL);
 }
 
 static bool batch_enabled(void) {
@@ -259,6 +302,11 @@ ERROR_CODE tsp_compute_costs(void) {
         log_fatal("computing costs of empty graph");
         tsp_handlefatal();
     }
+    pad_inputfile();
+    /* the points were just (re)built: whatever device context exists describes an older instance, even if the new
+     * array sits at the same address with the same size */
+    g_generation++;
+    if (g_mgpu) { tspcuda_mgpu_destroy(g_mgpu); g_mgpu = NULL; }
     tspcuda_ctx *c = ctx_for_instance();
     if (!c) return INTERNAL;
     /* The unchanged host code still reads tsp_inst.costs (tsp_get_cost users: ExtraMileage, CPLEX,
@@ -285,18 +333,35 @@ ERROR_CODE tsp_compute_costs(void) {
 
 static bool foreign_costs(const double *costs) { return costs != tsp_inst.costs; }
 
-/* A caller-supplied matrix (h_Greedy_2opt_mod_costs and its helpers, heuristics.c:118-149): uploaded for
- * the call.  The content behind the pointer may change between calls (the CPLEX callback refills its
- * buffers), so nothing is cached across calls. */
-static tspcuda_mx *mx_for(double *costs) {
-    tspcuda_mx *m = NULL;
-    int e = tspcuda_mx_create(&m, costs, tsp_inst.nnodes, device_index());
+/* A caller-supplied matrix (h_Greedy_2opt_mod_costs and its helpers, heuristics.c:118-149).  The content behind the
+ * pointer may change between calls (the CPLEX callback refills its buffers), so the matrix is uploaded for every call
+ * -- but into ONE pooled device context (grow-only: re-created only when n changes), not a cudaMalloc / cudaFree pair of
+ * an n^2 buffer per call: the relaxation callback makes thousands of calls, and cudaFree alone was measured at
+ * 0.1 - 1.5 s on the B200 boxes.  The callback may run on up to 32 CPLEX threads with thread-private buffers
+ * (cplex_model.c:1187-1217): the pooled context is guarded by one mutex, held from mx_acquire() to mx_release(). */
+static pthread_mutex_t g_mx_lock = PTHREAD_MUTEX_INITIALIZER;
+static int g_mx_n = -1;
+
+static tspcuda_mx *mx_acquire(double *costs) {
+    pthread_mutex_lock(&g_mx_lock);
+    int e;
+    if (g_mx && g_mx_n == tsp_inst.nnodes) {
+        e = tspcuda_mx_update(g_mx, costs);
+    } else {
+        if (g_mx) { tspcuda_mx_destroy(g_mx); g_mx = NULL; }
+        e = tspcuda_mx_create(&g_mx, costs, tsp_inst.nnodes, device_index());
+        g_mx_n = e == TSPCUDA_OK ? tsp_inst.nnodes : -1;
+        if (e == TSPCUDA_OK) register_cleanup();
+    }
     if (e != TSPCUDA_OK) {
         log_error("code %d : libtspcuda: %s", e, tspcuda_last_error());
+        pthread_mutex_unlock(&g_mx_lock);
         return NULL;
     }
-    return m;
+    return g_mx;
 }
+
+static void mx_release(void) { pthread_mutex_unlock(&g_mx_lock); }
 
 /* ---- h_greedyutil, src/algorithms/heuristics.c:216-288 ------------------------------------- */
 ERROR_CODE h_greedyutil(int starting_node, tsp_solution *solution, double *costs) {
@@ -314,11 +379,11 @@ ERROR_CODE h_greedyutil(int starting_node, tsp_solution *solution, double *costs
         return DEADLINE_EXCEEDED;
     }
     if (foreign_costs(costs)) {
-        tspcuda_mx *m = mx_for(costs);
+        tspcuda_mx *m = mx_acquire(costs);
         if (!m) return INTERNAL;
         int rc = tspcuda_mx_nn(m, starting_node, solution->path, &solution->cost, NULL);
         if (rc != TSPCUDA_OK) log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
-        tspcuda_mx_destroy(m);
+        mx_release();
         return (ERROR_CODE)rc;
     }
     tspcuda_ctx *c = ctx_for_instance();
@@ -337,10 +402,10 @@ ERROR_CODE ref_2opt(tsp_solution *solution, double *costs, bool update_incumbent
     int rc;
     /* left == 0: the reference recomputes the cost (:6-9) and leaves at the first time check (:17-24) */
     if (foreign_costs(costs)) {
-        tspcuda_mx *m = mx_for(costs);
+        tspcuda_mx *m = mx_acquire(costs);
         if (!m) return INTERNAL;
         rc = tspcuda_mx_two_opt(m, solution->path, &solution->cost, left == 0.0 ? 0 : -1, left, &moves, NULL, 0);
-        tspcuda_mx_destroy(m);
+        mx_release();
     } else {
         tspcuda_ctx *c = ctx_for_instance();
         if (!c) return INTERNAL;
@@ -366,9 +431,9 @@ double ref_2opt_once(tsp_solution *solution, double *costs) {
     double delta = 0;
     int rc;
     if (foreign_costs(costs)) {
-        tspcuda_mx *m = mx_for(costs);
+        tspcuda_mx *m = mx_acquire(costs);
         rc = m ? tspcuda_mx_two_opt_once(m, solution->path, &solution->cost, &delta) : TSPCUDA_INTERNAL;
-        tspcuda_mx_destroy(m);
+        if (m) mx_release();
     } else {
         tspcuda_ctx *c = ctx_for_instance();
         rc = c ? tspcuda_two_opt_once(c, solution->path, &solution->cost, &delta, NULL) : TSPCUDA_INTERNAL;
@@ -400,7 +465,7 @@ typedef ERROR_CODE (*void_fn)(void);
  * on a strictly smaller cost (:58 and tsp.c:671), so its final state is the FIRST start attaining
  * the minimum -- exactly what tspcuda_nn_multi returns -- and starting_node is that start (:60). */
 ERROR_CODE h_Greedy_iterative(void) {
-    if (!batch_enabled() || tsp_env.timelimit != -1.0)
+    if (!batch_enabled())
         return ((void_fn)dlsym(RTLD_NEXT, "h_Greedy_iterative"))();      /* the reference loop over the interposed helpers */
     g_calls[C_ALLNN]++;
     log_info("running All Nearest Neighbour");
@@ -408,26 +473,27 @@ ERROR_CODE h_Greedy_iterative(void) {
     tsp_init_solution(tsp_inst.nnodes, &solution);
     int best_start = -1;
     int rc = all_starts(0, &best_start, solution.path, &solution.cost);
-    if (rc != TSPCUDA_OK) {
+    if (rc != TSPCUDA_OK && rc != TSPCUDA_DEADLINE_EXCEEDED) {
         log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
         utils_safe_free(solution.path);
         return (ERROR_CODE)rc;
     }
-    if (solution.cost < tsp_inst.best_solution.cost) {
+    /* time limit (:43-49): the incumbent is the best of the prefix of starts reached, possibly none */
+    if (best_start >= 0 && solution.cost < tsp_inst.best_solution.cost) {
         log_info("found new best, node %d", best_start);
         tsp_inst.starting_node = best_start;
         ERROR_CODE error = tsp_update_best_solution(&solution);
         if (!err_ok(error)) log_error("code %d : error in updating best solution of greedy iterative", error);
     }
     utils_safe_free(solution.path);
-    return T_OK;
+    return rc == TSPCUDA_DEADLINE_EXCEEDED ? DEADLINE_EXCEEDED : T_OK;
 }
 
 /* h_greedy_2opt, heuristics.c:74-116: NN + ref_2opt(update_incumbent) per start.  Final incumbent =
  * first start attaining the minimum final cost; starting_node is set on EVERY iteration whose
  * ref_2opt returns T_OK (:105-109), so it ends as nnodes-1. */
 ERROR_CODE h_greedy_2opt(void) {
-    if (!batch_enabled() || tsp_env.timelimit != -1.0)
+    if (!batch_enabled())
         return ((void_fn)dlsym(RTLD_NEXT, "h_greedy_2opt"))();
     g_calls[C_MULTI]++;
     log_info("running All Nearest Neighbour + 2OPT");
@@ -435,16 +501,26 @@ ERROR_CODE h_greedy_2opt(void) {
     tsp_init_solution(tsp_inst.nnodes, &solution);
     int best_start = -1;
     int rc = all_starts(1, &best_start, solution.path, &solution.cost);
-    if (rc != TSPCUDA_OK) {
+    if (rc != TSPCUDA_OK && rc != TSPCUDA_DEADLINE_EXCEEDED) {
         log_error("code %d : libtspcuda: %s", rc, tspcuda_last_error());
         utils_safe_free(solution.path);
         return (ERROR_CODE)rc;
     }
-    ERROR_CODE error = tsp_update_best_solution(&solution);
-    if (!err_ok(error)) log_error("code %d : Error in 2opt solution update", error);
-    tsp_inst.starting_node = tsp_inst.nnodes - 1;
+    if (best_start >= 0) {
+        ERROR_CODE error = tsp_update_best_solution(&solution);
+        if (!err_ok(error)) log_error("code %d : Error in 2opt solution update", error);
+    }
+    if (rc == TSPCUDA_DEADLINE_EXCEEDED) {
+        /* :83-90: the loop stops at the first start past the limit; descents cut short still fed the incumbent, as
+         * ref_2opt's update_incumbent does (refinment.c:29-34).  starting_node keeps the last start whose ref_2opt
+         * returned T_OK, which the batch does not report: it is left at the best start. */
+        log_warn("time limit exceeded in greedy 2opt");
+        if (best_start >= 0) tsp_inst.starting_node = best_start;
+    } else {
+        tsp_inst.starting_node = tsp_inst.nnodes - 1;
+    }
     utils_safe_free(solution.path);
-    return T_OK;
+    return rc == TSPCUDA_DEADLINE_EXCEEDED ? DEADLINE_EXCEEDED : T_OK;
 }
 
 /* mh_TabuSearch, metaheuristic.c:86-186.  Same steps in the same order -- tabu_init, results file,
@@ -609,17 +685,26 @@ ERROR_CODE h_Greedy_2opt_mod_costs(tsp_solution *solution, double *costs) {
         log_error("matrix of costs not found");
         return T_OK;                                                /* every iteration logs and continues (:134-137) */
     }
-    tspcuda_mx *m = mx_for(costs);
+    tspcuda_mx *m = mx_acquire(costs);
     if (!m) return T_OK;                                            /* errors inside the loop are logged, e stays T_OK */
-    int rc = tspcuda_mx_nn(m, tsp_inst.nnodes - 1, solution->path, &solution->cost, NULL);
+    int len = 0;
+    int rc = tspcuda_mx_nn(m, tsp_inst.nnodes - 1, solution->path, &solution->cost, &len);
+    if (rc == TSPCUDA_OK && len < tsp_inst.nnodes) {
+        /* NOT_CONNECTED (-1) entries closed the path early (heuristics.c:257): what the reference then hands to
+         * ref_2opt depends on the starts before the last one (stale path entries), which only its own loop reproduces */
+        mx_release();
+        return ((mod_fn)dlsym(RTLD_NEXT, "h_Greedy_2opt_mod_costs"))(solution, costs);
+    }
     if (rc == TSPCUDA_OK) {
         int64_t moves = 0;
         rc = tspcuda_mx_two_opt(m, solution->path, &solution->cost, -1, time_left(), &moves, NULL, 0);
     }
     if (rc != TSPCUDA_OK && rc != TSPCUDA_DEADLINE_EXCEEDED)
         log_error("code %d : error in 2opt (libtspcuda: %s)", rc, tspcuda_last_error());
-    tspcuda_mx_destroy(m);
-    return T_OK;
+    mx_release();
+    /* the limit passed inside the last descent: the reference's loop would have stopped at an earlier start with
+     * e = DEADLINE_EXCEEDED (:124-130) */
+    return rc == TSPCUDA_DEADLINE_EXCEEDED ? DEADLINE_EXCEEDED : T_OK;
 }
 
 /* ---- Extra Mileage, heuristics.c:156-210 and :290-367 --------------------------- */

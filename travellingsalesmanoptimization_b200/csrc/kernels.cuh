@@ -434,11 +434,11 @@ __host__ __device__ inline size_t cta_smem_bytes(int n, int CTA_WARPS) {
 template <class M, int CTA_BLOCK>
 __global__ void __launch_bounds__(CTA_BLOCK, 1024 / CTA_BLOCK)
 descend_cta_kernel(const double2 *__restrict__ xy, int n, const int *__restrict__ order_all, int nstarts,
-                   int *next_start, long long *final_cost, long long *moves_out, int *path_all) {
+                   int *next_start, long long *final_cost, long long *moves_out, int *path_all, int *status_out, const int *stop) {
     constexpr int CTA_WARPS = CTA_BLOCK / 32;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ unsigned long long s_key;
-    __shared__ int s_best, s_cur;
+    __shared__ int s_best, s_cur, s_stop;
     __shared__ long long s_cost;
     const size_t n1 = (size_t)n + 1;
     TourView V;
@@ -457,8 +457,11 @@ descend_cta_kernel(const double2 *__restrict__ xy, int n, const int *__restrict_
     const long long total = strip_prefix(nstrips, n);
     const long long lo = total * warp / CTA_WARPS, hi = total * (warp + 1) / CTA_WARPS;
 
+    // stop (may be NULL): raised by the host when the caller's time limit has passed; looked at before a start is taken
+    // (heuristics.c:83-90) and before every scan (refinment.c:17-24).  status_out: 1 = descent complete, 2 = cut.
+    if (t == 0) s_stop = 0;
     for (;;) {
-        if (t == 0) s_cur = atomicAdd(next_start, 1);
+        if (t == 0) s_cur = (stop != nullptr && *(volatile const int *)stop != 0) ? nstarts : atomicAdd(next_start, 1);
         __syncthreads();
         const int cur = s_cur;
         if (cur >= nstarts) break;
@@ -482,6 +485,7 @@ descend_cta_kernel(const double2 *__restrict__ xy, int n, const int *__restrict_
         for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(FULL, local, o);
         if (lane == 0) atomicAdd((unsigned long long *)&s_cost, (unsigned long long)local);
         long long moves = 0;
+        bool cut = false;
         for (;;) {
             if (t == 0) { s_key = KEY_EMPTY; s_best = -1; }
             __syncthreads();
@@ -496,12 +500,16 @@ descend_cta_kernel(const double2 *__restrict__ xy, int n, const int *__restrict_
             const int a = key_a(kbest), b = key_b(kbest);
             int seg_s, seg_e;
             apply_move<M>(V, a, b, t, CTA_BLOCK, false, seg_s, seg_e);
-            if (t == 0) s_cost += key_delta(kbest);
+            if (t == 0) {
+                s_cost += key_delta(kbest);
+                if (stop != nullptr) s_stop = *(volatile const int *)stop;
+            }
             ++moves;
             __syncthreads();
             if (t == 0) { V.pos[b] = seg_s; V.pos[V.tid[seg_e]] = seg_e; }
+            if (stop != nullptr && s_stop != 0) { cut = true; break; }
         }
-        if (t == 0) { final_cost[cur] = s_cost; moves_out[cur] = moves; }
+        if (t == 0) { final_cost[cur] = s_cost; moves_out[cur] = moves; status_out[cur] = cut ? 2 : 1; }
         if (path_all) {
             int *path = path_all + (size_t)cur * n;
             for (int p = t; p < n; p += CTA_BLOCK) path[V.tid[p]] = V.tid[p + 1];

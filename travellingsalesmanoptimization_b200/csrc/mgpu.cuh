@@ -19,6 +19,7 @@
 #include <pthread.h>
 #include <unistd.h>
 
+#include <functional>
 #include <thread>
 
 namespace {
@@ -136,9 +137,13 @@ extern "C" int tspcuda_mgpu_create(tspcuda_mgpu **out, const double *xy, int n, 
 
 extern "C" int tspcuda_mgpu_ndev(const tspcuda_mgpu *m) { return m ? m->ndev : 0; }
 
-extern "C" int tspcuda_mgpu_multistart(tspcuda_mgpu *m, int two_opt, int first_start, int nstarts, int stride,
-                                       int *best_start_out, int *best_path_out, double *best_cost_out,
-                                       double *compute_ms_out, double *reduce_ms_out) {
+// One shard's work: starts f, f + st, ... (count of them) on context c; its best under the incumbent rule in
+// (*bs, path, *bc), *bs < 0 when it got to none; *taken = starts it got to.  Returns an ERROR_CODE.
+typedef std::function<int(tspcuda_ctx *c, int f, int count, int st, int *bs, int *path, double *bc, int *taken)> ShardJob;
+
+static int mgpu_run(tspcuda_mgpu *m, const ShardJob &job, int first_start, int nstarts, int stride,
+                    int *best_start_out, int *best_path_out, double *best_cost_out, int *starts_done_out,
+                    double *compute_ms_out, double *reduce_ms_out) {
     if (!m) return fail(TSPCUDA_INVALID_ARGUMENT, "null handle");
     const int n = m->n, G = m->ndev;
     if (nstarts <= 0 || stride <= 0) return fail(TSPCUDA_INVALID_ARGUMENT, "nstarts/stride");
@@ -149,7 +154,9 @@ extern "C" int tspcuda_mgpu_multistart(tspcuda_mgpu *m, int two_opt, int first_s
     NcclApi *N = G > 1 ? nccl_api(why) : nullptr;
     if (G > 1 && !N) return fail(TSPCUDA_UNAVAILABLE, "%s", why.c_str());
 
-    std::vector<int> code(G, TSPCUDA_OK);
+    if (starts_done_out) *starts_done_out = 0;
+    std::vector<int> code(G, TSPCUDA_OK), taken(G, 0);
+    std::vector<char> late(G, 0);
     std::vector<std::string> msg(G);
     std::vector<unsigned long long> key(G, MGPU_NO_RESULT), winner(G, MGPU_NO_RESULT);
     std::vector<double> t_compute(G, 0.0), t_reduce(G, 0.0);
@@ -168,9 +175,12 @@ extern "C" int tspcuda_mgpu_multistart(tspcuda_mgpu *m, int two_opt, int first_s
             int bs = -1;
             double bc = 0;
             const int f = first_start + g * stride, st = stride * G;
-            int e = two_opt ? tspcuda_multistart_two_opt(c, f, count, st, nullptr, nullptr, nullptr, &bs, path.data(), &bc)
-                            : tspcuda_nn_multi(c, f, count, st, nullptr, &bs, path.data(), &bc);
+            // every GPU runs against the same limit and keeps the best of the prefix of ITS shard it got to (the union of
+            // those prefixes is what a time-limited run of the reference's ascending loop corresponds to, heuristics.c:83-90)
+            int e = job(c, f, count, st, &bs, path.data(), &bc, &taken[g]);
+            if (e == TSPCUDA_DEADLINE_EXCEEDED) { late[g] = 1; e = TSPCUDA_OK; }
             if (e) fail_here(e, tspcuda_last_error());
+            else if (bs < 0) key[g] = MGPU_NO_RESULT;                            // the limit passed before this shard's first start
             else if (bc < 0 || bc >= (double)(1ll << 42)) fail_here(TSPCUDA_OUT_OF_RANGE, "tour cost beyond the reduction key");
             else key[g] = ((unsigned long long)(long long)bc << MGPU_START_BITS) | (unsigned long long)bs;
         }
@@ -216,9 +226,38 @@ extern "C" int tspcuda_mgpu_multistart(tspcuda_mgpu *m, int two_opt, int first_s
     m->last_reduce_ms = *std::max_element(t_reduce.begin(), t_reduce.end());
     if (compute_ms_out) *compute_ms_out = m->last_compute_ms;
     if (reduce_ms_out) *reduce_ms_out = m->last_reduce_ms;
-    if (winner[0] == MGPU_NO_RESULT) return fail(TSPCUDA_INTERNAL, "no shard produced a tour");
+    bool any_late = false;
+    int total_taken = 0;
+    for (int g = 0; g < G; ++g) { any_late = any_late || late[g]; total_taken += taken[g]; }
+    if (starts_done_out) *starts_done_out = total_taken;
+    if (winner[0] == MGPU_NO_RESULT) {
+        if (any_late) { if (best_start_out) *best_start_out = -1; return TSPCUDA_DEADLINE_EXCEEDED; }
+        return fail(TSPCUDA_INTERNAL, "no shard produced a tour");
+    }
     if (best_start_out) *best_start_out = (int)(winner[0] & ((1ull << MGPU_START_BITS) - 1));
     if (best_cost_out) *best_cost_out = (double)(long long)(winner[0] >> MGPU_START_BITS);
     if (best_path_out) std::memcpy(best_path_out, h_path.data(), sizeof(int) * (size_t)n);
-    return TSPCUDA_OK;
+    return any_late ? TSPCUDA_DEADLINE_EXCEEDED : TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_mgpu_multistart(tspcuda_mgpu *m, int two_opt, int first_start, int nstarts, int stride, double time_limit_s,
+                                       int *best_start_out, int *best_path_out, double *best_cost_out, int *starts_done_out,
+                                       double *compute_ms_out, double *reduce_ms_out) {
+    const ShardJob job = [=](tspcuda_ctx *c, int f, int count, int st, int *bs, int *path, double *bc, int *taken) {
+        return two_opt ? tspcuda_multistart_two_opt(c, f, count, st, time_limit_s, nullptr, nullptr, nullptr, bs, path, bc, taken)
+                       : tspcuda_nn_multi(c, f, count, st, time_limit_s, nullptr, bs, path, bc, taken);
+    };
+    return mgpu_run(m, job, first_start, nstarts, stride, best_start_out, best_path_out, best_cost_out, starts_done_out, compute_ms_out,
+                    reduce_ms_out);
+}
+
+// Config 5: tabu / VNS restarts sharded over the GPUs (tspcuda_restarts on every shard, same reduction as the multi-start).
+extern "C" int tspcuda_mgpu_restarts(tspcuda_mgpu *m, int kind, int first_start, int nstarts, int stride, int iters, unsigned seed,
+                                     double time_limit_s, int *best_start_out, int *best_path_out, double *best_cost_out,
+                                     int *restarts_done_out, double *compute_ms_out, double *reduce_ms_out) {
+    const ShardJob job = [=](tspcuda_ctx *c, int f, int count, int st, int *bs, int *path, double *bc, int *taken) {
+        return tspcuda_restarts(c, kind, f, count, st, iters, seed, time_limit_s, bs, path, bc, taken);
+    };
+    return mgpu_run(m, job, first_start, nstarts, stride, best_start_out, best_path_out, best_cost_out, restarts_done_out, compute_ms_out,
+                    reduce_ms_out);
 }

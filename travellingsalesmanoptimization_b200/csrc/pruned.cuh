@@ -241,7 +241,10 @@ __device__ __forceinline__ void probe_load(const TourView &V, int p, Probe &P, i
 // right after the barrier that ends that move (every thread reads pos[a], pos[b] on entry of
 // apply_move, so it cannot be written earlier); scans that start behind the same barrier take those
 // two positions from registers instead of racing with that write.
-struct PosPatch { int node0, pos0, node1, pos1; };
+// node2 / node3: the other two nodes whose tour edges the previous move changed (a and succ b); together with node0 (b)
+// and node1 (succ a) they are the only nodes whose cached neighbour list (NbCache below) is out of date.
+struct PosPatch { int node0, pos0, node1, pos1, node2, node3; };
+#define POSPATCH_NONE {-1, 0, -1, 0, -1, -1}
 
 // Cell box that contains every node w with cost(u,w) < max(dn[p], dn[p-1]).  false: empty search.
 template <class M>
@@ -264,7 +267,7 @@ __device__ __forceinline__ bool probe_box(const SpatialGrid &G, const Probe &P, 
 // compaction, no atomics), and the records are EVALUATED afterwards one per lane, several in flight
 // per lane: every lane busy whatever the box sizes were, and no gather chain inside the search loops.
 #ifndef TSP_PR_WBUF
-#define TSP_PR_WBUF 2048
+#define TSP_PR_WBUF 512
 #endif
 constexpr int PR_WBUF = TSP_PR_WBUF;        // records per warp buffer (16 bytes each); flushed when nearly full
 
@@ -467,6 +470,140 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
     pairs_eval<M, NE, TABU>(V, F, wbuf, wcount, best, bestkey);
 }
 
+// ---- per-node neighbour cache: phase 1 without the searches ----------------------------------------------
+// What a search around node u returns -- the nodes w with cost(u,w) below the larger of u's two tour-edge costs,
+// and those costs -- depends on u's two tour edges only, and a 2-opt move changes the tour edges of exactly FOUR
+// nodes (a, succ a, b, succ b; every node inside the reversed segment keeps both edges, only their orientation
+// flips).  So the result is kept per NODE, one 128-byte line each: slot 0 = {count, -}, slots 1..NB_CAP = {w, K-offset
+// cost(u,w)}.  A scan then reads the line of the node at every position, re-derives which of the two pair types each
+// record feeds from the CURRENT edge costs (orientation-independent: K < dn[p] -> pair {p, pos w}, K < dn[p-1] ->
+// pair {p-1, pos w - 1}) and hands the records to pairs_eval as before: the candidate set is the same set of
+// (u, w, cost) triples the searches would produce, so the argmin is unchanged.  Only stale nodes are searched: the
+// four of the previous move (carried in registers, PosPatch -- the kernel never has to write a "stale" mark), nodes
+// never searched yet (count NB_STALE), and nodes whose list does not fit a line (they stay NB_STALE and are searched
+// in every scan, as every node was before).  A search is done by the whole warp over the box's cell rows and
+// rewrites the line; boxes beyond PR_COOP_MAX nodes go to the phase-2 queue.  pla85900: 1.47e6 candidate nodes per
+// scan become ~n line reads + a handful of searches.
+constexpr int NB_STRIDE = 16;                  // int2 slots per node
+constexpr int NB_CAP = NB_STRIDE - 1;
+constexpr int NB_STALE = -1;
+#ifndef TSP_PR_COOP_MAX
+#define TSP_PR_COOP_MAX 512
+#endif
+constexpr int PR_COOP_MAX = TSP_PR_COOP_MAX;
+
+__global__ void nb_invalidate_kernel(int2 *nb, int n) {
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) nb[(size_t)u * NB_STRIDE].x = NB_STALE;
+}
+__global__ void nb_invalidate_list_kernel(int2 *nb, const int *nodes, int count) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) nb[(size_t)nodes[k] * NB_STRIDE].x = NB_STALE;
+}
+
+template <class M, int NE>
+__device__ __forceinline__ void pruned_phase1_cached(const TourView &V, const SpatialGrid &G, const PosPatch &F, int t, int nthreads,
+                                                     unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, int2 *nb, int &best,
+                                                     unsigned long long &bestkey, long long &ncand) {
+    int wcount = 0;
+    const int n = V.n;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1;
+    for (int p0 = t - lane; p0 < n; p0 += nthreads) {              // warp-uniform trip count
+        const int p = p0 + lane;
+        int ida = 0, dnp = 0, dnm = 0, cnt = 0;
+        bool stale = false;
+        if (p < n) {
+            ida = V.tid[p];
+            dnp = V.dn[p];
+            dnm = V.dn[p == 0 ? n - 1 : p - 1];
+            cnt = nb[(size_t)ida * NB_STRIDE].x;
+            stale = cnt < 0 || ida == F.node0 || ida == F.node1 || ida == F.node2 || ida == F.node3;
+            if (stale) cnt = 0;
+        }
+        // the cached lists of the warp's 32 positions, in lockstep
+        const int maxc = __reduce_max_sync(FULL, cnt);
+        const int2 *line = nb + (size_t)ida * NB_STRIDE + 1;
+        for (int j = 0; j < maxc; ++j) {
+            if (wcount > PR_WBUF - 32) {                           // warp-uniform: flush
+                __syncwarp();
+                pairs_eval<M, NE, false>(V, F, wbuf, wcount, best, bestkey);
+                __syncwarp();
+                wcount = 0;
+            }
+            int2 r = make_int2(0, 0);
+            if (j < cnt) r = line[j];
+            const unsigned type = j < cnt ? ((r.y < dnp ? 1u : 0u) | (r.y < dnm ? 2u : 0u)) : 0u;
+            const unsigned mask = __ballot_sync(FULL, type != 0);
+            if (type) wbuf[wcount + __popc(mask & lt)] = make_uint4((unsigned)p, (unsigned)r.x, (unsigned)r.y, type);
+            wcount += __popc(mask);
+        }
+        ncand += cnt;
+        // stale nodes: one warp-wide search each, which also rewrites the node's line
+        unsigned sm = __ballot_sync(FULL, stale);
+        while (sm) {
+            const int src = __ffs(sm) - 1;
+            sm &= sm - 1;
+            const int sp = __shfl_sync(FULL, p, src), su = __shfl_sync(FULL, ida, src);
+            const int sdnp = __shfl_sync(FULL, dnp, src), sdnm = __shfl_sync(FULL, dnm, src);
+            int2 *blk = nb + (size_t)su * NB_STRIDE;
+            const int rr = max(sdnp, sdnm) - KOFF;
+            if (rr <= 0) {                                         // both tour edges cost 0: nothing can be cheaper
+                if (lane == 0) blk[0].x = 0;
+                continue;
+            }
+            const double2 u = V.pxy[sp];
+            const double Rad = M::radius((double)rr);
+            const int cx0 = max(0, min(G.W - 1, __double2int_rd((u.x - Rad - G.gx0) * G.inv_cell)));
+            const int cx1 = max(0, min(G.W - 1, __double2int_rd((u.x + Rad - G.gx0) * G.inv_cell)));
+            const int cy0 = max(0, min(G.H - 1, __double2int_rd((u.y - Rad - G.gy0) * G.inv_cell)));
+            const int cy1 = max(0, min(G.H - 1, __double2int_rd((u.y + Rad - G.gy0) * G.inv_cell)));
+            const int nrows = cy1 - cy0 + 1;
+            int tot = 0;
+            for (int r = lane; r < nrows; r += 32) tot += G.cell_start[(cy0 + r) * G.W + cx1 + 1] - G.cell_start[(cy0 + r) * G.W + cx0];
+            tot = __reduce_add_sync(FULL, tot);
+            if (tot > PR_COOP_MAX) {                               // a long tour edge: the box goes to phase 2, the line stays stale
+                if (lane == 0) {
+                    const unsigned long long old = atomicAdd(qctr, (1ull << 40) | (unsigned long long)nrows);
+                    BigBox bx;
+                    bx.p = sp; bx.cy0 = cy0; bx.cx0 = cx0; bx.cx1 = cx1; bx.nrows = nrows; bx.pad = 0;
+                    bx.base = (long long)(old & PR_UNIT_MASK);
+                    boxes[old >> 40] = bx;
+                    blk[0].x = NB_STALE;
+                }
+                continue;
+            }
+            if (lane == 0) ncand += tot;
+            int stored = 0;
+            for (int r = 0; r < nrows; ++r) {
+                const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
+                for (int k0 = lo; k0 < hi; k0 += 32) {
+                    if (wcount > PR_WBUF - 32) {
+                        __syncwarp();
+                        pairs_eval<M, NE, false>(V, F, wbuf, wcount, best, bestkey);
+                        __syncwarp();
+                        wcount = 0;
+                    }
+                    const int k = min(k0 + lane, hi - 1);
+                    const double2 c = G.cxy[k];
+                    const int w = G.cnode[k];
+                    const int K = M::K(u.x, u.y, c.x, c.y);
+                    const unsigned type = (k0 + lane < hi && w != su) ? ((K < sdnp ? 1u : 0u) | (K < sdnm ? 2u : 0u)) : 0u;
+                    const unsigned mask = __ballot_sync(FULL, type != 0);
+                    if (type) {
+                        const int o = __popc(mask & lt);
+                        if (stored + o < NB_CAP) blk[1 + stored + o] = make_int2(w, K);
+                        wbuf[wcount + o] = make_uint4((unsigned)sp, (unsigned)w, (unsigned)K, type);
+                    }
+                    stored += __popc(mask);
+                    wcount += __popc(mask);
+                }
+            }
+            if (lane == 0) blk[0].x = stored <= NB_CAP ? stored : NB_STALE;
+        }
+    }
+    __syncwarp();
+    pairs_eval<M, NE, false>(V, F, wbuf, wcount, best, bestkey);
+}
+
 // Phase 2 (behind a barrier): the queued boxes, cut into (box, cell row) units -- one contiguous
 // range of the cell-sorted node array each -- split evenly over the `nwarps` cooperating warps;
 // this warp is number `gw`.  q = the packed counter after phase 1.
@@ -519,12 +656,11 @@ __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGr
 }
 
 // ---- K7: whole-GPU persistent pruned descent (cooperative launch, one CTA per SM) ----------------
-template <class M, int BLK, int L>
+template <class M, int BLK>
 __global__ void __launch_bounds__(BLK, 1)
 descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
-                      long long max_moves, unsigned long long *qctr, BigBox *boxes, uint4 *wbuf_all) {
+                      long long max_moves, unsigned long long *qctr, BigBox *boxes, uint4 *wbuf_all, int2 *nb) {
     constexpr int WARPS = BLK / 32;
-    constexpr int NC1 = BLK > 512 ? PR_NC_BIG : PR_NC;   // candidates per lane and trip while collecting
     constexpr int NE = BLK > 512 ? 2 : 4;                // records in flight per lane while evaluating (64 / 128 registers)
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned long long s_key;
@@ -534,7 +670,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
     const long long gw = (long long)blockIdx.x * WARPS + warp;
     const long long Wtot = (long long)gridDim.x * WARPS;
     uint4 *wbuf = wbuf_all + (size_t)gw * PR_WBUF;
-    PosPatch F = {-1, 0, -1, 0};
+    PosPatch F = POSPATCH_NONE;
 #ifdef TSP_PHASE_TIMING
     unsigned long long tprev = 0;
     if (gtid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tprev));
@@ -558,7 +694,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #ifdef TSP_PHASE_TIMING
         unsigned long long tw0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw0));
 #endif
-        pruned_phase1<M, NC1, NE, L, false>(V, G, F, gtid, gsize, qctr, boxes, wbuf, best, bestkey, ncand, 0);
+        pruned_phase1_cached<M, NE>(V, G, F, gtid, gsize, qctr, boxes, wbuf, nb, best, bestkey, ncand);
 #ifdef TSP_PHASE_TIMING
         {   // slowest and average warp of phase 1 (phase_ns[3] = sum over scans of the max, [4]/[5] reused below)
             unsigned long long tw1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw1));
@@ -606,7 +742,14 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         grid.sync();
         PHASE_MARK(2)
         F.node0 = b; F.pos0 = seg_s; F.node1 = V.tid[seg_e]; F.pos1 = seg_e;
+        F.node2 = a; F.node3 = V.tid[seg_e + 1];                               // with node0/node1: the four nodes whose tour edges changed
         if (gtid == 0) { V.pos[F.node0] = F.pos0; V.pos[F.node1] = F.pos1; }   // deferred end-node positions
+    }
+    // move cap reached: the last move's four nodes were not searched again in this launch, so their cached lines are
+    // marked in memory for the next one (after a local optimum F's nodes were rewritten by the final scan: harmless)
+    if (gtid == 0 && F.node0 >= 0) {
+        nb[(size_t)F.node0 * NB_STRIDE].x = NB_STALE; nb[(size_t)F.node1 * NB_STRIDE].x = NB_STALE;
+        nb[(size_t)F.node2 * NB_STRIDE].x = NB_STALE; nb[(size_t)F.node3 * NB_STRIDE].x = NB_STALE;
     }
 }
 
@@ -638,7 +781,7 @@ tabu_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, TabuCtl T
     const long long gw = (long long)blockIdx.x * WARPS + warp;
     const long long Wtot = (long long)gridDim.x * WARPS;
     uint4 *wbuf = wbuf_all + (size_t)gw * PR_WBUF;
-    PosPatch F = {-1, 0, -1, 0};
+    PosPatch F = POSPATCH_NONE;
     if (threadIdx.x == 0) { s_cost = T.cost; s_bestcost = T.best_cost; s_moves = 0; s_bestiter = -1; s_lastdelta = 0; }
     int bound = bound0;
     unsigned slot = 0;
@@ -706,63 +849,63 @@ tabu_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, TabuCtl T
 }
 
 // ---- K8: one CTA per descent, pruned scan, tours in CTA-private global-memory slots -------------------
-// Multi-start work (h_greedy_2opt, heuristics.c:74-116): a pruned scan is a few hundred thousand
-// candidate evaluations, far too little to fill 148 SMs, so the SMs run independent descents
-// instead.  CTAs pull start indices from an atomic counter in ascending order; the tour of the
-// current start lives in the CTA's own slot of global memory (L1/L2 resident, any n), every
-// barrier is a __syncthreads.  Each CTA keeps its best tour under the reference's incumbent rule
-// (strict '<' in ascending start order, tsp.c:671); the host takes the (cost, start)-minimum.
+// Multi-start work (h_greedy_2opt, heuristics.c:74-116): a pruned scan is a few thousand record
+// evaluations, far too little to fill 148 SMs, so the SMs run independent descents instead.  CTAs pull
+// start indices from an atomic counter in ascending order; the tour of the current start and its
+// neighbour cache live in the CTA's own slot of global memory (L1/L2 resident, any n), every barrier is
+// a __syncthreads.  Each CTA keeps its best tour under the reference's incumbent rule (strict '<' in
+// ascending start order, tsp.c:671); the host takes the (cost, start)-minimum.
 struct MultiSlots {
     double2 *pxy;      // [slots][n+1]
     int *tid, *dn;     // [slots][n+1]
     int *pos;          // [slots][n]
     BigBox *boxes;     // [slots][n]
+    int2 *nb;          // [slots][n * NB_STRIDE]  neighbour cache of the slot's current descent
     int *best_path;    // [slots][n]  successor array of the CTA's best tour
     long long *best_cost;   // [slots]
     int *best_start;        // [slots]
 };
 
+// per-start outcome of a batch (status_out): a start is handed out at most once, in ascending order
+enum { MS_NOT_STARTED = 0, MS_COMPLETE = 1, MS_CUT = 2 };
+
 // CL > 1: a thread-block CLUSTER of CL CTAs (CL SMs) shares one descent -- for batches with fewer starts than SMs,
 // where one CTA per descent would leave SMs idle while every descent still takes its full single-SM time.  The
-// tour stays in the cluster's global-memory slot; the few scalars of a scan (argmin key, box-queue counter, cost,
-// current start) live in the shared memory of the cluster's first CTA and are reached by the others through
-// distributed shared memory; every barrier is a cluster barrier (barrier.cluster, release/acquire at cluster scope).
+// tour stays in the cluster's global-memory slot; the few scalars of a scan (box-queue counter, cost, current start,
+// stop flag) live in the shared memory of the cluster's first CTA and are reached by the others through distributed
+// shared memory; every barrier is a cluster barrier (barrier.cluster, release/acquire at cluster scope), which also
+// orders the team's global-memory accesses to the tour (scripts/cluster_probe.cu: no stale read without extra fences).
 template <int CL>
 __device__ __forceinline__ void team_sync() {
-    if (CL == 1) {
-        __syncthreads();
-    } else {
-        // the tour lives in GLOBAL memory and is read through each SM's own L1.  The cluster barrier's own release /
-        // acquire already orders those accesses (scripts/cluster_probe.cu sees no stale read without fences); the
-        // gpu-scope fences are kept as a cheap guard (~1 us against scans of 0.1 - 2 ms)
-        __threadfence();
-        cg::this_cluster().sync();
-        __threadfence();
-    }
+    if (CL == 1) __syncthreads();
+    else cg::this_cluster().sync();
 }
 
+// stop (may be NULL): a device word the host raises when the caller's time limit has passed.  It is looked at where the
+// reference looks at its clock: before a start is taken (heuristics.c:83-90) and before every scan of a descent
+// (refinment.c:17-24); a descent that is cut keeps the tour it has reached, which still competes for the incumbent
+// exactly as ref_2opt's update_incumbent does after DEADLINE_EXCEEDED (refinment.c:29-34).
 template <class M, int BLK, int CL>
 __global__ void __launch_bounds__(BLK, 1)
 multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const int *__restrict__ order_all, int first_start,
                     int stride, int nstarts, int *next_start, MultiSlots S, long long *final_cost, long long *moves_out,
-                    unsigned long long *cand_total, uint4 *wbuf_all) {
+                    int *status_out, unsigned long long *cand_total, uint4 *wbuf_all, const int *stop) {
     constexpr int WARPS = BLK / 32;
-    constexpr int NC1 = BLK > 512 ? PR_NC_BIG : PR_NC;
     constexpr int NE = BLK > 512 ? 2 : 4;
     constexpr int TEAM = BLK * CL;                      // threads sharing a descent
-    __shared__ unsigned long long s_key_, s_q_;
+    __shared__ unsigned long long s_key_[2], s_q_;
     __shared__ long long s_cost_, s_bestcost_;
-    __shared__ int s_cur_;
+    __shared__ int s_cur_, s_stop_;
     unsigned rank = 0;
     unsigned long long *s_q = &s_q_;
     long long *s_cost = &s_cost_, *s_bestcost = &s_bestcost_;
-    int *s_cur = &s_cur_;
+    int *s_cur = &s_cur_, *s_stop = &s_stop_;
     if (CL > 1) {                                       // the scalars of the cluster's first CTA, through DSMEM
         cg::cluster_group cluster = cg::this_cluster();
         rank = cluster.block_rank();
         s_q = cluster.map_shared_rank(&s_q_, 0);
         s_cost = cluster.map_shared_rank(&s_cost_, 0); s_bestcost = cluster.map_shared_rank(&s_bestcost_, 0);
-        s_cur = cluster.map_shared_rank(&s_cur_, 0);
+        s_cur = cluster.map_shared_rank(&s_cur_, 0); s_stop = cluster.map_shared_rank(&s_stop_, 0);
     }
     const int t = (int)rank * BLK + threadIdx.x, warp = t >> 5, lane = t & 31;
     const size_t n1 = (size_t)n + 1, slot = blockIdx.x / CL;
@@ -774,14 +917,18 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     V.dns = V.dn;
     V.pos = S.pos + slot * (size_t)n;
     BigBox *boxes = S.boxes + slot * (size_t)n;
+    int2 *nb = S.nb + slot * (size_t)n * NB_STRIDE;
     int *best_path = S.best_path + slot * (size_t)n;
     uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * PR_WBUF;
-    if (t == 0) { *s_bestcost = -1; S.best_cost[slot] = -1; S.best_start[slot] = -1; }
+    if (t == 0) { *s_bestcost = -1; *s_stop = 0; S.best_cost[slot] = -1; S.best_start[slot] = -1; }
     long long ncand = 0;
 
     for (;;) {
         team_sync<CL>();
-        if (t == 0) *s_cur = atomicAdd(next_start, 1);
+        if (t == 0) {
+            const bool halted = stop != nullptr && *(volatile const int *)stop != 0;
+            *s_cur = halted ? nstarts : atomicAdd(next_start, 1);
+        }
         team_sync<CL>();
         const int cur = *s_cur;
         if (CL > 1) team_sync<CL>();                    // nobody leaves (or rewrites s_cur) while a peer still reads it remotely
@@ -791,9 +938,10 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             const int node = order[p == n ? 0 : p];
             V.pxy[p] = xy[node];
             V.tid[p] = node;
-            if (p < n) V.pos[node] = p;
+            if (p < n) { V.pos[node] = p; nb[(size_t)p * NB_STRIDE].x = NB_STALE; }    // a new tour: every cached line is stale
         }
-        if (t == 0) *s_cost = 0;
+        if (t == 0) { *s_cost = 0; *s_q = 0; }
+        if (threadIdx.x == 0) { s_key_[0] = KEY_EMPTY; s_key_[1] = KEY_EMPTY; }
         team_sync<CL>();
         long long local = 0;
         for (int p = t; p < n; p += TEAM) {
@@ -805,42 +953,52 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
         }
         for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(FULL, local, o);
         if (lane == 0) atomicAdd((unsigned long long *)s_cost, (unsigned long long)local);
+        team_sync<CL>();
         long long moves = 0;
-        PosPatch F = {-1, 0, -1, 0};
+        unsigned par = 0;
+        bool cut = false;
+        PosPatch F = POSPATCH_NONE;
+        // three barriers per scan + move.  The argmin key is double-buffered by iteration parity and the queue counter is
+        // re-armed during the move, when nobody uses it; the positions of the two segment ends are written behind the last
+        // barrier and bridged by F.  The key stays per CTA and is combined by reading the peers' copies: a 64-bit atomicMin
+        // is not atomic between a CTA's own shared-memory path and its peers' distributed-shared-memory path (measured,
+        // scripts/cluster_probe.cu: lost updates), 64-bit atomicAdd is.
         for (;;) {
-            // the argmin key stays per CTA and is combined by reading the peers' copies: a 64-bit atomicMin is not
-            // atomic between a CTA's own shared-memory path and its peers' distributed-shared-memory path
-            // (measured, scripts/cluster_probe.cu: lost updates), 64-bit atomicAdd is
-            if (threadIdx.x == 0) s_key_ = KEY_EMPTY;
-            if (t == 0) *s_q = 0;
-            team_sync<CL>();
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
-            pruned_phase1<M, NC1, NE, 1, false>(V, G, F, t, TEAM, s_q, boxes, wbuf, best, bestkey, ncand, 0);
+            pruned_phase1_cached<M, NE>(V, G, F, t, TEAM, s_q, boxes, wbuf, nb, best, bestkey, ncand);
             team_sync<CL>();
             pruned_phase2<M, NE, false>(V, G, F, warp, WARPS * CL, *s_q, boxes, wbuf, best, bestkey, ncand, 0);
             bestkey = warp_min_key(bestkey);
-            if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key_, bestkey);
+            if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key_[par], bestkey);
             team_sync<CL>();
-            unsigned long long kbest = s_key_;
+            unsigned long long kbest = s_key_[par];
             if (CL > 1) {
                 cg::cluster_group cluster = cg::this_cluster();
 #pragma unroll
-                for (int r = 0; r < CL; ++r) kbest = min(kbest, *cluster.map_shared_rank(&s_key_, r));
+                for (int r = 0; r < CL; ++r) kbest = min(kbest, *cluster.map_shared_rank(&s_key_[par], r));
             }
             if (kbest == KEY_EMPTY) break;                      // local optimum (refinment.c:27)
             const int a = key_a(kbest), b = key_b(kbest);
             int seg_s, seg_e;
             apply_move<M>(V, a, b, t, TEAM, false, seg_s, seg_e);
-            if (t == 0) *s_cost += key_delta(kbest);
+            if (t == 0) {
+                *s_cost += key_delta(kbest);
+                *s_q = 0;
+                if (stop != nullptr) *s_stop = *(volatile const int *)stop;
+            }
+            if (threadIdx.x == 0) s_key_[par ^ 1] = KEY_EMPTY;
             ++moves;
+            par ^= 1;
             team_sync<CL>();
             F.node0 = b; F.pos0 = seg_s; F.node1 = V.tid[seg_e]; F.pos1 = seg_e;
+            F.node2 = a; F.node3 = V.tid[seg_e + 1];
             if (t == 0) { V.pos[F.node0] = F.pos0; V.pos[F.node1] = F.pos1; }
+            if (stop != nullptr && *s_stop != 0) { cut = true; break; }      // time limit: checked before the next scan
         }
-        // kbest == KEY_EMPTY was read behind a barrier: every thread is here, the tour is final
+        // left behind a barrier with a team-uniform condition: every thread is here, the tour is final
         const long long fc = *s_cost;
-        if (t == 0) { final_cost[cur] = fc; moves_out[cur] = moves; }
+        if (t == 0) { final_cost[cur] = fc; moves_out[cur] = moves; status_out[cur] = cut ? MS_CUT : MS_COMPLETE; }
         const long long bcst = *s_bestcost;
         const bool better = bcst < 0 || fc < bcst;                        // strict '<', ascending starts per team
         if (better)

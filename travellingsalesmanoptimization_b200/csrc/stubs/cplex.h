@@ -1,5 +1,5 @@
 /*
- * Build-time stand-in for IBM CPLEX's <cplex.h> (TEST INFRASTRUCTURE, oracle/ only).
+ * Build-time stand-in for IBM CPLEX's <cplex.h> (needed wherever the reference driver is compiled without CPLEX: the drop-in CLI and the test builds).
  *
  * The reference's driver (src/main.c) includes algorithms/matheuristics.h:1 -> <cplex.h>
  * only to see a handful of opaque handle types in prototypes (cplex_model.h:16-18,44-88).
@@ -7,8 +7,8 @@
  * out of scope (north_star: "may be stubbed at build time when the library is absent").
  * Only the opaque types the headers mention are declared here; no CPLEX entry point exists.
  */
-#ifndef TSPCUDA_ORACLE_CPLEX_STUB_H_
-#define TSPCUDA_ORACLE_CPLEX_STUB_H_
+#ifndef TSPCUDA_CPLEX_STUB_H_
+#define TSPCUDA_CPLEX_STUB_H_
 
 typedef struct tspcuda_stub_cpxenv *CPXENVptr;
 typedef struct tspcuda_stub_cpxlp *CPXLPptr;

@@ -2,9 +2,11 @@
 // kernels of kernels.cuh.  No CPU implementation of any algorithm lives here: without a CUDA
 // device every compute entry point fails with TSPCUDA_UNAVAILABLE.
 #include <cuda_runtime.h>
+#include <unistd.h>
 
 #include <algorithm>
 #include <chrono>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -58,8 +60,8 @@ enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3, M_G
 struct ScratchBuf { void *p = nullptr; size_t bytes = 0; };
 enum {
     SC_NN_CXY, SC_NN_CID, SC_NN_ORDER, SC_NN_COST, SC_NN_SLOT, SC_BEST_PATH, SC_NEXT, SC_DCOST, SC_DMOVES, SC_DPATHS,
-    SC_M_PXY, SC_M_TID, SC_M_DN, SC_M_POS, SC_M_BOXES, SC_M_BPATH, SC_M_BCOST, SC_M_BSTART, SC_M_CAND,
-    SC_T_TEN, SC_T_TRACE, SC_T_BEST, SC_T_OUT, SC_COUNT
+    SC_M_PXY, SC_M_TID, SC_M_DN, SC_M_POS, SC_M_BOXES, SC_M_BPATH, SC_M_BCOST, SC_M_BSTART, SC_M_CAND, SC_M_NB, SC_DSTATUS,
+    SC_T_TEN, SC_T_TRACE, SC_T_BEST, SC_T_OUT, SC_NB_LIST, SC_COUNT
 };
 
 struct tspcuda_ctx {
@@ -92,6 +94,11 @@ struct tspcuda_ctx {
     unsigned long long *d_qctr = nullptr;
     BigBox *d_boxes = nullptr;
     uint4 *d_wbuf = nullptr;         // per-warp record buffers of the pruned kernels (num_sms * 32 warps)
+    int2 *d_nb = nullptr;            // neighbour cache of the resident tour (pruned.cuh: one 128-byte line per node)
+    bool nb_valid = false;           // false: the tour changed behind the cache's back (upload, full-scan or tabu moves)
+    int *d_stop = nullptr;           // time-limit flag of the batched multi-start kernels, raised through aux_stream
+    int *h_one = nullptr;            // pinned constant 1: source of that copy (a DMA copy needs no SM, a memset kernel might)
+    cudaStream_t aux_stream = nullptr;
     int pruned_blocks = 0;           // cooperative grid of descend_pruned_kernel (0: unavailable)
     int k8_clusters[4] = {0, 0, 0, 0};   // co-resident K8 clusters of 1/2/4/8 CTAs (cudaOccupancyMaxActiveClusters), filled at first use
     int pruned_block = 0;            // its CTA size
@@ -133,7 +140,9 @@ extern "C" void tspcuda_destroy(tspcuda_ctx *c) {
     cudaFree(c->d_tabu); cudaFree(c->d_key); cudaFree(c->d_state); cudaFree(c->d_log);
     cudaFree(c->d_matrix); cudaFree(c->d_sum); cudaFree(c->d_flush);
     cudaFree(c->d_cell_start); cudaFree(c->d_cell_count); cudaFree(c->d_cnode); cudaFree(c->d_cxy);
-    cudaFree(c->d_qctr); cudaFree(c->d_boxes); cudaFree(c->d_wbuf);
+    cudaFree(c->d_qctr); cudaFree(c->d_boxes); cudaFree(c->d_wbuf); cudaFree(c->d_nb); cudaFree(c->d_stop);
+    if (c->h_one) cudaFreeHost(c->h_one);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     for (ScratchBuf &b : c->scratch) cudaFree(b.p);
     if (c->tev0) cudaEventDestroy(c->tev0);
     if (c->tev1) cudaEventDestroy(c->tev1);
@@ -199,6 +208,10 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
     if (bps <= 0) { tspcuda_destroy(c); return fail(TSPCUDA_INTERNAL, "descent kernel cannot be resident (built for sm_100a; device is sm_%d%d)", prop.major, prop.minor); }
     c->max_coop_blocks = bps * c->num_sms;
     CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKC(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    CKC(cudaMalloc(&c->d_stop, sizeof(int)));
+    CKC(cudaMallocHost(&c->h_one, sizeof(int)));
+    *c->h_one = 1;
     CKC(cudaEventCreate(&c->ev0));
     CKC(cudaEventCreate(&c->ev1));
     CKC(cudaEventCreate(&c->tev0));
@@ -254,6 +267,7 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         CKC(cudaMalloc(&c->d_qctr, sizeof(unsigned long long)));
         CKC(cudaMalloc(&c->d_boxes, sizeof(BigBox) * n));
         CKC(cudaMalloc(&c->d_wbuf, sizeof(uint4) * (size_t)PR_WBUF * 32 * c->num_sms));
+        CKC(cudaMalloc(&c->d_nb, sizeof(int2) * (size_t)NB_STRIDE * n));
         G.cell_start = c->d_cell_start; G.cnode = c->d_cnode; G.cxy = c->d_cxy;
         CKC(cudaMemsetAsync(c->d_cell_count, 0, sizeof(int) * ncells, c->stream));
         CKC(cudaMemsetAsync(c->d_qctr, 0, sizeof(unsigned long long), c->stream));
@@ -268,8 +282,8 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         // threads with two tour positions in phase 1
         c->pruned_block = (long long)c->num_sms * PRUNED_BLOCK >= n ? PRUNED_BLOCK : 1024;
         int pb = 0;
-        if (c->pruned_block == PRUNED_BLOCK) { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, PRUNED_BLOCK, 1>, PRUNED_BLOCK, 0))); }
-        else { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, 1024, 1>, 1024, 0))); }
+        if (c->pruned_block == PRUNED_BLOCK) { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, PRUNED_BLOCK>, PRUNED_BLOCK, 0))); }
+        else { DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&pb, descend_pruned_kernel<M, 1024>, 1024, 0))); }
         c->pruned_blocks = (pb > 0 && c->metric != M_GEO) ? c->num_sms : 0;     // the grid search is Euclidean
     }
     *out = c;
@@ -300,12 +314,13 @@ static inline int grid_for(int n, int cap) { return std::max(1, std::min(cap, (n
 
 // ---- tour slot -----------------------------------------------------------------------------
 // order already in c->d_order (device): build pxy/tid/pos/dn and the cost.
-static int tour_from_device_order(tspcuda_ctx *c) {
+static int tour_from_device_order(tspcuda_ctx *c, bool keep_nb = false) {
     const int n = c->n;
     const int g = grid_for(n + 1, 4 * c->num_sms);
     CK(cudaMemsetAsync(c->d_state, 0, sizeof(DescState), c->stream));
     c->dev_moves = 0;
     c->dev_candidates = 0;
+    if (!keep_nb) c->nb_valid = false;
     tour_init_kernel<<<g, 256, 0, c->stream>>>(c->tour, c->d_xy, c->d_order);
     DISPATCH_METRIC(c->metric, (tour_edges_kernel<M><<<g, 256, 0, c->stream>>>(c->tour, c->d_state)));
     c->stats.kernel_launches += 2;
@@ -380,12 +395,16 @@ static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max
     long long log_cap = c->log_cap;
     BigBox *boxes = c->d_boxes;
     uint4 *wbuf = c->d_wbuf;
-    void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &qctr, &boxes, &wbuf};
+    int2 *nb = c->d_nb;
+    if (!c->nb_valid) {                                        // the tour was replaced or moved by another kernel: every line is stale
+        nb_invalidate_kernel<<<grid_for(c->n, 4 * c->num_sms), 256, 0, c->stream>>>(nb, c->n);
+        c->stats.kernel_launches += 1;
+        c->nb_valid = true;
+    }
+    void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &qctr, &boxes, &wbuf, &nb};
     if (c->pruned_block == 1024)
-        return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, 1024, 1>, dim3(grid), dim3(1024), args, 0, c->stream);
-    if (4LL * c->n <= (long long)grid * PRUNED_BLOCK)          // four lanes per tour position in phase 1
-        return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK, 4>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
-    return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK, 1>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
+        return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, 1024>, dim3(grid), dim3(1024), args, 0, c->stream);
+    return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
 }
 
 // Run up to max_moves scan+move iterations on the device-resident tour (max_moves < 0: until no
@@ -427,7 +446,7 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
         c->chunk_no++;
         const double est = pruned ? std::max(c->est_pruned_s, 2e-6) : c->est_scan_s;
         long long chunk = (long long)std::max(4.0, std::min(8192.0, 0.1 / est));
-        if (probe) chunk = 4;
+        if (probe) chunk = 8;                                                          // (the first pruned scan after full scans rebuilds the neighbour cache)
         else if (can_prune && !pruned) chunk = std::min<long long>(chunk, 96);         // full scans in AUTO: re-probe soon
         c->probe_due = can_prune && !pruned;                                         // after a full chunk, probe again
         if (max_moves >= 0) chunk = std::min(chunk, max_moves - done);
@@ -445,6 +464,7 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
         CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         const long long applied = c->h_state->moves - c->dev_moves;
         c->dev_moves = c->h_state->moves;
+        if (!pruned && applied > 0) c->nb_valid = false;       // moves the neighbour cache has not seen
         const long long scans = applied + (c->h_state->status == 1 ? 1 : 0);
         c->stats.moves += applied;
         c->stats.scans += scans;
@@ -681,7 +701,13 @@ extern "C" int tspcuda_tabu_search(tspcuda_ctx *c, int *path, double *cost_inout
     const int grid = (int)std::max<long long>(1, std::min<long long>(c->max_coop_blocks, total_cols / ((c->block / 32) * 48)));
     TabuCtl T;
     T.tabu_list = c->d_tabu; T.best_tid = d_best.as<int>();
-    T.cost = (long long)*cost_inout; T.best_cost = (long long)incumbent_cost; T.pad = 0;
+    // the reference's "no incumbent yet" is DBL_MAX (tsp.c:37), API callers may pass +inf: both mean "anything is better"
+    if (std::isnan(incumbent_cost) || std::isnan(*cost_inout) || !std::isfinite(*cost_inout) || std::fabs(*cost_inout) >= 9.0e18)
+        return fail(TSPCUDA_INVALID_ARGUMENT, "tour cost / incumbent cost is not a usable number");
+    T.cost = (long long)*cost_inout;
+    T.best_cost = incumbent_cost >= 9.0e18 ? LLONG_MAX : (incumbent_cost <= -9.0e18 ? LLONG_MIN : (long long)incumbent_cost);
+    T.pad = 0;
+    c->nb_valid = false;                               // the tabu kernels move the tour without maintaining the neighbour cache
     TabuOut h_out{};
     h_out.best_iter = -1;
     long long moves = 0;
@@ -820,22 +846,58 @@ static int nn_alloc(tspcuda_ctx *c, NNScratch &S, int batch) {
     return TSPCUDA_OK;
 }
 
-extern "C" int tspcuda_nn_multi(tspcuda_ctx *c, int first_start, int nstarts, int stride, double *costs_out,
-                                int *best_start_out, int *best_path_out, double *best_cost_out) {
+// ---- time limits of the batched entry points ---------------------------------------------------------------
+// The reference looks at its clock before every start (heuristics.c:42-50, :83-90) and before every 2-opt scan
+// (refinment.c:17-24).  The batched kernels look at a device word instead, which the host raises once the limit has passed.
+struct Deadline {
+    bool on = false;
+    std::chrono::steady_clock::time_point end;
+    explicit Deadline(double limit_s) {
+        if (limit_s >= 0) { on = true; end = std::chrono::steady_clock::now() + std::chrono::duration_cast<std::chrono::steady_clock::duration>(std::chrono::duration<double>(limit_s)); }
+    }
+    bool passed() const { return on && std::chrono::steady_clock::now() >= end; }
+    double left() const { return on ? std::max(0.0, std::chrono::duration<double>(end - std::chrono::steady_clock::now()).count()) : -1.0; }
+};
+
+// Wait for everything queued on the context's stream; when the deadline passes meanwhile, raise the stop word by a DMA
+// copy on the auxiliary stream (a copy engine needs no SM; a memset kernel queued behind persistent CTAs might never run).
+static int wait_with_deadline(tspcuda_ctx *c, const Deadline &dl, bool *raised) {
+    if (dl.on) {
+        for (;;) {
+            const cudaError_t q = cudaStreamQuery(c->stream);
+            if (q == cudaSuccess) break;
+            if (q != cudaErrorNotReady) CK(q);
+            if (!*raised && dl.passed()) {
+                CK(cudaMemcpyAsync(c->d_stop, c->h_one, sizeof(int), cudaMemcpyHostToDevice, c->aux_stream));
+                *raised = true;
+            }
+            usleep(100);
+        }
+    }
+    CK(cudaStreamSynchronize(c->stream));
+    return TSPCUDA_OK;
+}
+
+extern "C" int tspcuda_nn_multi(tspcuda_ctx *c, int first_start, int nstarts, int stride, double time_limit_s, double *costs_out,
+                                int *best_start_out, int *best_path_out, double *best_cost_out, int *starts_done_out) {
     int e = use(c);
     if (e) return e;
     const int n = c->n;
+    if (starts_done_out) *starts_done_out = 0;
     if (nstarts <= 0 || stride <= 0) return fail(TSPCUDA_INVALID_ARGUMENT, "nstarts/stride");
     const long long last = (long long)first_start + (long long)(nstarts - 1) * stride;
     if (first_start < 0 || last >= n) return fail(TSPCUDA_UNAVAILABLE, "starting node not correct");   // heuristics.c:223-226
-    const int batch = std::min(nstarts, 8 * c->num_sms);
+    const Deadline dl(time_limit_s);
+    // with a time limit the clock is looked at between batches (the reference: before every start, heuristics.c:42-50)
+    const int batch = std::min(nstarts, (dl.on ? 2 : 8) * c->num_sms);
     NNScratch S;
     e = nn_alloc(c, S, batch);
     if (e) return e;
     std::vector<long long> hc(batch);
     long long best = -1;
-    int best_start = -1;
-    for (int done = 0; done < nstarts; done += batch) {
+    int best_start = -1, done = 0;
+    for (; done < nstarts; done += batch) {
+        if (dl.passed()) break;
         const int cnt = std::min(batch, nstarts - done);
         const int fs = first_start + done * stride;
         e = nn_batch(c, S, fs, cnt, stride, hc.data());
@@ -854,22 +916,24 @@ extern "C" int tspcuda_nn_multi(tspcuda_ctx *c, int first_start, int nstarts, in
             c->stats.d2h_bytes += (int64_t)sizeof(int) * n;
         }
     }
+    done = std::min(done, nstarts);
+    if (starts_done_out) *starts_done_out = done;
     if (best_start_out) *best_start_out = best_start;
     if (best_cost_out) *best_cost_out = (double)best;
-    return TSPCUDA_OK;
+    return done < nstarts ? TSPCUDA_DEADLINE_EXCEEDED : TSPCUDA_OK;
 }
 
 extern "C" int tspcuda_nn(tspcuda_ctx *c, int start, int *path_out, double *cost_out) {
     if (!c) return fail(TSPCUDA_INVALID_ARGUMENT, "null context");
     if (start < 0 || start >= c->n) return fail(TSPCUDA_UNAVAILABLE, "starting node not correct");     // heuristics.c:223-226
     int bs = -1;
-    return tspcuda_nn_multi(c, start, 1, 1, nullptr, &bs, path_out, cost_out);
+    return tspcuda_nn_multi(c, start, 1, 1, -1.0, nullptr, &bs, path_out, cost_out, nullptr);
 }
 
 // ---- multi-start NN + 2-opt (heuristics.c:74-116) --------------------------------------------
 template <class M, int BLK>
 static cudaError_t launch_cta_descents(tspcuda_ctx *c, const int *d_order, int count, int *d_next, long long *d_cost,
-                                       long long *d_moves, int *d_paths) {
+                                       long long *d_moves, int *d_paths, int *d_status, const int *d_stop) {
     const size_t smem = cta_smem_bytes(c->n, BLK / 32);
     cudaError_t e = cudaFuncSetAttribute(descend_cta_kernel<M, BLK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
@@ -877,7 +941,7 @@ static cudaError_t launch_cta_descents(tspcuda_ctx *c, const int *d_order, int c
     e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, descend_cta_kernel<M, BLK>, BLK, smem);
     if (e != cudaSuccess) return e;
     const int grid = std::max(1, std::min(count, std::max(1, per_sm) * c->num_sms));
-    descend_cta_kernel<M, BLK><<<grid, BLK, smem, c->stream>>>(c->d_xy, c->n, d_order, count, d_next, d_cost, d_moves, d_paths);
+    descend_cta_kernel<M, BLK><<<grid, BLK, smem, c->stream>>>(c->d_xy, c->n, d_order, count, d_next, d_cost, d_moves, d_paths, d_status, d_stop);
     return cudaGetLastError();
 }
 
@@ -906,16 +970,18 @@ struct PhaseClock {
 constexpr int K8_CLUSTER_MIN_N = 8192;
 constexpr int K8_CLUSTER_MIN_STARTS = 12;
 
-extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int nstarts, int stride, double *nn_costs_out,
-                                          double *final_costs_out, int64_t *moves_out, int *best_start_out,
-                                          int *best_path_out, double *best_cost_out) {
+extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int nstarts, int stride, double time_limit_s,
+                                          double *nn_costs_out, double *final_costs_out, int64_t *moves_out, int *best_start_out,
+                                          int *best_path_out, double *best_cost_out, int *starts_done_out) {
     PhaseClock clk;
     int e = use(c);
     if (e) return e;
     const int n = c->n;
+    if (starts_done_out) *starts_done_out = 0;
     if (nstarts <= 0 || stride <= 0) return fail(TSPCUDA_INVALID_ARGUMENT, "nstarts/stride");
     const long long last = (long long)first_start + (long long)(nstarts - 1) * stride;
     if (first_start < 0 || last >= n) return fail(TSPCUDA_UNAVAILABLE, "starting node not correct");
+    const Deadline dl(time_limit_s);
     // K8 (one CTA per descent, pruned scan, any n) when there are enough starts to occupy the SMs;
     // K6 (one CTA per descent, full scan, tour in shared memory) when every pair must be evaluated;
     // otherwise the starts descend one after the other on the whole GPU (K2 / K7).
@@ -927,10 +993,11 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
     NNScratch S;
     e = nn_alloc(c, S, batch);
     if (e) return e;
-    DevBuf best_path, next, dcost, dmoves, dpaths;
+    DevBuf best_path, next, dcost, dmoves, dpaths, dstatus;
     CK(scratch_get(c, SC_BEST_PATH, sizeof(int) * n, best_path));
     std::vector<long long> hc(batch), hf(batch), hm(batch);
-    DevBuf m_pxy, m_tid, m_dn, m_pos, m_boxes, m_bpath, m_bcost, m_bstart, m_cand;
+    std::vector<int> hs(batch);
+    DevBuf m_pxy, m_tid, m_dn, m_pos, m_boxes, m_bpath, m_bcost, m_bstart, m_cand, m_nb;
     MultiSlots MS{};
     const int mslots = multi_path ? std::min(batch, c->num_sms) : 0;
     if (multi_path) {
@@ -940,44 +1007,52 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
         CK(scratch_get(c, SC_M_DN, sizeof(int) * n1 * sl, m_dn));
         CK(scratch_get(c, SC_M_POS, sizeof(int) * (size_t)n * sl, m_pos));
         CK(scratch_get(c, SC_M_BOXES, sizeof(BigBox) * (size_t)n * sl, m_boxes));
+        CK(scratch_get(c, SC_M_NB, sizeof(int2) * (size_t)NB_STRIDE * (size_t)n * sl, m_nb));
         CK(scratch_get(c, SC_M_BPATH, sizeof(int) * (size_t)n * sl, m_bpath));
         CK(scratch_get(c, SC_M_BCOST, sizeof(long long) * sl, m_bcost));
         CK(scratch_get(c, SC_M_BSTART, sizeof(int) * sl, m_bstart));
         CK(scratch_get(c, SC_M_CAND, sizeof(unsigned long long), m_cand));
-        CK(scratch_get(c, SC_NEXT, sizeof(int), next));
-        CK(scratch_get(c, SC_DCOST, sizeof(long long) * batch, dcost));
-        CK(scratch_get(c, SC_DMOVES, sizeof(long long) * batch, dmoves));
         MS.pxy = m_pxy.as<double2>(); MS.tid = m_tid.as<int>(); MS.dn = m_dn.as<int>(); MS.pos = m_pos.as<int>();
-        MS.boxes = m_boxes.as<BigBox>(); MS.best_path = m_bpath.as<int>(); MS.best_cost = m_bcost.as<long long>();
-        MS.best_start = m_bstart.as<int>();
+        MS.boxes = m_boxes.as<BigBox>(); MS.nb = m_nb.as<int2>(); MS.best_path = m_bpath.as<int>();
+        MS.best_cost = m_bcost.as<long long>(); MS.best_start = m_bstart.as<int>();
     }
     std::vector<long long> hbc(std::max(1, mslots));
     std::vector<int> hbs(std::max(1, mslots));
-    if (cta_path) {
+    if (cta_path || multi_path) {
         CK(scratch_get(c, SC_NEXT, sizeof(int), next));
         CK(scratch_get(c, SC_DCOST, sizeof(long long) * batch, dcost));
         CK(scratch_get(c, SC_DMOVES, sizeof(long long) * batch, dmoves));
-        CK(scratch_get(c, SC_DPATHS, sizeof(int) * (size_t)n * batch, dpaths));
+        CK(scratch_get(c, SC_DSTATUS, sizeof(int) * batch, dstatus));
     }
+    if (cta_path) CK(scratch_get(c, SC_DPATHS, sizeof(int) * (size_t)n * batch, dpaths));
+    const int *d_stop = dl.on ? c->d_stop : nullptr;
+    bool raised = false, cut_short = false;
+    if (dl.on) CK(cudaMemsetAsync(c->d_stop, 0, sizeof(int), c->stream));
     long long best = -1;
-    int best_start = -1;
+    int best_start = -1, done = 0;
     clk.lap(clk.alloc);
-    for (int done = 0; done < nstarts; done += batch) {
+    for (; done < nstarts && !cut_short; done += batch) {
+        if (dl.passed()) break;                                          // heuristics.c:83-90: no further start is taken
         const int cnt = std::min(batch, nstarts - done);
         const int fs = first_start + done * stride;
         clk.lap(clk.rest);
         e = nn_batch(c, S, fs, cnt, stride, hc.data());
         if (e) return e;
         clk.lap(clk.nn);
-        if (multi_path) {
+        if (multi_path || cta_path) {
             CK(cudaMemsetAsync(next.p, 0, sizeof(int), c->stream));
+            CK(cudaMemsetAsync(dstatus.p, 0, sizeof(int) * cnt, c->stream));
+            CK(cudaMemsetAsync(dmoves.p, 0, sizeof(long long) * cnt, c->stream));
+            CK(cudaMemsetAsync(dcost.p, 0xFF, sizeof(long long) * cnt, c->stream));      // -1: start never taken
+        }
+        int g = 0;
+        if (multi_path) {
             CK(cudaMemsetAsync(m_cand.p, 0, sizeof(unsigned long long), c->stream));
             CK(cudaEventRecord(c->ev0, c->stream));
             // fewer starts than SMs: a cluster of CL CTAs per descent (pruned.cuh), CL the largest of 8/4/2 that still
-            // gives every start of the batch its own cluster
-            // a cluster occupies CL SMs of ONE GPC, so fewer than num_sms / CL clusters are co-resident (GPCs of 16-20 SMs):
-            // the count the driver reports decides, not the SM count (148 SMs: 37 clusters of 4 do not fit and the
-            // last one would start after the others have drained the queue)
+            // gives every start of the batch its own cluster.  A cluster occupies CL SMs of ONE GPC, so fewer than
+            // num_sms / CL clusters are co-resident (GPCs of 16-20 SMs): the count the driver reports decides, not the SM
+            // count (148 SMs: 37 clusters of 4 do not fit and the last one would start after the others have drained the queue)
             if (!c->k8_clusters[0]) {
                 for (int k = 0, v = 1; k < 4; ++k, v *= 2) {
                     cudaLaunchConfig_t q = {};
@@ -1001,12 +1076,12 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
             }
             int cl = 1, ck = 0;
             if (n >= K8_CLUSTER_MIN_N) while (cl < 8 && cnt <= c->k8_clusters[ck + 1]) { cl *= 2; ++ck; }
-            if (const char *kc = getenv("TSPCUDA_K8_CLUSTER")) {
-                cl = std::max(1, std::min(8, atoi(kc)));
+            if (k8env) {
+                cl = std::max(1, std::min(8, atoi(k8env)));
                 ck = cl >= 8 ? 3 : cl >= 4 ? 2 : cl >= 2 ? 1 : 0;
                 cl = 1 << ck;
             }
-            const int g = std::max(1, std::min(std::min(cnt, mslots), c->k8_clusters[ck]));   // teams (clusters): one tour slot each, cl record-buffer sets
+            g = std::max(1, std::min(std::min(cnt, mslots), c->k8_clusters[ck]));   // teams (clusters): one tour slot each, cl record-buffer sets
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(g * cl); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = c->stream;
             cudaLaunchAttribute attr[1];
@@ -1014,87 +1089,94 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
             attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
             cudaError_t le = cudaSuccess;
-#define K8_LAUNCH(CLV)                                                                                                        \
-    DISPATCH_METRIC(c->metric, (le = cudaLaunchKernelEx(&cfg, multi_pruned_kernel<M, 1024, CLV>, (const double2 *)c->d_xy, n, c->grid, \
+#define K8_LAUNCH(BLKV, CLV)                                                                                                  \
+    DISPATCH_METRIC(c->metric, (le = cudaLaunchKernelEx(&cfg, multi_pruned_kernel<M, BLKV, CLV>, (const double2 *)c->d_xy, n, c->grid, \
         (const int *)S.order, fs, stride, cnt, next.as<int>(), MS, dcost.as<long long>(), dmoves.as<long long>(),                     \
-        m_cand.as<unsigned long long>(), c->d_wbuf)))
-            if (cl == 8) { K8_LAUNCH(8); } else if (cl == 4) { K8_LAUNCH(4); } else if (cl == 2) { K8_LAUNCH(2); } else { K8_LAUNCH(1); }
+        dstatus.as<int>(), m_cand.as<unsigned long long>(), c->d_wbuf, d_stop)))
+            // TSPCUDA_K8_BLOCK=512 (measurement knob): 16 warps of 128 registers per descent instead of 32 of 64
+            const char *kb = getenv("TSPCUDA_K8_BLOCK");
+            if (kb && atoi(kb) == 512) {
+                cfg.blockDim = dim3(512);
+                if (cl == 8) { K8_LAUNCH(512, 8); } else if (cl == 4) { K8_LAUNCH(512, 4); } else if (cl == 2) { K8_LAUNCH(512, 2); } else { K8_LAUNCH(512, 1); }
+            } else {
+                if (cl == 8) { K8_LAUNCH(1024, 8); } else if (cl == 4) { K8_LAUNCH(1024, 4); } else if (cl == 2) { K8_LAUNCH(1024, 2); } else { K8_LAUNCH(1024, 1); }
+            }
 #undef K8_LAUNCH
             CK(le);
             CK(cudaGetLastError());
             CK(cudaEventRecord(c->ev1, c->stream));
+            CK(cudaMemcpyAsync(hbc.data(), m_bcost.p, sizeof(long long) * g, cudaMemcpyDeviceToHost, c->stream));
+            CK(cudaMemcpyAsync(hbs.data(), m_bstart.p, sizeof(int) * g, cudaMemcpyDeviceToHost, c->stream));
+        } else if (cta_path) {
+            // K6: every start of the batch descends inside one CTA, no grid barrier per move
+            CK(cudaEventRecord(c->ev0, c->stream));
+            cudaError_t le = cudaSuccess;
+            if (n <= CTA_SMALL_N) { DISPATCH_METRIC(c->metric, (le = launch_cta_descents<M, 512>(c, S.order, cnt, next.as<int>(), dcost.as<long long>(), dmoves.as<long long>(), dpaths.as<int>(), dstatus.as<int>(), d_stop))); }
+            else { DISPATCH_METRIC(c->metric, (le = launch_cta_descents<M, 1024>(c, S.order, cnt, next.as<int>(), dcost.as<long long>(), dmoves.as<long long>(), dpaths.as<int>(), dstatus.as<int>(), d_stop))); }
+            CK(le);
+            CK(cudaEventRecord(c->ev1, c->stream));
+        }
+        if (multi_path || cta_path) {
             c->stats.kernel_launches += 1;
             unsigned long long hcand = 0;
             CK(cudaMemcpyAsync(hf.data(), dcost.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(hm.data(), dmoves.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaMemcpyAsync(hbc.data(), m_bcost.p, sizeof(long long) * g, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaMemcpyAsync(hbs.data(), m_bstart.p, sizeof(int) * g, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaMemcpyAsync(&hcand, m_cand.p, sizeof(hcand), cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
+            CK(cudaMemcpyAsync(hs.data(), dstatus.p, sizeof(int) * cnt, cudaMemcpyDeviceToHost, c->stream));
+            if (multi_path) CK(cudaMemcpyAsync(&hcand, m_cand.p, sizeof(hcand), cudaMemcpyDeviceToHost, c->stream));
+            e = wait_with_deadline(c, dl, &raised);
+            if (e) return e;
             clk.lap(clk.descents);
-            c->stats.d2h_bytes += (int64_t)sizeof(long long) * 2 * cnt + 12 * g + 8;
+            c->stats.d2h_bytes += (int64_t)(sizeof(long long) * 2 + sizeof(int)) * cnt + 12 * g + 8;
             float ms = 0;
             CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-            c->stats.pruned_kernel_ms += ms;
+            if (multi_path) { c->stats.pruned_kernel_ms += ms; c->stats.candidate_evals += (int64_t)hcand; }
+            else c->stats.scan_kernel_ms += ms;
             c->stats.last_kernel_ms = ms;
-            c->stats.candidate_evals += (int64_t)hcand;
+            int bi = -1, taken = 0;
             for (int k = 0; k < cnt; k++) {
-                c->stats.moves += hm[k];
-                c->stats.scans += hm[k] + 1;
-                c->stats.pruned_scans += hm[k] + 1;
                 if (nn_costs_out) nn_costs_out[done + k] = (double)hc[k];
+                if (hs[k] == MS_NOT_STARTED) {                           // starts are handed out in ascending order: a suffix of the batch
+                    cut_short = true;
+                    if (final_costs_out) final_costs_out[done + k] = -1.0;
+                    if (moves_out) moves_out[done + k] = -1;
+                    continue;
+                }
+                ++taken;
+                if (hs[k] == MS_CUT) cut_short = true;
+                const long long scans = hm[k] + (hs[k] == MS_COMPLETE ? 1 : 0);
+                c->stats.moves += hm[k];
+                c->stats.scans += scans;
+                if (multi_path) c->stats.pruned_scans += scans;
+                else c->stats.pair_evals += scans * ((long long)n * (n - 1) / 2);
                 if (final_costs_out) final_costs_out[done + k] = (double)hf[k];
                 if (moves_out) moves_out[done + k] = hm[k];
+                if (cta_path && (best_start < 0 || hf[k] < best)) { best = hf[k]; best_start = fs + k * stride; bi = k; }   // strict '<', tsp.c:671
             }
-            int bslot = -1;                                  // (cost, start)-minimum over the CTAs' own bests
-            for (int q = 0; q < g; q++) {
-                if (hbs[q] < 0) continue;
-                if (best_start < 0 || hbc[q] < best || (hbc[q] == best && hbs[q] < best_start)) { best = hbc[q]; best_start = hbs[q]; bslot = q; }
-            }
-            if (bslot >= 0)
-                CK(cudaMemcpyAsync(best_path.p, MS.best_path + (size_t)bslot * n, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
-            continue;
-        }
-        if (cta_path) {
-            // K6: every start of the batch descends inside one CTA, no grid barrier per move
-            CK(cudaMemsetAsync(next.p, 0, sizeof(int), c->stream));
-            CK(cudaEventRecord(c->ev0, c->stream));
-            cudaError_t le = cudaSuccess;
-            if (n <= CTA_SMALL_N) { DISPATCH_METRIC(c->metric, (le = launch_cta_descents<M, 512>(c, S.order, cnt, next.as<int>(), dcost.as<long long>(), dmoves.as<long long>(), dpaths.as<int>()))); }
-            else { DISPATCH_METRIC(c->metric, (le = launch_cta_descents<M, 1024>(c, S.order, cnt, next.as<int>(), dcost.as<long long>(), dmoves.as<long long>(), dpaths.as<int>()))); }
-            CK(le);
-            CK(cudaEventRecord(c->ev1, c->stream));
-            c->stats.kernel_launches += 1;
-            CK(cudaMemcpyAsync(hf.data(), dcost.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaMemcpyAsync(hm.data(), dmoves.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaStreamSynchronize(c->stream));
-            c->stats.d2h_bytes += (int64_t)sizeof(long long) * 2 * cnt;
-            float ms = 0;
-            CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
-            c->stats.scan_kernel_ms += ms;
-            c->stats.last_kernel_ms = ms;
-            int bi = -1;
-            for (int k = 0; k < cnt; k++) {
-                c->stats.moves += hm[k];
-                c->stats.scans += hm[k] + 1;
-                c->stats.pair_evals += (hm[k] + 1) * ((long long)n * (n - 1) / 2);
-                if (nn_costs_out) nn_costs_out[done + k] = (double)hc[k];
-                if (final_costs_out) final_costs_out[done + k] = (double)hf[k];
-                if (moves_out) moves_out[done + k] = hm[k];
-                if (best_start < 0 || hf[k] < best) { best = hf[k]; best_start = fs + k * stride; bi = k; }   // strict '<', tsp.c:671
-            }
-            if (bi >= 0)
+            if (multi_path) {                                            // (cost, start)-minimum over the teams' own bests
+                int bslot = -1;
+                for (int q = 0; q < g; q++) {
+                    if (hbs[q] < 0) continue;
+                    if (best_start < 0 || hbc[q] < best || (hbc[q] == best && hbs[q] < best_start)) { best = hbc[q]; best_start = hbs[q]; bslot = q; }
+                }
+                if (bslot >= 0)
+                    CK(cudaMemcpyAsync(best_path.p, MS.best_path + (size_t)bslot * n, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
+            } else if (bi >= 0) {
                 CK(cudaMemcpyAsync(best_path.p, dpaths.as<int>() + (size_t)bi * n, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
+            }
+            if (cut_short) { done += taken; break; }
             continue;
         }
-        for (int k = 0; k < cnt; k++) {
+        int k = 0;
+        for (; k < cnt; k++) {
+            if (k > 0 && dl.passed()) { cut_short = true; break; }
             if (nn_costs_out) nn_costs_out[done + k] = (double)hc[k];
             // the NN visit order IS the tour-position order: no host round trip
             CK(cudaMemcpyAsync(c->d_order, S.order + (size_t)k * n, sizeof(int) * n, cudaMemcpyDeviceToDevice, c->stream));
             e = tour_from_device_order(c);
             if (e) return e;
             c->tour_loaded = false;
-            e = descend(c, -1, 0, -1.0, nullptr);
+            bool dcut = false;
+            e = descend(c, -1, 0, dl.left(), &dcut);
             if (e) return e;
             const long long fc = c->h_state->cost;
             if (final_costs_out) final_costs_out[done + k] = (double)fc;
@@ -1105,17 +1187,22 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
                 c->stats.kernel_launches += 1;
                 CK(cudaGetLastError());
             }
+            if (dcut) { cut_short = true; ++k; break; }
         }
+        if (cut_short) { done += k; break; }
     }
+    done = std::min(done, nstarts);
     if (best_path_out && best_start >= 0) {
         CK(cudaMemcpyAsync(best_path_out, best_path.p, sizeof(int) * n, cudaMemcpyDeviceToHost, c->stream));
         c->stats.d2h_bytes += (int64_t)sizeof(int) * n;
     }
     CK(cudaStreamSynchronize(c->stream));
+    if (raised) CK(cudaStreamSynchronize(c->aux_stream));
     clk.lap(clk.rest);
+    if (starts_done_out) *starts_done_out = done;
     if (best_start_out) *best_start_out = best_start;
     if (best_cost_out) *best_cost_out = (double)best;
-    return TSPCUDA_OK;
+    return (cut_short || done < nstarts) ? TSPCUDA_DEADLINE_EXCEEDED : TSPCUDA_OK;
 }
 
 // ---- K1 cost matrix ---------------------------------------------------------------------------
@@ -1330,12 +1417,30 @@ extern "C" int tspcuda_extra_mileage(tspcuda_ctx *c, int node_a, int node_b, int
 // The reference reads tour[-1] / tour[n] out of bounds in that test; under glibc both read 0 unless n = 2 (mod 4)
 // (checked against the reference objects on small n, where the case is frequent), and 0 is
 // what is used here.
-static void vns_kick_order(int n, int *ord, int *tmp) {
+// Where the random numbers of a VNS run come from.  The reference draws from the process-wide glibc stream (rand(),
+// never seeded on file instances), and so does tspcuda_vns_search.  The restarts entry points give every restart its OWN
+// generator instead -- glibc's reentrant random_r with the 128-byte state srand()/rand() use, i.e. the SAME sequence as
+// `srand(seed); rand(); ...` -- so that restarts running on several GPUs (worker threads) at once stay reproducible.
+struct RandSource {
+    bool own = false;
+    struct random_data rd;
+    char state[128];
+    RandSource() { std::memset(&rd, 0, sizeof(rd)); std::memset(state, 0, sizeof(state)); }
+    void seed(unsigned s) { own = true; std::memset(&rd, 0, sizeof(rd)); initstate_r(s, state, sizeof(state), &rd); }
+    int next() {
+        if (!own) return rand();
+        int32_t r = 0;
+        random_r(&rd, &r);
+        return (int)r;
+    }
+};
+
+static void vns_kick_order(int n, int *ord, int *tmp, RandSource &rng) {
     int idx[3];
     for (int i = 0; i < 3; i++) {
         int r;
         do {
-            r = rand() % n;
+            r = rng.next() % n;
             for (int j = 0; j < i; j++) {
                 const int lo = idx[j] - 1, hi = idx[j] + 1;
                 const int tlo = lo >= 0 ? ord[lo] : 0, thi = hi < n ? ord[hi] : 0;
@@ -1353,9 +1458,21 @@ static void vns_kick_order(int n, int *ord, int *tmp) {
     std::memcpy(ord + i0 + 1 + len2, tmp, sizeof(int) * len1);
 }
 
+static int vns_search_impl(tspcuda_ctx *c, int *path, double *cost_inout, int n_iters, double time_limit_s,
+                           double *cost_trace_out, int *best_path_out, double *best_cost_inout, int *best_iter_out,
+                           int *iters_done_out, RandSource &rng);
+
 extern "C" int tspcuda_vns_search(tspcuda_ctx *c, int *path, double *cost_inout, int n_iters, double time_limit_s,
                                   double *cost_trace_out, int *best_path_out, double *best_cost_inout, int *best_iter_out,
                                   int *iters_done_out) {
+    RandSource process_stream;                                 // rand(): the caller's (the reference driver's) own stream
+    return vns_search_impl(c, path, cost_inout, n_iters, time_limit_s, cost_trace_out, best_path_out, best_cost_inout, best_iter_out,
+                           iters_done_out, process_stream);
+}
+
+static int vns_search_impl(tspcuda_ctx *c, int *path, double *cost_inout, int n_iters, double time_limit_s,
+                           double *cost_trace_out, int *best_path_out, double *best_cost_inout, int *best_iter_out,
+                           int *iters_done_out, RandSource &rng) {
     int e = use(c);
     if (e) return e;
     if (!path || !best_cost_inout) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
@@ -1366,7 +1483,7 @@ extern "C" int tspcuda_vns_search(tspcuda_ctx *c, int *path, double *cost_inout,
     c->tour_loaded = false;
     e = tspcuda_tour_upload(c, path);                          // validates the tour; device order starts at node 0
     if (e) return e;
-    std::vector<int> ord(n), tmp(n), best_ord;
+    std::vector<int> ord(n), tmp(n), best_ord, before(n), where(n), changed;
     const auto t_begin = std::chrono::steady_clock::now();
     auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); };
     bool deadline = false;
@@ -1394,14 +1511,39 @@ extern "C" int tspcuda_vns_search(tspcuda_ctx *c, int *path, double *cost_inout,
         }
         if (cost_trace_out) cost_trace_out[i] = cost;          // :303
         done = i + 1;
-        const int r = rand() % (10 - 2 + 1) - 2;               // :306, UPPER 10 / LOWER 2 (metaheuristic.h:7-8)
-        for (int j = 0; j < r; j++) vns_kick_order(n, ord.data(), tmp.data());
+        const int r = rng.next() % (10 - 2 + 1) - 2;           // :306, UPPER 10 / LOWER 2 (metaheuristic.h:7-8)
+        if (r > 0) before = ord;
+        for (int j = 0; j < r; j++) vns_kick_order(n, ord.data(), tmp.data(), rng);
         std::memcpy(c->h_buf, ord.data(), sizeof(int) * n);
         CK(cudaMemcpyAsync(c->d_order, c->h_buf, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
         c->stats.h2d_bytes += (int64_t)sizeof(int) * n;
-        e = tour_from_device_order(c);                         // cost recomputed from the kicked tour (refinment.c:6-9)
+        // A kick exchanges two blocks: it changes three tour edges, i.e. the neighbours of at most six nodes.  The device's
+        // neighbour cache (pruned.cuh) is kept per NODE and depends on a node's two tour edges only, so only the nodes whose
+        // neighbour pair differs between the tour before and after the kicks are marked stale -- the descent after a kick
+        // then costs a handful of searches instead of one per node.
+        const bool keep = c->nb_valid;
+        changed.clear();
+        if (keep && r > 0) {
+            for (int k = 0; k < n; k++) where[before[k]] = k;
+            for (int k = 0; k < n; k++) {
+                const int u = ord[k], kb = where[u];
+                const int p1 = ord[k == 0 ? n - 1 : k - 1], s1 = ord[k + 1 == n ? 0 : k + 1];
+                const int p0 = before[kb == 0 ? n - 1 : kb - 1], s0 = before[kb + 1 == n ? 0 : kb + 1];
+                if (!((p1 == p0 && s1 == s0) || (p1 == s0 && s1 == p0))) changed.push_back(u);
+            }
+        }
+        e = tour_from_device_order(c, keep);                   // cost recomputed from the kicked tour (refinment.c:6-9)
         if (e) return e;
-        CK(cudaStreamSynchronize(c->stream));                  // h_buf is reused
+        if (!changed.empty()) {
+            DevBuf d_list;
+            CK(scratch_get(c, SC_NB_LIST, sizeof(int) * (size_t)n, d_list));
+            CK(cudaMemcpyAsync(d_list.p, changed.data(), sizeof(int) * changed.size(), cudaMemcpyHostToDevice, c->stream));
+            nb_invalidate_list_kernel<<<1, 256, 0, c->stream>>>(c->d_nb, d_list.as<int>(), (int)changed.size());
+            c->stats.kernel_launches += 1;
+            c->stats.h2d_bytes += (int64_t)sizeof(int) * changed.size();
+            CK(cudaGetLastError());
+        }
+        CK(cudaStreamSynchronize(c->stream));                  // h_buf and `changed` are reused
     }
     // the solution as the reference leaves it: the tour after the last kicks, cost = after the last descent
     if (done > 0)
@@ -1413,6 +1555,96 @@ extern "C" int tspcuda_vns_search(tspcuda_ctx *c, int *path, double *cost_inout,
     if (best_iter_out) *best_iter_out = best_iter;
     if (iters_done_out) *iters_done_out = done;
     return deadline ? TSPCUDA_DEADLINE_EXCEEDED : TSPCUDA_OK;
+}
+
+// ---- config 5 "restarts" (BASELINE.json configs[4]) -----------------------------------------------
+// A framework addition: the reference runs ONE tabu / VNS trajectory.  Restart r = start node first_start + r*stride, each
+// an independent unit (it depends on the instance, its start node and the seed only), so restarts shard over GPUs exactly
+// like the multi-start drivers and merge under the same incumbent rule (strict '<' in ascending start order, tsp.c:671).
+//   kind 0, tabu: NN(start) -> 2-opt local optimum (ref_2opt) -> `iters` iterations of the loop of mh_TabuSearch
+//                 (metaheuristic.c:128-164) with the reference's default linear tenure schedule (tabu_init :65-84,
+//                 tabu_linear_policy :40-59), incumbent = the local optimum
+//   kind 1, VNS:  NN(start) -> `iters` iterations of the loop of mh_VNS (:277-321), kicks drawn from a private generator
+//                 seeded as srand(seed + start) would seed the process stream; no incumbent to beat (the first local
+//                 optimum always enters)
+static void linear_tenures(int n, int k, std::vector<int> &out) {
+    int tenure = (int)(0.125 * n + 1);                          // tabu_init: MIN_FRACTION * nnodes + 1, truncated by the int field
+    const int hi = (int)(0.25 * n), lo = (int)(0.125 * n);
+    bool inc = true;
+    out.resize(k);
+    for (int i = 0; i < k; i++) {
+        if (hi == tenure || lo == tenure) inc = !inc;
+        tenure += inc ? 1 : -1;
+        out[i] = tenure;
+    }
+}
+
+extern "C" int tspcuda_restarts(tspcuda_ctx *c, int kind, int first_start, int nstarts, int stride, int iters, unsigned seed,
+                                double time_limit_s, int *best_start_out, int *best_path_out, double *best_cost_out,
+                                int *restarts_done_out) {
+    int e = use(c);
+    if (e) return e;
+    const int n = c->n;
+    if (restarts_done_out) *restarts_done_out = 0;
+    if (best_start_out) *best_start_out = -1;
+    if (kind != TSPCUDA_RESTART_TABU && kind != TSPCUDA_RESTART_VNS) return fail(TSPCUDA_INVALID_ARGUMENT, "restart kind %d", kind);
+    if (nstarts <= 0 || stride <= 0 || iters < 0) return fail(TSPCUDA_INVALID_ARGUMENT, "nstarts/stride/iters");
+    const long long last = (long long)first_start + (long long)(nstarts - 1) * stride;
+    if (first_start < 0 || last >= n) return fail(TSPCUDA_UNAVAILABLE, "starting node not correct");
+    const Deadline dl(time_limit_s);
+    std::vector<int> path(n), run_best(n), tabu(n), bestp(n), tenures;
+    if (kind == TSPCUDA_RESTART_TABU) linear_tenures(n, iters, tenures);
+    double best = 0;
+    int best_start = -1, done = 0;
+    bool late = false;
+    for (int r = 0; r < nstarts; r++) {
+        if (dl.passed()) { late = true; break; }
+        const int start = first_start + r * stride;
+        double cost = 0, run_cost = 0;
+        e = tspcuda_nn(c, start, path.data(), &cost);
+        if (e) return e;
+        bool have = false;
+        if (kind == TSPCUDA_RESTART_TABU) {
+            int64_t mv = 0;
+            e = tspcuda_two_opt(c, path.data(), &cost, -1, dl.left(), &mv, nullptr, 0);
+            if (e == TSPCUDA_DEADLINE_EXCEEDED) late = true;
+            else if (e) return e;
+            run_cost = cost;
+            run_best = path;
+            have = true;
+            if (!late && iters > 0) {
+                std::fill(tabu.begin(), tabu.end(), -1);
+                double bc = cost;
+                int bi = -1;
+                e = tspcuda_tabu_search(c, path.data(), &cost, tabu.data(), tenures.data(), 0, iters, run_cost, nullptr, bestp.data(), &bc, &bi);
+                if (e) return e;
+                if (bi >= 0) {                                  // some iteration improved on the local optimum
+                    run_cost = bc;
+                    run_best = bestp;
+                }
+            }
+        } else {
+            RandSource rng;
+            rng.seed(seed + (unsigned)start);
+            double bc = __DBL_MAX__;
+            int bi = -1, it_done = 0;
+            e = vns_search_impl(c, path.data(), &cost, iters, dl.left(), nullptr, run_best.data(), &bc, &bi, &it_done, rng);
+            if (e == TSPCUDA_DEADLINE_EXCEEDED) late = true;
+            else if (e) return e;
+            if (bi >= 0) { run_cost = bc; have = true; }
+        }
+        if (have && (best_start < 0 || run_cost < best)) {      // strict '<' in ascending start order
+            best = run_cost;
+            best_start = start;
+            if (best_path_out) std::memcpy(best_path_out, run_best.data(), sizeof(int) * n);
+        }
+        ++done;
+        if (late) break;
+    }
+    if (restarts_done_out) *restarts_done_out = done;
+    if (best_start_out) *best_start_out = best_start;
+    if (best_cost_out && best_start >= 0) *best_cost_out = best;
+    return (late || done < nstarts) ? TSPCUDA_DEADLINE_EXCEEDED : TSPCUDA_OK;
 }
 
 // ---- patching (cplex_model.c:693-755 cx_patching, the Benders loop's while (ncomp > 1), :205-212) -----
@@ -1586,6 +1818,18 @@ extern "C" int tspcuda_mx_create(tspcuda_mx **out, const double *costs, int n, i
     CKM(cudaStreamSynchronize(m->stream));
     m->stats.h2d_bytes += (int64_t)(sizeof(double) * N * N);
     *out = m;
+    return TSPCUDA_OK;
+}
+
+// Replace the matrix of an existing context (same n): what a caller that is handed a fresh matrix per call -- the CPLEX
+// relaxation callback through h_Greedy_2opt_mod_costs -- needs instead of a create / destroy pair per call.
+extern "C" int tspcuda_mx_update(tspcuda_mx *m, const double *costs) {
+    if (!m || !costs) return fail(TSPCUDA_INVALID_ARGUMENT, "null argument");
+    CK(cudaSetDevice(m->device));
+    const size_t N = (size_t)m->n;
+    CK(cudaMemcpyAsync(m->d_C, costs, sizeof(double) * N * N, cudaMemcpyHostToDevice, m->stream));
+    CK(cudaStreamSynchronize(m->stream));
+    m->stats.h2d_bytes += (int64_t)(sizeof(double) * N * N);
     return TSPCUDA_OK;
 }
 
