@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--full-descent", type=int, default=-1, help="1/0: also time NN tour -> local optimum (default: on at N=1)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU-baseline sample budget")
     ap.add_argument("--multistart", type=int, default=148, help="config 4: NN + 2-opt starts per GPU (0 = skip)")
+    ap.add_argument("--fixed", type=int, default=1, help="1/0: fixed start sets through the library's own multi-GPU path (strong scaling) + config-5 restarts")
     return ap.parse_args()
 
 
@@ -155,6 +156,60 @@ def run_reference(args):
     })
 
 
+def fixed_sets(T, ndev, multistart, best_ref=None):
+    """Rank 0: fixed start sets on 1 and on `ndev` GPUs through tspcuda_mgpu_multistart / tspcuda_mgpu_restarts."""
+    res = {}
+    sets = (("usa13509", 1184), ("pla85900", 296))
+    fixed = {}
+    for name, S in sets:
+        xy, _ = T.load_instance(name)
+        row = {"S": S}
+        for g in sorted({1, ndev}):
+            with T.MultiGpuInstance(xy, T.EUC_REF, g) as M:
+                M.multistart(True, 0, min(S, 2 * g), 1)                       # warm (module load, scratch growth, NCCL)
+                t0 = time.perf_counter()
+                bs, bp, bc, cms, rms = M.multistart(True, 0, S, 1)
+                wall = time.perf_counter() - t0
+            row["ndev%d" % g] = {"seconds": wall, "compute_ms": cms, "reduce_ms": rms, "best_cost": int(bc), "best_start": int(bs)}
+        one, many = row["ndev1"], row["ndev%d" % ndev]
+        assert (one["best_cost"], one["best_start"]) == (many["best_cost"], many["best_start"]), row       # same incumbent on 1 and N GPUs
+        row.update(seconds=many["seconds"], speedup_vs_ndev1=one["seconds"] / many["seconds"], reduce_ms=many["reduce_ms"],
+                   best_cost=many["best_cost"], best_start=many["best_start"], starts_per_s=S / many["seconds"])
+        fixed[name] = row
+    # the torch.distributed twin (one process per GPU, bench `multistart`) ran starts 0 .. 148 N - 1 of pla85900: where
+    # that set contains the fixed one's 296 starts the better incumbent cannot be worse, and at N = 2 the sets are equal
+    if multistart and best_ref and multistart["starts"] == 296:
+        assert best_ref == (fixed["pla85900"]["best_cost"], fixed["pla85900"]["best_start"]), (best_ref, fixed["pla85900"])
+        fixed["pla85900"]["equals_torch_distributed_result"] = True
+    fixed["note"] = ("FIXED start sets (strong scaling) through the library's own multi-GPU path: one worker thread + context per GPU in one "
+                     "process, starts sharded block-cyclically, ncclAllReduce(min) of (cost << 20 | start) + ncclBroadcast of the winner's "
+                     "tour; wall clock of tspcuda_mgpu_multistart; speedup_vs_ndev1 measured in this run on the same set")
+    res["multistart_fixed"] = fixed
+    # config 5: tabu / VNS restarts on d15112 (restart r = start node r), sharded the same way
+    xy, _ = T.load_instance("d15112")
+    R = 8 * ndev
+    rs = {"instance": "d15112", "restarts": R}
+    for label, kind, iters in (("tabu", T.RESTART_TABU, 1000), ("vns", T.RESTART_VNS, 100)):
+        row = {}
+        for g in sorted({1, ndev}):
+            with T.MultiGpuInstance(xy, T.EUC_REF, g) as M:
+                M.restarts(kind, 0, g, 1, iters=8, seed=1)
+                t0 = time.perf_counter()
+                code, done, bs, bp, bc, cms, rms = M.restarts(kind, 0, R, 1, iters=iters, seed=1)
+                wall = time.perf_counter() - t0
+            assert code == 0 and done == R
+            row["ndev%d" % g] = {"seconds": wall, "best_cost": int(bc), "best_start": int(bs), "reduce_ms": rms}
+        one, many = row["ndev1"], row["ndev%d" % ndev]
+        assert (one["best_cost"], one["best_start"]) == (many["best_cost"], many["best_start"]), row
+        row.update(iters=iters, seconds=many["seconds"], restarts_per_s=R / many["seconds"], speedup_vs_ndev1=one["seconds"] / many["seconds"],
+                   best_cost=many["best_cost"], best_start=many["best_start"])
+        rs[label] = row
+    rs["note"] = ("config 5: restart r = NN(r) -> 2-opt -> 1000 tabu iterations (linear tenure) resp. 100 iterations of the mh_VNS loop with a "
+                  "private srand(seed + r) stream; restarts sharded over the GPUs by tspcuda_mgpu_restarts, (cost, start) min-reduce over NCCL")
+    res["restarts"] = rs
+    return res
+
+
 _REAL_STDOUT = None
 
 
@@ -186,8 +241,10 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (libtspcuda has no CPU fallback)")
     torch.cuda.set_device(local)
+    gloo = None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        gloo = dist.new_group(backend="gloo")       # CPU-side barrier: parks ranks without a spinning NCCL kernel on their GPU
 
     def barrier():
         if world > 1:
@@ -339,6 +396,7 @@ def main():
             dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
             agg = [float(tmax.item())] + [float(v) for v in tsum.tolist()]
         multistart = {"starts": S_total, "starts_per_gpu": args.multistart, "seconds": agg[0], "starts_per_s": S_total / agg[0],
+                      "start0": [int(nn_costs[0]), int(mvs[0]), int(final[0])] if rank == 0 else None,
                       "moves": int(agg[1]), "scans": int(agg[2]), "best_cost": int(bc), "best_start": int(bs),
                       "note": "starts 0..S-1, rank r takes r, r+W, ... (heuristics.c:82 order, block-cyclic); NN on the device, "
                               "descents by the CTA-per-descent pruned kernel (bit-identical tours to the full scan); wall clock "
@@ -356,6 +414,21 @@ def main():
     }
     if multistart:
         out["multistart"] = multistart
+
+    # ---- fixed start sets through the library's OWN multi-GPU path (tspcuda_mgpu: one worker thread + context per GPU in
+    # ONE process, ncclCommInitAll -- what the unchanged C driver uses with TSPCUDA_GPUS=N): strong scaling, and the
+    # config-5 restarts.  Rank 0 drives all N GPUs; the other ranks release theirs and wait at a CPU barrier.
+    if args.fixed:
+        if world > 1:
+            torch.cuda.synchronize()
+            dist.barrier(group=gloo)
+        if rank == 0:
+            try:
+                out.update(fixed_sets(T, world, multistart, best_ref=(int(bc), int(bs)) if multistart else None))
+            except Exception as ex:                                  # never lose the headline line over the extras
+                out["multistart_fixed"] = {"error": repr(ex)}
+        if world > 1:
+            dist.barrier(group=gloo)
 
     if rank == 0 and world == 1 and args.multistart > 0:
         # K1 (tsp_compute_costs, tsp.c:608-636) on the same instance: 8 n^2 bytes written to HBM (59 GB)
@@ -405,6 +478,21 @@ def main():
                                    "(csrc/pruned.cuh); identical move sequence and final tour (md5 checked here)")
             out["time_to_local_optimum"] = res["full_scan"]
             out["time_to_local_optimum_auto"] = res["auto"]
+            if multistart:
+                # config 4's own kernels against this descent: start 0 of the multi-start batch (K4b + K8, one CTA per
+                # descent) must have made the same moves to the same cost, and the same start alone on an 8-SM cluster
+                # must return the same tour
+                assert multistart["start0"] == [res["auto"]["start_cost"], res["auto"]["moves"], res["auto"]["final_cost"]], multistart["start0"]
+                os.environ["TSPCUDA_K8_CLUSTER"] = "8"
+                I.set_scan_mode(T.SCAN_AUTO)
+                t0 = time.perf_counter()
+                bs1, bp1, bc1, nn1, fin1, mv1 = I.multistart_two_opt(0, 1, 1)
+                wall1 = time.perf_counter() - t0
+                del os.environ["TSPCUDA_K8_CLUSTER"]
+                I.set_scan_mode(T.SCAN_FULL)
+                assert hashlib.md5(bp1.tobytes()).hexdigest() == res["auto"]["tour_md5"] and int(mv1[0]) == res["auto"]["moves"]
+                multistart["start0_check"] = {"equals_time_to_local_optimum": True, "cluster8_one_descent_seconds": wall1,
+                                              "tour_md5": res["auto"]["tour_md5"]}
     if rank == 0:
         emit(out)
     I.close()

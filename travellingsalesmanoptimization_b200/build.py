@@ -14,6 +14,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-shared",
 ]
+SPEED_FLAGS = ["-split-compile", str(min(8, os.cpu_count() or 1))]      # parallel back end; not part of the source hash
 
 
 STAMP = LIB + ".srchash"      # content hash of the sources the library was built from (mtimes do not survive a snapshot copy)
@@ -40,7 +41,7 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + SPEED_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES
     subprocess.check_call(cmd, cwd=CSRC)
     with open(STAMP, "w") as f:
         f.write(_source_hash())

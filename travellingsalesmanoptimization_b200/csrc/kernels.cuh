@@ -60,7 +60,8 @@ struct TourView {
     int *dns;
     int *pos;
     int n;
-};
+    unsigned char *o8;     // [n] per NODE, or NULL: bit 0 flips whenever the node's successor and predecessor trade places,
+};                         //   i.e. whenever it lies in a reversed segment (the delta cache of pruned.cuh; apply_move keeps it)
 
 struct DescState {
     long long moves;       // moves applied since upload
@@ -71,7 +72,14 @@ struct DescState {
     long long candidates;  // candidate nodes examined by the pruned scan (pruned.cuh)
     long long phase_sum;   // -DTSP_PHASE_TIMING: sum over warps and scans of the phase-1 duration
     long long phase_ns[6]; // -DTSP_PHASE_TIMING: ns in scan phase 1 / phase 2 / apply (each incl. its barrier), -, units, boxes
+    long long nbstat[8];   // -DTSP_NB_STATS: delta-cache events (rebuilds, queued boxes, long lists, dirty, hits, evaluated, attend calls, box nodes)
 };
+#ifdef TSP_NB_STATS
+#define NBSTAT(slot, v) atomicAdd((unsigned long long *)&g_nbstat[slot], (unsigned long long)(v))
+__device__ unsigned long long g_nbstat[8];
+#else
+#define NBSTAT(slot, v)
+#endif
 
 struct MoveRec { int a, b, delta, reserved; };
 
@@ -245,6 +253,11 @@ __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int 
         if (k != 0) { V.pos[tq] = p; V.pos[tp] = q; }   // k == 0: the end nodes, deferred (see above)
         if (p == 0) { V.pxy[n] = xq; V.tid[n] = tq; }
         if (q == 0) { V.pxy[n] = xp; V.tid[n] = tp; }
+        if (V.o8) { V.o8[tq] ^= 1; V.o8[tp] ^= 1; }     // one owner per node: plain byte updates
+    }
+    if (V.o8 && (L & 1) && t == 0) {                    // the middle node of an odd segment stays in place but turns round too
+        int m = s + half; if (m >= n) m -= n;
+        V.o8[V.tid[m]] ^= 1;
     }
     for (int k = t; k < ehalf; k += nthreads) {
         int p = s + k; if (p >= n) p -= n;
@@ -447,6 +460,7 @@ descend_cta_kernel(const double2 *__restrict__ xy, int n, const int *__restrict_
     V.tid = reinterpret_cast<int *>(smem_raw + 16 * n1);
     V.dn = V.tid + n1;
     V.dns = V.dn;
+    V.o8 = nullptr;
     V.pos = V.dn + n1;
     size_t off = (16 * n1 + 4 * n1 * 2 + 4 * (size_t)n + 15) & ~(size_t)15;
     double2 *stage_xy = reinterpret_cast<double2 *>(smem_raw + off);
@@ -593,25 +607,33 @@ __device__ __forceinline__ double cost_as_double(int koff) {
 #ifndef TSP_K1_CTAS
 #define TSP_K1_CTAS 16
 #endif
-// A CTA fills TSP_K1_ROWS rows at a time, so that the column coordinates -- which every row needs and which do not
-// fit L1 for large n -- are read from L2 once per row group instead of once per row (ncu on the one-row version:
-// long-scoreboard stalls on those loads dominate, L2->SM traffic is twice the bytes written).  Rows of a group have the
-// same 16-byte alignment: consecutive rows when n is even, every other row when n is odd (row i starts at cell i*n).
+// A work unit is TSP_K1_ROWS rows x one CHUNK of columns.  Several rows at a time, so that the column coordinates --
+// which every row needs and which do not fit L1 for large n -- are read from L2 once per row group instead of once per
+// row (ncu on the one-row version: long-scoreboard stalls on those loads dominate, L2->SM traffic is twice the bytes
+// written).  Units are numbered chunk-fastest and dealt out grid-stride, so the CTAs resident at any time write ONE
+// compact band of the matrix (a few hundred MB) instead of eight rows each spread over n / 8 row groups (pla85900:
+// 2368 CTAs x 8 rows x 687 KB = 13 GB of open pages -- measured 0.80 of the copy bandwidth against 0.99 at n = 20 000).
+// Rows of a group have the same 16-byte alignment: consecutive rows when n is even, every other row when n is odd
+// (row i starts at cell i*n).  chunk_pairs: 16-byte cell pairs per unit and row (a multiple of the block size).
 template <class M>
 __global__ void __launch_bounds__(TSP_K1_BLOCK)
-cost_matrix_kernel(const double2 *__restrict__ xy, int n, double *__restrict__ out) {
+cost_matrix_kernel(const double2 *__restrict__ xy, int n, double *__restrict__ out, int chunk_pairs) {
     constexpr int RB = TSP_K1_ROWS;
     const int s = (n & 1) ? 2 : 1;                       // row stride inside a group
     const int span = RB * s;                             // consecutive rows covered by s groups
     const int ngroups = ((n + span - 1) / span) * s;
-    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+    const int nchunks = max(1, ((n >> 1) + chunk_pairs - 1) / chunk_pairs);  // covers (n - off) / 2 pairs for off = 0 and 1
+    const long long nunits = (long long)ngroups * nchunks;
+    for (long long u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int g = (int)(u / nchunks), ch = (int)(u - (long long)g * nchunks);
         const int first = (g / s) * span + (g % s);      // rows first, first + s, ...
         const int off = (int)(((size_t)first * (size_t)n) & 1);
         double2 pr[RB];
 #pragma unroll
         for (int k = 0; k < RB; ++k) pr[k] = xy[min(first + k * s, n - 1)];
         const int npairs = (n - off) >> 1;
-        for (int t = threadIdx.x; t < npairs; t += blockDim.x) {
+        const int t1 = min(npairs, (ch + 1) * chunk_pairs);
+        for (int t = ch * chunk_pairs + threadIdx.x; t < t1; t += blockDim.x) {
             const int j = off + 2 * t;
             const double2 p0 = xy[j], p1 = xy[j + 1];
 #pragma unroll
@@ -624,7 +646,7 @@ cost_matrix_kernel(const double2 *__restrict__ xy, int n, double *__restrict__ o
                 }
             }
         }
-        if (threadIdx.x < RB) {                          // the unpaired first / last cell of each row
+        if (ch == 0 && threadIdx.x < RB) {               // the unpaired first / last cell of each row
             const int k = threadIdx.x, i = first + k * s;
             if (i < n) {
                 double *row = out + (size_t)i * (size_t)n;

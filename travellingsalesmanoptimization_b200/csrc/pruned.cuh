@@ -276,6 +276,7 @@ __device__ __forceinline__ void pairs_eval(const TourView &V, const PosPatch &F,
                                            unsigned long long &bestkey) {
     const int n = V.n;
     const int lane = threadIdx.x & 31;
+    if (lane == 0) NBSTAT(5, count);
     for (int base = 0; base < count; base += 32 * NE) {
         uint4 e[NE];
         int q[NE];
@@ -470,138 +471,396 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
     pairs_eval<M, NE, TABU>(V, F, wbuf, wcount, best, bestkey);
 }
 
-// ---- per-node neighbour cache: phase 1 without the searches ----------------------------------------------
-// What a search around node u returns -- the nodes w with cost(u,w) below the larger of u's two tour-edge costs,
-// and those costs -- depends on u's two tour edges only, and a 2-opt move changes the tour edges of exactly FOUR
-// nodes (a, succ a, b, succ b; every node inside the reversed segment keeps both edges, only their orientation
-// flips).  So the result is kept per NODE, one 128-byte line each: slot 0 = {count, -}, slots 1..NB_CAP = {w, K-offset
-// cost(u,w)}.  A scan then reads the line of the node at every position, re-derives which of the two pair types each
-// record feeds from the CURRENT edge costs (orientation-independent: K < dn[p] -> pair {p, pos w}, K < dn[p-1] ->
-// pair {p-1, pos w - 1}) and hands the records to pairs_eval as before: the candidate set is the same set of
-// (u, w, cost) triples the searches would produce, so the argmin is unchanged.  Only stale nodes are searched: the
-// four of the previous move (carried in registers, PosPatch -- the kernel never has to write a "stale" mark), nodes
-// never searched yet (count NB_STALE), and nodes whose list does not fit a line (they stay NB_STALE and are searched
-// in every scan, as every node was before).  A search is done by the whole warp over the box's cell rows and
-// rewrites the line; boxes beyond PR_COOP_MAX nodes go to the phase-2 queue.  pla85900: 1.47e6 candidate nodes per
-// scan become ~n line reads + a handful of searches.
-constexpr int NB_STRIDE = 16;                  // int2 slots per node
-constexpr int NB_CAP = NB_STRIDE - 1;
-constexpr int NB_STALE = -1;
-#ifndef TSP_PR_COOP_MAX
-#define TSP_PR_COOP_MAX 512
+// ---- per-node DELTA cache: a scan that streams instead of searching ---------------------------------------
+// A search around node u returns the nodes w with cost(u,w) below the larger of u's two tour-edge costs; each such
+// RECORD (u,w) stands for the 2-opt moves that create the edge (u,w).  Write x, y for u's two tour neighbours and
+// z, z' for w's.  Whatever the direction the tour is walked in, the move pairs x with z and y with z', or x with z'
+// and y with z -- which of the two depends only on whether u and w are traversed in the same relative direction as
+// when the record was made -- and each of the four deltas
+//     cost(u,w) + cost(x,z) - cost(u,x) - cost(w,z),  ...
+// depends on the identities of x, y, z, z' only.  A 2-opt move changes the tour edges of exactly FOUR nodes (a, succ a,
+// b, succ b); every node strictly inside the reversed segment keeps both edges and merely swaps successor and
+// predecessor.  So the cache keeps, per node u, the list of its records as {w, d0, d1}:
+//     d[r] = the smaller of the two deltas that are valid 2-opt moves when  o8[u] ^ o8[w] == r,
+// where o8[] is one orientation bit per node that apply_move flips for every node of a reversed segment (kernels.cuh).
+// A scan then is a STREAM over the node lines: load the record, look up one byte o8[w], select d0 or d1, compare with
+// the running best.  No position, coordinate or edge-cost gather, and no arithmetic, for a record that cannot win.
+// Only records at or below the running best are re-evaluated exactly from the position arrays (pairs_eval: both
+// deltas, adjacency test, packed keys), so the argmin -- ties included -- is taken over exact keys as before; the
+// record set is the one the searches produce, which contains every pair with delta < 0 (header of this file).
+// What is recomputed after a move:
+//   * the lists of the four nodes whose edges changed: one warp-wide search each (F carries them in registers);
+//   * records (u,w) in OTHER lists whose w is one of those four (w's neighbours changed): found while streaming
+//     (four compares per record) and recomputed in place by the lane that meets them; a record whose d0 is NB_DIRTY
+//     is treated the same way (marked from the host side after a VNS kick);
+//   * nothing else.  pla85900: a scan reads 64 bytes per node instead of evaluating 2.5e5 candidates with three
+//     dependent gathers each.
+// Layout: one 64-byte line per node = header word + NB_CAP records of three words; header = count (10 bits, NB_CF_BIG /
+// NB_CF_STALE as specials) | (pool slot + 1) << 10.  A list longer than NB_CAP lives in a slot of an extension pool
+// (NB_EXT records, handed out by a bump counter the first time a node needs one and kept by that node).  A node whose
+// search box holds more than NB_WALK_MAX nodes (a long tour edge: a nearest-neighbour tour has a few dozen, gone after
+// the first few percent of the moves) is not cached: its box goes to the phase-2 queue in every scan, as before.
+constexpr int NB_WORDS = 16;                   // ints per node line
+constexpr int NB_CAP = 5;                      // records held in the line itself
+#ifndef TSP_NB_EXT
+#define TSP_NB_EXT 128
 #endif
-constexpr int PR_COOP_MAX = TSP_PR_COOP_MAX;
+constexpr int NB_EXT = TSP_NB_EXT;             // records per pool slot
+constexpr int NB_WALK_MAX = 512;               // largest search box (in nodes) a warp walks itself
+constexpr int NB_CF_STALE = 1023, NB_CF_BIG = 1022;
+constexpr int NB_HDR_STALE = NB_CF_STALE;      // stale, no pool slot
+constexpr int NB_DIRTY = (int)0x80000000;      // d0 of a record that must be recomputed before use
 
-__global__ void nb_invalidate_kernel(int2 *nb, int n) {
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) nb[(size_t)u * NB_STRIDE].x = NB_STALE;
+struct NbCache {
+    int *lines;         // [n][NB_WORDS]
+    int *pool;          // [slots][NB_EXT * 3]
+    int *pool_next;     // bump counter of the pool
+    int slots;
+};
+__host__ __device__ inline int nb_pool_slots(int n) { return n / 4 + 64; }
+
+__global__ void nb_invalidate_kernel(NbCache C, unsigned char *o8, int n) {
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) { C.lines[(size_t)u * NB_WORDS] = NB_HDR_STALE; o8[u] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *C.pool_next = 0;
 }
-__global__ void nb_invalidate_list_kernel(int2 *nb, const int *nodes, int count) {
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) nb[(size_t)nodes[k] * NB_STRIDE].x = NB_STALE;
+// after the tour was changed from outside WITHOUT any reversal (a VNS kick exchanges blocks): the listed nodes got new
+// neighbours.  Their own lists are marked stale (first kernel, which also raises flag[]), every record pointing at one
+// of them is marked dirty (second kernel), the flags are lowered again (third).
+__global__ void nb_mark_nodes_kernel(NbCache C, const int *nodes, int count, unsigned char *flag, int raise) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
+        const int u = nodes[k];
+        flag[u] = (unsigned char)raise;
+        if (raise) { int *h = C.lines + (size_t)u * NB_WORDS; *h = (*h & ~0x3FF) | NB_CF_STALE; }
+    }
+}
+__global__ void nb_mark_records_kernel(NbCache C, const unsigned char *flag, int n) {
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+        int *line = C.lines + (size_t)u * NB_WORDS;
+        const int hdr = line[0], cf = hdr & 0x3FF, ext = (hdr >> 10) - 1;
+        if (cf >= NB_CF_BIG) continue;
+        int *rec = cf <= NB_CAP ? line + 1 : C.pool + (size_t)ext * NB_EXT * 3;
+        for (int j = 0; j < cf; ++j)
+            if (flag[rec[3 * j]]) rec[3 * j + 1] = NB_DIRTY;
+    }
 }
 
-template <class M, int NE>
-__device__ __forceinline__ void pruned_phase1_cached(const TourView &V, const SpatialGrid &G, const PosPatch &F, int t, int nthreads,
-                                                     unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, int2 *nb, int &best,
-                                                     unsigned long long &bestkey, long long &ncand) {
-    int wcount = 0;
+__device__ __forceinline__ bool in_patch(const PosPatch &F, int node) {
+    return node == F.node0 || node == F.node1 || node == F.node2 || node == F.node3;
+}
+__device__ __forceinline__ int pos_of(const TourView &V, const PosPatch &F, int node) {
+    return node == F.node0 ? F.pos0 : node == F.node1 ? F.pos1 : V.pos[node];
+}
+
+// what the records of node u need from the tour: its position, both neighbours (ids, coordinates) and both edge costs
+struct NodeCtx {
+    double2 u, s, m;       // coordinates of the node, its successor, its predecessor
+    int p, dnp, dnm, su, pu;
+};
+__device__ __forceinline__ void node_ctx(const TourView &V, const PosPatch &F, int node, NodeCtx &c) {
     const int n = V.n;
+    c.p = pos_of(V, F, node);
+    const int pm = c.p == 0 ? n - 1 : c.p - 1;
+    c.u = V.pxy[c.p]; c.s = V.pxy[c.p + 1]; c.m = V.pxy[pm];
+    c.dnp = V.dn[c.p]; c.dnm = V.dn[pm];
+    c.su = V.tid[c.p + 1]; c.pu = V.tid[pm];
+}
+
+// the four deltas of record (u,w), K = K-offset cost(u,w): dsame = the moves valid in the CURRENT relative direction
+// ({p,q}: successors paired, {p-1,q-1}: predecessors paired), dflip = those valid once exactly one of u, w has turned
+template <class M>
+__device__ __forceinline__ void record_deltas(const TourView &V, const PosPatch &F, const NodeCtx &c, int w, int K, int &dsame, int &dflip) {
+    const int n = V.n;
+    const int q = pos_of(V, F, w), qm = q == 0 ? n - 1 : q - 1;
+    const double2 sw = V.pxy[q + 1], pw = V.pxy[qm];
+    const unsigned dnq = (unsigned)V.dn[q], dnqm = (unsigned)V.dn[qm];
+    const unsigned kss = (unsigned)M::K(c.s.x, c.s.y, sw.x, sw.y), kpp = (unsigned)M::K(c.m.x, c.m.y, pw.x, pw.y);
+    const unsigned ksp = (unsigned)M::K(c.s.x, c.s.y, pw.x, pw.y), kps = (unsigned)M::K(c.m.x, c.m.y, sw.x, sw.y);
+    const unsigned k = (unsigned)K;
+    const int dss = (int)(k + kss - (unsigned)c.dnp - dnq), dpp = (int)(k + kpp - (unsigned)c.dnm - dnqm);
+    const int dsp = (int)(k + ksp - (unsigned)c.dnp - dnqm), dps = (int)(k + kps - (unsigned)c.dnm - dnq);
+    dsame = min(dss, dpp);
+    dflip = min(dsp, dps);
+}
+
+// The streaming loop itself contains no call and no gather other than o8[w]: whatever needs more -- a record at or below
+// the lane's running best (exact evaluation), a dirty record, a node whose list is stale, long or uncached -- is appended
+// to a warp-private ATTENTION buffer (the first half of the warp's record buffer) and dealt with by one separate
+// (noinline) function after the loop, or when the buffer runs full.  The second half collects the records for the exact
+// evaluation (pairs_eval).
+constexpr int AB_CAP = PR_WBUF / 2;            // attention entries per warp
+constexpr int EB_CAP = PR_WBUF - AB_CAP;       // evaluation records per warp
+constexpr unsigned AT_HIT = 0, AT_DIRTY = 1, AT_NODE = 2;
+
+struct ScanAcc {
+    unsigned long long bestkey;
+    long long ncand;
+    int best, ecount;
+};
+
+// append the warp's records (hit lanes) to the evaluation half, evaluating it first when it is nearly full
+template <class M, int NE>
+__device__ __forceinline__ void eval_push(const TourView &V, const PosPatch &F, uint4 *ebuf, ScanAcc &a, bool hit, int p, int w, int K) {
+    const unsigned mask = __ballot_sync(FULL, hit);
+    if (mask == 0) return;                                         // warp-uniform
+    if (a.ecount > EB_CAP - 32) {
+        __syncwarp();
+        pairs_eval<M, NE, false>(V, F, ebuf, a.ecount, a.best, a.bestkey);
+        __syncwarp();
+        a.ecount = 0;
+    }
+    if (hit) ebuf[a.ecount + __popc(mask & ((1u << (threadIdx.x & 31)) - 1))] = make_uint4((unsigned)p, (unsigned)w, (unsigned)K, 3u);
+    a.ecount += __popc(mask);
+}
+
+__device__ __forceinline__ void enqueue_box(unsigned long long *qctr, BigBox *boxes, int p, int cy0, int cx0, int cx1, int nrows) {
+    const unsigned long long old = atomicAdd(qctr, (1ull << 40) | (unsigned long long)nrows);
+    BigBox bx;
+    bx.p = p; bx.cy0 = cy0; bx.cx0 = cx0; bx.cx1 = cx1; bx.nrows = nrows; bx.pad = 0;
+    bx.base = (long long)(old & PR_UNIT_MASK);
+    boxes[old >> 40] = bx;
+}
+
+template <class M>
+__device__ __forceinline__ bool node_box(const SpatialGrid &G, const NodeCtx &c, int &cx0, int &cx1, int &cy0, int &cy1) {
+    const int rr = max(c.dnp, c.dnm) - KOFF;
+    if (rr <= 0) return false;                                     // both tour edges cost 0: nothing can be cheaper
+    const double Rad = M::radius((double)rr);
+    cx0 = max(0, min(G.W - 1, __double2int_rd((c.u.x - Rad - G.gx0) * G.inv_cell)));
+    cx1 = max(0, min(G.W - 1, __double2int_rd((c.u.x + Rad - G.gx0) * G.inv_cell)));
+    cy0 = max(0, min(G.H - 1, __double2int_rd((c.u.y - Rad - G.gy0) * G.inv_cell)));
+    cy1 = max(0, min(G.H - 1, __double2int_rd((c.u.y + Rad - G.gy0) * G.inv_cell)));
+    return true;
+}
+
+// Warp-wide search around node u: rewrites u's list and hands the records that can win NOW to the exact evaluation.
+// SETTLE: only bring the cache up to date (no candidates, no queue): used when a launch ends right after a move.
+template <class M, int NE, bool SETTLE>
+__device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGrid &G, const PosPatch &F, const NbCache &C, int u, int ext,
+                                             unsigned long long *qctr, BigBox *boxes, uint4 *ebuf, ScanAcc &a) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
-    for (int p0 = t - lane; p0 < n; p0 += nthreads) {              // warp-uniform trip count
-        const int p = p0 + lane;
-        int ida = 0, dnp = 0, dnm = 0, cnt = 0;
-        bool stale = false;
-        if (p < n) {
-            ida = V.tid[p];
-            dnp = V.dn[p];
-            dnm = V.dn[p == 0 ? n - 1 : p - 1];
-            cnt = nb[(size_t)ida * NB_STRIDE].x;
-            stale = cnt < 0 || ida == F.node0 || ida == F.node1 || ida == F.node2 || ida == F.node3;
-            if (stale) cnt = 0;
+    int *line = C.lines + (size_t)u * NB_WORDS;
+    NodeCtx c;
+    node_ctx(V, F, u, c);
+    int cx0, cx1, cy0, cy1;
+    if (!node_box<M>(G, c, cx0, cx1, cy0, cy1)) {
+        if (lane == 0) line[0] = (ext + 1) << 10;
+        return;
+    }
+    const int nrows = cy1 - cy0 + 1;
+    int tot = 0;
+    for (int r = lane; r < nrows; r += 32) tot += G.cell_start[(cy0 + r) * G.W + cx1 + 1] - G.cell_start[(cy0 + r) * G.W + cx0];
+    tot = __reduce_add_sync(FULL, tot);
+    if (lane == 0) { NBSTAT(0, 1); NBSTAT(7, tot); }
+    if (tot > NB_WALK_MAX) {                                       // a long tour edge: phase 2, in this and every later scan
+        if (lane == 0) {
+            line[0] = ((ext + 1) << 10) | NB_CF_BIG;
+            if (!SETTLE) enqueue_box(qctr, boxes, c.p, cy0, cx0, cx1, nrows);
+            NBSTAT(1, 1);
         }
-        // the cached lists of the warp's 32 positions, in lockstep
-        const int maxc = __reduce_max_sync(FULL, cnt);
-        const int2 *line = nb + (size_t)ida * NB_STRIDE + 1;
-        for (int j = 0; j < maxc; ++j) {
-            if (wcount > PR_WBUF - 32) {                           // warp-uniform: flush
-                __syncwarp();
-                pairs_eval<M, NE, false>(V, F, wbuf, wcount, best, bestkey);
-                __syncwarp();
-                wcount = 0;
-            }
-            int2 r = make_int2(0, 0);
-            if (j < cnt) r = line[j];
-            const unsigned type = j < cnt ? ((r.y < dnp ? 1u : 0u) | (r.y < dnm ? 2u : 0u)) : 0u;
-            const unsigned mask = __ballot_sync(FULL, type != 0);
-            if (type) wbuf[wcount + __popc(mask & lt)] = make_uint4((unsigned)p, (unsigned)r.x, (unsigned)r.y, type);
-            wcount += __popc(mask);
-        }
-        ncand += cnt;
-        // stale nodes: one warp-wide search each, which also rewrites the node's line
-        unsigned sm = __ballot_sync(FULL, stale);
-        while (sm) {
-            const int src = __ffs(sm) - 1;
-            sm &= sm - 1;
-            const int sp = __shfl_sync(FULL, p, src), su = __shfl_sync(FULL, ida, src);
-            const int sdnp = __shfl_sync(FULL, dnp, src), sdnm = __shfl_sync(FULL, dnm, src);
-            int2 *blk = nb + (size_t)su * NB_STRIDE;
-            const int rr = max(sdnp, sdnm) - KOFF;
-            if (rr <= 0) {                                         // both tour edges cost 0: nothing can be cheaper
-                if (lane == 0) blk[0].x = 0;
-                continue;
-            }
-            const double2 u = V.pxy[sp];
-            const double Rad = M::radius((double)rr);
-            const int cx0 = max(0, min(G.W - 1, __double2int_rd((u.x - Rad - G.gx0) * G.inv_cell)));
-            const int cx1 = max(0, min(G.W - 1, __double2int_rd((u.x + Rad - G.gx0) * G.inv_cell)));
-            const int cy0 = max(0, min(G.H - 1, __double2int_rd((u.y - Rad - G.gy0) * G.inv_cell)));
-            const int cy1 = max(0, min(G.H - 1, __double2int_rd((u.y + Rad - G.gy0) * G.inv_cell)));
-            const int nrows = cy1 - cy0 + 1;
-            int tot = 0;
-            for (int r = lane; r < nrows; r += 32) tot += G.cell_start[(cy0 + r) * G.W + cx1 + 1] - G.cell_start[(cy0 + r) * G.W + cx0];
-            tot = __reduce_add_sync(FULL, tot);
-            if (tot > PR_COOP_MAX) {                               // a long tour edge: the box goes to phase 2, the line stays stale
+        return;
+    }
+    int *pool = ext >= 0 ? C.pool + (size_t)ext * NB_EXT * 3 : nullptr;
+    bool asked = ext >= 0;
+    const int ou = V.o8[u];
+    const int thr = max(c.dnp, c.dnm);
+    if (lane == 0) a.ncand += tot;
+    int stored = 0;
+    for (int r = 0; r < nrows; ++r) {
+        const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
+        for (int k0 = lo; k0 < hi; k0 += 32) {
+            const int k = min(k0 + lane, hi - 1);
+            const double2 cw = G.cxy[k];
+            const int w = G.cnode[k];
+            const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
+            const bool pass = k0 + lane < hi && K < thr && w != u && w != c.su && w != c.pu;      // tour neighbours: refinment.c:55
+            int dsame = 0, dflip = 0;
+            if (pass) record_deltas<M>(V, F, c, w, K, dsame, dflip);
+            const unsigned mask = __ballot_sync(FULL, pass);
+            if (!asked && stored + __popc(mask) > NB_CAP) {        // the list outgrows the line: the node gets a pool slot, for good
+                asked = true;
                 if (lane == 0) {
-                    const unsigned long long old = atomicAdd(qctr, (1ull << 40) | (unsigned long long)nrows);
-                    BigBox bx;
-                    bx.p = sp; bx.cy0 = cy0; bx.cx0 = cx0; bx.cx1 = cx1; bx.nrows = nrows; bx.pad = 0;
-                    bx.base = (long long)(old & PR_UNIT_MASK);
-                    boxes[old >> 40] = bx;
-                    blk[0].x = NB_STALE;
+                    ext = atomicAdd(C.pool_next, 1);
+                    if (ext >= C.slots) ext = -1;                  // pool dry: the node stays stale
                 }
-                continue;
-            }
-            if (lane == 0) ncand += tot;
-            int stored = 0;
-            for (int r = 0; r < nrows; ++r) {
-                const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
-                for (int k0 = lo; k0 < hi; k0 += 32) {
-                    if (wcount > PR_WBUF - 32) {
-                        __syncwarp();
-                        pairs_eval<M, NE, false>(V, F, wbuf, wcount, best, bestkey);
-                        __syncwarp();
-                        wcount = 0;
-                    }
-                    const int k = min(k0 + lane, hi - 1);
-                    const double2 c = G.cxy[k];
-                    const int w = G.cnode[k];
-                    const int K = M::K(u.x, u.y, c.x, c.y);
-                    const unsigned type = (k0 + lane < hi && w != su) ? ((K < sdnp ? 1u : 0u) | (K < sdnm ? 2u : 0u)) : 0u;
-                    const unsigned mask = __ballot_sync(FULL, type != 0);
-                    if (type) {
-                        const int o = __popc(mask & lt);
-                        if (stored + o < NB_CAP) blk[1 + stored + o] = make_int2(w, K);
-                        wbuf[wcount + o] = make_uint4((unsigned)sp, (unsigned)w, (unsigned)K, type);
-                    }
-                    stored += __popc(mask);
-                    wcount += __popc(mask);
+                ext = __shfl_sync(FULL, ext, 0);
+                if (ext >= 0) {
+                    pool = C.pool + (size_t)ext * NB_EXT * 3;
+                    __syncwarp();                                  // the records written to the line so far, by other lanes
+                    if (lane < 3 * stored) pool[lane] = line[1 + lane];
                 }
             }
-            if (lane == 0) blk[0].x = stored <= NB_CAP ? stored : NB_STALE;
+            if (pass) {
+                const int o = stored + __popc(mask & lt);
+                const bool rel = ((ou ^ V.o8[w]) & 1) != 0;
+                const int d0 = rel ? dflip : dsame, d1 = rel ? dsame : dflip;
+                if (o < NB_CAP) { line[1 + 3 * o] = w; line[2 + 3 * o] = d0; line[3 + 3 * o] = d1; }
+                if (pool && o < NB_EXT) { pool[3 * o] = w; pool[3 * o + 1] = d0; pool[3 * o + 2] = d1; }
+            }
+            stored += __popc(mask);
+            if (!SETTLE) {
+                const bool hit = pass && dsame <= a.best;
+                if (hit) a.best = dsame;
+                eval_push<M, NE>(V, F, ebuf, a, hit, c.p, w, K);
+            }
+        }
+    }
+    if (lane == 0) line[0] = ((ext + 1) << 10) | (stored <= (ext >= 0 ? NB_EXT : NB_CAP) ? stored : NB_CF_STALE);
+}
+
+// one cached record of node u that needs the position arrays: dirty -> recomputed and written back; at or below the
+// lane's best -> to the exact evaluation
+template <class M, int NE, bool SETTLE>
+__device__ __forceinline__ void record_attend(const TourView &V, const PosPatch &F, uint4 *ebuf, ScanAcc &a, bool live, bool dirty,
+                                              int u, int w, int *rec) {
+    bool hit = live && !dirty;
+    int p = 0, K = 0;
+    if (live) {
+        NBSTAT(dirty ? 3 : 4, 1);
+        NodeCtx c;
+        node_ctx(V, F, u, c);
+        p = c.p;
+        const double2 wxy = V.pxy[pos_of(V, F, w)];
+        K = M::K(c.u.x, c.u.y, wxy.x, wxy.y);
+        if (dirty) {
+            int dsame, dflip;
+            record_deltas<M>(V, F, c, w, K, dsame, dflip);
+            const bool rel = ((V.o8[u] ^ V.o8[w]) & 1) != 0;
+            rec[1] = rel ? dflip : dsame;
+            rec[2] = rel ? dsame : dflip;
+            hit = dsame <= a.best;
+            if (hit) a.best = dsame;
+        }
+    }
+    if (!SETTLE) eval_push<M, NE>(V, F, ebuf, a, hit, p, w, K);
+}
+
+// the attention entries of a warp: {u, w, record address | kind}
+template <class M, int NE, bool SETTLE>
+__device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPatch F, NbCache C, unsigned long long *qctr, BigBox *boxes,
+                                       uint4 *abuf, int acount, ScanAcc a) {
+    const SpatialGrid &G = *Gp;
+    const int lane = threadIdx.x & 31;
+    uint4 *ebuf = abuf + AB_CAP;
+    if (lane == 0) NBSTAT(6, 1);
+    __syncwarp();
+    for (int base = 0; base < acount; base += 32) {
+        const bool have = base + lane < acount;
+        uint4 e = make_uint4(0, 0, AT_NODE, 0);
+        if (have) e = abuf[base + lane];
+        const unsigned kind = e.z & 3u;
+        int *rec = reinterpret_cast<int *>(((unsigned long long)e.w << 32) | (unsigned long long)(e.z & ~3u));
+        // records: every lane its own
+        const bool isrec = have && kind != AT_NODE;
+        if (__any_sync(FULL, isrec)) record_attend<M, NE, SETTLE>(V, F, ebuf, a, isrec, kind == AT_DIRTY, (int)e.x, (int)e.y, rec);
+        // nodes: one at a time, the whole warp
+        unsigned nm = __ballot_sync(FULL, have && kind == AT_NODE);
+        while (nm) {
+            const int src = __ffs(nm) - 1;
+            nm &= nm - 1;
+            const int u = (int)__shfl_sync(FULL, e.x, src), hdr = (int)__shfl_sync(FULL, e.y, src);
+            const int cf = hdr & 0x3FF, ext = (hdr >> 10) - 1;
+            if (cf == NB_CF_STALE || in_patch(F, u)) {             // the four of the last move, never searched, list that did not fit
+                rebuild_list<M, NE, SETTLE>(V, G, F, C, u, ext, qctr, boxes, ebuf, a);
+            } else if (cf == NB_CF_BIG) {                          // uncached (long tour edge): the box goes to phase 2
+                if (!SETTLE && lane == 0) {
+                    NBSTAT(1, 1);
+                    NodeCtx c;
+                    node_ctx(V, F, u, c);
+                    int cx0, cx1, cy0, cy1;
+                    if (node_box<M>(G, c, cx0, cx1, cy0, cy1)) enqueue_box(qctr, boxes, c.p, cy0, cx0, cx1, cy1 - cy0 + 1);
+                }
+            } else {                                               // a long list: all lanes striding over the node's pool slot
+                int *sl = C.pool + (size_t)ext * NB_EXT * 3;
+                const int ou = V.o8[u];
+                if (lane == 0) { a.ncand += cf; NBSTAT(2, 1); }
+                for (int j0 = 0; j0 < cf; j0 += 32) {
+                    const int j = j0 + lane;
+                    bool live = j < cf, dirty = false;
+                    int w = 0;
+                    if (live) {
+                        w = sl[3 * j];
+                        const int d0 = sl[3 * j + 1], d1 = sl[3 * j + 2];
+                        dirty = d0 == NB_DIRTY || in_patch(F, w);
+                        const int d = ((ou ^ V.o8[w]) & 1) ? d1 : d0;
+                        if (!dirty) { live = d <= a.best; if (live) a.best = d; }
+                    }
+                    if (__any_sync(FULL, live)) record_attend<M, NE, SETTLE>(V, F, ebuf, a, live, dirty, u, w, sl + 3 * j);
+                }
+            }
         }
     }
     __syncwarp();
-    pairs_eval<M, NE, false>(V, F, wbuf, wcount, best, bestkey);
+    return a;
+}
+
+// The cached scan: thread `t` of `nthreads` cooperating threads (a grid, a cluster or one CTA; t's warp is complete)
+// takes the NODES t, t + nthreads, ...
+template <class M, int NE, bool SETTLE>
+__device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid &G, const PosPatch &F, int t, int nthreads,
+                                            unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, const NbCache &C, int &best,
+                                            unsigned long long &bestkey, long long &ncand) {
+    ScanAcc a;
+    a.bestkey = bestkey; a.ncand = ncand; a.best = best; a.ecount = 0;
+    int acount = 0;
+    const int n = V.n;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt = (1u << lane) - 1;
+    for (int u0 = t - lane; u0 < n; u0 += nthreads) {              // warp-uniform trip count
+        if (acount > AB_CAP - 32 * (NB_CAP + 1)) {                 // warp-uniform, rare
+            a = attend<M, NE, SETTLE>(V, &G, F, C, qctr, boxes, wbuf, acount, a);
+            acount = 0;
+        }
+        const int u = u0 + lane;
+        int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
+        int ou = 0;
+        bool inF = false;
+        int *line = C.lines + (size_t)min(u, n - 1) * NB_WORDS;
+        if (u < n) {
+            const int4 *L = reinterpret_cast<const int4 *>(line);
+            q0 = L[0]; q1 = L[1]; q2 = L[2]; q3 = L[3];
+            ou = V.o8[u];
+            inF = in_patch(F, u);
+        }
+        const int cf = q0.x & 0x3FF;
+        const bool node_work = u < n && (inF || cf > NB_CAP);      // stale, uncached or long: all of it happens in attend()
+        const int inl = node_work ? 0 : cf;
+        a.ncand += inl;
+        {
+            const unsigned m = __ballot_sync(FULL, node_work);
+            if (node_work) wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)u, (unsigned)q0.x, AT_NODE, 0u);
+            acount += __popc(m);
+        }
+        const int rw[NB_CAP] = {q0.y, q1.x, q1.w, q2.z, q3.y};
+        const int r0[NB_CAP] = {q0.z, q1.y, q2.x, q2.w, q3.z};
+        const int r1[NB_CAP] = {q0.w, q1.z, q2.y, q3.x, q3.w};
+        const int maxinl = __reduce_max_sync(FULL, inl);
+#pragma unroll
+        for (int j = 0; j < NB_CAP; ++j) {
+            if (j < maxinl) {                                      // warp-uniform
+                bool flag = false;
+                unsigned kind = AT_HIT;
+                if (j < inl) {
+                    const int w = rw[j];
+                    const int d = ((ou ^ V.o8[w]) & 1) ? r1[j] : r0[j];
+                    if (r0[j] == NB_DIRTY || in_patch(F, w)) { flag = true; kind = AT_DIRTY; }
+                    else if (!SETTLE && d <= a.best) { flag = true; a.best = d; }
+                }
+                const unsigned m = __ballot_sync(FULL, flag);
+                if (flag) {
+                    const unsigned long long ra = (unsigned long long)(line + 1 + 3 * j);
+                    wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)u, (unsigned)rw[j], (unsigned)(ra & 0xFFFFFFFFu) | kind, (unsigned)(ra >> 32));
+                }
+                acount += __popc(m);
+            }
+        }
+    }
+    if (acount > 0) a = attend<M, NE, SETTLE>(V, &G, F, C, qctr, boxes, wbuf, acount, a);
+    if (!SETTLE && a.ecount > 0) {
+        __syncwarp();
+        pairs_eval<M, NE, false>(V, F, wbuf + AB_CAP, a.ecount, a.best, a.bestkey);
+    }
+    best = a.best; bestkey = a.bestkey; ncand = a.ncand;
 }
 
 // Phase 2 (behind a barrier): the queued boxes, cut into (box, cell row) units -- one contiguous
@@ -659,7 +918,7 @@ __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGr
 template <class M, int BLK>
 __global__ void __launch_bounds__(BLK, 1)
 descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
-                      long long max_moves, unsigned long long *qctr, BigBox *boxes, uint4 *wbuf_all, int2 *nb) {
+                      long long max_moves, unsigned long long *qctr, BigBox *boxes, uint4 *wbuf_all, NbCache C) {
     constexpr int WARPS = BLK / 32;
     constexpr int NE = BLK > 512 ? 2 : 4;                // records in flight per lane while evaluating (64 / 128 registers)
     cg::grid_group grid = cg::this_grid();
@@ -671,6 +930,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
     const long long Wtot = (long long)gridDim.x * WARPS;
     uint4 *wbuf = wbuf_all + (size_t)gw * PR_WBUF;
     PosPatch F = POSPATCH_NONE;
+    bool optimum = false;
 #ifdef TSP_PHASE_TIMING
     unsigned long long tprev = 0;
     if (gtid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tprev));
@@ -694,7 +954,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #ifdef TSP_PHASE_TIMING
         unsigned long long tw0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw0));
 #endif
-        pruned_phase1_cached<M, NE>(V, G, F, gtid, gsize, qctr, boxes, wbuf, nb, best, bestkey, ncand);
+        cached_scan<M, NE, false>(V, G, F, gtid, gsize, qctr, boxes, wbuf, C, best, bestkey, ncand);
 #ifdef TSP_PHASE_TIMING
         {   // slowest and average warp of phase 1 (phase_ns[3] = sum over scans of the max, [4]/[5] reused below)
             unsigned long long tw1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw1));
@@ -724,6 +984,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         const unsigned long long kbest = *(volatile unsigned long long *)kslot;
         if (kbest == KEY_EMPTY) {
             if (gtid == 0) { st->status = 1; *qctr = 0; }
+            optimum = true;
             break;
         }
         const int a = key_a(kbest), b = key_b(kbest), delta = key_delta(kbest);
@@ -745,11 +1006,13 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         F.node2 = a; F.node3 = V.tid[seg_e + 1];                               // with node0/node1: the four nodes whose tour edges changed
         if (gtid == 0) { V.pos[F.node0] = F.pos0; V.pos[F.node1] = F.pos1; }   // deferred end-node positions
     }
-    // move cap reached: the last move's four nodes were not searched again in this launch, so their cached lines are
-    // marked in memory for the next one (after a local optimum F's nodes were rewritten by the final scan: harmless)
-    if (gtid == 0 && F.node0 >= 0) {
-        nb[(size_t)F.node0 * NB_STRIDE].x = NB_STALE; nb[(size_t)F.node1 * NB_STRIDE].x = NB_STALE;
-        nb[(size_t)F.node2 * NB_STRIDE].x = NB_STALE; nb[(size_t)F.node3 * NB_STRIDE].x = NB_STALE;
+    // move cap reached: no scan has followed the last move in this launch, and the next launch knows nothing of F --
+    // bring the cache up to date now (the four lists, the records pointing at those four nodes), without candidates
+    if (!optimum && F.node0 >= 0) {
+        int best = -1;
+        unsigned long long bestkey = KEY_EMPTY;
+        long long ncand = 0;
+        cached_scan<M, NE, true>(V, G, F, gtid, gsize, qctr, boxes, wbuf, C, best, bestkey, ncand);
     }
 }
 
@@ -860,7 +1123,10 @@ struct MultiSlots {
     int *tid, *dn;     // [slots][n+1]
     int *pos;          // [slots][n]
     BigBox *boxes;     // [slots][n]
-    int2 *nb;          // [slots][n * NB_STRIDE]  neighbour cache of the slot's current descent
+    int *nb;           // [slots][n * NB_WORDS]  delta cache of the slot's current descent: node lines,
+    int *nb_pool;      // [slots][nb_pool_slots(n) * NB_EXT * 3]                               extension pool,
+    int *nb_next;      // [slots]                                                              its bump counter,
+    unsigned char *o8; // [slots][n]                                                           orientation bits
     int *best_path;    // [slots][n]  successor array of the CTA's best tour
     long long *best_cost;   // [slots]
     int *best_start;        // [slots]
@@ -917,7 +1183,12 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     V.dns = V.dn;
     V.pos = S.pos + slot * (size_t)n;
     BigBox *boxes = S.boxes + slot * (size_t)n;
-    int2 *nb = S.nb + slot * (size_t)n * NB_STRIDE;
+    NbCache C;
+    C.lines = S.nb + slot * (size_t)n * NB_WORDS;
+    C.slots = nb_pool_slots(n);
+    C.pool = S.nb_pool + slot * (size_t)C.slots * NB_EXT * 3;
+    C.pool_next = S.nb_next + slot;
+    V.o8 = S.o8 + slot * (size_t)n;
     int *best_path = S.best_path + slot * (size_t)n;
     uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * PR_WBUF;
     if (t == 0) { *s_bestcost = -1; *s_stop = 0; S.best_cost[slot] = -1; S.best_start[slot] = -1; }
@@ -938,9 +1209,9 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             const int node = order[p == n ? 0 : p];
             V.pxy[p] = xy[node];
             V.tid[p] = node;
-            if (p < n) { V.pos[node] = p; nb[(size_t)p * NB_STRIDE].x = NB_STALE; }    // a new tour: every cached line is stale
+            if (p < n) { V.pos[node] = p; C.lines[(size_t)p * NB_WORDS] = NB_HDR_STALE; V.o8[p] = 0; }    // a new tour: every cached list is stale
         }
-        if (t == 0) { *s_cost = 0; *s_q = 0; }
+        if (t == 0) { *s_cost = 0; *s_q = 0; *C.pool_next = 0; }
         if (threadIdx.x == 0) { s_key_[0] = KEY_EMPTY; s_key_[1] = KEY_EMPTY; }
         team_sync<CL>();
         long long local = 0;
@@ -966,7 +1237,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
         for (;;) {
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
-            pruned_phase1_cached<M, NE>(V, G, F, t, TEAM, s_q, boxes, wbuf, nb, best, bestkey, ncand);
+            cached_scan<M, NE, false>(V, G, F, t, TEAM, s_q, boxes, wbuf, C, best, bestkey, ncand);
             team_sync<CL>();
             pruned_phase2<M, NE, false>(V, G, F, warp, WARPS * CL, *s_q, boxes, wbuf, best, bestkey, ncand, 0);
             bestkey = warp_min_key(bestkey);

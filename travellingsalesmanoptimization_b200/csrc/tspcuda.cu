@@ -60,7 +60,7 @@ enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3, M_G
 struct ScratchBuf { void *p = nullptr; size_t bytes = 0; };
 enum {
     SC_NN_CXY, SC_NN_CID, SC_NN_ORDER, SC_NN_COST, SC_NN_SLOT, SC_BEST_PATH, SC_NEXT, SC_DCOST, SC_DMOVES, SC_DPATHS,
-    SC_M_PXY, SC_M_TID, SC_M_DN, SC_M_POS, SC_M_BOXES, SC_M_BPATH, SC_M_BCOST, SC_M_BSTART, SC_M_CAND, SC_M_NB, SC_DSTATUS,
+    SC_M_PXY, SC_M_TID, SC_M_DN, SC_M_POS, SC_M_BOXES, SC_M_BPATH, SC_M_BCOST, SC_M_BSTART, SC_M_CAND, SC_M_NB, SC_M_NBPOOL, SC_M_NBNEXT, SC_M_O8, SC_DSTATUS,
     SC_T_TEN, SC_T_TRACE, SC_T_BEST, SC_T_OUT, SC_NB_LIST, SC_COUNT
 };
 
@@ -94,7 +94,11 @@ struct tspcuda_ctx {
     unsigned long long *d_qctr = nullptr;
     BigBox *d_boxes = nullptr;
     uint4 *d_wbuf = nullptr;         // per-warp record buffers of the pruned kernels (num_sms * 32 warps)
-    int2 *d_nb = nullptr;            // neighbour cache of the resident tour (pruned.cuh: one 128-byte line per node)
+    int *d_nb = nullptr;             // delta cache of the resident tour (pruned.cuh: one 64-byte line per node,
+    int *d_nb_pool = nullptr;        //   an extension pool for the long lists,
+    int *d_nb_next = nullptr;        //   the pool's bump counter,
+    unsigned char *d_o8 = nullptr;   //   one orientation byte per node) and a byte-per-node flag array for nb_mark_*_kernel
+    unsigned char *d_nbflag = nullptr;
     bool nb_valid = false;           // false: the tour changed behind the cache's back (upload, full-scan or tabu moves)
     int *d_stop = nullptr;           // time-limit flag of the batched multi-start kernels, raised through aux_stream
     int *h_one = nullptr;            // pinned constant 1: source of that copy (a DMA copy needs no SM, a memset kernel might)
@@ -140,7 +144,7 @@ extern "C" void tspcuda_destroy(tspcuda_ctx *c) {
     cudaFree(c->d_tabu); cudaFree(c->d_key); cudaFree(c->d_state); cudaFree(c->d_log);
     cudaFree(c->d_matrix); cudaFree(c->d_sum); cudaFree(c->d_flush);
     cudaFree(c->d_cell_start); cudaFree(c->d_cell_count); cudaFree(c->d_cnode); cudaFree(c->d_cxy);
-    cudaFree(c->d_qctr); cudaFree(c->d_boxes); cudaFree(c->d_wbuf); cudaFree(c->d_nb); cudaFree(c->d_stop);
+    cudaFree(c->d_qctr); cudaFree(c->d_boxes); cudaFree(c->d_wbuf); cudaFree(c->d_nb); cudaFree(c->d_nb_pool); cudaFree(c->d_nb_next); cudaFree(c->d_o8); cudaFree(c->d_nbflag); cudaFree(c->d_stop);
     if (c->h_one) cudaFreeHost(c->h_one);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     for (ScratchBuf &b : c->scratch) cudaFree(b.p);
@@ -267,7 +271,12 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         CKC(cudaMalloc(&c->d_qctr, sizeof(unsigned long long)));
         CKC(cudaMalloc(&c->d_boxes, sizeof(BigBox) * n));
         CKC(cudaMalloc(&c->d_wbuf, sizeof(uint4) * (size_t)PR_WBUF * 32 * c->num_sms));
-        CKC(cudaMalloc(&c->d_nb, sizeof(int2) * (size_t)NB_STRIDE * n));
+        CKC(cudaMalloc(&c->d_nb, sizeof(int) * (size_t)NB_WORDS * n));
+        CKC(cudaMalloc(&c->d_nb_pool, sizeof(int) * 3 * (size_t)NB_EXT * nb_pool_slots(n)));
+        CKC(cudaMalloc(&c->d_nb_next, sizeof(int)));
+        CKC(cudaMalloc(&c->d_o8, n));
+        CKC(cudaMalloc(&c->d_nbflag, n));
+        CKC(cudaMemsetAsync(c->d_nbflag, 0, n, c->stream));
         G.cell_start = c->d_cell_start; G.cnode = c->d_cnode; G.cxy = c->d_cxy;
         CKC(cudaMemsetAsync(c->d_cell_count, 0, sizeof(int) * ncells, c->stream));
         CKC(cudaMemsetAsync(c->d_qctr, 0, sizeof(unsigned long long), c->stream));
@@ -388,6 +397,7 @@ template <class M>
 static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max_moves) {
     TourView V = c->tour;
     V.dns = V.dn;
+    V.o8 = c->d_o8;
     SpatialGrid G = c->grid;
     unsigned long long *key = c->d_key, *qctr = c->d_qctr;
     DescState *st = c->d_state;
@@ -395,9 +405,10 @@ static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max
     long long log_cap = c->log_cap;
     BigBox *boxes = c->d_boxes;
     uint4 *wbuf = c->d_wbuf;
-    int2 *nb = c->d_nb;
-    if (!c->nb_valid) {                                        // the tour was replaced or moved by another kernel: every line is stale
-        nb_invalidate_kernel<<<grid_for(c->n, 4 * c->num_sms), 256, 0, c->stream>>>(nb, c->n);
+    NbCache nb;
+    nb.lines = c->d_nb; nb.pool = c->d_nb_pool; nb.pool_next = c->d_nb_next; nb.slots = nb_pool_slots(c->n);
+    if (!c->nb_valid) {                                        // the tour was replaced or moved by another kernel: every list is stale
+        nb_invalidate_kernel<<<grid_for(c->n, 4 * c->num_sms), 256, 0, c->stream>>>(nb, c->d_o8, c->n);
         c->stats.kernel_launches += 1;
         c->nb_valid = true;
     }
@@ -491,6 +502,17 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
                     c->h_state->phase_ns[1] * 1e-6, c->h_state->phase_ns[2] * 1e-6,
                     (double)c->h_state->phase_ns[4] / std::max<long long>(1, c->h_state->moves + 1),
                     (double)c->h_state->phase_ns[5] / std::max<long long>(1, c->h_state->moves + 1));
+#endif
+#ifdef TSP_NB_STATS
+        if (pruned && c->h_state->status == 1) {
+            unsigned long long h[8];
+            cudaMemcpyFromSymbol(h, g_nbstat, sizeof(h));
+            const double sc = (double)std::max<long long>(1, c->h_state->moves + 1);
+            fprintf(stderr, "[tspcuda] delta cache per scan: rebuilds %.1f (box nodes %.0f)  queued boxes %.1f  long lists %.1f  dirty %.1f  hits %.1f  evaluated %.1f  attend calls %.1f\n",
+                    h[0] / sc, h[7] / sc, h[1] / sc, h[2] / sc, h[3] / sc, h[4] / sc, h[5] / sc, h[6] / sc);
+            unsigned long long z[8] = {0};
+            cudaMemcpyToSymbol(g_nbstat, z, sizeof(z));
+        }
 #endif
         if (c->h_state->status == 1) break;
         if (time_limit_s >= 0) {
@@ -997,7 +1019,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
     CK(scratch_get(c, SC_BEST_PATH, sizeof(int) * n, best_path));
     std::vector<long long> hc(batch), hf(batch), hm(batch);
     std::vector<int> hs(batch);
-    DevBuf m_pxy, m_tid, m_dn, m_pos, m_boxes, m_bpath, m_bcost, m_bstart, m_cand, m_nb;
+    DevBuf m_pxy, m_tid, m_dn, m_pos, m_boxes, m_bpath, m_bcost, m_bstart, m_cand, m_nb, m_nbpool, m_nbnext, m_o8;
     MultiSlots MS{};
     const int mslots = multi_path ? std::min(batch, c->num_sms) : 0;
     if (multi_path) {
@@ -1007,13 +1029,16 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
         CK(scratch_get(c, SC_M_DN, sizeof(int) * n1 * sl, m_dn));
         CK(scratch_get(c, SC_M_POS, sizeof(int) * (size_t)n * sl, m_pos));
         CK(scratch_get(c, SC_M_BOXES, sizeof(BigBox) * (size_t)n * sl, m_boxes));
-        CK(scratch_get(c, SC_M_NB, sizeof(int2) * (size_t)NB_STRIDE * (size_t)n * sl, m_nb));
+        CK(scratch_get(c, SC_M_NB, sizeof(int) * (size_t)NB_WORDS * (size_t)n * sl, m_nb));
+        CK(scratch_get(c, SC_M_NBPOOL, sizeof(int) * 3 * (size_t)NB_EXT * (size_t)nb_pool_slots(n) * sl, m_nbpool));
+        CK(scratch_get(c, SC_M_NBNEXT, sizeof(int) * sl, m_nbnext));
+        CK(scratch_get(c, SC_M_O8, (size_t)n * sl, m_o8));
         CK(scratch_get(c, SC_M_BPATH, sizeof(int) * (size_t)n * sl, m_bpath));
         CK(scratch_get(c, SC_M_BCOST, sizeof(long long) * sl, m_bcost));
         CK(scratch_get(c, SC_M_BSTART, sizeof(int) * sl, m_bstart));
         CK(scratch_get(c, SC_M_CAND, sizeof(unsigned long long), m_cand));
         MS.pxy = m_pxy.as<double2>(); MS.tid = m_tid.as<int>(); MS.dn = m_dn.as<int>(); MS.pos = m_pos.as<int>();
-        MS.boxes = m_boxes.as<BigBox>(); MS.nb = m_nb.as<int2>(); MS.best_path = m_bpath.as<int>();
+        MS.boxes = m_boxes.as<BigBox>(); MS.nb = m_nb.as<int>(); MS.nb_pool = m_nbpool.as<int>(); MS.nb_next = m_nbnext.as<int>(); MS.o8 = m_o8.as<unsigned char>(); MS.best_path = m_bpath.as<int>();
         MS.best_cost = m_bcost.as<long long>(); MS.best_start = m_bstart.as<int>();
     }
     std::vector<long long> hbc(std::max(1, mslots));
@@ -1105,8 +1130,6 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
             CK(le);
             CK(cudaGetLastError());
             CK(cudaEventRecord(c->ev1, c->stream));
-            CK(cudaMemcpyAsync(hbc.data(), m_bcost.p, sizeof(long long) * g, cudaMemcpyDeviceToHost, c->stream));
-            CK(cudaMemcpyAsync(hbs.data(), m_bstart.p, sizeof(int) * g, cudaMemcpyDeviceToHost, c->stream));
         } else if (cta_path) {
             // K6: every start of the batch descends inside one CTA, no grid barrier per move
             CK(cudaEventRecord(c->ev0, c->stream));
@@ -1119,12 +1142,19 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
         if (multi_path || cta_path) {
             c->stats.kernel_launches += 1;
             unsigned long long hcand = 0;
+            // the clock is watched while the kernel runs; the results are fetched afterwards (a device-to-host copy into
+            // pageable memory blocks the calling thread until everything queued before it has finished)
+            e = wait_with_deadline(c, dl, &raised);
+            if (e) return e;
+            if (multi_path) {
+                CK(cudaMemcpyAsync(hbc.data(), m_bcost.p, sizeof(long long) * g, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(hbs.data(), m_bstart.p, sizeof(int) * g, cudaMemcpyDeviceToHost, c->stream));
+                CK(cudaMemcpyAsync(&hcand, m_cand.p, sizeof(hcand), cudaMemcpyDeviceToHost, c->stream));
+            }
             CK(cudaMemcpyAsync(hf.data(), dcost.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(hm.data(), dmoves.p, sizeof(long long) * cnt, cudaMemcpyDeviceToHost, c->stream));
             CK(cudaMemcpyAsync(hs.data(), dstatus.p, sizeof(int) * cnt, cudaMemcpyDeviceToHost, c->stream));
-            if (multi_path) CK(cudaMemcpyAsync(&hcand, m_cand.p, sizeof(hcand), cudaMemcpyDeviceToHost, c->stream));
-            e = wait_with_deadline(c, dl, &raised);
-            if (e) return e;
+            CK(cudaStreamSynchronize(c->stream));
             clk.lap(clk.descents);
             c->stats.d2h_bytes += (int64_t)(sizeof(long long) * 2 + sizeof(int)) * cnt + 12 * g + 8;
             float ms = 0;
@@ -1211,9 +1241,14 @@ extern "C" int tspcuda_cost_matrix_device(tspcuda_ctx *c, double *ms_out) {
     if (e) return e;
     const size_t n = (size_t)c->n;
     if (!c->d_matrix) CK(cudaMalloc(&c->d_matrix, sizeof(double) * n * n));
-    const int grid = (int)std::min<size_t>(n, (size_t)c->num_sms * TSP_K1_CTAS);
+    // columns per work unit: 4 block-wide trips (2048 cells = 16 KB per row); TSPCUDA_K1_CHUNK (in trips, 0 = whole rows) for measurements
+    int trips = 4;
+    if (const char *e2 = getenv("TSPCUDA_K1_CHUNK")) trips = atoi(e2);
+    const int chunk_pairs = trips > 0 ? trips * TSP_K1_BLOCK : (int)((n / 2 + TSP_K1_BLOCK) / TSP_K1_BLOCK) * TSP_K1_BLOCK;
+    const size_t nunits = ((n + TSP_K1_ROWS - 1) / TSP_K1_ROWS + 1) * std::max<size_t>(1, (n / 2 + chunk_pairs - 1) / chunk_pairs);
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>(nunits, (size_t)c->num_sms * TSP_K1_CTAS));
     CK(cudaEventRecord(c->ev0, c->stream));
-    DISPATCH_METRIC(c->metric, (cost_matrix_kernel<M><<<grid, TSP_K1_BLOCK, 0, c->stream>>>(c->d_xy, c->n, c->d_matrix)));
+    DISPATCH_METRIC(c->metric, (cost_matrix_kernel<M><<<grid, TSP_K1_BLOCK, 0, c->stream>>>(c->d_xy, c->n, c->d_matrix, chunk_pairs)));
     CK(cudaEventRecord(c->ev1, c->stream));
     c->stats.kernel_launches += 1;
     CK(cudaGetLastError());
@@ -1517,10 +1552,11 @@ static int vns_search_impl(tspcuda_ctx *c, int *path, double *cost_inout, int n_
         std::memcpy(c->h_buf, ord.data(), sizeof(int) * n);
         CK(cudaMemcpyAsync(c->d_order, c->h_buf, sizeof(int) * n, cudaMemcpyHostToDevice, c->stream));
         c->stats.h2d_bytes += (int64_t)sizeof(int) * n;
-        // A kick exchanges two blocks: it changes three tour edges, i.e. the neighbours of at most six nodes.  The device's
-        // neighbour cache (pruned.cuh) is kept per NODE and depends on a node's two tour edges only, so only the nodes whose
-        // neighbour pair differs between the tour before and after the kicks are marked stale -- the descent after a kick
-        // then costs a handful of searches instead of one per node.
+        // A kick exchanges two blocks without turning either round: it changes three tour edges, i.e. the neighbours of at
+        // most six nodes, and no node's direction.  The device's delta cache (pruned.cuh) depends, per record (u,w), on the
+        // neighbours of u and w only, so only the nodes whose neighbour pair differs between the tour before and after the
+        // kicks are marked (their lists stale, the records pointing at them dirty) -- the descent after a kick then costs
+        // a handful of searches instead of one per node.
         const bool keep = c->nb_valid;
         changed.clear();
         if (keep && r > 0) {
@@ -1529,7 +1565,7 @@ static int vns_search_impl(tspcuda_ctx *c, int *path, double *cost_inout, int n_
                 const int u = ord[k], kb = where[u];
                 const int p1 = ord[k == 0 ? n - 1 : k - 1], s1 = ord[k + 1 == n ? 0 : k + 1];
                 const int p0 = before[kb == 0 ? n - 1 : kb - 1], s0 = before[kb + 1 == n ? 0 : kb + 1];
-                if (!((p1 == p0 && s1 == s0) || (p1 == s0 && s1 == p0))) changed.push_back(u);
+                if (!(p1 == p0 && s1 == s0)) changed.push_back(u);     // same neighbours in the same direction (the cache's o8 bits stay valid)
             }
         }
         e = tour_from_device_order(c, keep);                   // cost recomputed from the kicked tour (refinment.c:6-9)
@@ -1538,8 +1574,13 @@ static int vns_search_impl(tspcuda_ctx *c, int *path, double *cost_inout, int n_
             DevBuf d_list;
             CK(scratch_get(c, SC_NB_LIST, sizeof(int) * (size_t)n, d_list));
             CK(cudaMemcpyAsync(d_list.p, changed.data(), sizeof(int) * changed.size(), cudaMemcpyHostToDevice, c->stream));
-            nb_invalidate_list_kernel<<<1, 256, 0, c->stream>>>(c->d_nb, d_list.as<int>(), (int)changed.size());
-            c->stats.kernel_launches += 1;
+            NbCache nb;
+            nb.lines = c->d_nb; nb.pool = c->d_nb_pool; nb.pool_next = c->d_nb_next; nb.slots = nb_pool_slots(n);
+            const int cn = (int)changed.size();
+            nb_mark_nodes_kernel<<<1, 256, 0, c->stream>>>(nb, d_list.as<int>(), cn, c->d_nbflag, 1);
+            nb_mark_records_kernel<<<grid_for(n, 4 * c->num_sms), 256, 0, c->stream>>>(nb, c->d_nbflag, n);
+            nb_mark_nodes_kernel<<<1, 256, 0, c->stream>>>(nb, d_list.as<int>(), cn, c->d_nbflag, 0);
+            c->stats.kernel_launches += 3;
             c->stats.h2d_bytes += (int64_t)sizeof(int) * changed.size();
             CK(cudaGetLastError());
         }
