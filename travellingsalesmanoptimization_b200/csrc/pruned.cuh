@@ -503,7 +503,7 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
 constexpr int NB_WORDS = 16;                   // ints per node line
 constexpr int NB_CAP = 5;                      // records held in the line itself
 #ifndef TSP_NB_EXT
-#define TSP_NB_EXT 128
+#define TSP_NB_EXT 256
 #endif
 constexpr int NB_EXT = TSP_NB_EXT;             // records per pool slot
 constexpr int NB_WALK_MAX = 512;               // largest search box (in nodes) a warp walks itself
@@ -512,16 +512,22 @@ constexpr int NB_HDR_STALE = NB_CF_STALE;      // stale, no pool slot
 constexpr int NB_DIRTY = (int)0x80000000;      // d0 of a record that must be recomputed before use
 
 struct NbCache {
-    int *lines;         // [n][NB_WORDS]
-    int *pool;          // [slots][NB_EXT * 3]
-    int *pool_next;     // bump counter of the pool
+    int *lines;             // [n][NB_WORDS]
+    int *pool;              // [slots][NB_EXT * 3]
+    int *pool_next;         // bump counter of the pool
+    unsigned char *cnt8;    // [n] non-zero: the node's line must be looked at (records, stale, uncached); zero: nothing there
+    int *nbig;              // number of uncached (NB_CF_BIG) nodes: phase 2 and its barrier run only while there are any
     int slots;
 };
-__host__ __device__ inline int nb_pool_slots(int n) { return n / 4 + 64; }
+__host__ __device__ inline int nb_pool_slots(int n) { return n / 6 + 64; }
 
 __global__ void nb_invalidate_kernel(NbCache C, unsigned char *o8, int n) {
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) { C.lines[(size_t)u * NB_WORDS] = NB_HDR_STALE; o8[u] = 0; }
-    if (blockIdx.x == 0 && threadIdx.x == 0) *C.pool_next = 0;
+    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+        C.lines[(size_t)u * NB_WORDS] = NB_HDR_STALE;
+        C.cnt8[u] = 1;
+        o8[u] = 0;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { *C.pool_next = 0; *C.nbig = 0; }
 }
 // after the tour was changed from outside WITHOUT any reversal (a VNS kick exchanges blocks): the listed nodes got new
 // neighbours.  Their own lists are marked stale (first kernel, which also raises flag[]), every record pointing at one
@@ -530,11 +536,17 @@ __global__ void nb_mark_nodes_kernel(NbCache C, const int *nodes, int count, uns
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
         const int u = nodes[k];
         flag[u] = (unsigned char)raise;
-        if (raise) { int *h = C.lines + (size_t)u * NB_WORDS; *h = (*h & ~0x3FF) | NB_CF_STALE; }
+        if (raise) {
+            int *h = C.lines + (size_t)u * NB_WORDS;
+            if ((*h & 0x3FF) == NB_CF_BIG) atomicSub(C.nbig, 1);
+            *h = (*h & ~0x3FF) | NB_CF_STALE;
+            C.cnt8[u] = 1;
+        }
     }
 }
 __global__ void nb_mark_records_kernel(NbCache C, const unsigned char *flag, int n) {
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+        if (!C.cnt8[u]) continue;
         int *line = C.lines + (size_t)u * NB_WORDS;
         const int hdr = line[0], cf = hdr & 0x3FF, ext = (hdr >> 10) - 1;
         if (cf >= NB_CF_BIG) continue;
@@ -582,14 +594,20 @@ __device__ __forceinline__ void record_deltas(const TourView &V, const PosPatch 
     dflip = min(dsp, dps);
 }
 
-// The streaming loop itself contains no call and no gather other than o8[w]: whatever needs more -- a record at or below
-// the lane's running best (exact evaluation), a dirty record, a node whose list is stale, long or uncached -- is appended
-// to a warp-private ATTENTION buffer (the first half of the warp's record buffer) and dealt with by one separate
-// (noinline) function after the loop, or when the buffer runs full.  The second half collects the records for the exact
-// evaluation (pairs_eval).
+// The streaming loop itself contains no call and no gather other than o8[w].  A warp owns a contiguous range of nodes:
+// it reads their count bytes (cnt8, 32 at a time), compacts the ids of the nodes that have anything to look at into a small
+// ring in shared memory and works through them 32 per step, every lane a node with a non-empty line -- on pla85900 nine
+// nodes in ten have no candidate at all and cost one byte per scan.  The running best is shared: reduced over the warp
+// after every step and exchanged between the warps of a CTA through one shared-memory word, so only records that tie
+// or beat the best found so far ANYWHERE in the CTA are evaluated exactly; those go straight to the evaluation half of
+// the warp's record buffer as node-id records.  Whatever needs the position arrays -- a dirty record, a node whose list
+// is stale, long or uncached -- is appended to the ATTENTION half and dealt with by one separate (noinline) function
+// after the loop, or when the buffer runs full.
 constexpr int AB_CAP = PR_WBUF / 2;            // attention entries per warp
 constexpr int EB_CAP = PR_WBUF - AB_CAP;       // evaluation records per warp
-constexpr unsigned AT_HIT = 0, AT_DIRTY = 1, AT_NODE = 2;
+constexpr unsigned AT_DIRTY = 1, AT_NODE = 2;
+constexpr unsigned EV_NODEIDS = 4;             // evaluation record {u, w, -, 3 | EV_NODEIDS}: node ids instead of {p, w, K, type}
+constexpr int NB_RING = 64;                    // per-warp ring of pending node ids (shared memory)
 
 struct ScanAcc {
     unsigned long long bestkey;
@@ -597,18 +615,32 @@ struct ScanAcc {
     int best, ecount;
 };
 
+// evaluate the warp's evaluation half: node-id records are completed to {p, w, K, type} first
+template <class M, int NE>
+__device__ __noinline__ ScanAcc flush_records(TourView V, PosPatch F, uint4 *ebuf, ScanAcc a) {
+    __syncwarp();
+    for (int idx = threadIdx.x & 31; idx < a.ecount; idx += 32) {
+        uint4 e = ebuf[idx];
+        if (e.w & EV_NODEIDS) {
+            const int p = pos_of(V, F, (int)e.x);
+            const double2 x = V.pxy[p], y = V.pxy[pos_of(V, F, (int)e.y)];
+            ebuf[idx] = make_uint4((unsigned)p, e.y, (unsigned)M::K(x.x, x.y, y.x, y.y), 3u);
+        }
+    }
+    __syncwarp();
+    pairs_eval<M, NE, false>(V, F, ebuf, a.ecount, a.best, a.bestkey);
+    __syncwarp();
+    a.ecount = 0;
+    return a;
+}
+
 // append the warp's records (hit lanes) to the evaluation half, evaluating it first when it is nearly full
 template <class M, int NE>
-__device__ __forceinline__ void eval_push(const TourView &V, const PosPatch &F, uint4 *ebuf, ScanAcc &a, bool hit, int p, int w, int K) {
+__device__ __forceinline__ void eval_push(const TourView &V, const PosPatch &F, uint4 *ebuf, ScanAcc &a, bool hit, int p, int w, int K, unsigned type) {
     const unsigned mask = __ballot_sync(FULL, hit);
     if (mask == 0) return;                                         // warp-uniform
-    if (a.ecount > EB_CAP - 32) {
-        __syncwarp();
-        pairs_eval<M, NE, false>(V, F, ebuf, a.ecount, a.best, a.bestkey);
-        __syncwarp();
-        a.ecount = 0;
-    }
-    if (hit) ebuf[a.ecount + __popc(mask & ((1u << (threadIdx.x & 31)) - 1))] = make_uint4((unsigned)p, (unsigned)w, (unsigned)K, 3u);
+    if (a.ecount > EB_CAP - 32) a = flush_records<M, NE>(V, F, ebuf, a);
+    if (hit) ebuf[a.ecount + __popc(mask & ((1u << (threadIdx.x & 31)) - 1))] = make_uint4((unsigned)p, (unsigned)w, (unsigned)K, type);
     a.ecount += __popc(mask);
 }
 
@@ -632,19 +664,42 @@ __device__ __forceinline__ bool node_box(const SpatialGrid &G, const NodeCtx &c,
     return true;
 }
 
+// an uncached node while phase 2 is not running: its box is walked here, by this warp alone (the searches' own rule:
+// cost(u,w) below dn[p] -> pair {p, pos w}, below dn[p-1] -> pair {p-1, pos w - 1}; everything else is pairs_eval's)
+template <class M, int NE>
+__device__ __forceinline__ void walk_box(const TourView &V, const SpatialGrid &G, const PosPatch &F, const NodeCtx &c, int cx0, int cx1,
+                                         int cy0, int cy1, uint4 *ebuf, ScanAcc &a) {
+    const int lane = threadIdx.x & 31;
+    for (int cy = cy0; cy <= cy1; ++cy) {
+        const int lo = G.cell_start[cy * G.W + cx0], hi = G.cell_start[cy * G.W + cx1 + 1];
+        if (lane == 0) a.ncand += hi - lo;
+        for (int k0 = lo; k0 < hi; k0 += 32) {
+            const int k = min(k0 + lane, hi - 1);
+            const double2 cw = G.cxy[k];
+            const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
+            const unsigned type = k0 + lane < hi ? ((K < c.dnp ? 1u : 0u) | (K < c.dnm ? 2u : 0u)) : 0u;
+            eval_push<M, NE>(V, F, ebuf, a, type != 0, c.p, G.cnode[k], K, type);
+        }
+    }
+}
+
 // Warp-wide search around node u: rewrites u's list and hands the records that can win NOW to the exact evaluation.
 // SETTLE: only bring the cache up to date (no candidates, no queue): used when a launch ends right after a move.
+// p2: phase 2 runs in this scan (uncached nodes existed when the scan began): a box too large to cache is queued for it,
+// otherwise walked on the spot.
 template <class M, int NE, bool SETTLE>
-__device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGrid &G, const PosPatch &F, const NbCache &C, int u, int ext,
-                                             unsigned long long *qctr, BigBox *boxes, uint4 *ebuf, ScanAcc &a) {
+__device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGrid &G, const PosPatch &F, const NbCache &C, int u, int hdr,
+                                             bool p2, unsigned long long *qctr, BigBox *boxes, uint4 *ebuf, ScanAcc &a) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
     int *line = C.lines + (size_t)u * NB_WORDS;
+    int ext = (hdr >> 10) - 1;
+    const bool was_big = (hdr & 0x3FF) == NB_CF_BIG;
     NodeCtx c;
     node_ctx(V, F, u, c);
     int cx0, cx1, cy0, cy1;
     if (!node_box<M>(G, c, cx0, cx1, cy0, cy1)) {
-        if (lane == 0) line[0] = (ext + 1) << 10;
+        if (lane == 0) { line[0] = (ext + 1) << 10; C.cnt8[u] = 0; if (was_big) atomicSub(C.nbig, 1); }
         return;
     }
     const int nrows = cy1 - cy0 + 1;
@@ -652,60 +707,67 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
     for (int r = lane; r < nrows; r += 32) tot += G.cell_start[(cy0 + r) * G.W + cx1 + 1] - G.cell_start[(cy0 + r) * G.W + cx0];
     tot = __reduce_add_sync(FULL, tot);
     if (lane == 0) { NBSTAT(0, 1); NBSTAT(7, tot); }
-    if (tot > NB_WALK_MAX) {                                       // a long tour edge: phase 2, in this and every later scan
-        if (lane == 0) {
-            line[0] = ((ext + 1) << 10) | NB_CF_BIG;
-            if (!SETTLE) enqueue_box(qctr, boxes, c.p, cy0, cx0, cx1, nrows);
-            NBSTAT(1, 1);
+    bool big = tot > NB_WALK_MAX;                                  // a long tour edge: not cached
+    int stored = 0;
+    if (!big) {
+        int *pool = ext >= 0 ? C.pool + (size_t)ext * NB_EXT * 3 : nullptr;
+        bool asked = ext >= 0;
+        const int ou = V.o8[u];
+        const int thr = max(c.dnp, c.dnm);
+        if (lane == 0) a.ncand += tot;
+        for (int r = 0; r < nrows; ++r) {
+            const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
+            for (int k0 = lo; k0 < hi; k0 += 32) {
+                const int k = min(k0 + lane, hi - 1);
+                const double2 cw = G.cxy[k];
+                const int w = G.cnode[k];
+                const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
+                const bool pass = k0 + lane < hi && K < thr && w != u && w != c.su && w != c.pu;      // tour neighbours: refinment.c:55
+                int dsame = 0, dflip = 0;
+                if (pass) record_deltas<M>(V, F, c, w, K, dsame, dflip);
+                const unsigned mask = __ballot_sync(FULL, pass);
+                if (!asked && stored + __popc(mask) > NB_CAP) {    // the list outgrows the line: the node gets a pool slot, for good
+                    asked = true;
+                    if (lane == 0) {
+                        ext = atomicAdd(C.pool_next, 1);
+                        if (ext >= C.slots) ext = -1;              // pool dry
+                    }
+                    ext = __shfl_sync(FULL, ext, 0);
+                    if (ext >= 0) {
+                        pool = C.pool + (size_t)ext * NB_EXT * 3;
+                        __syncwarp();                              // the records written to the line so far, by other lanes
+                        if (lane < 3 * stored) pool[lane] = line[1 + lane];
+                    }
+                }
+                if (pass) {
+                    const int o = stored + __popc(mask & lt);
+                    const bool rel = ((ou ^ V.o8[w]) & 1) != 0;
+                    const int d0 = rel ? dflip : dsame, d1 = rel ? dsame : dflip;
+                    if (o < NB_CAP) { line[1 + 3 * o] = w; line[2 + 3 * o] = d0; line[3 + 3 * o] = d1; }
+                    if (pool && o < NB_EXT) { pool[3 * o] = w; pool[3 * o + 1] = d0; pool[3 * o + 2] = d1; }
+                }
+                stored += __popc(mask);
+                if (!SETTLE) {
+                    const bool hit = pass && dsame <= a.best;
+                    if (hit) a.best = dsame;
+                    eval_push<M, NE>(V, F, ebuf, a, hit, c.p, w, K, 3u);
+                }
+            }
         }
+        // a list that fits neither the line nor a pool slot is not cached either.  Its candidates of THIS scan were all
+        // handed over above (every record at or below the lane's best), so nothing is walked or queued now.
+        if (stored > (ext >= 0 ? NB_EXT : NB_CAP)) {
+            if (lane == 0) { line[0] = ((ext + 1) << 10) | NB_CF_BIG; C.cnt8[u] = 1; if (!was_big) atomicAdd(C.nbig, 1); NBSTAT(1, 1); }
+            return;
+        }
+        if (lane == 0) { line[0] = ((ext + 1) << 10) | stored; C.cnt8[u] = stored > 0; if (was_big) atomicSub(C.nbig, 1); }
         return;
     }
-    int *pool = ext >= 0 ? C.pool + (size_t)ext * NB_EXT * 3 : nullptr;
-    bool asked = ext >= 0;
-    const int ou = V.o8[u];
-    const int thr = max(c.dnp, c.dnm);
-    if (lane == 0) a.ncand += tot;
-    int stored = 0;
-    for (int r = 0; r < nrows; ++r) {
-        const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
-        for (int k0 = lo; k0 < hi; k0 += 32) {
-            const int k = min(k0 + lane, hi - 1);
-            const double2 cw = G.cxy[k];
-            const int w = G.cnode[k];
-            const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
-            const bool pass = k0 + lane < hi && K < thr && w != u && w != c.su && w != c.pu;      // tour neighbours: refinment.c:55
-            int dsame = 0, dflip = 0;
-            if (pass) record_deltas<M>(V, F, c, w, K, dsame, dflip);
-            const unsigned mask = __ballot_sync(FULL, pass);
-            if (!asked && stored + __popc(mask) > NB_CAP) {        // the list outgrows the line: the node gets a pool slot, for good
-                asked = true;
-                if (lane == 0) {
-                    ext = atomicAdd(C.pool_next, 1);
-                    if (ext >= C.slots) ext = -1;                  // pool dry: the node stays stale
-                }
-                ext = __shfl_sync(FULL, ext, 0);
-                if (ext >= 0) {
-                    pool = C.pool + (size_t)ext * NB_EXT * 3;
-                    __syncwarp();                                  // the records written to the line so far, by other lanes
-                    if (lane < 3 * stored) pool[lane] = line[1 + lane];
-                }
-            }
-            if (pass) {
-                const int o = stored + __popc(mask & lt);
-                const bool rel = ((ou ^ V.o8[w]) & 1) != 0;
-                const int d0 = rel ? dflip : dsame, d1 = rel ? dsame : dflip;
-                if (o < NB_CAP) { line[1 + 3 * o] = w; line[2 + 3 * o] = d0; line[3 + 3 * o] = d1; }
-                if (pool && o < NB_EXT) { pool[3 * o] = w; pool[3 * o + 1] = d0; pool[3 * o + 2] = d1; }
-            }
-            stored += __popc(mask);
-            if (!SETTLE) {
-                const bool hit = pass && dsame <= a.best;
-                if (hit) a.best = dsame;
-                eval_push<M, NE>(V, F, ebuf, a, hit, c.p, w, K);
-            }
-        }
+    if (lane == 0) { line[0] = ((ext + 1) << 10) | NB_CF_BIG; C.cnt8[u] = 1; if (!was_big) atomicAdd(C.nbig, 1); NBSTAT(1, 1); }
+    if (!SETTLE) {
+        if (p2) { if (lane == 0) enqueue_box(qctr, boxes, c.p, cy0, cx0, cx1, nrows); }
+        else walk_box<M, NE>(V, G, F, c, cx0, cx1, cy0, cy1, ebuf, a);
     }
-    if (lane == 0) line[0] = ((ext + 1) << 10) | (stored <= (ext >= 0 ? NB_EXT : NB_CAP) ? stored : NB_CF_STALE);
 }
 
 // one cached record of node u that needs the position arrays: dirty -> recomputed and written back; at or below the
@@ -732,13 +794,13 @@ __device__ __forceinline__ void record_attend(const TourView &V, const PosPatch 
             if (hit) a.best = dsame;
         }
     }
-    if (!SETTLE) eval_push<M, NE>(V, F, ebuf, a, hit, p, w, K);
+    if (!SETTLE) eval_push<M, NE>(V, F, ebuf, a, hit, p, w, K, 3u);
 }
 
-// the attention entries of a warp: {u, w, record address | kind}
+// the attention entries of a warp: records {u, w, record address | AT_DIRTY} and nodes {u, header, AT_NODE}
 template <class M, int NE, bool SETTLE>
-__device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPatch F, NbCache C, unsigned long long *qctr, BigBox *boxes,
-                                       uint4 *abuf, int acount, ScanAcc a) {
+__device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPatch F, NbCache C, bool p2, unsigned long long *qctr,
+                                       BigBox *boxes, uint4 *abuf, int acount, ScanAcc a) {
     const SpatialGrid &G = *Gp;
     const int lane = threadIdx.x & 31;
     uint4 *ebuf = abuf + AB_CAP;
@@ -746,13 +808,13 @@ __device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPat
     __syncwarp();
     for (int base = 0; base < acount; base += 32) {
         const bool have = base + lane < acount;
-        uint4 e = make_uint4(0, 0, AT_NODE, 0);
+        uint4 e = make_uint4(0, 0, 0, 0);
         if (have) e = abuf[base + lane];
         const unsigned kind = e.z & 3u;
         int *rec = reinterpret_cast<int *>(((unsigned long long)e.w << 32) | (unsigned long long)(e.z & ~3u));
-        // records: every lane its own
-        const bool isrec = have && kind != AT_NODE;
-        if (__any_sync(FULL, isrec)) record_attend<M, NE, SETTLE>(V, F, ebuf, a, isrec, kind == AT_DIRTY, (int)e.x, (int)e.y, rec);
+        // dirty records: every lane its own
+        const bool isrec = have && kind == AT_DIRTY;
+        if (__any_sync(FULL, isrec)) record_attend<M, NE, SETTLE>(V, F, ebuf, a, isrec, true, (int)e.x, (int)e.y, rec);
         // nodes: one at a time, the whole warp
         unsigned nm = __ballot_sync(FULL, have && kind == AT_NODE);
         while (nm) {
@@ -760,9 +822,9 @@ __device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPat
             nm &= nm - 1;
             const int u = (int)__shfl_sync(FULL, e.x, src), hdr = (int)__shfl_sync(FULL, e.y, src);
             const int cf = hdr & 0x3FF, ext = (hdr >> 10) - 1;
-            if (cf == NB_CF_STALE || in_patch(F, u)) {             // the four of the last move, never searched, list that did not fit
-                rebuild_list<M, NE, SETTLE>(V, G, F, C, u, ext, qctr, boxes, ebuf, a);
-            } else if (cf == NB_CF_BIG) {                          // uncached (long tour edge): the box goes to phase 2
+            if (cf == NB_CF_STALE || in_patch(F, u)) {             // the four of the last move, or never searched
+                rebuild_list<M, NE, SETTLE>(V, G, F, C, u, hdr, p2, qctr, boxes, ebuf, a);
+            } else if (cf == NB_CF_BIG) {                          // uncached (long tour edge): phase 2 runs, the box goes there
                 if (!SETTLE && lane == 0) {
                     NBSTAT(1, 1);
                     NodeCtx c;
@@ -783,7 +845,7 @@ __device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPat
                         const int d0 = sl[3 * j + 1], d1 = sl[3 * j + 2];
                         dirty = d0 == NB_DIRTY || in_patch(F, w);
                         const int d = ((ou ^ V.o8[w]) & 1) ? d1 : d0;
-                        if (!dirty) { live = d <= a.best; if (live) a.best = d; }
+                        if (!dirty) { live = !SETTLE && d <= a.best; if (live) a.best = d; }
                     }
                     if (__any_sync(FULL, live)) record_attend<M, NE, SETTLE>(V, F, ebuf, a, live, dirty, u, w, sl + 3 * j);
                 }
@@ -794,37 +856,63 @@ __device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPat
     return a;
 }
 
-// The cached scan: thread `t` of `nthreads` cooperating threads (a grid, a cluster or one CTA; t's warp is complete)
-// takes the NODES t, t + nthreads, ...
+// The cached scan: warp `gw` of `nwarps` cooperating warps (a grid, a cluster or one CTA) takes a contiguous range of
+// NODES.  ring: NB_RING ints of shared memory private to the warp; s_best: the CTA's shared running best (armed to -1
+// by the caller behind a barrier); p2: phase 2 runs after this scan (uniform over the team).
 template <class M, int NE, bool SETTLE>
-__device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid &G, const PosPatch &F, int t, int nthreads,
-                                            unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, const NbCache &C, int &best,
-                                            unsigned long long &bestkey, long long &ncand) {
+__device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid &G, const PosPatch &F, int gw, int nwarps, bool p2,
+                                            unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, const NbCache &C, int *ring, int *s_best,
+                                            int &best, unsigned long long &bestkey, long long &ncand) {
     ScanAcc a;
     a.bestkey = bestkey; a.ncand = ncand; a.best = best; a.ecount = 0;
     int acount = 0;
     const int n = V.n;
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
-    for (int u0 = t - lane; u0 < n; u0 += nthreads) {              // warp-uniform trip count
+    uint4 *ebuf = wbuf + AB_CAP;
+    // the four nodes of the last move: one designated warp each (their searches are the longest dependent chains of a scan)
+    if (gw < 4) {
+        const int fu = gw == 0 ? F.node0 : gw == 1 ? F.node1 : gw == 2 ? F.node2 : F.node3;
+        if (fu >= 0) {
+            if (lane == 0) wbuf[0] = make_uint4((unsigned)fu, (unsigned)C.lines[(size_t)fu * NB_WORDS], AT_NODE, 0u);
+            acount = 1;
+        }
+    }
+    const int chunk = (((n + nwarps - 1) / nwarps) + 31) & ~31;
+    const int lo = min(n, gw * chunk), hi = min(n, lo + chunk);
+    int base = lo, head = 0, tail = 0;
+    for (;;) {
+        while (base < hi && tail - head < 32) {                    // refill: the next 32 count bytes
+            const int u = base + lane;
+            const bool want = u < hi && C.cnt8[u] != 0 && !in_patch(F, u);
+            const unsigned m = __ballot_sync(FULL, want);
+            if (want) ring[(tail + __popc(m & lt)) & (NB_RING - 1)] = u;
+            tail += __popc(m);
+            base += 32;
+        }
+        const int step = min(32, tail - head);
+        if (step == 0) break;
+        __syncwarp();
+        const bool have = lane < step;
+        const int u = have ? ring[(head + lane) & (NB_RING - 1)] : 0;
+        head += step;
+        __syncwarp();
         if (acount > AB_CAP - 32 * (NB_CAP + 1)) {                 // warp-uniform, rare
-            a = attend<M, NE, SETTLE>(V, &G, F, C, qctr, boxes, wbuf, acount, a);
+            a = attend<M, NE, SETTLE>(V, &G, F, C, p2, qctr, boxes, wbuf, acount, a);
             acount = 0;
         }
-        const int u = u0 + lane;
+        if (!SETTLE && a.ecount > EB_CAP - 32 * NB_CAP) a = flush_records<M, NE>(V, F, ebuf, a);
         int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
         int ou = 0;
-        bool inF = false;
-        int *line = C.lines + (size_t)min(u, n - 1) * NB_WORDS;
-        if (u < n) {
+        int *line = C.lines + (size_t)u * NB_WORDS;
+        if (have) {
             const int4 *L = reinterpret_cast<const int4 *>(line);
             q0 = L[0]; q1 = L[1]; q2 = L[2]; q3 = L[3];
             ou = V.o8[u];
-            inF = in_patch(F, u);
         }
         const int cf = q0.x & 0x3FF;
-        const bool node_work = u < n && (inF || cf > NB_CAP);      // stale, uncached or long: all of it happens in attend()
-        const int inl = node_work ? 0 : cf;
+        const bool node_work = have && cf > NB_CAP;                // stale, uncached or long: all of it happens in attend()
+        const int inl = (have && !node_work) ? cf : 0;
         a.ncand += inl;
         {
             const unsigned m = __ballot_sync(FULL, node_work);
@@ -834,32 +922,49 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
         const int rw[NB_CAP] = {q0.y, q1.x, q1.w, q2.z, q3.y};
         const int r0[NB_CAP] = {q0.z, q1.y, q2.x, q2.w, q3.z};
         const int r1[NB_CAP] = {q0.w, q1.z, q2.y, q3.x, q3.w};
-        const int maxinl = __reduce_max_sync(FULL, inl);
+        int d[NB_CAP];
+        unsigned dirty = 0;
+        int mine = 0x7FFFFFFF;
 #pragma unroll
         for (int j = 0; j < NB_CAP; ++j) {
-            if (j < maxinl) {                                      // warp-uniform
-                bool flag = false;
-                unsigned kind = AT_HIT;
-                if (j < inl) {
-                    const int w = rw[j];
-                    const int d = ((ou ^ V.o8[w]) & 1) ? r1[j] : r0[j];
-                    if (r0[j] == NB_DIRTY || in_patch(F, w)) { flag = true; kind = AT_DIRTY; }
-                    else if (!SETTLE && d <= a.best) { flag = true; a.best = d; }
-                }
-                const unsigned m = __ballot_sync(FULL, flag);
-                if (flag) {
+            d[j] = 0x7FFFFFFF;
+            if (j < inl) {
+                const int w = rw[j];
+                if (r0[j] == NB_DIRTY || in_patch(F, w)) dirty |= 1u << j;
+                else { d[j] = ((ou ^ V.o8[w]) & 1) ? r1[j] : r0[j]; mine = min(mine, d[j]); }
+            }
+        }
+        if (__any_sync(FULL, dirty != 0)) {                        // rare
+#pragma unroll
+            for (int j = 0; j < NB_CAP; ++j) {
+                const bool f = (dirty >> j) & 1u;
+                const unsigned m = __ballot_sync(FULL, f);
+                if (f) {
                     const unsigned long long ra = (unsigned long long)(line + 1 + 3 * j);
-                    wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)u, (unsigned)rw[j], (unsigned)(ra & 0xFFFFFFFFu) | kind, (unsigned)(ra >> 32));
+                    wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)u, (unsigned)rw[j], (unsigned)(ra & 0xFFFFFFFFu) | AT_DIRTY, (unsigned)(ra >> 32));
                 }
                 acount += __popc(m);
             }
         }
+        if (!SETTLE) {
+            // the best anywhere in the CTA so far; only records that tie or beat it are worth an exact evaluation
+            const int seen = *(volatile int *)s_best;
+            const int wm = __reduce_min_sync(FULL, min(mine, min(a.best, seen)));
+            a.best = wm;
+            if (lane == 0 && wm < seen) atomicMin(s_best, wm);
+            if (__any_sync(FULL, mine <= wm)) {
+#pragma unroll
+                for (int j = 0; j < NB_CAP; ++j) {
+                    const bool hit = d[j] <= wm;
+                    const unsigned m = __ballot_sync(FULL, hit);
+                    if (hit) ebuf[a.ecount + __popc(m & lt)] = make_uint4((unsigned)u, (unsigned)rw[j], 0u, 3u | EV_NODEIDS);
+                    a.ecount += __popc(m);
+                }
+            }
+        }
     }
-    if (acount > 0) a = attend<M, NE, SETTLE>(V, &G, F, C, qctr, boxes, wbuf, acount, a);
-    if (!SETTLE && a.ecount > 0) {
-        __syncwarp();
-        pairs_eval<M, NE, false>(V, F, wbuf + AB_CAP, a.ecount, a.best, a.bestkey);
-    }
+    if (acount > 0) a = attend<M, NE, SETTLE>(V, &G, F, C, p2, qctr, boxes, wbuf, acount, a);
+    if (!SETTLE && a.ecount > 0) a = flush_records<M, NE>(V, F, ebuf, a);
     best = a.best; bestkey = a.bestkey; ncand = a.ncand;
 }
 
@@ -923,12 +1028,15 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
     constexpr int NE = BLK > 512 ? 2 : 4;                // records in flight per lane while evaluating (64 / 128 registers)
     cg::grid_group grid = cg::this_grid();
     __shared__ unsigned long long s_key;
+    __shared__ int s_best;
+    __shared__ int s_ring[WARPS][NB_RING];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gtid = blockIdx.x * BLK + threadIdx.x;
     const int gsize = gridDim.x * BLK;
-    const long long gw = (long long)blockIdx.x * WARPS + warp;
+    // consecutive global warp numbers go to different SMs: the warps that own nodes (and the four that search) spread out
+    const long long gw = (long long)warp * gridDim.x + blockIdx.x;
     const long long Wtot = (long long)gridDim.x * WARPS;
-    uint4 *wbuf = wbuf_all + (size_t)gw * PR_WBUF;
+    uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + warp) * PR_WBUF;
     PosPatch F = POSPATCH_NONE;
     bool optimum = false;
 #ifdef TSP_PHASE_TIMING
@@ -945,8 +1053,12 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #define PHASE_MARK(slot)
 #endif
 
+    // phase 2 (and its grid barrier) runs only while uncached nodes exist.  Every thread takes the count where nobody
+    // changes it: here, before the first scan of the launch, and between the last two barriers of an iteration.
+    bool p2 = *(volatile int *)C.nbig > 0;
+    grid.sync();
     for (long long it = 0; it < max_moves; ++it) {
-        if (threadIdx.x == 0) s_key = KEY_EMPTY;
+        if (threadIdx.x == 0) { s_key = KEY_EMPTY; s_best = -1; }
         __syncthreads();
         int best = -1;
         unsigned long long bestkey = KEY_EMPTY;
@@ -954,16 +1066,16 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #ifdef TSP_PHASE_TIMING
         unsigned long long tw0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw0));
 #endif
-        cached_scan<M, NE, false>(V, G, F, gtid, gsize, qctr, boxes, wbuf, C, best, bestkey, ncand);
+        cached_scan<M, NE, false>(V, G, F, (int)gw, (int)Wtot, p2, qctr, boxes, wbuf, C, s_ring[warp], &s_best, best, bestkey, ncand);
 #ifdef TSP_PHASE_TIMING
         {   // slowest and average warp of phase 1 (phase_ns[3] = sum over scans of the max, [4]/[5] reused below)
             unsigned long long tw1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw1));
             if (lane == 0) { atomicMax((unsigned long long *)&st->phase_ns[3], tw1 - tw0); atomicAdd((unsigned long long *)&st->phase_sum, tw1 - tw0); }
         }
 #endif
-        grid.sync();
-        PHASE_MARK(0)
-        {
+        if (p2) {
+            grid.sync();
+            PHASE_MARK(0)
             const unsigned long long q = *(volatile unsigned long long *)qctr;
 #ifdef TSP_PHASE_TIMING
             if (gtid == 0) { st->phase_ns[4] += (long long)(q & PR_UNIT_MASK); st->phase_ns[5] += (long long)(q >> 40); }
@@ -987,6 +1099,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
             optimum = true;
             break;
         }
+        p2 = *(volatile int *)C.nbig > 0;
         const int a = key_a(kbest), b = key_b(kbest), delta = key_delta(kbest);
         int seg_s, seg_e;
         apply_move<M>(V, a, b, gtid, gsize, false, seg_s, seg_e);
@@ -1012,7 +1125,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         int best = -1;
         unsigned long long bestkey = KEY_EMPTY;
         long long ncand = 0;
-        cached_scan<M, NE, true>(V, G, F, gtid, gsize, qctr, boxes, wbuf, C, best, bestkey, ncand);
+        cached_scan<M, NE, true>(V, G, F, (int)gw, (int)Wtot, false, qctr, boxes, wbuf, C, s_ring[warp], nullptr, best, bestkey, ncand);
     }
 }
 
@@ -1126,7 +1239,9 @@ struct MultiSlots {
     int *nb;           // [slots][n * NB_WORDS]  delta cache of the slot's current descent: node lines,
     int *nb_pool;      // [slots][nb_pool_slots(n) * NB_EXT * 3]                               extension pool,
     int *nb_next;      // [slots]                                                              its bump counter,
-    unsigned char *o8; // [slots][n]                                                           orientation bits
+    unsigned char *o8; // [slots][n]                                                           orientation bits,
+    unsigned char *cnt8; // [slots][n]                                                         count bytes,
+    int *nbig;         // [slots]                                                              number of uncached nodes
     int *best_path;    // [slots][n]  successor array of the CTA's best tour
     long long *best_cost;   // [slots]
     int *best_start;        // [slots]
@@ -1161,7 +1276,8 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     constexpr int TEAM = BLK * CL;                      // threads sharing a descent
     __shared__ unsigned long long s_key_[2], s_q_;
     __shared__ long long s_cost_, s_bestcost_;
-    __shared__ int s_cur_, s_stop_;
+    __shared__ int s_cur_, s_stop_, s_best;
+    __shared__ int s_ring[WARPS][NB_RING];
     unsigned rank = 0;
     unsigned long long *s_q = &s_q_;
     long long *s_cost = &s_cost_, *s_bestcost = &s_bestcost_;
@@ -1188,6 +1304,8 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     C.slots = nb_pool_slots(n);
     C.pool = S.nb_pool + slot * (size_t)C.slots * NB_EXT * 3;
     C.pool_next = S.nb_next + slot;
+    C.cnt8 = S.cnt8 + slot * (size_t)n;
+    C.nbig = S.nbig + slot;
     V.o8 = S.o8 + slot * (size_t)n;
     int *best_path = S.best_path + slot * (size_t)n;
     uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * PR_WBUF;
@@ -1209,10 +1327,10 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             const int node = order[p == n ? 0 : p];
             V.pxy[p] = xy[node];
             V.tid[p] = node;
-            if (p < n) { V.pos[node] = p; C.lines[(size_t)p * NB_WORDS] = NB_HDR_STALE; V.o8[p] = 0; }    // a new tour: every cached list is stale
+            if (p < n) { V.pos[node] = p; C.lines[(size_t)p * NB_WORDS] = NB_HDR_STALE; C.cnt8[p] = 1; V.o8[p] = 0; }    // a new tour: every cached list is stale
         }
-        if (t == 0) { *s_cost = 0; *s_q = 0; *C.pool_next = 0; }
-        if (threadIdx.x == 0) { s_key_[0] = KEY_EMPTY; s_key_[1] = KEY_EMPTY; }
+        if (t == 0) { *s_cost = 0; *s_q = 0; *C.pool_next = 0; *C.nbig = 0; }
+        if (threadIdx.x == 0) { s_key_[0] = KEY_EMPTY; s_key_[1] = KEY_EMPTY; s_best = -1; }
         team_sync<CL>();
         long long local = 0;
         for (int p = t; p < n; p += TEAM) {
@@ -1234,12 +1352,15 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
         // barrier and bridged by F.  The key stays per CTA and is combined by reading the peers' copies: a 64-bit atomicMin
         // is not atomic between a CTA's own shared-memory path and its peers' distributed-shared-memory path (measured,
         // scripts/cluster_probe.cu: lost updates), 64-bit atomicAdd is.
+        bool p2 = false;                                        // phase 2 runs only while uncached nodes exist (none known yet)
         for (;;) {
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
-            cached_scan<M, NE, false>(V, G, F, t, TEAM, s_q, boxes, wbuf, C, best, bestkey, ncand);
-            team_sync<CL>();
-            pruned_phase2<M, NE, false>(V, G, F, warp, WARPS * CL, *s_q, boxes, wbuf, best, bestkey, ncand, 0);
+            cached_scan<M, NE, false>(V, G, F, warp, WARPS * CL, p2, s_q, boxes, wbuf, C, s_ring[threadIdx.x >> 5], &s_best, best, bestkey, ncand);
+            if (p2) {
+                team_sync<CL>();
+                pruned_phase2<M, NE, false>(V, G, F, warp, WARPS * CL, *s_q, boxes, wbuf, best, bestkey, ncand, 0);
+            }
             bestkey = warp_min_key(bestkey);
             if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key_[par], bestkey);
             team_sync<CL>();
@@ -1250,6 +1371,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
                 for (int r = 0; r < CL; ++r) kbest = min(kbest, *cluster.map_shared_rank(&s_key_[par], r));
             }
             if (kbest == KEY_EMPTY) break;                      // local optimum (refinment.c:27)
+            p2 = *(volatile int *)C.nbig > 0;                   // between the last two barriers: nobody changes it here
             const int a = key_a(kbest), b = key_b(kbest);
             int seg_s, seg_e;
             apply_move<M>(V, a, b, t, TEAM, false, seg_s, seg_e);
@@ -1258,7 +1380,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
                 *s_q = 0;
                 if (stop != nullptr) *s_stop = *(volatile const int *)stop;
             }
-            if (threadIdx.x == 0) s_key_[par ^ 1] = KEY_EMPTY;
+            if (threadIdx.x == 0) { s_key_[par ^ 1] = KEY_EMPTY; s_best = -1; }
             ++moves;
             par ^= 1;
             team_sync<CL>();
