@@ -222,9 +222,11 @@ __device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k)
 // reads pos[a], pos[b] on entry, so those two entries must stay stable until all threads have
 // passed that read.  The caller writes them after its next barrier: pos[b] = s_out, and
 // pos[tid[e_out]] = e_out (tid[e_out] is succ_a after the reversal).
+// ep (delta cache only, V.o8 != NULL): the epoch of this move; the o8 bytes of the four nodes whose tour edges change
+// (a, succ a, b, succ b) are stamped with it in bits 1..7 (pruned.cuh).
 template <class M>
 __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int t, int nthreads, bool has_dns,
-                                           int &s_out, int &e_out) {
+                                           int &s_out, int &e_out, int ep = 0) {
     const int n = V.n;
     const int i = V.pos[a], j = V.pos[b];
     const int s = (i + 1 == n) ? 0 : i + 1;           // position of succ(a)
@@ -253,7 +255,17 @@ __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int 
         if (k != 0) { V.pos[tq] = p; V.pos[tp] = q; }   // k == 0: the end nodes, deferred (see above)
         if (p == 0) { V.pxy[n] = xq; V.tid[n] = tq; }
         if (q == 0) { V.pxy[n] = xp; V.tid[n] = tp; }
-        if (V.o8) { V.o8[tq] ^= 1; V.o8[tp] ^= 1; }     // one owner per node: plain byte updates
+        if (V.o8) {                                     // one owner per node: plain byte updates
+            if (k == 0) {                               // the segment ends: succ a and b
+                V.o8[tq] = (unsigned char)(((V.o8[tq] ^ 1) & 1) | (ep << 1));
+                V.o8[tp] = (unsigned char)(((V.o8[tp] ^ 1) & 1) | (ep << 1));
+            } else { V.o8[tq] ^= 1; V.o8[tp] ^= 1; }
+        }
+    }
+    if (V.o8 && t == 0) {                               // a and succ b keep their direction
+        const int sb = V.tid[e + 1];
+        V.o8[a] = (unsigned char)((V.o8[a] & 1) | (ep << 1));
+        V.o8[sb] = (unsigned char)((V.o8[sb] & 1) | (ep << 1));
     }
     if (V.o8 && (L & 1) && t == 0) {                    // the middle node of an odd segment stays in place but turns round too
         int m = s + half; if (m >= n) m -= n;

@@ -480,79 +480,86 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
 //     cost(u,w) + cost(x,z) - cost(u,x) - cost(w,z),  ...
 // depends on the identities of x, y, z, z' only.  A 2-opt move changes the tour edges of exactly FOUR nodes (a, succ a,
 // b, succ b); every node strictly inside the reversed segment keeps both edges and merely swaps successor and
-// predecessor.  So the cache keeps, per node u, the list of its records as {w, d0, d1}:
-//     d[r] = the smaller of the two deltas that are valid 2-opt moves when  o8[u] ^ o8[w] == r,
-// where o8[] is one orientation bit per node that apply_move flips for every node of a reversed segment (kernels.cuh).
-// A scan then is a STREAM over the node lines: load the record, look up one byte o8[w], select d0 or d1, compare with
-// the running best.  No position, coordinate or edge-cost gather, and no arithmetic, for a record that cannot win.
+// predecessor.  So the cache keeps every record as {w, d0, d1}:
+//     d[r] = the smaller of the two deltas that are valid 2-opt moves when  (o8[u] ^ o8[w]) & 1 == r,
+// where bit 0 of o8[] is an orientation bit per node that apply_move flips for every node of a reversed segment
+// (kernels.cuh).  A scan then is a STREAM over the records: load one, look up the byte o8[w], select d0 or d1, compare
+// with the running best.  No position, coordinate or edge-cost gather, and no arithmetic, for a record that cannot win.
 // Only records at or below the running best are re-evaluated exactly from the position arrays (pairs_eval: both
 // deltas, adjacency test, packed keys), so the argmin -- ties included -- is taken over exact keys as before; the
 // record set is the one the searches produce, which contains every pair with delta < 0 (header of this file).
 // What is recomputed after a move:
-//   * the lists of the four nodes whose edges changed: one warp-wide search each (F carries them in registers);
-//   * records (u,w) in OTHER lists whose w is one of those four (w's neighbours changed): found while streaming
-//     (four compares per record) and recomputed in place by the lane that meets them; a record whose d0 is NB_DIRTY
-//     is treated the same way (marked from the host side after a VNS kick);
-//   * nothing else.  pla85900: a scan reads 64 bytes per node instead of evaluating 2.5e5 candidates with three
-//     dependent gathers each.
-// Layout: one 64-byte line per node = header word + NB_CAP records of three words; header = count (10 bits, NB_CF_BIG /
-// NB_CF_STALE as specials) | (pool slot + 1) << 10.  A list longer than NB_CAP lives in a slot of an extension pool
-// (NB_EXT records, handed out by a bump counter the first time a node needs one and kept by that node).  A node whose
-// search box holds more than NB_WALK_MAX nodes (a long tour edge: a nearest-neighbour tour has a few dozen, gone after
-// the first few percent of the moves) is not cached: its box goes to the phase-2 queue in every scan, as before.
+//   * the lists of the four nodes whose edges changed: one warp-wide search each, by four designated warps;
+//   * records (u,w) in OTHER lists whose w is one of those four (w's neighbours changed): apply_move stamps the four
+//     nodes' o8 bytes (bits 1..7) with the move's epoch, the scan compares the byte it loads anyway with the current
+//     epoch and recomputes such a record in place (a stamp that is 126 moves old may alias: a needless but harmless
+//     recomputation); a record whose d0 is NB_DIRTY is treated the same way (marked from the host after a VNS kick);
+//   * nothing else.
+// Layout.  Most nodes have few records -- on a nearest-neighbour tour of pla85900 nine nodes in ten have none, a few
+// hundred nodes with a long tour edge have thousands.  So: one 64-byte LINE per node = header word + NB_CAP records of
+// three words, and one count byte per node (cnt8) that says whether the line has to be looked at at all; a list longer
+// than NB_CAP lives as a contiguous run of {u, w, d0, d1} records in a HEAP (bump allocation; a rebuilt list abandons
+// its old run after overwriting the u fields with -1), which the scan streams linearly, evenly split over all
+// cooperating threads whatever the list sizes -- no queue, no second phase, no barrier.  When the heap is three
+// quarters full the whole cache is declared stale and the heap reset (between two barriers); a list that finds no
+// room stays stale and is searched again in every scan: slower, still exact.
 constexpr int NB_WORDS = 16;                   // ints per node line
 constexpr int NB_CAP = 5;                      // records held in the line itself
-#ifndef TSP_NB_EXT
-#define TSP_NB_EXT 256
-#endif
-constexpr int NB_EXT = TSP_NB_EXT;             // records per pool slot
-constexpr int NB_WALK_MAX = 512;               // largest search box (in nodes) a warp walks itself
-constexpr int NB_CF_STALE = 1023, NB_CF_BIG = 1022;
-constexpr int NB_HDR_STALE = NB_CF_STALE;      // stale, no pool slot
+constexpr int NB_CF_STALE = 1023, NB_CF_HEAP = 1022;          // header: never searched / list in the heap (words 1, 2: start, count)
+constexpr int NB_HDR_STALE = NB_CF_STALE;
 constexpr int NB_DIRTY = (int)0x80000000;      // d0 of a record that must be recomputed before use
+constexpr int NB_EPOCHS = 126;                 // epochs 0..125 cycle; 126: "no move yet"; 127: a node no move has touched
+constexpr int NB_EP_NONE = 126, NB_EP_INIT = 127;
 
 struct NbCache {
     int *lines;             // [n][NB_WORDS]
-    int *pool;              // [slots][NB_EXT * 3]
-    int *pool_next;         // bump counter of the pool
-    unsigned char *cnt8;    // [n] non-zero: the node's line must be looked at (records, stale, uncached); zero: nothing there
-    int *nbig;              // number of uncached (NB_CF_BIG) nodes: phase 2 and its barrier run only while there are any
-    int slots;
+    int4 *heap;             // [heap_cap] records {u, w, d0, d1}; u < 0: abandoned
+    int *heap_next;         // [0], [1]: bump counters of the heap, [2]: which of the two is in use (they swap at a reset), [3]: live records
+    unsigned char *cnt8;    // [n] non-zero: the node's line must be looked at (records, stale); zero: nothing there
+    int heap_cap;
 };
-__host__ __device__ inline int nb_pool_slots(int n) { return n / 6 + 64; }
+__host__ __device__ inline int nb_heap_cap(int n) { return (int)min((long long)24 * n + 4096, (long long)0x3FFFFFF0); }
 
 __global__ void nb_invalidate_kernel(NbCache C, unsigned char *o8, int n) {
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
         C.lines[(size_t)u * NB_WORDS] = NB_HDR_STALE;
         C.cnt8[u] = 1;
-        o8[u] = 0;
+        o8[u] = NB_EP_INIT << 1;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { *C.pool_next = 0; *C.nbig = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { C.heap_next[0] = 0; C.heap_next[1] = 0; C.heap_next[2] = 0; C.heap_next[3] = 0; }
 }
 // after the tour was changed from outside WITHOUT any reversal (a VNS kick exchanges blocks): the listed nodes got new
-// neighbours.  Their own lists are marked stale (first kernel, which also raises flag[]), every record pointing at one
-// of them is marked dirty (second kernel), the flags are lowered again (third).
+// neighbours.  Their own lists are marked stale (first kernel, which also raises flag[] and abandons their heap runs),
+// every record pointing at one of them is marked dirty (second kernel), the flags are lowered again (third).
 __global__ void nb_mark_nodes_kernel(NbCache C, const int *nodes, int count, unsigned char *flag, int raise) {
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < count; k += gridDim.x * blockDim.x) {
         const int u = nodes[k];
         flag[u] = (unsigned char)raise;
         if (raise) {
             int *h = C.lines + (size_t)u * NB_WORDS;
-            if ((*h & 0x3FF) == NB_CF_BIG) atomicSub(C.nbig, 1);
-            *h = (*h & ~0x3FF) | NB_CF_STALE;
+            if ((h[0] & 0x3FF) == NB_CF_HEAP) {
+                for (int j = 0; j < h[2]; ++j) C.heap[h[1] + j].x = -1;
+                atomicSub(C.heap_next + 3, h[2]);
+            }
+            h[0] = NB_HDR_STALE;
             C.cnt8[u] = 1;
         }
     }
 }
 __global__ void nb_mark_records_kernel(NbCache C, const unsigned char *flag, int n) {
-    for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
+    const int stride = gridDim.x * blockDim.x, t = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int u = t; u < n; u += stride) {
         if (!C.cnt8[u]) continue;
         int *line = C.lines + (size_t)u * NB_WORDS;
-        const int hdr = line[0], cf = hdr & 0x3FF, ext = (hdr >> 10) - 1;
-        if (cf >= NB_CF_BIG) continue;
-        int *rec = cf <= NB_CAP ? line + 1 : C.pool + (size_t)ext * NB_EXT * 3;
+        const int cf = line[0] & 0x3FF;
+        if (cf > NB_CAP) continue;
         for (int j = 0; j < cf; ++j)
-            if (flag[rec[3 * j]]) rec[3 * j + 1] = NB_DIRTY;
+            if (flag[line[1 + 3 * j]]) line[2 + 3 * j] = NB_DIRTY;
+    }
+    const int hn = min(C.heap_next[C.heap_next[2]], C.heap_cap);
+    for (int k = t; k < hn; k += stride) {
+        const int4 r = C.heap[k];
+        if (r.x >= 0 && flag[r.y]) C.heap[k].z = NB_DIRTY;
     }
 }
 
@@ -594,15 +601,11 @@ __device__ __forceinline__ void record_deltas(const TourView &V, const PosPatch 
     dflip = min(dsp, dps);
 }
 
-// The streaming loop itself contains no call and no gather other than o8[w].  A warp owns a contiguous range of nodes:
-// it reads their count bytes (cnt8, 32 at a time), compacts the ids of the nodes that have anything to look at into a small
-// ring in shared memory and works through them 32 per step, every lane a node with a non-empty line -- on pla85900 nine
-// nodes in ten have no candidate at all and cost one byte per scan.  The running best is shared: reduced over the warp
-// after every step and exchanged between the warps of a CTA through one shared-memory word, so only records that tie
-// or beat the best found so far ANYWHERE in the CTA are evaluated exactly; those go straight to the evaluation half of
-// the warp's record buffer as node-id records.  Whatever needs the position arrays -- a dirty record, a node whose list
-// is stale, long or uncached -- is appended to the ATTENTION half and dealt with by one separate (noinline) function
-// after the loop, or when the buffer runs full.
+// The streaming loops contain no call and no gather other than o8[]: whatever needs the position arrays -- a dirty
+// record, a stale node -- is appended to a warp-private ATTENTION buffer (the first half of the warp's record buffer) and
+// dealt with by one separate (noinline) function after the loops, or when the buffer runs full.  Records that tie or
+// beat the running best go to the second half as node-id records for the exact evaluation.  The running best is shared:
+// reduced over the warp after every step and exchanged between the warps of a CTA through one shared-memory word.
 constexpr int AB_CAP = PR_WBUF / 2;            // attention entries per warp
 constexpr int EB_CAP = PR_WBUF - AB_CAP;       // evaluation records per warp
 constexpr unsigned AT_DIRTY = 1, AT_NODE = 2;
@@ -636,20 +639,12 @@ __device__ __noinline__ ScanAcc flush_records(TourView V, PosPatch F, uint4 *ebu
 
 // append the warp's records (hit lanes) to the evaluation half, evaluating it first when it is nearly full
 template <class M, int NE>
-__device__ __forceinline__ void eval_push(const TourView &V, const PosPatch &F, uint4 *ebuf, ScanAcc &a, bool hit, int p, int w, int K, unsigned type) {
+__device__ __forceinline__ void eval_push(const TourView &V, const PosPatch &F, uint4 *ebuf, ScanAcc &a, bool hit, int p, int w, int K) {
     const unsigned mask = __ballot_sync(FULL, hit);
     if (mask == 0) return;                                         // warp-uniform
     if (a.ecount > EB_CAP - 32) a = flush_records<M, NE>(V, F, ebuf, a);
-    if (hit) ebuf[a.ecount + __popc(mask & ((1u << (threadIdx.x & 31)) - 1))] = make_uint4((unsigned)p, (unsigned)w, (unsigned)K, type);
+    if (hit) ebuf[a.ecount + __popc(mask & ((1u << (threadIdx.x & 31)) - 1))] = make_uint4((unsigned)p, (unsigned)w, (unsigned)K, 3u);
     a.ecount += __popc(mask);
-}
-
-__device__ __forceinline__ void enqueue_box(unsigned long long *qctr, BigBox *boxes, int p, int cy0, int cx0, int cx1, int nrows) {
-    const unsigned long long old = atomicAdd(qctr, (1ull << 40) | (unsigned long long)nrows);
-    BigBox bx;
-    bx.p = p; bx.cy0 = cy0; bx.cx0 = cx0; bx.cx1 = cx1; bx.nrows = nrows; bx.pad = 0;
-    bx.base = (long long)(old & PR_UNIT_MASK);
-    boxes[old >> 40] = bx;
 }
 
 template <class M>
@@ -664,143 +659,107 @@ __device__ __forceinline__ bool node_box(const SpatialGrid &G, const NodeCtx &c,
     return true;
 }
 
-// an uncached node while phase 2 is not running: its box is walked here, by this warp alone (the searches' own rule:
-// cost(u,w) below dn[p] -> pair {p, pos w}, below dn[p-1] -> pair {p-1, pos w - 1}; everything else is pairs_eval's)
-template <class M, int NE>
-__device__ __forceinline__ void walk_box(const TourView &V, const SpatialGrid &G, const PosPatch &F, const NodeCtx &c, int cx0, int cx1,
-                                         int cy0, int cy1, uint4 *ebuf, ScanAcc &a) {
-    const int lane = threadIdx.x & 31;
-    for (int cy = cy0; cy <= cy1; ++cy) {
-        const int lo = G.cell_start[cy * G.W + cx0], hi = G.cell_start[cy * G.W + cx1 + 1];
-        if (lane == 0) a.ncand += hi - lo;
-        for (int k0 = lo; k0 < hi; k0 += 32) {
-            const int k = min(k0 + lane, hi - 1);
-            const double2 cw = G.cxy[k];
-            const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
-            const unsigned type = k0 + lane < hi ? ((K < c.dnp ? 1u : 0u) | (K < c.dnm ? 2u : 0u)) : 0u;
-            eval_push<M, NE>(V, F, ebuf, a, type != 0, c.p, G.cnode[k], K, type);
-        }
-    }
-}
-
 // Warp-wide search around node u: rewrites u's list and hands the records that can win NOW to the exact evaluation.
-// SETTLE: only bring the cache up to date (no candidates, no queue): used when a launch ends right after a move.
-// p2: phase 2 runs in this scan (uncached nodes existed when the scan began): a box too large to cache is queued for it,
-// otherwise walked on the spot.
+// Two passes over the search box: the first counts the records (costs only), so that a long list gets a heap run of
+// its size class; the second computes the deltas and writes.  A node keeps its run while its list fits the run's
+// capacity (header words 1..3: start, count, capacity), so the many nodes that are searched again and again with lists of
+// six to a few dozen records do not leave dead records behind.
+// SETTLE: only bring the cache up to date (no candidates): used when a launch ends right after a move.
 template <class M, int NE, bool SETTLE>
-__device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGrid &G, const PosPatch &F, const NbCache &C, int u, int hdr,
-                                             bool p2, unsigned long long *qctr, BigBox *boxes, uint4 *ebuf, ScanAcc &a) {
+__device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGrid &G, const PosPatch &F, const NbCache &C, int hp, int u,
+                                             uint4 *ebuf, ScanAcc &a) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
     int *line = C.lines + (size_t)u * NB_WORDS;
-    int ext = (hdr >> 10) - 1;
-    const bool was_big = (hdr & 0x3FF) == NB_CF_BIG;
+    const int h0 = line[0], ostart = line[1], ocount = line[2], ocap = line[3];
+    const bool had = (h0 & 0x3FF) == NB_CF_HEAP;
+    __syncwarp();                                                  // every lane has the old header before lane 0 rewrites it
     NodeCtx c;
     node_ctx(V, F, u, c);
-    int cx0, cx1, cy0, cy1;
-    if (!node_box<M>(G, c, cx0, cx1, cy0, cy1)) {
-        if (lane == 0) { line[0] = (ext + 1) << 10; C.cnt8[u] = 0; if (was_big) atomicSub(C.nbig, 1); }
-        return;
+    int cx0 = 0, cx1 = 0, cy0 = 0, cy1 = -1;
+    const bool any = node_box<M>(G, c, cx0, cx1, cy0, cy1);
+    const int nrows = any ? cy1 - cy0 + 1 : 0;
+    const int thr = max(c.dnp, c.dnm);
+    int count = 0, tot = 0;
+    for (int r = 0; r < nrows; ++r) {
+        const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
+        tot += hi - lo;
+        for (int k0 = lo; k0 < hi; k0 += 32) {
+            const int k = min(k0 + lane, hi - 1);
+            const double2 cw = G.cxy[k];
+            const int w = G.cnode[k];
+            const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
+            const bool pass = k0 + lane < hi && K < thr && w != u && w != c.su && w != c.pu;          // tour neighbours: refinment.c:55
+            count += __popc(__ballot_sync(FULL, pass));
+        }
     }
-    const int nrows = cy1 - cy0 + 1;
-    int tot = 0;
-    for (int r = lane; r < nrows; r += 32) tot += G.cell_start[(cy0 + r) * G.W + cx1 + 1] - G.cell_start[(cy0 + r) * G.W + cx0];
-    tot = __reduce_add_sync(FULL, tot);
-    if (lane == 0) { NBSTAT(0, 1); NBSTAT(7, tot); }
-    bool big = tot > NB_WALK_MAX;                                  // a long tour edge: not cached
-    int stored = 0;
-    if (!big) {
-        int *pool = ext >= 0 ? C.pool + (size_t)ext * NB_EXT * 3 : nullptr;
-        bool asked = ext >= 0;
-        const int ou = V.o8[u];
-        const int thr = max(c.dnp, c.dnm);
-        if (lane == 0) a.ncand += tot;
-        for (int r = 0; r < nrows; ++r) {
-            const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
-            for (int k0 = lo; k0 < hi; k0 += 32) {
-                const int k = min(k0 + lane, hi - 1);
-                const double2 cw = G.cxy[k];
-                const int w = G.cnode[k];
-                const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
-                const bool pass = k0 + lane < hi && K < thr && w != u && w != c.su && w != c.pu;      // tour neighbours: refinment.c:55
-                int dsame = 0, dflip = 0;
-                if (pass) record_deltas<M>(V, F, c, w, K, dsame, dflip);
-                const unsigned mask = __ballot_sync(FULL, pass);
-                if (!asked && stored + __popc(mask) > NB_CAP) {    // the list outgrows the line: the node gets a pool slot, for good
-                    asked = true;
-                    if (lane == 0) {
-                        ext = atomicAdd(C.pool_next, 1);
-                        if (ext >= C.slots) ext = -1;              // pool dry
-                    }
-                    ext = __shfl_sync(FULL, ext, 0);
-                    if (ext >= 0) {
-                        pool = C.pool + (size_t)ext * NB_EXT * 3;
-                        __syncwarp();                              // the records written to the line so far, by other lanes
-                        if (lane < 3 * stored) pool[lane] = line[1 + lane];
-                    }
-                }
-                if (pass) {
-                    const int o = stored + __popc(mask & lt);
-                    const bool rel = ((ou ^ V.o8[w]) & 1) != 0;
-                    const int d0 = rel ? dflip : dsame, d1 = rel ? dsame : dflip;
-                    if (o < NB_CAP) { line[1 + 3 * o] = w; line[2 + 3 * o] = d0; line[3 + 3 * o] = d1; }
-                    if (pool && o < NB_EXT) { pool[3 * o] = w; pool[3 * o + 1] = d0; pool[3 * o + 2] = d1; }
-                }
-                stored += __popc(mask);
-                if (!SETTLE) {
-                    const bool hit = pass && dsame <= a.best;
-                    if (hit) a.best = dsame;
-                    eval_push<M, NE>(V, F, ebuf, a, hit, c.p, w, K, 3u);
-                }
+    if (lane == 0) { NBSTAT(0, 1); NBSTAT(7, tot); a.ncand += tot; }
+    int start = -1, cap = 0;
+    if (count > NB_CAP) {
+        if (had && count <= ocap) { start = ostart; cap = ocap; }  // the node's own run, again
+        else {
+            cap = count <= 16 ? 16 : count <= 64 ? 64 : count + (count >> 2);
+            if (lane == 0)                                         // a counter beyond the capacity stays where it is (no overflow)
+                start = *(volatile int *)(C.heap_next + hp) > C.heap_cap ? -1 : atomicAdd(C.heap_next + hp, cap);
+            start = __shfl_sync(FULL, start, 0);
+            if (start < 0 || start > C.heap_cap - cap) {           // no room: the node stays stale; what the run covers is void
+                if (start >= 0)
+                    for (int j = start + lane; j < C.heap_cap; j += 32) C.heap[j].x = -1;
+                start = -1;
             }
         }
-        // a list that fits neither the line nor a pool slot is not cached either.  Its candidates of THIS scan were all
-        // handed over above (every record at or below the lane's best), so nothing is walked or queued now.
-        if (stored > (ext >= 0 ? NB_EXT : NB_CAP)) {
-            if (lane == 0) { line[0] = ((ext + 1) << 10) | NB_CF_BIG; C.cnt8[u] = 1; if (!was_big) atomicAdd(C.nbig, 1); NBSTAT(1, 1); }
-            return;
-        }
-        if (lane == 0) { line[0] = ((ext + 1) << 10) | stored; C.cnt8[u] = stored > 0; if (was_big) atomicSub(C.nbig, 1); }
+    }
+    if (had && start != ostart)                                    // the old run is abandoned
+        for (int j = lane; j < ocount; j += 32) C.heap[ostart + j].x = -1;
+    if (lane == 0 && (had || start >= 0)) atomicAdd(C.heap_next + 3, (start >= 0 ? count : 0) - (had ? ocount : 0));       // live records
+    if (count == 0) {
+        if (lane == 0) { line[0] = 0; C.cnt8[u] = 0; }
         return;
     }
-    if (lane == 0) { line[0] = ((ext + 1) << 10) | NB_CF_BIG; C.cnt8[u] = 1; if (!was_big) atomicAdd(C.nbig, 1); NBSTAT(1, 1); }
-    if (!SETTLE) {
-        if (p2) { if (lane == 0) enqueue_box(qctr, boxes, c.p, cy0, cx0, cx1, nrows); }
-        else walk_box<M, NE>(V, G, F, c, cx0, cx1, cy0, cy1, ebuf, a);
-    }
-}
-
-// one cached record of node u that needs the position arrays: dirty -> recomputed and written back; at or below the
-// lane's best -> to the exact evaluation
-template <class M, int NE, bool SETTLE>
-__device__ __forceinline__ void record_attend(const TourView &V, const PosPatch &F, uint4 *ebuf, ScanAcc &a, bool live, bool dirty,
-                                              int u, int w, int *rec) {
-    bool hit = live && !dirty;
-    int p = 0, K = 0;
-    if (live) {
-        NBSTAT(dirty ? 3 : 4, 1);
-        NodeCtx c;
-        node_ctx(V, F, u, c);
-        p = c.p;
-        const double2 wxy = V.pxy[pos_of(V, F, w)];
-        K = M::K(c.u.x, c.u.y, wxy.x, wxy.y);
-        if (dirty) {
-            int dsame, dflip;
-            record_deltas<M>(V, F, c, w, K, dsame, dflip);
-            const bool rel = ((V.o8[u] ^ V.o8[w]) & 1) != 0;
-            rec[1] = rel ? dflip : dsame;
-            rec[2] = rel ? dsame : dflip;
-            hit = dsame <= a.best;
-            if (hit) a.best = dsame;
+    const int ou = V.o8[u];
+    int stored = 0;
+    for (int r = 0; r < nrows; ++r) {
+        const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
+        for (int k0 = lo; k0 < hi; k0 += 32) {
+            const int k = min(k0 + lane, hi - 1);
+            const double2 cw = G.cxy[k];
+            const int w = G.cnode[k];
+            const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
+            const bool pass = k0 + lane < hi && K < thr && w != u && w != c.su && w != c.pu;
+            const unsigned mask = __ballot_sync(FULL, pass);
+            if (mask == 0) continue;                               // warp-uniform
+            int dsame = 0, dflip = 0;
+            if (pass) {
+                record_deltas<M>(V, F, c, w, K, dsame, dflip);
+                const int o = stored + __popc(mask & lt);
+                const bool rel = ((ou ^ V.o8[w]) & 1) != 0;
+                const int d0 = rel ? dflip : dsame, d1 = rel ? dsame : dflip;
+                if (count <= NB_CAP) { line[1 + 3 * o] = w; line[2 + 3 * o] = d0; line[3 + 3 * o] = d1; }
+                else if (start >= 0) C.heap[start + o] = make_int4(u, w, d0, d1);
+            }
+            stored += __popc(mask);
+            if (!SETTLE) {
+                const bool hit = pass && dsame <= a.best;
+                if (hit) a.best = dsame;
+                eval_push<M, NE>(V, F, ebuf, a, hit, c.p, w, K);
+            }
         }
     }
-    if (!SETTLE) eval_push<M, NE>(V, F, ebuf, a, hit, p, w, K, 3u);
+    if (start >= 0) {                                              // the rest of the run: what an earlier, longer list left there, or nothing yet
+        const int end = start == ostart && had ? max(ocount, count) : cap;
+        for (int j = start + count + lane; j < start + end; j += 32) C.heap[j].x = -1;
+    }
+    if (lane == 0) {
+        if (count <= NB_CAP) { line[0] = count; C.cnt8[u] = 1; }
+        else if (start >= 0) { line[0] = NB_CF_HEAP; line[1] = start; line[2] = count; line[3] = cap; C.cnt8[u] = 0; }
+        else { line[0] = NB_HDR_STALE; C.cnt8[u] = 1; NBSTAT(1, 1); }
+    }
 }
 
-// the attention entries of a warp: records {u, w, record address | AT_DIRTY} and nodes {u, header, AT_NODE}
+// the attention entries of a warp: dirty records {u, w, address of the record's w field | AT_DIRTY} -- recomputed in
+// place, every lane its own -- and stale nodes {u, -, AT_NODE}: searched again, one at a time, by the whole warp
 template <class M, int NE, bool SETTLE>
-__device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPatch F, NbCache C, bool p2, unsigned long long *qctr,
-                                       BigBox *boxes, uint4 *abuf, int acount, ScanAcc a) {
+__device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPatch F, NbCache C, int hp, uint4 *abuf, int acount, ScanAcc a) {
     const SpatialGrid &G = *Gp;
     const int lane = threadIdx.x & 31;
     uint4 *ebuf = abuf + AB_CAP;
@@ -811,58 +770,50 @@ __device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPat
         uint4 e = make_uint4(0, 0, 0, 0);
         if (have) e = abuf[base + lane];
         const unsigned kind = e.z & 3u;
-        int *rec = reinterpret_cast<int *>(((unsigned long long)e.w << 32) | (unsigned long long)(e.z & ~3u));
-        // dirty records: every lane its own
         const bool isrec = have && kind == AT_DIRTY;
-        if (__any_sync(FULL, isrec)) record_attend<M, NE, SETTLE>(V, F, ebuf, a, isrec, true, (int)e.x, (int)e.y, rec);
-        // nodes: one at a time, the whole warp
+        if (__any_sync(FULL, isrec)) {
+            bool hit = false;
+            int p = 0, K = 0;
+            const int u = (int)e.x, w = (int)e.y;
+            if (isrec) {
+                NBSTAT(3, 1);
+                int *rec = reinterpret_cast<int *>(((unsigned long long)e.w << 32) | (unsigned long long)(e.z & ~3u));
+                NodeCtx c;
+                node_ctx(V, F, u, c);
+                p = c.p;
+                const double2 wxy = V.pxy[pos_of(V, F, w)];
+                K = M::K(c.u.x, c.u.y, wxy.x, wxy.y);
+                int dsame, dflip;
+                record_deltas<M>(V, F, c, w, K, dsame, dflip);
+                const bool rel = ((V.o8[u] ^ V.o8[w]) & 1) != 0;
+                rec[1] = rel ? dflip : dsame;
+                rec[2] = rel ? dsame : dflip;
+                hit = dsame <= a.best;
+                if (hit) a.best = dsame;
+            }
+            if (!SETTLE) eval_push<M, NE>(V, F, ebuf, a, hit, p, w, K);
+        }
         unsigned nm = __ballot_sync(FULL, have && kind == AT_NODE);
         while (nm) {
             const int src = __ffs(nm) - 1;
             nm &= nm - 1;
-            const int u = (int)__shfl_sync(FULL, e.x, src), hdr = (int)__shfl_sync(FULL, e.y, src);
-            const int cf = hdr & 0x3FF, ext = (hdr >> 10) - 1;
-            if (cf == NB_CF_STALE || in_patch(F, u)) {             // the four of the last move, or never searched
-                rebuild_list<M, NE, SETTLE>(V, G, F, C, u, hdr, p2, qctr, boxes, ebuf, a);
-            } else if (cf == NB_CF_BIG) {                          // uncached (long tour edge): phase 2 runs, the box goes there
-                if (!SETTLE && lane == 0) {
-                    NBSTAT(1, 1);
-                    NodeCtx c;
-                    node_ctx(V, F, u, c);
-                    int cx0, cx1, cy0, cy1;
-                    if (node_box<M>(G, c, cx0, cx1, cy0, cy1)) enqueue_box(qctr, boxes, c.p, cy0, cx0, cx1, cy1 - cy0 + 1);
-                }
-            } else {                                               // a long list: all lanes striding over the node's pool slot
-                int *sl = C.pool + (size_t)ext * NB_EXT * 3;
-                const int ou = V.o8[u];
-                if (lane == 0) { a.ncand += cf; NBSTAT(2, 1); }
-                for (int j0 = 0; j0 < cf; j0 += 32) {
-                    const int j = j0 + lane;
-                    bool live = j < cf, dirty = false;
-                    int w = 0;
-                    if (live) {
-                        w = sl[3 * j];
-                        const int d0 = sl[3 * j + 1], d1 = sl[3 * j + 2];
-                        dirty = d0 == NB_DIRTY || in_patch(F, w);
-                        const int d = ((ou ^ V.o8[w]) & 1) ? d1 : d0;
-                        if (!dirty) { live = !SETTLE && d <= a.best; if (live) a.best = d; }
-                    }
-                    if (__any_sync(FULL, live)) record_attend<M, NE, SETTLE>(V, F, ebuf, a, live, dirty, u, w, sl + 3 * j);
-                }
-            }
+            rebuild_list<M, NE, SETTLE>(V, G, F, C, hp, (int)__shfl_sync(FULL, e.x, src), ebuf, a);
         }
     }
     __syncwarp();
     return a;
 }
 
-// The cached scan: warp `gw` of `nwarps` cooperating warps (a grid, a cluster or one CTA) takes a contiguous range of
-// NODES.  ring: NB_RING ints of shared memory private to the warp; s_best: the CTA's shared running best (armed to -1
-// by the caller behind a barrier); p2: phase 2 runs after this scan (uniform over the team).
+// The cached scan: warp `gw` of `nwarps` cooperating warps (a grid, a cluster or one CTA).
+//   ep     epoch of the last move (NB_EP_NONE: none): nodes whose o8 byte carries it had their neighbours changed
+//   hsnap  number of heap records to stream (the heap counter as it stood between the barriers before this scan)
+//   hp     which of the two heap counters is in use
+//   ring   NB_RING ints of shared memory private to the warp
+//   s_best the CTA's shared running best (armed to -1 by the caller behind a barrier)
 template <class M, int NE, bool SETTLE>
-__device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid &G, const PosPatch &F, int gw, int nwarps, bool p2,
-                                            unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, const NbCache &C, int *ring, int *s_best,
-                                            int &best, unsigned long long &bestkey, long long &ncand) {
+__device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid &G, const PosPatch &F, int ep, int gw, int nwarps, int hsnap,
+                                            int hp, uint4 *wbuf, const NbCache &C, int *ring, int *s_best, int &best,
+                                            unsigned long long &bestkey, long long &ncand) {
     ScanAcc a;
     a.bestkey = bestkey; a.ncand = ncand; a.best = best; a.ecount = 0;
     int acount = 0;
@@ -874,17 +825,53 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
     if (gw < 4) {
         const int fu = gw == 0 ? F.node0 : gw == 1 ? F.node1 : gw == 2 ? F.node2 : F.node3;
         if (fu >= 0) {
-            if (lane == 0) wbuf[0] = make_uint4((unsigned)fu, (unsigned)C.lines[(size_t)fu * NB_WORDS], AT_NODE, 0u);
+            if (lane == 0) wbuf[0] = make_uint4((unsigned)fu, 0u, AT_NODE, 0u);
             acount = 1;
         }
     }
+    // ---- the heap: every cooperating thread a strided share of the records
+    for (int k0 = gw * 32; k0 < hsnap; k0 += nwarps * 32) {
+        if (acount > AB_CAP - 32) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, wbuf, acount, a); acount = 0; }      // warp-uniform, rare
+        if (!SETTLE && a.ecount > EB_CAP - 32) a = flush_records<M, NE>(V, F, ebuf, a);
+        const int k = k0 + lane;
+        int4 r = make_int4(-1, 0, 0, 0);
+        if (k < hsnap) r = C.heap[k];
+        bool live = r.x >= 0, dirty = false;
+        int d = 0x7FFFFFFF;
+        if (live) {
+            const int ou = V.o8[r.x], ow = V.o8[r.y];
+            if ((ou >> 1) == ep && in_patch(F, r.x)) live = false; // u's own list is being rebuilt by a designated warp
+            else if (r.z == NB_DIRTY || (ow >> 1) == ep) dirty = true;
+            else d = ((ou ^ ow) & 1) ? r.w : r.z;
+        }
+        a.ncand += live ? 1 : 0;
+        {
+            const unsigned m = __ballot_sync(FULL, dirty);
+            if (dirty) {
+                const unsigned long long ra = (unsigned long long)(&C.heap[k].y);
+                wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)r.x, (unsigned)r.y, (unsigned)(ra & 0xFFFFFFFFu) | AT_DIRTY, (unsigned)(ra >> 32));
+            }
+            acount += __popc(m);
+        }
+        if (!SETTLE) {
+            const int seen = *(volatile int *)s_best;
+            const int wm = __reduce_min_sync(FULL, min(d, min(a.best, seen)));
+            a.best = wm;
+            if (lane == 0 && wm < seen) atomicMin(s_best, wm);
+            const bool hit = d <= wm;
+            const unsigned m = __ballot_sync(FULL, hit);
+            if (hit) ebuf[a.ecount + __popc(m & lt)] = make_uint4((unsigned)r.x, (unsigned)r.y, 0u, 3u | EV_NODEIDS);
+            a.ecount += __popc(m);
+        }
+    }
+    // ---- the lines: a contiguous range of nodes per warp; count bytes first, non-empty lines 32 per step
     const int chunk = (((n + nwarps - 1) / nwarps) + 31) & ~31;
     const int lo = min(n, gw * chunk), hi = min(n, lo + chunk);
     int base = lo, head = 0, tail = 0;
     for (;;) {
         while (base < hi && tail - head < 32) {                    // refill: the next 32 count bytes
             const int u = base + lane;
-            const bool want = u < hi && C.cnt8[u] != 0 && !in_patch(F, u);
+            const bool want = u < hi && C.cnt8[u] != 0;
             const unsigned m = __ballot_sync(FULL, want);
             if (want) ring[(tail + __popc(m & lt)) & (NB_RING - 1)] = u;
             tail += __popc(m);
@@ -893,14 +880,11 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
         const int step = min(32, tail - head);
         if (step == 0) break;
         __syncwarp();
-        const bool have = lane < step;
+        bool have = lane < step;
         const int u = have ? ring[(head + lane) & (NB_RING - 1)] : 0;
         head += step;
         __syncwarp();
-        if (acount > AB_CAP - 32 * (NB_CAP + 1)) {                 // warp-uniform, rare
-            a = attend<M, NE, SETTLE>(V, &G, F, C, p2, qctr, boxes, wbuf, acount, a);
-            acount = 0;
-        }
+        if (acount > AB_CAP - 32 * (NB_CAP + 1)) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, wbuf, acount, a); acount = 0; }
         if (!SETTLE && a.ecount > EB_CAP - 32 * NB_CAP) a = flush_records<M, NE>(V, F, ebuf, a);
         int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
         int ou = 0;
@@ -909,14 +893,15 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
             const int4 *L = reinterpret_cast<const int4 *>(line);
             q0 = L[0]; q1 = L[1]; q2 = L[2]; q3 = L[3];
             ou = V.o8[u];
+            if ((ou >> 1) == ep && in_patch(F, u)) have = false;   // one of the four: a designated warp searches it
         }
         const int cf = q0.x & 0x3FF;
-        const bool node_work = have && cf > NB_CAP;                // stale, uncached or long: all of it happens in attend()
-        const int inl = (have && !node_work) ? cf : 0;
+        const bool stale = have && cf == NB_CF_STALE;
+        const int inl = (have && cf <= NB_CAP) ? cf : 0;
         a.ncand += inl;
         {
-            const unsigned m = __ballot_sync(FULL, node_work);
-            if (node_work) wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)u, (unsigned)q0.x, AT_NODE, 0u);
+            const unsigned m = __ballot_sync(FULL, stale);
+            if (stale) wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)u, 0u, AT_NODE, 0u);
             acount += __popc(m);
         }
         const int rw[NB_CAP] = {q0.y, q1.x, q1.w, q2.z, q3.y};
@@ -929,9 +914,9 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
         for (int j = 0; j < NB_CAP; ++j) {
             d[j] = 0x7FFFFFFF;
             if (j < inl) {
-                const int w = rw[j];
-                if (r0[j] == NB_DIRTY || in_patch(F, w)) dirty |= 1u << j;
-                else { d[j] = ((ou ^ V.o8[w]) & 1) ? r1[j] : r0[j]; mine = min(mine, d[j]); }
+                const int ow = V.o8[rw[j]];
+                if (r0[j] == NB_DIRTY || (ow >> 1) == ep) dirty |= 1u << j;
+                else { d[j] = ((ou ^ ow) & 1) ? r1[j] : r0[j]; mine = min(mine, d[j]); }
             }
         }
         if (__any_sync(FULL, dirty != 0)) {                        // rare
@@ -963,9 +948,21 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
             }
         }
     }
-    if (acount > 0) a = attend<M, NE, SETTLE>(V, &G, F, C, p2, qctr, boxes, wbuf, acount, a);
+    if (acount > 0) a = attend<M, NE, SETTLE>(V, &G, F, C, hp, wbuf, acount, a);
     if (!SETTLE && a.ecount > 0) a = flush_records<M, NE>(V, F, ebuf, a);
     best = a.best; bestkey = a.bestkey; ncand = a.ncand;
+}
+
+// between the last two barriers of an iteration, every cooperating thread (t of nthreads): the heap fill the next scan
+// streams -- or, when the heap is three quarters full, a clean slate: every line stale, the other (zeroed) counter
+__device__ __forceinline__ int heap_checkpoint(const NbCache &C, int n, int t, int nthreads, int &hp) {
+    const int hn = *(volatile int *)(C.heap_next + hp), live = *(volatile int *)(C.heap_next + 3);
+    // full, or mostly dead records (the giant lists of a tour's first long edges, long gone): start over
+    if (hn <= C.heap_cap / 4 * 3 && hn <= 4 * live + n) return hn;
+    for (int u = t; u < n; u += nthreads) { C.lines[(size_t)u * NB_WORDS] = NB_HDR_STALE; C.cnt8[u] = 1; }
+    hp ^= 1;
+    if (t == 0) { C.heap_next[hp] = 0; C.heap_next[2] = hp; C.heap_next[3] = 0; }      // nobody looks at these before the next barrier
+    return 0;
 }
 
 // Phase 2 (behind a barrier): the queued boxes, cut into (box, cell row) units -- one contiguous
@@ -1020,10 +1017,12 @@ __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGr
 }
 
 // ---- K7: whole-GPU persistent pruned descent (cooperative launch, one CTA per SM) ----------------
+// Two grid barriers per scan + move: scan (stream the delta cache, four searches, exact evaluation of the few records
+// that can win) -> argmin -> barrier -> move -> barrier.
 template <class M, int BLK>
 __global__ void __launch_bounds__(BLK, 1)
 descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
-                      long long max_moves, unsigned long long *qctr, BigBox *boxes, uint4 *wbuf_all, NbCache C) {
+                      long long max_moves, uint4 *wbuf_all, NbCache C, long long moves0) {
     constexpr int WARPS = BLK / 32;
     constexpr int NE = BLK > 512 ? 2 : 4;                // records in flight per lane while evaluating (64 / 128 registers)
     cg::grid_group grid = cg::this_grid();
@@ -1034,11 +1033,17 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
     const int gtid = blockIdx.x * BLK + threadIdx.x;
     const int gsize = gridDim.x * BLK;
     // consecutive global warp numbers go to different SMs: the warps that own nodes (and the four that search) spread out
-    const long long gw = (long long)warp * gridDim.x + blockIdx.x;
-    const long long Wtot = (long long)gridDim.x * WARPS;
+    const int gw = warp * gridDim.x + blockIdx.x;
+    const int Wtot = gridDim.x * WARPS;
     uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + warp) * PR_WBUF;
     PosPatch F = POSPATCH_NONE;
     bool optimum = false;
+    int ep = NB_EP_NONE;
+    // taken where nobody changes them: before the first scan of the launch (the barrier below), later between the last
+    // two barriers of an iteration
+    int hp = *(volatile int *)(C.heap_next + 2);
+    int hsnap = min(*(volatile int *)(C.heap_next + hp), C.heap_cap);
+    grid.sync();                                         // moves0: moves this cache has seen before the launch (epoch numbering)
 #ifdef TSP_PHASE_TIMING
     unsigned long long tprev = 0;
     if (gtid == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tprev));
@@ -1052,11 +1057,6 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #else
 #define PHASE_MARK(slot)
 #endif
-
-    // phase 2 (and its grid barrier) runs only while uncached nodes exist.  Every thread takes the count where nobody
-    // changes it: here, before the first scan of the launch, and between the last two barriers of an iteration.
-    bool p2 = *(volatile int *)C.nbig > 0;
-    grid.sync();
     for (long long it = 0; it < max_moves; ++it) {
         if (threadIdx.x == 0) { s_key = KEY_EMPTY; s_best = -1; }
         __syncthreads();
@@ -1066,22 +1066,13 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #ifdef TSP_PHASE_TIMING
         unsigned long long tw0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw0));
 #endif
-        cached_scan<M, NE, false>(V, G, F, (int)gw, (int)Wtot, p2, qctr, boxes, wbuf, C, s_ring[warp], &s_best, best, bestkey, ncand);
+        cached_scan<M, NE, false>(V, G, F, ep, gw, Wtot, hsnap, hp, wbuf, C, s_ring[warp], &s_best, best, bestkey, ncand);
 #ifdef TSP_PHASE_TIMING
-        {   // slowest and average warp of phase 1 (phase_ns[3] = sum over scans of the max, [4]/[5] reused below)
+        {   // slowest and average warp of the scan (phase_ns[3] = max over scans and warps)
             unsigned long long tw1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw1));
             if (lane == 0) { atomicMax((unsigned long long *)&st->phase_ns[3], tw1 - tw0); atomicAdd((unsigned long long *)&st->phase_sum, tw1 - tw0); }
         }
 #endif
-        if (p2) {
-            grid.sync();
-            PHASE_MARK(0)
-            const unsigned long long q = *(volatile unsigned long long *)qctr;
-#ifdef TSP_PHASE_TIMING
-            if (gtid == 0) { st->phase_ns[4] += (long long)(q & PR_UNIT_MASK); st->phase_ns[5] += (long long)(q >> 40); }
-#endif
-            pruned_phase2<M, NE, false>(V, G, F, gw, Wtot, q, boxes, wbuf, best, bestkey, ncand, 0);
-        }
         bestkey = warp_min_key(bestkey);
         for (int off = 16; off > 0; off >>= 1) ncand += __shfl_down_sync(FULL, ncand, off);
         if (lane == 0) {
@@ -1092,20 +1083,20 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         unsigned long long *kslot = key + (it & 1);
         if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(kslot, s_key);
         grid.sync();
-        PHASE_MARK(1)
+        PHASE_MARK(0)
         const unsigned long long kbest = *(volatile unsigned long long *)kslot;
         if (kbest == KEY_EMPTY) {
-            if (gtid == 0) { st->status = 1; *qctr = 0; }
+            if (gtid == 0) st->status = 1;
             optimum = true;
             break;
         }
-        p2 = *(volatile int *)C.nbig > 0;
+        hsnap = heap_checkpoint(C, V.n, gtid, gsize, hp);
+        ep = (int)((moves0 + it) % NB_EPOCHS);
         const int a = key_a(kbest), b = key_b(kbest), delta = key_delta(kbest);
         int seg_s, seg_e;
-        apply_move<M>(V, a, b, gtid, gsize, false, seg_s, seg_e);
+        apply_move<M>(V, a, b, gtid, gsize, false, seg_s, seg_e, ep);
         if (gtid == 0) {
             key[(it + 1) & 1] = KEY_EMPTY;
-            *qctr = 0;
             const long long lc = st->log_count;
             if (lc < log_cap) { log[lc].a = a; log[lc].b = b; log[lc].delta = delta; log[lc].reserved = 0; }
             st->log_count = lc + 1;
@@ -1125,7 +1116,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         int best = -1;
         unsigned long long bestkey = KEY_EMPTY;
         long long ncand = 0;
-        cached_scan<M, NE, true>(V, G, F, (int)gw, (int)Wtot, false, qctr, boxes, wbuf, C, s_ring[warp], nullptr, best, bestkey, ncand);
+        cached_scan<M, NE, true>(V, G, F, ep, gw, Wtot, hsnap, hp, wbuf, C, s_ring[warp], nullptr, best, bestkey, ncand);
     }
 }
 
@@ -1235,13 +1226,11 @@ struct MultiSlots {
     double2 *pxy;      // [slots][n+1]
     int *tid, *dn;     // [slots][n+1]
     int *pos;          // [slots][n]
-    BigBox *boxes;     // [slots][n]
     int *nb;           // [slots][n * NB_WORDS]  delta cache of the slot's current descent: node lines,
-    int *nb_pool;      // [slots][nb_pool_slots(n) * NB_EXT * 3]                               extension pool,
-    int *nb_next;      // [slots]                                                              its bump counter,
-    unsigned char *o8; // [slots][n]                                                           orientation bits,
-    unsigned char *cnt8; // [slots][n]                                                         count bytes,
-    int *nbig;         // [slots]                                                              number of uncached nodes
+    int4 *nb_heap;     // [slots][nb_heap_cap(n)]                                              record heap,
+    int *nb_next;      // [slots][4]                                                           its counters,
+    unsigned char *o8; // [slots][n]                                                           orientation / epoch bytes,
+    unsigned char *cnt8; // [slots][n]                                                         count bytes
     int *best_path;    // [slots][n]  successor array of the CTA's best tour
     long long *best_cost;   // [slots]
     int *best_start;        // [slots]
@@ -1252,8 +1241,8 @@ enum { MS_NOT_STARTED = 0, MS_COMPLETE = 1, MS_CUT = 2 };
 
 // CL > 1: a thread-block CLUSTER of CL CTAs (CL SMs) shares one descent -- for batches with fewer starts than SMs,
 // where one CTA per descent would leave SMs idle while every descent still takes its full single-SM time.  The
-// tour stays in the cluster's global-memory slot; the few scalars of a scan (box-queue counter, cost, current start,
-// stop flag) live in the shared memory of the cluster's first CTA and are reached by the others through distributed
+// tour stays in the cluster's global-memory slot; the few scalars of a descent (cost, current start, stop flag) live in
+// the shared memory of the cluster's first CTA and are reached by the others through distributed
 // shared memory; every barrier is a cluster barrier (barrier.cluster, release/acquire at cluster scope), which also
 // orders the team's global-memory accesses to the tour (scripts/cluster_probe.cu: no stale read without extra fences).
 template <int CL>
@@ -1274,18 +1263,16 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     constexpr int WARPS = BLK / 32;
     constexpr int NE = BLK > 512 ? 2 : 4;
     constexpr int TEAM = BLK * CL;                      // threads sharing a descent
-    __shared__ unsigned long long s_key_[2], s_q_;
+    __shared__ unsigned long long s_key_[2];
     __shared__ long long s_cost_, s_bestcost_;
     __shared__ int s_cur_, s_stop_, s_best;
     __shared__ int s_ring[WARPS][NB_RING];
     unsigned rank = 0;
-    unsigned long long *s_q = &s_q_;
     long long *s_cost = &s_cost_, *s_bestcost = &s_bestcost_;
     int *s_cur = &s_cur_, *s_stop = &s_stop_;
     if (CL > 1) {                                       // the scalars of the cluster's first CTA, through DSMEM
         cg::cluster_group cluster = cg::this_cluster();
         rank = cluster.block_rank();
-        s_q = cluster.map_shared_rank(&s_q_, 0);
         s_cost = cluster.map_shared_rank(&s_cost_, 0); s_bestcost = cluster.map_shared_rank(&s_bestcost_, 0);
         s_cur = cluster.map_shared_rank(&s_cur_, 0); s_stop = cluster.map_shared_rank(&s_stop_, 0);
     }
@@ -1298,14 +1285,12 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     V.dn = S.dn + slot * n1;
     V.dns = V.dn;
     V.pos = S.pos + slot * (size_t)n;
-    BigBox *boxes = S.boxes + slot * (size_t)n;
     NbCache C;
     C.lines = S.nb + slot * (size_t)n * NB_WORDS;
-    C.slots = nb_pool_slots(n);
-    C.pool = S.nb_pool + slot * (size_t)C.slots * NB_EXT * 3;
-    C.pool_next = S.nb_next + slot;
+    C.heap_cap = nb_heap_cap(n);
+    C.heap = S.nb_heap + slot * (size_t)C.heap_cap;
+    C.heap_next = S.nb_next + slot * 4;
     C.cnt8 = S.cnt8 + slot * (size_t)n;
-    C.nbig = S.nbig + slot;
     V.o8 = S.o8 + slot * (size_t)n;
     int *best_path = S.best_path + slot * (size_t)n;
     uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * PR_WBUF;
@@ -1327,9 +1312,9 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             const int node = order[p == n ? 0 : p];
             V.pxy[p] = xy[node];
             V.tid[p] = node;
-            if (p < n) { V.pos[node] = p; C.lines[(size_t)p * NB_WORDS] = NB_HDR_STALE; C.cnt8[p] = 1; V.o8[p] = 0; }    // a new tour: every cached list is stale
+            if (p < n) { V.pos[node] = p; C.lines[(size_t)p * NB_WORDS] = NB_HDR_STALE; C.cnt8[p] = 1; V.o8[p] = NB_EP_INIT << 1; }    // a new tour: every cached list is stale
         }
-        if (t == 0) { *s_cost = 0; *s_q = 0; *C.pool_next = 0; *C.nbig = 0; }
+        if (t == 0) { *s_cost = 0; C.heap_next[0] = 0; C.heap_next[1] = 0; C.heap_next[2] = 0; C.heap_next[3] = 0; }
         if (threadIdx.x == 0) { s_key_[0] = KEY_EMPTY; s_key_[1] = KEY_EMPTY; s_best = -1; }
         team_sync<CL>();
         long long local = 0;
@@ -1347,20 +1332,15 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
         unsigned par = 0;
         bool cut = false;
         PosPatch F = POSPATCH_NONE;
-        // three barriers per scan + move.  The argmin key is double-buffered by iteration parity and the queue counter is
-        // re-armed during the move, when nobody uses it; the positions of the two segment ends are written behind the last
-        // barrier and bridged by F.  The key stays per CTA and is combined by reading the peers' copies: a 64-bit atomicMin
+        // two barriers per scan + move.  The argmin key is double-buffered by iteration parity; the positions of the two
+        // segment ends are written behind the last barrier and bridged by F.  The key stays per CTA and is combined by reading the peers' copies: a 64-bit atomicMin
         // is not atomic between a CTA's own shared-memory path and its peers' distributed-shared-memory path (measured,
         // scripts/cluster_probe.cu: lost updates), 64-bit atomicAdd is.
-        bool p2 = false;                                        // phase 2 runs only while uncached nodes exist (none known yet)
+        int ep = NB_EP_NONE, hp = 0, hsnap = 0;
         for (;;) {
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
-            cached_scan<M, NE, false>(V, G, F, warp, WARPS * CL, p2, s_q, boxes, wbuf, C, s_ring[threadIdx.x >> 5], &s_best, best, bestkey, ncand);
-            if (p2) {
-                team_sync<CL>();
-                pruned_phase2<M, NE, false>(V, G, F, warp, WARPS * CL, *s_q, boxes, wbuf, best, bestkey, ncand, 0);
-            }
+            cached_scan<M, NE, false>(V, G, F, ep, warp, WARPS * CL, hsnap, hp, wbuf, C, s_ring[threadIdx.x >> 5], &s_best, best, bestkey, ncand);
             bestkey = warp_min_key(bestkey);
             if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key_[par], bestkey);
             team_sync<CL>();
@@ -1371,13 +1351,13 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
                 for (int r = 0; r < CL; ++r) kbest = min(kbest, *cluster.map_shared_rank(&s_key_[par], r));
             }
             if (kbest == KEY_EMPTY) break;                      // local optimum (refinment.c:27)
-            p2 = *(volatile int *)C.nbig > 0;                   // between the last two barriers: nobody changes it here
+            hsnap = heap_checkpoint(C, n, t, TEAM, hp);        // between the last two barriers: nobody changes it here
+            ep = (int)(moves % NB_EPOCHS);
             const int a = key_a(kbest), b = key_b(kbest);
             int seg_s, seg_e;
-            apply_move<M>(V, a, b, t, TEAM, false, seg_s, seg_e);
+            apply_move<M>(V, a, b, t, TEAM, false, seg_s, seg_e, ep);
             if (t == 0) {
                 *s_cost += key_delta(kbest);
-                *s_q = 0;
                 if (stop != nullptr) *s_stop = *(volatile const int *)stop;
             }
             if (threadIdx.x == 0) { s_key_[par ^ 1] = KEY_EMPTY; s_best = -1; }

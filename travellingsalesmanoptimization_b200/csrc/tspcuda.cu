@@ -60,7 +60,7 @@ enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3, M_G
 struct ScratchBuf { void *p = nullptr; size_t bytes = 0; };
 enum {
     SC_NN_CXY, SC_NN_CID, SC_NN_ORDER, SC_NN_COST, SC_NN_SLOT, SC_BEST_PATH, SC_NEXT, SC_DCOST, SC_DMOVES, SC_DPATHS,
-    SC_M_PXY, SC_M_TID, SC_M_DN, SC_M_POS, SC_M_BOXES, SC_M_BPATH, SC_M_BCOST, SC_M_BSTART, SC_M_CAND, SC_M_NB, SC_M_NBPOOL, SC_M_NBNEXT, SC_M_O8, SC_M_CNT8, SC_M_NBIG, SC_DSTATUS,
+    SC_M_PXY, SC_M_TID, SC_M_DN, SC_M_POS, SC_M_BPATH, SC_M_BCOST, SC_M_BSTART, SC_M_CAND, SC_M_NB, SC_M_NBHEAP, SC_M_NBNEXT, SC_M_O8, SC_M_CNT8, SC_DSTATUS,
     SC_T_TEN, SC_T_TRACE, SC_T_BEST, SC_T_OUT, SC_NB_LIST, SC_COUNT
 };
 
@@ -95,12 +95,12 @@ struct tspcuda_ctx {
     BigBox *d_boxes = nullptr;
     uint4 *d_wbuf = nullptr;         // per-warp record buffers of the pruned kernels (num_sms * 32 warps)
     int *d_nb = nullptr;             // delta cache of the resident tour (pruned.cuh: one 64-byte line per node,
-    int *d_nb_pool = nullptr;        //   an extension pool for the long lists,
-    int *d_nb_next = nullptr;        //   the pool's bump counter,
-    unsigned char *d_o8 = nullptr;   //   one orientation byte and one count byte per node, the number of uncached nodes)
+    int4 *d_nb_heap = nullptr;       //   a record heap for the long lists,
+    int *d_nb_next = nullptr;        //   the heap's counters,
+    unsigned char *d_o8 = nullptr;   //   one orientation / epoch byte and one count byte per node)
     unsigned char *d_cnt8 = nullptr; //   and a byte-per-node flag array for nb_mark_*_kernel
-    int *d_nbig = nullptr;
     unsigned char *d_nbflag = nullptr;
+    long long nb_moves = 0;          // moves the delta cache has followed since it was last invalidated (epoch numbering)
     bool nb_valid = false;           // false: the tour changed behind the cache's back (upload, full-scan or tabu moves)
     int *d_stop = nullptr;           // time-limit flag of the batched multi-start kernels, raised through aux_stream
     int *h_one = nullptr;            // pinned constant 1: source of that copy (a DMA copy needs no SM, a memset kernel might)
@@ -146,7 +146,7 @@ extern "C" void tspcuda_destroy(tspcuda_ctx *c) {
     cudaFree(c->d_tabu); cudaFree(c->d_key); cudaFree(c->d_state); cudaFree(c->d_log);
     cudaFree(c->d_matrix); cudaFree(c->d_sum); cudaFree(c->d_flush);
     cudaFree(c->d_cell_start); cudaFree(c->d_cell_count); cudaFree(c->d_cnode); cudaFree(c->d_cxy);
-    cudaFree(c->d_qctr); cudaFree(c->d_boxes); cudaFree(c->d_wbuf); cudaFree(c->d_nb); cudaFree(c->d_nb_pool); cudaFree(c->d_nb_next); cudaFree(c->d_o8); cudaFree(c->d_cnt8); cudaFree(c->d_nbig); cudaFree(c->d_nbflag); cudaFree(c->d_stop);
+    cudaFree(c->d_qctr); cudaFree(c->d_boxes); cudaFree(c->d_wbuf); cudaFree(c->d_nb); cudaFree(c->d_nb_heap); cudaFree(c->d_nb_next); cudaFree(c->d_o8); cudaFree(c->d_cnt8); cudaFree(c->d_nbflag); cudaFree(c->d_stop);
     if (c->h_one) cudaFreeHost(c->h_one);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     for (ScratchBuf &b : c->scratch) cudaFree(b.p);
@@ -274,12 +274,11 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         CKC(cudaMalloc(&c->d_boxes, sizeof(BigBox) * n));
         CKC(cudaMalloc(&c->d_wbuf, sizeof(uint4) * (size_t)PR_WBUF * 32 * c->num_sms));
         CKC(cudaMalloc(&c->d_nb, sizeof(int) * (size_t)NB_WORDS * n));
-        CKC(cudaMalloc(&c->d_nb_pool, sizeof(int) * 3 * (size_t)NB_EXT * nb_pool_slots(n)));
-        CKC(cudaMalloc(&c->d_nb_next, sizeof(int)));
+        CKC(cudaMalloc(&c->d_nb_heap, sizeof(int4) * (size_t)nb_heap_cap(n)));
+        CKC(cudaMalloc(&c->d_nb_next, sizeof(int) * 4));
+        CKC(cudaMemsetAsync(c->d_nb_next, 0, sizeof(int) * 4, c->stream));
         CKC(cudaMalloc(&c->d_o8, n));
         CKC(cudaMalloc(&c->d_cnt8, n));
-        CKC(cudaMalloc(&c->d_nbig, sizeof(int)));
-        CKC(cudaMemsetAsync(c->d_nbig, 0, sizeof(int), c->stream));
         CKC(cudaMalloc(&c->d_nbflag, n));
         CKC(cudaMemsetAsync(c->d_nbflag, 0, n, c->stream));
         G.cell_start = c->d_cell_start; G.cnode = c->d_cnode; G.cxy = c->d_cxy;
@@ -404,20 +403,21 @@ static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max
     V.dns = V.dn;
     V.o8 = c->d_o8;
     SpatialGrid G = c->grid;
-    unsigned long long *key = c->d_key, *qctr = c->d_qctr;
+    unsigned long long *key = c->d_key;
     DescState *st = c->d_state;
     MoveRec *log = c->d_log;
     long long log_cap = c->log_cap;
-    BigBox *boxes = c->d_boxes;
     uint4 *wbuf = c->d_wbuf;
     NbCache nb;
-    nb.lines = c->d_nb; nb.pool = c->d_nb_pool; nb.pool_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.nbig = c->d_nbig; nb.slots = nb_pool_slots(c->n);
+    nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(c->n);
     if (!c->nb_valid) {                                        // the tour was replaced or moved by another kernel: every list is stale
         nb_invalidate_kernel<<<grid_for(c->n, 4 * c->num_sms), 256, 0, c->stream>>>(nb, c->d_o8, c->n);
         c->stats.kernel_launches += 1;
         c->nb_valid = true;
+        c->nb_moves = 0;
     }
-    void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &qctr, &boxes, &wbuf, &nb};
+    long long moves0 = c->nb_moves;
+    void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &wbuf, &nb, &moves0};
     if (c->pruned_block == 1024)
         return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, 1024>, dim3(grid), dim3(1024), args, 0, c->stream);
     return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
@@ -480,7 +480,8 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
         CK(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         const long long applied = c->h_state->moves - c->dev_moves;
         c->dev_moves = c->h_state->moves;
-        if (!pruned && applied > 0) c->nb_valid = false;       // moves the neighbour cache has not seen
+        if (!pruned && applied > 0) c->nb_valid = false;       // moves the delta cache has not seen
+        if (pruned) c->nb_moves += applied;
         const long long scans = applied + (c->h_state->status == 1 ? 1 : 0);
         c->stats.moves += applied;
         c->stats.scans += scans;
@@ -1024,7 +1025,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
     CK(scratch_get(c, SC_BEST_PATH, sizeof(int) * n, best_path));
     std::vector<long long> hc(batch), hf(batch), hm(batch);
     std::vector<int> hs(batch);
-    DevBuf m_pxy, m_tid, m_dn, m_pos, m_boxes, m_bpath, m_bcost, m_bstart, m_cand, m_nb, m_nbpool, m_nbnext, m_o8, m_cnt8, m_nbig;
+    DevBuf m_pxy, m_tid, m_dn, m_pos, m_bpath, m_bcost, m_bstart, m_cand, m_nb, m_nbheap, m_nbnext, m_o8, m_cnt8;
     MultiSlots MS{};
     const int mslots = multi_path ? std::min(batch, c->num_sms) : 0;
     if (multi_path) {
@@ -1033,19 +1034,17 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
         CK(scratch_get(c, SC_M_TID, sizeof(int) * n1 * sl, m_tid));
         CK(scratch_get(c, SC_M_DN, sizeof(int) * n1 * sl, m_dn));
         CK(scratch_get(c, SC_M_POS, sizeof(int) * (size_t)n * sl, m_pos));
-        CK(scratch_get(c, SC_M_BOXES, sizeof(BigBox) * (size_t)n * sl, m_boxes));
         CK(scratch_get(c, SC_M_NB, sizeof(int) * (size_t)NB_WORDS * (size_t)n * sl, m_nb));
-        CK(scratch_get(c, SC_M_NBPOOL, sizeof(int) * 3 * (size_t)NB_EXT * (size_t)nb_pool_slots(n) * sl, m_nbpool));
-        CK(scratch_get(c, SC_M_NBNEXT, sizeof(int) * sl, m_nbnext));
+        CK(scratch_get(c, SC_M_NBHEAP, sizeof(int4) * (size_t)nb_heap_cap(n) * sl, m_nbheap));
+        CK(scratch_get(c, SC_M_NBNEXT, sizeof(int) * 4 * sl, m_nbnext));
         CK(scratch_get(c, SC_M_O8, (size_t)n * sl, m_o8));
         CK(scratch_get(c, SC_M_CNT8, (size_t)n * sl, m_cnt8));
-        CK(scratch_get(c, SC_M_NBIG, sizeof(int) * sl, m_nbig));
         CK(scratch_get(c, SC_M_BPATH, sizeof(int) * (size_t)n * sl, m_bpath));
         CK(scratch_get(c, SC_M_BCOST, sizeof(long long) * sl, m_bcost));
         CK(scratch_get(c, SC_M_BSTART, sizeof(int) * sl, m_bstart));
         CK(scratch_get(c, SC_M_CAND, sizeof(unsigned long long), m_cand));
         MS.pxy = m_pxy.as<double2>(); MS.tid = m_tid.as<int>(); MS.dn = m_dn.as<int>(); MS.pos = m_pos.as<int>();
-        MS.boxes = m_boxes.as<BigBox>(); MS.nb = m_nb.as<int>(); MS.nb_pool = m_nbpool.as<int>(); MS.nb_next = m_nbnext.as<int>(); MS.o8 = m_o8.as<unsigned char>(); MS.cnt8 = m_cnt8.as<unsigned char>(); MS.nbig = m_nbig.as<int>(); MS.best_path = m_bpath.as<int>();
+        MS.nb = m_nb.as<int>(); MS.nb_heap = m_nbheap.as<int4>(); MS.nb_next = m_nbnext.as<int>(); MS.o8 = m_o8.as<unsigned char>(); MS.cnt8 = m_cnt8.as<unsigned char>(); MS.best_path = m_bpath.as<int>();
         MS.best_cost = m_bcost.as<long long>(); MS.best_start = m_bstart.as<int>();
     }
     std::vector<long long> hbc(std::max(1, mslots));
@@ -1582,7 +1581,7 @@ static int vns_search_impl(tspcuda_ctx *c, int *path, double *cost_inout, int n_
             CK(scratch_get(c, SC_NB_LIST, sizeof(int) * (size_t)n, d_list));
             CK(cudaMemcpyAsync(d_list.p, changed.data(), sizeof(int) * changed.size(), cudaMemcpyHostToDevice, c->stream));
             NbCache nb;
-            nb.lines = c->d_nb; nb.pool = c->d_nb_pool; nb.pool_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.nbig = c->d_nbig; nb.slots = nb_pool_slots(n);
+            nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(n);
             const int cn = (int)changed.size();
             nb_mark_nodes_kernel<<<1, 256, 0, c->stream>>>(nb, d_list.as<int>(), cn, c->d_nbflag, 1);
             nb_mark_records_kernel<<<grid_for(n, 4 * c->num_sms), 256, 0, c->stream>>>(nb, c->d_nbflag, n);
