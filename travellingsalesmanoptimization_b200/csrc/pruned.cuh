@@ -508,6 +508,7 @@ constexpr int NB_CAP = 5;                      // records held in the line itsel
 constexpr int NB_CF_STALE = 1023, NB_CF_HEAP = 1022;          // header: never searched / list in the heap (words 1, 2: start, count)
 constexpr int NB_HDR_STALE = NB_CF_STALE;
 constexpr int NB_DIRTY = (int)0x80000000;      // d0 of a record that must be recomputed before use
+constexpr int NB_GIANT = 512;                  // a search box with more nodes than this is not walked by one warp: giant_phase()
 constexpr int NB_EPOCHS = 126;                 // epochs 0..125 cycle; 126: "no move yet"; 127: a node no move has touched
 constexpr int NB_EP_NONE = 126, NB_EP_INIT = 127;
 
@@ -667,7 +668,7 @@ __device__ __forceinline__ bool node_box(const SpatialGrid &G, const NodeCtx &c,
 // SETTLE: only bring the cache up to date (no candidates): used when a launch ends right after a move.
 template <class M, int NE, bool SETTLE>
 __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGrid &G, const PosPatch &F, const NbCache &C, int hp, int u,
-                                             uint4 *ebuf, ScanAcc &a) {
+                                             unsigned long long *qctr, BigBox *boxes, uint4 *ebuf, ScanAcc &a) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
     int *line = C.lines + (size_t)u * NB_WORDS;
@@ -681,6 +682,50 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
     const int nrows = any ? cy1 - cy0 + 1 : 0;
     const int thr = max(c.dnp, c.dnm);
     int count = 0, tot = 0;
+    for (int r = lane; r < nrows; r += 32) tot += G.cell_start[(cy0 + r) * G.W + cx1 + 1] - G.cell_start[(cy0 + r) * G.W + cx0];
+    tot = __reduce_add_sync(FULL, tot);
+    if (tot > NB_GIANT) {
+        // A long tour edge (a nearest-neighbour tour has a few hundred, a VNS kick makes three): thousands of candidates.
+        // The box is not walked by this warp alone: it gets a heap run with one slot per node of the box and is queued;
+        // behind the scan's barrier all cooperating warps fill the run row by row (giant_phase).  When a launch is
+        // settling there is no such barrier: the node stays stale for the next launch.
+        if (had)
+            for (int j = lane; j < ocount; j += 32) C.heap[ostart + j].x = -1;
+        int start = -1;
+        if (!SETTLE && lane == 0) start = *(volatile int *)(C.heap_next + hp) > C.heap_cap ? -1 : atomicAdd(C.heap_next + hp, tot);
+        start = __shfl_sync(FULL, start, 0);
+        if (start > C.heap_cap - tot) {                            // no room: what the run covers is void
+            for (int j = start + lane; j < C.heap_cap; j += 32) C.heap[j].x = -1;
+            start = -1;
+        }
+        if (lane == 0) {
+            NBSTAT(0, 1); NBSTAT(7, tot); NBSTAT(1, 1);
+            atomicAdd(C.heap_next + 3, (start >= 0 ? tot : 0) - (had ? ocount : 0));
+            if (start >= 0) {
+                line[0] = NB_CF_HEAP; line[1] = start; line[2] = tot; line[3] = tot; C.cnt8[u] = 0;
+                const unsigned long long old = atomicAdd(qctr, (1ull << 40) | (unsigned long long)nrows);
+                BigBox bx;
+                bx.p = c.p; bx.cy0 = cy0; bx.cx0 = cx0; bx.cx1 = cx1; bx.nrows = nrows; bx.pad = start;
+                bx.base = (long long)(old & PR_UNIT_MASK);
+                boxes[old >> 40] = bx;
+            } else { line[0] = NB_HDR_STALE; C.cnt8[u] = 1; }
+        }
+        if (start >= 0 || SETTLE) return;
+        // no room in the heap: this warp walks the box after all, evaluating only (the node stays stale)
+        for (int r = 0; r < nrows; ++r) {
+            const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
+            if (lane == 0) a.ncand += hi - lo;
+            for (int k0 = lo; k0 < hi; k0 += 32) {
+                const int k = min(k0 + lane, hi - 1);
+                const double2 cw = G.cxy[k];
+                const int w = G.cnode[k];
+                const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
+                eval_push<M, NE>(V, F, ebuf, a, k0 + lane < hi && K < thr && w != u && w != c.su && w != c.pu, c.p, w, K);
+            }
+        }
+        return;
+    }
+    tot = 0;
     for (int r = 0; r < nrows; ++r) {
         const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
         tot += hi - lo;
@@ -759,7 +804,8 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
 // the attention entries of a warp: dirty records {u, w, address of the record's w field | AT_DIRTY} -- recomputed in
 // place, every lane its own -- and stale nodes {u, -, AT_NODE}: searched again, one at a time, by the whole warp
 template <class M, int NE, bool SETTLE>
-__device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPatch F, NbCache C, int hp, uint4 *abuf, int acount, ScanAcc a) {
+__device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPatch F, NbCache C, int hp, unsigned long long *qctr, BigBox *boxes,
+                                       uint4 *abuf, int acount, ScanAcc a) {
     const SpatialGrid &G = *Gp;
     const int lane = threadIdx.x & 31;
     uint4 *ebuf = abuf + AB_CAP;
@@ -797,7 +843,7 @@ __device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPat
         while (nm) {
             const int src = __ffs(nm) - 1;
             nm &= nm - 1;
-            rebuild_list<M, NE, SETTLE>(V, G, F, C, hp, (int)__shfl_sync(FULL, e.x, src), ebuf, a);
+            rebuild_list<M, NE, SETTLE>(V, G, F, C, hp, (int)__shfl_sync(FULL, e.x, src), qctr, boxes, ebuf, a);
         }
     }
     __syncwarp();
@@ -808,11 +854,12 @@ __device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPat
 //   ep     epoch of the last move (NB_EP_NONE: none): nodes whose o8 byte carries it had their neighbours changed
 //   hsnap  number of heap records to stream (the heap counter as it stood between the barriers before this scan)
 //   hp     which of the two heap counters is in use
+//   qctr, boxes   queue of the giant search boxes met in this scan (giant_phase, behind the caller's barrier)
 //   ring   NB_RING ints of shared memory private to the warp
 //   s_best the CTA's shared running best (armed to -1 by the caller behind a barrier)
 template <class M, int NE, bool SETTLE>
 __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid &G, const PosPatch &F, int ep, int gw, int nwarps, int hsnap,
-                                            int hp, uint4 *wbuf, const NbCache &C, int *ring, int *s_best, int &best,
+                                            int hp, unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, const NbCache &C, int *ring, int *s_best, int &best,
                                             unsigned long long &bestkey, long long &ncand) {
     ScanAcc a;
     a.bestkey = bestkey; a.ncand = ncand; a.best = best; a.ecount = 0;
@@ -831,7 +878,7 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
     }
     // ---- the heap: every cooperating thread a strided share of the records
     for (int k0 = gw * 32; k0 < hsnap; k0 += nwarps * 32) {
-        if (acount > AB_CAP - 32) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, wbuf, acount, a); acount = 0; }      // warp-uniform, rare
+        if (acount > AB_CAP - 32) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a); acount = 0; }      // warp-uniform, rare
         if (!SETTLE && a.ecount > EB_CAP - 32) a = flush_records<M, NE>(V, F, ebuf, a);
         const int k = k0 + lane;
         int4 r = make_int4(-1, 0, 0, 0);
@@ -884,7 +931,7 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
         const int u = have ? ring[(head + lane) & (NB_RING - 1)] : 0;
         head += step;
         __syncwarp();
-        if (acount > AB_CAP - 32 * (NB_CAP + 1)) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, wbuf, acount, a); acount = 0; }
+        if (acount > AB_CAP - 32 * (NB_CAP + 1)) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a); acount = 0; }
         if (!SETTLE && a.ecount > EB_CAP - 32 * NB_CAP) a = flush_records<M, NE>(V, F, ebuf, a);
         int4 q0 = make_int4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0;
         int ou = 0;
@@ -948,9 +995,85 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
             }
         }
     }
-    if (acount > 0) a = attend<M, NE, SETTLE>(V, &G, F, C, hp, wbuf, acount, a);
+    if (acount > 0) a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a);
     if (!SETTLE && a.ecount > 0) a = flush_records<M, NE>(V, F, ebuf, a);
     best = a.best; bestkey = a.bestkey; ncand = a.ncand;
+}
+
+// Behind the scan's barrier, when giant boxes were queued (q = the packed counter): their cell rows are split evenly
+// over the `nwarps` cooperating warps (this one is `gw`), as in pruned_phase2.  Candidate number i of a box (row by
+// row) owns slot i of the box's heap run: a record where the candidate passes, an abandoned slot where it does not --
+// no counting, no atomics; the records that can win now go to the exact evaluation.
+template <class M, int NE>
+__device__ __noinline__ void giant_phase(TourView V, const SpatialGrid *Gp, PosPatch F, NbCache C, long long gw, long long nwarps,
+                                         unsigned long long q, const BigBox *boxes, uint4 *wbuf, int *best_io, unsigned long long *key_io,
+                                         long long *ncand_io) {
+    const SpatialGrid &G = *Gp;
+    const int lane = threadIdx.x & 31;
+    const long long nunits = (long long)(q & PR_UNIT_MASK);
+    const int nboxes = (int)(q >> 40);
+    const long long per = (nunits + nwarps - 1) / nwarps;
+    const long long g0 = gw * per, g1 = min(nunits, g0 + per);
+    if (g0 >= g1) return;
+    ScanAcc a;
+    a.bestkey = *key_io; a.ncand = *ncand_io; a.best = *best_io; a.ecount = 0;
+    uint4 *ebuf = wbuf + AB_CAP;
+    int lo_b = 0, hi_b = nboxes;                                  // last box with base <= g0: 33-ary search
+    while (hi_b - lo_b > 1) {
+        const int step = (hi_b - lo_b + 32) / 33;
+        const int idx = lo_b + (lane + 1) * step;
+        const bool ok = idx < hi_b && boxes[idx].base <= g0;
+        const int cnt = __popc(__ballot_sync(FULL, ok));
+        const int nlo = lo_b + cnt * step;
+        hi_b = min(hi_b, lo_b + (cnt + 1) * step);
+        lo_b = nlo;
+    }
+    int bi = lo_b;
+    BigBox b = boxes[bi];
+    NodeCtx c;
+    int u = 0, ou = 0, thr = 0, rowoff = 0;
+    bool fresh = true;
+    for (long long g = g0; g < g1; ++g) {
+        while (g >= b.base + b.nrows) { b = boxes[++bi]; fresh = true; }
+        const int row = (int)(g - b.base);
+        if (fresh) {                                               // a new box: its node, and the slots the rows before this one own
+            u = V.tid[b.p];
+            node_ctx(V, F, u, c);
+            ou = V.o8[u];
+            thr = max(c.dnp, c.dnm);
+            int off = 0;
+            for (int r = lane; r < row; r += 32) off += G.cell_start[(b.cy0 + r) * G.W + b.cx1 + 1] - G.cell_start[(b.cy0 + r) * G.W + b.cx0];
+            rowoff = __reduce_add_sync(FULL, off);
+            fresh = false;
+        }
+        const int cy = b.cy0 + row;
+        const int lo = G.cell_start[cy * G.W + b.cx0], hi = G.cell_start[cy * G.W + b.cx1 + 1];
+        if (lane == 0) a.ncand += hi - lo;
+        for (int k0 = lo; k0 < hi; k0 += 32) {
+            const int k = k0 + lane;
+            bool pass = false;
+            int w = 0, K = 0, dsame = 0, dflip = 0;
+            if (k < hi) {
+                const double2 cw = G.cxy[k];
+                w = G.cnode[k];
+                K = M::K(c.u.x, c.u.y, cw.x, cw.y);
+                pass = K < thr && w != u && w != c.su && w != c.pu;
+                int4 rec = make_int4(-1, 0, 0, 0);
+                if (pass) {
+                    record_deltas<M>(V, F, c, w, K, dsame, dflip);
+                    const bool rel = ((ou ^ V.o8[w]) & 1) != 0;
+                    rec = make_int4(u, w, rel ? dflip : dsame, rel ? dsame : dflip);
+                }
+                C.heap[b.pad + rowoff + (k - lo)] = rec;
+            }
+            const bool hit = pass && dsame <= a.best;
+            if (hit) a.best = dsame;
+            eval_push<M, NE>(V, F, ebuf, a, hit, c.p, w, K);
+        }
+        rowoff += hi - lo;
+    }
+    if (a.ecount > 0) a = flush_records<M, NE>(V, F, ebuf, a);
+    *best_io = a.best; *key_io = a.bestkey; *ncand_io = a.ncand;
 }
 
 // between the last two barriers of an iteration, every cooperating thread (t of nthreads): the heap fill the next scan
@@ -1022,7 +1145,7 @@ __device__ __forceinline__ void pruned_phase2(const TourView &V, const SpatialGr
 template <class M, int BLK>
 __global__ void __launch_bounds__(BLK, 1)
 descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescState *st, MoveRec *log, long long log_cap,
-                      long long max_moves, uint4 *wbuf_all, NbCache C, long long moves0) {
+                      long long max_moves, unsigned long long *qctr, BigBox *boxes, uint4 *wbuf_all, NbCache C, long long moves0) {
     constexpr int WARPS = BLK / 32;
     constexpr int NE = BLK > 512 ? 2 : 4;                // records in flight per lane while evaluating (64 / 128 registers)
     cg::grid_group grid = cg::this_grid();
@@ -1066,7 +1189,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
 #ifdef TSP_PHASE_TIMING
         unsigned long long tw0; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw0));
 #endif
-        cached_scan<M, NE, false>(V, G, F, ep, gw, Wtot, hsnap, hp, wbuf, C, s_ring[warp], &s_best, best, bestkey, ncand);
+        cached_scan<M, NE, false>(V, G, F, ep, gw, Wtot, hsnap, hp, qctr, boxes, wbuf, C, s_ring[warp], &s_best, best, bestkey, ncand);
 #ifdef TSP_PHASE_TIMING
         {   // slowest and average warp of the scan (phase_ns[3] = max over scans and warps)
             unsigned long long tw1; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tw1));
@@ -1084,6 +1207,25 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(kslot, s_key);
         grid.sync();
         PHASE_MARK(0)
+        {   // giant search boxes met in this scan (rare): all warps fill their heap runs now, one more barrier
+            const unsigned long long q = *(volatile unsigned long long *)qctr;
+            if (q >> 40) {
+                bestkey = KEY_EMPTY;
+                ncand = 0;
+                giant_phase<M, NE>(V, &G, F, C, gw, Wtot, q, boxes, wbuf, &best, &bestkey, &ncand);
+                bestkey = warp_min_key(bestkey);
+                for (int off = 16; off > 0; off >>= 1) ncand += __shfl_down_sync(FULL, ncand, off);
+                if (lane == 0) {
+                    if (bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
+                    if (ncand) atomicAdd((unsigned long long *)&st->candidates, (unsigned long long)ncand);
+                }
+                __syncthreads();
+                if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(kslot, s_key);
+                grid.sync();
+                if (gtid == 0) *qctr = 0;
+                PHASE_MARK(1)
+            }
+        }
         const unsigned long long kbest = *(volatile unsigned long long *)kslot;
         if (kbest == KEY_EMPTY) {
             if (gtid == 0) st->status = 1;
@@ -1116,7 +1258,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         int best = -1;
         unsigned long long bestkey = KEY_EMPTY;
         long long ncand = 0;
-        cached_scan<M, NE, true>(V, G, F, ep, gw, Wtot, hsnap, hp, wbuf, C, s_ring[warp], nullptr, best, bestkey, ncand);
+        cached_scan<M, NE, true>(V, G, F, ep, gw, Wtot, hsnap, hp, qctr, boxes, wbuf, C, s_ring[warp], nullptr, best, bestkey, ncand);
     }
 }
 
@@ -1226,6 +1368,7 @@ struct MultiSlots {
     double2 *pxy;      // [slots][n+1]
     int *tid, *dn;     // [slots][n+1]
     int *pos;          // [slots][n]
+    BigBox *boxes;     // [slots][n]  queue of giant search boxes
     int *nb;           // [slots][n * NB_WORDS]  delta cache of the slot's current descent: node lines,
     int4 *nb_heap;     // [slots][nb_heap_cap(n)]                                              record heap,
     int *nb_next;      // [slots][4]                                                           its counters,
@@ -1263,16 +1406,18 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     constexpr int WARPS = BLK / 32;
     constexpr int NE = BLK > 512 ? 2 : 4;
     constexpr int TEAM = BLK * CL;                      // threads sharing a descent
-    __shared__ unsigned long long s_key_[2];
+    __shared__ unsigned long long s_key_[2], s_q_;
     __shared__ long long s_cost_, s_bestcost_;
     __shared__ int s_cur_, s_stop_, s_best;
     __shared__ int s_ring[WARPS][NB_RING];
     unsigned rank = 0;
+    unsigned long long *s_q = &s_q_;
     long long *s_cost = &s_cost_, *s_bestcost = &s_bestcost_;
     int *s_cur = &s_cur_, *s_stop = &s_stop_;
     if (CL > 1) {                                       // the scalars of the cluster's first CTA, through DSMEM
         cg::cluster_group cluster = cg::this_cluster();
         rank = cluster.block_rank();
+        s_q = cluster.map_shared_rank(&s_q_, 0);
         s_cost = cluster.map_shared_rank(&s_cost_, 0); s_bestcost = cluster.map_shared_rank(&s_bestcost_, 0);
         s_cur = cluster.map_shared_rank(&s_cur_, 0); s_stop = cluster.map_shared_rank(&s_stop_, 0);
     }
@@ -1285,6 +1430,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     V.dn = S.dn + slot * n1;
     V.dns = V.dn;
     V.pos = S.pos + slot * (size_t)n;
+    BigBox *boxes = S.boxes + slot * (size_t)n;
     NbCache C;
     C.lines = S.nb + slot * (size_t)n * NB_WORDS;
     C.heap_cap = nb_heap_cap(n);
@@ -1314,7 +1460,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             V.tid[p] = node;
             if (p < n) { V.pos[node] = p; C.lines[(size_t)p * NB_WORDS] = NB_HDR_STALE; C.cnt8[p] = 1; V.o8[p] = NB_EP_INIT << 1; }    // a new tour: every cached list is stale
         }
-        if (t == 0) { *s_cost = 0; C.heap_next[0] = 0; C.heap_next[1] = 0; C.heap_next[2] = 0; C.heap_next[3] = 0; }
+        if (t == 0) { *s_cost = 0; *s_q = 0; C.heap_next[0] = 0; C.heap_next[1] = 0; C.heap_next[2] = 0; C.heap_next[3] = 0; }
         if (threadIdx.x == 0) { s_key_[0] = KEY_EMPTY; s_key_[1] = KEY_EMPTY; s_best = -1; }
         team_sync<CL>();
         long long local = 0;
@@ -1340,10 +1486,21 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
         for (;;) {
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
-            cached_scan<M, NE, false>(V, G, F, ep, warp, WARPS * CL, hsnap, hp, wbuf, C, s_ring[threadIdx.x >> 5], &s_best, best, bestkey, ncand);
+            cached_scan<M, NE, false>(V, G, F, ep, warp, WARPS * CL, hsnap, hp, s_q, boxes, wbuf, C, s_ring[threadIdx.x >> 5], &s_best, best, bestkey, ncand);
             bestkey = warp_min_key(bestkey);
             if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key_[par], bestkey);
             team_sync<CL>();
+            {   // giant search boxes met in this scan (rare): all warps of the team fill their heap runs now, one more barrier
+                const unsigned long long q = *s_q;
+                if (q >> 40) {
+                    bestkey = KEY_EMPTY;
+                    giant_phase<M, NE>(V, &G, F, C, warp, WARPS * CL, q, boxes, wbuf, &best, &bestkey, &ncand);
+                    bestkey = warp_min_key(bestkey);
+                    if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key_[par], bestkey);
+                    team_sync<CL>();
+                    if (t == 0) *s_q = 0;
+                }
+            }
             unsigned long long kbest = s_key_[par];
             if (CL > 1) {
                 cg::cluster_group cluster = cg::this_cluster();

@@ -60,7 +60,7 @@ enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3, M_G
 struct ScratchBuf { void *p = nullptr; size_t bytes = 0; };
 enum {
     SC_NN_CXY, SC_NN_CID, SC_NN_ORDER, SC_NN_COST, SC_NN_SLOT, SC_BEST_PATH, SC_NEXT, SC_DCOST, SC_DMOVES, SC_DPATHS,
-    SC_M_PXY, SC_M_TID, SC_M_DN, SC_M_POS, SC_M_BPATH, SC_M_BCOST, SC_M_BSTART, SC_M_CAND, SC_M_NB, SC_M_NBHEAP, SC_M_NBNEXT, SC_M_O8, SC_M_CNT8, SC_DSTATUS,
+    SC_M_PXY, SC_M_TID, SC_M_DN, SC_M_POS, SC_M_BOXES, SC_M_BPATH, SC_M_BCOST, SC_M_BSTART, SC_M_CAND, SC_M_NB, SC_M_NBHEAP, SC_M_NBNEXT, SC_M_O8, SC_M_CNT8, SC_DSTATUS,
     SC_T_TEN, SC_T_TRACE, SC_T_BEST, SC_T_OUT, SC_NB_LIST, SC_COUNT
 };
 
@@ -403,10 +403,11 @@ static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max
     V.dns = V.dn;
     V.o8 = c->d_o8;
     SpatialGrid G = c->grid;
-    unsigned long long *key = c->d_key;
+    unsigned long long *key = c->d_key, *qctr = c->d_qctr;
     DescState *st = c->d_state;
     MoveRec *log = c->d_log;
     long long log_cap = c->log_cap;
+    BigBox *boxes = c->d_boxes;
     uint4 *wbuf = c->d_wbuf;
     NbCache nb;
     nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(c->n);
@@ -416,8 +417,10 @@ static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max
         c->nb_valid = true;
         c->nb_moves = 0;
     }
+    cudaError_t me = cudaMemsetAsync(c->d_qctr, 0, sizeof(unsigned long long), c->stream);      // the giant-box queue (shared with the tabu kernel)
+    if (me != cudaSuccess) return me;
     long long moves0 = c->nb_moves;
-    void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &wbuf, &nb, &moves0};
+    void *args[] = {&V, &G, &key, &st, &log, &log_cap, &max_moves, &qctr, &boxes, &wbuf, &nb, &moves0};
     if (c->pruned_block == 1024)
         return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, 1024>, dim3(grid), dim3(1024), args, 0, c->stream);
     return cudaLaunchCooperativeKernel((void *)descend_pruned_kernel<M, PRUNED_BLOCK>, dim3(grid), dim3(PRUNED_BLOCK), args, 0, c->stream);
@@ -1025,7 +1028,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
     CK(scratch_get(c, SC_BEST_PATH, sizeof(int) * n, best_path));
     std::vector<long long> hc(batch), hf(batch), hm(batch);
     std::vector<int> hs(batch);
-    DevBuf m_pxy, m_tid, m_dn, m_pos, m_bpath, m_bcost, m_bstart, m_cand, m_nb, m_nbheap, m_nbnext, m_o8, m_cnt8;
+    DevBuf m_pxy, m_tid, m_dn, m_pos, m_boxes, m_bpath, m_bcost, m_bstart, m_cand, m_nb, m_nbheap, m_nbnext, m_o8, m_cnt8;
     MultiSlots MS{};
     const int mslots = multi_path ? std::min(batch, c->num_sms) : 0;
     if (multi_path) {
@@ -1034,6 +1037,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
         CK(scratch_get(c, SC_M_TID, sizeof(int) * n1 * sl, m_tid));
         CK(scratch_get(c, SC_M_DN, sizeof(int) * n1 * sl, m_dn));
         CK(scratch_get(c, SC_M_POS, sizeof(int) * (size_t)n * sl, m_pos));
+        CK(scratch_get(c, SC_M_BOXES, sizeof(BigBox) * (size_t)n * sl, m_boxes));
         CK(scratch_get(c, SC_M_NB, sizeof(int) * (size_t)NB_WORDS * (size_t)n * sl, m_nb));
         CK(scratch_get(c, SC_M_NBHEAP, sizeof(int4) * (size_t)nb_heap_cap(n) * sl, m_nbheap));
         CK(scratch_get(c, SC_M_NBNEXT, sizeof(int) * 4 * sl, m_nbnext));
@@ -1044,7 +1048,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
         CK(scratch_get(c, SC_M_BSTART, sizeof(int) * sl, m_bstart));
         CK(scratch_get(c, SC_M_CAND, sizeof(unsigned long long), m_cand));
         MS.pxy = m_pxy.as<double2>(); MS.tid = m_tid.as<int>(); MS.dn = m_dn.as<int>(); MS.pos = m_pos.as<int>();
-        MS.nb = m_nb.as<int>(); MS.nb_heap = m_nbheap.as<int4>(); MS.nb_next = m_nbnext.as<int>(); MS.o8 = m_o8.as<unsigned char>(); MS.cnt8 = m_cnt8.as<unsigned char>(); MS.best_path = m_bpath.as<int>();
+        MS.boxes = m_boxes.as<BigBox>(); MS.nb = m_nb.as<int>(); MS.nb_heap = m_nbheap.as<int4>(); MS.nb_next = m_nbnext.as<int>(); MS.o8 = m_o8.as<unsigned char>(); MS.cnt8 = m_cnt8.as<unsigned char>(); MS.best_path = m_bpath.as<int>();
         MS.best_cost = m_bcost.as<long long>(); MS.best_start = m_bstart.as<int>();
     }
     std::vector<long long> hbc(std::max(1, mslots));
