@@ -38,8 +38,8 @@ if "k7" in what:
                   % (name, moves, c2, wall, s["pruned_kernel_ms"], 1e3 * s["pruned_kernel_ms"] / max(1, s["pruned_scans"]),
                      s["candidate_evals"] / max(1, s["pruned_scans"]), s["kernel_launches"]), flush=True)
 
-if "k8" in what:
-    for blk in ("1024", "512"):
+if "k8" in what or "k8fast" in what:
+    for blk in (("1024", "512") if "k8" in what else ("1024",)):
         os.environ["TSPCUDA_K8_BLOCK"] = blk
         for name, count in (("pr2392", 2392), ("usa13509", 296), ("usa13509", 1184), ("d15112", 296), ("pla85900", 148), ("pla85900", 296)):
             xy, _ = T.load_instance(name)

@@ -515,10 +515,12 @@ constexpr int NB_EP_NONE = 126, NB_EP_INIT = 127;
 struct NbCache {
     int *lines;             // [n][NB_WORDS]
     int4 *heap;             // [heap_cap] records {u, w, d0, d1}; u < 0: abandoned
-    int *heap_next;         // [0], [1]: bump counters of the heap, [2]: which of the two is in use (they swap at a reset), [3]: live records
+    int *heap_next;         // [0], [1]: bump counters of the heap, [2]: which of the two is in use (they swap at a reset), [3]: live
+                            // records, [4]: nodes whose list lives in the heap (8 ints)
     unsigned char *cnt8;    // [n] non-zero: the node's line must be looked at (records, stale); zero: nothing there
     int heap_cap;
 };
+__host__ __device__ inline int nb_cnt8_stride(int n) { return (n + 127) & ~127; }      // read four bytes at a time
 __host__ __device__ inline int nb_heap_cap(int n) { return (int)min((long long)24 * n + 4096, (long long)0x3FFFFFF0); }
 
 __global__ void nb_invalidate_kernel(NbCache C, unsigned char *o8, int n) {
@@ -527,7 +529,7 @@ __global__ void nb_invalidate_kernel(NbCache C, unsigned char *o8, int n) {
         C.cnt8[u] = 1;
         o8[u] = NB_EP_INIT << 1;
     }
-    if (blockIdx.x == 0 && threadIdx.x == 0) { C.heap_next[0] = 0; C.heap_next[1] = 0; C.heap_next[2] = 0; C.heap_next[3] = 0; }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { C.heap_next[0] = 0; C.heap_next[1] = 0; C.heap_next[2] = 0; C.heap_next[3] = 0; C.heap_next[4] = 0; }
 }
 // after the tour was changed from outside WITHOUT any reversal (a VNS kick exchanges blocks): the listed nodes got new
 // neighbours.  Their own lists are marked stale (first kernel, which also raises flag[] and abandons their heap runs),
@@ -541,6 +543,7 @@ __global__ void nb_mark_nodes_kernel(NbCache C, const int *nodes, int count, uns
             if ((h[0] & 0x3FF) == NB_CF_HEAP) {
                 for (int j = 0; j < h[2]; ++j) C.heap[h[1] + j].x = -1;
                 atomicSub(C.heap_next + 3, h[2]);
+                atomicSub(C.heap_next + 4, 1);
             }
             h[0] = NB_HDR_STALE;
             C.cnt8[u] = 1;
@@ -611,7 +614,8 @@ constexpr int AB_CAP = PR_WBUF / 2;            // attention entries per warp
 constexpr int EB_CAP = PR_WBUF - AB_CAP;       // evaluation records per warp
 constexpr unsigned AT_DIRTY = 1, AT_NODE = 2;
 constexpr unsigned EV_NODEIDS = 4;             // evaluation record {u, w, -, 3 | EV_NODEIDS}: node ids instead of {p, w, K, type}
-constexpr int NB_RING = 64;                    // per-warp ring of pending node ids (shared memory)
+constexpr int NB_RING = 256;                   // per-warp ring of pending node ids (shared memory): 31 left over + 128 new at most
+constexpr int NB_HU = 4;                       // heap records in flight per lane
 
 struct ScanAcc {
     unsigned long long bestkey;
@@ -701,6 +705,7 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
         if (lane == 0) {
             NBSTAT(0, 1); NBSTAT(7, tot); NBSTAT(1, 1);
             atomicAdd(C.heap_next + 3, (start >= 0 ? tot : 0) - (had ? ocount : 0));
+            if ((start >= 0) != had) atomicAdd(C.heap_next + 4, had ? -1 : 1);
             if (start >= 0) {
                 line[0] = NB_CF_HEAP; line[1] = start; line[2] = tot; line[3] = tot; C.cnt8[u] = 0;
                 const unsigned long long old = atomicAdd(qctr, (1ull << 40) | (unsigned long long)nrows);
@@ -756,7 +761,10 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
     }
     if (had && start != ostart)                                    // the old run is abandoned
         for (int j = lane; j < ocount; j += 32) C.heap[ostart + j].x = -1;
-    if (lane == 0 && (had || start >= 0)) atomicAdd(C.heap_next + 3, (start >= 0 ? count : 0) - (had ? ocount : 0));       // live records
+    if (lane == 0 && (had || start >= 0)) {
+        atomicAdd(C.heap_next + 3, (start >= 0 ? count : 0) - (had ? ocount : 0));                   // live records
+        if ((start >= 0) != had) atomicAdd(C.heap_next + 4, had ? -1 : 1);                              // nodes with a run
+    }
     if (count == 0) {
         if (lane == 0) { line[0] = 0; C.cnt8[u] = 0; }
         return;
@@ -876,53 +884,97 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
             acount = 1;
         }
     }
-    // ---- the heap: every cooperating thread a strided share of the records
-    for (int k0 = gw * 32; k0 < hsnap; k0 += nwarps * 32) {
-        if (acount > AB_CAP - 32) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a); acount = 0; }      // warp-uniform, rare
-        if (!SETTLE && a.ecount > EB_CAP - 32) a = flush_records<M, NE>(V, F, ebuf, a);
-        const int k = k0 + lane;
-        int4 r = make_int4(-1, 0, 0, 0);
-        if (k < hsnap) r = C.heap[k];
-        bool live = r.x >= 0, dirty = false;
-        int d = 0x7FFFFFFF;
-        if (live) {
-            const int ou = V.o8[r.x], ow = V.o8[r.y];
-            if ((ou >> 1) == ep && in_patch(F, r.x)) live = false; // u's own list is being rebuilt by a designated warp
-            else if (r.z == NB_DIRTY || (ow >> 1) == ep) dirty = true;
-            else d = ((ou ^ ow) & 1) ? r.w : r.z;
+    // ---- the heap: every cooperating thread a strided share of the records, NB_HU loads in flight per lane (a warp that
+    // waits for one 16-byte record at a time is bound by the memory latency, not by the bandwidth)
+    for (int k0 = gw * 32; k0 < hsnap; k0 += nwarps * 32 * NB_HU) {
+        if (acount > AB_CAP - 32 * NB_HU) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a); acount = 0; }      // warp-uniform, rare
+        if (!SETTLE && a.ecount > EB_CAP - 32 * NB_HU) a = flush_records<M, NE>(V, F, ebuf, a);
+        int4 r[NB_HU];
+#pragma unroll
+        for (int j = 0; j < NB_HU; ++j) {
+            const int k = k0 + j * nwarps * 32 + lane;
+            r[j] = make_int4(-1, 0, 0, 0);
+            if (k < hsnap) r[j] = C.heap[k];
         }
-        a.ncand += live ? 1 : 0;
-        {
-            const unsigned m = __ballot_sync(FULL, dirty);
-            if (dirty) {
-                const unsigned long long ra = (unsigned long long)(&C.heap[k].y);
-                wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)r.x, (unsigned)r.y, (unsigned)(ra & 0xFFFFFFFFu) | AT_DIRTY, (unsigned)(ra >> 32));
+        int ou[NB_HU], ow[NB_HU];
+#pragma unroll
+        for (int j = 0; j < NB_HU; ++j) {
+            ou[j] = r[j].x >= 0 ? V.o8[r[j].x] : 0;
+            ow[j] = r[j].x >= 0 ? V.o8[r[j].y] : 0;
+        }
+        int d[NB_HU];
+        unsigned dirty = 0;
+        int mine = 0x7FFFFFFF;
+#pragma unroll
+        for (int j = 0; j < NB_HU; ++j) {
+            d[j] = 0x7FFFFFFF;
+            bool live = r[j].x >= 0;
+            if (live && (ou[j] >> 1) == ep && in_patch(F, r[j].x)) live = false;      // u's own list is being rebuilt by a designated warp
+            if (live) {
+                if (r[j].z == NB_DIRTY || (ow[j] >> 1) == ep) dirty |= 1u << j;
+                else { d[j] = ((ou[j] ^ ow[j]) & 1) ? r[j].w : r[j].z; mine = min(mine, d[j]); }
             }
-            acount += __popc(m);
+            a.ncand += live ? 1 : 0;
+            NBSTAT(2, 1);
+            if (live) NBSTAT(4, 1);
+        }
+        if (__any_sync(FULL, dirty != 0)) {                        // rare
+#pragma unroll
+            for (int j = 0; j < NB_HU; ++j) {
+                const bool f = (dirty >> j) & 1u;
+                const unsigned m = __ballot_sync(FULL, f);
+                if (f) {
+                    const unsigned long long ra = (unsigned long long)(&C.heap[k0 + j * nwarps * 32 + lane].y);
+                    wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)r[j].x, (unsigned)r[j].y, (unsigned)(ra & 0xFFFFFFFFu) | AT_DIRTY, (unsigned)(ra >> 32));
+                }
+                acount += __popc(m);
+            }
         }
         if (!SETTLE) {
             const int seen = *(volatile int *)s_best;
-            const int wm = __reduce_min_sync(FULL, min(d, min(a.best, seen)));
+            const int wm = __reduce_min_sync(FULL, min(mine, min(a.best, seen)));
             a.best = wm;
             if (lane == 0 && wm < seen) atomicMin(s_best, wm);
-            const bool hit = d <= wm;
-            const unsigned m = __ballot_sync(FULL, hit);
-            if (hit) ebuf[a.ecount + __popc(m & lt)] = make_uint4((unsigned)r.x, (unsigned)r.y, 0u, 3u | EV_NODEIDS);
-            a.ecount += __popc(m);
+            if (__any_sync(FULL, mine <= wm)) {
+#pragma unroll
+                for (int j = 0; j < NB_HU; ++j) {
+                    const bool hit = d[j] <= wm;
+                    const unsigned m = __ballot_sync(FULL, hit);
+                    if (hit) ebuf[a.ecount + __popc(m & lt)] = make_uint4((unsigned)r[j].x, (unsigned)r[j].y, 0u, 3u | EV_NODEIDS);
+                    a.ecount += __popc(m);
+                }
+            }
         }
     }
     // ---- the lines: a contiguous range of nodes per warp; count bytes first, non-empty lines 32 per step
-    const int chunk = (((n + nwarps - 1) / nwarps) + 31) & ~31;
+    // many warps, few nodes each (the whole GPU on one descent): 32-node ranges, so that every warp gets some; otherwise
+    // ranges in multiples of 128 nodes, whose count bytes are read four per lane
+    const int per = (n + nwarps - 1) / nwarps;
+    const bool wide = per > 64;
+    const int chunk = wide ? (per + 127) & ~127 : (per + 31) & ~31;
     const int lo = min(n, gw * chunk), hi = min(n, lo + chunk);
     int base = lo, head = 0, tail = 0;
     for (;;) {
-        while (base < hi && tail - head < 32) {                    // refill: the next 32 count bytes
-            const int u = base + lane;
-            const bool want = u < hi && C.cnt8[u] != 0;
-            const unsigned m = __ballot_sync(FULL, want);
-            if (want) ring[(tail + __popc(m & lt)) & (NB_RING - 1)] = u;
-            tail += __popc(m);
-            base += 32;
+        while (base < hi && tail - head < 32) {                    // refill
+            if (wide) {                                            // (cnt8 is allocated in whole words; base is a multiple of 128)
+                const int u4 = base + 4 * lane;
+                const unsigned c4 = u4 < hi ? *reinterpret_cast<const unsigned *>(C.cnt8 + u4) : 0u;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const bool want = ((c4 >> (8 * j)) & 0xFFu) != 0 && u4 + j < hi;
+                    const unsigned m = __ballot_sync(FULL, want);
+                    if (want) ring[(tail + __popc(m & lt)) & (NB_RING - 1)] = u4 + j;
+                    tail += __popc(m);
+                }
+                base += 128;
+            } else {
+                const int u1 = base + lane;
+                const bool want = u1 < hi && C.cnt8[u1] != 0;
+                const unsigned m = __ballot_sync(FULL, want);
+                if (want) ring[(tail + __popc(m & lt)) & (NB_RING - 1)] = u1;
+                tail += __popc(m);
+                base += 32;
+            }
         }
         const int step = min(32, tail - head);
         if (step == 0) break;
@@ -1077,14 +1129,21 @@ __device__ __noinline__ void giant_phase(TourView V, const SpatialGrid *Gp, PosP
 }
 
 // between the last two barriers of an iteration, every cooperating thread (t of nthreads): the heap fill the next scan
-// streams -- or, when the heap is three quarters full, a clean slate: every line stale, the other (zeroed) counter
+// streams -- or a fresh heap.  Abandoned records are streamed like live ones.  Reading them costs the less the more
+// threads share a descent, searching a node again does not get cheaper: once the abandoned records outnumber the live
+// ones (one CTA per descent; proportionally more for a cluster or the whole GPU), or the heap is three quarters full, the
+// nodes whose lists live in the heap are declared stale and the heap starts over at the other, zeroed, counter.  Lists
+// held in the lines are not affected.
 __device__ __forceinline__ int heap_checkpoint(const NbCache &C, int n, int t, int nthreads, int &hp) {
     const int hn = *(volatile int *)(C.heap_next + hp), live = *(volatile int *)(C.heap_next + 3);
-    // full, or mostly dead records (the giant lists of a tour's first long edges, long gone): start over
-    if (hn <= C.heap_cap / 4 * 3 && hn <= 4 * live + n) return hn;
-    for (int u = t; u < n; u += nthreads) { C.lines[(size_t)u * NB_WORDS] = NB_HDR_STALE; C.cnt8[u] = 1; }
+    const long long teams = max(1, nthreads >> 10);
+    if (hn <= C.heap_cap / 4 * 3 && (long long)hn - live <= teams * live + (n >> 1)) return min(hn, C.heap_cap);
+    for (int u = t; u < n; u += nthreads) {
+        int *h = C.lines + (size_t)u * NB_WORDS;
+        if ((*h & 0x3FF) == NB_CF_HEAP) { *h = NB_HDR_STALE; C.cnt8[u] = 1; }
+    }
     hp ^= 1;
-    if (t == 0) { C.heap_next[hp] = 0; C.heap_next[2] = hp; C.heap_next[3] = 0; }      // nobody looks at these before the next barrier
+    if (t == 0) { C.heap_next[hp] = 0; C.heap_next[2] = hp; C.heap_next[3] = 0; C.heap_next[4] = 0; }      // nobody looks at these before the next barrier
     return 0;
 }
 
@@ -1371,9 +1430,9 @@ struct MultiSlots {
     BigBox *boxes;     // [slots][n]  queue of giant search boxes
     int *nb;           // [slots][n * NB_WORDS]  delta cache of the slot's current descent: node lines,
     int4 *nb_heap;     // [slots][nb_heap_cap(n)]                                              record heap,
-    int *nb_next;      // [slots][4]                                                           its counters,
+    int *nb_next;      // [slots][8]                                                           its counters,
     unsigned char *o8; // [slots][n]                                                           orientation / epoch bytes,
-    unsigned char *cnt8; // [slots][n]                                                         count bytes
+    unsigned char *cnt8; // [slots][nb_cnt8_stride(n)]                                         count bytes
     int *best_path;    // [slots][n]  successor array of the CTA's best tour
     long long *best_cost;   // [slots]
     int *best_start;        // [slots]
@@ -1435,8 +1494,8 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     C.lines = S.nb + slot * (size_t)n * NB_WORDS;
     C.heap_cap = nb_heap_cap(n);
     C.heap = S.nb_heap + slot * (size_t)C.heap_cap;
-    C.heap_next = S.nb_next + slot * 4;
-    C.cnt8 = S.cnt8 + slot * (size_t)n;
+    C.heap_next = S.nb_next + slot * 8;
+    C.cnt8 = S.cnt8 + slot * (size_t)nb_cnt8_stride(n);
     V.o8 = S.o8 + slot * (size_t)n;
     int *best_path = S.best_path + slot * (size_t)n;
     uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * PR_WBUF;
@@ -1460,7 +1519,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             V.tid[p] = node;
             if (p < n) { V.pos[node] = p; C.lines[(size_t)p * NB_WORDS] = NB_HDR_STALE; C.cnt8[p] = 1; V.o8[p] = NB_EP_INIT << 1; }    // a new tour: every cached list is stale
         }
-        if (t == 0) { *s_cost = 0; *s_q = 0; C.heap_next[0] = 0; C.heap_next[1] = 0; C.heap_next[2] = 0; C.heap_next[3] = 0; }
+        if (t == 0) { *s_cost = 0; *s_q = 0; C.heap_next[0] = 0; C.heap_next[1] = 0; C.heap_next[2] = 0; C.heap_next[3] = 0; C.heap_next[4] = 0; }
         if (threadIdx.x == 0) { s_key_[0] = KEY_EMPTY; s_key_[1] = KEY_EMPTY; s_best = -1; }
         team_sync<CL>();
         long long local = 0;

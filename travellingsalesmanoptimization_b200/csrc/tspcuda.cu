@@ -275,10 +275,10 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         CKC(cudaMalloc(&c->d_wbuf, sizeof(uint4) * (size_t)PR_WBUF * 32 * c->num_sms));
         CKC(cudaMalloc(&c->d_nb, sizeof(int) * (size_t)NB_WORDS * n));
         CKC(cudaMalloc(&c->d_nb_heap, sizeof(int4) * (size_t)nb_heap_cap(n)));
-        CKC(cudaMalloc(&c->d_nb_next, sizeof(int) * 4));
-        CKC(cudaMemsetAsync(c->d_nb_next, 0, sizeof(int) * 4, c->stream));
+        CKC(cudaMalloc(&c->d_nb_next, sizeof(int) * 8));
+        CKC(cudaMemsetAsync(c->d_nb_next, 0, sizeof(int) * 8, c->stream));
         CKC(cudaMalloc(&c->d_o8, n));
-        CKC(cudaMalloc(&c->d_cnt8, n));
+        CKC(cudaMalloc(&c->d_cnt8, nb_cnt8_stride(n)));
         CKC(cudaMalloc(&c->d_nbflag, n));
         CKC(cudaMemsetAsync(c->d_nbflag, 0, n, c->stream));
         G.cell_start = c->d_cell_start; G.cnode = c->d_cnode; G.cxy = c->d_cxy;
@@ -517,7 +517,7 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
             unsigned long long h[8];
             cudaMemcpyFromSymbol(h, g_nbstat, sizeof(h));
             const double sc = (double)std::max<long long>(1, c->h_state->moves + 1);
-            fprintf(stderr, "[tspcuda] delta cache per scan: rebuilds %.1f (box nodes %.0f)  queued boxes %.1f  long lists %.1f  dirty %.1f  hits %.1f  evaluated %.1f  attend calls %.1f\n",
+            fprintf(stderr, "[tspcuda] delta cache per scan: rebuilds %.1f (box nodes %.0f)  giants/no-room %.2f  heap slots %.0f  dirty %.1f  heap live %.0f  evaluated %.1f  attend calls %.1f\n",
                     h[0] / sc, h[7] / sc, h[1] / sc, h[2] / sc, h[3] / sc, h[4] / sc, h[5] / sc, h[6] / sc);
             unsigned long long z[8] = {0};
             cudaMemcpyToSymbol(g_nbstat, z, sizeof(z));
@@ -1040,9 +1040,9 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
         CK(scratch_get(c, SC_M_BOXES, sizeof(BigBox) * (size_t)n * sl, m_boxes));
         CK(scratch_get(c, SC_M_NB, sizeof(int) * (size_t)NB_WORDS * (size_t)n * sl, m_nb));
         CK(scratch_get(c, SC_M_NBHEAP, sizeof(int4) * (size_t)nb_heap_cap(n) * sl, m_nbheap));
-        CK(scratch_get(c, SC_M_NBNEXT, sizeof(int) * 4 * sl, m_nbnext));
+        CK(scratch_get(c, SC_M_NBNEXT, sizeof(int) * 8 * sl, m_nbnext));
         CK(scratch_get(c, SC_M_O8, (size_t)n * sl, m_o8));
-        CK(scratch_get(c, SC_M_CNT8, (size_t)n * sl, m_cnt8));
+        CK(scratch_get(c, SC_M_CNT8, (size_t)nb_cnt8_stride(n) * sl, m_cnt8));
         CK(scratch_get(c, SC_M_BPATH, sizeof(int) * (size_t)n * sl, m_bpath));
         CK(scratch_get(c, SC_M_BCOST, sizeof(long long) * sl, m_bcost));
         CK(scratch_get(c, SC_M_BSTART, sizeof(int) * sl, m_bstart));
@@ -1239,6 +1239,17 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
     CK(cudaStreamSynchronize(c->stream));
     if (raised) CK(cudaStreamSynchronize(c->aux_stream));
     clk.lap(clk.rest);
+#ifdef TSP_NB_STATS
+    if (multi_path) {
+        unsigned long long h[8];
+        cudaMemcpyFromSymbol(h, g_nbstat, sizeof(h));
+        const double sc = (double)std::max<long long>(1, c->stats.pruned_scans);
+        fprintf(stderr, "[tspcuda] K8 delta cache per scan: rebuilds %.1f (box nodes %.0f)  giants/no-room %.2f  heap slots %.0f (live %.0f)  dirty %.1f  evaluated %.1f  attend calls %.1f\n",
+                h[0] / sc, h[7] / sc, h[1] / sc, h[2] / sc, h[4] / sc, h[3] / sc, h[5] / sc, h[6] / sc);
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbol(g_nbstat, z, sizeof(z));
+    }
+#endif
     if (starts_done_out) *starts_done_out = done;
     if (best_start_out) *best_start_out = best_start;
     if (best_cost_out) *best_cost_out = (double)best;
