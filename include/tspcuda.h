@@ -299,7 +299,9 @@ int tspcuda_flush_l2(tspcuda_ctx *ctx);
  * (thread-level, not warp-level).  kind: 0 DADD, 1 DMUL, 2 DFMA, 3 F2F.F32.F64, 4 MUFU.RSQ,
  * 5 FFMA, 6 the full EUC_REF edge-cost sequence (general coordinates), 7 the same for integer coordinates
  * (edge costs/s: the arithmetic ceiling of a scan that needs one edge cost per pair), 8 F2F.F32.F64 alone,
- * 9 the integer-coordinate sequence two costs at a time with packed FP32x2 instructions (what the scan runs). */
+ * 9 the integer-coordinate sequence two costs at a time with packed FP32x2 instructions (what the scan runs);
+ * 100 (after tspcuda_cost_matrix_device) bytes/s of the driver's own fill (cudaMemsetAsync) of the HBM-resident matrix
+ * buffer: what a pure writer reaches on this device, next to which the matrix build is read. */
 int tspcuda_pipe_rate(tspcuda_ctx *ctx, int kind, double *ops_per_s_out);
 /* Exhaustive self-check of the in-kernel float sqrt against IEEE sqrt.rn.f32 over every float in
  * [2^-60, 2^64): number of mismatches in *mismatches_out (must be 0). */

@@ -11,7 +11,7 @@ try:
 except Exception:
     pass
 O = Oracle()
-for name in ("pr2392", "usa13509", "d15112", "rand20000", "pla85900"):
+for name in (sys.argv[1:] or ("pr2392", "usa13509", "d15112", "rand20000", "pla85900")):
     xy = O.random_points(20000, 123) if name == "rand20000" else load_instance(name)[0]
     n = xy.shape[0]
     with T.Instance(xy) as I:

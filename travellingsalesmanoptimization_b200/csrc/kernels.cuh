@@ -224,7 +224,7 @@ __device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k)
 // pos[tid[e_out]] = e_out (tid[e_out] is succ_a after the reversal).
 // ep (delta cache only, V.o8 != NULL): the epoch of this move; the o8 bytes of the four nodes whose tour edges change
 // (a, succ a, b, succ b) are stamped with it in bits 1..7 (pruned.cuh).
-template <class M>
+template <class M, bool CACHE = false>
 __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int t, int nthreads, bool has_dns,
                                            int &s_out, int &e_out, int ep = 0) {
     const int n = V.n;
@@ -255,19 +255,19 @@ __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int 
         if (k != 0) { V.pos[tq] = p; V.pos[tp] = q; }   // k == 0: the end nodes, deferred (see above)
         if (p == 0) { V.pxy[n] = xq; V.tid[n] = tq; }
         if (q == 0) { V.pxy[n] = xp; V.tid[n] = tp; }
-        if (V.o8) {                                     // one owner per node: plain byte updates
+        if (CACHE) {                                    // one owner per node: plain byte updates
             if (k == 0) {                               // the segment ends: succ a and b
                 V.o8[tq] = (unsigned char)(((V.o8[tq] ^ 1) & 1) | (ep << 1));
                 V.o8[tp] = (unsigned char)(((V.o8[tp] ^ 1) & 1) | (ep << 1));
             } else { V.o8[tq] ^= 1; V.o8[tp] ^= 1; }
         }
     }
-    if (V.o8 && t == 0) {                               // a and succ b keep their direction
+    if (CACHE && t == 0) {                              // a and succ b keep their direction
         const int sb = V.tid[e + 1];
         V.o8[a] = (unsigned char)((V.o8[a] & 1) | (ep << 1));
         V.o8[sb] = (unsigned char)((V.o8[sb] & 1) | (ep << 1));
     }
-    if (V.o8 && (L & 1) && t == 0) {                    // the middle node of an odd segment stays in place but turns round too
+    if (CACHE && (L & 1) && t == 0) {                   // the middle node of an odd segment stays in place but turns round too
         int m = s + half; if (m >= n) m -= n;
         V.o8[V.tid[m]] ^= 1;
     }
@@ -627,8 +627,11 @@ __device__ __forceinline__ double cost_as_double(int koff) {
 // 2368 CTAs x 8 rows x 687 KB = 13 GB of open pages -- measured 0.80 of the copy bandwidth against 0.99 at n = 20 000).
 // Rows of a group have the same 16-byte alignment: consecutive rows when n is even, every other row when n is odd
 // (row i starts at cell i*n).  chunk_pairs: 16-byte cell pairs per unit and row (a multiple of the block size).
+#ifndef TSP_K1_MINB
+#define TSP_K1_MINB 1
+#endif
 template <class M>
-__global__ void __launch_bounds__(TSP_K1_BLOCK)
+__global__ void __launch_bounds__(TSP_K1_BLOCK, TSP_K1_MINB)
 cost_matrix_kernel(const double2 *__restrict__ xy, int n, double *__restrict__ out, int chunk_pairs) {
     constexpr int RB = TSP_K1_ROWS;
     const int s = (n & 1) ? 2 : 1;                       // row stride inside a group

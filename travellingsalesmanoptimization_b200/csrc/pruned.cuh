@@ -1295,7 +1295,7 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         ep = (int)((moves0 + it) % NB_EPOCHS);
         const int a = key_a(kbest), b = key_b(kbest), delta = key_delta(kbest);
         int seg_s, seg_e;
-        apply_move<M>(V, a, b, gtid, gsize, false, seg_s, seg_e, ep);
+        apply_move<M, true>(V, a, b, gtid, gsize, false, seg_s, seg_e, ep);
         if (gtid == 0) {
             key[(it + 1) & 1] = KEY_EMPTY;
             const long long lc = st->log_count;
@@ -1571,7 +1571,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             ep = (int)(moves % NB_EPOCHS);
             const int a = key_a(kbest), b = key_b(kbest);
             int seg_s, seg_e;
-            apply_move<M>(V, a, b, t, TEAM, false, seg_s, seg_e, ep);
+            apply_move<M, true>(V, a, b, t, TEAM, false, seg_s, seg_e, ep);
             if (t == 0) {
                 *s_cost += key_delta(kbest);
                 if (stop != nullptr) *s_stop = *(volatile const int *)stop;
