@@ -300,6 +300,8 @@ int tspcuda_flush_l2(tspcuda_ctx *ctx);
  * 5 FFMA, 6 the full EUC_REF edge-cost sequence (general coordinates), 7 the same for integer coordinates
  * (edge costs/s: the arithmetic ceiling of a scan that needs one edge cost per pair), 8 F2F.F32.F64 alone,
  * 9 the integer-coordinate sequence two costs at a time with packed FP32x2 instructions (what the scan runs);
+ * 10 the same two costs from FP32 instructions only (error-free transformation, no FP64, no F2F: measured slower, unused),
+ * 101 its mismatch count against kind 9's sequence over 1.5e9 integer coordinate triples (must be 0);
  * 100 (after tspcuda_cost_matrix_device) bytes/s of the driver's own fill (cudaMemsetAsync) of the HBM-resident matrix
  * buffer: what a pure writer reaches on this device, next to which the matrix build is read. */
 int tspcuda_pipe_rate(tspcuda_ctx *ctx, int kind, double *ops_per_s_out);

@@ -53,6 +53,7 @@
 
 static tspcuda_ctx *g_ctx = NULL;
 static tspcuda_mgpu *g_mgpu = NULL;             /* TSPCUDA_GPUS > 1: one context per GPU for the whole-loop overrides */
+static int g_gpus_used = 1;                     /* GPUs the last multi-start override ran on (call counters) */
 static point *g_mgpu_points = NULL;
 static int g_mgpu_n = -1;
 static int g_weight_type = TSPCUDA_EUC_REF;     /* set by the interposed tsp_read_input */
@@ -76,7 +77,7 @@ static void on_exit_hook(int status, void *arg) {
     if (s && *s == '1') {
         fprintf(stderr, "[tspcuda] interposed calls:");
         for (int i = 0; i < N_CALLS; i++) fprintf(stderr, " %s=%ld", g_names[i], g_calls[i]);
-        fprintf(stderr, " gpus=%d", g_mgpu ? tspcuda_mgpu_ndev(g_mgpu) : 1);
+        fprintf(stderr, " gpus=%d", g_gpus_used);          /* (the contexts themselves are gone by now: the cleanup handler ran first) */
         fprintf(stderr, "\n");
     }
     const char *f = getenv("TSPCUDA_FAST_EXIT");
@@ -184,6 +185,7 @@ static tspcuda_mgpu *mgpu_for_instance(void) {
         return NULL;
     }
     register_cleanup();
+    g_gpus_used = tspcuda_mgpu_ndev(g_mgpu);
     g_mgpu_points = tsp_inst.points;
     g_mgpu_n = tsp_inst.nnodes;
     g_mgpu_generation = g_generation;

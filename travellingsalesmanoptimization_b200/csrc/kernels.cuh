@@ -788,6 +788,7 @@ __global__ void pipe_rate_kernel(int iters, double seed, double *sink) {
             else if (KIND == 6) { int kk = EucGeneral::K(d[k], d[(k + 1) & 7], 3.25, 7.5); d[k] = __hiloint2double(__double2hiint(d[k]), __double2loint(d[k]) ^ (kk & 1)); }
             else if (KIND == 8) { f[k] = __double2float_rn(d[k]); d[k] = __hiloint2double(__double2hiint(d[k]), __double2loint(d[k]) ^ (__float_as_int(f[k]) & 1)); }
             else if (KIND == 9) { int ka, kb; EucInt::K2(d[k], d[(k + 1) & 7], d[(k + 1) & 7], d[k], 3.0, 7.0, ka, kb); d[k] = __hiloint2double(__double2hiint(d[k]), __double2loint(d[k]) ^ ((ka ^ kb) & 1)); }
+            else if (KIND == 10) { int ka, kb; EucIntF32::K2(f[k], f[(k + 1) & 7], f[(k + 1) & 7], f[k], 3.0f, 7.0f, ka, kb); f[k] = __int_as_float(__float_as_int(f[k]) ^ ((ka ^ kb) & 1)); }
             else if (KIND == 7) { int kk = EucInt::K(d[k], d[(k + 1) & 7], 3.0, 7.0); d[k] = __hiloint2double(__double2hiint(d[k]), __double2loint(d[k]) ^ (kk & 1)); }
         }
     }
@@ -795,6 +796,24 @@ __global__ void pipe_rate_kernel(int iters, double seed, double *sink) {
 #pragma unroll
     for (int k = 0; k < 8; ++k) acc += d[k] + (double)f[k];
     if (acc == 123.456) sink[0] = acc;
+}
+
+// EucIntF32 against EucInt over pseudo-random integer coordinates below 2^23 (measurement companion of pipe_rate kind 10)
+__global__ void f32cost_selfcheck_kernel(unsigned seed, int trials, unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    unsigned s = seed ^ (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u;
+    for (int it = 0; it < trials; ++it) {
+        int v[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { s = s * 1664525u + 1013904223u; v[k] = (int)(s >> 9); }       // 23 bits
+        if ((it & 7) == 0) { v[2] = v[0] + (v[2] & 1023) - 512; v[3] = v[1] + (v[3] & 1023) - 512; v[4] = v[0]; v[5] = v[1]; }   // near / coincident
+        int ka, kb, ra, rb;
+        EucIntF32::K2((float)v[0], (float)v[1], (float)v[2], (float)v[3], (float)v[4], (float)v[5], ka, kb);
+        EucInt::K2((double)v[0], (double)v[1], (double)v[2], (double)v[3], (double)v[4], (double)v[5], ra, rb);
+        if (ka != ra) bad++;
+        if (kb != rb) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
 }
 
 __global__ void sqrt_selfcheck_kernel(unsigned lo_bits, unsigned hi_bits, unsigned long long *mismatches) {

@@ -155,6 +155,44 @@ struct EucInt {
     static __device__ __forceinline__ double cost_floor(double d) { return d * 0.999999 - 1.0; }
 };
 
+// MEASUREMENT ONLY (tspcuda_pipe_rate kind 10, profiles/r02_k2.md): the same two costs for integer coordinates below 2^23
+// WITHOUT any FP64 instruction and without F2F.F32.F64 -- the float the reference hands to sqrtf(), RN32(dx^2 + dy^2),
+// from an error-free transformation in FP32: dx, dy exact; q = -(dx*dx) rounded, e = fma(dx, dx, q) its exact residual;
+// TwoSum of the two rounded squares; the residuals are integers below 2^24, so their sum is exact and ONE final rounding
+// add gives the correctly rounded (negated) sum.  15 packed FP32x2 instructions + 4 LOP3 + 2 FMNMX per two costs replace
+// 4 DADD + 4 DFMA + 2 F2F: one XU operation per cost instead of two, but 21 packed FP32 instructions per two costs on a
+// pipe that retires one packed instruction per two cycles.  It measures SLOWER than EucInt::K2 (see the profile note), so
+// no kernel uses it.
+struct EucIntF32 {
+    static __device__ __forceinline__ void K2(float xa, float ya, float xb, float yb, float xj, float yj, int &ka, int &kb) {
+        unsigned long long X, Y, XJ, YJ, dx, dy, ndx, ndy, q1, q2, e1, e2, sm, bb, t0, t1, t, es, rn, nf;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(X) : "f"(xa), "f"(xb));
+        asm("mov.b64 %0, {%1, %2};" : "=l"(Y) : "f"(ya), "f"(yb));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(XJ) : "f"(xj));
+        asm("mov.b64 %0, {%1, %1};" : "=l"(YJ) : "f"(yj));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dx) : "l"(XJ), "l"(X));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(dy) : "l"(YJ), "l"(Y));
+        ndx = dx ^ 0x8000000080000000ull;
+        ndy = dy ^ 0x8000000080000000ull;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q1) : "l"(dx), "l"(ndx));               // -(dx^2), rounded
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(q2) : "l"(dy), "l"(ndy));
+        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(e1) : "l"(dx), "l"(q1));            // dx^2 + q1: exact
+        asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(e2) : "l"(dy), "l"(q2));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(sm) : "l"(q1), "l"(q2));                // TwoSum(q1, q2) = (sm, t)
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(bb) : "l"(sm), "l"(q1));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t0) : "l"(sm), "l"(bb));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t0) : "l"(q1), "l"(t0));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(t1) : "l"(q2), "l"(bb));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(t) : "l"(t0), "l"(t1));
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(es) : "l"(e1), "l"(e2));
+        asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(rn) : "l"(t), "l"(es));                 // exact: integers below 2^24
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(nf) : "l"(sm), "l"(rn));                // -RN32(dx^2 + dy^2)
+        float n0, n1;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(n0), "=f"(n1) : "l"(nf));
+        koff2_from_negsumsq(fminf(n0, -TINY_F), fminf(n1, -TINY_F), ka, kb);
+    }
+};
+
 // TSPLIB95 CEIL_2D: ceil(sqrt(dx^2+dy^2)) in double.
 struct Ceil2D : ScalarScan<Ceil2D> {
     static __device__ __forceinline__ int K(double xi, double yi, double xj, double yj) {

@@ -1335,7 +1335,20 @@ extern "C" int tspcuda_pipe_rate(tspcuda_ctx *c, int kind, double *ops_per_s_out
         *ops_per_s_out = (double)bytes / (best * 1e-3);
         return TSPCUDA_OK;
     }
-    if (kind < 0 || kind > 9 || !ops_per_s_out) return fail(TSPCUDA_INVALID_ARGUMENT, "kind");
+    if (kind == 101 && ops_per_s_out) {
+        // mismatches of the FP32-only cost sequence (kind 10) against the shipped one over 1.5e9 integer coordinate triples
+        unsigned long long *d_bad = nullptr, h_bad = 0;
+        CK(cudaMalloc(&d_bad, sizeof(unsigned long long)));
+        CK(cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), c->stream));
+        f32cost_selfcheck_kernel<<<c->num_sms * 8, 256, 0, c->stream>>>(12345u, 5000, d_bad);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&h_bad, d_bad, sizeof(h_bad), cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        cudaFree(d_bad);
+        *ops_per_s_out = (double)h_bad;
+        return TSPCUDA_OK;
+    }
+    if (kind < 0 || kind > 10 || !ops_per_s_out) return fail(TSPCUDA_INVALID_ARGUMENT, "kind");
     double *d_sink = nullptr;
     CK(cudaMalloc(&d_sink, sizeof(double)));
     const int iters = 4096;
@@ -1353,6 +1366,7 @@ extern "C" int tspcuda_pipe_rate(tspcuda_ctx *c, int kind, double *ops_per_s_out
             case 6: le = run_pipe<6>(c, iters, d_sink); break;
             case 7: le = run_pipe<7>(c, iters, d_sink); break;
             case 8: le = run_pipe<8>(c, iters, d_sink); break;
+            case 10: le = run_pipe<10>(c, iters, d_sink); break;
             default: le = run_pipe<9>(c, iters, d_sink); break;
         }
         CK(le);
@@ -1364,7 +1378,7 @@ extern "C" int tspcuda_pipe_rate(tspcuda_ctx *c, int kind, double *ops_per_s_out
         if (rep > 0) best_ms = std::min(best_ms, ms);
     }
     cudaFree(d_sink);
-    const double per_iter = (kind == 3 || kind == 9) ? 16.0 : 8.0;   // kind 3: two conversions, kind 9: two edge costs per chain step       // kind 3 = F2F.F32.F64 + F2F.F64.F32 per chain step
+    const double per_iter = (kind == 3 || kind == 9 || kind == 10) ? 16.0 : 8.0;   // kind 3: two conversions, kind 9: two edge costs per chain step       // kind 3 = F2F.F32.F64 + F2F.F64.F32 per chain step
     const double ops = (double)c->num_sms * 8 * 256 * (double)iters * per_iter;
     *ops_per_s_out = ops / (best_ms * 1e-3);
     return TSPCUDA_OK;
