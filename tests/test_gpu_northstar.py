@@ -256,3 +256,38 @@ def test_restarts_c_abi(tsp, oracle):
         assert (merged[2], merged[4]) == (bs, bc) and np.array_equal(merged[3], bp)
         code, done, bs2, bp2, bc2 = I.restarts(tsp.RESTART_TABU, 0, 50, 1, iters=2000, time_limit=0.2)
         assert code == tsp.DEADLINE_EXCEEDED and 0 < done < 50 and oracle.is_tour(bp2) and oracle.tour_cost(xy, bp2) == bc2
+
+
+@pytest.mark.parametrize("per_node", ["0", "2"])
+def test_delta_cache_under_heap_pressure(tsp, monkeypatch, per_node):
+    """The rare paths of the delta cache (csrc/pruned.cuh): with TSPCUDA_NB_HEAP the record heap holds 4096 (+ 2 n)
+    records instead of 24 n, so long lists find no room (they stay stale and are searched again in every scan, giant
+    search boxes are walked by one warp without being cached) and the heap restarts every few moves.  Slower, and
+    move for move the reference's descent: usa13509 NN(0) -> 1983 moves -> 21119812 (golden), a kicked tour, and the
+    multi-start kernel start by start against the default configuration."""
+    xy, _ = load_instance("usa13509")
+    with tsp.Instance(xy) as I:                                   # default heap
+        I.set_scan_mode(tsp.SCAN_PRUNED)
+        code, p, c = I.nn(0)
+        code, m0, p0, c0, log0 = I.two_opt(p, log_cap=4096)
+        bs0, bp0, bc0, nn0, fin0, mv0 = I.multistart_two_opt(0, 40)
+        # a tour with three instance-spanning edges (what a VNS kick makes): giant boxes in the first scans
+        order = np.empty(len(p0), dtype=np.int64)
+        cur = 0
+        for k in range(len(p0)):
+            order[k] = cur
+            cur = p0[cur]
+        kicked = np.concatenate([order[:3000], order[9000:12000], order[3000:9000], order[12000:]])
+        pk = np.empty_like(p0)
+        pk[kicked] = np.roll(kicked, -1)
+        code, mk0, pk0, ck0, logk0 = I.two_opt(pk, log_cap=4096)
+    assert (m0, c0) == (1983, 21119812.0)
+    monkeypatch.setenv("TSPCUDA_NB_HEAP", per_node)
+    with tsp.Instance(xy) as I:
+        I.set_scan_mode(tsp.SCAN_PRUNED)
+        code, m1, p1, c1, log1 = I.two_opt(p, log_cap=4096)
+        assert (m1, c1) == (m0, c0) and log1 == log0 and np.array_equal(p1, p0)
+        code, mk1, pk1, ck1, logk1 = I.two_opt(pk, log_cap=4096)
+        assert (mk1, ck1) == (mk0, ck0) and logk1 == logk0 and np.array_equal(pk1, pk0)
+        bs1, bp1, bc1, nn1, fin1, mv1 = I.multistart_two_opt(0, 40)
+        assert (bs1, bc1) == (bs0, bc0) and np.array_equal(fin1, fin0) and np.array_equal(mv1, mv0) and np.array_equal(bp1, bp0)

@@ -60,6 +60,7 @@ template <class M, int BLK>
 __global__ void __launch_bounds__(BLK)
 extra_mileage_kernel(const double2 *__restrict__ xy, int n, EmState S) {
     cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned long long s_bk;
     const int gtid = blockIdx.x * BLK + threadIdx.x, gsize = gridDim.x * BLK;
     const int lane = threadIdx.x & 31;
     const int gw = gtid >> 5, nw = gsize >> 5;
@@ -131,25 +132,54 @@ extra_mileage_kernel(const double2 *__restrict__ xy, int n, EmState S) {
             *S.cost += mileage;                                     // :360
             S.key[par] = ~0ull;                                     // slot of the insertion after next
         }
+        // One CTA per queued node once the edge array is long (its threads stride over the edges; a single warp walking
+        // 40 000 edges with two gathers each was the whole cost of an insertion on pla85900: 475 us), one warp below that.
         const int nlist = *(volatile int *)&S.list_count[par];
-        for (int q = gw; q < nlist; q += nw) {
-            const int i = S.list[q];
-            const double2 pi = xy[i];
-            unsigned long long bk = ~0ull;                          // (mileage, edge index): first minimum in edge order
-            for (int j = lane; j <= m; j += 32) {
-                int eu = S.eu[j], ev = S.ev[j];
-                if (j == jstar) { eu = u; ev = istar; }
-                if (j == m) { eu = istar; ev = v; }
-                const double2 a = xy[eu], b = xy[ev];
-                const int kuv = M::K(a.x, a.y, b.x, b.y) - KOFF;
-                const int d = (M::K(a.x, a.y, pi.x, pi.y) - KOFF) + (M::K(pi.x, pi.y, b.x, b.y) - KOFF) - kuv;
-                bk = min(bk, ((unsigned long long)(unsigned)(d + EM_BIAS) << 32) | (unsigned)j);
+        if (m >= 4 * BLK) {
+            for (int q = blockIdx.x; q < nlist; q += gridDim.x) {   // CTA-uniform trip count
+                if (threadIdx.x == 0) s_bk = ~0ull;
+                __syncthreads();
+                const int i = S.list[q];
+                const double2 pi = xy[i];
+                unsigned long long bk = ~0ull;                      // (mileage, edge index): first minimum in edge order
+                for (int j = threadIdx.x; j <= m; j += BLK) {
+                    int eu = S.eu[j], ev = S.ev[j];
+                    if (j == jstar) { eu = u; ev = istar; }
+                    if (j == m) { eu = istar; ev = v; }
+                    const double2 a = xy[eu], b = xy[ev];
+                    const int kuv = M::K(a.x, a.y, b.x, b.y) - KOFF;
+                    const int d = (M::K(a.x, a.y, pi.x, pi.y) - KOFF) + (M::K(pi.x, pi.y, b.x, b.y) - KOFF) - kuv;
+                    bk = min(bk, ((unsigned long long)(unsigned)(d + EM_BIAS) << 32) | (unsigned)j);
+                }
+                for (int off = 16; off > 0; off >>= 1) bk = min(bk, __shfl_down_sync(FULL, bk, off));
+                if (lane == 0) atomicMin(&s_bk, bk);
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    const int bd = (int)(s_bk >> 32) - EM_BIAS;
+                    S.best[i] = bd; S.bedge[i] = (int)(s_bk & 0xFFFFFFFFu);
+                    atomicMin(&S.key[par ^ 1], ((unsigned long long)(unsigned)(bd + EM_BIAS) << 32) | (unsigned)i);
+                }
             }
-            for (int off = 16; off > 0; off >>= 1) bk = min(bk, __shfl_down_sync(FULL, bk, off));
-            if (lane == 0) {
-                const int bd = (int)(bk >> 32) - EM_BIAS;
-                S.best[i] = bd; S.bedge[i] = (int)(bk & 0xFFFFFFFFu);
-                atomicMin(&S.key[par ^ 1], ((unsigned long long)(unsigned)(bd + EM_BIAS) << 32) | (unsigned)i);
+        } else {
+            for (int q = gw; q < nlist; q += nw) {
+                const int i = S.list[q];
+                const double2 pi = xy[i];
+                unsigned long long bk = ~0ull;
+                for (int j = lane; j <= m; j += 32) {
+                    int eu = S.eu[j], ev = S.ev[j];
+                    if (j == jstar) { eu = u; ev = istar; }
+                    if (j == m) { eu = istar; ev = v; }
+                    const double2 a = xy[eu], b = xy[ev];
+                    const int kuv = M::K(a.x, a.y, b.x, b.y) - KOFF;
+                    const int d = (M::K(a.x, a.y, pi.x, pi.y) - KOFF) + (M::K(pi.x, pi.y, b.x, b.y) - KOFF) - kuv;
+                    bk = min(bk, ((unsigned long long)(unsigned)(d + EM_BIAS) << 32) | (unsigned)j);
+                }
+                for (int off = 16; off > 0; off >>= 1) bk = min(bk, __shfl_down_sync(FULL, bk, off));
+                if (lane == 0) {
+                    const int bd = (int)(bk >> 32) - EM_BIAS;
+                    S.best[i] = bd; S.bedge[i] = (int)(bk & 0xFFFFFFFFu);
+                    atomicMin(&S.key[par ^ 1], ((unsigned long long)(unsigned)(bd + EM_BIAS) << 32) | (unsigned)i);
+                }
             }
         }
         grid.sync();

@@ -521,7 +521,13 @@ struct NbCache {
     int heap_cap;
 };
 __host__ __device__ inline int nb_cnt8_stride(int n) { return (n + 127) & ~127; }      // read four bytes at a time
-__host__ __device__ inline int nb_heap_cap(int n) { return (int)min((long long)24 * n + 4096, (long long)0x3FFFFFF0); }
+// records of heap per node of the instance (default NB_HEAP_PER_NODE; TSPCUDA_NB_HEAP for tests that want the "no room" and
+// restart paths taken: tests/test_gpu_northstar.py)
+constexpr int NB_HEAP_PER_NODE = 24;
+inline int nb_heap_cap(int n, int per_node) {
+    const long long cap = (long long)per_node * n + 4096;
+    return (int)(cap < 0x3FFFFFF0LL ? cap : 0x3FFFFFF0LL);
+}
 
 __global__ void nb_invalidate_kernel(NbCache C, unsigned char *o8, int n) {
     for (int u = blockIdx.x * blockDim.x + threadIdx.x; u < n; u += gridDim.x * blockDim.x) {
@@ -1429,7 +1435,8 @@ struct MultiSlots {
     int *pos;          // [slots][n]
     BigBox *boxes;     // [slots][n]  queue of giant search boxes
     int *nb;           // [slots][n * NB_WORDS]  delta cache of the slot's current descent: node lines,
-    int4 *nb_heap;     // [slots][nb_heap_cap(n)]                                              record heap,
+    int4 *nb_heap;     // [slots][heap_cap]                                                    record heap,
+    int heap_cap;
     int *nb_next;      // [slots][8]                                                           its counters,
     unsigned char *o8; // [slots][n]                                                           orientation / epoch bytes,
     unsigned char *cnt8; // [slots][nb_cnt8_stride(n)]                                         count bytes
@@ -1492,7 +1499,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     BigBox *boxes = S.boxes + slot * (size_t)n;
     NbCache C;
     C.lines = S.nb + slot * (size_t)n * NB_WORDS;
-    C.heap_cap = nb_heap_cap(n);
+    C.heap_cap = S.heap_cap;
     C.heap = S.nb_heap + slot * (size_t)C.heap_cap;
     C.heap_next = S.nb_next + slot * 8;
     C.cnt8 = S.cnt8 + slot * (size_t)nb_cnt8_stride(n);
