@@ -13,6 +13,10 @@
 // "no candidate improves" proves local optimality.  tests/test_gpu_parity.py checks move logs of the
 // two kernels against each other and against the CPU restatement of the reference.
 //
+// Round 2: the 2-opt kernels (K7, K8) no longer search and evaluate in every scan: they keep the records of the searches
+// with their move deltas and STREAM them (the delta cache, second half of this file); the search-and-evaluate phases
+// described next remain the scan of the tabu loop (K5c), whose bound changes from iteration to iteration.
+//
 // Work distribution.  Phase 1: one thread per tour position; search boxes holding at most
 // PR_SMALL_NODES nodes are walked by that thread, larger ones (the long edges of a nearest-neighbour
 // tour) are queued.  Phase 2 (after a grid barrier): the queued boxes are cut into (box, cell row)
@@ -1426,7 +1430,7 @@ tabu_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, TabuCtl T
 // Multi-start work (h_greedy_2opt, heuristics.c:74-116): a pruned scan is a few thousand record
 // evaluations, far too little to fill 148 SMs, so the SMs run independent descents instead.  CTAs pull
 // start indices from an atomic counter in ascending order; the tour of the current start and its
-// neighbour cache live in the CTA's own slot of global memory (L1/L2 resident, any n), every barrier is
+// delta cache live in the CTA's own slot of global memory (any n; streamed from HBM with 148 descents resident), every barrier is
 // a __syncthreads.  Each CTA keeps its best tour under the reference's incumbent rule (strict '<' in
 // ascending start order, tsp.c:671); the host takes the (cost, start)-minimum.
 struct MultiSlots {

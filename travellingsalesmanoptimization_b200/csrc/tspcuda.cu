@@ -467,7 +467,7 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
         c->chunk_no++;
         const double est = pruned ? std::max(c->est_pruned_s, 2e-6) : c->est_scan_s;
         long long chunk = (long long)std::max(4.0, std::min(8192.0, 0.1 / est));
-        if (probe) chunk = 8;                                                          // (the first pruned scan after full scans rebuilds the neighbour cache)
+        if (probe) chunk = 8;                                                          // (the first pruned scan after full scans rebuilds the delta cache)
         else if (can_prune && !pruned) chunk = std::min<long long>(chunk, 96);         // full scans in AUTO: re-probe soon
         c->probe_due = can_prune && !pruned;                                         // after a full chunk, probe again
         if (max_moves >= 0) chunk = std::min(chunk, max_moves - done);
@@ -740,7 +740,7 @@ extern "C" int tspcuda_tabu_search(tspcuda_ctx *c, int *path, double *cost_inout
     T.cost = (long long)*cost_inout;
     T.best_cost = incumbent_cost >= 9.0e18 ? LLONG_MAX : (incumbent_cost <= -9.0e18 ? LLONG_MIN : (long long)incumbent_cost);
     T.pad = 0;
-    c->nb_valid = false;                               // the tabu kernels move the tour without maintaining the neighbour cache
+    c->nb_valid = false;                               // the tabu kernels move the tour without maintaining the delta cache
     TabuOut h_out{};
     h_out.best_iter = -1;
     long long moves = 0;
