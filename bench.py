@@ -447,7 +447,8 @@ def main():
                                    "peak": peak, "unit": "GB/s", "frac": gbs / peak, "fill_gbs": fill, "frac_of_fill": gbs / fill,
                                    "note": "algorithmic bytes 8 n^2 (write-only, streaming 16-byte stores); peak = MEASURED_PEAKS.json hbm_gbs "
                                            "(copy bandwidth) if present, else the 6551 GB/s measured on this pool; fill_gbs = cudaMemsetAsync "
-                                           "over the same 59 GB buffer in the same job (what a pure writer reaches)"}
+                                           "over the same 59 GB buffer in the same job (what a pure writer reaches: a write-only kernel can exceed the COPY figure, "
+                                           "so frac may be above 1; frac_of_fill is the fraction of the pure-write rate)"}
         except Exception as ex:                                  # e.g. not enough free HBM next to another job
             out["matrix_build"] = {"error": str(ex)}
     if rank == 0 and world == 1:

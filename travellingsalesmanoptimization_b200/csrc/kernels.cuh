@@ -262,12 +262,16 @@ __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int 
             } else { V.o8[tq] ^= 1; V.o8[tp] ^= 1; }
         }
     }
-    if (CACHE && t == 0) {                              // a and succ b keep their direction
+    // The three single-thread jobs of a move -- the new edge costs and the end pair (thread 0 above), the stamps of a and
+    // succ b, the middle node -- are chains of dependent loads: three different threads (of different warps where there are
+    // any) take them, so that the longest of them, not their sum, is what the barrier after the move waits for.  a, succ b
+    // (outside the segment) and the middle node are touched by nobody else.
+    if (CACHE && t == nthreads - 1) {                   // a and succ b keep their direction
         const int sb = V.tid[e + 1];
         V.o8[a] = (unsigned char)((V.o8[a] & 1) | (ep << 1));
         V.o8[sb] = (unsigned char)((V.o8[sb] & 1) | (ep << 1));
     }
-    if (CACHE && (L & 1) && t == 0) {                   // the middle node of an odd segment stays in place but turns round too
+    if (CACHE && (L & 1) && t == (nthreads > 32 ? nthreads - 33 : 0)) {   // the middle node of an odd segment stays in place but turns round too
         int m = s + half; if (m >= n) m -= n;
         V.o8[V.tid[m]] ^= 1;
     }
@@ -321,7 +325,11 @@ descend_kernel(TourView V, unsigned long long *key, DescState *st, MoveRec *log,
         unsigned long long *kslot = key + (it & 1);
         if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(kslot, s_key);
         grid.sync();
-        const unsigned long long kbest = *(volatile unsigned long long *)kslot;
+        // one reader per CTA, handed on through shared memory: thousands of warps loading the same word (volatile, so past
+        // L1) queue up at one L2 slice for microseconds (profiles/r02_pruned.md).  s_key is re-armed behind a later barrier.
+        if (threadIdx.x == 0) s_key = *(volatile unsigned long long *)kslot;
+        __syncthreads();
+        const unsigned long long kbest = s_key;
         if (kbest == KEY_EMPTY) {
             if (gtid == 0) st->status = 1;
             break;
@@ -409,7 +417,11 @@ tabu_kernel(TourView V, unsigned long long *key, TabuCtl T, TabuOut *out, long l
         unsigned long long *kslot = key + (k & 1);
         if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(kslot, s_key);
         grid.sync();
-        const unsigned long long kbest = *(volatile unsigned long long *)kslot;
+        // one reader per CTA, handed on through shared memory: thousands of warps loading the same word (volatile, so past
+        // L1) queue up at one L2 slice for microseconds (profiles/r02_pruned.md).  s_key is re-armed behind a later barrier.
+        if (threadIdx.x == 0) s_key = *(volatile unsigned long long *)kslot;
+        __syncthreads();
+        const unsigned long long kbest = s_key;
         int seg_s = -1, seg_e = -1, b = -1;
         if (kbest != KEY_EMPTY) {                    // every pair tabu: no move this iteration (:225)
             const int a = key_a(kbest);
@@ -614,22 +626,79 @@ __device__ __forceinline__ double cost_as_double(int koff) {
 #define TSP_K1_ROWS 8
 #endif
 #ifndef TSP_K1_BLOCK
-#define TSP_K1_BLOCK 256
+#define TSP_K1_BLOCK 128
 #endif
-#ifndef TSP_K1_CTAS
-#define TSP_K1_CTAS 16
-#endif
-// A work unit is TSP_K1_ROWS rows x one CHUNK of columns.  Several rows at a time, so that the column coordinates --
-// which every row needs and which do not fit L1 for large n -- are read from L2 once per row group instead of once per
-// row (ncu on the one-row version: long-scoreboard stalls on those loads dominate, L2->SM traffic is twice the bytes
-// written).  Units are numbered chunk-fastest and dealt out grid-stride, so the CTAs resident at any time write ONE
-// compact band of the matrix (a few hundred MB) instead of eight rows each spread over n / 8 row groups (pla85900:
-// 2368 CTAs x 8 rows x 687 KB = 13 GB of open pages -- measured 0.80 of the copy bandwidth against 0.99 at n = 20 000).
-// Rows of a group have the same 16-byte alignment: consecutive rows when n is even, every other row when n is odd
-// (row i starts at cell i*n).  chunk_pairs: 16-byte cell pairs per unit and row (a multiple of the block size).
+// A work unit is TSP_K1_ROWS rows x one CHUNK of columns, and a CTA does ONE unit (grid = number of units).  Several rows
+// at a time, so that the column coordinates -- which every row needs and which do not fit L1 for large n -- are read from
+// L2 once per row group instead of once per row.  Units are numbered chunk-fastest and the hardware hands CTAs out in
+// index order, so the CTAs resident at any moment write one compact, advancing band of the matrix.  Rounds 1-2 dealt the
+// same units out grid-stride to 16 CTAs per SM: those drift apart, the write front frays, and pla85900 (59 GB) stayed at
+// 0.80-0.86 of the copy bandwidth whatever the occupancy; a persistent grid (lock-step CTAs) was worse still, 0.70.  One
+// unit per CTA writes at the rate cudaMemset reaches on the same buffer (profiles/r02_k1.md: 7.3 TB/s, 1.11 x the
+// measured copy bandwidth).  Rows of a group have the same 16-byte alignment: consecutive rows when n is even, every
+// other row when n is odd (row i starts at cell i*n).  chunk_pairs: 16-byte cell pairs per unit and row (a multiple of
+// the block size; 4 block-wide trips measured best).  TSP_K1_ROT: CTA b starts with trip b mod trips (measured +1-3 %).
 #ifndef TSP_K1_MINB
 #define TSP_K1_MINB 1
 #endif
+#ifndef TSP_K1_ROT
+#define TSP_K1_ROT 1
+#endif
+// The two cells (row, column j) and (row, column j + 1) as doubles.  Metrics with a packed scan form compute both costs
+// with FP32x2 instructions (K2 with the roles swapped: (xj - xa)^2 == (xa - xj)^2 bit for bit); the cost leaves the
+// sequence as the bit pattern 0xCB000000 + cost, which one integer subtraction and the 2^52 trick turn into a double.
+template <class M>
+__device__ __forceinline__ double2 k1_two_cells(const double2 pr, const double2 p0, const double2 p1) {
+    if constexpr (M::SCAN_XOR == SCAN_FLIP) {
+        int k0, k1;
+        M::K2(p0.x, p0.y, p1.x, p1.y, pr.x, pr.y, k0, k1);
+        return make_double2(__hiloint2double(0x43300000, (int)((unsigned)k0 - ((unsigned)KOFF ^ SCAN_FLIP))) - 4503599627370496.0,
+                            __hiloint2double(0x43300000, (int)((unsigned)k1 - ((unsigned)KOFF ^ SCAN_FLIP))) - 4503599627370496.0);
+    } else {
+        return make_double2(cost_as_double(M::K(pr.x, pr.y, p0.x, p0.y)), cost_as_double(M::K(pr.x, pr.y, p1.x, p1.y)));
+    }
+}
+
+// One unit: RB rows x the column pairs [t0, t1).  The loop body has NO data-dependent control flow -- the diagonal is
+// computed like any other cell (cost 0) and overwritten with -1.0 afterwards by the very thread that stored it (program
+// order, same address) -- so the 2 * RB cost chains of a trip are independent straight-line code the scheduler can
+// interleave.  (Round 1/2's loop selected -1.0 per cell: nvcc turned each select into a branch around the cost sequence,
+// leaving 16 serial dependent chains per trip, 27 instructions per cell and `wait` as the top stall, r02_ncu.md.)
+template <class M, bool FULL_GROUP>
+__device__ __forceinline__ void k1_unit(const double2 *__restrict__ xy, int n, double *__restrict__ out, int first, int s, int off,
+                                        int t0, int t1) {
+    constexpr int RB = TSP_K1_ROWS;
+    double2 pr[RB];
+#pragma unroll
+    for (int k = 0; k < RB; ++k) pr[k] = xy[FULL_GROUP ? first + k * s : min(first + k * s, n - 1)];
+    double *base = out + (size_t)first * (size_t)n + off;
+    const size_t rstride = (size_t)s * (size_t)n;
+#if TSP_K1_ROT
+    const int T = (t1 - t0 + TSP_K1_BLOCK - 1) / TSP_K1_BLOCK, rot = (int)(blockIdx.x % (unsigned)T);
+    for (int m = 0; m < T; ++m) {
+        int trip = m + rot; if (trip >= T) trip -= T;
+        const int t = t0 + trip * TSP_K1_BLOCK + threadIdx.x;
+        if (t >= t1) continue;
+#else
+    for (int t = t0 + threadIdx.x; t < t1; t += TSP_K1_BLOCK) {
+#endif
+        const double2 p0 = xy[off + 2 * t], p1 = xy[off + 2 * t + 1];
+        double *cell = base + 2 * (size_t)t;
+#pragma unroll
+        for (int k = 0; k < RB; ++k) {
+            const double2 v = k1_two_cells<M>(pr[k], p0, p1);
+            if (FULL_GROUP || first + k * s < n)
+                __stcs(reinterpret_cast<double2 *>(cell + k * rstride), v);   // written once: streaming store (plain / .wt / .cg stores: 0.57-0.72)
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {                       // diagonal cells of this unit, each by the thread that wrote it above
+        const int i = first + k * s, ti = (i - off) >> 1;
+        if (i >= off && ti >= t0 && ti < t1 && ((ti - t0) % TSP_K1_BLOCK) == (int)threadIdx.x && (FULL_GROUP || i < n))
+            out[(size_t)i * (size_t)n + i] = -1.0;
+    }
+}
+
 template <class M>
 __global__ void __launch_bounds__(TSP_K1_BLOCK, TSP_K1_MINB)
 cost_matrix_kernel(const double2 *__restrict__ xy, int n, double *__restrict__ out, int chunk_pairs) {
@@ -643,24 +712,10 @@ cost_matrix_kernel(const double2 *__restrict__ xy, int n, double *__restrict__ o
         const int g = (int)(u / nchunks), ch = (int)(u - (long long)g * nchunks);
         const int first = (g / s) * span + (g % s);      // rows first, first + s, ...
         const int off = (int)(((size_t)first * (size_t)n) & 1);
-        double2 pr[RB];
-#pragma unroll
-        for (int k = 0; k < RB; ++k) pr[k] = xy[min(first + k * s, n - 1)];
         const int npairs = (n - off) >> 1;
-        const int t1 = min(npairs, (ch + 1) * chunk_pairs);
-        for (int t = ch * chunk_pairs + threadIdx.x; t < t1; t += blockDim.x) {
-            const int j = off + 2 * t;
-            const double2 p0 = xy[j], p1 = xy[j + 1];
-#pragma unroll
-            for (int k = 0; k < RB; ++k) {
-                const int i = first + k * s;
-                if (i < n) {
-                    const double v0 = (j == i) ? -1.0 : cost_as_double(M::K(pr[k].x, pr[k].y, p0.x, p0.y));
-                    const double v1 = (j + 1 == i) ? -1.0 : cost_as_double(M::K(pr[k].x, pr[k].y, p1.x, p1.y));
-                    __stcs(reinterpret_cast<double2 *>(out + (size_t)i * (size_t)n + j), make_double2(v0, v1));   // written once: streaming store
-                }
-            }
-        }
+        const int t0 = ch * chunk_pairs, t1 = min(npairs, t0 + chunk_pairs);
+        if (first + (RB - 1) * s < n) k1_unit<M, true>(xy, n, out, first, s, off, t0, t1);
+        else k1_unit<M, false>(xy, n, out, first, s, off, t0, t1);
         if (ch == 0 && threadIdx.x < RB) {               // the unpaired first / last cell of each row
             const int k = threadIdx.x, i = first + k * s;
             if (i < n) {

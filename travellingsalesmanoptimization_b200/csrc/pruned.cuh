@@ -510,9 +510,10 @@ __device__ __forceinline__ void pruned_phase1(const TourView &V, const SpatialGr
 constexpr int NB_WORDS = 16;                   // ints per node line
 constexpr int NB_CAP = 5;                      // records held in the line itself
 constexpr int NB_CF_STALE = 1023, NB_CF_HEAP = 1022;          // header: never searched / list in the heap (words 1, 2: start, count)
-constexpr int NB_HDR_STALE = NB_CF_STALE;
+constexpr int NB_HDR_STALE = NB_CF_STALE;      // (bits 10..: how often a stale node's giant box has been evaluated without caching, see giant_age)
 constexpr int NB_DIRTY = (int)0x80000000;      // d0 of a record that must be recomputed before use
 constexpr int NB_GIANT = 512;                  // a search box with more nodes than this is not walked by one warp: giant_phase()
+constexpr int NB_FLAT = 64;                    // a search box with at most this many nodes is walked in one step (rebuild_list)
 constexpr int NB_EPOCHS = 126;                 // epochs 0..125 cycle; 126: "no move yet"; 127: a node no move has touched
 constexpr int NB_EP_NONE = 126, NB_EP_INIT = 127;
 
@@ -523,6 +524,9 @@ struct NbCache {
                             // records, [4]: nodes whose list lives in the heap (8 ints)
     unsigned char *cnt8;    // [n] non-zero: the node's line must be looked at (records, stale); zero: nothing there
     int heap_cap;
+    int giant_age;          // a GIANT search box is only evaluated (as in round 1), not cached, the first giant_age times the node is
+                            // searched with the same tour edges: the three instance-spanning edges of a VNS kick are gone after
+                            // two or three moves -- caching their ~n records each only fills the heap.  0: cache at once (descents).
 };
 __host__ __device__ inline int nb_cnt8_stride(int n) { return (n + 127) & ~127; }      // read four bytes at a time
 // records of heap per node of the instance (default NB_HEAP_PER_NODE; TSPCUDA_NB_HEAP for tests that want the "no room" and
@@ -626,6 +630,10 @@ constexpr unsigned AT_DIRTY = 1, AT_NODE = 2;
 constexpr unsigned EV_NODEIDS = 4;             // evaluation record {u, w, -, 3 | EV_NODEIDS}: node ids instead of {p, w, K, type}
 constexpr int NB_RING = 256;                   // per-warp ring of pending node ids (shared memory): 31 left over + 128 new at most
 constexpr int NB_HU = 4;                       // heap records in flight per lane
+#ifndef TSP_NB_SPLIT_WARPS
+#define TSP_NB_SPLIT_WARPS 256
+#endif
+constexpr int NB_SPLIT_WARPS = TSP_NB_SPLIT_WARPS;   // cooperating warps from which on the four searching warps take no share of the stream
 
 struct ScanAcc {
     unsigned long long bestkey;
@@ -681,7 +689,7 @@ __device__ __forceinline__ bool node_box(const SpatialGrid &G, const NodeCtx &c,
 // six to a few dozen records do not leave dead records behind.
 // SETTLE: only bring the cache up to date (no candidates): used when a launch ends right after a move.
 template <class M, int NE, bool SETTLE>
-__device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGrid &G, const PosPatch &F, const NbCache &C, int hp, int u,
+__device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGrid &G, const PosPatch &F, const NbCache &C, int hp, int u, bool fresh,
                                              unsigned long long *qctr, BigBox *boxes, uint4 *ebuf, ScanAcc &a) {
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
@@ -696,7 +704,10 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
     const int nrows = any ? cy1 - cy0 + 1 : 0;
     const int thr = max(c.dnp, c.dnm);
     int count = 0, tot = 0;
-    for (int r = lane; r < nrows; r += 32) tot += G.cell_start[(cy0 + r) * G.W + cx1 + 1] - G.cell_start[(cy0 + r) * G.W + cx0];
+    int rlo = 0, rcnt = 0;                                         // lane r: the cell-sorted range of box row r
+    if (lane < nrows) { rlo = G.cell_start[(cy0 + lane) * G.W + cx0]; rcnt = G.cell_start[(cy0 + lane) * G.W + cx1 + 1] - rlo; }
+    tot = rcnt;
+    for (int r = lane + 32; r < nrows; r += 32) tot += G.cell_start[(cy0 + r) * G.W + cx1 + 1] - G.cell_start[(cy0 + r) * G.W + cx0];
     tot = __reduce_add_sync(FULL, tot);
     if (tot > NB_GIANT) {
         // A long tour edge (a nearest-neighbour tour has a few hundred, a VNS kick makes three): thousands of candidates.
@@ -705,6 +716,22 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
         // settling there is no such barrier: the node stays stale for the next launch.
         if (had)
             for (int j = lane; j < ocount; j += 32) C.heap[ostart + j].x = -1;
+        // fresh: the node's tour edges have just changed (one of the four nodes of the last move); otherwise the header says
+        // how often this box has been evaluated without caching since
+        const int age = (!fresh && (h0 & 0x3FF) == NB_CF_STALE) ? (h0 >> 10) : 0;
+        if (!SETTLE && age < C.giant_age) {                        // evaluate only: queued without a heap run, the node stays stale
+            if (lane == 0) {
+                NBSTAT(0, 1); NBSTAT(7, tot); NBSTAT(1, 1);
+                if (had) { atomicAdd(C.heap_next + 3, -ocount); atomicAdd(C.heap_next + 4, -1); }
+                line[0] = NB_CF_STALE | ((age + 1) << 10); C.cnt8[u] = 1;
+                const unsigned long long old = atomicAdd(qctr, (1ull << 40) | (unsigned long long)nrows);
+                BigBox bx;
+                bx.p = c.p; bx.cy0 = cy0; bx.cx0 = cx0; bx.cx1 = cx1; bx.nrows = nrows; bx.pad = -1;
+                bx.base = (long long)(old & PR_UNIT_MASK);
+                boxes[old >> 40] = bx;
+            }
+            return;
+        }
         int start = -1;
         if (!SETTLE && lane == 0) start = *(volatile int *)(C.heap_next + hp) > C.heap_cap ? -1 : atomicAdd(C.heap_next + hp, tot);
         start = __shfl_sync(FULL, start, 0);
@@ -740,17 +767,58 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
         }
         return;
     }
-    tot = 0;
-    for (int r = 0; r < nrows; ++r) {
-        const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
-        tot += hi - lo;
-        for (int k0 = lo; k0 < hi; k0 += 32) {
-            const int k = min(k0 + lane, hi - 1);
-            const double2 cw = G.cxy[k];
-            const int w = G.cnode[k];
-            const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
-            const bool pass = k0 + lane < hi && K < thr && w != u && w != c.su && w != c.pu;          // tour neighbours: refinment.c:55
-            count += __popc(__ballot_sync(FULL, pass));
+    // The usual box (a node with two short tour edges) holds a few dozen nodes in two to five cell rows.  Walked row by row
+    // it costs one round trip to L2 per row and pass; FLAT: the (at most NB_FLAT) candidates are numbered across the rows
+    // (prefix sums of the row sizes, in registers), every lane loads its one or two candidates at once, and what the first
+    // pass found stays in registers for the second: the search of one of the four nodes of a move -- the longest dependent
+    // chain of a whole-GPU scan -- shrinks from 3 + 3 x rows round trips to 6.
+#ifdef TSP_NB_NOFLAT
+    const bool flat = false;                                       // (measurements: the row-by-row walk for every box)
+#else
+    const bool flat = nrows <= 32 && tot <= NB_FLAT;
+#endif
+    int fw[NB_FLAT / 32], fK[NB_FLAT / 32];
+    unsigned fm[NB_FLAT / 32];
+    if (flat) {
+        int pre = rcnt;                                            // inclusive prefix of the row sizes
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) { const int v = __shfl_up_sync(FULL, pre, off); if (lane >= off) pre += v; }
+        int row[NB_FLAT / 32];
+#pragma unroll
+        for (int j = 0; j < NB_FLAT / 32; ++j) row[j] = 0;
+        for (int r = 0; r + 1 < nrows; ++r) {                      // row of candidate idx: the first whose prefix exceeds it (empty rows skipped)
+            const int pr = __shfl_sync(FULL, pre, r);
+#pragma unroll
+            for (int j = 0; j < NB_FLAT / 32; ++j) row[j] += (lane + 32 * j >= pr) ? 1 : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < NB_FLAT / 32; ++j) {
+            const int idx = lane + 32 * j;
+            const int k = __shfl_sync(FULL, rlo, row[j]) + idx - (__shfl_sync(FULL, pre, row[j]) - __shfl_sync(FULL, rcnt, row[j]));
+            bool pass = false;
+            fw[j] = 0; fK[j] = 0;
+            if (idx < tot) {
+                const double2 cw = G.cxy[k];
+                fw[j] = G.cnode[k];
+                fK[j] = M::K(c.u.x, c.u.y, cw.x, cw.y);
+                pass = fK[j] < thr && fw[j] != u && fw[j] != c.su && fw[j] != c.pu;                  // tour neighbours: refinment.c:55
+            }
+            fm[j] = __ballot_sync(FULL, pass);
+            count += __popc(fm[j]);
+        }
+    } else {
+        tot = 0;
+        for (int r = 0; r < nrows; ++r) {
+            const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
+            tot += hi - lo;
+            for (int k0 = lo; k0 < hi; k0 += 32) {
+                const int k = min(k0 + lane, hi - 1);
+                const double2 cw = G.cxy[k];
+                const int w = G.cnode[k];
+                const int K = M::K(c.u.x, c.u.y, cw.x, cw.y);
+                const bool pass = k0 + lane < hi && K < thr && w != u && w != c.su && w != c.pu;          // tour neighbours: refinment.c:55
+                count += __popc(__ballot_sync(FULL, pass));
+            }
         }
     }
     if (lane == 0) { NBSTAT(0, 1); NBSTAT(7, tot); a.ncand += tot; }
@@ -781,6 +849,32 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
     }
     const int ou = V.o8[u];
     int stored = 0;
+    if (flat) {
+        int ds[NB_FLAT / 32], df[NB_FLAT / 32], ow[NB_FLAT / 32];
+#pragma unroll
+        for (int j = 0; j < NB_FLAT / 32; ++j) { ds[j] = 0; df[j] = 0; ow[j] = ((fm[j] >> lane) & 1u) ? V.o8[fw[j]] : 0; }
+#pragma unroll
+        for (int j = 0; j < NB_FLAT / 32; ++j)
+            if ((fm[j] >> lane) & 1u) record_deltas<M>(V, F, c, fw[j], fK[j], ds[j], df[j]);
+#pragma unroll
+        for (int j = 0; j < NB_FLAT / 32; ++j) {
+            if (fm[j] == 0) continue;                              // warp-uniform
+            const bool pass = (fm[j] >> lane) & 1u;
+            if (pass) {
+                const int o = stored + __popc(fm[j] & lt);
+                const bool rel = ((ou ^ ow[j]) & 1) != 0;
+                const int d0 = rel ? df[j] : ds[j], d1 = rel ? ds[j] : df[j];
+                if (count <= NB_CAP) { line[1 + 3 * o] = fw[j]; line[2 + 3 * o] = d0; line[3 + 3 * o] = d1; }
+                else if (start >= 0) C.heap[start + o] = make_int4(u, fw[j], d0, d1);
+            }
+            stored += __popc(fm[j]);
+            if (!SETTLE) {
+                const bool hit = pass && ds[j] <= a.best;
+                if (hit) a.best = ds[j];
+                eval_push<M, NE>(V, F, ebuf, a, hit, c.p, fw[j], fK[j]);
+            }
+        }
+    } else
     for (int r = 0; r < nrows; ++r) {
         const int lo = G.cell_start[(cy0 + r) * G.W + cx0], hi = G.cell_start[(cy0 + r) * G.W + cx1 + 1];
         for (int k0 = lo; k0 < hi; k0 += 32) {
@@ -861,7 +955,7 @@ __device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPat
         while (nm) {
             const int src = __ffs(nm) - 1;
             nm &= nm - 1;
-            rebuild_list<M, NE, SETTLE>(V, G, F, C, hp, (int)__shfl_sync(FULL, e.x, src), qctr, boxes, ebuf, a);
+            rebuild_list<M, NE, SETTLE>(V, G, F, C, hp, (int)__shfl_sync(FULL, e.x, src), __shfl_sync(FULL, e.y, src) != 0u, qctr, boxes, ebuf, a);
         }
     }
     __syncwarp();
@@ -886,23 +980,29 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
     const int lane = threadIdx.x & 31;
     const unsigned lt = (1u << lane) - 1;
     uint4 *ebuf = wbuf + AB_CAP;
-    // the four nodes of the last move: one designated warp each (their searches are the longest dependent chains of a scan)
+    // the four nodes of the last move: one designated warp each (their searches are the longest dependent chains of a scan).
+    // With many cooperating warps (the whole GPU on one descent) a warp's share of the stream is one or two records -- a few
+    // dependent loads -- and the search is the longer chain: the four warps then ONLY search, at once, and the stream is
+    // dealt out over the others (sgw of snw); with few warps (one CTA per descent) the stream dominates and all warps take part.
+    const bool split = nwarps >= NB_SPLIT_WARPS && F.node0 >= 0;                             // the same for every cooperating warp
+    const int sgw = split ? gw - 4 : gw, snw = split ? nwarps - 4 : nwarps;
     if (gw < 4) {
         const int fu = gw == 0 ? F.node0 : gw == 1 ? F.node1 : gw == 2 ? F.node2 : F.node3;
         if (fu >= 0) {
-            if (lane == 0) wbuf[0] = make_uint4((unsigned)fu, 0u, AT_NODE, 0u);
+            if (lane == 0) wbuf[0] = make_uint4((unsigned)fu, 1u, AT_NODE, 0u);              // .y = 1: fresh edges
             acount = 1;
         }
     }
+    if (!(split && gw < 4)) {
     // ---- the heap: every cooperating thread a strided share of the records, NB_HU loads in flight per lane (a warp that
     // waits for one 16-byte record at a time is bound by the memory latency, not by the bandwidth)
-    for (int k0 = gw * 32; k0 < hsnap; k0 += nwarps * 32 * NB_HU) {
+    for (int k0 = sgw * 32; k0 < hsnap; k0 += snw * 32 * NB_HU) {
         if (acount > AB_CAP - 32 * NB_HU) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a); acount = 0; }      // warp-uniform, rare
         if (!SETTLE && a.ecount > EB_CAP - 32 * NB_HU) a = flush_records<M, NE>(V, F, ebuf, a);
         int4 r[NB_HU];
 #pragma unroll
         for (int j = 0; j < NB_HU; ++j) {
-            const int k = k0 + j * nwarps * 32 + lane;
+            const int k = k0 + j * snw * 32 + lane;
             r[j] = make_int4(-1, 0, 0, 0);
             if (k < hsnap) r[j] = C.heap[k];
         }
@@ -934,7 +1034,7 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
                 const bool f = (dirty >> j) & 1u;
                 const unsigned m = __ballot_sync(FULL, f);
                 if (f) {
-                    const unsigned long long ra = (unsigned long long)(&C.heap[k0 + j * nwarps * 32 + lane].y);
+                    const unsigned long long ra = (unsigned long long)(&C.heap[k0 + j * snw * 32 + lane].y);
                     wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)r[j].x, (unsigned)r[j].y, (unsigned)(ra & 0xFFFFFFFFu) | AT_DIRTY, (unsigned)(ra >> 32));
                 }
                 acount += __popc(m);
@@ -959,10 +1059,10 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
     // ---- the lines: a contiguous range of nodes per warp; count bytes first, non-empty lines 32 per step
     // many warps, few nodes each (the whole GPU on one descent): 32-node ranges, so that every warp gets some; otherwise
     // ranges in multiples of 128 nodes, whose count bytes are read four per lane
-    const int per = (n + nwarps - 1) / nwarps;
+    const int per = (n + snw - 1) / snw;
     const bool wide = per > 64;
     const int chunk = wide ? (per + 127) & ~127 : (per + 31) & ~31;
-    const int lo = min(n, gw * chunk), hi = min(n, lo + chunk);
+    const int lo = min(n, sgw * chunk), hi = min(n, lo + chunk);
     int base = lo, head = 0, tail = 0;
     for (;;) {
         while (base < hi && tail - head < 32) {                    // refill
@@ -1057,6 +1157,7 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
             }
         }
     }
+    }   // !(split && gw < 4)
     if (acount > 0) a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a);
     if (!SETTLE && a.ecount > 0) a = flush_records<M, NE>(V, F, ebuf, a);
     best = a.best; bestkey = a.bestkey; ncand = a.ncand;
@@ -1120,16 +1221,21 @@ __device__ __noinline__ void giant_phase(TourView V, const SpatialGrid *Gp, PosP
                 w = G.cnode[k];
                 K = M::K(c.u.x, c.u.y, cw.x, cw.y);
                 pass = K < thr && w != u && w != c.su && w != c.pu;
-                int4 rec = make_int4(-1, 0, 0, 0);
-                if (pass) {
-                    record_deltas<M>(V, F, c, w, K, dsame, dflip);
-                    const bool rel = ((ou ^ V.o8[w]) & 1) != 0;
-                    rec = make_int4(u, w, rel ? dflip : dsame, rel ? dsame : dflip);
+                if (b.pad >= 0) {
+                    int4 rec = make_int4(-1, 0, 0, 0);
+                    if (pass) {
+                        record_deltas<M>(V, F, c, w, K, dsame, dflip);
+                        const bool rel = ((ou ^ V.o8[w]) & 1) != 0;
+                        rec = make_int4(u, w, rel ? dflip : dsame, rel ? dsame : dflip);
+                    }
+                    C.heap[b.pad + rowoff + (k - lo)] = rec;
                 }
-                C.heap[b.pad + rowoff + (k - lo)] = rec;
             }
-            const bool hit = pass && dsame <= a.best;
-            if (hit) a.best = dsame;
+            bool hit = pass;                                       // a box without a run (giant_age): every passing candidate is evaluated exactly
+            if (b.pad >= 0) {
+                hit = pass && dsame <= a.best;
+                if (hit) a.best = dsame;
+            }
             eval_push<M, NE>(V, F, ebuf, a, hit, c.p, w, K);
         }
         rowoff += hi - lo;
@@ -1144,8 +1250,9 @@ __device__ __noinline__ void giant_phase(TourView V, const SpatialGrid *Gp, PosP
 // ones (one CTA per descent; proportionally more for a cluster or the whole GPU), or the heap is three quarters full, the
 // nodes whose lists live in the heap are declared stale and the heap starts over at the other, zeroed, counter.  Lists
 // held in the lines are not affected.
-__device__ __forceinline__ int heap_checkpoint(const NbCache &C, int n, int t, int nthreads, int &hp) {
-    const int hn = *(volatile int *)(C.heap_next + hp), live = *(volatile int *)(C.heap_next + 3);
+// hn, live: the counters heap_next[hp] and heap_next[3] as they stand between those barriers (read by the caller: one thread
+// per CTA and a shared-memory broadcast where a whole grid cooperates)
+__device__ __forceinline__ int heap_checkpoint(const NbCache &C, int n, int t, int nthreads, int &hp, int hn, int live) {
     const long long teams = max(1, nthreads >> 10);
     if (hn <= C.heap_cap / 4 * 3 && (long long)hn - live <= teams * live + (n >> 1)) return min(hn, C.heap_cap);
     for (int u = t; u < n; u += nthreads) {
@@ -1221,6 +1328,12 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
     __shared__ unsigned long long s_key;
     __shared__ int s_best;
     __shared__ int s_ring[WARPS][NB_RING];
+    // What every thread of the grid needs to know after a barrier -- the winning key, the giant-box counter, the heap
+    // counters -- is read by ONE thread per CTA and handed on through shared memory: 4 736 warps loading the same word
+    // (volatile, so past L1) queue up at one L2 slice for microseconds, and there were three such rounds, one after the
+    // other, per move (profiles/r02_pruned.md).
+    __shared__ unsigned long long s_bq, s_bk;
+    __shared__ int s_bhn, s_blive;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int gtid = blockIdx.x * BLK + threadIdx.x;
     const int gsize = gridDim.x * BLK;
@@ -1276,8 +1389,15 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
         if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(kslot, s_key);
         grid.sync();
         PHASE_MARK(0)
+        if (threadIdx.x == 0) {
+            s_bq = *(volatile unsigned long long *)qctr; s_bk = *(volatile unsigned long long *)kslot;
+            s_bhn = *(volatile int *)(C.heap_next + hp); s_blive = *(volatile int *)(C.heap_next + 3);
+        }
+        __syncthreads();
+        unsigned long long kbest = s_bk;
+        int hn = s_bhn, live = s_blive;
         {   // giant search boxes met in this scan (rare): all warps fill their heap runs now, one more barrier
-            const unsigned long long q = *(volatile unsigned long long *)qctr;
+            const unsigned long long q = s_bq;
             if (q >> 40) {
                 bestkey = KEY_EMPTY;
                 ncand = 0;
@@ -1292,21 +1412,26 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
                 if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(kslot, s_key);
                 grid.sync();
                 if (gtid == 0) *qctr = 0;
+                if (threadIdx.x == 0) {                          // (everybody has read the first values: barriers in between)
+                    s_bk = *(volatile unsigned long long *)kslot;
+                    s_bhn = *(volatile int *)(C.heap_next + hp); s_blive = *(volatile int *)(C.heap_next + 3);
+                }
+                __syncthreads();
+                kbest = s_bk; hn = s_bhn; live = s_blive;
                 PHASE_MARK(1)
             }
         }
-        const unsigned long long kbest = *(volatile unsigned long long *)kslot;
         if (kbest == KEY_EMPTY) {
             if (gtid == 0) st->status = 1;
             optimum = true;
             break;
         }
-        hsnap = heap_checkpoint(C, V.n, gtid, gsize, hp);
+        hsnap = heap_checkpoint(C, V.n, gtid, gsize, hp, hn, live);
         ep = (int)((moves0 + it) % NB_EPOCHS);
         const int a = key_a(kbest), b = key_b(kbest), delta = key_delta(kbest);
         int seg_s, seg_e;
         apply_move<M, true>(V, a, b, gtid, gsize, false, seg_s, seg_e, ep);
-        if (gtid == 0) {
+        if (gtid == 96) {                                // the bookkeeping: not the thread that carries the move's own chains (apply_move)
             key[(it + 1) & 1] = KEY_EMPTY;
             const long long lc = st->log_count;
             if (lc < log_cap) { log[lc].a = a; log[lc].b = b; log[lc].delta = delta; log[lc].reserved = 0; }
@@ -1349,7 +1474,7 @@ tabu_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, TabuCtl T
     constexpr int NC1 = BLK > 512 ? PR_NC_BIG : PR_NC;
     constexpr int NE = BLK > 512 ? 2 : 4;
     cg::grid_group grid = cg::this_grid();
-    __shared__ unsigned long long s_key;
+    __shared__ unsigned long long s_key, s_bq, s_bk;      // s_bq, s_bk: one reader per CTA of the words the whole grid needs (see K7)
     __shared__ long long s_cost, s_bestcost, s_moves;
     __shared__ int s_bestiter, s_lastdelta;
     const int n = V.n;
@@ -1385,13 +1510,17 @@ tabu_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, TabuCtl T
             const int h = (B + 1) / 2;
             pruned_phase1<M, NC1, NE, L, true>(V, G, F, gtid, gsize, qctr, boxes, wbuf, best, bestkey, ncand, h);
             grid.sync();
-            pruned_phase2<M, NE, true>(V, G, F, gw, Wtot, *(volatile unsigned long long *)qctr, boxes, wbuf, best, bestkey, ncand, h);
+            if (threadIdx.x == 0) s_bq = *(volatile unsigned long long *)qctr;
+            __syncthreads();
+            pruned_phase2<M, NE, true>(V, G, F, gw, Wtot, s_bq, boxes, wbuf, best, bestkey, ncand, h);
             bestkey = warp_min_key(bestkey);
             if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key, bestkey);
             __syncthreads();
             if (threadIdx.x == 0 && s_key != KEY_EMPTY) atomicMin(key + slot, s_key);
             grid.sync();
-            kbest = *(volatile unsigned long long *)(key + slot);
+            if (threadIdx.x == 0) s_bk = *(volatile unsigned long long *)(key + slot);
+            __syncthreads();
+            kbest = s_bk;
             if (gtid == 0) { key[slot ^ 1] = KEY_EMPTY; *qctr = 0; }
             slot ^= 1;
             if (kbest != KEY_EMPTY) break;
@@ -1504,6 +1633,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     NbCache C;
     C.lines = S.nb + slot * (size_t)n * NB_WORDS;
     C.heap_cap = S.heap_cap;
+    C.giant_age = 0;
     C.heap = S.nb_heap + slot * (size_t)C.heap_cap;
     C.heap_next = S.nb_next + slot * 8;
     C.cnt8 = S.cnt8 + slot * (size_t)nb_cnt8_stride(n);
@@ -1578,7 +1708,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
                 for (int r = 0; r < CL; ++r) kbest = min(kbest, *cluster.map_shared_rank(&s_key_[par], r));
             }
             if (kbest == KEY_EMPTY) break;                      // local optimum (refinment.c:27)
-            hsnap = heap_checkpoint(C, n, t, TEAM, hp);        // between the last two barriers: nobody changes it here
+            hsnap = heap_checkpoint(C, n, t, TEAM, hp, *(volatile int *)(C.heap_next + hp), *(volatile int *)(C.heap_next + 3));   // between the last two barriers: nobody changes it here
             ep = (int)(moves % NB_EPOCHS);
             const int a = key_a(kbest), b = key_b(kbest);
             int seg_s, seg_e;

@@ -101,6 +101,7 @@ struct tspcuda_ctx {
     unsigned char *d_cnt8 = nullptr; //   and a byte-per-node flag array for nb_mark_*_kernel
     unsigned char *d_nbflag = nullptr;
     int nb_heap_per_node = NB_HEAP_PER_NODE;
+    int nb_giant_age = 0;                 // NbCache::giant_age of the next descents (the VNS loop raises it)
     long long nb_moves = 0;          // moves the delta cache has followed since it was last invalidated (epoch numbering)
     bool nb_valid = false;           // false: the tour changed behind the cache's back (upload, full-scan or tabu moves)
     int *d_stop = nullptr;           // time-limit flag of the batched multi-start kernels, raised through aux_stream
@@ -412,7 +413,7 @@ static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max
     BigBox *boxes = c->d_boxes;
     uint4 *wbuf = c->d_wbuf;
     NbCache nb;
-    nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(c->n, c->nb_heap_per_node);
+    nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(c->n, c->nb_heap_per_node); nb.giant_age = c->nb_giant_age;
     if (!c->nb_valid) {                                        // the tour was replaced or moved by another kernel: every list is stale
         nb_invalidate_kernel<<<grid_for(c->n, 4 * c->num_sms), 256, 0, c->stream>>>(nb, c->d_o8, c->n);
         c->stats.kernel_launches += 1;
@@ -1265,12 +1266,16 @@ extern "C" int tspcuda_cost_matrix_device(tspcuda_ctx *c, double *ms_out) {
     if (e) return e;
     const size_t n = (size_t)c->n;
     if (!c->d_matrix) CK(cudaMalloc(&c->d_matrix, sizeof(double) * n * n));
-    // columns per work unit: 4 block-wide trips (2048 cells = 16 KB per row); TSPCUDA_K1_CHUNK (in trips, 0 = whole rows) for measurements
-    int trips = 4;
+    // columns per work unit: 4 block-wide trips (1024 cells = 8 KB per row); one unit per CTA, handed out in index order by the
+    // hardware (kernels.cuh).  For measurements: TSPCUDA_K1_CHUNK (trips, 0 = whole rows), TSPCUDA_K1_CTAS (> 0: that many
+    // CTAs per SM dealing the units out grid-stride, the round-1/2 launch shape).
+    int trips = 4, ctas = 0;
     if (const char *e2 = getenv("TSPCUDA_K1_CHUNK")) trips = atoi(e2);
+    if (const char *e2 = getenv("TSPCUDA_K1_CTAS")) ctas = atoi(e2);
     const int chunk_pairs = trips > 0 ? trips * TSP_K1_BLOCK : (int)((n / 2 + TSP_K1_BLOCK) / TSP_K1_BLOCK) * TSP_K1_BLOCK;
-    const size_t nunits = ((n + TSP_K1_ROWS - 1) / TSP_K1_ROWS + 1) * std::max<size_t>(1, (n / 2 + chunk_pairs - 1) / chunk_pairs);
-    const int grid = (int)std::max<size_t>(1, std::min<size_t>(nunits, (size_t)c->num_sms * TSP_K1_CTAS));
+    const size_t k1_s = (n & 1) ? 2 : 1, k1_span = TSP_K1_ROWS * k1_s;
+    const size_t nunits = ((n + k1_span - 1) / k1_span) * k1_s * std::max<size_t>(1, (n / 2 + chunk_pairs - 1) / chunk_pairs);   // as the kernel counts them
+    const int grid = (int)std::max<size_t>(1, std::min<size_t>(nunits, ctas > 0 ? (size_t)c->num_sms * ctas : (size_t)0x7fffffff));
     CK(cudaEventRecord(c->ev0, c->stream));
     DISPATCH_METRIC(c->metric, (cost_matrix_kernel<M><<<grid, TSP_K1_BLOCK, 0, c->stream>>>(c->d_xy, c->n, c->d_matrix, chunk_pairs)));
     CK(cudaEventRecord(c->ev1, c->stream));
@@ -1573,6 +1578,11 @@ static int vns_search_impl(tspcuda_ctx *c, int *path, double *cost_inout, int n_
     c->tour_loaded = false;
     e = tspcuda_tour_upload(c, path);                          // validates the tour; device order starts at node 0
     if (e) return e;
+    // the descents of this loop start from kicked local optima: giant search boxes are evaluated, not cached, the first few
+    // times (pruned.cuh, NbCache::giant_age; TSPCUDA_NB_GIANT_AGE for measurements)
+    struct AgeGuard { tspcuda_ctx *c; ~AgeGuard() { c->nb_giant_age = 0; } } age_guard{c};
+    c->nb_giant_age = 5;
+    if (const char *ga = getenv("TSPCUDA_NB_GIANT_AGE")) c->nb_giant_age = std::max(0, std::min(1000, atoi(ga)));
     std::vector<int> ord(n), tmp(n), best_ord, before(n), where(n), changed;
     const auto t_begin = std::chrono::steady_clock::now();
     auto elapsed = [&]() { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_begin).count(); };
@@ -1630,7 +1640,7 @@ static int vns_search_impl(tspcuda_ctx *c, int *path, double *cost_inout, int n_
             CK(scratch_get(c, SC_NB_LIST, sizeof(int) * (size_t)n, d_list));
             CK(cudaMemcpyAsync(d_list.p, changed.data(), sizeof(int) * changed.size(), cudaMemcpyHostToDevice, c->stream));
             NbCache nb;
-            nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(n, c->nb_heap_per_node);
+            nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(n, c->nb_heap_per_node); nb.giant_age = 0;
             const int cn = (int)changed.size();
             nb_mark_nodes_kernel<<<1, 256, 0, c->stream>>>(nb, d_list.as<int>(), cn, c->d_nbflag, 1);
             nb_mark_records_kernel<<<grid_for(n, 4 * c->num_sms), 256, 0, c->stream>>>(nb, c->d_nbflag, n);
