@@ -23,6 +23,8 @@
 // units -- a cell row of a box is one contiguous range of the cell-sorted node array -- and the units
 // are split evenly over all warps of the grid, lanes striding over the nodes of a row.
 #pragma once
+#include <type_traits>
+
 #include "kernels.cuh"
 
 namespace tspcuda {
@@ -635,6 +637,49 @@ constexpr int NB_HU = 4;                       // heap records in flight per lan
 #endif
 constexpr int NB_SPLIT_WARPS = TSP_NB_SPLIT_WARPS;   // cooperating warps from which on the four searching warps take no share of the stream
 
+// ---- the heap stream through shared memory (K8): bulk asynchronous copies completing on mbarriers -----------------
+// MEASUREMENT ONLY (-DTSP_NB_STAGE=1; profiles/r02_pruned.md): built to test the reading "K8's scan waits for its heap records"
+// (ncu: 14 % of the stall samples at the first use of a record).  Same tours, and SLOWER than the direct loads the library
+// ships -- pla85900 148 starts 354 against 315 us per scan with 4 stages per warp, 347 with 3, 388 with 5: the more shared memory
+// the ring takes from L1, the slower the o8[] gathers and the line reads that the scan does next to the stream.  The stream's
+// latency is not what limits K8.
+#ifndef TSP_NB_STAGE
+#define TSP_NB_STAGE 0
+#endif
+#ifndef TSP_NB_STAGES
+#define TSP_NB_STAGES 4
+#endif
+constexpr int NB_STAGES = TSP_NB_STAGES;       // stages per warp
+constexpr int NB_STAGE_RECS = 64;              // records per stage (1 KB)
+struct StageRing {
+    int4 *buf;                    // [NB_STAGES][NB_STAGE_RECS], shared memory, private to the warp
+    unsigned long long *bar;      // [NB_STAGES] mbarriers (shared memory), one arrival (the issuing lane's expect_tx) per use
+    unsigned phase;               // bit st: the parity the next wait on stage st expects
+};
+__host__ __device__ constexpr size_t stage_smem_bytes(int warps) { return (size_t)warps * NB_STAGES * (NB_STAGE_RECS * sizeof(int4) + sizeof(unsigned long long)); }
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared, size a multiple of 16 bytes, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+// heap records are written by ordinary stores (generic proxy) and read by the bulk copies of LATER scans (async proxy):
+// every writer fences across the proxies before the barrier that ends its phase
+__device__ __forceinline__ void heap_writes_to_async_proxy() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
+
 struct ScanAcc {
     unsigned long long bestkey;
     long long ncand;
@@ -969,10 +1014,11 @@ __device__ __noinline__ ScanAcc attend(TourView V, const SpatialGrid *Gp, PosPat
 //   qctr, boxes   queue of the giant search boxes met in this scan (giant_phase, behind the caller's barrier)
 //   ring   NB_RING ints of shared memory private to the warp
 //   s_best the CTA's shared running best (armed to -1 by the caller behind a barrier)
-template <class M, int NE, bool SETTLE>
+//   sr     STAGED only: the warp's shared-memory stages for the heap stream (below)
+template <class M, int NE, bool SETTLE, bool STAGED = false>
 __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid &G, const PosPatch &F, int ep, int gw, int nwarps, int hsnap,
                                             int hp, unsigned long long *qctr, BigBox *boxes, uint4 *wbuf, const NbCache &C, int *ring, int *s_best, int &best,
-                                            unsigned long long &bestkey, long long &ncand) {
+                                            unsigned long long &bestkey, long long &ncand, StageRing *sr = nullptr) {
     ScanAcc a;
     a.bestkey = bestkey; a.ncand = ncand; a.best = best; a.ecount = 0;
     int acount = 0;
@@ -994,29 +1040,21 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
         }
     }
     if (!(split && gw < 4)) {
-    // ---- the heap: every cooperating thread a strided share of the records, NB_HU loads in flight per lane (a warp that
-    // waits for one 16-byte record at a time is bound by the memory latency, not by the bandwidth)
-    for (int k0 = sgw * 32; k0 < hsnap; k0 += snw * 32 * NB_HU) {
-        if (acount > AB_CAP - 32 * NB_HU) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a); acount = 0; }      // warp-uniform, rare
-        if (!SETTLE && a.ecount > EB_CAP - 32 * NB_HU) a = flush_records<M, NE>(V, F, ebuf, a);
-        int4 r[NB_HU];
+    // ---- the heap: every cooperating thread a share of the records.  What is done with the records of a step (HU per lane,
+    // record j of this lane = heap[kidx[j]]) is the same for both ways of fetching them:
+    auto heap_step = [&](auto hu_tag, const int4 *r, const int *kidx) {
+        constexpr int HU = decltype(hu_tag)::value;
+        int ou[HU], ow[HU];
 #pragma unroll
-        for (int j = 0; j < NB_HU; ++j) {
-            const int k = k0 + j * snw * 32 + lane;
-            r[j] = make_int4(-1, 0, 0, 0);
-            if (k < hsnap) r[j] = C.heap[k];
-        }
-        int ou[NB_HU], ow[NB_HU];
-#pragma unroll
-        for (int j = 0; j < NB_HU; ++j) {
+        for (int j = 0; j < HU; ++j) {
             ou[j] = r[j].x >= 0 ? V.o8[r[j].x] : 0;
             ow[j] = r[j].x >= 0 ? V.o8[r[j].y] : 0;
         }
-        int d[NB_HU];
+        int d[HU];
         unsigned dirty = 0;
         int mine = 0x7FFFFFFF;
 #pragma unroll
-        for (int j = 0; j < NB_HU; ++j) {
+        for (int j = 0; j < HU; ++j) {
             d[j] = 0x7FFFFFFF;
             bool live = r[j].x >= 0;
             if (live && (ou[j] >> 1) == ep && in_patch(F, r[j].x)) live = false;      // u's own list is being rebuilt by a designated warp
@@ -1030,11 +1068,11 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
         }
         if (__any_sync(FULL, dirty != 0)) {                        // rare
 #pragma unroll
-            for (int j = 0; j < NB_HU; ++j) {
+            for (int j = 0; j < HU; ++j) {
                 const bool f = (dirty >> j) & 1u;
                 const unsigned m = __ballot_sync(FULL, f);
                 if (f) {
-                    const unsigned long long ra = (unsigned long long)(&C.heap[k0 + j * snw * 32 + lane].y);
+                    const unsigned long long ra = (unsigned long long)(&C.heap[kidx[j]].y);
                     wbuf[acount + __popc(m & lt)] = make_uint4((unsigned)r[j].x, (unsigned)r[j].y, (unsigned)(ra & 0xFFFFFFFFu) | AT_DIRTY, (unsigned)(ra >> 32));
                 }
                 acount += __popc(m);
@@ -1047,7 +1085,7 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
             if (lane == 0 && wm < seen) atomicMin(s_best, wm);
             if (__any_sync(FULL, mine <= wm)) {
 #pragma unroll
-                for (int j = 0; j < NB_HU; ++j) {
+                for (int j = 0; j < HU; ++j) {
                     const bool hit = d[j] <= wm;
                     const unsigned m = __ballot_sync(FULL, hit);
                     if (hit) ebuf[a.ecount + __popc(m & lt)] = make_uint4((unsigned)r[j].x, (unsigned)r[j].y, 0u, 3u | EV_NODEIDS);
@@ -1055,14 +1093,73 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
                 }
             }
         }
+    };
+    if (STAGED) {
+        // One CTA (or a small cluster) per descent: the stream IS the scan (pla85900: 5.8 MB of records per scan and descent,
+        // 148 descents resident -- HBM traffic).  A warp that loads its records into registers has them in flight only
+        // between the loads and their first use, about half the time.  Here the records travel by bulk asynchronous copies
+        // (TMA, cp.async.bulk) into a ring of NB_STAGES shared-memory stages per warp, NB_STAGE_RECS records (1 KB) each,
+        // completion on one mbarrier per stage: the copy of a stage is re-issued the moment its records are in registers,
+        // so NB_STAGES - 1 stages per warp are in flight ALL the time, whatever the warp does with the records.  The heap
+        // is dealt out in NB_STAGE_RECS-record blocks, block b to warp b mod snw.
+        constexpr int HU = NB_STAGE_RECS / 32;
+        const int nblk = (hsnap + NB_STAGE_RECS - 1) / NB_STAGE_RECS;
+        const int nmine = sgw < nblk ? (nblk - sgw + snw - 1) / snw : 0;
+        auto issue = [&](int i) {                                  // lane 0: block i of this warp into stage i mod NB_STAGES
+            const int b = sgw + i * snw, st = i % NB_STAGES;
+            const unsigned bytes = 16u * (unsigned)min(NB_STAGE_RECS, hsnap - b * NB_STAGE_RECS);
+            mbar_expect_tx(&sr->bar[st], bytes);
+            bulk_g2s(sr->buf + st * NB_STAGE_RECS, C.heap + (size_t)b * NB_STAGE_RECS, bytes, &sr->bar[st]);
+        };
+        if (lane == 0)
+            for (int i = 0; i < min(NB_STAGES, nmine); ++i) issue(i);
+        for (int i = 0; i < nmine; ++i) {
+            if (acount > AB_CAP - 32 * HU) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a); acount = 0; }      // warp-uniform, rare
+            if (!SETTLE && a.ecount > EB_CAP - 32 * HU) a = flush_records<M, NE>(V, F, ebuf, a);
+            const int st = i % NB_STAGES, k0 = (sgw + i * snw) * NB_STAGE_RECS;
+            mbar_wait(&sr->bar[st], (sr->phase >> st) & 1u);
+            sr->phase ^= 1u << st;
+            int4 r[HU];
+            int kidx[HU];
+#pragma unroll
+            for (int j = 0; j < HU; ++j) {
+                kidx[j] = k0 + 32 * j + lane;
+                r[j] = sr->buf[st * NB_STAGE_RECS + 32 * j + lane];
+                if (kidx[j] >= hsnap) r[j] = make_int4(-1, 0, 0, 0);           // beyond the bytes the copy brought
+            }
+            __syncwarp();                                          // the stage is in registers: its next block may land
+            if (lane == 0 && i + NB_STAGES < nmine) issue(i + NB_STAGES);
+            heap_step(std::integral_constant<int, HU>{}, r, kidx);
+        }
+    } else {
+        // NB_HU loads in flight per lane (a warp that waits for one 16-byte record at a time is bound by the memory latency)
+        for (int k0 = sgw * 32; k0 < hsnap; k0 += snw * 32 * NB_HU) {
+            if (acount > AB_CAP - 32 * NB_HU) { a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a); acount = 0; }      // warp-uniform, rare
+            if (!SETTLE && a.ecount > EB_CAP - 32 * NB_HU) a = flush_records<M, NE>(V, F, ebuf, a);
+            int4 r[NB_HU];
+            int kidx[NB_HU];
+#pragma unroll
+            for (int j = 0; j < NB_HU; ++j) {
+                kidx[j] = k0 + j * snw * 32 + lane;
+                r[j] = make_int4(-1, 0, 0, 0);
+                if (kidx[j] < hsnap) r[j] = C.heap[kidx[j]];
+            }
+            heap_step(std::integral_constant<int, NB_HU>{}, r, kidx);
+        }
     }
-    // ---- the lines: a contiguous range of nodes per warp; count bytes first, non-empty lines 32 per step
-    // many warps, few nodes each (the whole GPU on one descent): 32-node ranges, so that every warp gets some; otherwise
-    // ranges in multiples of 128 nodes, whose count bytes are read four per lane
+    // ---- the lines: count bytes first, non-empty lines 32 per step
+    // many warps, few nodes each (the whole GPU on one descent): one 32-node range per warp, so that every warp gets some;
+    // otherwise blocks of 128 nodes, whose count bytes are read four per lane, dealt out round-robin (TSP_NB_LINE_RANGES: one
+    // contiguous range per warp, as before -- node ids follow the geography in most files and the nodes with records are
+    // not spread evenly, so contiguous ranges leave the warps of a CTA with unequal work before the scan's barrier)
     const int per = (n + snw - 1) / snw;
     const bool wide = per > 64;
     const int chunk = wide ? (per + 127) & ~127 : (per + 31) & ~31;
-    const int lo = min(n, sgw * chunk), hi = min(n, lo + chunk);
+#ifdef TSP_NB_LINE_RANGES
+    const int lo = min(n, sgw * chunk), hi = min(n, lo + chunk), wstep = 128;
+#else
+    const int lo = min(n, wide ? sgw * 128 : sgw * chunk), hi = wide ? n : min(n, lo + chunk), wstep = snw * 128;
+#endif
     int base = lo, head = 0, tail = 0;
     for (;;) {
         while (base < hi && tail - head < 32) {                    // refill
@@ -1076,7 +1173,7 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
                     if (want) ring[(tail + __popc(m & lt)) & (NB_RING - 1)] = u4 + j;
                     tail += __popc(m);
                 }
-                base += 128;
+                base += wstep;
             } else {
                 const int u1 = base + lane;
                 const bool want = u1 < hi && C.cnt8[u1] != 0;
@@ -1160,6 +1257,7 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
     }   // !(split && gw < 4)
     if (acount > 0) a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a);
     if (!SETTLE && a.ecount > 0) a = flush_records<M, NE>(V, F, ebuf, a);
+    if (STAGED) heap_writes_to_async_proxy();
     best = a.best; bestkey = a.bestkey; ncand = a.ncand;
 }
 
@@ -1241,6 +1339,7 @@ __device__ __noinline__ void giant_phase(TourView V, const SpatialGrid *Gp, PosP
         rowoff += hi - lo;
     }
     if (a.ecount > 0) a = flush_records<M, NE>(V, F, ebuf, a);
+    heap_writes_to_async_proxy();
     *best_io = a.best; *key_io = a.bestkey; *ncand_io = a.ncand;
 }
 
@@ -1440,6 +1539,15 @@ descend_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, DescSt
             st->cost += delta;
             st->last_a = a; st->last_b = b; st->last_delta = delta;
         }
+#ifdef TSP_PHASE_TIMING
+        if (gtid == 0) {                                 // slot 4: nodes in the reversed segments; slot 5: CTA 0's own share of the move phase (ns)
+            unsigned long long tn_;
+            asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn_));
+            int L_ = seg_e - seg_s + 1; if (L_ <= 0) L_ += V.n;
+            st->phase_ns[4] += L_;
+            st->phase_ns[5] += (long long)(tn_ - tprev);
+        }
+#endif
         grid.sync();
         PHASE_MARK(2)
         F.node0 = b; F.pos0 = seg_s; F.node1 = V.tid[seg_e]; F.pos1 = seg_e;
@@ -1609,6 +1717,24 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     __shared__ long long s_cost_, s_bestcost_;
     __shared__ int s_cur_, s_stop_, s_best;
     __shared__ int s_ring[WARPS][NB_RING];
+    // dynamic shared memory: the stages of the heap stream and their mbarriers (cached_scan, STAGED) -- a team of fewer than
+    // NB_SPLIT_WARPS warps streams through them; the 8-SM cluster (256 warps, a few records per lane) loads directly
+#if TSP_NB_STAGE
+    constexpr bool STG = WARPS * CL < NB_SPLIT_WARPS;
+#else
+    constexpr bool STG = false;                         // default: every team loads its records directly (measured faster, see StageRing)
+#endif
+    extern __shared__ __align__(128) unsigned char k8_dyn_smem[];
+    StageRing sr;
+    sr.buf = reinterpret_cast<int4 *>(k8_dyn_smem) + (size_t)(threadIdx.x >> 5) * NB_STAGES * NB_STAGE_RECS;
+    sr.bar = reinterpret_cast<unsigned long long *>(k8_dyn_smem + (size_t)WARPS * NB_STAGES * NB_STAGE_RECS * sizeof(int4)) + (threadIdx.x >> 5) * NB_STAGES;
+    sr.phase = 0;
+    if (STG) {
+        if ((threadIdx.x & 31) == 0)
+            for (int st = 0; st < NB_STAGES; ++st) mbar_init(&sr.bar[st], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        __syncthreads();
+    }
     unsigned rank = 0;
     unsigned long long *s_q = &s_q_;
     long long *s_cost = &s_cost_, *s_bestcost = &s_bestcost_;
@@ -1686,7 +1812,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
         for (;;) {
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
-            cached_scan<M, NE, false>(V, G, F, ep, warp, WARPS * CL, hsnap, hp, s_q, boxes, wbuf, C, s_ring[threadIdx.x >> 5], &s_best, best, bestkey, ncand);
+            cached_scan<M, NE, false, STG>(V, G, F, ep, warp, WARPS * CL, hsnap, hp, s_q, boxes, wbuf, C, s_ring[threadIdx.x >> 5], &s_best, best, bestkey, ncand, &sr);
             bestkey = warp_min_key(bestkey);
             if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key_[par], bestkey);
             team_sync<CL>();

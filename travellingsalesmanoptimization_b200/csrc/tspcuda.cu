@@ -54,6 +54,13 @@ enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3, M_G
         default: { using M = Att; EXPR; } break;                          \
     }
 
+// dynamic shared memory of multi_pruned_kernel<M, blk, cl>: the stages of its heap stream (pruned.cuh, STG)
+#if TSP_NB_STAGE
+static size_t k8_dyn_smem(int blk, int cl) { return (blk / 32) * cl < NB_SPLIT_WARPS ? stage_smem_bytes(blk / 32) : 0; }
+#else
+static size_t k8_dyn_smem(int, int) { return 0; }
+#endif
+
 // Grow-only device scratch of the multi-start entry points, kept in the context between calls: cudaFree of the per-call
 // buffers sporadically took 0.1 - 1.5 s on the B200 boxes (TSPCUDA_VERBOSE phase clock, profiles/r01_cluster.md), more
 // than the descents of a small batch.  Released by tspcuda_destroy.
@@ -508,7 +515,7 @@ static int descend(tspcuda_ctx *c, long long max_moves, int mode, double time_li
         c->stats.last_kernel_ms = ms;
 #ifdef TSP_PHASE_TIMING
         if (pruned && c->h_state->status == 1)
-            fprintf(stderr, "[tspcuda] pruned phases: scan1 %.1f ms (slowest warp ever %.1f us, mean warp %.2f us)  scan2 %.1f ms  apply %.1f ms | units/scan %.0f boxes/scan %.0f\n",
+            fprintf(stderr, "[tspcuda] pruned phases: scan1 %.1f ms (slowest warp ever %.1f us, mean warp %.2f us)  scan2 %.1f ms  apply %.1f ms | nodes reversed per move %.0f, CTA 0 own part of the move phase %.0f ns\n",
                     c->h_state->phase_ns[0] * 1e-6, c->h_state->phase_ns[3] * 1e-3,
                     c->h_state->phase_sum * 1e-3 / ((double)(c->h_state->moves + 1) * c->pruned_blocks * (c->pruned_block / 32)),
                     c->h_state->phase_ns[1] * 1e-6, c->h_state->phase_ns[2] * 1e-6,
@@ -1096,16 +1103,17 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
                 for (int k = 0, v = 1; k < 4; ++k, v *= 2) {
                     cudaLaunchConfig_t q = {};
                     q.gridDim = dim3(c->num_sms / v * v); q.blockDim = dim3(1024);
+                    q.dynamicSmemBytes = k8_dyn_smem(1024, v);
                     cudaLaunchAttribute qa[1];
                     qa[0].id = cudaLaunchAttributeClusterDimension;
                     qa[0].val.clusterDim.x = v; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
                     q.attrs = qa; q.numAttrs = 1;
                     int nc = 0;
                     cudaError_t qe = cudaSuccess;
-                    if (v == 8) { DISPATCH_METRIC(c->metric, (qe = cudaOccupancyMaxActiveClusters(&nc, multi_pruned_kernel<M, 1024, 8>, &q))); }
-                    else if (v == 4) { DISPATCH_METRIC(c->metric, (qe = cudaOccupancyMaxActiveClusters(&nc, multi_pruned_kernel<M, 1024, 4>, &q))); }
-                    else if (v == 2) { DISPATCH_METRIC(c->metric, (qe = cudaOccupancyMaxActiveClusters(&nc, multi_pruned_kernel<M, 1024, 2>, &q))); }
-                    else { DISPATCH_METRIC(c->metric, (qe = cudaOccupancyMaxActiveClusters(&nc, multi_pruned_kernel<M, 1024, 1>, &q))); }
+#define K8_QUERY(CLV) DISPATCH_METRIC(c->metric, (qe = cudaFuncSetAttribute(multi_pruned_kernel<M, 1024, CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.dynamicSmemBytes), \
+                                                   qe = qe != cudaSuccess ? qe : cudaOccupancyMaxActiveClusters(&nc, multi_pruned_kernel<M, 1024, CLV>, &q)))
+                    if (v == 8) { K8_QUERY(8); } else if (v == 4) { K8_QUERY(4); } else if (v == 2) { K8_QUERY(2); } else { K8_QUERY(1); }
+#undef K8_QUERY
                     if (qe != cudaSuccess) { cudaGetLastError(); nc = 0; }
                     c->k8_clusters[k] = std::max(1, std::min(nc, c->num_sms / v));
                 }
@@ -1129,7 +1137,9 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
             cfg.attrs = attr; cfg.numAttrs = 1;
             cudaError_t le = cudaSuccess;
 #define K8_LAUNCH(BLKV, CLV)                                                                                                  \
-    DISPATCH_METRIC(c->metric, (le = cudaLaunchKernelEx(&cfg, multi_pruned_kernel<M, BLKV, CLV>, (const double2 *)c->d_xy, n, c->grid, \
+    cfg.dynamicSmemBytes = k8_dyn_smem(BLKV, CLV);                                                                            \
+    DISPATCH_METRIC(c->metric, (le = cudaFuncSetAttribute(multi_pruned_kernel<M, BLKV, CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes))); \
+    if (le == cudaSuccess) DISPATCH_METRIC(c->metric, (le = cudaLaunchKernelEx(&cfg, multi_pruned_kernel<M, BLKV, CLV>, (const double2 *)c->d_xy, n, c->grid, \
         (const int *)S.order, fs, stride, cnt, next.as<int>(), MS, dcost.as<long long>(), dmoves.as<long long>(),                     \
         dstatus.as<int>(), m_cand.as<unsigned long long>(), c->d_wbuf, d_stop)))
             // TSPCUDA_K8_BLOCK=512 (measurement knob): 16 warps of 128 registers per descent instead of 32 of 64
