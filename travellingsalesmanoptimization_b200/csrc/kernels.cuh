@@ -224,7 +224,7 @@ __device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k)
 // pos[tid[e_out]] = e_out (tid[e_out] is succ_a after the reversal).
 // ep (delta cache only, V.o8 != NULL): the epoch of this move; the o8 bytes of the four nodes whose tour edges change
 // (a, succ a, b, succ b) are stamped with it in bits 1..7 (pruned.cuh).
-template <class M, bool CACHE = false>
+template <class M, bool CACHE = false, int AM_B = CACHE ? 4 : 1>
 __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int t, int nthreads, bool has_dns,
                                            int &s_out, int &e_out, int ep = 0) {
     const int n = V.n;
@@ -245,21 +245,46 @@ __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int 
         if (i == 0) { V.dn[n] = k_ab; if (has_dns) V.dns[n] = k_ab; }
         if (e == 0) { V.dn[n] = k_ss; if (has_dns) V.dns[n] = k_ss; }
     }
-    for (int k = t; k < half; k += nthreads) {
-        int p = s + k; if (p >= n) p -= n;
-        int q = e - k; if (q < 0) q += n;
-        const double2 xp = V.pxy[p], xq = V.pxy[q];
-        const int tp = V.tid[p], tq = V.tid[q];
-        V.pxy[p] = xq; V.pxy[q] = xp;
-        V.tid[p] = tq; V.tid[q] = tp;
-        if (k != 0) { V.pos[tq] = p; V.pos[tp] = q; }   // k == 0: the end nodes, deferred (see above)
-        if (p == 0) { V.pxy[n] = xq; V.tid[n] = tq; }
-        if (q == 0) { V.pxy[n] = xp; V.tid[n] = tp; }
-        if (CACHE) {                                    // one owner per node: plain byte updates
-            if (k == 0) {                               // the segment ends: succ a and b
-                V.o8[tq] = (unsigned char)(((V.o8[tq] ^ 1) & 1) | (ep << 1));
-                V.o8[tp] = (unsigned char)(((V.o8[tp] ^ 1) & 1) | (ep << 1));
-            } else { V.o8[tq] ^= 1; V.o8[tp] ^= 1; }
+    // AM_B pairs per thread and trip, all loads of a trip before its stores: when few threads share a long segment (one CTA
+    // per descent: pla85900 reverses 48 000 nodes per move on average, 24 pairs per thread) a pair at a time is a chain of
+    // dependent memory round trips per pair -- 76 us of a 300 us scan + move (profiles/r02_pruned.md).  No pair is touched by
+    // two threads or twice by one, so the order of loads and stores within a trip is free.  (AM_B = 1 for the full-scan
+    // kernels, whose moves are spread over the whole grid or live in shared memory.)
+    for (int k0 = t; k0 < half; k0 += AM_B * nthreads) {
+        double2 xp[AM_B], xq[AM_B];
+        int tp[AM_B], tq[AM_B], pp[AM_B], qq[AM_B], op[AM_B], oq[AM_B];
+#pragma unroll
+        for (int j = 0; j < AM_B; ++j) {
+            const int k = k0 + j * nthreads;
+            pp[j] = -1;
+            if (k < half) {
+                int p = s + k; if (p >= n) p -= n;
+                int q = e - k; if (q < 0) q += n;
+                pp[j] = p; qq[j] = q;
+                xp[j] = V.pxy[p]; xq[j] = V.pxy[q];
+                tp[j] = V.tid[p]; tq[j] = V.tid[q];
+            }
+        }
+        if (CACHE) {
+#pragma unroll
+            for (int j = 0; j < AM_B; ++j)
+                if (pp[j] >= 0) { oq[j] = V.o8[tq[j]]; op[j] = V.o8[tp[j]]; }
+        }
+#pragma unroll
+        for (int j = 0; j < AM_B; ++j) {
+            if (pp[j] < 0) continue;
+            const int k = k0 + j * nthreads, p = pp[j], q = qq[j];
+            V.pxy[p] = xq[j]; V.pxy[q] = xp[j];
+            V.tid[p] = tq[j]; V.tid[q] = tp[j];
+            if (k != 0) { V.pos[tq[j]] = p; V.pos[tp[j]] = q; }   // k == 0: the end nodes, deferred (see above)
+            if (p == 0) { V.pxy[n] = xq[j]; V.tid[n] = tq[j]; }
+            if (q == 0) { V.pxy[n] = xp[j]; V.tid[n] = tp[j]; }
+            if (CACHE) {                                // one owner per node: plain byte updates
+                if (k == 0) {                           // the segment ends: succ a and b
+                    V.o8[tq[j]] = (unsigned char)(((oq[j] ^ 1) & 1) | (ep << 1));
+                    V.o8[tp[j]] = (unsigned char)(((op[j] ^ 1) & 1) | (ep << 1));
+                } else { V.o8[tq[j]] = (unsigned char)(oq[j] ^ 1); V.o8[tp[j]] = (unsigned char)(op[j] ^ 1); }
+            }
         }
     }
     // The three single-thread jobs of a move -- the new edge costs and the end pair (thread 0 above), the stamps of a and
@@ -275,14 +300,28 @@ __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int 
         int m = s + half; if (m >= n) m -= n;
         V.o8[V.tid[m]] ^= 1;
     }
-    for (int k = t; k < ehalf; k += nthreads) {
-        int p = s + k; if (p >= n) p -= n;
-        int q = e - 1 - k; if (q < 0) q += n;
-        const int dp = V.dn[p], dq = V.dn[q];
-        V.dn[p] = dq; V.dn[q] = dp;
-        if (has_dns) { V.dns[p] = dq; V.dns[q] = dp; }
-        if (p == 0) { V.dn[n] = dq; if (has_dns) V.dns[n] = dq; }
-        if (q == 0) { V.dn[n] = dp; if (has_dns) V.dns[n] = dp; }
+    for (int k0 = t; k0 < ehalf; k0 += AM_B * nthreads) {
+        int dp[AM_B], dq[AM_B], pp[AM_B], qq[AM_B];
+#pragma unroll
+        for (int j = 0; j < AM_B; ++j) {
+            const int k = k0 + j * nthreads;
+            pp[j] = -1;
+            if (k < ehalf) {
+                int p = s + k; if (p >= n) p -= n;
+                int q = e - 1 - k; if (q < 0) q += n;
+                pp[j] = p; qq[j] = q;
+                dp[j] = V.dn[p]; dq[j] = V.dn[q];
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < AM_B; ++j) {
+            if (pp[j] < 0) continue;
+            const int p = pp[j], q = qq[j];
+            V.dn[p] = dq[j]; V.dn[q] = dp[j];
+            if (has_dns) { V.dns[p] = dq[j]; V.dns[q] = dp[j]; }
+            if (p == 0) { V.dn[n] = dq[j]; if (has_dns) V.dns[n] = dq[j]; }
+            if (q == 0) { V.dn[n] = dp[j]; if (has_dns) V.dns[n] = dp[j]; }
+        }
     }
 }
 

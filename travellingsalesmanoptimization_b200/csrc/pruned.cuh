@@ -515,6 +515,9 @@ constexpr int NB_CF_STALE = 1023, NB_CF_HEAP = 1022;          // header: never s
 constexpr int NB_HDR_STALE = NB_CF_STALE;      // (bits 10..: how often a stale node's giant box has been evaluated without caching, see giant_age)
 constexpr int NB_DIRTY = (int)0x80000000;      // d0 of a record that must be recomputed before use
 constexpr int NB_GIANT = 512;                  // a search box with more nodes than this is not walked by one warp: giant_phase()
+#ifndef TSP_NB_GIANT_KEEP
+#define TSP_NB_GIANT_KEEP 1
+#endif
 constexpr int NB_FLAT = 64;                    // a search box with at most this many nodes is walked in one step (rebuild_list)
 constexpr int NB_EPOCHS = 126;                 // epochs 0..125 cycle; 126: "no move yet"; 127: a node no move has touched
 constexpr int NB_EP_NONE = 126, NB_EP_INIT = 127;
@@ -526,6 +529,7 @@ struct NbCache {
                             // records, [4]: nodes whose list lives in the heap (8 ints)
     unsigned char *cnt8;    // [n] non-zero: the node's line must be looked at (records, stale); zero: nothing there
     int heap_cap;
+    int restart_pct;        // heap restart policy (heap_checkpoint): abandoned records tolerated, in percent of the default rule
     int giant_age;          // a GIANT search box is only evaluated (as in round 1), not cached, the first giant_age times the node is
                             // searched with the same tour edges: the three instance-spanning edges of a VNS kick are gone after
                             // two or three moves -- caching their ~n records each only fills the heap.  0: cache at once (descents).
@@ -759,12 +763,24 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
         // The box is not walked by this warp alone: it gets a heap run with one slot per node of the box and is queued;
         // behind the scan's barrier all cooperating warps fill the run row by row (giant_phase).  When a launch is
         // settling there is no such barrier: the node stays stale for the next launch.
+        // A node that had a run of at least this size KEEPS it (a long edge usually survives the change of the node's other
+        // edge: same box, same size): every slot below tot is rewritten in giant_phase, and until then nobody uses the old
+        // records -- a node with a run is only searched again as one of the four nodes of the last move, whose records the
+        // streaming warps skip.  (Rounds 1-2 abandoned the run and took a new one: thousands of dead slots per giant search,
+        // the main source of the abandoned records a scan streams.)
+#if TSP_NB_GIANT_KEEP
+        const bool keep = !SETTLE && had && tot <= ocap;
+#else
+        const bool keep = false;
+#endif
         if (had)
-            for (int j = lane; j < ocount; j += 32) C.heap[ostart + j].x = -1;
+            for (int j = (keep ? tot : 0) + lane; j < ocount; j += 32) C.heap[ostart + j].x = -1;
         // fresh: the node's tour edges have just changed (one of the four nodes of the last move); otherwise the header says
         // how often this box has been evaluated without caching since
         const int age = (!fresh && (h0 & 0x3FF) == NB_CF_STALE) ? (h0 >> 10) : 0;
         if (!SETTLE && age < C.giant_age) {                        // evaluate only: queued without a heap run, the node stays stale
+            if (keep)
+                for (int j = lane; j < tot; j += 32) C.heap[ostart + j].x = -1;
             if (lane == 0) {
                 NBSTAT(0, 1); NBSTAT(7, tot); NBSTAT(1, 1);
                 if (had) { atomicAdd(C.heap_next + 3, -ocount); atomicAdd(C.heap_next + 4, -1); }
@@ -778,18 +794,21 @@ __device__ __forceinline__ void rebuild_list(const TourView &V, const SpatialGri
             return;
         }
         int start = -1;
-        if (!SETTLE && lane == 0) start = *(volatile int *)(C.heap_next + hp) > C.heap_cap ? -1 : atomicAdd(C.heap_next + hp, tot);
-        start = __shfl_sync(FULL, start, 0);
-        if (start > C.heap_cap - tot) {                            // no room: what the run covers is void
-            for (int j = start + lane; j < C.heap_cap; j += 32) C.heap[j].x = -1;
-            start = -1;
+        if (keep) start = ostart;
+        else {
+            if (!SETTLE && lane == 0) start = *(volatile int *)(C.heap_next + hp) > C.heap_cap ? -1 : atomicAdd(C.heap_next + hp, tot);
+            start = __shfl_sync(FULL, start, 0);
+            if (start > C.heap_cap - tot) {                        // no room: what the run covers is void
+                for (int j = start + lane; j < C.heap_cap; j += 32) C.heap[j].x = -1;
+                start = -1;
+            }
         }
         if (lane == 0) {
             NBSTAT(0, 1); NBSTAT(7, tot); NBSTAT(1, 1);
             atomicAdd(C.heap_next + 3, (start >= 0 ? tot : 0) - (had ? ocount : 0));
             if ((start >= 0) != had) atomicAdd(C.heap_next + 4, had ? -1 : 1);
             if (start >= 0) {
-                line[0] = NB_CF_HEAP; line[1] = start; line[2] = tot; line[3] = tot; C.cnt8[u] = 0;
+                line[0] = NB_CF_HEAP; line[1] = start; line[2] = tot; line[3] = keep ? ocap : tot; C.cnt8[u] = 0;
                 const unsigned long long old = atomicAdd(qctr, (1ull << 40) | (unsigned long long)nrows);
                 BigBox bx;
                 bx.p = c.p; bx.cy0 = cy0; bx.cx0 = cx0; bx.cx1 = cx1; bx.nrows = nrows; bx.pad = start;
@@ -1353,7 +1372,7 @@ __device__ __noinline__ void giant_phase(TourView V, const SpatialGrid *Gp, PosP
 // per CTA and a shared-memory broadcast where a whole grid cooperates)
 __device__ __forceinline__ int heap_checkpoint(const NbCache &C, int n, int t, int nthreads, int &hp, int hn, int live) {
     const long long teams = max(1, nthreads >> 10);
-    if (hn <= C.heap_cap / 4 * 3 && (long long)hn - live <= teams * live + (n >> 1)) return min(hn, C.heap_cap);
+    if (hn <= C.heap_cap / 4 * 3 && ((long long)hn - live) * 100 <= (teams * live + (n >> 1)) * C.restart_pct) return min(hn, C.heap_cap);
     for (int u = t; u < n; u += nthreads) {
         int *h = C.lines + (size_t)u * NB_WORDS;
         if ((*h & 0x3FF) == NB_CF_HEAP) { *h = NB_HDR_STALE; C.cnt8[u] = 1; }
@@ -1677,7 +1696,7 @@ struct MultiSlots {
     BigBox *boxes;     // [slots][n]  queue of giant search boxes
     int *nb;           // [slots][n * NB_WORDS]  delta cache of the slot's current descent: node lines,
     int4 *nb_heap;     // [slots][heap_cap]                                                    record heap,
-    int heap_cap;
+    int heap_cap, restart_pct;
     int *nb_next;      // [slots][8]                                                           its counters,
     unsigned char *o8; // [slots][n]                                                           orientation / epoch bytes,
     unsigned char *cnt8; // [slots][nb_cnt8_stride(n)]                                         count bytes
@@ -1759,6 +1778,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     NbCache C;
     C.lines = S.nb + slot * (size_t)n * NB_WORDS;
     C.heap_cap = S.heap_cap;
+    C.restart_pct = S.restart_pct;
     C.giant_age = 0;
     C.heap = S.nb_heap + slot * (size_t)C.heap_cap;
     C.heap_next = S.nb_next + slot * 8;
@@ -1809,13 +1829,23 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
         // is not atomic between a CTA's own shared-memory path and its peers' distributed-shared-memory path (measured,
         // scripts/cluster_probe.cu: lost updates), 64-bit atomicAdd is.
         int ep = NB_EP_NONE, hp = 0, hsnap = 0;
+#ifdef TSP_PHASE_TIMING
+        // thread 0 of team 0: ns in the scan (own part / incl. the wait at its barrier), the giant phase, the move (own part / incl. barrier)
+        unsigned long long k8t[5] = {0, 0, 0, 0, 0}, k8a = 0, k8b = 0;
+#define K8_MARK(slot) { asm volatile("mov.u64 %0, %globaltimer;" : "=l"(k8b)); k8t[slot] += k8b - k8a; k8a = k8b; }
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(k8a));
+#else
+#define K8_MARK(slot)
+#endif
         for (;;) {
             int best = -1;
             unsigned long long bestkey = KEY_EMPTY;
             cached_scan<M, NE, false, STG>(V, G, F, ep, warp, WARPS * CL, hsnap, hp, s_q, boxes, wbuf, C, s_ring[threadIdx.x >> 5], &s_best, best, bestkey, ncand, &sr);
             bestkey = warp_min_key(bestkey);
             if (lane == 0 && bestkey != KEY_EMPTY) atomicMin(&s_key_[par], bestkey);
+            K8_MARK(0)
             team_sync<CL>();
+            K8_MARK(1)
             {   // giant search boxes met in this scan (rare): all warps of the team fill their heap runs now, one more barrier
                 const unsigned long long q = *s_q;
                 if (q >> 40) {
@@ -1838,7 +1868,9 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             ep = (int)(moves % NB_EPOCHS);
             const int a = key_a(kbest), b = key_b(kbest);
             int seg_s, seg_e;
+            K8_MARK(2)
             apply_move<M, true>(V, a, b, t, TEAM, false, seg_s, seg_e, ep);
+            K8_MARK(3)
             if (t == 0) {
                 *s_cost += key_delta(kbest);
                 if (stop != nullptr) *s_stop = *(volatile const int *)stop;
@@ -1847,11 +1879,18 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             ++moves;
             par ^= 1;
             team_sync<CL>();
+            K8_MARK(4)
             F.node0 = b; F.pos0 = seg_s; F.node1 = V.tid[seg_e]; F.pos1 = seg_e;
             F.node2 = a; F.node3 = V.tid[seg_e + 1];
             if (t == 0) { V.pos[F.node0] = F.pos0; V.pos[F.node1] = F.pos1; }
             if (stop != nullptr && *s_stop != 0) { cut = true; break; }      // time limit: checked before the next scan
         }
+#ifdef TSP_PHASE_TIMING
+        if (t == 0 && blockIdx.x == 0)
+            printf("[tspcuda] K8 team 0, start %d: %lld moves; per scan+move ns: scan own %llu, wait at its barrier %llu, giant phase + checkpoint %llu, move own %llu, bookkeeping + barrier %llu\n",
+                   first_start + cur * stride, moves, k8t[0] / (moves + 1), k8t[1] / (moves + 1), k8t[2] / (moves + 1), k8t[3] / (moves + 1), k8t[4] / (moves + 1));
+#endif
+#undef K8_MARK
         // left behind a barrier with a team-uniform condition: every thread is here, the tour is final
         const long long fc = *s_cost;
         if (t == 0) { final_cost[cur] = fc; moves_out[cur] = moves; status_out[cur] = cut ? MS_CUT : MS_COMPLETE; }

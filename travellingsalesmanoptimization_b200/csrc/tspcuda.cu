@@ -108,6 +108,7 @@ struct tspcuda_ctx {
     unsigned char *d_cnt8 = nullptr; //   and a byte-per-node flag array for nb_mark_*_kernel
     unsigned char *d_nbflag = nullptr;
     int nb_heap_per_node = NB_HEAP_PER_NODE;
+    int nb_restart_pct = 100;             // NbCache::restart_pct (TSPCUDA_NB_RESTART_PCT, measurements)
     int nb_giant_age = 0;                 // NbCache::giant_age of the next descents (the VNS loop raises it)
     long long nb_moves = 0;          // moves the delta cache has followed since it was last invalidated (epoch numbering)
     bool nb_valid = false;           // false: the tour changed behind the cache's back (upload, full-scan or tabu moves)
@@ -284,6 +285,7 @@ extern "C" int tspcuda_create(tspcuda_ctx **out, const double *xy, int n, int we
         CKC(cudaMalloc(&c->d_wbuf, sizeof(uint4) * (size_t)PR_WBUF * 32 * c->num_sms));
         CKC(cudaMalloc(&c->d_nb, sizeof(int) * (size_t)NB_WORDS * n));
         if (const char *hv = getenv("TSPCUDA_NB_HEAP")) c->nb_heap_per_node = std::max(0, atoi(hv));
+        if (const char *hv = getenv("TSPCUDA_NB_RESTART_PCT")) c->nb_restart_pct = std::max(1, std::min(100000, atoi(hv)));
         CKC(cudaMalloc(&c->d_nb_heap, sizeof(int4) * (size_t)nb_heap_cap(n, c->nb_heap_per_node)));
         CKC(cudaMalloc(&c->d_nb_next, sizeof(int) * 8));
         CKC(cudaMemsetAsync(c->d_nb_next, 0, sizeof(int) * 8, c->stream));
@@ -420,7 +422,7 @@ static cudaError_t launch_descend_pruned(tspcuda_ctx *c, int grid, long long max
     BigBox *boxes = c->d_boxes;
     uint4 *wbuf = c->d_wbuf;
     NbCache nb;
-    nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(c->n, c->nb_heap_per_node); nb.giant_age = c->nb_giant_age;
+    nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(c->n, c->nb_heap_per_node); nb.giant_age = c->nb_giant_age; nb.restart_pct = c->nb_restart_pct;
     if (!c->nb_valid) {                                        // the tour was replaced or moved by another kernel: every list is stale
         nb_invalidate_kernel<<<grid_for(c->n, 4 * c->num_sms), 256, 0, c->stream>>>(nb, c->d_o8, c->n);
         c->stats.kernel_launches += 1;
@@ -1051,6 +1053,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
         CK(scratch_get(c, SC_M_NB, sizeof(int) * (size_t)NB_WORDS * (size_t)n * sl, m_nb));
         CK(scratch_get(c, SC_M_NBHEAP, sizeof(int4) * (size_t)nb_heap_cap(n, c->nb_heap_per_node) * sl, m_nbheap));
         MS.heap_cap = nb_heap_cap(n, c->nb_heap_per_node);
+        MS.restart_pct = c->nb_restart_pct;
         CK(scratch_get(c, SC_M_NBNEXT, sizeof(int) * 8 * sl, m_nbnext));
         CK(scratch_get(c, SC_M_O8, (size_t)n * sl, m_o8));
         CK(scratch_get(c, SC_M_CNT8, (size_t)nb_cnt8_stride(n) * sl, m_cnt8));
@@ -1650,7 +1653,7 @@ static int vns_search_impl(tspcuda_ctx *c, int *path, double *cost_inout, int n_
             CK(scratch_get(c, SC_NB_LIST, sizeof(int) * (size_t)n, d_list));
             CK(cudaMemcpyAsync(d_list.p, changed.data(), sizeof(int) * changed.size(), cudaMemcpyHostToDevice, c->stream));
             NbCache nb;
-            nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(n, c->nb_heap_per_node); nb.giant_age = 0;
+            nb.lines = c->d_nb; nb.heap = c->d_nb_heap; nb.heap_next = c->d_nb_next; nb.cnt8 = c->d_cnt8; nb.heap_cap = nb_heap_cap(n, c->nb_heap_per_node); nb.giant_age = 0; nb.restart_pct = c->nb_restart_pct;
             const int cn = (int)changed.size();
             nb_mark_nodes_kernel<<<1, 256, 0, c->stream>>>(nb, d_list.as<int>(), cn, c->d_nbflag, 1);
             nb_mark_records_kernel<<<grid_for(n, 4 * c->num_sms), 256, 0, c->stream>>>(nb, c->d_nbflag, n);
