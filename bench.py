@@ -166,7 +166,8 @@ def fixed_sets(T, ndev, multistart, best_ref=None):
         row = {"S": S}
         for g in sorted({1, ndev}):
             with T.MultiGpuInstance(xy, T.EUC_REF, g) as M:
-                M.multistart(True, 0, min(S, 2 * g), 1)                       # warm (module load, scratch growth, NCCL)
+                M.multistart(True, 0, min(S, 2 * g), 1)                       # warm (module load, NCCL)
+                M.multistart(True, 0, S, 1, time_limit=0.05)                   # the contexts' grow-only scratch at this batch's size (cut by its deadline)
                 t0 = time.perf_counter()
                 bs, bp, bc, cms, rms = M.multistart(True, 0, S, 1)
                 wall = time.perf_counter() - t0
@@ -379,6 +380,9 @@ def main():
         with T.Instance(xy[:512], T.EUC_REF, local) as Iw:          # warm: load the CTA-per-descent kernels (lazy module loading)
             Iw.multistart_two_opt(0, 64, 1)                          # on a 512-node slice; a pla85900 descent per CTA takes seconds
         I.multistart_two_opt(first, min(count, 2), stride)
+        # the context's grow-only scratch at this batch's size: the same batch, cut by a 50 ms deadline (re-growing GBs of scratch
+        # inside the timed call cost a sporadic 0.1 - 0.9 s of cudaFree / cudaMalloc)
+        I.multistart_two_opt(first, count, stride, time_limit=0.05)
         barrier()
         I.reset_stats()
         t0 = time.perf_counter()
@@ -400,7 +404,8 @@ def main():
                       "moves": int(agg[1]), "scans": int(agg[2]), "best_cost": int(bc), "best_start": int(bs),
                       "note": "starts 0..S-1, rank r takes r, r+W, ... (heuristics.c:82 order, block-cyclic); NN on the device, "
                               "descents by the CTA-per-descent pruned kernel (bit-identical tours to the full scan); wall clock "
-                              "incl. the NCCL best-tour reduction, max over ranks"}
+                              "incl. the NCCL best-tour reduction, max over ranks; the context's device scratch was sized beforehand by a "
+                              "deadline-cut call of the same batch"}
         I.set_scan_mode(T.SCAN_FULL)
 
     out = {

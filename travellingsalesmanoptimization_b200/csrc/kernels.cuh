@@ -224,7 +224,10 @@ __device__ __forceinline__ unsigned long long warp_min_key(unsigned long long k)
 // pos[tid[e_out]] = e_out (tid[e_out] is succ_a after the reversal).
 // ep (delta cache only, V.o8 != NULL): the epoch of this move; the o8 bytes of the four nodes whose tour edges change
 // (a, succ a, b, succ b) are stamped with it in bits 1..7 (pruned.cuh).
-template <class M, bool CACHE = false, int AM_B = CACHE ? 4 : 1>
+#ifndef TSP_AM_B
+#define TSP_AM_B 4
+#endif
+template <class M, bool CACHE = false, int AM_B = 1>
 __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int t, int nthreads, bool has_dns,
                                            int &s_out, int &e_out, int ep = 0) {
     const int n = V.n;
@@ -245,11 +248,12 @@ __device__ __forceinline__ void apply_move(const TourView &V, int a, int b, int 
         if (i == 0) { V.dn[n] = k_ab; if (has_dns) V.dns[n] = k_ab; }
         if (e == 0) { V.dn[n] = k_ss; if (has_dns) V.dns[n] = k_ss; }
     }
-    // AM_B pairs per thread and trip, all loads of a trip before its stores: when few threads share a long segment (one CTA
-    // per descent: pla85900 reverses 48 000 nodes per move on average, 24 pairs per thread) a pair at a time is a chain of
-    // dependent memory round trips per pair -- 76 us of a 300 us scan + move (profiles/r02_pruned.md).  No pair is touched by
-    // two threads or twice by one, so the order of loads and stores within a trip is free.  (AM_B = 1 for the full-scan
-    // kernels, whose moves are spread over the whole grid or live in shared memory.)
+    // AM_B pairs per thread and trip, all loads of a trip -- the o8 bytes included -- before its stores: when few threads share
+    // a long segment (one CTA per descent: pla85900 reverses 48 000 nodes per move on average, 24 pairs per thread) a pair at
+    // a time is a chain of dependent memory round trips per pair.  No pair is touched by two threads or twice by one, so the
+    // order of loads and stores within a trip is free.  K8 passes AM_B = 4 (pla85900 318 -> 300, d15112 139 -> 106 us per scan);
+    // where the move is spread over the whole grid (at most one pair per thread) 1 is best, and batches cost registers
+    // (K7 pla85900 0.109 s with 1, 0.117 with 2, 0.126 with 4: profiles/r02_pruned.md).
     for (int k0 = t; k0 < half; k0 += AM_B * nthreads) {
         double2 xp[AM_B], xq[AM_B];
         int tp[AM_B], tq[AM_B], pp[AM_B], qq[AM_B], op[AM_B], oq[AM_B];

@@ -1869,7 +1869,7 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             const int a = key_a(kbest), b = key_b(kbest);
             int seg_s, seg_e;
             K8_MARK(2)
-            apply_move<M, true>(V, a, b, t, TEAM, false, seg_s, seg_e, ep);
+            apply_move<M, true, (CL >= 8 ? 1 : TSP_AM_B)>(V, a, b, t, TEAM, false, seg_s, seg_e, ep);
             K8_MARK(3)
             if (t == 0) {
                 *s_cost += key_delta(kbest);
