@@ -291,3 +291,30 @@ def test_delta_cache_under_heap_pressure(tsp, monkeypatch, per_node):
         assert (mk1, ck1) == (mk0, ck0) and logk1 == logk0 and np.array_equal(pk1, pk0)
         bs1, bp1, bc1, nn1, fin1, mv1 = I.multistart_two_opt(0, 40)
         assert (bs1, bc1) == (bs0, bc0) and np.array_equal(fin1, fin0) and np.array_equal(mv1, mv0) and np.array_equal(bp1, bp0)
+
+
+@pytest.mark.parametrize("knob,value", [("TSPCUDA_NB_GIANT_AGE", "0"), ("TSPCUDA_NB_GIANT_AGE", "2"), ("TSPCUDA_NB_GIANT_AGE", "1000"),
+                                         ("TSPCUDA_NB_RESTART_PCT", "25"), ("TSPCUDA_NB_RESTART_PCT", "400")])
+def test_delta_cache_policies_do_not_change_results(tsp, monkeypatch, knob, value):
+    """Two policies of the delta cache (csrc/pruned.cuh) decide only WHEN work is done, never what the scan returns:
+    giant_age (a search box of more than 512 nodes is evaluated k times before it is cached: the VNS loop, whose kicks make
+    instance-spanning edges) and the heap restart rule (how many abandoned records are streamed before the heap starts
+    over; 25 % restarts every few moves, 400 % almost never -- with giant runs kept in place across searches).  d15112: the
+    mh_VNS loop (metaheuristic.c:277-321) with a fixed rand() stream, the NN(0) descent and a multi-start batch, against the
+    library defaults: same traces, tours, move logs and incumbents."""
+    libc = ctypes.CDLL(None)
+    xy, _ = load_instance("d15112")
+
+    def run():
+        with tsp.Instance(xy) as I:
+            I.set_scan_mode(tsp.SCAN_PRUNED)
+            code, p, c = I.nn(0)
+            code, m, p1, c1, log = I.two_opt(p, log_cap=4096)
+            libc.srand(11)
+            code, pv, cv, tr, bi, bp, bc, done = I.vns_search(p1, 12, c1)
+            ms = I.multistart_two_opt(0, 12)
+        return (m, c1, log, fnv1a(p1), cv, tr.tolist(), bi, bc, fnv1a(pv), ms[0], ms[2], ms[4].tolist(), ms[5].tolist(), fnv1a(ms[1]))
+
+    ref = run()
+    monkeypatch.setenv(knob, value)
+    assert run() == ref

@@ -66,6 +66,24 @@ def test_cost_matrix_random(tsp, oracle, n, integer):
     assert np.array_equal(M, E) and np.all(np.diag(M) == -1.0)
 
 
+@pytest.mark.parametrize("n,integer", [(1030, True), (2049, False), (2055, True), (4104, False)])
+def test_cost_matrix_unit_shapes(tsp, oracle, monkeypatch, n, integer):
+    """K1's work units (8 rows x 1024 columns, one per CTA, kernels.cuh): several column chunks per row, a last row group
+    with fewer than 8 rows, odd n (row groups of every other row, unpaired first / last cells), the diagonal in a partial
+    trip -- against the oracle cell by cell, and the same matrix from the round-1 launch shape (units dealt out grid-stride,
+    TSPCUDA_K1_CTAS) and from whole-row units (TSPCUDA_K1_CHUNK=0)."""
+    xy = _rand_xy(300 + n, n, integer)
+    E = oracle.cost_matrix(xy)
+    with tsp.Instance(xy) as I:
+        M = I.cost_matrix()
+    assert np.array_equal(M, E) and np.all(np.diag(M) == -1.0)
+    for key, val in (("TSPCUDA_K1_CTAS", "3"), ("TSPCUDA_K1_CHUNK", "0"), ("TSPCUDA_K1_CHUNK", "1")):
+        monkeypatch.setenv(key, val)
+        with tsp.Instance(xy) as I:
+            assert np.array_equal(I.cost_matrix(), E)
+        monkeypatch.delenv(key)
+
+
 def test_cost_matrix_large_coordinates(tsp, oracle):
     """Magnitudes of usa13509 / pla85900 (where float-sqrt rounding differs most from TSPLIB)."""
     xy = _rand_xy(5, 600, False, 245552.778, 1244961.111)

@@ -684,6 +684,15 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 // every writer fences across the proxies before the barrier that ends its phase
 __device__ __forceinline__ void heap_writes_to_async_proxy() { asm volatile("fence.proxy.async.global;" ::: "memory"); }
 
+#ifdef TSP_PHASE_TIMING
+// sections of cached_scan as warp 1 of CTA 0 sees them (a warp that does not search): ns in the heap stream, the lines, the
+// attention / evaluation tail; [3] = scans
+__device__ unsigned long long g_scan_ns[4];
+#define SCAN_MARK(slot) if (blockIdx.x == 0 && threadIdx.x == 32) { unsigned long long tn_; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tn_)); atomicAdd(&g_scan_ns[slot], tn_ - scan_t_); scan_t_ = tn_; }
+#else
+#define SCAN_MARK(slot)
+#endif
+
 struct ScanAcc {
     unsigned long long bestkey;
     long long ncand;
@@ -1049,6 +1058,10 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
     // With many cooperating warps (the whole GPU on one descent) a warp's share of the stream is one or two records -- a few
     // dependent loads -- and the search is the longer chain: the four warps then ONLY search, at once, and the stream is
     // dealt out over the others (sgw of snw); with few warps (one CTA per descent) the stream dominates and all warps take part.
+#ifdef TSP_PHASE_TIMING
+    unsigned long long scan_t_ = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 32) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(scan_t_));
+#endif
     const bool split = nwarps >= NB_SPLIT_WARPS && F.node0 >= 0;                             // the same for every cooperating warp
     const int sgw = split ? gw - 4 : gw, snw = split ? nwarps - 4 : nwarps;
     if (gw < 4) {
@@ -1166,6 +1179,7 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
             heap_step(std::integral_constant<int, NB_HU>{}, r, kidx);
         }
     }
+    SCAN_MARK(0)
     // ---- the lines: count bytes first, non-empty lines 32 per step
     // many warps, few nodes each (the whole GPU on one descent): one 32-node range per warp, so that every warp gets some;
     // otherwise blocks of 128 nodes, whose count bytes are read four per lane, dealt out round-robin (TSP_NB_LINE_RANGES: one
@@ -1273,9 +1287,14 @@ __device__ __forceinline__ void cached_scan(const TourView &V, const SpatialGrid
             }
         }
     }
+    SCAN_MARK(1)
     }   // !(split && gw < 4)
     if (acount > 0) a = attend<M, NE, SETTLE>(V, &G, F, C, hp, qctr, boxes, wbuf, acount, a);
     if (!SETTLE && a.ecount > 0) a = flush_records<M, NE>(V, F, ebuf, a);
+    SCAN_MARK(2)
+#ifdef TSP_PHASE_TIMING
+    if (blockIdx.x == 0 && threadIdx.x == 32) atomicAdd(&g_scan_ns[3], 1ull);
+#endif
     if (STAGED) heap_writes_to_async_proxy();
     best = a.best; bestkey = a.bestkey; ncand = a.ncand;
 }
@@ -1886,6 +1905,9 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
             if (stop != nullptr && *s_stop != 0) { cut = true; break; }      // time limit: checked before the next scan
         }
 #ifdef TSP_PHASE_TIMING
+        if (t == 0 && blockIdx.x == 0)
+            printf("[tspcuda] K8 CTA 0 warp 1, all its scans so far: heap stream %llu ns, lines %llu ns, attention + evaluation tail %llu ns per scan (%llu scans)\n",
+                   g_scan_ns[0] / (g_scan_ns[3] + 1), g_scan_ns[1] / (g_scan_ns[3] + 1), g_scan_ns[2] / (g_scan_ns[3] + 1), g_scan_ns[3]);
         if (t == 0 && blockIdx.x == 0)
             printf("[tspcuda] K8 team 0, start %d: %lld moves; per scan+move ns: scan own %llu, wait at its barrier %llu, giant phase + checkpoint %llu, move own %llu, bookkeeping + barrier %llu\n",
                    first_start + cur * stride, moves, k8t[0] / (moves + 1), k8t[1] / (moves + 1), k8t[2] / (moves + 1), k8t[3] / (moves + 1), k8t[4] / (moves + 1));
