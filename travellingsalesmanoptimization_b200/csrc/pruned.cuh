@@ -635,7 +635,10 @@ constexpr int EB_CAP = PR_WBUF - AB_CAP;       // evaluation records per warp
 constexpr unsigned AT_DIRTY = 1, AT_NODE = 2;
 constexpr unsigned EV_NODEIDS = 4;             // evaluation record {u, w, -, 3 | EV_NODEIDS}: node ids instead of {p, w, K, type}
 constexpr int NB_RING = 256;                   // per-warp ring of pending node ids (shared memory): 31 left over + 128 new at most
-constexpr int NB_HU = 4;                       // heap records in flight per lane
+#ifndef TSP_NB_HU
+#define TSP_NB_HU 4
+#endif
+constexpr int NB_HU = TSP_NB_HU;               // heap records in flight per lane
 #ifndef TSP_NB_SPLIT_WARPS
 #define TSP_NB_SPLIT_WARPS 256
 #endif
