@@ -25,6 +25,8 @@ struct EmState {
     int *list;               // [n] nodes whose best edge was replaced (rescan queue)
     unsigned long long *key; // [2] argmin slots (double-buffered)
     int *list_count;         // [2]
+    unsigned long long *rk;  // [n] rescan keys (mileage, edge index) of the queued nodes, ~0 when idle
+    int *done;               // [1] CTAs that have finished their share of the rescans of this insertion
     long long *cost;         // [1] tour cost: 2 c(A,B) + the mileage of every insertion
     int *init_pair;          // [2] nodeA, nodeB
 };
@@ -60,7 +62,8 @@ template <class M, int BLK>
 __global__ void __launch_bounds__(BLK)
 extra_mileage_kernel(const double2 *__restrict__ xy, int n, EmState S) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ unsigned long long s_bk;
+    __shared__ unsigned long long s_bk, s_kb;
+    __shared__ int s_nlist, s_last;
     const int gtid = blockIdx.x * BLK + threadIdx.x, gsize = gridDim.x * BLK;
     const int lane = threadIdx.x & 31;
     const int gw = gtid >> 5, nw = gsize >> 5;
@@ -94,7 +97,10 @@ extra_mileage_kernel(const double2 *__restrict__ xy, int n, EmState S) {
 
     for (int m = 2; m < n; ++m) {                   // m = edges so far = nodes in the tour
         const int par = m & 1;                      // key[par] holds the argmin of this insertion
-        const unsigned long long kb = *(volatile unsigned long long *)&S.key[par];
+        // (one reader per CTA of the words the whole grid needs, handed on through shared memory: see K7, pruned.cuh)
+        if (threadIdx.x == 0) s_kb = *(volatile unsigned long long *)&S.key[par];
+        __syncthreads();
+        const unsigned long long kb = s_kb;
         if (kb == ~0ull) break;                     // no unvisited node left (cannot happen before m == n)
         const int istar = (int)(kb & 0xFFFFFFFFu);
         const int mileage = (int)(kb >> 32) - EM_BIAS;
@@ -132,17 +138,26 @@ extra_mileage_kernel(const double2 *__restrict__ xy, int n, EmState S) {
             *S.cost += mileage;                                     // :360
             S.key[par] = ~0ull;                                     // slot of the insertion after next
         }
-        // One CTA per queued node once the edge array is long (its threads stride over the edges; a single warp walking
-        // 40 000 edges with two gathers each was the whole cost of an insertion on pla85900: 475 us), one warp below that.
-        const int nlist = *(volatile int *)&S.list_count[par];
+        // Once the edge array is long, the rescans are cut into (queued node, chunk of the edge array) items that just cover
+        // the grid (round 2 first gave each queued node ONE CTA: up to 335 trips of two dependent gathers per thread while
+        // the CTAs without a node idled, 80 us per insertion on pla85900): warp and CTA minima in shared memory, one global
+        // atomicMin per item into rk[], and the CTA that finishes LAST (a counter behind a fence) writes the nodes' new
+        // (best, edge) and their keys -- no third grid barrier.
+        if (threadIdx.x == 0) s_nlist = *(volatile int *)&S.list_count[par];
+        __syncthreads();
+        const int nlist = s_nlist;
         if (m >= 4 * BLK) {
-            for (int q = blockIdx.x; q < nlist; q += gridDim.x) {   // CTA-uniform trip count
+            // work items (queued node q, chunk of the edge array): nch chunks per node so that the items just cover the grid
+            const int nch = max(1, min((int)gridDim.x / max(1, nlist), (m + BLK) / BLK));
+            const int len = (m + nch) / nch;                        // ceil((m + 1) / nch) edges per chunk
+            for (int item = blockIdx.x; item < nlist * nch; item += gridDim.x) {     // CTA-uniform trip count
                 if (threadIdx.x == 0) s_bk = ~0ull;
                 __syncthreads();
+                const int q = item / nch, j0 = (item - q * nch) * len, j1 = min(m + 1, j0 + len);
                 const int i = S.list[q];
                 const double2 pi = xy[i];
                 unsigned long long bk = ~0ull;                      // (mileage, edge index): first minimum in edge order
-                for (int j = threadIdx.x; j <= m; j += BLK) {
+                for (int j = j0 + threadIdx.x; j < j1; j += BLK) {
                     int eu = S.eu[j], ev = S.ev[j];
                     if (j == jstar) { eu = u; ev = istar; }
                     if (j == m) { eu = istar; ev = v; }
@@ -152,12 +167,28 @@ extra_mileage_kernel(const double2 *__restrict__ xy, int n, EmState S) {
                     bk = min(bk, ((unsigned long long)(unsigned)(d + EM_BIAS) << 32) | (unsigned)j);
                 }
                 for (int off = 16; off > 0; off >>= 1) bk = min(bk, __shfl_down_sync(FULL, bk, off));
-                if (lane == 0) atomicMin(&s_bk, bk);
+                if (lane == 0 && bk != ~0ull) atomicMin(&s_bk, bk);
+                __syncthreads();
+                if (threadIdx.x == 0 && s_bk != ~0ull) atomicMin(&S.rk[q], s_bk);
+            }
+            if (nlist > 0) {
                 __syncthreads();
                 if (threadIdx.x == 0) {
-                    const int bd = (int)(s_bk >> 32) - EM_BIAS;
-                    S.best[i] = bd; S.bedge[i] = (int)(s_bk & 0xFFFFFFFFu);
-                    atomicMin(&S.key[par ^ 1], ((unsigned long long)(unsigned)(bd + EM_BIAS) << 32) | (unsigned)i);
+                    __threadfence();                                // this CTA's rk[] minima before its tick
+                    s_last = atomicAdd(S.done, 1) == (int)gridDim.x - 1;
+                }
+                __syncthreads();
+                if (s_last) {                                       // every CTA's minima are in rk[]
+                    __threadfence();
+                    for (int q = threadIdx.x; q < nlist; q += BLK) {
+                        const unsigned long long rk = *(volatile unsigned long long *)&S.rk[q];
+                        const int i = S.list[q];
+                        const int bd = (int)(rk >> 32) - EM_BIAS;
+                        S.best[i] = bd; S.bedge[i] = (int)(rk & 0xFFFFFFFFu);
+                        atomicMin(&S.key[par ^ 1], ((unsigned long long)(unsigned)(bd + EM_BIAS) << 32) | (unsigned)i);
+                        S.rk[q] = ~0ull;
+                    }
+                    if (threadIdx.x == 0) *S.done = 0;
                 }
             }
         } else {

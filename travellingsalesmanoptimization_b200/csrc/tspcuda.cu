@@ -1464,11 +1464,14 @@ extern "C" int tspcuda_extra_mileage(tspcuda_ctx *c, int node_a, int node_b, int
     if (n < 2) return fail(TSPCUDA_INVALID_ARGUMENT, "extra mileage needs at least two nodes");
     if (node_a >= 0 && (node_a >= n || node_b < 0 || node_b >= n || node_a == node_b))
         return fail(TSPCUDA_INVALID_ARGUMENT, "initial edge (%d,%d)", node_a, node_b);
-    DevBuf vis, eu, ev, best, bedge, list, key, lc, cost, pair;
+    DevBuf vis, eu, ev, best, bedge, list, key, lc, cost, pair, rk, done;
     CK(cudaMalloc(&vis.p, sizeof(int) * n)); CK(cudaMalloc(&eu.p, sizeof(int) * n)); CK(cudaMalloc(&ev.p, sizeof(int) * n));
     CK(cudaMalloc(&best.p, sizeof(int) * n)); CK(cudaMalloc(&bedge.p, sizeof(int) * n)); CK(cudaMalloc(&list.p, sizeof(int) * n));
     CK(cudaMalloc(&key.p, sizeof(unsigned long long) * 2)); CK(cudaMalloc(&lc.p, sizeof(int) * 2));
     CK(cudaMalloc(&cost.p, sizeof(long long))); CK(cudaMalloc(&pair.p, sizeof(int) * 2));
+    CK(cudaMalloc(&rk.p, sizeof(unsigned long long) * n)); CK(cudaMalloc(&done.p, sizeof(int)));
+    CK(cudaMemsetAsync(rk.p, 0xFF, sizeof(unsigned long long) * n, c->stream));
+    CK(cudaMemsetAsync(done.p, 0, sizeof(int), c->stream));
     int h_pair[2] = {node_a, node_b};
     CK(cudaEventRecord(c->ev0, c->stream));
     if (node_a < 0) {                                   // EM_MAX, heuristics.c:169-178
@@ -1489,6 +1492,7 @@ extern "C" int tspcuda_extra_mileage(tspcuda_ctx *c, int node_a, int node_b, int
     S.visited = vis.as<int>(); S.eu = eu.as<int>(); S.ev = ev.as<int>(); S.best = best.as<int>(); S.bedge = bedge.as<int>();
     S.path = c->d_path; S.list = list.as<int>(); S.key = key.as<unsigned long long>(); S.list_count = lc.as<int>();
     S.cost = cost.as<long long>(); S.init_pair = pair.as<int>();
+    S.rk = rk.as<unsigned long long>(); S.done = done.as<int>();
     int bps = 0;
     DISPATCH_METRIC(c->metric, (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, extra_mileage_kernel<M, EM_BLOCK>, EM_BLOCK, 0)));
     if (bps <= 0) return fail(TSPCUDA_INTERNAL, "extra mileage kernel cannot be resident");
