@@ -173,6 +173,7 @@ descend_matrix_kernel(const double *__restrict__ C, MxTour T, unsigned long long
     constexpr int WARPS = MX_BLOCK / 32;
     __shared__ MxBest s_best[WARPS];
     __shared__ MxBest s_cta;
+    __shared__ unsigned long long s_word;               // one reader per CTA of the words the whole grid needs (see K7, pruned.cuh)
     const int n = T.n;
     const size_t N = (size_t)n;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -224,7 +225,9 @@ descend_matrix_kernel(const double *__restrict__ C, MxTour T, unsigned long long
             if (cb.a >= 0) atomicMin(slot_d, ordered_bits(cb.delta));
         }
         grid.sync();
-        const unsigned long long dmin = *(volatile unsigned long long *)slot_d;
+        if (threadIdx.x == 0) s_word = *(volatile unsigned long long *)slot_d;
+        __syncthreads();
+        const unsigned long long dmin = s_word;
         if (threadIdx.x == 0 && s_cta.a >= 0 && ordered_bits(s_cta.delta) == dmin)
             atomicMin(slot_ab, ((unsigned long long)(unsigned)s_cta.a << 32) | (unsigned)s_cta.b);
         grid.sync();
@@ -232,7 +235,9 @@ descend_matrix_kernel(const double *__restrict__ C, MxTour T, unsigned long long
             if (gtid == 0) st->status = 1;
             break;
         }
-        const unsigned long long ab = *(volatile unsigned long long *)slot_ab;
+        if (threadIdx.x == 0) s_word = *(volatile unsigned long long *)slot_ab;      // (everybody has read dmin: a grid barrier lies between)
+        __syncthreads();
+        const unsigned long long ab = s_word;
         const int a = (int)(ab >> 32), b = (int)(ab & 0xFFFFFFFFu);
         // delta of the winner: recompute from its key bits (exact inverse of ordered_bits)
         const unsigned long long db = (dmin >> 63) ? (dmin & 0x7FFFFFFFFFFFFFFFull) : ~dmin;
