@@ -1,6 +1,6 @@
-"""A small pass through the changed kernels for compute-sanitizer (memcheck / racecheck): K1 (odd and even n, tail rows), NN, the
+"""A small pass through the changed kernels as a quick end-to-end pass (compute-sanitizer is not available on this pool): K1 (odd and even n, tail rows), NN, the
 pruned descent K7 (flat and row-by-row searches, settle pass), the tabu loop K5c, the VNS loop (giant boxes evaluated, then cached),
-K8 multi-start.  Instances are small: the sanitizer slows the kernels down 10 - 100 times."""
+K8 multi-start.  Instances are small."""
 import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
