@@ -175,8 +175,8 @@ nn_grid_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, int first_s
                     const int lo = G.cell_start[cy * G.W + x0], hi = G.cell_start[cy * G.W + x1 + 1];
                     for (int k = lo + lane; k < hi; k += 32) {
                         const int w = G.cnode[k];
+                        const double2 p = G.cxy[k];          // requested with the id, not behind the visited test: one round trip
                         if ((s_vis[w >> 5] >> (w & 31)) & 1u) continue;
-                        const double2 p = G.cxy[k];
                         const int d = M::K(cur.x, cur.y, p.x, p.y) - KOFF;
                         bk = min(bk, ((unsigned long long)(unsigned)d << 32) | (unsigned)w);
                     }
