@@ -1704,6 +1704,10 @@ tabu_pruned_kernel(TourView V, SpatialGrid G, unsigned long long *key, TabuCtl T
     }
 }
 
+#ifndef TSP_K8_O8_SMEM
+#define TSP_K8_O8_SMEM 1
+#endif
+constexpr bool K8_O8_SMEM = TSP_K8_O8_SMEM != 0;
 // ---- K8: one CTA per descent, pruned scan, tours in CTA-private global-memory slots -------------------
 // Multi-start work (h_greedy_2opt, heuristics.c:74-116): a pruned scan is a few thousand record
 // evaluations, far too little to fill 148 SMs, so the SMs run independent descents instead.  CTAs pull
@@ -1806,6 +1810,14 @@ multi_pruned_kernel(const double2 *__restrict__ xy, int n, SpatialGrid G, const 
     C.heap_next = S.nb_next + slot * 8;
     C.cnt8 = S.cnt8 + slot * (size_t)nb_cnt8_stride(n);
     V.o8 = S.o8 + slot * (size_t)n;
+    // One CTA per descent: the orientation / epoch bytes live in SHARED memory for the whole descent (n bytes of dynamic
+    // shared memory; nothing outside this kernel reads them).  The scan looks up two of them per live record and the move
+    // flips one per reversed node -- as global bytes these were L1 gathers and scattered one-byte stores to HBM (K8_O8_SMEM:
+    // pla85900 300 -> 271, usa13509 96 -> 88, d15112 106 -> 92 us per scan + move, profiles/r02_pruned.md; on pr2392, whose
+    // bytes fit L1 anyway, the smaller L1 costs 4 %).  Unconditional for this instantiation, so that the compiler KNOWS the
+    // address space (LDS / STS, not generic loads: a run-time switch on n lost the whole gain).  A cluster keeps the bytes
+    // in global memory: its CTAs would each need a copy and every flip in all of them.
+    if (K8_O8_SMEM && CL == 1 && !STG) V.o8 = k8_dyn_smem;
     int *best_path = S.best_path + slot * (size_t)n;
     uint4 *wbuf = wbuf_all + ((size_t)blockIdx.x * WARPS + (threadIdx.x >> 5)) * PR_WBUF;
     if (t == 0) { *s_bestcost = -1; *s_stop = 0; S.best_cost[slot] = -1; S.best_start[slot] = -1; }

@@ -56,9 +56,10 @@ enum MetricId { M_EUC_GENERAL = 0, M_EUC_INTEGER = 1, M_CEIL = 2, M_ATT = 3, M_G
 
 // dynamic shared memory of multi_pruned_kernel<M, blk, cl>: the stages of its heap stream (pruned.cuh, STG)
 #if TSP_NB_STAGE
-static size_t k8_dyn_smem(int blk, int cl) { return (blk / 32) * cl < NB_SPLIT_WARPS ? stage_smem_bytes(blk / 32) : 0; }
+static size_t k8_dyn_smem(int blk, int cl, int) { return (blk / 32) * cl < NB_SPLIT_WARPS ? stage_smem_bytes(blk / 32) : 0; }
 #else
-static size_t k8_dyn_smem(int, int) { return 0; }
+// one CTA per descent: the n orientation / epoch bytes of the descent (pruned.cuh, K8_O8_SMEM); n <= 131 072
+static size_t k8_dyn_smem(int, int cl, int n) { return (K8_O8_SMEM && cl == 1) ? (((size_t)n + 127) & ~(size_t)127) : 0; }
 #endif
 
 // Grow-only device scratch of the multi-start entry points, kept in the context between calls: cudaFree of the per-call
@@ -1106,7 +1107,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
                 for (int k = 0, v = 1; k < 4; ++k, v *= 2) {
                     cudaLaunchConfig_t q = {};
                     q.gridDim = dim3(c->num_sms / v * v); q.blockDim = dim3(1024);
-                    q.dynamicSmemBytes = k8_dyn_smem(1024, v);
+                    q.dynamicSmemBytes = k8_dyn_smem(1024, v, n);
                     cudaLaunchAttribute qa[1];
                     qa[0].id = cudaLaunchAttributeClusterDimension;
                     qa[0].val.clusterDim.x = v; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
@@ -1140,7 +1141,7 @@ extern "C" int tspcuda_multistart_two_opt(tspcuda_ctx *c, int first_start, int n
             cfg.attrs = attr; cfg.numAttrs = 1;
             cudaError_t le = cudaSuccess;
 #define K8_LAUNCH(BLKV, CLV)                                                                                                  \
-    cfg.dynamicSmemBytes = k8_dyn_smem(BLKV, CLV);                                                                            \
+    cfg.dynamicSmemBytes = k8_dyn_smem(BLKV, CLV, n);                                                                            \
     DISPATCH_METRIC(c->metric, (le = cudaFuncSetAttribute(multi_pruned_kernel<M, BLKV, CLV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes))); \
     if (le == cudaSuccess) DISPATCH_METRIC(c->metric, (le = cudaLaunchKernelEx(&cfg, multi_pruned_kernel<M, BLKV, CLV>, (const double2 *)c->d_xy, n, c->grid, \
         (const int *)S.order, fs, stride, cnt, next.as<int>(), MS, dcost.as<long long>(), dmoves.as<long long>(),                     \
